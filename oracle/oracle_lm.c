@@ -1,0 +1,600 @@
+/*
+ * oracle_lm.c -- CPU ORACLE (test infrastructure, NOT product code).  See oracle_lm.h.
+ */
+#include "oracle_lm.h"
+#include "visgeom_oracle.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#define MAX_K 16
+#define MAX_CHAIN 5
+
+typedef struct {
+    int model, K, constant, shared_off;
+    double params[MAX_K], lo[MAX_K], hi[MAX_K];
+} cam_t;
+
+typedef struct {
+    int is_global, constant, n;
+    int shared_off;   /* global & free */
+    int pose_off;     /* sequence & free */
+    double *values;
+} tr_t;
+
+typedef struct {
+    int cam, P, n_img, L, D, ne;
+    int tr[MAX_CHAIN], status[MAX_CHAIN];
+    double *board, *obs;
+    int *seq_index;
+    double *H;        /* n_img x ne */
+} ds_t;
+
+struct vgo_problem {
+    int n_cam, n_tr, n_ds;
+    cam_t *cams;
+    tr_t *trs;
+    ds_t *dss;
+};
+
+static double now_s(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+void vgo_solve_options_default(vgo_solve_options *o)
+{
+    o->max_num_iterations = 1000;
+    o->function_tolerance = 1e-15;
+    o->gradient_tolerance = 1e-15;
+    o->parameter_tolerance = 1e-15;
+    o->initial_radius = 1e4;
+    o->max_radius = 1e16;
+    o->min_radius = 1e-32;
+    o->min_relative_decrease = 1e-3;
+    o->min_lm_diagonal = 1e-6;
+    o->max_lm_diagonal = 1e32;
+    o->jacobi_scaling = 1;
+    o->max_consecutive_invalid = 5;
+    o->verbose = 0;
+    o->threads = 1;
+}
+
+vgo_problem *vgo_problem_create(void)
+{
+    return (vgo_problem *)calloc(1, sizeof(vgo_problem));
+}
+
+void vgo_problem_destroy(vgo_problem *p)
+{
+    if (!p) return;
+    for (int i = 0; i < p->n_tr; i++) free(p->trs[i].values);
+    for (int i = 0; i < p->n_ds; i++) {
+        free(p->dss[i].board); free(p->dss[i].obs); free(p->dss[i].seq_index); free(p->dss[i].H);
+    }
+    free(p->cams); free(p->trs); free(p->dss); free(p);
+}
+
+int vgo_problem_add_camera(vgo_problem *p, int model, const double *value, int constant)
+{
+    int K = vgo_num_params(model);
+    if (K < 0) return -1;
+    p->cams = (cam_t *)realloc(p->cams, sizeof(cam_t) * (size_t)(p->n_cam + 1));
+    cam_t *c = &p->cams[p->n_cam];
+    memset(c, 0, sizeof *c);
+    c->model = model; c->K = K; c->constant = constant; c->shared_off = -1;
+    for (int i = 0; i < K; i++) {
+        c->params[i] = value[i];
+        c->lo[i] = vgo_lower_bound(model, i);   /* unified_calibration.cpp:621-626 */
+        c->hi[i] = vgo_upper_bound(model, i);
+    }
+    return p->n_cam++;
+}
+
+int vgo_problem_set_bounds(vgo_problem *p, int cam, int idx, double lo, double hi)
+{
+    if (cam < 0 || cam >= p->n_cam || idx < 0 || idx >= p->cams[cam].K) return -1;
+    p->cams[cam].lo[idx] = lo; p->cams[cam].hi[idx] = hi;
+    return 0;
+}
+
+int vgo_problem_add_transform(vgo_problem *p, int is_global, int constant, int n, const double *values)
+{
+    if (n < 1 || (is_global && n != 1)) return -1;
+    p->trs = (tr_t *)realloc(p->trs, sizeof(tr_t) * (size_t)(p->n_tr + 1));
+    tr_t *t = &p->trs[p->n_tr];
+    t->is_global = is_global; t->constant = constant; t->n = n;
+    t->shared_off = t->pose_off = -1;
+    t->values = (double *)malloc(sizeof(double) * 6 * (size_t)n);
+    memcpy(t->values, values, sizeof(double) * 6 * (size_t)n);
+    return p->n_tr++;
+}
+
+int vgo_problem_add_dataset(vgo_problem *p, int cam, int P, const double *board,
+                            int n_img, const double *obs, const int *seq_index,
+                            int chain_len, const int *transform_ids, const int *status)
+{
+    if (cam < 0 || cam >= p->n_cam || chain_len < 1 || chain_len > MAX_CHAIN || P < 1 || n_img < 0)
+        return -1;
+    int nseq = 0, seq_tr = -1;
+    for (int e = 0; e < chain_len; e++) {
+        if (transform_ids[e] < 0 || transform_ids[e] >= p->n_tr) return -1;
+        if (!p->trs[transform_ids[e]].is_global) { nseq++; seq_tr = transform_ids[e]; }
+    }
+    if (nseq != 1) return -2;          /* unified_calibration.cpp:223-228 */
+    for (int i = 0; i < n_img; i++) {
+        int s = seq_index ? seq_index[i] : i;
+        if (s < 0 || s >= p->trs[seq_tr].n) return -3;
+    }
+    p->dss = (ds_t *)realloc(p->dss, sizeof(ds_t) * (size_t)(p->n_ds + 1));
+    ds_t *d = &p->dss[p->n_ds];
+    memset(d, 0, sizeof *d);
+    d->cam = cam; d->P = P; d->n_img = n_img; d->L = chain_len;
+    d->D = p->cams[cam].K + 6 * chain_len;
+    d->ne = (d->D + 1) * (d->D + 2) / 2;
+    for (int e = 0; e < chain_len; e++) { d->tr[e] = transform_ids[e]; d->status[e] = status[e]; }
+    d->board = (double *)malloc(sizeof(double) * 3 * (size_t)P);
+    memcpy(d->board, board, sizeof(double) * 3 * (size_t)P);
+    d->obs = (double *)malloc(sizeof(double) * 2 * (size_t)P * (size_t)(n_img ? n_img : 1));
+    memcpy(d->obs, obs, sizeof(double) * 2 * (size_t)P * (size_t)n_img);
+    d->seq_index = (int *)malloc(sizeof(int) * (size_t)(n_img ? n_img : 1));
+    for (int i = 0; i < n_img; i++) d->seq_index[i] = seq_index ? seq_index[i] : i;
+    d->H = (double *)malloc(sizeof(double) * (size_t)d->ne * (size_t)(n_img ? n_img : 1));
+    return p->n_ds++;
+}
+
+int vgo_problem_get_camera(const vgo_problem *p, int cam, double *out)
+{
+    if (cam < 0 || cam >= p->n_cam) return -1;
+    memcpy(out, p->cams[cam].params, sizeof(double) * (size_t)p->cams[cam].K);
+    return 0;
+}
+
+int vgo_problem_set_camera(vgo_problem *p, int cam, const double *value)
+{
+    if (cam < 0 || cam >= p->n_cam) return -1;
+    memcpy(p->cams[cam].params, value, sizeof(double) * (size_t)p->cams[cam].K);
+    return 0;
+}
+
+int vgo_problem_get_transform(const vgo_problem *p, int tr, double *out)
+{
+    if (tr < 0 || tr >= p->n_tr) return -1;
+    memcpy(out, p->trs[tr].values, sizeof(double) * 6 * (size_t)p->trs[tr].n);
+    return 0;
+}
+
+int vgo_problem_set_transform(vgo_problem *p, int tr, const double *values)
+{
+    if (tr < 0 || tr >= p->n_tr) return -1;
+    memcpy(p->trs[tr].values, values, sizeof(double) * 6 * (size_t)p->trs[tr].n);
+    return 0;
+}
+
+/* --- evaluation of one dataset at the problem's current parameters --- */
+static void ds_gather_xi(const vgo_problem *p, const ds_t *d, double **seq_tmp,
+                         const double *xi[MAX_CHAIN], int is_global[MAX_CHAIN])
+{
+    *seq_tmp = NULL;
+    for (int e = 0; e < d->L; e++) {
+        const tr_t *t = &p->trs[d->tr[e]];
+        is_global[e] = t->is_global;
+        if (t->is_global) xi[e] = t->values;
+        else {
+            /* gather the per-image poses through seq_index */
+            double *g = (double *)malloc(sizeof(double) * 6 * (size_t)(d->n_img ? d->n_img : 1));
+            for (int i = 0; i < d->n_img; i++)
+                memcpy(g + 6 * (size_t)i, t->values + 6 * (size_t)d->seq_index[i], 6 * sizeof(double));
+            xi[e] = g;
+            *seq_tmp = g;
+        }
+    }
+}
+
+static void ds_eval(const vgo_problem *p, ds_t *d, double *r, int with_H, int threads)
+{
+    const double *xi[MAX_CHAIN];
+    int is_global[MAX_CHAIN];
+    double *tmp;
+    ds_gather_xi(p, d, &tmp, xi, is_global);
+    vgo_evaluate_batch(p->cams[d->cam].model, p->cams[d->cam].params, d->n_img, d->P,
+                       d->board, d->obs, d->L, d->status, is_global, xi,
+                       r, NULL, NULL, with_H ? d->H : NULL, threads);
+    free(tmp);
+}
+
+int vgo_problem_residuals(vgo_problem *p, int dataset, double *r)
+{
+    if (dataset < 0 || dataset >= p->n_ds) return -1;
+    ds_eval(p, &p->dss[dataset], r, 0, 1);
+    return 0;
+}
+
+/* --- LM working set --- */
+typedef struct {
+    int Ks, n_pose;
+    double *A, *ga;            /* Ks x Ks, Ks */
+    double *C, *E, *b;         /* n_pose x 36, n_pose x Ks x 6, n_pose x 6 */
+    double cost;
+} normal_eq;
+
+static void layout(vgo_problem *p, int *Ks, int *n_pose)
+{
+    int off = 0, po = 0;
+    for (int i = 0; i < p->n_cam; i++) {
+        cam_t *c = &p->cams[i];
+        if (c->constant) c->shared_off = -1; else { c->shared_off = off; off += c->K; }
+    }
+    for (int i = 0; i < p->n_tr; i++) {
+        tr_t *t = &p->trs[i];
+        t->shared_off = t->pose_off = -1;
+        if (t->constant) continue;
+        if (t->is_global) { t->shared_off = off; off += 6; }
+        else { t->pose_off = po; po += t->n; }
+    }
+    *Ks = off; *n_pose = po;
+}
+
+static double evaluate_all(vgo_problem *p, int threads)
+{
+    double cost = 0;
+    for (int k = 0; k < p->n_ds; k++) {
+        ds_t *d = &p->dss[k];
+        ds_eval(p, d, NULL, 1, threads);
+        for (int i = 0; i < d->n_img; i++) cost += 0.5 * d->H[(size_t)i * d->ne + d->ne - 1];
+    }
+    return cost;
+}
+
+int vgo_problem_evaluate(vgo_problem *p, int threads, double *cost)
+{
+    *cost = evaluate_all(p, threads);
+    return 0;
+}
+
+static void assemble(const vgo_problem *p, normal_eq *n)
+{
+    const int Ks = n->Ks;
+    memset(n->A, 0, sizeof(double) * (size_t)Ks * Ks);
+    memset(n->ga, 0, sizeof(double) * (size_t)Ks);
+    memset(n->C, 0, sizeof(double) * 36 * (size_t)n->n_pose);
+    memset(n->E, 0, sizeof(double) * 6 * (size_t)Ks * (size_t)n->n_pose);
+    memset(n->b, 0, sizeof(double) * 6 * (size_t)n->n_pose);
+    n->cost = 0;
+    for (int k = 0; k < p->n_ds; k++) {
+        const ds_t *d = &p->dss[k];
+        const cam_t *c = &p->cams[d->cam];
+        const int W = d->D + 1;
+        /* kind: 0 const, 1 shared(idx), 2 pose(dim), 3 residual */
+        int kind[64], idx[64], pose_base = -1;
+        for (int a = 0; a < c->K; a++) {
+            kind[a] = c->shared_off >= 0 ? 1 : 0; idx[a] = c->shared_off + a;
+        }
+        for (int e = 0; e < d->L; e++) {
+            const tr_t *t = &p->trs[d->tr[e]];
+            for (int q = 0; q < 6; q++) {
+                int a = c->K + 6 * e + q;
+                if (t->is_global) { kind[a] = t->shared_off >= 0 ? 1 : 0; idx[a] = t->shared_off + q; }
+                else { kind[a] = t->pose_off >= 0 ? 2 : 0; idx[a] = q; pose_base = t->pose_off; }
+            }
+        }
+        kind[d->D] = 3; idx[d->D] = 0;
+        for (int i = 0; i < d->n_img; i++) {
+            const double *H = d->H + (size_t)i * d->ne;
+            const int pz = pose_base >= 0 ? pose_base + d->seq_index[i] : -1;
+            int e = 0;
+            for (int a = 0; a < W; a++) {
+                for (int bb = a; bb < W; bb++, e++) {
+                    const double h = H[e];
+                    const int ka = kind[a], kb = kind[bb];
+                    if (ka == 0 || kb == 0) continue;
+                    if (ka == 1 && kb == 1) {
+                        n->A[idx[a] * Ks + idx[bb]] += h;
+                        if (a != bb) n->A[idx[bb] * Ks + idx[a]] += h;
+                    } else if (ka == 1 && kb == 2) {
+                        n->E[((size_t)pz * Ks + idx[a]) * 6 + idx[bb]] += h;
+                    } else if (ka == 2 && kb == 1) {
+                        n->E[((size_t)pz * Ks + idx[bb]) * 6 + idx[a]] += h;
+                    } else if (ka == 2 && kb == 2) {
+                        n->C[(size_t)pz * 36 + idx[a] * 6 + idx[bb]] += h;
+                        if (a != bb) n->C[(size_t)pz * 36 + idx[bb] * 6 + idx[a]] += h;
+                    } else if (ka == 1 && kb == 3) {
+                        n->ga[idx[a]] += h;
+                    } else if (ka == 2 && kb == 3) {
+                        n->b[(size_t)pz * 6 + idx[a]] += h;
+                    } else if (ka == 3 && kb == 3) {
+                        n->cost += 0.5 * h;
+                    }
+                }
+            }
+        }
+    }
+}
+
+/* in-place Cholesky of an n x n SPD matrix (row-major, lower); returns 0 on success */
+static int chol(double *M, int n)
+{
+    for (int j = 0; j < n; j++) {
+        double s = M[j * n + j];
+        for (int k = 0; k < j; k++) s -= M[j * n + k] * M[j * n + k];
+        if (!(s > 0.0)) return -1;
+        s = sqrt(s);
+        M[j * n + j] = s;
+        for (int i = j + 1; i < n; i++) {
+            double t = M[i * n + j];
+            for (int k = 0; k < j; k++) t -= M[i * n + k] * M[j * n + k];
+            M[i * n + j] = t / s;
+        }
+    }
+    return 0;
+}
+
+static void chol_solve(const double *Lm, int n, double *x)
+{
+    for (int i = 0; i < n; i++) {
+        double s = x[i];
+        for (int k = 0; k < i; k++) s -= Lm[i * n + k] * x[k];
+        x[i] = s / Lm[i * n + i];
+    }
+    for (int i = n - 1; i >= 0; i--) {
+        double s = x[i];
+        for (int k = i + 1; k < n; k++) s -= Lm[k * n + i] * x[k];
+        x[i] = s / Lm[i * n + i];
+    }
+}
+
+static double clampd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+typedef struct { double *cam; double **tr; } snapshot;
+
+static void save_params(const vgo_problem *p, snapshot *s)
+{
+    s->cam = (double *)malloc(sizeof(double) * MAX_K * (size_t)(p->n_cam ? p->n_cam : 1));
+    s->tr = (double **)malloc(sizeof(double *) * (size_t)(p->n_tr ? p->n_tr : 1));
+    for (int i = 0; i < p->n_cam; i++) memcpy(s->cam + MAX_K * i, p->cams[i].params, sizeof(double) * MAX_K);
+    for (int i = 0; i < p->n_tr; i++) {
+        s->tr[i] = (double *)malloc(sizeof(double) * 6 * (size_t)p->trs[i].n);
+        memcpy(s->tr[i], p->trs[i].values, sizeof(double) * 6 * (size_t)p->trs[i].n);
+    }
+}
+
+static void restore_params(vgo_problem *p, const snapshot *s)
+{
+    for (int i = 0; i < p->n_cam; i++) memcpy(p->cams[i].params, s->cam + MAX_K * i, sizeof(double) * MAX_K);
+    for (int i = 0; i < p->n_tr; i++)
+        memcpy(p->trs[i].values, s->tr[i], sizeof(double) * 6 * (size_t)p->trs[i].n);
+}
+
+static void free_snapshot(vgo_problem *p, snapshot *s)
+{
+    for (int i = 0; i < p->n_tr; i++) free(s->tr[i]);
+    free(s->tr); free(s->cam);
+}
+
+int vgo_problem_solve(vgo_problem *p, const vgo_solve_options *o, vgo_solve_summary *sum)
+{
+    const double t_start = now_s();
+    double t_eval = 0;
+    int n_eval = 0;
+    normal_eq n;
+    layout(p, &n.Ks, &n.n_pose);
+    const int Ks = n.Ks, NP = n.n_pose;
+    n.A = (double *)calloc((size_t)(Ks * Ks + 1), sizeof(double));
+    n.ga = (double *)calloc((size_t)(Ks + 1), sizeof(double));
+    n.C = (double *)calloc(36 * (size_t)(NP + 1), sizeof(double));
+    n.E = (double *)calloc(6 * (size_t)(Ks + 1) * (size_t)(NP + 1), sizeof(double));
+    n.b = (double *)calloc(6 * (size_t)(NP + 1), sizeof(double));
+    double *scale_a = (double *)malloc(sizeof(double) * (size_t)(Ks + 1));
+    double *scale_p = (double *)malloc(sizeof(double) * 6 * (size_t)(NP + 1));
+    double *Lp = (double *)malloc(sizeof(double) * 36 * (size_t)(NP + 1));   /* chol factors */
+    double *S = (double *)malloc(sizeof(double) * (size_t)(Ks * Ks + 1));
+    double *rhs = (double *)malloc(sizeof(double) * (size_t)(Ks + 1));
+    double *da = (double *)malloc(sizeof(double) * (size_t)(Ks + 1));
+    double *dp = (double *)malloc(sizeof(double) * 6 * (size_t)(NP + 1));
+    double *Y = (double *)malloc(sizeof(double) * 6 * (size_t)(Ks + 1));
+    memset(sum, 0, sizeof *sum);
+
+    double t0 = now_s();
+    double cost = evaluate_all(p, o->threads);
+    t_eval += now_s() - t0; n_eval++;
+    assemble(p, &n);
+    cost = n.cost;
+    sum->initial_cost = cost;
+
+    /* Jacobi scaling, fixed at iteration 0: s_j = 1/(1+sqrt(sum J_ij^2)) */
+    for (int j = 0; j < Ks; j++)
+        scale_a[j] = o->jacobi_scaling ? 1.0 / (1.0 + sqrt(n.A[j * Ks + j])) : 1.0;
+    for (int q = 0; q < NP; q++)
+        for (int k = 0; k < 6; k++)
+            scale_p[6 * q + k] = o->jacobi_scaling ? 1.0 / (1.0 + sqrt(n.C[(size_t)q * 36 + 7 * k])) : 1.0;
+
+    double radius = o->initial_radius, decrease_factor = 2.0;
+    int invalid_run = 0;
+    sum->termination = 3;
+    int iter = 0;
+
+    /* gradient check at the start (Ceres IterationZero) */
+    for (;;) {
+        /* max-norm of the projected gradient */
+        double gmax = 0;
+        for (int i = 0; i < p->n_cam; i++) {
+            const cam_t *c = &p->cams[i];
+            if (c->shared_off < 0) continue;
+            for (int k = 0; k < c->K; k++) {
+                double x = c->params[k], g = n.ga[c->shared_off + k];
+                double pg = x - clampd(x - g, c->lo[k], c->hi[k]);
+                if (fabs(pg) > gmax) gmax = fabs(pg);
+            }
+        }
+        for (int i = 0; i < p->n_tr; i++) {
+            const tr_t *t = &p->trs[i];
+            if (t->shared_off >= 0)
+                for (int k = 0; k < 6; k++) if (fabs(n.ga[t->shared_off + k]) > gmax) gmax = fabs(n.ga[t->shared_off + k]);
+        }
+        for (size_t q = 0; q < (size_t)NP * 6; q++) if (fabs(n.b[q]) > gmax) gmax = fabs(n.b[q]);
+        if (gmax <= o->gradient_tolerance) { sum->termination = 1; break; }
+        if (iter >= o->max_num_iterations) { sum->termination = 3; break; }
+        if (radius < o->min_radius) { sum->termination = 4; break; }
+        iter++;
+
+        /* ---- LM step at the current radius ---- */
+        int ok = 1;
+        memcpy(S, n.A, sizeof(double) * (size_t)Ks * Ks);
+        for (int j = 0; j < Ks; j++) {
+            double s2 = scale_a[j] * scale_a[j];
+            S[j * Ks + j] += clampd(s2 * n.A[j * Ks + j], o->min_lm_diagonal, o->max_lm_diagonal) / (radius * s2);
+            rhs[j] = -n.ga[j];
+        }
+        for (int q = 0; q < NP && ok; q++) {
+            double *Lq = Lp + (size_t)q * 36;
+            const double *Cq = n.C + (size_t)q * 36;
+            const double *Eq = n.E + (size_t)q * Ks * 6;
+            const double *bq = n.b + (size_t)q * 6;
+            int empty = 1;
+            for (int k = 0; k < 6; k++) if (Cq[7 * k] != 0.0) empty = 0;
+            if (empty) { memset(Lq, 0, 36 * sizeof(double)); continue; }
+            memcpy(Lq, Cq, 36 * sizeof(double));
+            for (int k = 0; k < 6; k++) {
+                double s2 = scale_p[6 * q + k] * scale_p[6 * q + k];
+                Lq[7 * k] += clampd(s2 * Cq[7 * k], o->min_lm_diagonal, o->max_lm_diagonal) / (radius * s2);
+            }
+            if (chol(Lq, 6)) { ok = 0; break; }
+            /* Y = E C~^-1 (row s of E solved against C~), S -= Y E^T, rhs += Y b */
+            for (int s = 0; s < Ks; s++) {
+                double *y = Y + 6 * s;
+                memcpy(y, Eq + 6 * s, 6 * sizeof(double));
+                chol_solve(Lq, 6, y);
+            }
+            for (int s = 0; s < Ks; s++) {
+                const double *y = Y + 6 * s;
+                for (int s2 = 0; s2 < Ks; s2++) {
+                    const double *e2 = Eq + 6 * s2;
+                    S[s * Ks + s2] -= y[0] * e2[0] + y[1] * e2[1] + y[2] * e2[2] + y[3] * e2[3] + y[4] * e2[4] + y[5] * e2[5];
+                }
+                rhs[s] += y[0] * bq[0] + y[1] * bq[1] + y[2] * bq[2] + y[3] * bq[3] + y[4] * bq[4] + y[5] * bq[5];
+            }
+        }
+        if (ok && Ks > 0) {
+            if (chol(S, Ks)) ok = 0;
+            else { memcpy(da, rhs, sizeof(double) * (size_t)Ks); chol_solve(S, Ks, da); }
+        }
+        double model_change = 0, step2 = 0, x2 = 0;
+        if (ok) {
+            /* back substitution + model cost change = -g^T d - 1/2 d^T H d */
+            double gd = 0, dHd = 0;
+            for (int s = 0; s < Ks; s++) {
+                gd += n.ga[s] * da[s];
+                double t = 0;
+                for (int s2 = 0; s2 < Ks; s2++) t += n.A[s * Ks + s2] * da[s2];
+                dHd += da[s] * t;
+            }
+            for (int q = 0; q < NP; q++) {
+                const double *Lq = Lp + (size_t)q * 36;
+                const double *Cq = n.C + (size_t)q * 36;
+                const double *Eq = n.E + (size_t)q * Ks * 6;
+                const double *bq = n.b + (size_t)q * 6;
+                double *d = dp + 6 * (size_t)q;
+                if (Lq[0] == 0.0) { memset(d, 0, 6 * sizeof(double)); continue; }
+                double Etd[6];
+                for (int k = 0; k < 6; k++) {
+                    double t = 0;
+                    for (int s = 0; s < Ks; s++) t += Eq[6 * s + k] * da[s];
+                    Etd[k] = t;
+                    d[k] = -(bq[k] + t);
+                }
+                chol_solve(Lq, 6, d);
+                for (int k = 0; k < 6; k++) {
+                    gd += bq[k] * d[k];
+                    double t = 0;
+                    for (int k2 = 0; k2 < 6; k2++) t += Cq[6 * k + k2] * d[k2];
+                    dHd += d[k] * t + 2.0 * d[k] * Etd[k];
+                }
+            }
+            model_change = -gd - 0.5 * dHd;
+            if (!(model_change > 0.0)) ok = 0;
+        }
+        if (!ok) {
+            /* invalid step (Ceres: StepIsInvalid) */
+            invalid_run++;
+            sum->num_unsuccessful++;
+            if (invalid_run >= o->max_consecutive_invalid) { sum->termination = 5; break; }
+            radius /= decrease_factor; decrease_factor *= 2.0;
+            continue;
+        }
+        invalid_run = 0;
+
+        /* candidate = Pi(x + delta) */
+        snapshot snap;
+        save_params(p, &snap);
+        for (int i = 0; i < p->n_cam; i++) {
+            cam_t *c = &p->cams[i];
+            if (c->shared_off < 0) continue;
+            for (int k = 0; k < c->K; k++) {
+                double x = c->params[k];
+                double xn = clampd(x + da[c->shared_off + k], c->lo[k], c->hi[k]);
+                x2 += x * x; step2 += (xn - x) * (xn - x);
+                c->params[k] = xn;
+            }
+        }
+        for (int i = 0; i < p->n_tr; i++) {
+            tr_t *t = &p->trs[i];
+            if (t->shared_off >= 0) {
+                for (int k = 0; k < 6; k++) {
+                    double x = t->values[k], dd = da[t->shared_off + k];
+                    x2 += x * x; step2 += dd * dd;
+                    t->values[k] = x + dd;
+                }
+            } else if (t->pose_off >= 0) {
+                for (int q = 0; q < t->n; q++)
+                    for (int k = 0; k < 6; k++) {
+                        double x = t->values[6 * q + k], dd = dp[6 * (size_t)(t->pose_off + q) + k];
+                        x2 += x * x; step2 += dd * dd;
+                        t->values[6 * q + k] = x + dd;
+                    }
+            }
+        }
+        if (sqrt(step2) <= o->parameter_tolerance * (sqrt(x2) + o->parameter_tolerance)) {
+            restore_params(p, &snap);
+            free_snapshot(p, &snap);
+            sum->termination = 2;
+            break;
+        }
+        t0 = now_s();
+        double new_cost = evaluate_all(p, o->threads);
+        t_eval += now_s() - t0; n_eval++;
+        const double rho = (cost - new_cost) / model_change;
+        if (o->verbose)
+            printf("%4d  cost %.12e  new %.12e  rho %.3e  radius %.3e  |step| %.3e\n",
+                   iter, cost, new_cost, rho, radius, sqrt(step2));
+        if (rho > o->min_relative_decrease) {
+            const double cost_change = cost - new_cost;
+            const double old_cost = cost;
+            assemble(p, &n);
+            cost = n.cost;
+            sum->num_successful++;
+            radius = radius / fmax(1.0 / 3.0, 1.0 - pow(2.0 * rho - 1.0, 3.0));
+            if (radius > o->max_radius) radius = o->max_radius;
+            decrease_factor = 2.0;
+            free_snapshot(p, &snap);
+            if (fabs(cost_change) <= o->function_tolerance * old_cost) { sum->termination = 0; break; }
+        } else {
+            restore_params(p, &snap);
+            free_snapshot(p, &snap);
+            sum->num_unsuccessful++;
+            radius /= decrease_factor; decrease_factor *= 2.0;
+        }
+    }
+    sum->iterations = iter;
+    sum->final_cost = cost;
+    sum->seconds_total = now_s() - t_start;
+    sum->seconds_evaluate = t_eval;
+    sum->num_evaluations = n_eval;
+    free(n.A); free(n.ga); free(n.C); free(n.E); free(n.b);
+    free(scale_a); free(scale_p); free(Lp); free(S); free(rhs); free(da); free(dp); free(Y);
+    return 0;
+}

@@ -1,0 +1,257 @@
+"""ctypes view of the CPU oracle (TEST INFRASTRUCTURE ONLY).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module.  Nothing under visgeom_b200/ does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "libvisgeom_oracle.so")
+_REF = os.path.join(_HERE, "_ref", "libvisgeom_ref.so")
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int)
+
+
+def build(force: bool = False) -> str:
+    srcs = [os.path.join(_HERE, f) for f in ("visgeom_oracle.c", "oracle_lm.c", "visgeom_oracle.h", "oracle_lm.h")]
+    if force or not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "libvisgeom_oracle.so"])
+    return _LIB
+
+
+def build_ref(force: bool = False):
+    """Compile the reference's own sources against oracle/shim (only where /root/reference exists)."""
+    if os.path.isdir("/root/reference/include") and (force or not os.path.exists(_REF)):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "ref"])
+    return _REF if os.path.exists(_REF) else None
+
+
+class SolveOptions(C.Structure):
+    _fields_ = [("max_num_iterations", C.c_int), ("function_tolerance", C.c_double),
+                ("gradient_tolerance", C.c_double), ("parameter_tolerance", C.c_double),
+                ("initial_radius", C.c_double), ("max_radius", C.c_double), ("min_radius", C.c_double),
+                ("min_relative_decrease", C.c_double), ("min_lm_diagonal", C.c_double),
+                ("max_lm_diagonal", C.c_double), ("jacobi_scaling", C.c_int),
+                ("max_consecutive_invalid", C.c_int), ("verbose", C.c_int), ("threads", C.c_int)]
+
+
+class SolveSummary(C.Structure):
+    _fields_ = [("iterations", C.c_int), ("num_successful", C.c_int), ("num_unsuccessful", C.c_int),
+                ("termination", C.c_int), ("initial_cost", C.c_double), ("final_cost", C.c_double),
+                ("seconds_total", C.c_double), ("seconds_evaluate", C.c_double), ("num_evaluations", C.c_int)]
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_dp)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class _Evaluator:
+    """Shared driver for the two libraries exporting the *_evaluate_batch entry point."""
+
+    def __init__(self, lib, prefix):
+        self.lib = lib
+        self.prefix = prefix
+        fn = getattr(lib, prefix + "_evaluate_batch")
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_int, c_dp, C.c_int, C.c_int, c_dp, c_dp, C.c_int, c_ip, c_ip,
+                       C.POINTER(c_dp), c_dp, c_dp, C.POINTER(c_dp), c_dp, C.c_int]
+        self._batch = fn
+
+    def evaluate_batch(self, model, intr, board, obs, xi_list, status, is_global,
+                       want_r=True, want_J=True, want_H=False, threads=1):
+        """obs (n_img, 2P); xi_list[e] (n_img,6) or (6,).  Returns dict(r, J_intr, J_xi[], H)."""
+        K = {0: 6, 1: 5, 2: 10}[model]
+        intr = _f64(intr); board = _f64(board); obs = _f64(obs)
+        n_img = obs.shape[0]
+        P = board.shape[0]
+        L = len(xi_list)
+        xis = [_f64(x) for x in xi_list]
+        st = np.ascontiguousarray(status, dtype=np.int32)
+        ig = np.ascontiguousarray(is_global, dtype=np.int32)
+        xi_ptrs = (c_dp * L)(*[_dp(x) for x in xis])
+        r = np.zeros((n_img, 2 * P)) if want_r else None
+        Ja = np.zeros((n_img, 2 * P, K)) if want_J else None
+        Je = [np.zeros((n_img, 2 * P, 6)) for _ in range(L)] if want_J else None
+        ne = (K + 6 * L + 1) * (K + 6 * L + 2) // 2
+        H = np.zeros((n_img, ne)) if want_H else None
+        je_ptrs = (c_dp * L)(*[_dp(j) for j in Je]) if want_J else None
+        rc = self._batch(model, _dp(intr), n_img, P, _dp(board), _dp(obs), L,
+                         st.ctypes.data_as(c_ip), ig.ctypes.data_as(c_ip), xi_ptrs,
+                         _dp(r) if want_r else None, _dp(Ja) if want_J else None,
+                         je_ptrs, _dp(H) if want_H else None, threads)
+        if rc != 0:
+            raise RuntimeError(f"{self.prefix}_evaluate_batch failed: {rc}")
+        return dict(r=r, J_intr=Ja, J_xi=Je, H=H)
+
+
+class Oracle(_Evaluator):
+    def __init__(self):
+        lib = C.CDLL(build())
+        super().__init__(lib, "vgo")
+        lib.vgo_max_threads.restype = C.c_int
+        lib.vgo_lower_bound.restype = C.c_double
+        lib.vgo_upper_bound.restype = C.c_double
+        lib.vgo_lower_bound.argtypes = [C.c_int, C.c_int]
+        lib.vgo_upper_bound.argtypes = [C.c_int, C.c_int]
+        for name, n_in in (("vgo_rotation_matrix", 3), ("vgo_inter_omega_rot", 3)):
+            getattr(lib, name).argtypes = [c_dp, c_dp]
+        for name in ("vgo_compose", "vgo_compose_inverse", "vgo_inverse_compose"):
+            getattr(lib, name).argtypes = [c_dp, c_dp, c_dp]
+        lib.vgo_project.argtypes = [C.c_int, c_dp, c_dp, c_dp]
+        lib.vgo_projection_jacobian.argtypes = [C.c_int, c_dp, c_dp, c_dp, c_dp]
+        lib.vgo_intrinsic_jacobian.argtypes = [C.c_int, c_dp, c_dp, c_dp, c_dp]
+        lib.vgo_reconstruct.argtypes = [C.c_int, c_dp, c_dp, c_dp]
+        lib.vgo_problem_create.restype = C.c_void_p
+        lib.vgo_problem_destroy.argtypes = [C.c_void_p]
+        lib.vgo_problem_add_camera.argtypes = [C.c_void_p, C.c_int, c_dp, C.c_int]
+        lib.vgo_problem_set_bounds.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double]
+        lib.vgo_problem_add_transform.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, c_dp]
+        lib.vgo_problem_add_dataset.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp, C.c_int, c_dp, c_ip,
+                                                C.c_int, c_ip, c_ip]
+        lib.vgo_problem_solve.argtypes = [C.c_void_p, C.POINTER(SolveOptions), C.POINTER(SolveSummary)]
+        lib.vgo_problem_get_camera.argtypes = [C.c_void_p, C.c_int, c_dp]
+        lib.vgo_problem_get_transform.argtypes = [C.c_void_p, C.c_int, c_dp]
+        lib.vgo_problem_set_camera.argtypes = [C.c_void_p, C.c_int, c_dp]
+        lib.vgo_problem_set_transform.argtypes = [C.c_void_p, C.c_int, c_dp]
+        lib.vgo_problem_residuals.argtypes = [C.c_void_p, C.c_int, c_dp]
+        lib.vgo_problem_evaluate.argtypes = [C.c_void_p, C.c_int, c_dp]
+        lib.vgo_solve_options_default.argtypes = [C.POINTER(SolveOptions)]
+
+    def max_threads(self):
+        return self.lib.vgo_max_threads()
+
+    def default_options(self) -> SolveOptions:
+        o = SolveOptions()
+        self.lib.vgo_solve_options_default(C.byref(o))
+        return o
+
+    # ---- small geometry helpers (for the unit tests of the restatement) ----
+    def rotation_matrix(self, v):
+        v = _f64(v); R = np.zeros(9)
+        self.lib.vgo_rotation_matrix(_dp(v), _dp(R))
+        return R.reshape(3, 3)
+
+    def inter_omega_rot(self, v):
+        v = _f64(v); R = np.zeros(9)
+        self.lib.vgo_inter_omega_rot(_dp(v), _dp(R))
+        return R.reshape(3, 3)
+
+    def compose(self, a, b, kind="compose"):
+        a = _f64(a); b = _f64(b); o = np.zeros(6)
+        getattr(self.lib, "vgo_" + kind)(_dp(a), _dp(b), _dp(o))
+        return o
+
+    def project(self, model, params, X):
+        params = _f64(params); X = _f64(X); uv = np.zeros(2)
+        ok = self.lib.vgo_project(model, _dp(params), _dp(X), _dp(uv))
+        return uv, bool(ok)
+
+    def projection_jacobian(self, model, params, X):
+        params = _f64(params); X = _f64(X); du = np.zeros(3); dv = np.zeros(3)
+        ok = self.lib.vgo_projection_jacobian(model, _dp(params), _dp(X), _dp(du), _dp(dv))
+        return np.stack([du, dv]), bool(ok)
+
+    def intrinsic_jacobian(self, model, params, X):
+        K = {0: 6, 1: 5, 2: 10}[model]
+        params = _f64(params); X = _f64(X); du = np.zeros(K); dv = np.zeros(K)
+        ok = self.lib.vgo_intrinsic_jacobian(model, _dp(params), _dp(X), _dp(du), _dp(dv))
+        return np.stack([du, dv]), bool(ok)
+
+    def reconstruct(self, model, params, uv):
+        params = _f64(params); uv = _f64(uv); X = np.zeros(3)
+        ok = self.lib.vgo_reconstruct(model, _dp(params), _dp(uv), _dp(X))
+        return X, bool(ok)
+
+
+class OracleProblem:
+    """Thin OO wrapper over vgo_problem_* mirroring visgeom_b200.Problem."""
+
+    def __init__(self, oracle: Oracle):
+        self.o = oracle
+        self.lib = oracle.lib
+        self.h = C.c_void_p(self.lib.vgo_problem_create())
+        self._K = {}
+        self._n = {}
+
+    def close(self):
+        if self.h:
+            self.lib.vgo_problem_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def add_camera(self, model, value, constant=False):
+        v = _f64(value)
+        cid = self.lib.vgo_problem_add_camera(self.h, model, _dp(v), int(constant))
+        if cid < 0:
+            raise ValueError("add_camera failed")
+        self._K[cid] = len(v)
+        return cid
+
+    def set_bounds(self, cam, idx, lo, hi):
+        return self.lib.vgo_problem_set_bounds(self.h, cam, idx, lo, hi)
+
+    def add_transform(self, values, is_global, constant=False):
+        v = _f64(values).reshape(-1, 6)
+        tid = self.lib.vgo_problem_add_transform(self.h, int(is_global), int(constant), v.shape[0], _dp(v))
+        if tid < 0:
+            raise ValueError("add_transform failed")
+        self._n[tid] = v.shape[0]
+        return tid
+
+    def add_dataset(self, cam, board, obs, transform_ids, status, seq_index=None):
+        board = _f64(board); obs = _f64(obs)
+        ids = np.ascontiguousarray(transform_ids, dtype=np.int32)
+        st = np.ascontiguousarray(status, dtype=np.int32)
+        si = None if seq_index is None else np.ascontiguousarray(seq_index, dtype=np.int32)
+        did = self.lib.vgo_problem_add_dataset(self.h, cam, board.shape[0], _dp(board), obs.shape[0], _dp(obs),
+                                               None if si is None else si.ctypes.data_as(c_ip),
+                                               len(ids), ids.ctypes.data_as(c_ip), st.ctypes.data_as(c_ip))
+        if did < 0:
+            raise ValueError(f"add_dataset failed: {did}")
+        return did
+
+    def solve(self, options=None):
+        o = options or self.o.default_options()
+        s = SolveSummary()
+        rc = self.lib.vgo_problem_solve(self.h, C.byref(o), C.byref(s))
+        if rc != 0:
+            raise RuntimeError("solve failed")
+        return s
+
+    def camera(self, cid):
+        out = np.zeros(self._K[cid])
+        self.lib.vgo_problem_get_camera(self.h, cid, _dp(out))
+        return out
+
+    def transform(self, tid):
+        out = np.zeros((self._n[tid], 6))
+        self.lib.vgo_problem_get_transform(self.h, tid, _dp(out))
+        return out
+
+    def evaluate(self, threads=1):
+        c = C.c_double()
+        self.lib.vgo_problem_evaluate(self.h, threads, C.cast(C.byref(c), c_dp))
+        return c.value
+
+
+class Reference(_Evaluator):
+    """The reference's own hot-path sources compiled against oracle/shim (oracle/_ref)."""
+
+    def __init__(self):
+        path = build_ref()
+        if path is None:
+            raise FileNotFoundError("oracle/_ref/libvisgeom_ref.so not built (needs /root/reference)")
+        super().__init__(C.CDLL(path), "vgref")
