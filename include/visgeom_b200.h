@@ -1,0 +1,206 @@
+/*
+ * visgeom_b200.h -- C ABI of the B200-native reprojection-residual engine.
+ *
+ * This is the drop-in boundary for visgeom's calibration hot path.  Every entry
+ * point names the reference interface it replaces (paths relative to the visgeom
+ * tree).  Plain pointers and sizes only; no C++/torch types; nothing throws across
+ * the boundary.  All functions return VG_OK (0) or a negative VG_ERR_* code and
+ * leave a message retrievable with vg_last_error() (thread local).
+ *
+ * Two nested boundaries:
+ *   inner  -- the Ceres cost-function contract of GenericProjectionJac::Evaluate
+ *             (include/calibration/calib_cost_functions.h:53-54,
+ *              src/calibration/calib_cost_functions.cpp:28-117), batched over the
+ *             images of one dataset: vg_eval_chain / vg_eval_chain_dev.
+ *   outer  -- what GenericCameraCalibration asks of ceres::Problem / ceres::Solve
+ *             (src/calibration/unified_calibration.cpp:514-630, :39-53):
+ *             vg_problem_*.
+ *
+ * There is NO CPU fallback: every compute entry point needs a CUDA device and
+ * fails with VG_ERR_CUDA when none is usable.
+ */
+#ifndef VISGEOM_B200_H
+#define VISGEOM_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VG_OK               0
+#define VG_ERR_INVALID     -1   /* bad argument (the reference throws runtime_error for config errors) */
+#define VG_ERR_CUDA        -2   /* CUDA runtime failure / no device */
+#define VG_ERR_NOMEM       -3
+#define VG_ERR_UNSUPPORTED -4   /* e.g. board too large for one CTA's shared memory */
+#define VG_ERR_NUMERIC     -5   /* linear solve failed repeatedly */
+
+/* camera models: include/projection/eucm.h, ucm.h, mei.h; parameter order as there:
+ * EUCM [alpha,beta,fu,fv,u0,v0]  UCM [xi,fu,fv,u0,v0]  MEI [xi,k1..k5,fu,fv,u0,v0] */
+#define VG_MODEL_EUCM 0
+#define VG_MODEL_UCM  1
+#define VG_MODEL_MEI  2
+
+/* enum TransformationStatus, include/calibration/calib_cost_functions.h:25 */
+#define VG_TRANSFORM_DIRECT  0
+#define VG_TRANSFORM_INVERSE 1
+
+#define VG_MAX_CHAIN 5          /* unified_calibration.cpp:567 */
+#define VG_MAX_INTRINSICS 10
+
+/* residual written when a projection fails: DOUBLE_BIG, include/std.h:71,
+ * calib_cost_functions.cpp:66-70 */
+#define VG_DOUBLE_BIG 1e15
+
+const char *vg_last_error(void);
+int vg_version(void);
+/* number of usable CUDA devices (0 = none; compute calls will fail) */
+int vg_device_count(void);
+
+/* ICamera::numParams / lowerBound / upperBound -- generic_camera.h:116-119,
+ * eucm.h:228-246, ucm.h:199-215, mei.h:287-313 */
+int vg_model_num_params(int model);
+int vg_model_bounds(int model, int idx, double *lower, double *upper);
+
+/* number of doubles of one per-image normal-equation block: the packed upper
+ * triangle of [J r]^T [J r], W = K + 6*chain_len + 1, (W)(W+1)/2; column order
+ * [intrinsics(K), chain element 0 (6), .., chain element L-1 (6), residual]. */
+int vg_hessian_entries(int model, int chain_len);
+
+/* ------------------------------------------------------------------------- *
+ * Inner boundary: GenericProjectionJac::Evaluate batched over n_img images.
+ * Replaces, per image: calib_cost_functions.cpp:28-117 (+ InterJacobian
+ * jacobian.h:136-171, ICamera::{projectPoint,projectionJacobian,
+ * intrinsicJacobian}, Transformation::compose/composeInverse/transform).
+ *
+ *   intr      K doubles                      (params[0] of the functor)
+ *   board     P x 3 doubles                  (_grid)
+ *   obs       n_img x P x 2 doubles          (_proj of each image's functor)
+ *   status    chain_len x {DIRECT,INVERSE}   (_transformStatusVec)
+ *   is_global chain_len flags; xi[e] points at 6 doubles if global, else at
+ *             n_img x 6 doubles [tx,ty,tz,rx,ry,rz] (params[1+e] of image i)
+ *   r         n_img x 2P doubles, [u0,v0,u1,v1..] = projected - observed, or
+ *             (1e15,1e15) where the projection fails.           May be NULL.
+ *   J_intr    n_img x 2P x K, row-major rows u_i, v_i.          May be NULL.
+ *   J_xi      chain_len pointers (array may be NULL, entries may be NULL),
+ *             each n_img x 2P x 6, columns [d/dt(3), d/dr(3)].
+ *   H         n_img x vg_hessian_entries() per-image normal-equation blocks
+ *             (what Ceres accumulates from the block's Jacobians). May be NULL.
+ * Host variant: all pointers are host memory; the call copies in, launches,
+ * copies out and synchronises.  Device variant: all pointers are device memory
+ * on the current device (16-byte aligned), the launch is asynchronous on
+ * `stream` (a cudaStream_t passed as void*).
+ * ------------------------------------------------------------------------- */
+int vg_eval_chain(int model, const double *intr, int n_img, int P,
+                  const double *board, const double *obs,
+                  int chain_len, const int *status, const int *is_global,
+                  const double *const *xi,
+                  double *r, double *J_intr, double *const *J_xi, double *H);
+
+int vg_eval_chain_dev(int model, const double *intr, int n_img, int P,
+                      const double *board, const double *obs,
+                      int chain_len, const int *status, const int *is_global,
+                      const double *const *xi, const int *seq_index /* nullable, device */,
+                      double *r, double *J_intr, double *const *J_xi, double *H,
+                      void *stream);
+
+/* Number of kernel launches this library has issued in the calling process
+ * (monotonic counter; used by bench.py for its gpu_launches claim). */
+unsigned long long vg_launch_count(void);
+
+/* ------------------------------------------------------------------------- *
+ * Outer boundary: the problem GenericCameraCalibration builds and solves.
+ * ------------------------------------------------------------------------- */
+typedef struct vg_problem vg_problem;
+
+/* Solver::Options as the reference sets them (unified_calibration.cpp:42-53);
+ * remaining fields are Ceres' documented trust-region defaults. */
+typedef struct {
+    int max_num_iterations;        /* 1000 */
+    double function_tolerance;     /* 1e-15 */
+    double gradient_tolerance;     /* 1e-15 */
+    double parameter_tolerance;    /* 1e-15 */
+    double initial_radius;         /* 1e4 */
+    double max_radius;             /* 1e16 */
+    double min_radius;             /* 1e-32 */
+    double min_relative_decrease;  /* 1e-3 */
+    double min_lm_diagonal;        /* 1e-6 */
+    double max_lm_diagonal;        /* 1e32 */
+    int jacobi_scaling;            /* 1 */
+    int max_consecutive_invalid;   /* 5 */
+    int verbose;                   /* minimizer_progress_to_stdout */
+    int reserved;
+} vg_solve_options;
+
+/* Solver::Summary subset */
+typedef struct {
+    int iterations;
+    int num_successful;
+    int num_unsuccessful;
+    int termination;               /* 0 function tol, 1 gradient tol, 2 parameter tol, 3 max iterations, 4 radius, 5 failure */
+    double initial_cost;
+    double final_cost;
+    double seconds_total;
+    double seconds_evaluate;       /* device time in the fused residual+Jacobian+normal-equation kernels */
+    int num_evaluations;
+} vg_solve_summary;
+
+void vg_solve_options_default(vg_solve_options *o);
+
+/* device < 0 -> current device */
+vg_problem *vg_problem_create(int device);
+void vg_problem_destroy(vg_problem *p);
+
+/* parseCameras, unified_calibration.cpp:134-180: returns camera id >= 0.
+ * Bounds default to the model's (SetParameterLower/UpperBound, :621-626);
+ * constant -> SetParameterBlockConstant (:614-617). */
+int vg_problem_add_camera(vg_problem *p, int model, const double *value, int constant);
+int vg_problem_set_bounds(vg_problem *p, int camera, int idx, double lower, double upper);
+
+/* parseTransforms, :91-132: a global transform (n == 1) or a sequence of n
+ * transforms; values n x 6 [t,r]; constant -> SetParameterBlockConstant (:604-610).
+ * Returns transform id >= 0. */
+int vg_problem_add_transform(vg_problem *p, int is_global, int constant, int n, const double *values);
+
+/* addGridResidualBlocks, :514-568: one residual block per image of the dataset.
+ * obs n_img x P x 2 (host).  seq_index (nullable -> identity) maps image i to the
+ * element of the chain's sequence transform; images without an extracted board
+ * are simply not listed (:520).  Exactly one chain element must be a sequence
+ * (:223-228), chain_len <= 5 (:567).  Returns dataset id >= 0. */
+int vg_problem_add_dataset(vg_problem *p, int camera, int P, const double *board,
+                           int n_img, const double *obs, const int *seq_index,
+                           int chain_len, const int *transform_ids, const int *status);
+
+/* Route the cross-GPU sum of the reduced normal equations through the host
+ * application (one process per GPU): fn must sum `count` doubles at device
+ * pointer `buf` in place across all ranks, ordered after the work already queued
+ * on `stream`.  NULL -> single GPU.  Images are sharded by the caller: each rank
+ * adds only its own images/poses; shared parameters are replicated. */
+typedef int (*vg_allreduce_fn)(void *ctx, double *buf, int count, void *stream);
+int vg_problem_set_allreduce(vg_problem *p, vg_allreduce_fn fn, void *ctx);
+
+/* ceres::Solve, :53.  Parameters are updated in place inside the handle. */
+int vg_problem_solve(vg_problem *p, const vg_solve_options *o, vg_solve_summary *s);
+
+/* One residual + Jacobian + normal-equation pass at the current parameters
+ * (what one Ceres evaluation costs): cost = 1/2 sum r^2 over all datasets.
+ * reduced (nullable, host) receives Ks*Ks + Ks doubles: J^T J and J^T r of the
+ * shared (intrinsic + global transform) block. */
+int vg_problem_evaluate(vg_problem *p, double *cost, double *reduced);
+int vg_problem_num_shared(vg_problem *p);
+
+int vg_problem_get_camera(vg_problem *p, int camera, double *out);
+int vg_problem_set_camera(vg_problem *p, int camera, const double *value);
+int vg_problem_get_transform(vg_problem *p, int transform, double *out /* n x 6 */);
+int vg_problem_set_transform(vg_problem *p, int transform, const double *values);
+/* replace the observations / poses of a dataset from (pinned) host memory -- the
+ * per-step input upload of the end-to-end benchmark */
+int vg_problem_update_observations(vg_problem *p, int dataset, const double *obs);
+/* residuals of one dataset at the current parameters (writeImageResidual,
+ * :1186-1213 needs err = -r and proj = r + obs), n_img x 2P doubles to host */
+int vg_problem_residuals(vg_problem *p, int dataset, double *r);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

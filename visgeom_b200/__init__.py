@@ -1,0 +1,280 @@
+"""visgeom_b200 -- B200-native reprojection-residual engine (calibration hot path of visgeom).
+
+This package is a thin ctypes view of libvisgeom_b200.so (CUDA, sm_100a).  It has
+NO CPU implementation: importing works anywhere (so symbols can be inspected), but
+every compute call needs the CUDA library and a GPU and raises otherwise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvisgeom_b200.so")
+
+EUCM, UCM, MEI = 0, 1, 2
+TRANSFORM_DIRECT, TRANSFORM_INVERSE = 0, 1
+NUM_PARAMS = {EUCM: 6, UCM: 5, MEI: 10}
+MODEL_BY_NAME = {"eucm": EUCM, "ucm": UCM, "mei": MEI}   # unified_calibration.cpp:146-178
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int)
+
+
+class VisgeomError(RuntimeError):
+    pass
+
+
+class SolveOptions(C.Structure):
+    _fields_ = [("max_num_iterations", C.c_int), ("function_tolerance", C.c_double),
+                ("gradient_tolerance", C.c_double), ("parameter_tolerance", C.c_double),
+                ("initial_radius", C.c_double), ("max_radius", C.c_double), ("min_radius", C.c_double),
+                ("min_relative_decrease", C.c_double), ("min_lm_diagonal", C.c_double),
+                ("max_lm_diagonal", C.c_double), ("jacobi_scaling", C.c_int),
+                ("max_consecutive_invalid", C.c_int), ("verbose", C.c_int), ("reserved", C.c_int)]
+
+
+class SolveSummary(C.Structure):
+    _fields_ = [("iterations", C.c_int), ("num_successful", C.c_int), ("num_unsuccessful", C.c_int),
+                ("termination", C.c_int), ("initial_cost", C.c_double), ("final_cost", C.c_double),
+                ("seconds_total", C.c_double), ("seconds_evaluate", C.c_double), ("num_evaluations", C.c_int)]
+
+
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p)
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load the CUDA library; fail loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise VisgeomError(
+            f"{LIB_PATH} is missing: build it with `python -m visgeom_b200.build` "
+            "(there is no CPU fallback for this engine)")
+    L = C.CDLL(LIB_PATH)
+    L.vg_last_error.restype = C.c_char_p
+    L.vg_launch_count.restype = C.c_ulonglong
+    L.vg_model_bounds.argtypes = [C.c_int, C.c_int, c_dp, c_dp]
+    L.vg_eval_chain.argtypes = [C.c_int, c_dp, C.c_int, C.c_int, c_dp, c_dp, C.c_int, c_ip, c_ip,
+                                C.POINTER(c_dp), c_dp, c_dp, C.POINTER(c_dp), c_dp]
+    L.vg_eval_chain_dev.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                    c_ip, c_ip, C.POINTER(C.c_void_p), C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]
+    if hasattr(L, "vg_problem_create"):
+        L.vg_problem_create.restype = C.c_void_p
+        L.vg_problem_create.argtypes = [C.c_int]
+        L.vg_problem_destroy.argtypes = [C.c_void_p]
+        L.vg_problem_add_camera.argtypes = [C.c_void_p, C.c_int, c_dp, C.c_int]
+        L.vg_problem_set_bounds.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double]
+        L.vg_problem_add_transform.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, c_dp]
+        L.vg_problem_add_dataset.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp, C.c_int, c_dp, c_ip,
+                                             C.c_int, c_ip, c_ip]
+        L.vg_problem_set_allreduce.argtypes = [C.c_void_p, ALLREDUCE_FN, C.c_void_p]
+        L.vg_problem_solve.argtypes = [C.c_void_p, C.POINTER(SolveOptions), C.POINTER(SolveSummary)]
+        L.vg_problem_evaluate.argtypes = [C.c_void_p, c_dp, c_dp]
+        L.vg_problem_num_shared.argtypes = [C.c_void_p]
+        L.vg_problem_get_camera.argtypes = [C.c_void_p, C.c_int, c_dp]
+        L.vg_problem_set_camera.argtypes = [C.c_void_p, C.c_int, c_dp]
+        L.vg_problem_get_transform.argtypes = [C.c_void_p, C.c_int, c_dp]
+        L.vg_problem_set_transform.argtypes = [C.c_void_p, C.c_int, c_dp]
+        L.vg_problem_update_observations.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.vg_problem_residuals.argtypes = [C.c_void_p, C.c_int, c_dp]
+        L.vg_solve_options_default.argtypes = [C.POINTER(SolveOptions)]
+    _lib = L
+    return L
+
+
+def _check(rc: int):
+    if rc < 0:
+        raise VisgeomError(f"visgeom_b200 error {rc}: {lib().vg_last_error().decode()}")
+    return rc
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_dp)
+
+
+def device_count() -> int:
+    return lib().vg_device_count()
+
+
+def launch_count() -> int:
+    return int(lib().vg_launch_count())
+
+
+def hessian_entries(model: int, chain_len: int) -> int:
+    return _check(lib().vg_hessian_entries(model, chain_len))
+
+
+def model_bounds(model: int):
+    lo, hi = C.c_double(), C.c_double()
+    out = []
+    for i in range(NUM_PARAMS[model]):
+        _check(lib().vg_model_bounds(model, i, C.byref(lo), C.byref(hi)))
+        out.append((lo.value, hi.value))
+    return out
+
+
+def eval_chain(model, intr, board, obs, xi_list, status, is_global,
+               want_r=True, want_J=True, want_H=False):
+    """Batched GenericProjectionJac::Evaluate through the host-buffer C ABI.
+
+    obs (n_img, 2P); xi_list[e] is (n_img, 6) for a sequence or (6,) for a global
+    transform.  Returns dict(r, J_intr, J_xi[], H) of numpy arrays (Ceres layout).
+    """
+    K = _check(lib().vg_model_num_params(model))       # "invalid camera model name" comes from the library
+    intr = _f64(intr); board = _f64(board); obs = _f64(obs)
+    n_img, P, Lc = obs.shape[0], board.shape[0], len(xi_list)
+    if Lc > 5:
+        _check(lib().vg_eval_chain(model, _dp(intr), n_img, P, _dp(board), _dp(obs), Lc, None, None, None,
+                                   None, None, None, None))
+    xis = [_f64(x) for x in xi_list]
+    st = np.ascontiguousarray(status, dtype=np.int32)
+    ig = np.ascontiguousarray(is_global, dtype=np.int32)
+    xi_ptrs = (c_dp * Lc)(*[_dp(x) for x in xis])
+    r = np.empty((n_img, 2 * P)) if want_r else None
+    Ja = np.empty((n_img, 2 * P, K)) if want_J else None
+    Je = [np.empty((n_img, 2 * P, 6)) for _ in range(Lc)] if want_J else None
+    H = np.empty((n_img, hessian_entries(model, Lc))) if want_H else None
+    je_ptrs = (c_dp * Lc)(*[_dp(j) for j in Je]) if want_J else None
+    _check(lib().vg_eval_chain(model, _dp(intr), n_img, P, _dp(board), _dp(obs), Lc,
+                               st.ctypes.data_as(c_ip), ig.ctypes.data_as(c_ip), xi_ptrs,
+                               _dp(r) if want_r else None, _dp(Ja) if want_J else None, je_ptrs,
+                               _dp(H) if want_H else None))
+    return dict(r=r, J_intr=Ja, J_xi=Je, H=H)
+
+
+def eval_chain_dev(model, intr, board, obs, xi_list, status, is_global, n_img, P,
+                   r=None, J_intr=None, J_xi=None, H=None, seq_index=None, stream=0):
+    """Device-pointer variant: every array argument is an integer device address
+    (e.g. torch.Tensor.data_ptr()); asynchronous on `stream`."""
+    Lc = len(xi_list)
+    st = np.ascontiguousarray(status, dtype=np.int32)
+    ig = np.ascontiguousarray(is_global, dtype=np.int32)
+    xi_ptrs = (C.c_void_p * Lc)(*[C.c_void_p(x) for x in xi_list])
+    je_ptrs = (C.c_void_p * Lc)(*[C.c_void_p(x) if x else None for x in J_xi]) if J_xi else None
+    _check(lib().vg_eval_chain_dev(model, intr, n_img, P, board, obs, Lc,
+                                   st.ctypes.data_as(c_ip), ig.ctypes.data_as(c_ip), xi_ptrs,
+                                   seq_index, r, J_intr, je_ptrs, H, stream))
+
+
+class Problem:
+    """Mirror of what GenericCameraCalibration assembles (unified_calibration.cpp:514-630)
+    and hands to ceres::Solve (:39-53), executed on the GPU."""
+
+    def __init__(self, device: int = -1):
+        self.L = lib()
+        if not hasattr(self.L, "vg_problem_create"):
+            raise VisgeomError("library was built without the problem API")
+        h = self.L.vg_problem_create(device)
+        if not h:
+            raise VisgeomError(f"vg_problem_create failed: {self.L.vg_last_error().decode()}")
+        self.h = C.c_void_p(h)
+        self._K, self._n = {}, {}
+        self._cb = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.vg_problem_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def add_camera(self, model, value, constant=False):
+        v = _f64(value)
+        if len(v) != NUM_PARAMS[model]:
+            raise VisgeomError("invalid number of intrinsic parameters")   # unified_calibration.cpp:151,160,169
+        cid = _check(self.L.vg_problem_add_camera(self.h, model, _dp(v), int(constant)))
+        self._K[cid] = len(v)
+        return cid
+
+    def set_bounds(self, cam, idx, lo, hi):
+        _check(self.L.vg_problem_set_bounds(self.h, cam, idx, lo, hi))
+
+    def add_transform(self, values, is_global, constant=False):
+        v = _f64(values).reshape(-1, 6)
+        tid = _check(self.L.vg_problem_add_transform(self.h, int(is_global), int(constant), v.shape[0], _dp(v)))
+        self._n[tid] = v.shape[0]
+        return tid
+
+    def add_dataset(self, cam, board, obs, transform_ids, status, seq_index=None):
+        board = _f64(board); obs = _f64(obs)
+        ids = np.ascontiguousarray(transform_ids, dtype=np.int32)
+        st = np.ascontiguousarray(status, dtype=np.int32)
+        si = None if seq_index is None else np.ascontiguousarray(seq_index, dtype=np.int32)
+        return _check(self.L.vg_problem_add_dataset(
+            self.h, cam, board.shape[0], _dp(board), obs.shape[0], _dp(obs),
+            None if si is None else si.ctypes.data_as(c_ip), len(ids),
+            ids.ctypes.data_as(c_ip), st.ctypes.data_as(c_ip)))
+
+    def set_allreduce(self, fn):
+        """fn(buf_ptr:int, count:int, stream:int) -> None sums count doubles in place across ranks."""
+        def tramp(ctx, buf, count, stream):
+            try:
+                fn(buf or 0, count, stream or 0)
+                return 0
+            except Exception:   # never let an exception cross the C boundary
+                import traceback
+                traceback.print_exc()
+                return -1
+        self._cb = ALLREDUCE_FN(tramp)
+        _check(self.L.vg_problem_set_allreduce(self.h, self._cb, None))
+
+    def default_options(self) -> SolveOptions:
+        o = SolveOptions()
+        self.L.vg_solve_options_default(C.byref(o))
+        return o
+
+    def solve(self, options: SolveOptions | None = None) -> SolveSummary:
+        o = options or self.default_options()
+        s = SolveSummary()
+        _check(self.L.vg_problem_solve(self.h, C.byref(o), C.byref(s)))
+        return s
+
+    def evaluate(self, want_reduced=False):
+        c = C.c_double()
+        red = None
+        if want_reduced:
+            ks = _check(self.L.vg_problem_num_shared(self.h))
+            red = np.zeros(ks * ks + ks)
+        _check(self.L.vg_problem_evaluate(self.h, C.cast(C.byref(c), c_dp), _dp(red) if red is not None else None))
+        return (c.value, red) if want_reduced else c.value
+
+    def camera(self, cid):
+        out = np.zeros(self._K[cid])
+        _check(self.L.vg_problem_get_camera(self.h, cid, _dp(out)))
+        return out
+
+    def set_camera(self, cid, value):
+        v = _f64(value)
+        _check(self.L.vg_problem_set_camera(self.h, cid, _dp(v)))
+
+    def transform(self, tid):
+        out = np.zeros((self._n[tid], 6))
+        _check(self.L.vg_problem_get_transform(self.h, tid, _dp(out)))
+        return out
+
+    def set_transform(self, tid, values):
+        v = _f64(values).reshape(-1, 6)
+        _check(self.L.vg_problem_set_transform(self.h, tid, _dp(v)))
+
+    def update_observations(self, dataset, host_ptr: int):
+        _check(self.L.vg_problem_update_observations(self.h, dataset, host_ptr))
+
+    def residuals(self, dataset, n_img, P):
+        out = np.zeros((n_img, 2 * P))
+        _check(self.L.vg_problem_residuals(self.h, dataset, _dp(out)))
+        return out

@@ -1,0 +1,91 @@
+// vg_solver_kernels.cuh -- device side of the Levenberg-Marquardt step that replaces
+// the normal-equation build / elimination Ceres performs inside ceres::Solve
+// (unified_calibration.cpp:53; structure described in SURVEY.md 3.2).
+//
+// The Hessian of the calibration problem is an arrowhead: one shared block (all
+// free intrinsics + free global transforms, Ks columns) plus one independent 6x6
+// block per free sequence pose.  Per evaluation the fused kernel (vg_eval.cu) leaves
+// one packed [J r]^T [J r] block per image; the kernels here
+//   accumulate_shared : sum the shared x shared / shared x residual / residual^2
+//                       entries over images -> A (Ks x Ks), g_a, cost, deterministic
+//   pose_factor       : per pose gather C (6x6), E (Ks x 6), b; damp, Cholesky,
+//                       Z = L^-1 E^T, z = L^-1 b
+//   gram_reduce       : S_red = sum Z^T Z, v_red = sum Z^T z  (the Schur complement terms)
+//   pose_backsub      : delta_p = -L^-T (z + Z delta_a), candidate poses, model-decrease
+//                       and step-norm partial sums
+#pragma once
+
+#include <cuda_runtime.h>
+
+namespace vg {
+
+constexpr int MAX_W = 41;          // 10 intrinsics + 5*6 + residual column
+constexpr int MAX_SHARED_LOCAL = 34;
+
+// column kinds of a dataset's local layout
+constexpr int COL_CONST = 0, COL_SHARED = 1, COL_POSE = 2, COL_RESID = 3;
+
+struct DatasetDesc {
+    const double *H;               // n_img x ne (the set being reduced)
+    const int *seq_index;          // nullable
+    int n_img, ne, W;
+    int pose_col;                  // first local column of the sequence element, -1 if that element is constant
+    int pose_base;                 // index of pose 0 of its sequence in the global pose list
+    int n_sl;                      // number of local columns that map to shared parameters
+    int sl_col[MAX_SHARED_LOCAL];  // their local column
+    int sl_idx[MAX_SHARED_LOCAL];  // their global shared index
+    int kind[MAX_W];
+    int idx[MAX_W];
+};
+
+struct LmConsts {
+    double radius, min_diag, max_diag;
+    int init_scale;                // 1: (re)compute the Jacobi scaling from this evaluation
+    int jacobi_scaling;
+};
+
+// ws layout (doubles) per pose p, SoA over poses would not coalesce better for one thread
+// per pose, so the scratch is pose-major: [L (21) | lambda (6) | z (6) | Z (6 x Ks)]
+__host__ __device__ inline int pose_ws_stride(int Ks) { return 21 + 6 + 6 + 6 * Ks; }
+
+// Reduction buffer layout (doubles), all sums over the local images / poses:
+//   [0, Ks*Ks)            A        (row-major, symmetric)
+//   [Ks*Ks, +Ks)          g_a
+//   +0                    cost  (1/2 sum r^2)
+//   +1                    max |g_pose|  (max-reduced, not summed)
+//   then Ks*Ks + Ks       S_red, v_red
+//   then 3                model partial (sum m_p), step^2, x^2 over poses
+__host__ __device__ inline int red_off_A(int) { return 0; }
+__host__ __device__ inline int red_off_g(int Ks) { return Ks * Ks; }
+__host__ __device__ inline int red_off_cost(int Ks) { return Ks * Ks + Ks; }
+__host__ __device__ inline int red_off_gmax(int Ks) { return Ks * Ks + Ks + 1; }
+__host__ __device__ inline int red_off_S(int Ks) { return Ks * Ks + Ks + 2; }
+__host__ __device__ inline int red_off_v(int Ks) { return 2 * Ks * Ks + Ks + 2; }
+__host__ __device__ inline int red_off_model(int Ks) { return 2 * Ks * Ks + 2 * Ks + 2; }
+__host__ __device__ inline int red_size(int Ks) { return 2 * Ks * Ks + 2 * Ks + 5; }
+
+struct SolverLaunch {
+    cudaStream_t stream;
+    unsigned long long *launches;
+};
+
+// A, g_a, cost of all datasets -> red[A..cost]; partial is scratch of >= blocks*MAX_NE doubles
+cudaError_t launch_accumulate_shared(const DatasetDesc *d_desc, const DatasetDesc *h_desc, int n_ds, int Ks,
+                                     double *partial, size_t partial_doubles, double *red, SolverLaunch sl);
+
+// per-pose factorisation + Schur terms -> ws, red[S,v], red[gmax]
+cudaError_t launch_pose_schur(const DatasetDesc *d_desc, int n_pose, int Ks,
+                              const int *pose_start, const int *contrib_ds, const int *contrib_img,
+                              double *scale, LmConsts lm, double *ws, double *partial, size_t partial_doubles,
+                              double *red, SolverLaunch sl);
+
+// candidate poses and model / norm partial sums -> red[model..]
+// pose_ptr_cur/cand: per pose-list entry the device address of its 6 doubles is
+// base_cur[seq] + 6*i, expressed through pose_seq (sequence id) and pose_local (index).
+cudaError_t launch_pose_backsub(int n_pose, int Ks, const double *delta_a,
+                                const double *const *seq_cur, double *const *seq_cand,
+                                const int *pose_seq, const int *pose_local,
+                                const double *ws, double *partial, size_t partial_doubles, double *red,
+                                SolverLaunch sl);
+
+}  // namespace vg
