@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""bench.py -- corner reprojection residual+Jacobian evaluations/s (BASELINE.json metric).
+
+A *step* is one pass of the calibration hot path over one batch of synthetic input:
+for every board corner of every image the residual 2-vector and the analytic
+Jacobian blocks (Ceres layout, materialised in memory), plus the J^T J / J^T r
+normal-equation build and its reduction to the shared (intrinsic) block -- what one
+Ceres evaluation of the reference costs (calib_cost_functions.cpp:28-117 driven by
+ceres::Solve, unified_calibration.cpp:53).  With N > 1 GPUs every rank owns its own
+images (weak scaling) and the reduced block is summed with one NCCL all-reduce.
+
+Workload at N=1: BASELINE.json configs[1] -- monocular EUCM, 10 000 synthetic images
+x 54 corners (9x6 board), fp64.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          # the CUDA engine
+  python bench.py --impl reference [...]                        # reference CPU path, host threads
+
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import synthdata as sd  # noqa: E402
+
+METRIC = "corner_residual_jacobian_evals_per_s"
+UNIT = "corner evaluations/s"
+P_CORNERS = 54
+# algorithmic bytes per image, eucm mono: 54 corners x 224 B + 680 B of per-image blocks
+ALGO_BYTES_PER_IMAGE = {"eucm": 54 * 224 + 680, "ucm": 54 * 208 + 632, "mei": 54 * 288 + 872}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--images-per-gpu", type=int, default=10000)
+    ap.add_argument("--model", default="eucm", choices=["eucm", "ucm", "mei"])
+    ap.add_argument("--sets", type=int, default=4, help="rotating buffer sets (working set > L2)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline leg")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampling during the timed regions."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            fields = self.Q
+            probe = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={fields}", "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=20)
+            if probe.returncode != 0 or "not a valid field" in (probe.stdout + probe.stderr).lower():
+                fields = fields.replace("clocks_event_reasons", "clocks_throttle_reasons")
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={fields}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, windows):
+        sm, smax, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, line in self.rows:
+            if not any(a <= t <= b for a, b in windows):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0])); smax = max(smax, float(f[1]))
+            except Exception:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ----------------------------------------------------------------------------------------
+def cpu_reference_leg(d, model_id, n_img_step, steps, warmup, threads=None):
+    """Times the reference's CPU implementation of the step on the host cores:
+    oracle/_ref (the reference's own sources) when it was built, else the oracle port."""
+    from oracle import pyoracle
+    kind, ev = "port", None
+    try:
+        ev = pyoracle.Reference()
+        kind = "reference"
+    except Exception:
+        ev = pyoracle.Oracle()
+    orc = pyoracle.Oracle()
+    threads = threads or orc.max_threads()
+    K, P = d["K"], d["P"]
+    n = n_img_step
+    obs = np.ascontiguousarray(d["obs"][:n]); xi = np.ascontiguousarray(d["xi_init"][:n])
+    ne = (K + 7) * (K + 8) // 2
+    r = np.empty((n, 2 * P)); Ja = np.empty((n, 2 * P, K)); Je = np.empty((n, 2 * P, 6)); H = np.empty((n, ne))
+    import ctypes as C
+    dp = lambda a: a.ctypes.data_as(pyoracle.c_dp)
+    st = np.zeros(1, dtype=np.int32); ig = np.zeros(1, dtype=np.int32)
+    xi_ptrs = (pyoracle.c_dp * 1)(dp(xi)); je_ptrs = (pyoracle.c_dp * 1)(dp(Je))
+    intr = np.ascontiguousarray(d["intr_init"]); board = np.ascontiguousarray(d["board"])
+
+    def step():
+        rc = ev._batch(model_id, dp(intr), n, P, dp(board), dp(obs), 1, st.ctypes.data_as(pyoracle.c_ip),
+                       ig.ctypes.data_as(pyoracle.c_ip), xi_ptrs, dp(r), dp(Ja), je_ptrs, dp(H), threads)
+        assert rc == 0
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return dict(value=n * P * steps / dt, seconds=dt, kind=kind, cores=threads,
+                sample=f"{steps} passes over {n} images x {P} corners (r + J + per-image J^T J), {threads} OpenMP threads")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    model_id = {"eucm": sd.EUCM, "ucm": sd.UCM, "mei": sd.MEI}[args.model]
+    n_img = args.images_per_gpu
+    d = sd.make_mono(model_id, n_img, seed=20242)
+    # bound the run: one probe pass decides how many images a step covers
+    probe = cpu_reference_leg(d, model_id, min(n_img, 2000), 1, 1)
+    rate = probe["value"]
+    budget_s = 150.0
+    per_step = max(200, min(n_img, int(rate * budget_s / max(1, args.steps + args.warmup) / d["P"])))
+    res = cpu_reference_leg(d, model_id, per_step, args.steps, args.warmup)
+    total_imgs = n_img * args.gpus
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * res["seconds"] / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"monocular {args.model}, {total_imgs} synthetic images x {d['P']} corners (9x6 board), "
+                               f"residual + analytic Jacobian + normal-equation build per step",
+                   "images_per_step": per_step, "cpu_threads": res["cores"]},
+        "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": res["kind"], "sample": res["sample"]},
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------
+class DevView:
+    """__cuda_array_interface__ view of a raw device pointer (for torch.distributed)."""
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from visgeom_b200 import build as vg_build
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if rank == 0:
+        vg_build.build()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+    import visgeom_b200 as vg
+    if vg.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device (the engine has no CPU path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    model_id = {"eucm": sd.EUCM, "ucm": sd.UCM, "mei": sd.MEI}[args.model]
+    n_img, P = args.images_per_gpu, P_CORNERS
+    d = sd.make_mono(model_id, n_img, seed=20242 + rank)
+    K = d["K"]
+    stream = torch.cuda.Stream(device=dev)
+    sampler = ClockSampler(local)
+    windows = []
+    launches0 = vg.launch_count()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- NSETS problems (own device buffers each) sharing one stream: working set > L2 -------
+    probs, ds_ids, tr_ids, cam_ids = [], [], [], []
+    for s in range(args.sets):
+        Pm = vg.Problem(local)
+        cam = Pm.add_camera(model_id, d["intr_init"])
+        tr = Pm.add_transform(d["xi_init"], is_global=False)
+        ds = Pm.add_dataset(cam, d["board"], d["obs"], [tr], [0])
+        Pm.materialize_jacobians(True)
+        Pm.set_stream(stream.cuda_stream)
+        if world > 1:
+            def allreduce(buf, count, strm):
+                t = torch.as_tensor(DevView(buf, count), device=dev)
+                with torch.cuda.stream(torch.cuda.ExternalStream(strm, device=dev)):
+                    dist.all_reduce(t)
+            Pm.set_allreduce(allreduce, rank, world)
+        probs.append(Pm); ds_ids.append(ds); tr_ids.append(tr); cam_ids.append(cam)
+    ks = probs[0].evaluate(want_reduced=True)[1].size
+    out_bytes = n_img * (2 * P * 8 * (1 + K + 6) + vg.hessian_entries(model_id, 1) * 8)
+    sampler.start()
+    time.sleep(0.3)
+
+    # ---- leg 1: device-resident steps (value) ---------------------------------------------------
+    with torch.cuda.stream(stream):
+        for i in range(args.warmup):
+            probs[i % args.sets].evaluate_async()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = vg.launch_count()
+        t_w0 = time.time()
+        e0.record(stream)
+        for i in range(args.steps):
+            probs[i % args.sets].evaluate_async()
+        e1.record(stream)
+        barrier()
+        windows.append((t_w0, time.time()))
+        step_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+        launches_per_step = (vg.launch_count() - l0) / args.steps
+    cost, red = probs[(args.steps - 1) % args.sets].fetch_reduced()
+    value = world * n_img * P / (step_ms * 1e-3)
+
+    # ---- leg 2: the dominant kernel alone (roofline), same buffers, launched back to back -------
+    bufs = []
+    for s in range(args.sets):
+        Pm = probs[s]
+        bufs.append(dict(obs=Pm.device_buffer(ds_ids[s], -1)[0], r=Pm.device_buffer(ds_ids[s], 0)[0],
+                         Ja=Pm.device_buffer(ds_ids[s], 1)[0], Je=Pm.device_buffer(ds_ids[s], 2)[0],
+                         H=Pm.device_buffer(ds_ids[s], -2)[0]))
+    t_intr = torch.from_numpy(d["intr_init"]).to(dev)
+    t_board = torch.from_numpy(d["board"]).to(dev)
+    t_xi = torch.from_numpy(d["xi_init"]).to(dev)
+
+    def kernel_only(s):
+        b = bufs[s]
+        vg.eval_chain_dev(model_id, t_intr.data_ptr(), t_board.data_ptr(), b["obs"], [t_xi.data_ptr()], [0], [0],
+                          n_img, P, r=b["r"], J_intr=b["Ja"], J_xi=[b["Je"]], H=b["H"], stream=stream.cuda_stream)
+    with torch.cuda.stream(stream):
+        for i in range(max(3, args.warmup)):
+            kernel_only(i % args.sets)
+        torch.cuda.synchronize()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_w0 = time.time()
+        k0.record(stream)
+        for i in range(args.steps):
+            kernel_only(i % args.sets)
+        k1.record(stream)
+        torch.cuda.synchronize()
+        windows.append((t_w0, time.time()))
+        kernel_us = k0.elapsed_time(k1) * 1e3 / args.steps
+    peak, peak_src = measured_peak()
+    algo_bytes = ALGO_BYTES_PER_IMAGE[args.model] * n_img
+    achieved = algo_bytes / (kernel_us * 1e-6) / 1e9
+
+    # ---- leg 3: end to end through the problem API with HOST buffers ---------------------------
+    # per step: pinned host -> device copy of that step's observations, poses and intrinsics, the same
+    # device work as leg 1, device -> host read of the cost and the reduced normal equations
+    h_obs = torch.from_numpy(d["obs"]).pin_memory()
+    h_xi = torch.from_numpy(d["xi_init"]).pin_memory()
+    h2d = h_obs.numel() * 8 + h_xi.numel() * 8 + K * 8
+    d2h = (ks + 1) * 8
+
+    def e2e_step(i):
+        Pm = probs[i % args.sets]
+        Pm.update_observations(ds_ids[i % args.sets], h_obs.data_ptr())
+        Pm.set_transform_ptr(tr_ids[i % args.sets], h_xi.data_ptr())
+        Pm.set_camera(cam_ids[i % args.sets], d["intr_init"])
+        Pm.evaluate_async()
+        return Pm.fetch_reduced()
+    n_e2e = max(10, min(args.steps, 100))
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    t_w0 = time.time()
+    t0 = time.perf_counter()
+    for i in range(n_e2e):
+        c_e2e, _ = e2e_step(i)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / n_e2e)
+    windows.append((t_w0, time.time()))
+    e2e_value = world * n_img * P / e2e_s
+
+    # the inner (Ceres cost-function) contract end to end: r and every Jacobian block back on the host
+    full_value = None
+    if rank == 0:
+        xs = [d["xi_init"]]
+        vg.eval_chain(model_id, d["intr_init"], d["board"], d["obs"], xs, [0], [0], want_H=True)
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            vg.eval_chain(model_id, d["intr_init"], d["board"], d["obs"], xs, [0], [0], want_H=True)
+        full_value = n_img * P * reps / (time.perf_counter() - t0)
+
+    sampler.stop()
+    clocks = sampler.summary(windows)
+    total_launches = vg.launch_count() - launches0
+
+    # ---- CPU baseline on the host cores (rank 0, N=1 only) --------------------------------------
+    cpu = None
+    if rank == 0 and world == 1:
+        probe = cpu_reference_leg(d, model_id, min(n_img, 2000), 1, 1)
+        passes = max(1, int(args.cpu_seconds * probe["value"] / (n_img * P)))
+        res = cpu_reference_leg(d, model_id, n_img, passes, 1)
+        one = cpu_reference_leg(d, model_id, min(n_img, 2000), 3, 1, threads=1)
+        cpu = {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": res["kind"], "sample": res["sample"],
+               "single_thread_value": one["value"]}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"monocular {args.model}, {world * n_img} synthetic images x {P} corners (9x6 board); "
+                                   "step = fused residual + analytic Jacobian (Ceres layout, written to HBM) + per-image "
+                                   "J^T J/J^T r + shared-block reduction" + (" + NCCL all-reduce" if world > 1 else ""),
+                       "images_per_gpu": n_img, "corners_per_image": P, "model": None,
+                       "l2": f"{args.sets} rotating buffer sets, {args.sets * out_bytes / 1e6:.0f} MB of outputs in flight (> 126 MB L2)",
+                       "cost_check": cost},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "reproj_eval_kernel", "kernel_us": kernel_us,
+                         "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_s * 1e3,
+                    "what": "vg_problem_* with pinned host inputs every step; result = cost + reduced normal equations"},
+            "e2e_ceres_contract": {"value": full_value, "unit": UNIT,
+                                   "what": "vg_eval_chain with host buffers: r, J_intr, J_pose and H copied back (PCIe bound)"},
+            "gpu_launches": int(round(launches_per_step * args.steps)), "gpu_launches_per_step": launches_per_step,
+            "gpu_launches_total": int(total_launches),
+            "clocks": clocks,
+        }
+        del line["config"]["model"]
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -104,6 +104,9 @@ int vg_eval_chain_dev(int model, const double *intr, int n_img, int P,
                       double *r, double *J_intr, double *const *J_xi, double *H,
                       void *stream);
 
+/* vg_eval_chain keeps a grow-only device workspace between calls; this frees it */
+void vg_release_workspace(void);
+
 /* Number of kernel launches this library has issued in the calling process
  * (monotonic counter; used by bench.py for its gpu_launches claim). */
 unsigned long long vg_launch_count(void);
@@ -177,7 +180,25 @@ int vg_problem_add_dataset(vg_problem *p, int camera, int P, const double *board
  * on `stream`.  NULL -> single GPU.  Images are sharded by the caller: each rank
  * adds only its own images/poses; shared parameters are replicated. */
 typedef int (*vg_allreduce_fn)(void *ctx, double *buf, int count, void *stream);
-int vg_problem_set_allreduce(vg_problem *p, vg_allreduce_fn fn, void *ctx);
+int vg_problem_set_allreduce(vg_problem *p, vg_allreduce_fn fn, void *ctx, int rank, int nranks);
+
+/* When enabled, every evaluation also materialises r and all Jacobian blocks in
+ * device memory in the Ceres layout (what GenericProjectionJac::Evaluate hands to
+ * Ceres); the LM loop itself only needs the per-image normal-equation blocks and
+ * runs with this off. */
+int vg_problem_materialize_jacobians(vg_problem *p, int enable);
+/* device pointers of dataset buffers (valid until the problem is destroyed):
+ * which = 0 residual, 1 J_intr, 2+e J_xi[e], -1 observations, -2 normal-equation blocks */
+int vg_problem_device_buffer(vg_problem *p, int dataset, int which, void **ptr, size_t *bytes);
+/* the CUDA stream (cudaStream_t) all of this problem's work is queued on; set_stream
+ * makes the problem use a caller-owned stream instead of its own */
+void *vg_problem_stream(vg_problem *p);
+int vg_problem_set_stream(vg_problem *p, void *stream);
+/* vg_problem_evaluate without the read-back: queues the fused kernels, the shared-block
+ * reduction and (multi-GPU) its all-reduce on the problem's stream and returns.
+ * vg_problem_fetch_reduced then copies cost / reduced (nullable) to the host and waits. */
+int vg_problem_evaluate_async(vg_problem *p);
+int vg_problem_fetch_reduced(vg_problem *p, double *cost, double *reduced);
 
 /* ceres::Solve, :53.  Parameters are updated in place inside the handle. */
 int vg_problem_solve(vg_problem *p, const vg_solve_options *o, vg_solve_summary *s);

@@ -1,0 +1,186 @@
+"""GPU parity of the problem-level path (vg_problem_*): normal-equation reduction and the
+Levenberg-Marquardt solve against the CPU oracle running the same algorithm, i.e. what
+GenericCameraCalibration::compute obtains from ceres::Solve (unified_calibration.cpp:39-53).
+
+north_star tolerance: final intrinsics within 1e-6 relative.  Held to 1e-8 here."""
+import numpy as np
+import pytest
+
+import synthdata as sd
+from oracle.pyoracle import OracleProblem
+
+pytestmark = pytest.mark.gpu
+D, I = 0, 1
+FINAL_RTOL = 1e-8
+
+
+def build_mono(P, d, intr=None, xi=None, constant_cam=False, constant_tr=False, seq_index=None, obs=None):
+    cam = P.add_camera(d["model"], d["intr_init"] if intr is None else intr, constant=constant_cam)
+    tr = P.add_transform(d["xi_init"] if xi is None else xi, is_global=False, constant=constant_tr)
+    ds = P.add_dataset(cam, d["board"], d["obs"] if obs is None else obs, [tr], [D], seq_index=seq_index)
+    return cam, tr, ds
+
+
+def build_stereo(P, s, n=None):
+    c1 = P.add_camera(sd.EUCM, s["intr1_init"])
+    c2 = P.add_camera(sd.EUCM, s["intr2_init"])
+    t12 = P.add_transform(s["xi12_init"], is_global=True)
+    tb = P.add_transform(s["xi_init"], is_global=False)
+    P.add_dataset(c1, s["board"], s["obs1"], [tb], [D])
+    P.add_dataset(c2, s["board"], s["obs2"], [t12, tb], [I, D])
+    return c1, c2, t12, tb
+
+
+def rel(a, b):
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-3)))
+
+
+@pytest.mark.parametrize("model", [sd.EUCM, sd.UCM, sd.MEI])
+def test_evaluate_matches_oracle(gpu, oracle, model):
+    d = sd.make_mono(model, 50, seed=31 + model)
+    G, O = gpu.Problem(), OracleProblem(oracle)
+    build_mono(G, d); build_mono(O, d)
+    cost, red = G.evaluate(want_reduced=True)
+    assert abs(cost - O.evaluate()) <= 1e-10 * cost
+    K = d["K"]
+    # J^T J / J^T r of the intrinsic block straight from the oracle's Jacobians
+    o = oracle.evaluate_batch(model, d["intr_init"], d["board"], d["obs"], [d["xi_init"]], [D], [0])
+    Ja = o["J_intr"].reshape(-1, K); r = o["r"].reshape(-1)
+    A = Ja.T @ Ja; g = Ja.T @ r
+    sc = np.sqrt(np.outer(np.diag(A), np.diag(A)))
+    assert np.abs(red[:K * K].reshape(K, K) - A).max() / sc.max() < 1e-10
+    assert np.abs((red[:K * K].reshape(K, K) - A) / sc).max() < 1e-9
+    assert np.abs(red[K * K:] - g).max() <= 1e-9 * np.abs(g).max()
+
+
+@pytest.mark.parametrize("model,n_img", [(sd.EUCM, 20), (sd.UCM, 20), (sd.MEI, 40)])
+def test_solve_matches_oracle_lm(gpu, oracle, model, n_img):
+    """C1: 20 images x 54 corners, noisy observations, reference options (tolerances 1e-15)."""
+    d = sd.make_mono(model, n_img, seed=20241 + model)
+    G, O = gpu.Problem(), OracleProblem(oracle)
+    gc, gt, _ = build_mono(G, d); oc, ot, _ = build_mono(O, d)
+    sg, so = G.solve(), O.solve()
+    assert sg.termination in (0, 1, 2) and so.termination in (0, 1, 2)
+    assert abs(sg.final_cost - so.final_cost) <= 1e-9 * so.final_cost
+    if model == sd.MEI:
+        # xi / focal length are nearly degenerate for MEI on a planar board (100+ LM iterations along a
+        # flat valley): hold the north_star tolerance, not the tighter one
+        assert rel(G.camera(gc), O.camera(oc)) < 1e-6
+        return
+    assert rel(G.camera(gc), O.camera(oc)) < FINAL_RTOL
+    assert np.abs(G.transform(gt) - O.transform(ot)).max() < 1e-8
+    # and the minimum is the right one: within noise of the ground truth
+    assert rel(G.camera(gc), d["intr_gt"]) < 0.05
+
+
+def test_noise_free_recovers_ground_truth(gpu):
+    d = sd.make_mono(sd.EUCM, 30, seed=5, noise_px=0.0)
+    G = gpu.Problem()
+    gc, gt, _ = build_mono(G, d)
+    s = G.solve()
+    assert s.final_cost < 1e-15
+    assert rel(G.camera(gc), d["intr_gt"]) < 1e-8
+    assert np.abs(G.transform(gt) - d["xi_gt"]).max() < 1e-8
+
+
+def test_stereo_solve_matches_oracle(gpu, oracle):
+    """C4 shape: shared block = 2 x 6 intrinsics + xiCam12 (18 columns), one pose per pair."""
+    s = sd.make_stereo(60, seed=20244)
+    G, O = gpu.Problem(), OracleProblem(oracle)
+    g = build_stereo(G, s); o = build_stereo(O, s)
+    sg, so = G.solve(), O.solve()
+    assert abs(sg.final_cost - so.final_cost) <= 1e-9 * so.final_cost
+    for a, b in ((g[0], o[0]), (g[1], o[1])):
+        assert rel(G.camera(a), O.camera(b)) < FINAL_RTOL
+    assert np.abs(G.transform(g[2]) - O.transform(o[2])).max() < 1e-8
+    assert np.abs(G.transform(g[3]) - O.transform(o[3])).max() < 1e-8
+    assert np.abs(G.transform(g[2])[0] - s["xi12_gt"]).max() < 5e-3
+
+
+def test_constant_blocks(gpu, oracle):
+    """SetParameterBlockConstant for the camera (unified_calibration.cpp:614-617) and for a transform (:604-610)."""
+    d = sd.make_mono(sd.EUCM, 12, seed=77)
+    for const_cam, const_tr in ((True, False), (False, True)):
+        G, O = gpu.Problem(), OracleProblem(oracle)
+        kw = dict(constant_cam=const_cam, constant_tr=const_tr,
+                  intr=d["intr_gt"] if const_cam else None, xi=d["xi_gt"] if const_tr else None)
+        gc, gt, _ = build_mono(G, d, **kw); oc, ot, _ = build_mono(O, d, **kw)
+        sg, so = G.solve(), O.solve()
+        assert abs(sg.final_cost - so.final_cost) <= 1e-9 * so.final_cost
+        assert rel(G.camera(gc), O.camera(oc)) < FINAL_RTOL
+        assert np.abs(G.transform(gt) - O.transform(ot)).max() < 1e-8
+        if const_cam:
+            assert (G.camera(gc) == d["intr_gt"]).all()
+        if const_tr:
+            assert (G.transform(gt) == d["xi_gt"]).all()
+
+
+def test_active_bounds(gpu, oracle):
+    """Box bounds by projection (SetParameterLower/UpperBound, unified_calibration.cpp:621-626)."""
+    d = sd.make_mono(sd.EUCM, 15, seed=78)
+    G, O = gpu.Problem(), OracleProblem(oracle)
+    gc, _, _ = build_mono(G, d); oc, _, _ = build_mono(O, d)
+    for P, c in ((G, gc), (O, oc)):
+        P.set_bounds(c, 0, 0.0, 0.55)      # alpha's optimum (0.59) is outside
+    sg, so = G.solve(), O.solve()
+    assert G.camera(gc)[0] == pytest.approx(0.55, abs=1e-12)
+    assert rel(G.camera(gc), O.camera(oc)) < 1e-6
+    assert abs(sg.final_cost - so.final_cost) <= 1e-8 * so.final_cost
+
+
+def test_missing_images_seq_index(gpu, oracle):
+    """Images without an extracted board are skipped (unified_calibration.cpp:520): the dataset lists
+    only the images it has and maps them onto the pose sequence."""
+    d = sd.make_mono(sd.EUCM, 25, seed=79)
+    keep = np.array([i for i in range(25) if i % 4 != 1], dtype=np.int32)
+    G, O = gpu.Problem(), OracleProblem(oracle)
+    kw = dict(seq_index=keep, obs=d["obs"][keep])
+    gc, gt, _ = build_mono(G, d, **kw); oc, ot, _ = build_mono(O, d, **kw)
+    sg, so = G.solve(), O.solve()
+    assert abs(sg.final_cost - so.final_cost) <= 1e-9 * so.final_cost
+    assert rel(G.camera(gc), O.camera(oc)) < FINAL_RTOL
+    missing = np.setdiff1d(np.arange(25), keep)
+    assert (G.transform(gt)[missing] == d["xi_init"][missing]).all()      # untouched poses
+    assert np.abs(G.transform(gt) - O.transform(ot)).max() < 1e-8
+
+
+def test_residuals_readback(gpu, oracle):
+    d = sd.make_mono(sd.MEI, 7, seed=80)
+    G = gpu.Problem()
+    _, _, ds = build_mono(G, d)
+    r = G.residuals(ds, d["n_img"], d["P"])
+    o = oracle.evaluate_batch(sd.MEI, d["intr_init"], d["board"], d["obs"], [d["xi_init"]], [D], [0], want_J=False)
+    assert np.abs(r - o["r"]).max() < 1e-9
+
+
+def test_problem_errors(gpu):
+    d = sd.make_mono(sd.EUCM, 3, seed=1)
+    G = gpu.Problem()
+    cam = G.add_camera(sd.EUCM, d["intr_init"])
+    g1 = G.add_transform(np.zeros(6), is_global=True)
+    g2 = G.add_transform(np.zeros(6), is_global=True)
+    sq = G.add_transform(d["xi_init"], is_global=False)
+    with pytest.raises(gpu.VisgeomError, match="not one sequences"):      # unified_calibration.cpp:228
+        G.add_dataset(cam, d["board"], d["obs"], [g1, g2], [D, D])
+    with pytest.raises(gpu.VisgeomError, match="too long"):               # :567
+        G.add_dataset(cam, d["board"], d["obs"], [g1, g2, sq, g1, g2, sq], [D] * 6)
+    with pytest.raises(gpu.VisgeomError, match="invalid number of intrinsic"):   # :151
+        G.add_camera(sd.EUCM, d["intr_init"][:5])
+
+
+def test_full_size_solve_properties(gpu):
+    """C2 at full size (10 000 images): the oracle LM would take minutes, so check size-independent
+    properties: monotone accepted costs, convergence to the noise floor, gradient ~ 0 at the end."""
+    d = sd.make_mono(sd.EUCM, 10000, seed=20242)
+    G = gpu.Problem()
+    gc, _, _ = build_mono(G, d)
+    o = G.default_options(); o.max_num_iterations = 30
+    s = G.solve(o)
+    dof = 2 * d["P"] * d["n_img"] - 6 - 6 * d["n_img"]
+    assert s.final_cost == pytest.approx(0.5 * 0.01 * dof, rel=0.02)     # sigma = 0.1 px
+    assert rel(G.camera(gc), d["intr_gt"]) < 2e-3
+    cost, red = G.evaluate(want_reduced=True)
+    K = 6
+    g = red[K * K:]
+    A = red[:K * K].reshape(K, K)
+    assert np.abs(g / np.sqrt(np.diag(A))).max() < 1e-6 * np.sqrt(2 * cost)

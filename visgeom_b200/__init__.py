@@ -74,7 +74,15 @@ def lib() -> C.CDLL:
         L.vg_problem_add_transform.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, c_dp]
         L.vg_problem_add_dataset.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp, C.c_int, c_dp, c_ip,
                                              C.c_int, c_ip, c_ip]
-        L.vg_problem_set_allreduce.argtypes = [C.c_void_p, ALLREDUCE_FN, C.c_void_p]
+        L.vg_problem_set_allreduce.argtypes = [C.c_void_p, ALLREDUCE_FN, C.c_void_p, C.c_int, C.c_int]
+        L.vg_problem_materialize_jacobians.argtypes = [C.c_void_p, C.c_int]
+        L.vg_problem_device_buffer.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p),
+                                               C.POINTER(C.c_size_t)]
+        L.vg_problem_stream.restype = C.c_void_p
+        L.vg_problem_stream.argtypes = [C.c_void_p]
+        L.vg_problem_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        L.vg_problem_evaluate_async.argtypes = [C.c_void_p]
+        L.vg_problem_fetch_reduced.argtypes = [C.c_void_p, c_dp, c_dp]
         L.vg_problem_solve.argtypes = [C.c_void_p, C.POINTER(SolveOptions), C.POINTER(SolveSummary)]
         L.vg_problem_evaluate.argtypes = [C.c_void_p, c_dp, c_dp]
         L.vg_problem_num_shared.argtypes = [C.c_void_p]
@@ -220,7 +228,7 @@ class Problem:
             None if si is None else si.ctypes.data_as(c_ip), len(ids),
             ids.ctypes.data_as(c_ip), st.ctypes.data_as(c_ip)))
 
-    def set_allreduce(self, fn):
+    def set_allreduce(self, fn, rank, nranks):
         """fn(buf_ptr:int, count:int, stream:int) -> None sums count doubles in place across ranks."""
         def tramp(ctx, buf, count, stream):
             try:
@@ -231,7 +239,34 @@ class Problem:
                 traceback.print_exc()
                 return -1
         self._cb = ALLREDUCE_FN(tramp)
-        _check(self.L.vg_problem_set_allreduce(self.h, self._cb, None))
+        _check(self.L.vg_problem_set_allreduce(self.h, self._cb, None, rank, nranks))
+
+    def materialize_jacobians(self, enable=True):
+        _check(self.L.vg_problem_materialize_jacobians(self.h, int(enable)))
+
+    def device_buffer(self, dataset, which):
+        ptr, nb = C.c_void_p(), C.c_size_t()
+        _check(self.L.vg_problem_device_buffer(self.h, dataset, which, C.byref(ptr), C.byref(nb)))
+        return ptr.value, nb.value
+
+    @property
+    def stream(self):
+        return self.L.vg_problem_stream(self.h)
+
+    def set_stream(self, stream_ptr):
+        _check(self.L.vg_problem_set_stream(self.h, stream_ptr))
+
+    def evaluate_async(self):
+        _check(self.L.vg_problem_evaluate_async(self.h))
+
+    def fetch_reduced(self, want_reduced=True):
+        c = C.c_double()
+        red = None
+        if want_reduced:
+            ks = _check(self.L.vg_problem_num_shared(self.h))
+            red = np.zeros(ks * ks + ks)
+        _check(self.L.vg_problem_fetch_reduced(self.h, C.cast(C.byref(c), c_dp), _dp(red) if red is not None else None))
+        return c.value, red
 
     def default_options(self) -> SolveOptions:
         o = SolveOptions()
@@ -270,6 +305,10 @@ class Problem:
     def set_transform(self, tid, values):
         v = _f64(values).reshape(-1, 6)
         _check(self.L.vg_problem_set_transform(self.h, tid, _dp(v)))
+
+    def set_transform_ptr(self, tid, host_ptr: int):
+        """values read from a (pinned) host address"""
+        _check(self.L.vg_problem_set_transform(self.h, tid, C.cast(host_ptr, c_dp)))
 
     def update_observations(self, dataset, host_ptr: int):
         _check(self.L.vg_problem_update_observations(self.h, dataset, host_ptr))

@@ -23,6 +23,10 @@ int fail_cuda(cudaError_t e, const char *where)
 }
 unsigned long long &launch_counter() { return g_launches; }
 
+static char *g_ws = nullptr;
+static size_t g_ws_bytes = 0;
+static int g_ws_dev = -1;
+
 static int model_K(int model)
 {
     switch (model) {
@@ -84,6 +88,11 @@ int vg_hessian_entries(int model, int chain_len)
 }
 
 unsigned long long vg_launch_count(void) { return g_launches; }
+
+void vg_release_workspace(void)
+{
+    if (g_ws) { cudaFree(g_ws); g_ws = nullptr; g_ws_bytes = 0; g_ws_dev = -1; }
+}
 
 static int check_eval_args(int model, int n_img, int P, int chain_len, const void *intr, const void *board,
                            const void *obs, const int *status, const int *is_global, const void *xi)
@@ -150,10 +159,18 @@ int vg_eval_chain(int model, const double *intr, int n_img, int P,
     Piece p_r = reserve(r ? rows * 8 : 0), p_ja = reserve(J_intr ? rows * K * 8 : 0);
     for (int e = 0; e < chain_len; e++) p_je[e] = reserve((J_xi && J_xi[e]) ? rows * 48 : 0);
     Piece p_h = reserve(H ? (size_t)n_img * ne * 8 : 0);
-    char *d = nullptr;
-    VG_CUDA(cudaMalloc(&d, total ? total : 256));
+    // grow-only device workspace kept between calls (released by vg_release_workspace)
+    int dev = 0;
+    VG_CUDA(cudaGetDevice(&dev));
+    if (g_ws && (g_ws_dev != dev || g_ws_bytes < total)) { cudaFree(g_ws); g_ws = nullptr; g_ws_bytes = 0; }
+    if (!g_ws) {
+        VG_CUDA(cudaMalloc(&g_ws, total ? total : 256));
+        g_ws_bytes = total ? total : 256;
+        g_ws_dev = dev;
+    }
+    char *d = g_ws;
     cudaStream_t st = nullptr;
-    auto cleanup = [&](int code) { cudaFree(d); return code; };
+    auto cleanup = [&](int code) { return code; };
 #define VG_TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cleanup(fail_cuda(e__, #call)); } while (0)
     VG_TRY(cudaMemcpyAsync(d + p_intr.off, intr, p_intr.bytes, cudaMemcpyHostToDevice, st));
     VG_TRY(cudaMemcpyAsync(d + p_board.off, board, p_board.bytes, cudaMemcpyHostToDevice, st));

@@ -1,0 +1,874 @@
+// vg_problem.cu -- C ABI, outer boundary: the problem GenericCameraCalibration
+// assembles (unified_calibration.cpp:514-630) and the Levenberg-Marquardt solve that
+// stands in for ceres::Solve (:39-53).  The loop follows Ceres' documented
+// trust-region defaults: Jacobi scaling fixed at iteration 0, LM
+// diagonal clamp(diag(J^T J),1e-6,1e32)/radius, step accepted when the relative
+// decrease exceeds 1e-3, radius /= max(1/3, 1-(2 rho-1)^3) on accept, radius /= nu
+// with nu doubling on reject, box bounds by projection.  Everything that touches an
+// image or a pose runs on the GPU; the host only solves the Ks x Ks reduced system
+// (Ks <= a few dozen) and takes the accept / reject decision.
+#include "vg_common.h"
+#include "vg_eval.cuh"
+#include "vg_solver_kernels.cuh"
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+using namespace vg;
+
+namespace {
+
+constexpr int CAM_STRIDE = 16;   // doubles per camera in the shared-parameter slab
+
+struct Cam {
+    int model, K, constant, shared_off;
+    double params[VG_MAX_INTRINSICS], lo[VG_MAX_INTRINSICS], hi[VG_MAX_INTRINSICS];
+};
+
+struct Tr {
+    int is_global, constant, n;
+    int shared_off, pose_off;      // free global / free sequence, else -1
+    int glob_slot;                 // index among global transforms (slab position)
+    int seq_slot;                  // index among sequence transforms
+    std::vector<double> host;      // n x 6
+    double *dev[2];                // sequences: device poses (set 0 / 1); constants alias one buffer
+};
+
+struct Ds {
+    int cam, P, n_img, L, D, W, ne;
+    int tr[VG_MAX_CHAIN], status[VG_MAX_CHAIN];
+    int seq_tr;                    // transform id of the chain's sequence element
+    std::vector<int> seq_index;
+    bool identity_index;
+    double *d_board, *d_obs;
+    int *d_seq_index;
+    double *d_H[2];
+    double *d_r, *d_Ja, *d_Je[VG_MAX_CHAIN];   // only when Jacobians are materialised
+};
+
+double now_s()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+int chol(std::vector<double> &M, int n)
+{
+    for (int j = 0; j < n; j++) {
+        double s = M[j * n + j];
+        for (int k = 0; k < j; k++) s -= M[j * n + k] * M[j * n + k];
+        if (!(s > 0.0)) return -1;
+        s = std::sqrt(s);
+        M[j * n + j] = s;
+        for (int i = j + 1; i < n; i++) {
+            double t = M[i * n + j];
+            for (int k = 0; k < j; k++) t -= M[i * n + k] * M[j * n + k];
+            M[i * n + j] = t / s;
+        }
+    }
+    return 0;
+}
+
+void chol_solve(const std::vector<double> &Lm, int n, double *x)
+{
+    for (int i = 0; i < n; i++) {
+        double s = x[i];
+        for (int k = 0; k < i; k++) s -= Lm[i * n + k] * x[k];
+        x[i] = s / Lm[i * n + i];
+    }
+    for (int i = n - 1; i >= 0; i--) {
+        double s = x[i];
+        for (int k = i + 1; k < n; k++) s -= Lm[k * n + i] * x[k];
+        x[i] = s / Lm[i * n + i];
+    }
+}
+
+double clampd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+}  // namespace
+
+struct vg_problem {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    std::vector<Cam> cams;
+    std::vector<Tr> trs;
+    std::vector<Ds> dss;
+    int n_glob = 0, n_seq = 0;
+    bool materialize = false;
+
+    // prepared state
+    bool prepared = false;
+    int Ks = 0, n_pose = 0, cur = 0;
+    int rank = 0, nranks = 1;
+    vg_allreduce_fn allreduce = nullptr;
+    void *allreduce_ctx = nullptr;
+    double *d_slab[2] = {nullptr, nullptr};   // [cams | globals], per parameter set
+    size_t slab_doubles = 0;
+    std::vector<double> h_slab;
+    DatasetDesc *d_desc[2] = {nullptr, nullptr};
+    std::vector<DatasetDesc> h_desc[2];
+    int *d_pose_start = nullptr, *d_contrib_ds = nullptr, *d_contrib_img = nullptr;
+    int *d_pose_seq = nullptr, *d_pose_local = nullptr, *d_fail = nullptr, *d_acc_tab = nullptr;
+    std::vector<int> h_acc_tab;
+    double **d_seq_ptr[2] = {nullptr, nullptr};
+    double *d_scale = nullptr, *d_ws = nullptr, *d_partial = nullptr, *d_red = nullptr, *d_delta = nullptr;
+    size_t partial_doubles = 0;
+    double *h_red = nullptr;                  // pinned
+    double *h_up = nullptr;                   // pinned upload staging: [slab | delta_a]
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double eval_ms = 0;
+    int n_eval = 0;
+
+    double *cam_ptr(int set, int cam) const { return d_slab[set] + (size_t)cam * CAM_STRIDE; }
+    double *glob_ptr(int set, int slot) const { return d_slab[set] + cams.size() * CAM_STRIDE + (size_t)slot * 6; }
+};
+
+namespace {
+
+void free_prepared(vg_problem *p)
+{
+    auto F = [](auto *&ptr) { if (ptr) { cudaFree(ptr); ptr = nullptr; } };
+    for (int s = 0; s < 2; s++) { F(p->d_slab[s]); F(p->d_desc[s]); F(p->d_seq_ptr[s]); }
+    F(p->d_pose_start); F(p->d_contrib_ds); F(p->d_contrib_img); F(p->d_pose_seq); F(p->d_pose_local);
+    F(p->d_fail); F(p->d_acc_tab); F(p->d_scale); F(p->d_ws); F(p->d_partial); F(p->d_red); F(p->d_delta);
+    if (p->h_red) { cudaFreeHost(p->h_red); p->h_red = nullptr; }
+    if (p->h_up) { cudaFreeHost(p->h_up); p->h_up = nullptr; }
+    for (auto &d : p->dss)
+        for (int s = 0; s < 2; s++) F(d.d_H[s]);
+    p->prepared = false;
+}
+
+void fill_slab(const vg_problem *p, double *dst)
+{
+    memset(dst, 0, p->slab_doubles * sizeof(double));
+    for (size_t c = 0; c < p->cams.size(); c++)
+        memcpy(dst + c * CAM_STRIDE, p->cams[c].params, sizeof(double) * p->cams[c].K);
+    for (const Tr &t : p->trs)
+        if (t.is_global) memcpy(dst + p->cams.size() * CAM_STRIDE + (size_t)t.glob_slot * 6, t.host.data(), 48);
+}
+
+// (re)build everything that depends on the problem structure
+int prepare(vg_problem *p)
+{
+    if (p->prepared) return VG_OK;
+    VG_CUDA(cudaSetDevice(p->device));
+    // parameter layout: free cameras then free globals are the shared block
+    int off = 0, po = 0;
+    for (Cam &c : p->cams) { c.shared_off = c.constant ? -1 : off; if (!c.constant) off += c.K; }
+    for (Tr &t : p->trs) {
+        t.shared_off = t.pose_off = -1;
+        if (t.constant) continue;
+        if (t.is_global) { t.shared_off = off; off += 6; }
+        else { t.pose_off = po; po += t.n; }
+    }
+    p->Ks = off;
+    p->n_pose = po;
+    const int Ks = p->Ks, NP = p->n_pose;
+
+    p->slab_doubles = p->cams.size() * CAM_STRIDE + (size_t)p->n_glob * 6 + 2;
+    p->h_slab.assign(p->slab_doubles, 0.0);
+    for (int s = 0; s < 2; s++) VG_CUDA(cudaMalloc(&p->d_slab[s], p->slab_doubles * sizeof(double)));
+    VG_CUDA(cudaMallocHost(&p->h_up, (p->slab_doubles + Ks + 2) * sizeof(double)));
+    VG_CUDA(cudaMalloc(&p->d_delta, (Ks + 2) * sizeof(double)));
+
+    // dataset descriptors (one per parameter set: they differ in the H pointer)
+    for (int s = 0; s < 2; s++) p->h_desc[s].assign(p->dss.size(), DatasetDesc());
+    std::vector<std::vector<std::pair<int, int>>> contrib(NP);
+    for (size_t k = 0; k < p->dss.size(); k++) {
+        Ds &d = p->dss[k];
+        const Cam &c = p->cams[d.cam];
+        DatasetDesc dd;
+        memset(&dd, 0, sizeof dd);
+        dd.n_img = d.n_img; dd.ne = d.ne; dd.W = d.W;
+        dd.seq_index = d.d_seq_index;
+        dd.pose_col = -1; dd.pose_base = -1; dd.n_sl = 0;
+        for (int a = 0; a < c.K; a++) {
+            dd.kind[a] = c.shared_off >= 0 ? COL_SHARED : COL_CONST;
+            dd.idx[a] = c.shared_off + a;
+        }
+        for (int e = 0; e < d.L; e++) {
+            const Tr &t = p->trs[d.tr[e]];
+            for (int q = 0; q < 6; q++) {
+                const int a = c.K + 6 * e + q;
+                if (t.is_global) { dd.kind[a] = t.shared_off >= 0 ? COL_SHARED : COL_CONST; dd.idx[a] = t.shared_off + q; }
+                else { dd.kind[a] = t.pose_off >= 0 ? COL_POSE : COL_CONST; dd.idx[a] = q; }
+            }
+            if (!t.is_global && t.pose_off >= 0) { dd.pose_col = c.K + 6 * e; dd.pose_base = t.pose_off; }
+        }
+        dd.kind[d.D] = COL_RESID; dd.idx[d.D] = 0;
+        for (int a = 0; a < d.D; a++)
+            if (dd.kind[a] == COL_SHARED) { dd.sl_col[dd.n_sl] = a; dd.sl_idx[dd.n_sl] = dd.idx[a]; dd.n_sl++; }
+        for (int s = 0; s < 2; s++) {
+            if (!d.d_H[s]) VG_CUDA(cudaMalloc(&d.d_H[s], sizeof(double) * (size_t)d.ne * (d.n_img ? d.n_img : 1)));
+            dd.H = d.d_H[s];
+            p->h_desc[s][k] = dd;
+        }
+        if (dd.pose_base >= 0)
+            for (int i = 0; i < d.n_img; i++) contrib[dd.pose_base + d.seq_index[i]].push_back({(int)k, i});
+    }
+    for (int s = 0; s < 2; s++) {
+        VG_CUDA(cudaMalloc(&p->d_desc[s], sizeof(DatasetDesc) * (p->dss.size() ? p->dss.size() : 1)));
+        if (!p->dss.empty())
+            VG_CUDA(cudaMemcpy(p->d_desc[s], p->h_desc[s].data(), sizeof(DatasetDesc) * p->dss.size(), cudaMemcpyHostToDevice));
+    }
+    // pose list: CSR of (dataset, image) contributions, owning sequence and local index
+    std::vector<int> pose_start(NP + 1, 0), cds, cimg, pseq(NP ? NP : 1, 0), ploc(NP ? NP : 1, 0);
+    for (int q = 0; q < NP; q++) {
+        pose_start[q] = (int)cds.size();
+        for (auto &pr : contrib[q]) { cds.push_back(pr.first); cimg.push_back(pr.second); }
+    }
+    pose_start[NP] = (int)cds.size();
+    std::vector<double *> seq_ptr[2];
+    for (const Tr &t : p->trs) {
+        if (t.is_global) continue;
+        for (int s = 0; s < 2; s++) seq_ptr[s].push_back(t.dev[s]);
+        if (t.pose_off >= 0)
+            for (int i = 0; i < t.n; i++) { pseq[t.pose_off + i] = t.seq_slot; ploc[t.pose_off + i] = i; }
+    }
+    auto upload_i = [&](int *&dptr, const std::vector<int> &v) -> cudaError_t {
+        cudaError_t e = cudaMalloc(&dptr, sizeof(int) * (v.size() ? v.size() : 1));
+        if (e != cudaSuccess || v.empty()) return e;
+        return cudaMemcpy(dptr, v.data(), sizeof(int) * v.size(), cudaMemcpyHostToDevice);
+    };
+    VG_CUDA(upload_i(p->d_pose_start, pose_start));
+    VG_CUDA(upload_i(p->d_contrib_ds, cds));
+    VG_CUDA(upload_i(p->d_contrib_img, cimg));
+    VG_CUDA(upload_i(p->d_pose_seq, pseq));
+    VG_CUDA(upload_i(p->d_pose_local, ploc));
+    for (int s = 0; s < 2; s++) {
+        VG_CUDA(cudaMalloc(&p->d_seq_ptr[s], sizeof(double *) * (seq_ptr[s].size() ? seq_ptr[s].size() : 1)));
+        if (!seq_ptr[s].empty())
+            VG_CUDA(cudaMemcpy(p->d_seq_ptr[s], seq_ptr[s].data(), sizeof(double *) * seq_ptr[s].size(), cudaMemcpyHostToDevice));
+    }
+    p->h_acc_tab.assign(2 * p->dss.size() + 2, 0);
+    accumulate_shared_table(p->h_desc[0].data(), (int)p->dss.size(), p->h_acc_tab.data());
+    VG_CUDA(upload_i(p->d_acc_tab, p->h_acc_tab));
+    VG_CUDA(cudaMalloc(&p->d_fail, sizeof(int)));
+    VG_CUDA(cudaMemset(p->d_fail, 0, sizeof(int)));
+    VG_CUDA(cudaMalloc(&p->d_scale, sizeof(double) * 6 * (size_t)(NP ? NP : 1)));
+    VG_CUDA(cudaMalloc(&p->d_ws, sizeof(double) * (size_t)pose_ws_stride(Ks) * (NP ? NP : 1)));
+    size_t pd = accumulate_shared_scratch(p->h_desc[0].data(), (int)p->dss.size());
+    const size_t pd2 = pose_scratch(NP, Ks);
+    if (pd2 > pd) pd = pd2;
+    p->partial_doubles = pd + 64;
+    VG_CUDA(cudaMalloc(&p->d_partial, sizeof(double) * p->partial_doubles));
+    const int rs = red_size(Ks, p->nranks);
+    VG_CUDA(cudaMalloc(&p->d_red, sizeof(double) * rs));
+    VG_CUDA(cudaMemset(p->d_red, 0, sizeof(double) * rs));
+    VG_CUDA(cudaMallocHost(&p->h_red, sizeof(double) * rs));
+    p->cur = 0;
+    // both parameter sets start from the host values
+    fill_slab(p, p->h_slab.data());
+    for (int s = 0; s < 2; s++)
+        VG_CUDA(cudaMemcpy(p->d_slab[s], p->h_slab.data(), p->slab_doubles * sizeof(double), cudaMemcpyHostToDevice));
+    for (Tr &t : p->trs)
+        if (!t.is_global)
+            for (int s = 0; s < 2; s++)
+                if (s == 0 || t.dev[1] != t.dev[0])
+                    VG_CUDA(cudaMemcpy(t.dev[s], t.host.data(), sizeof(double) * 6 * t.n, cudaMemcpyHostToDevice));
+    p->prepared = true;
+    return VG_OK;
+}
+
+// fused residual + Jacobian + normal-equation kernels of every dataset at parameter set s,
+// then the shared-block reduction -> d_red segment E (A, g_a, cost)
+int evaluate_set(vg_problem *p, int s, bool timed)
+{
+    if (timed) VG_CUDA(cudaEventRecord(p->ev0, p->stream));
+    for (Ds &d : p->dss) {
+        EvalArgs a;
+        memset(&a, 0, sizeof a);
+        a.intr = p->cam_ptr(s, d.cam);
+        a.board = d.d_board; a.obs = d.d_obs;
+        a.seq_index = d.identity_index ? nullptr : d.d_seq_index;
+        for (int e = 0; e < d.L; e++) {
+            const Tr &t = p->trs[d.tr[e]];
+            a.xi[e] = t.is_global ? p->glob_ptr(s, t.glob_slot) : t.dev[s];
+            a.xi_stride[e] = t.is_global ? 0 : 6;
+            a.inverse[e] = d.status[e] == VG_TRANSFORM_INVERSE;
+            a.Je[e] = p->materialize ? d.d_Je[e] : nullptr;
+        }
+        a.r = p->materialize ? d.d_r : nullptr;
+        a.Ja = p->materialize ? d.d_Ja : nullptr;
+        a.H = d.d_H[s];
+        a.n_img = d.n_img; a.P = d.P;
+        cudaError_t e = launch_eval(p->cams[d.cam].model, d.L, a, p->stream, &launch_counter());
+        if (e != cudaSuccess) return fail_cuda(e, "reproj_eval_kernel launch");
+    }
+    if (timed) VG_CUDA(cudaEventRecord(p->ev1, p->stream));
+    SolverLaunch sl{p->stream, &launch_counter()};
+    cudaError_t e = launch_accumulate_shared(p->d_desc[s], (int)p->dss.size(), p->Ks, p->d_partial,
+                                             p->h_acc_tab.data(), p->d_acc_tab, p->d_red, sl);
+    if (e != cudaSuccess) return fail_cuda(e, "accumulate_shared");
+    p->n_eval++;
+    return VG_OK;
+}
+
+// exchange a segment of the reduction buffer across ranks (if any) and fetch it
+int fetch_segment(vg_problem *p, int off, int count)
+{
+    if (p->allreduce && p->nranks > 1) {
+        if (p->allreduce(p->allreduce_ctx, p->d_red + off, count, p->stream) != 0)
+            return fail(VG_ERR_CUDA, "all-reduce callback failed");
+    }
+    VG_CUDA(cudaMemcpyAsync(p->h_red + off, p->d_red + off, sizeof(double) * count, cudaMemcpyDeviceToHost, p->stream));
+    VG_CUDA(cudaStreamSynchronize(p->stream));
+    return VG_OK;
+}
+
+int ensure_materialized(vg_problem *p)
+{
+    for (Ds &d : p->dss) {
+        const size_t rows = (size_t)(d.n_img ? d.n_img : 1) * 2 * d.P;
+        const int K = p->cams[d.cam].K;
+        if (!d.d_r) VG_CUDA(cudaMalloc(&d.d_r, rows * 8));
+        if (!d.d_Ja) VG_CUDA(cudaMalloc(&d.d_Ja, rows * K * 8));
+        for (int e = 0; e < d.L; e++)
+            if (!d.d_Je[e]) VG_CUDA(cudaMalloc(&d.d_Je[e], rows * 48));
+    }
+    return VG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void vg_solve_options_default(vg_solve_options *o)
+{
+    o->max_num_iterations = 1000;       // unified_calibration.cpp:46
+    o->function_tolerance = 1e-15;      // :47
+    o->gradient_tolerance = 1e-15;      // :48
+    o->parameter_tolerance = 1e-15;     // :49
+    o->initial_radius = 1e4;
+    o->max_radius = 1e16;
+    o->min_radius = 1e-32;
+    o->min_relative_decrease = 1e-3;
+    o->min_lm_diagonal = 1e-6;
+    o->max_lm_diagonal = 1e32;
+    o->jacobi_scaling = 1;
+    o->max_consecutive_invalid = 5;
+    o->verbose = 0;
+    o->reserved = 0;
+}
+
+vg_problem *vg_problem_create(int device)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n < 1) {
+        cudaGetLastError();
+        set_error("no CUDA device: this engine has no CPU path");
+        return nullptr;
+    }
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) { set_error("cudaGetDevice failed"); return nullptr; }
+    if (device >= n) { set_error("device index out of range"); return nullptr; }
+    vg_problem *p = new vg_problem();
+    p->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&p->ev0) != cudaSuccess || cudaEventCreate(&p->ev1) != cudaSuccess) {
+        set_error("CUDA stream / event creation failed");
+        delete p;
+        return nullptr;
+    }
+    p->stream = p->own_stream;
+    return p;
+}
+
+void vg_problem_destroy(vg_problem *p)
+{
+    if (!p) return;
+    cudaSetDevice(p->device);
+    cudaStreamSynchronize(p->stream);
+    free_prepared(p);
+    for (Tr &t : p->trs) {
+        if (!t.is_global) {
+            if (t.dev[1] && t.dev[1] != t.dev[0]) cudaFree(t.dev[1]);
+            if (t.dev[0]) cudaFree(t.dev[0]);
+        }
+    }
+    for (Ds &d : p->dss) {
+        cudaFree(d.d_board); cudaFree(d.d_obs); cudaFree(d.d_seq_index);
+        cudaFree(d.d_r); cudaFree(d.d_Ja);
+        for (int e = 0; e < VG_MAX_CHAIN; e++) cudaFree(d.d_Je[e]);
+    }
+    cudaEventDestroy(p->ev0); cudaEventDestroy(p->ev1);
+    cudaStreamDestroy(p->own_stream);
+    delete p;
+}
+
+int vg_problem_add_camera(vg_problem *p, int model, const double *value, int constant)
+{
+    if (!p || !value) return fail(VG_ERR_INVALID, "null argument");
+    const int K = vg_model_num_params(model);
+    if (K < 0) return K;
+    Cam c;
+    memset(&c, 0, sizeof c);
+    c.model = model; c.K = K; c.constant = constant ? 1 : 0; c.shared_off = -1;
+    for (int i = 0; i < K; i++) {
+        c.params[i] = value[i];
+        vg_model_bounds(model, i, &c.lo[i], &c.hi[i]);
+    }
+    cudaSetDevice(p->device);
+    free_prepared(p);
+    p->cams.push_back(c);
+    return (int)p->cams.size() - 1;
+}
+
+int vg_problem_set_bounds(vg_problem *p, int camera, int idx, double lower, double upper)
+{
+    if (!p || camera < 0 || camera >= (int)p->cams.size() || idx < 0 || idx >= p->cams[camera].K)
+        return fail(VG_ERR_INVALID, "vg_problem_set_bounds: bad camera or index");
+    p->cams[camera].lo[idx] = lower;
+    p->cams[camera].hi[idx] = upper;
+    return VG_OK;
+}
+
+int vg_problem_add_transform(vg_problem *p, int is_global, int constant, int n, const double *values)
+{
+    if (!p || !values || n < 1 || (is_global && n != 1)) return fail(VG_ERR_INVALID, "vg_problem_add_transform: bad arguments");
+    VG_CUDA(cudaSetDevice(p->device));
+    free_prepared(p);
+    Tr t;
+    t.is_global = is_global ? 1 : 0; t.constant = constant ? 1 : 0; t.n = n;
+    t.shared_off = t.pose_off = -1;
+    t.glob_slot = t.seq_slot = -1;
+    t.host.assign(values, values + (size_t)6 * n);
+    t.dev[0] = t.dev[1] = nullptr;
+    if (t.is_global) t.glob_slot = p->n_glob++;
+    else {
+        t.seq_slot = p->n_seq++;
+        VG_CUDA(cudaMalloc(&t.dev[0], sizeof(double) * 6 * n));
+        if (t.constant) t.dev[1] = t.dev[0];
+        else VG_CUDA(cudaMalloc(&t.dev[1], sizeof(double) * 6 * n));
+    }
+    p->trs.push_back(t);
+    return (int)p->trs.size() - 1;
+}
+
+int vg_problem_add_dataset(vg_problem *p, int camera, int P, const double *board,
+                           int n_img, const double *obs, const int *seq_index,
+                           int chain_len, const int *transform_ids, const int *status)
+{
+    if (!p || !board || !transform_ids || !status || (n_img > 0 && !obs)) return fail(VG_ERR_INVALID, "null argument");
+    if (camera < 0 || camera >= (int)p->cams.size()) return fail(VG_ERR_INVALID, "unknown camera");
+    if (chain_len < 1) return fail(VG_ERR_INVALID, "empty transform chain");
+    if (chain_len > VG_MAX_CHAIN)
+        return fail(VG_ERR_INVALID, "the transform chain is too long (5 transforms at max are supproted)");   // :567
+    if (P < 1 || n_img < 0) return fail(VG_ERR_INVALID, "P < 1 or n_img < 0");
+    int nseq = 0, seq_tr = -1;
+    for (int e = 0; e < chain_len; e++) {
+        if (transform_ids[e] < 0 || transform_ids[e] >= (int)p->trs.size()) return fail(VG_ERR_INVALID, "unknown transform");
+        for (int f = 0; f < e; f++)
+            if (transform_ids[f] == transform_ids[e]) return fail(VG_ERR_INVALID, "a transform appears twice in one chain");
+        if (!p->trs[transform_ids[e]].is_global) { nseq++; seq_tr = transform_ids[e]; }
+    }
+    if (nseq != 1) return fail(VG_ERR_INVALID, "not one sequences in a transform chain");   // :228
+    if (eval_smem_bytes(p->cams[camera].model, chain_len, P, nullptr, nullptr) < 0)
+        return fail(VG_ERR_UNSUPPORTED, "board has too many points for one CTA's shared memory");
+    Ds d;
+    memset(static_cast<void *>(&d), 0, offsetof(Ds, seq_index));
+    d.d_board = d.d_obs = nullptr; d.d_seq_index = nullptr;
+    d.d_H[0] = d.d_H[1] = nullptr; d.d_r = d.d_Ja = nullptr;
+    for (int e = 0; e < VG_MAX_CHAIN; e++) d.d_Je[e] = nullptr;
+    d.cam = camera; d.P = P; d.n_img = n_img; d.L = chain_len;
+    d.D = p->cams[camera].K + 6 * chain_len; d.W = d.D + 1; d.ne = d.W * (d.W + 1) / 2;
+    d.seq_tr = seq_tr;
+    d.identity_index = true;
+    d.seq_index.resize(n_img);
+    for (int i = 0; i < n_img; i++) {
+        const int s = seq_index ? seq_index[i] : i;
+        if (s < 0 || s >= p->trs[seq_tr].n) return fail(VG_ERR_INVALID, "seq_index out of range");
+        if (s != i) d.identity_index = false;
+        d.seq_index[i] = s;
+    }
+    for (int e = 0; e < chain_len; e++) { d.tr[e] = transform_ids[e]; d.status[e] = status[e]; }
+    VG_CUDA(cudaSetDevice(p->device));
+    free_prepared(p);
+    const size_t obs_bytes = sizeof(double) * 2 * (size_t)P * (n_img ? n_img : 1);
+    VG_CUDA(cudaMalloc(&d.d_board, sizeof(double) * 3 * P));
+    VG_CUDA(cudaMalloc(&d.d_obs, obs_bytes));
+    VG_CUDA(cudaMalloc(&d.d_seq_index, sizeof(int) * (n_img ? n_img : 1)));
+    VG_CUDA(cudaMemcpy(d.d_board, board, sizeof(double) * 3 * P, cudaMemcpyHostToDevice));
+    if (n_img) {
+        VG_CUDA(cudaMemcpy(d.d_obs, obs, sizeof(double) * 2 * (size_t)P * n_img, cudaMemcpyHostToDevice));
+        VG_CUDA(cudaMemcpy(d.d_seq_index, d.seq_index.data(), sizeof(int) * n_img, cudaMemcpyHostToDevice));
+    }
+    p->dss.push_back(d);
+    return (int)p->dss.size() - 1;
+}
+
+int vg_problem_set_allreduce(vg_problem *p, vg_allreduce_fn fn, void *ctx, int rank, int nranks)
+{
+    if (!p || nranks < 1 || rank < 0 || rank >= nranks) return fail(VG_ERR_INVALID, "vg_problem_set_allreduce: bad arguments");
+    cudaSetDevice(p->device);
+    free_prepared(p);
+    p->allreduce = fn; p->allreduce_ctx = ctx; p->rank = rank; p->nranks = fn ? nranks : 1;
+    if (!fn) p->rank = 0;
+    return VG_OK;
+}
+
+int vg_problem_materialize_jacobians(vg_problem *p, int enable)
+{
+    if (!p) return fail(VG_ERR_INVALID, "null problem");
+    VG_CUDA(cudaSetDevice(p->device));
+    p->materialize = enable != 0;
+    if (p->materialize) return ensure_materialized(p);
+    return VG_OK;
+}
+
+void *vg_problem_stream(vg_problem *p) { return p ? p->stream : nullptr; }
+
+int vg_problem_set_stream(vg_problem *p, void *stream)
+{
+    if (!p) return fail(VG_ERR_INVALID, "null problem");
+    VG_CUDA(cudaSetDevice(p->device));
+    VG_CUDA(cudaStreamSynchronize(p->stream));
+    p->stream = stream ? static_cast<cudaStream_t>(stream) : p->own_stream;
+    return VG_OK;
+}
+
+int vg_problem_evaluate_async(vg_problem *p)
+{
+    if (!p) return fail(VG_ERR_INVALID, "null problem");
+    int rc = prepare(p);
+    if (rc) return rc;
+    VG_CUDA(cudaSetDevice(p->device));
+    rc = evaluate_set(p, p->cur, false);
+    if (rc) return rc;
+    if (p->allreduce && p->nranks > 1) {
+        const int Ks = p->Ks;
+        if (p->allreduce(p->allreduce_ctx, p->d_red, red_off_model(Ks), p->stream) != 0)
+            return fail(VG_ERR_CUDA, "all-reduce callback failed");
+    }
+    return VG_OK;
+}
+
+int vg_problem_fetch_reduced(vg_problem *p, double *cost, double *reduced)
+{
+    if (!p || !p->prepared) return fail(VG_ERR_INVALID, "nothing evaluated yet");
+    VG_CUDA(cudaSetDevice(p->device));
+    const int Ks = p->Ks, n = red_off_model(Ks);
+    VG_CUDA(cudaMemcpyAsync(p->h_red, p->d_red, sizeof(double) * n, cudaMemcpyDeviceToHost, p->stream));
+    VG_CUDA(cudaStreamSynchronize(p->stream));
+    if (cost) *cost = p->h_red[red_off_cost(Ks)];
+    if (reduced) memcpy(reduced, p->h_red, sizeof(double) * (Ks * Ks + Ks));
+    return VG_OK;
+}
+
+int vg_problem_device_buffer(vg_problem *p, int dataset, int which, void **ptr, size_t *bytes)
+{
+    if (!p || dataset < 0 || dataset >= (int)p->dss.size() || !ptr) return fail(VG_ERR_INVALID, "bad dataset");
+    int rc = prepare(p);
+    if (rc) return rc;
+    Ds &d = p->dss[dataset];
+    const size_t rows = (size_t)d.n_img * 2 * d.P;
+    void *q = nullptr; size_t b = 0;
+    if (which == -1) { q = d.d_obs; b = rows * 8; }
+    else if (which == -2) { q = d.d_H[p->cur]; b = (size_t)d.n_img * d.ne * 8; }
+    else if (which == 0) { q = d.d_r; b = rows * 8; }
+    else if (which == 1) { q = d.d_Ja; b = rows * p->cams[d.cam].K * 8; }
+    else if (which >= 2 && which < 2 + d.L) { q = d.d_Je[which - 2]; b = rows * 48; }
+    else return fail(VG_ERR_INVALID, "bad buffer selector");
+    *ptr = q;
+    if (bytes) *bytes = b;
+    return VG_OK;
+}
+
+int vg_problem_num_shared(vg_problem *p)
+{
+    if (!p) return fail(VG_ERR_INVALID, "null problem");
+    int rc = prepare(p);
+    return rc ? rc : p->Ks;
+}
+
+int vg_problem_get_camera(vg_problem *p, int camera, double *out)
+{
+    if (!p || !out || camera < 0 || camera >= (int)p->cams.size()) return fail(VG_ERR_INVALID, "bad camera");
+    memcpy(out, p->cams[camera].params, sizeof(double) * p->cams[camera].K);
+    return VG_OK;
+}
+
+int vg_problem_set_camera(vg_problem *p, int camera, const double *value)
+{
+    if (!p || !value || camera < 0 || camera >= (int)p->cams.size()) return fail(VG_ERR_INVALID, "bad camera");
+    memcpy(p->cams[camera].params, value, sizeof(double) * p->cams[camera].K);
+    if (p->prepared) {
+        VG_CUDA(cudaSetDevice(p->device));
+        // source is pageable memory owned by the handle: the runtime stages it before returning
+        VG_CUDA(cudaMemcpyAsync(p->cam_ptr(p->cur, camera), p->cams[camera].params, sizeof(double) * p->cams[camera].K,
+                                cudaMemcpyHostToDevice, p->stream));
+    }
+    return VG_OK;
+}
+
+int vg_problem_get_transform(vg_problem *p, int transform, double *out)
+{
+    if (!p || !out || transform < 0 || transform >= (int)p->trs.size()) return fail(VG_ERR_INVALID, "bad transform");
+    Tr &t = p->trs[transform];
+    if (!t.is_global && p->prepared) {
+        VG_CUDA(cudaSetDevice(p->device));
+        VG_CUDA(cudaMemcpyAsync(t.host.data(), t.dev[p->cur], sizeof(double) * 6 * t.n, cudaMemcpyDeviceToHost, p->stream));
+        VG_CUDA(cudaStreamSynchronize(p->stream));
+    }
+    memcpy(out, t.host.data(), sizeof(double) * 6 * t.n);
+    return VG_OK;
+}
+
+int vg_problem_set_transform(vg_problem *p, int transform, const double *values)
+{
+    if (!p || !values || transform < 0 || transform >= (int)p->trs.size()) return fail(VG_ERR_INVALID, "bad transform");
+    Tr &t = p->trs[transform];
+    const bool same = (values == t.host.data());
+    if (!same) memcpy(t.host.data(), values, sizeof(double) * 6 * t.n);
+    if (p->prepared) {
+        VG_CUDA(cudaSetDevice(p->device));
+        if (t.is_global)
+            VG_CUDA(cudaMemcpyAsync(p->glob_ptr(p->cur, t.glob_slot), values, 48, cudaMemcpyHostToDevice, p->stream));
+        else
+            VG_CUDA(cudaMemcpyAsync(t.dev[p->cur], values, sizeof(double) * 6 * t.n, cudaMemcpyHostToDevice, p->stream));
+        if (!same) VG_CUDA(cudaStreamSynchronize(p->stream));
+    }
+    return VG_OK;
+}
+
+int vg_problem_update_observations(vg_problem *p, int dataset, const double *obs)
+{
+    if (!p || !obs || dataset < 0 || dataset >= (int)p->dss.size()) return fail(VG_ERR_INVALID, "bad dataset");
+    Ds &d = p->dss[dataset];
+    VG_CUDA(cudaSetDevice(p->device));
+    VG_CUDA(cudaMemcpyAsync(d.d_obs, obs, sizeof(double) * 2 * (size_t)d.P * d.n_img, cudaMemcpyHostToDevice, p->stream));
+    return VG_OK;
+}
+
+int vg_problem_evaluate(vg_problem *p, double *cost, double *reduced)
+{
+    if (!p) return fail(VG_ERR_INVALID, "null problem");
+    int rc = prepare(p);
+    if (rc) return rc;
+    VG_CUDA(cudaSetDevice(p->device));
+    rc = evaluate_set(p, p->cur, false);
+    if (rc) return rc;
+    const int Ks = p->Ks;
+    rc = fetch_segment(p, 0, red_segE_size(Ks));
+    if (rc) return rc;
+    if (cost) *cost = p->h_red[red_off_cost(Ks)];
+    if (reduced) memcpy(reduced, p->h_red, sizeof(double) * (Ks * Ks + Ks));
+    return VG_OK;
+}
+
+int vg_problem_residuals(vg_problem *p, int dataset, double *r)
+{
+    if (!p || !r || dataset < 0 || dataset >= (int)p->dss.size()) return fail(VG_ERR_INVALID, "bad dataset");
+    int rc = prepare(p);
+    if (rc) return rc;
+    VG_CUDA(cudaSetDevice(p->device));
+    Ds &d = p->dss[dataset];
+    const size_t bytes = sizeof(double) * 2 * (size_t)d.P * (d.n_img ? d.n_img : 1);
+    double *dr = nullptr;
+    VG_CUDA(cudaMalloc(&dr, bytes));
+    EvalArgs a;
+    memset(&a, 0, sizeof a);
+    a.intr = p->cam_ptr(p->cur, d.cam);
+    a.board = d.d_board; a.obs = d.d_obs;
+    a.seq_index = d.identity_index ? nullptr : d.d_seq_index;
+    for (int e = 0; e < d.L; e++) {
+        const Tr &t = p->trs[d.tr[e]];
+        a.xi[e] = t.is_global ? p->glob_ptr(p->cur, t.glob_slot) : t.dev[p->cur];
+        a.xi_stride[e] = t.is_global ? 0 : 6;
+        a.inverse[e] = d.status[e] == VG_TRANSFORM_INVERSE;
+    }
+    a.r = dr; a.n_img = d.n_img; a.P = d.P;
+    cudaError_t e = launch_eval(p->cams[d.cam].model, d.L, a, p->stream, &launch_counter());
+    if (e == cudaSuccess && d.n_img) e = cudaMemcpyAsync(r, dr, sizeof(double) * 2 * (size_t)d.P * d.n_img, cudaMemcpyDeviceToHost, p->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+    cudaFree(dr);
+    if (e != cudaSuccess) return fail_cuda(e, "vg_problem_residuals");
+    return VG_OK;
+}
+
+int vg_problem_solve(vg_problem *p, const vg_solve_options *opt, vg_solve_summary *sum)
+{
+    if (!p || !sum) return fail(VG_ERR_INVALID, "null argument");
+    vg_solve_options o;
+    if (opt) o = *opt; else vg_solve_options_default(&o);
+    const double t_start = now_s();
+    int rc = prepare(p);
+    if (rc) return rc;
+    VG_CUDA(cudaSetDevice(p->device));
+    memset(sum, 0, sizeof *sum);
+    p->eval_ms = 0; p->n_eval = 0;
+    const int Ks = p->Ks, NP = p->n_pose;
+    const int segE = red_segE_size(Ks), offS = red_off_S(Ks), segS = red_segS_size(Ks, p->nranks);
+    SolverLaunch sl{p->stream, &launch_counter()};
+    std::vector<double> A(Ks * Ks), ga(Ks), S(Ks * Ks), rhs(Ks), da(Ks), scale_a(Ks, 1.0);
+    std::vector<double> cand_slab(p->slab_doubles);
+    const size_t glob0 = p->cams.size() * CAM_STRIDE;
+
+    auto collect_eval_time = [&]() {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, p->ev0, p->ev1) == cudaSuccess) p->eval_ms += ms;
+    };
+
+    // iteration 0: evaluate at the starting point
+    VG_CUDA(cudaMemsetAsync(p->d_red + red_off_model(Ks), 0, 3 * sizeof(double), p->stream));
+    rc = evaluate_set(p, p->cur, true);
+    if (rc) return rc;
+    rc = fetch_segment(p, 0, segE);
+    if (rc) return rc;
+    collect_eval_time();
+    double cost = p->h_red[red_off_cost(Ks)];
+    memcpy(A.data(), p->h_red + red_off_A(Ks), sizeof(double) * Ks * Ks);
+    memcpy(ga.data(), p->h_red + red_off_g(Ks), sizeof(double) * Ks);
+    sum->initial_cost = cost;
+    for (int j = 0; j < Ks; j++) scale_a[j] = o.jacobi_scaling ? 1.0 / (1.0 + std::sqrt(A[j * Ks + j])) : 1.0;
+
+    double radius = o.initial_radius, decrease_factor = 2.0;
+    int invalid_run = 0, iter = 0;
+    bool init_scale = true;
+    sum->termination = 3;
+
+    for (;;) {
+        // per-pose damped factorisation + Schur terms at the current radius (also max |g_pose|)
+        LmConsts lm{radius, o.min_lm_diagonal, o.max_lm_diagonal, init_scale ? 1 : 0, o.jacobi_scaling};
+        cudaError_t ce = launch_pose_schur(p->d_desc[p->cur], NP, Ks, p->d_pose_start, p->d_contrib_ds, p->d_contrib_img,
+                                           p->d_scale, lm, p->d_ws, p->d_partial, p->partial_doubles, p->d_red,
+                                           p->d_fail, p->rank, p->nranks, sl);
+        if (ce != cudaSuccess) return fail_cuda(ce, "pose_schur");
+        init_scale = false;
+        rc = fetch_segment(p, offS, segS);
+        if (rc) return rc;
+        // gradient tolerance: max-norm of the projected gradient
+        double gmax = 0;
+        for (int r = 0; r < p->nranks; r++) gmax = std::fmax(gmax, p->h_red[red_off_gmax(Ks) + r]);
+        for (const Cam &c : p->cams) {
+            if (c.shared_off < 0) continue;
+            for (int k = 0; k < c.K; k++) {
+                const double x = c.params[k], g = ga[c.shared_off + k];
+                gmax = std::fmax(gmax, std::fabs(x - clampd(x - g, c.lo[k], c.hi[k])));
+            }
+        }
+        for (const Tr &t : p->trs)
+            if (t.shared_off >= 0)
+                for (int k = 0; k < 6; k++) gmax = std::fmax(gmax, std::fabs(ga[t.shared_off + k]));
+        if (gmax <= o.gradient_tolerance) { sum->termination = 1; break; }
+        if (iter >= o.max_num_iterations) { sum->termination = 3; break; }
+        if (radius < o.min_radius) { sum->termination = 4; break; }
+        iter++;
+
+        bool ok = p->h_red[red_off_fail(Ks)] == 0.0;
+        // reduced system  (A + D_a - S_red) delta_a = -(g_a - v_red)
+        if (ok && Ks > 0) {
+            for (int i = 0; i < Ks * Ks; i++) S[i] = A[i] - p->h_red[offS + i];
+            for (int j = 0; j < Ks; j++) {
+                const double s2 = scale_a[j] * scale_a[j];
+                S[j * Ks + j] += clampd(s2 * A[j * Ks + j], o.min_lm_diagonal, o.max_lm_diagonal) / (radius * s2);
+                rhs[j] = -(ga[j] - p->h_red[red_off_v(Ks) + j]);
+            }
+            if (chol(S, Ks)) ok = false;
+            else { da = rhs; chol_solve(S, Ks, da.data()); }
+        }
+        double model_change = 0, step2 = 0, x2 = 0, new_cost = 0;
+        const int cand = p->cur ^ 1;
+        if (ok) {
+            // candidate shared parameters = Pi(x + delta_a), uploaded together with delta_a
+            fill_slab(p, cand_slab.data());
+            for (size_t ci = 0; ci < p->cams.size(); ci++) {
+                const Cam &c = p->cams[ci];
+                if (c.shared_off < 0) continue;
+                for (int k = 0; k < c.K; k++) {
+                    const double x = c.params[k];
+                    const double xn = clampd(x + da[c.shared_off + k], c.lo[k], c.hi[k]);
+                    x2 += x * x; step2 += (xn - x) * (xn - x);
+                    cand_slab[ci * CAM_STRIDE + k] = xn;
+                }
+            }
+            for (const Tr &t : p->trs) {
+                if (t.shared_off < 0) continue;
+                for (int k = 0; k < 6; k++) {
+                    const double x = t.host[k], dd = da[t.shared_off + k];
+                    x2 += x * x; step2 += dd * dd;
+                    cand_slab[glob0 + (size_t)t.glob_slot * 6 + k] = x + dd;
+                }
+            }
+            memcpy(p->h_up, cand_slab.data(), p->slab_doubles * sizeof(double));
+            if (Ks) memcpy(p->h_up + p->slab_doubles, da.data(), sizeof(double) * Ks);
+            VG_CUDA(cudaMemcpyAsync(p->d_slab[cand], p->h_up, p->slab_doubles * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+            if (Ks) VG_CUDA(cudaMemcpyAsync(p->d_delta, p->h_up + p->slab_doubles, sizeof(double) * Ks, cudaMemcpyHostToDevice, p->stream));
+            // candidate poses + model-decrease / norm partial sums, then the evaluation there
+            ce = launch_pose_backsub(NP, Ks, p->d_delta, p->d_seq_ptr[p->cur], p->d_seq_ptr[cand], p->d_pose_seq,
+                                     p->d_pose_local, p->d_ws, p->d_partial, p->partial_doubles, p->d_red, sl);
+            if (ce != cudaSuccess) return fail_cuda(ce, "pose_backsub");
+            rc = evaluate_set(p, cand, true);
+            if (rc) return rc;
+            rc = fetch_segment(p, 0, segE);
+            if (rc) return rc;
+            collect_eval_time();
+            new_cost = p->h_red[red_off_cost(Ks)];
+            double gd = 0, dHd = 0;
+            for (int s_ = 0; s_ < Ks; s_++) {
+                gd += ga[s_] * da[s_];
+                double t = 0;
+                for (int s2 = 0; s2 < Ks; s2++) t += A[s_ * Ks + s2] * da[s2];
+                dHd += da[s_] * t;
+            }
+            model_change = -(gd + 0.5 * dHd + p->h_red[red_off_model(Ks)]);
+            step2 += p->h_red[red_off_model(Ks) + 1];
+            x2 += p->h_red[red_off_model(Ks) + 2];
+            if (!(model_change > 0.0)) ok = false;
+        }
+        if (!ok) {
+            // invalid step (linear solve failed or the model predicts no decrease)
+            invalid_run++;
+            sum->num_unsuccessful++;
+            if (invalid_run >= o.max_consecutive_invalid) { sum->termination = 5; break; }
+            radius /= decrease_factor; decrease_factor *= 2.0;
+            continue;
+        }
+        invalid_run = 0;
+        if (std::sqrt(step2) <= o.parameter_tolerance * (std::sqrt(x2) + o.parameter_tolerance)) {
+            sum->termination = 2;   // candidate discarded, as Ceres stops before taking the step
+            break;
+        }
+        const double rho = (cost - new_cost) / model_change;
+        if (o.verbose)
+            printf("%4d  cost %.12e  new %.12e  rho %.3e  radius %.3e  |step| %.3e\n", iter, cost, new_cost, rho,
+                   radius, std::sqrt(step2));
+        if (rho > o.min_relative_decrease) {
+            const double cost_change = cost - new_cost, old_cost = cost;
+            p->cur = cand;
+            for (size_t ci = 0; ci < p->cams.size(); ci++)
+                memcpy(p->cams[ci].params, &cand_slab[ci * CAM_STRIDE], sizeof(double) * p->cams[ci].K);
+            for (Tr &t : p->trs)
+                if (t.is_global) memcpy(t.host.data(), &cand_slab[glob0 + (size_t)t.glob_slot * 6], 48);
+            memcpy(A.data(), p->h_red + red_off_A(Ks), sizeof(double) * Ks * Ks);
+            memcpy(ga.data(), p->h_red + red_off_g(Ks), sizeof(double) * Ks);
+            cost = new_cost;
+            sum->num_successful++;
+            radius = radius / std::fmax(1.0 / 3.0, 1.0 - std::pow(2.0 * rho - 1.0, 3.0));
+            if (radius > o.max_radius) radius = o.max_radius;
+            decrease_factor = 2.0;
+            if (std::fabs(cost_change) <= o.function_tolerance * old_cost) { sum->termination = 0; break; }
+        } else {
+            sum->num_unsuccessful++;
+            radius /= decrease_factor; decrease_factor *= 2.0;
+        }
+    }
+    // the non-current set keeps stale candidates: bring the shared slab of both sets in line
+    fill_slab(p, p->h_slab.data());
+    for (int s_ = 0; s_ < 2; s_++)
+        VG_CUDA(cudaMemcpyAsync(p->d_slab[s_], p->h_slab.data(), p->slab_doubles * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    for (Tr &t : p->trs)
+        if (!t.is_global)
+            VG_CUDA(cudaMemcpyAsync(t.host.data(), t.dev[p->cur], sizeof(double) * 6 * t.n, cudaMemcpyDeviceToHost, p->stream));
+    VG_CUDA(cudaStreamSynchronize(p->stream));
+    sum->iterations = iter;
+    sum->final_cost = cost;
+    sum->seconds_total = now_s() - t_start;
+    sum->seconds_evaluate = p->eval_ms * 1e-3;
+    sum->num_evaluations = p->n_eval;
+    return VG_OK;
+}
+
+}  // extern "C"

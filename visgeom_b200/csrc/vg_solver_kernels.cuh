@@ -48,21 +48,25 @@ struct LmConsts {
 // per pose, so the scratch is pose-major: [L (21) | lambda (6) | z (6) | Z (6 x Ks)]
 __host__ __device__ inline int pose_ws_stride(int Ks) { return 21 + 6 + 6 + 6 * Ks; }
 
-// Reduction buffer layout (doubles), all sums over the local images / poses:
-//   [0, Ks*Ks)            A        (row-major, symmetric)
-//   [Ks*Ks, +Ks)          g_a
-//   +0                    cost  (1/2 sum r^2)
-//   +1                    max |g_pose|  (max-reduced, not summed)
-//   then Ks*Ks + Ks       S_red, v_red
-//   then 3                model partial (sum m_p), step^2, x^2 over poses
+// Reduction buffer layout (doubles); every entry is a sum over the local images /
+// poses, laid out as the two segments that are exchanged across GPUs:
+//   segment E (fresh after every evaluation + back-substitution):
+//     A (Ks*Ks, row-major symmetric) | g_a (Ks) | cost (1/2 sum r^2) | model partial,
+//     step^2, x^2 over poses (3)
+//   segment S (fresh after every pose_schur):
+//     S_red (Ks*Ks) | v_red (Ks) | failed factorisations (count) | max |g_pose|, one
+//     slot per rank (only the own slot is non-zero, so a SUM all-reduce gathers them)
 __host__ __device__ inline int red_off_A(int) { return 0; }
 __host__ __device__ inline int red_off_g(int Ks) { return Ks * Ks; }
 __host__ __device__ inline int red_off_cost(int Ks) { return Ks * Ks + Ks; }
-__host__ __device__ inline int red_off_gmax(int Ks) { return Ks * Ks + Ks + 1; }
-__host__ __device__ inline int red_off_S(int Ks) { return Ks * Ks + Ks + 2; }
-__host__ __device__ inline int red_off_v(int Ks) { return 2 * Ks * Ks + Ks + 2; }
-__host__ __device__ inline int red_off_model(int Ks) { return 2 * Ks * Ks + 2 * Ks + 2; }
-__host__ __device__ inline int red_size(int Ks) { return 2 * Ks * Ks + 2 * Ks + 5; }
+__host__ __device__ inline int red_off_model(int Ks) { return Ks * Ks + Ks + 1; }
+__host__ __device__ inline int red_segE_size(int Ks) { return Ks * Ks + Ks + 4; }
+__host__ __device__ inline int red_off_S(int Ks) { return red_segE_size(Ks); }
+__host__ __device__ inline int red_off_v(int Ks) { return red_off_S(Ks) + Ks * Ks; }
+__host__ __device__ inline int red_off_fail(int Ks) { return red_off_v(Ks) + Ks; }
+__host__ __device__ inline int red_off_gmax(int Ks) { return red_off_fail(Ks) + 1; }
+__host__ __device__ inline int red_segS_size(int Ks, int nranks) { return Ks * Ks + Ks + 1 + nranks; }
+__host__ __device__ inline int red_size(int Ks, int nranks) { return red_segE_size(Ks) + red_segS_size(Ks, nranks); }
 
 struct SolverLaunch {
     cudaStream_t stream;
@@ -70,14 +74,18 @@ struct SolverLaunch {
 };
 
 // A, g_a, cost of all datasets -> red[A..cost]; partial is scratch of >= blocks*MAX_NE doubles
-cudaError_t launch_accumulate_shared(const DatasetDesc *d_desc, const DatasetDesc *h_desc, int n_ds, int Ks,
-                                     double *partial, size_t partial_doubles, double *red, SolverLaunch sl);
+void accumulate_shared_table(const DatasetDesc *h_desc, int n_ds, int *h_tab /* 2*n_ds ints */);
+cudaError_t launch_accumulate_shared(const DatasetDesc *d_desc, int n_ds, int Ks, double *partial,
+                                     const int *h_tab, const int *d_tab, double *red, SolverLaunch sl);
 
 // per-pose factorisation + Schur terms -> ws, red[S,v], red[gmax]
 cudaError_t launch_pose_schur(const DatasetDesc *d_desc, int n_pose, int Ks,
                               const int *pose_start, const int *contrib_ds, const int *contrib_img,
                               double *scale, LmConsts lm, double *ws, double *partial, size_t partial_doubles,
-                              double *red, SolverLaunch sl);
+                              double *red, int *fail_flag, int rank, int nranks, SolverLaunch sl);
+
+size_t accumulate_shared_scratch(const DatasetDesc *h_desc, int n_ds);   // doubles
+size_t pose_scratch(int n_pose, int Ks);                                 // doubles
 
 // candidate poses and model / norm partial sums -> red[model..]
 // pose_ptr_cur/cand: per pose-list entry the device address of its 6 doubles is
