@@ -1,0 +1,123 @@
+// ref_entry.cpp -- C entry points around the REFERENCE's own hot-path classes (TEST
+// INFRASTRUCTURE ONLY).  Compiled by `make -C oracle ref` together with
+// $(REFERENCE)/src/calibration/calib_cost_functions.cpp against oracle/shim; the output
+// oracle/_ref/libvisgeom_ref.so is git-ignored.  It drives GenericProjectionJac::Evaluate
+// (calib_cost_functions.cpp:28-117) exactly as Ceres does: one functor per image, Evaluate
+// with all Jacobian blocks requested.  No reference source is copied into this repository.
+#include "calibration/calib_cost_functions.h"
+#include "projection/eucm.h"
+#include "projection/ucm.h"
+#include "projection/mei.h"
+
+#include <cstring>
+#include <memory>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+static ICamera *make_camera(int model, const double *intr)
+{
+    switch (model) {
+    case 0: return new EnhancedCamera(intr);   // unified_calibration.cpp:153
+    case 1: return new UnifiedCamera(intr);    // :162
+    case 2: return new MeiCamera(intr);        // :171
+    default: return NULL;
+    }
+}
+
+extern "C" {
+
+int vgref_num_params(int model) { return model == 0 ? 6 : (model == 1 ? 5 : (model == 2 ? 10 : -1)); }
+
+int vgref_evaluate_batch(int model, const double *intr, int n_img, int P,
+                         const double *board, const double *obs,
+                         int chain_len, const int *status, const int *is_global,
+                         const double *const *xi,
+                         double *r, double *J_intr, double *const *J_xi, double *H, int threads)
+{
+    const int K = vgref_num_params(model);
+    if (K < 0 || chain_len < 1 || chain_len > 5) return -1;
+    const int L = chain_len, D = K + 6 * L, W = D + 1, ne = W * (W + 1) / 2;
+    Vector3dVec grid;
+    for (int i = 0; i < P; i++) grid.emplace_back(board[3 * i], board[3 * i + 1], board[3 * i + 2]);
+    vector<TransformationStatus> statusVec;
+    for (int e = 0; e < L; e++) statusVec.push_back(status[e] ? TRANSFORM_INVERSE : TRANSFORM_DIRECT);
+    std::unique_ptr<ICamera> cam(make_camera(model, intr));
+    (void)threads;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(threads > 1 ? threads : 1)
+#endif
+    for (int img = 0; img < n_img; img++) {
+        Vector2dVec proj;
+        for (int i = 0; i < P; i++) proj.emplace_back(obs[((size_t)img * P + i) * 2], obs[((size_t)img * P + i) * 2 + 1]);
+        // one cost function per image, as addGridResidualBlocks does (unified_calibration.cpp:532-533)
+        GenericProjectionJac cost(proj, grid, cam.get(), statusVec);
+        const double *params[6];
+        double *jac[6];
+        std::vector<double> scratch;
+        size_t need = (r ? 0 : (size_t)2 * P) + (J_intr ? 0 : (size_t)2 * P * K);
+        for (int e = 0; e < L; e++) need += (J_xi && J_xi[e]) ? 0 : (size_t)2 * P * 6;
+        scratch.resize(need + 1);
+        double *sp = scratch.data();
+        params[0] = intr;
+        double *rr = r ? r + (size_t)img * 2 * P : sp; if (!r) sp += (size_t)2 * P;
+        jac[0] = J_intr ? J_intr + (size_t)img * 2 * P * K : sp; if (!J_intr) sp += (size_t)2 * P * K;
+        for (int e = 0; e < L; e++) {
+            params[1 + e] = xi[e] + (is_global[e] ? 0 : (size_t)img * 6);
+            if (J_xi && J_xi[e]) jac[1 + e] = J_xi[e] + (size_t)img * 2 * P * 6;
+            else { jac[1 + e] = sp; sp += (size_t)2 * P * 6; }
+        }
+        cost.Evaluate(params, rr, jac);
+        if (H) {
+            // the J^T J / J^T r product Ceres forms from the block (not reference code)
+            double *h = H + (size_t)img * ne;
+            for (int i = 0; i < ne; i++) h[i] = 0.0;
+            double row[64];
+            for (int k = 0; k < 2 * P; k++) {
+                for (int c = 0; c < K; c++) row[c] = jac[0][(size_t)k * K + c];
+                for (int e = 0; e < L; e++)
+                    for (int c = 0; c < 6; c++) row[K + 6 * e + c] = jac[1 + e][(size_t)k * 6 + c];
+                row[D] = rr[k];
+                int idx = 0;
+                for (int a = 0; a < W; a++)
+                    for (int b = a; b < W; b++) h[idx++] += row[a] * row[b];
+            }
+        }
+    }
+    return 0;
+}
+
+// single-function probes used to pin the oracle's geometry / camera restatement
+void vgref_rotation_matrix(const double *v, double *R)
+{
+    Matrix3d M = rotationMatrix<double>(Vector3d(v[0], v[1], v[2]));
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) R[3 * i + j] = M(i, j);
+}
+void vgref_inter_omega_rot(const double *v, double *R)
+{
+    Matrix3d M = interOmegaRot<double>(Vector3d(v[0], v[1], v[2]));
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) R[3 * i + j] = M(i, j);
+}
+void vgref_compose(const double *a, const double *b, double *out, int kind)
+{
+    Transformation<double> A(a), B(b), Cc;
+    if (kind == 0) Cc = A.compose(B);
+    else if (kind == 1) Cc = A.composeInverse(B);
+    else Cc = A.inverseCompose(B);
+    Cc.toArray(out);
+}
+int vgref_reconstruct(int model, const double *intr, const double *uv, double *X)
+{
+    std::unique_ptr<ICamera> cam(make_camera(model, intr));
+    Vector3d Xv;
+    bool ok = cam->reconstructPoint(Vector2d(uv[0], uv[1]), Xv);
+    X[0] = Xv(0); X[1] = Xv(1); X[2] = Xv(2);
+    return ok ? 1 : 0;
+}
+double vgref_bound(int model, const double *intr, int idx, int upper)
+{
+    std::unique_ptr<ICamera> cam(make_camera(model, intr));
+    return upper ? cam->upperBound(idx) : cam->lowerBound(idx);
+}
+
+}  // extern "C"

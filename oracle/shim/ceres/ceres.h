@@ -1,0 +1,43 @@
+// Stand-in for the few Ceres declarations visgeom's include/ceres.h and
+// include/calibration/calib_cost_functions.h name.  TEST INFRASTRUCTURE ONLY (see oracle/shim/Eigen/Eigen).
+// Only the CostFunction interface is functional: the LM solver itself is restated in oracle/oracle_lm.c.
+#ifndef VISGEOM_ORACLE_CERES_SHIM
+#define VISGEOM_ORACLE_CERES_SHIM
+#include <vector>
+namespace ceres {
+class CostFunction {
+public:
+    CostFunction() : num_residuals_(0) {}
+    virtual ~CostFunction() {}
+    virtual bool Evaluate(double const *const *parameters, double *residuals, double **jacobians) const = 0;
+    const std::vector<int> &parameter_block_sizes() const { return parameter_block_sizes_; }
+    int num_residuals() const { return num_residuals_; }
+protected:
+    std::vector<int> *mutable_parameter_block_sizes() { return &parameter_block_sizes_; }
+    void set_num_residuals(int n) { num_residuals_ = n; }
+private:
+    std::vector<int> parameter_block_sizes_;
+    int num_residuals_;
+};
+template <int kNumResiduals, int... Ns> class SizedCostFunction : public CostFunction {
+public:
+    SizedCostFunction()
+    {
+        set_num_residuals(kNumResiduals);
+        const int sizes[] = {Ns...};
+        for (int s : sizes) mutable_parameter_block_sizes()->push_back(s);
+    }
+};
+template <typename F, int S = 4> class DynamicAutoDiffCostFunction;
+class FirstOrderFunction;
+class LossFunction { public: virtual ~LossFunction() {} };
+class SoftLOneLoss;
+class CauchyLoss;
+class Problem;
+class Solver;
+class GradientProblem;
+class GradientProblemSolver;
+template <typename G> class BiCubicInterpolator;
+void Solve();
+}  // namespace ceres
+#endif

@@ -1,0 +1,110 @@
+"""Generate the committed golden vectors from the REFERENCE's own code.
+
+Run in the authoring container only (needs /root/reference):
+    python tests/golden/make_golden.py
+It builds oracle/_ref (the reference's headers + calib_cost_functions.cpp compiled where they lie
+against the stand-in Eigen/Ceres headers of oracle/shim -- Eigen and Ceres themselves are not
+installed) and records inputs and GenericProjectionJac::Evaluate outputs
+(calib_cost_functions.cpp:28-117) for a set of small cases, plus single-function probes of
+rotationMatrix / interOmegaRot / Transformation::compose* / reconstructPoint / bounds.
+The reference cannot travel to the GPU box, these fixtures can."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+import synthdata as sd  # noqa: E402
+from oracle.pyoracle import Oracle, Reference, c_dp  # noqa: E402
+
+D, I = 0, 1
+
+
+def dp(a):
+    return a.ctypes.data_as(c_dp)
+
+
+def cases(oracle):
+    out = {}
+    for model, name in ((sd.EUCM, "eucm"), (sd.UCM, "ucm"), (sd.MEI, "mei")):
+        d = sd.make_mono(model, 4, seed=900 + model)
+        out[f"mono_{name}_gt"] = (model, d["intr_gt"], d["board"], d["obs"], [d["xi_gt"]], [D], [0])
+        out[f"mono_{name}_init"] = (model, d["intr_init"], d["board"], d["obs"], [d["xi_init"]], [D], [0])
+    s = sd.make_stereo(4, seed=910)
+    out["stereo_cam2"] = (sd.EUCM, s["intr2_init"], s["board"], s["obs2"], [s["xi12_init"], s["xi_init"]], [I, D], [1, 0])
+    # longer mixed chains (built like tests/test_eval_gpu.py::make_chain)
+    sys.path.insert(0, os.path.dirname(HERE))
+    from test_eval_gpu import make_chain
+    for model, name in ((sd.EUCM, "eucm"), (sd.MEI, "mei")):
+        d = sd.make_mono(model, 3, seed=920 + model)
+        for status, glob in (([D, I, D], [1, 1, 0]), ([I, D, I, D, D], [1, 0, 1, 1, 1])):
+            xis = make_chain(oracle, d["xi_gt"], status, glob, seed=5)
+            out[f"chain{len(status)}_{name}"] = (model, d["intr_gt"], d["board"], d["obs"], xis, status, glob)
+    # failed projections: eta < 1e-3 and the alpha > 0.5 hemisphere test (eucm.h:46-54)
+    d = sd.make_mono(sd.EUCM, 4, seed=930)
+    xi = d["xi_gt"].copy(); xi[0, 2] -= 3.0; xi[1, 2] = -0.01
+    out["sentinel_eucm"] = (sd.EUCM, d["intr_gt"], d["board"], d["obs"], [xi], [D], [0])
+    intr = d["intr_gt"].copy(); intr[0] = 0.4
+    out["sentinel_eucm_alpha04"] = (sd.EUCM, intr, d["board"], d["obs"], [xi], [D], [0])
+    # small-angle branches (geometry_core.h:44,162; quaternion.h:34,88)
+    xi = d["xi_gt"].copy(); xi[:, 3:] = 0; xi[:, :3] = [-0.4, -0.25, 0.8]
+    xi[1, 3:] = [3e-6, -2e-6, 1e-6]; xi[2, 3:] = [9.9e-6, 0, 0]; xi[3, 3:] = [1.01e-5, 0, 0]
+    out["small_angles"] = (sd.EUCM, d["intr_gt"], d["board"], d["obs"], [xi], [D], [0])
+    # a 2x2 "IR" grid with z != 0 points (unified_calibration.cpp:234-250)
+    d4 = sd.make_mono(sd.UCM, 3, seed=940, nx=2, ny=2, size=0.3)
+    b = d4["board"].copy(); b[:, 2] = [0.0, 0.02, -0.01, 0.03]
+    out["ir_grid_ucm"] = (sd.UCM, d4["intr_init"], b, d4["obs"], [d4["xi_init"]], [D], [0])
+    return out
+
+
+def main():
+    ref, orc = Reference(), Oracle()
+    lib = ref.lib
+    blob = {}
+    for name, (model, intr, board, obs, xis, status, glob) in cases(orc).items():
+        o = ref.evaluate_batch(model, intr, board, obs, xis, status, glob, want_H=True)
+        blob[f"{name}/model"] = np.array(model)
+        blob[f"{name}/intr"] = intr; blob[f"{name}/board"] = board; blob[f"{name}/obs"] = obs
+        blob[f"{name}/status"] = np.array(status); blob[f"{name}/is_global"] = np.array(glob)
+        for e, x in enumerate(xis):
+            blob[f"{name}/xi{e}"] = np.asarray(x)
+        blob[f"{name}/r"] = o["r"]; blob[f"{name}/J_intr"] = o["J_intr"]; blob[f"{name}/H"] = o["H"]
+        for e, j in enumerate(o["J_xi"]):
+            blob[f"{name}/J_xi{e}"] = j
+    # single-function probes
+    u = sd.uniform(77, 1, 3 * 12).reshape(12, 3) * 2 - 1
+    vecs = np.concatenate([u * 2.5, u[:4] * 1e-6, np.zeros((1, 3)), [[3.1, 0.2, -0.1]], [[1e-5, 0, 0]]])
+    R = np.zeros((len(vecs), 9)); B = np.zeros((len(vecs), 9))
+    for i, v in enumerate(vecs):
+        v = np.ascontiguousarray(v)
+        lib.vgref_rotation_matrix(dp(v), dp(R[i])); lib.vgref_inter_omega_rot(dp(v), dp(B[i]))
+    blob["probe/rotvec"] = vecs; blob["probe/rotation_matrix"] = R; blob["probe/inter_omega_rot"] = B
+    ta = np.concatenate([u[:6] * 0.5, u[6:12] * 2.0], axis=1)       # 6 transforms [t, r]
+    tb = np.concatenate([u[6:12] * 0.3, u[:6] * 1.5], axis=1)
+    comp = np.zeros((3, 6, 6))
+    for k in range(3):
+        for i in range(6):
+            a, b = np.ascontiguousarray(ta[i]), np.ascontiguousarray(tb[i])
+            lib.vgref_compose(dp(a), dp(b), dp(comp[k, i]), k)
+    blob["probe/ta"] = ta; blob["probe/tb"] = tb; blob["probe/compose"] = comp
+    lib.vgref_bound.restype = C.c_double
+    for model, intr, name in ((sd.EUCM, sd.EUCM_GT_LEFT, "eucm"), (sd.UCM, sd.UCM_GT, "ucm"), (sd.MEI, sd.MEI_GT, "mei")):
+        intr = np.ascontiguousarray(intr)
+        K = len(intr)
+        blob[f"probe/bounds_{name}"] = np.array([[lib.vgref_bound(model, dp(intr), i, 0), lib.vgref_bound(model, dp(intr), i, 1)]
+                                                 for i in range(K)])
+        uv = np.array([[700.0, 420.0], [100.0, 90.0], [1200.0, 750.0], [640.0, 400.0]])
+        X = np.zeros((len(uv), 3)); ok = np.zeros(len(uv))
+        for i in range(len(uv)):
+            p = np.ascontiguousarray(uv[i])
+            ok[i] = lib.vgref_reconstruct(model, dp(intr), dp(p), dp(X[i]))
+        blob[f"probe/reconstruct_{name}_uv"] = uv; blob[f"probe/reconstruct_{name}_X"] = X; blob[f"probe/reconstruct_{name}_ok"] = ok
+    path = os.path.join(HERE, "reference_vectors.npz")
+    np.savez_compressed(path, **blob)
+    print(f"wrote {path}: {len(blob)} arrays, {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    main()
