@@ -14,8 +14,9 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvisgeom_b200.so")
 OBJ = os.path.join(HERE, "_obj")
 
-SOURCES = ["vg_eval.cu", "vg_api.cu", "vg_solver_kernels.cu", "vg_problem.cu"]
-HEADERS = ["vg_math.cuh", "vg_eval.cuh", "vg_common.h", "vg_solver_kernels.cuh", "../../include/visgeom_b200.h"]
+SOURCES = ["vg_eval_eucm.cu", "vg_eval_ucm.cu", "vg_eval_mei.cu", "vg_eval.cu", "vg_api.cu", "vg_solver_kernels.cu",
+           "vg_problem.cu"]
+HEADERS = ["vg_math.cuh", "vg_eval.cuh", "vg_eval_impl.cuh", "vg_common.h", "vg_solver_kernels.cuh", "../../include/visgeom_b200.h"]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -59,6 +59,30 @@ __device__ __forceinline__ void rodrigues_and_left_jacobian(const double r0, con
     Jl[6] = k2 * u02 - k1 * u1; Jl[7] = k2 * u12 + k1 * u0;  Jl[8] = 1.0 + k2 * u22;
 }
 
+// Reciprocal / reciprocal square root for the per-corner path: hardware seed (MUFU.RCP64H /
+// MUFU.RSQ64H, ~2^-22) refined by two Newton steps in fp64 -> <= 1-2 ulp.  No denormal /
+// infinity slow paths: the operands here (eta, rho^2 of a point in front of the camera) are
+// ordinary numbers, and results for rejected points are discarded.
+__device__ __forceinline__ double fast_rcp(const double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+
+__device__ __forceinline__ double fast_rsqrt(const double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x * y, y, 1.0);                 // 1 - x y^2
+    y = fma(y * fma(0.375, e, 0.5), e, y);          // third-order step
+    e = fma(-x * y, y, 1.0);
+    return fma(0.5 * y, e, y);
+}
+
 __device__ __forceinline__ void mat3_mul(const double (&A)[9], const double (&B)[9], double (&C)[9])
 {
 #pragma unroll
@@ -90,29 +114,36 @@ template <int MODEL> struct Camera;
 
 template <> struct Camera<MODEL_EUCM> {
     static constexpr int K = 6;
-    __device__ __forceinline__ static bool eval(const double (&p)[K], const double x, const double y, const double z,
-                                                double &u, double &v, double (&Pu)[3], double (&Pv)[3],
+    struct Consts { double gamma, ab, hemi; bool hemi_test; };
+    __device__ __forceinline__ static Consts prepare(const double (&p)[K])
+    {
+        Consts c;
+        c.gamma = 1.0 - p[0];
+        c.ab = p[0] * p[1];
+        c.hemi_test = p[0] > 0.5;                                  // eucm.h:49
+        c.hemi = (p[0] - 1.0) / (p[0] + p[0] - 1.0);               // eucm.h:52
+        return c;
+    }
+    __device__ __forceinline__ static bool eval(const double (&p)[K], const Consts &cc, const double x, const double y,
+                                                const double z, double &u, double &v, double (&Pu)[3], double (&Pv)[3],
                                                 double (&Ju)[K], double (&Jv)[K])
     {
         const double alpha = p[0], beta = p[1], fu = p[2], fv = p[3], u0 = p[4], v0 = p[5];
-        const double gamma = 1.0 - alpha;
+        const double gamma = cc.gamma;
         const double x2y2 = fma(x, x, y * y);
         const double rho2 = fma(beta, x2y2, z * z);
-        const double rho = sqrt(rho2);
+        const double ir = fast_rsqrt(rho2);
+        const double rho = rho2 * ir;
         const double eta = fma(alpha, rho, gamma * z);
         bool ok = !(eta < 1e-3);                                   // eucm.h:46
-        const double ie = 1.0 / eta;
-        if (alpha > 0.5) {                                         // eucm.h:49-54
-            const double C = (alpha - 1.0) / (alpha + alpha - 1.0);
-            if (z * ie < C) ok = false;
-        }
-        const double ir = 1.0 / rho;
+        const double ie = fast_rcp(eta);
+        if (cc.hemi_test && z * ie < cc.hemi) ok = false;          // eucm.h:49-54
         const double xn = x * ie, yn = y * ie;
         u = fma(fu, xn, u0);
         v = fma(fv, yn, v0);
         // dP/dX (eucm.h:152-163)
         const double k = ie * ie;
-        const double ab = alpha * beta * ir;
+        const double ab = cc.ab * ir;
         const double fuk = fu * k, fvk = fv * k;
         const double jxy = ab * x * y;
         const double jz = fma(alpha * z, ir, gamma);
@@ -146,10 +177,11 @@ __device__ __forceinline__ void unified_normalise(const double xi, const double 
                                                   double &xn, double &yn, double &rho, double &d,
                                                   double (&mx)[3], double (&my)[3])
 {
-    rho = sqrt(fma(x, x, fma(y, y, z * z)));
-    const double ir = 1.0 / rho;
+    const double rho2 = fma(x, x, fma(y, y, z * z));
+    const double ir = fast_rsqrt(rho2);
+    rho = rho2 * ir;
     const double den = fma(xi, rho, z);
-    d = 1.0 / den;
+    d = fast_rcp(den);
     const double d2 = d * d;
     xn = x * d;
     yn = y * d;
@@ -166,7 +198,9 @@ __device__ __forceinline__ void unified_normalise(const double xi, const double 
 
 template <> struct Camera<MODEL_UCM> {
     static constexpr int K = 5;
-    __device__ __forceinline__ static bool eval(const double (&p)[K], const double x, const double y, const double z,
+    struct Consts {};
+    __device__ __forceinline__ static Consts prepare(const double (&)[K]) { return Consts(); }
+    __device__ __forceinline__ static bool eval(const double (&p)[K], const Consts &, const double x, const double y, const double z,
                                                 double &u, double &v, double (&Pu)[3], double (&Pv)[3],
                                                 double (&Ju)[K], double (&Jv)[K])
     {
@@ -186,7 +220,9 @@ template <> struct Camera<MODEL_UCM> {
 
 template <> struct Camera<MODEL_MEI> {
     static constexpr int K = 10;
-    __device__ __forceinline__ static bool eval(const double (&p)[K], const double x, const double y, const double z,
+    struct Consts {};
+    __device__ __forceinline__ static Consts prepare(const double (&)[K]) { return Consts(); }
+    __device__ __forceinline__ static bool eval(const double (&p)[K], const Consts &, const double x, const double y, const double z,
                                                 double &u, double &v, double (&Pu)[3], double (&Pv)[3],
                                                 double (&Ju)[K], double (&Jv)[K])
     {

@@ -115,7 +115,8 @@ struct vg_problem {
     std::vector<int> h_acc_tab;
     double **d_seq_ptr[2] = {nullptr, nullptr};
     double *d_scale = nullptr, *d_ws = nullptr, *d_partial = nullptr, *d_red = nullptr, *d_delta = nullptr;
-    size_t partial_doubles = 0;
+    double *d_cta_partial = nullptr;
+    size_t partial_doubles = 0, cta_partial_doubles = 0;
     double *h_red = nullptr;                  // pinned
     double *h_up = nullptr;                   // pinned upload staging: [slab | delta_a]
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -133,7 +134,7 @@ void free_prepared(vg_problem *p)
     auto F = [](auto *&ptr) { if (ptr) { cudaFree(ptr); ptr = nullptr; } };
     for (int s = 0; s < 2; s++) { F(p->d_slab[s]); F(p->d_desc[s]); F(p->d_seq_ptr[s]); }
     F(p->d_pose_start); F(p->d_contrib_ds); F(p->d_contrib_img); F(p->d_pose_seq); F(p->d_pose_local);
-    F(p->d_fail); F(p->d_acc_tab); F(p->d_scale); F(p->d_ws); F(p->d_partial); F(p->d_red); F(p->d_delta);
+    F(p->d_fail); F(p->d_acc_tab); F(p->d_cta_partial); F(p->d_scale); F(p->d_ws); F(p->d_partial); F(p->d_red); F(p->d_delta);
     if (p->h_red) { cudaFreeHost(p->h_red); p->h_red = nullptr; }
     if (p->h_up) { cudaFreeHost(p->h_up); p->h_up = nullptr; }
     for (auto &d : p->dss)
@@ -243,17 +244,19 @@ int prepare(vg_problem *p)
         if (!seq_ptr[s].empty())
             VG_CUDA(cudaMemcpy(p->d_seq_ptr[s], seq_ptr[s].data(), sizeof(double *) * seq_ptr[s].size(), cudaMemcpyHostToDevice));
     }
+    std::vector<int> grids(p->dss.size() + 1, 0);
+    for (size_t k = 0; k < p->dss.size(); k++)
+        VG_CUDA(eval_grid_size(p->cams[p->dss[k].cam].model, p->dss[k].L, p->dss[k].n_img, p->dss[k].P, &grids[k]));
     p->h_acc_tab.assign(2 * p->dss.size() + 2, 0);
-    accumulate_shared_table(p->h_desc[0].data(), (int)p->dss.size(), p->h_acc_tab.data());
+    shared_partial_table(p->h_desc[0].data(), grids.data(), (int)p->dss.size(), p->h_acc_tab.data());
     VG_CUDA(upload_i(p->d_acc_tab, p->h_acc_tab));
+    p->cta_partial_doubles = shared_partial_doubles(p->h_desc[0].data(), grids.data(), (int)p->dss.size());
+    VG_CUDA(cudaMalloc(&p->d_cta_partial, sizeof(double) * p->cta_partial_doubles));
     VG_CUDA(cudaMalloc(&p->d_fail, sizeof(int)));
     VG_CUDA(cudaMemset(p->d_fail, 0, sizeof(int)));
     VG_CUDA(cudaMalloc(&p->d_scale, sizeof(double) * 6 * (size_t)(NP ? NP : 1)));
     VG_CUDA(cudaMalloc(&p->d_ws, sizeof(double) * (size_t)pose_ws_stride(Ks) * (NP ? NP : 1)));
-    size_t pd = accumulate_shared_scratch(p->h_desc[0].data(), (int)p->dss.size());
-    const size_t pd2 = pose_scratch(NP, Ks);
-    if (pd2 > pd) pd = pd2;
-    p->partial_doubles = pd + 64;
+    p->partial_doubles = pose_scratch(NP, Ks) + 64;
     VG_CUDA(cudaMalloc(&p->d_partial, sizeof(double) * p->partial_doubles));
     const int rs = red_size(Ks, p->nranks);
     VG_CUDA(cudaMalloc(&p->d_red, sizeof(double) * rs));
@@ -294,15 +297,16 @@ int evaluate_set(vg_problem *p, int s, bool timed)
         a.r = p->materialize ? d.d_r : nullptr;
         a.Ja = p->materialize ? d.d_Ja : nullptr;
         a.H = d.d_H[s];
+        a.cta_partial = p->d_cta_partial + p->h_acc_tab[&d - p->dss.data()];
         a.n_img = d.n_img; a.P = d.P;
         cudaError_t e = launch_eval(p->cams[d.cam].model, d.L, a, p->stream, &launch_counter());
         if (e != cudaSuccess) return fail_cuda(e, "reproj_eval_kernel launch");
     }
     if (timed) VG_CUDA(cudaEventRecord(p->ev1, p->stream));
     SolverLaunch sl{p->stream, &launch_counter()};
-    cudaError_t e = launch_accumulate_shared(p->d_desc[s], (int)p->dss.size(), p->Ks, p->d_partial,
-                                             p->h_acc_tab.data(), p->d_acc_tab, p->d_red, sl);
-    if (e != cudaSuccess) return fail_cuda(e, "accumulate_shared");
+    cudaError_t e = launch_finalize_shared(p->d_desc[s], (int)p->dss.size(), p->Ks, p->d_cta_partial, p->d_acc_tab,
+                                           p->d_red, sl);
+    if (e != cudaSuccess) return fail_cuda(e, "finalize_shared");
     p->n_eval++;
     return VG_OK;
 }

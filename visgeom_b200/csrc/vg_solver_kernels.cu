@@ -11,25 +11,11 @@ __host__ __device__ inline int pk(int a, int b, int W) { return a * W - a * (a -
 __device__ __forceinline__ int pks(int a, int b, int W) { return a <= b ? pk(a, b, W) : pk(b, a, W); }
 
 constexpr int ACC_THREADS = 256;
-constexpr int ACC_IMGS = 128;        // images per block in accumulate_shared
 constexpr int POSE_THREADS = 128;
 constexpr int GRAM_POSES = 64;       // poses per block in gram_reduce
 constexpr int GRAM_THREADS = 224;    // >= Ks(Ks+1)/2 + Ks for Ks <= 18; larger Ks loops
 
-// ---- A, g_a, cost ---------------------------------------------------------------------
-__global__ void __launch_bounds__(ACC_THREADS)
-acc_shared_kernel(const DatasetDesc *desc_all, int ds, double *partial)
-{
-    const DatasetDesc &d = desc_all[ds];
-    const int i0 = blockIdx.x * ACC_IMGS;
-    const int i1 = min(d.n_img, i0 + ACC_IMGS);
-    for (int e = threadIdx.x; e < d.ne; e += blockDim.x) {
-        double s = 0.0;
-        for (int i = i0; i < i1; i++) s += d.H[(size_t)i * d.ne + e];
-        partial[(size_t)blockIdx.x * d.ne + e] = s;
-    }
-}
-
+// ---- A, g_a, cost: fold the per-CTA block sums of the evaluation kernel -------------------
 // one block; datasets are folded in sequentially so that two datasets sharing a
 // camera add into the same entries in a fixed order
 __global__ void __launch_bounds__(ACC_THREADS)
@@ -316,40 +302,32 @@ __global__ void finalize_backsub_kernel(int Ks, int n_blocks, const double *part
 
 }  // namespace
 
-// partial scratch layout for accumulate_shared: dataset ds starts at h_tab[ds] and owns
-// h_tab[n_ds + ds] blocks of ne doubles; d_tab is the same table on the device
-void accumulate_shared_table(const DatasetDesc *h_desc, int n_ds, int *h_tab)
+// The fused evaluation kernel leaves, per dataset, one row of ne block sums per persistent
+// CTA (EvalArgs::cta_partial).  h_tab = [offset(ds) | rows(ds)] in doubles / rows; d_tab is
+// the same table on the device.
+void shared_partial_table(const DatasetDesc *h_desc, const int *grids, int n_ds, int *h_tab)
 {
     size_t off = 0;
     for (int ds = 0; ds < n_ds; ds++) {
-        const int nb = (h_desc[ds].n_img + ACC_IMGS - 1) / ACC_IMGS;
         h_tab[ds] = (int)off;
-        h_tab[n_ds + ds] = nb;
-        off += (size_t)nb * h_desc[ds].ne;
+        h_tab[n_ds + ds] = h_desc[ds].n_img > 0 ? grids[ds] : 0;
+        off += (size_t)grids[ds] * h_desc[ds].ne;
     }
 }
 
-cudaError_t launch_accumulate_shared(const DatasetDesc *d_desc, int n_ds, int Ks, double *partial,
-                                     const int *h_tab, const int *d_tab, double *red, SolverLaunch sl)
+size_t shared_partial_doubles(const DatasetDesc *h_desc, const int *grids, int n_ds)
 {
-    for (int ds = 0; ds < n_ds; ds++) {
-        const int nb = h_tab[n_ds + ds];
-        if (nb > 0) {
-            acc_shared_kernel<<<nb, ACC_THREADS, 0, sl.stream>>>(d_desc, ds, partial + h_tab[ds]);
-            if (sl.launches) (*sl.launches)++;
-        }
-    }
+    size_t off = 0;
+    for (int ds = 0; ds < n_ds; ds++) off += (size_t)grids[ds] * h_desc[ds].ne;
+    return off + 8;
+}
+
+cudaError_t launch_finalize_shared(const DatasetDesc *d_desc, int n_ds, int Ks, const double *partial,
+                                   const int *d_tab, double *red, SolverLaunch sl)
+{
     finalize_shared_kernel<<<1, ACC_THREADS, 0, sl.stream>>>(d_desc, n_ds, Ks, partial, d_tab, d_tab + n_ds, red);
     if (sl.launches) (*sl.launches)++;
     return cudaGetLastError();
-}
-
-size_t accumulate_shared_scratch(const DatasetDesc *h_desc, int n_ds)
-{
-    size_t off = 0;
-    for (int ds = 0; ds < n_ds; ds++)
-        off += (size_t)((h_desc[ds].n_img + ACC_IMGS - 1) / ACC_IMGS) * h_desc[ds].ne;
-    return off + 8;
 }
 
 size_t pose_scratch(int n_pose, int Ks)

@@ -6,8 +6,8 @@
 // free intrinsics + free global transforms, Ks columns) plus one independent 6x6
 // block per free sequence pose.  Per evaluation the fused kernel (vg_eval.cu) leaves
 // one packed [J r]^T [J r] block per image; the kernels here
-//   accumulate_shared : sum the shared x shared / shared x residual / residual^2
-//                       entries over images -> A (Ks x Ks), g_a, cost, deterministic
+//   finalize_shared   : fold the per-CTA block sums the evaluation kernel leaves into
+//                       A (Ks x Ks), g_a, cost (shared x shared / shared x residual / residual^2)
 //   pose_factor       : per pose gather C (6x6), E (Ks x 6), b; damp, Cholesky,
 //                       Z = L^-1 E^T, z = L^-1 b
 //   gram_reduce       : S_red = sum Z^T Z, v_red = sum Z^T z  (the Schur complement terms)
@@ -74,9 +74,11 @@ struct SolverLaunch {
 };
 
 // A, g_a, cost of all datasets -> red[A..cost]; partial is scratch of >= blocks*MAX_NE doubles
-void accumulate_shared_table(const DatasetDesc *h_desc, int n_ds, int *h_tab /* 2*n_ds ints */);
-cudaError_t launch_accumulate_shared(const DatasetDesc *d_desc, int n_ds, int Ks, double *partial,
-                                     const int *h_tab, const int *d_tab, double *red, SolverLaunch sl);
+// grids[ds] = persistent CTAs of dataset ds' evaluation kernel = rows of its cta_partial region
+void shared_partial_table(const DatasetDesc *h_desc, const int *grids, int n_ds, int *h_tab /* 2*n_ds ints */);
+size_t shared_partial_doubles(const DatasetDesc *h_desc, const int *grids, int n_ds);
+cudaError_t launch_finalize_shared(const DatasetDesc *d_desc, int n_ds, int Ks, const double *partial,
+                                   const int *d_tab, double *red, SolverLaunch sl);
 
 // per-pose factorisation + Schur terms -> ws, red[S,v], red[gmax]
 cudaError_t launch_pose_schur(const DatasetDesc *d_desc, int n_pose, int Ks,
@@ -84,7 +86,6 @@ cudaError_t launch_pose_schur(const DatasetDesc *d_desc, int n_pose, int Ks,
                               double *scale, LmConsts lm, double *ws, double *partial, size_t partial_doubles,
                               double *red, int *fail_flag, int rank, int nranks, SolverLaunch sl);
 
-size_t accumulate_shared_scratch(const DatasetDesc *h_desc, int n_ds);   // doubles
 size_t pose_scratch(int n_pose, int Ks);                                 // doubles
 
 // candidate poses and model / norm partial sums -> red[model..]
