@@ -24,18 +24,18 @@ static long long smem_any(int model, int L, int G, int P, int PCG)
     }
 }
 
-// G images per group (power of two, G*P <= 256 so one corner pass covers a group),
-// PCG groups per pose prologue (about 16 KB of pose records, PCG*G <= threads).
+// G images per group (G*P <= 256 so that one corner pass covers a group; at most 8: one
+// normal-equation warp per image), PCG groups per pose prologue (about 6 KB of pose records).
 bool plan_eval(int model, int L, int P, LaunchPlan *pl)
 {
     if (P < 1 || L < 1 || L > MAX_CHAIN) return false;
     const long long LIMIT = 227 * 1024;
     const int pose_doubles = ((12 + 21 * L) + 1) & ~1;
-    for (int G = 4; G >= 1; G >>= 1) {   // G <= 4 keeps S = 32/G >= 8 row splits (the reduction works in chunks of 8)
-        if (G > 1 && G * P > 256) continue;
+    for (int G = 4; G >= 1; G >>= 1) {
+        if (G > 1 && G * P > 224) continue;
         int t = ((G * P + 31) / 32) * 32;
         if (t < 96) t = 96;
-        if (t > 256) t = 256;
+        if (t > 224) t = 224;   // __launch_bounds__ of the kernel
         int pcg = (6 * 1024) / (pose_doubles * 8 * G);
         if (pcg * G > t) pcg = t / G;
         if (pcg < 1) pcg = 1;

@@ -8,25 +8,25 @@
 //
 // Persistent CTAs: CTA b owns the image groups b, b + gridDim.x, ... (static, hence
 // deterministic); a group is G consecutive images.  Per group:
-//   0. pose   : (once per PCG groups) one thread per image accumulates the transform
-//               chain with rotation matrices and stages R, t and, per chain element,
-//               R12, M12, t13 (InterJacobian's members, jacobian.h:139-152).
-//   A. corner : one thread per (image, corner): X = R Xb + t, ONE evaluation of the
-//               camera model (projection, dP/dX, dP/dintr share rho, eta and their
-//               reciprocals), residual and Jacobian rows written into shared memory in
-//               exactly the Ceres block layout.  Observations: coalesced 16-byte loads.
-//   S. store  : the staged blocks of the G images are contiguous in global memory, so
-//               one elected thread streams each region out with a TMA bulk copy
+//   0. pose   : (once per PCG groups) one thread per image accumulates the transform chain
+//               with rotation matrices and stages R, t and, per chain element, R12, M12, t13
+//               (InterJacobian's members, jacobian.h:139-152).
+//   A. corner : one thread per (image, corner): X = R Xb + t, ONE evaluation of the camera
+//               model (projection, dP/dX, dP/dintr share rho, eta and their reciprocals),
+//               residual and Jacobian rows written into shared memory in exactly the Ceres
+//               block layout.  Observations: 16-byte streaming loads issued first.
+//   S. store  : the staged blocks of the G images are contiguous in global memory, so one
+//               elected thread streams each region out with a TMA bulk copy
 //               (cp.async.bulk shared::cta -> global, SASS UBLKCP); no register round trip.
-//   B. normal : every warp takes one balanced tile of the per-image packed
-//               [J r]^T [J r] (structural zeros of the intrinsic rows skipped), re-reads
-//               the staged rows, accumulates in registers with the rows split over
-//               S = 32/G lanes, and combines the splits through a small shared-memory
-//               transpose.  The blocks leave through coalesced stores; their per-CTA
-//               sums (for the shared normal-equation block) stay in registers until the
-//               CTA ends.
-// The kernel is HBM-write bound by design (224 B written per EUCM corner); tensor cores
-// are not used -- there is no dense contraction on this path.
+//   B. normal : the per-image block [J r]^T [J r] is a small dense Gram matrix (2P rows x
+//               K+6L+1 columns): one warp per image runs it on the FP64 MMA path
+//               (mma.sync.m8n8k4.f64, 256 FMAs per instruction, fragments loaded straight
+//               from the staged rows), which removes the cross-lane reduction and ~6x of
+//               the instructions a per-lane FMA formulation needs.  The blocks leave through
+//               coalesced stores; their per-CTA sums (for the shared normal-equation block)
+//               stay in registers until the CTA ends.
+// The kernel is HBM-write bound by design (224 B written per EUCM corner).  tcgen05/TMEM are
+// not applicable (no FP64 there); the only matrix-unit use is the legacy FP64 mma.sync above.
 #pragma once
 #include "vg_eval.cuh"
 #include "vg_math.cuh"
@@ -84,164 +84,18 @@ __host__ __device__ constexpr int round_up2(int x) { return (x + 1) & ~1; }
 // packed upper-triangular index of (a,b), a <= b, in a W x W symmetric matrix
 __host__ __device__ constexpr int pk(int a, int b, int W) { return a * W - a * (a - 1) / 2 + (b - a); }
 
-// ---- phase B plan: atoms, balanced tiles --------------------------------------------------
-// Every model's intrinsic Jacobian row has the shape (eucm.h:208-222, ucm.h:176-192,
-// mei.h:257-283)
-//     u-row: [ d_0 .. d_{KD-1} | f 0 | 1 0 ]      v-row: [ d_0 .. d_{KD-1} | 0 f | 0 1 ]
-// so a row is described by the operands  d_i, f, c (the 1, or 0 when the projection failed),
-// p_{e,j} (chain element e) and r, plus its parity.  The products that make up the packed
-// block are grouped into "atoms"; atoms are bin-packed (largest first) into NT tiles of
-// roughly equal accumulator count, one tile per warp.
-constexpr int MAX_TILES = 48;
-constexpr int MAX_ACC = 40;
-
-enum AtomKind { A_DDA, A_DDB, A_DR, A_DF, A_FF, A_FR, A_DPA, A_DPB, A_FP, A_PPA, A_PPB, A_PR, A_PQA, A_PQB };
-
-template <int KD, int L> struct Plan {
-    static constexpr int K = KD + 4;
-    static constexpr int KH = (KD + 1) / 2;
-    static constexpr int NA = 6 + 6 * L + L * (L - 1);
-    // symbolic operand codes
-    static constexpr int OP_F = KD, OP_C = KD + 1, OP_P = KD + 2, OP_R = KD + 2 + 6 * L, NOPS = OP_R + 1;
-
-    struct AtomDesc { int kind, e, b, n; };
-    __host__ __device__ static constexpr AtomDesc atom(int i)
-    {
-        const int dda = KH * KD - KH * (KH - 1) / 2, ddall = KD * (KD + 1) / 2;
-        if (i == 0) return {A_DDA, 0, 0, dda};
-        if (i == 1) return {A_DDB, 0, 0, ddall - dda};
-        if (i == 2) return {A_DR, 0, 0, KD};
-        if (i == 3) return {A_DF, 0, 0, 2 * KD};
-        if (i == 4) return {A_FF, 0, 0, 3};
-        if (i == 5) return {A_FR, 0, 0, 3};
-        i -= 6;
-        if (i < 6 * L) {
-            const int e = i / 6, q = i % 6;
-            if (q == 0) return {A_DPA, e, 0, 6 * KH};
-            if (q == 1) return {A_DPB, e, 0, 6 * (KD - KH)};
-            if (q == 2) return {A_FP, e, 0, 12};
-            if (q == 3) return {A_PPA, e, 0, 11};
-            if (q == 4) return {A_PPB, e, 0, 10};
-            return {A_PR, e, 0, 6};
-        }
-        i -= 6 * L;
-        for (int a = 0; a < L; a++)
-            for (int b = a + 1; b < L; b++) {
-                if (i < 2) return {i == 0 ? A_PQA : A_PQB, a, b, 18};
-                i -= 2;
-            }
-        return {A_FF, 0, 0, 0};
-    }
-    // j-th product of an atom -> (operand a, operand b)
-    struct Pair { int a, b; };
-    __host__ __device__ static constexpr Pair atom_pair(AtomDesc at, int j)
-    {
-        switch (at.kind) {
-        case A_DDA: case A_DDB: {
-            const int i0 = at.kind == A_DDA ? 0 : KH, i1 = at.kind == A_DDA ? KH : KD;
-            for (int i = i0; i < i1; i++) { if (j < KD - i) return {i, i + j}; j -= KD - i; }
-            return {0, 0};
-        }
-        case A_DR: return {j, OP_R};
-        case A_DF: return {j / 2, (j % 2) ? OP_C : OP_F};
-        case A_FF: return {j == 2 ? OP_C : OP_F, j == 0 ? OP_F : OP_C};
-        case A_FR: return {j == 0 ? OP_F : (j == 1 ? OP_C : OP_R), OP_R};
-        case A_DPA: return {j / 6, OP_P + 6 * at.e + j % 6};
-        case A_DPB: return {KH + j / 6, OP_P + 6 * at.e + j % 6};
-        case A_FP: return {j < 6 ? OP_F : OP_C, OP_P + 6 * at.e + j % 6};
-        case A_PPA: case A_PPB: {
-            const int i0 = at.kind == A_PPA ? 0 : 2, i1 = at.kind == A_PPA ? 2 : 6;
-            for (int i = i0; i < i1; i++) { if (j < 6 - i) return {OP_P + 6 * at.e + i, OP_P + 6 * at.e + i + j}; j -= 6 - i; }
-            return {0, 0};
-        }
-        case A_PR: return {OP_P + 6 * at.e + j, OP_R};
-        case A_PQA: return {OP_P + 6 * at.e + j / 6, OP_P + 6 * at.b + j % 6};
-        default: return {OP_P + 6 * at.e + 3 + j / 6, OP_P + 6 * at.b + j % 6};
-        }
-    }
-    // local column of an operand for a row of parity par
-    __host__ __device__ static constexpr int column(int op, int par)
-    {
-        if (op < KD) return op;
-        if (op == OP_F) return KD + par;
-        if (op == OP_C) return KD + 2 + par;
-        if (op == OP_R) return K + 6 * L;
-        return K + (op - OP_P);
-    }
-
-    int NT;
-    int TOT;                       // accumulators over all tiles
-    int off[MAX_TILES];            // first accumulator of a tile in plan order
-    int nacc[MAX_TILES];
-    short ta[MAX_TILES][MAX_ACC], tb[MAX_TILES][MAX_ACC];
-    bool has_ff[MAX_TILES];
-
-    __host__ __device__ constexpr Plan() : NT(0), TOT(0), off{}, nacc{}, ta{}, tb{}, has_ff{}
-    {
-        int total = 0, order[NA > 0 ? NA : 1] = {};
-        for (int i = 0; i < NA; i++) { total += atom(i).n; order[i] = i; }
-        int nt = (total + 23) / 24;     // ~22-24 accumulators per tile
-        if (nt < 1) nt = 1;
-        if (nt > MAX_TILES) nt = MAX_TILES;
-        NT = nt;
-        // largest first
-        for (int i = 0; i < NA; i++)
-            for (int j = i + 1; j < NA; j++)
-                if (atom(order[j]).n > atom(order[i]).n) { const int t = order[i]; order[i] = order[j]; order[j] = t; }
-        for (int i = 0; i < NA; i++) {
-            const AtomDesc at = atom(order[i]);
-            if (at.n == 0) continue;
-            int best = 0;
-            for (int t = 1; t < nt; t++) if (nacc[t] < nacc[best]) best = t;
-            for (int j = 0; j < at.n; j++) {
-                const Pair pr = atom_pair(at, j);
-                ta[best][nacc[best]] = (short)pr.a;
-                tb[best][nacc[best]] = (short)pr.b;
-                nacc[best]++;
-            }
-            if (at.kind == A_FF) has_ff[best] = true;
-        }
-        int o = 0;
-        for (int t = 0; t < nt; t++) { off[t] = o; o += nacc[t]; }
-        TOT = o;
-    }
-    // packed entry e of the W x W block -> (position in plan order) << 2 | mode
-    // mode 0: even-row sum + odd-row sum, 1: even rows only (u), 2: odd rows only (v), 3: structural zero
-    __host__ void entry_table(int *table) const
-    {
-        const int Wd = K + 6 * L + 1, ne = Wd * (Wd + 1) / 2;
-        for (int e = 0; e < ne; e++) table[e] = 3;
-        for (int t = 0; t < NT; t++)
-            for (int j = 0; j < nacc[t]; j++) {
-                const int ca0 = column(ta[t][j], 0), cb0 = column(tb[t][j], 0);
-                const int ca1 = column(ta[t][j], 1), cb1 = column(tb[t][j], 1);
-                const int cu = ca0 * Wd - ca0 * (ca0 - 1) / 2 + (cb0 - ca0);
-                const int cv = ca1 * Wd - ca1 * (ca1 - 1) / 2 + (cb1 - ca1);
-                const int pos = off[t] + j;
-                if (cu == cv) table[cu] = (pos << 2) | 0;
-                else { table[cu] = (pos << 2) | 1; table[cv] = (pos << 2) | 2; }
-            }
-    }
-};
-
-template <int KD, int L> struct PlanHolder { static constexpr Plan<KD, L> value{}; };
-
 template <int MODEL, int L> struct Layout {
     static constexpr int K = Camera<MODEL>::K;
-    static constexpr int KD = K - 4;              // columns before [fu, fv, u0, v0]
     static constexpr int D = K + 6 * L;
-    static constexpr int W = D + 1;
+    static constexpr int W = D + 1;               // columns of [J r]
     static constexpr int NE = W * (W + 1) / 2;
+    static constexpr int NCB = (W + 7) / 8;       // 8-column blocks of the Gram matrix
     static constexpr int POSE = round_up2(12 + 21 * L);
-    static constexpr int NT_ = PlanHolder<K - 4, L>::value.NT;
-    // reduction scratch: one 8 x (32 + 2 pad) slab per warp that can own a phase-B work unit
-    static constexpr int SCRATCH = (2 * NT_ < 8 ? 2 * NT_ : 8) * 8 * 34;
     static constexpr int NPART = (NE + 95) / 96;  // per-thread slots of the per-CTA block sums
-    static constexpr int TOT = PlanHolder<K - 4, L>::value.TOT;   // accumulators of all tiles (plan order)
-    // doubles of shared memory: poses of PCG groups + staging of one group of G images
+    // doubles of shared memory: poses of PCG groups + staging of one group of G images + packed blocks
     __host__ __device__ static constexpr long long smem_doubles(int G, int P, int PCG)
     {
-        return (long long)PCG * G * POSE + (long long)G * 2 * P * (1 + K + 6 * L) + 4LL * G * TOT + SCRATCH;
+        return (long long)PCG * G * POSE + (long long)G * 2 * P * (1 + K + 6 * L) + (long long)G * round_up2(NE);
     }
 };
 
@@ -261,7 +115,7 @@ __device__ __forceinline__ void store_row(double *p, const double (&a)[N], bool 
 // Shared-memory view of the staged group
 template <int MODEL, int L> struct Stage {
     using LY = Layout<MODEL, L>;
-    double *pose, *rs, *Jas, *Jes[L], *Hs, *scratch;
+    double *pose, *rs, *Jas, *Jes[L], *Hs;
     __device__ Stage(double *base, int G, int P, int PCG)
     {
         pose = base;            base += (size_t)PCG * G * LY::POSE;
@@ -269,119 +123,82 @@ template <int MODEL, int L> struct Stage {
         Jas = base;             base += (size_t)G * 2 * P * LY::K;
 #pragma unroll
         for (int e = 0; e < L; e++) { Jes[e] = base; base += (size_t)G * 2 * P * 6; }
-        scratch = base;         base += LY::SCRATCH;      // keeps 16-byte alignment (all sizes above are even)
         Hs = base;
     }
 };
 
-// ---- phase B: one tile ---------------------------------------------------------------------
-template <int MODEL, int L, int T>
-__device__ __forceinline__ void run_tile(const Stage<MODEL, L> &st, const int warp, const int lane, const int G,
-                                         const int S, const int P, const int nv, const int rg, const int RG)
+// D(8x8) += A(8x4) * B(4x8) in fp64 on the matrix unit (SASS: DMMA)
+__device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, const double a, const double b)
 {
-    using LY = Layout<MODEL, L>;
-    using PL = Plan<LY::KD, L>;
-    using PH = PlanHolder<LY::KD, L>;
-    constexpr int K = LY::K, KD = LY::KD, W = LY::W, NACC = PH::value.nacc[T];
-    if constexpr (NACC == 0) return;
-    const int g = lane / S, s = lane - g * S, par = s & 1;
-    const bool valid = g < nv;
-
-    // which operands this tile needs
-    constexpr auto needs = [](int op) {
-        for (int j = 0; j < PH::value.nacc[T]; j++)
-            if (PH::value.ta[T][j] == op || PH::value.tb[T][j] == op) return true;
-        return false;
-    };
-    double acc[NACC];
-#pragma unroll
-    for (int j = 0; j < NACC; j++) acc[j] = 0.0;
-
-    if (valid) {
-        // this warp's corner range (row group rg of RG); a lane keeps one row parity:
-        // rows k = 2 c + par for corners c = c_lo + (s >> 1), step S/2
-        const int cpg = (P + RG - 1) / RG;
-        const int c_lo = rg * cpg, c_hi = min(P, c_lo + cpg);
-        const int hs = S >> 1;
-        const int k0 = 2 * (c_lo + (s >> 1)) + par;
-        const int nit = (c_hi - c_lo - (s >> 1) + hs - 1) / hs;
-        const double *ja = st.Jas + ((size_t)g * 2 * P + k0) * K;
-        const double *pr = st.rs + (size_t)g * 2 * P + k0;
-        const double *pe[L];
-#pragma unroll
-        for (int e = 0; e < L; e++) pe[e] = st.Jes[e] + ((size_t)g * 2 * P + k0) * 6;
-        const int stepK = S * K, step6 = S * 6;
-#pragma unroll 2
-        for (int it = 0; it < nit; it++) {
-            double op[PL::NOPS];
-            static_for<0, KD>([&](auto ic) {
-                constexpr int i = decltype(ic)::value;
-                if constexpr (needs(i)) op[i] = ja[i];
-            });
-            if constexpr (needs(PL::OP_F)) op[PL::OP_F] = ja[KD + par];
-            if constexpr (needs(PL::OP_C)) op[PL::OP_C] = ja[KD + 2 + par];
-            if constexpr (needs(PL::OP_R)) op[PL::OP_R] = pr[0];
-            ja += stepK;
-            pr += S;
-            static_for<0, L>([&](auto ec) {
-                constexpr int e = decltype(ec)::value;
-                constexpr bool any = needs(PL::OP_P + 6 * e) || needs(PL::OP_P + 6 * e + 1) || needs(PL::OP_P + 6 * e + 2) ||
-                                     needs(PL::OP_P + 6 * e + 3) || needs(PL::OP_P + 6 * e + 4) || needs(PL::OP_P + 6 * e + 5);
-                if constexpr (any) {
-                    const double2 *q2 = reinterpret_cast<const double2 *>(pe[e]);
-                    pe[e] += step6;
-                    static_for<0, 3>([&](auto hc) {
-                        constexpr int h = decltype(hc)::value;
-                        if constexpr (needs(PL::OP_P + 6 * e + 2 * h) || needs(PL::OP_P + 6 * e + 2 * h + 1)) {
-                            const double2 v = q2[h];
-                            op[PL::OP_P + 6 * e + 2 * h] = v.x;
-                            op[PL::OP_P + 6 * e + 2 * h + 1] = v.y;
-                        }
-                    });
-                }
-            });
-            static_for<0, NACC>([&](auto jc) {
-                constexpr int j = decltype(jc)::value;
-                constexpr int a = PH::value.ta[T][j], b = PH::value.tb[T][j];
-                acc[j] = fma(op[a], op[b], acc[j]);
-            });
-        }
-    }
-
-    // ---- combine the S row splits through shared memory, 8 accumulators at a time: lane (qg, qa)
-    //      sums the S partials of accumulator 8c + qa of image qg, even and odd rows apart, and
-    //      leaves the pair in plan order; the store loop maps packed entries onto these slots
-    double *sc = st.scratch + (size_t)warp * (8 * 34);
-    double2 *hplan = reinterpret_cast<double2 *>(st.Hs) + (size_t)rg * G * LY::TOT;
-    const int qg = lane >> 3, qa = lane & 7;
-    constexpr int NCH = (NACC + 7) / 8;
-    static_for<0, NCH>([&](auto cc) {
-        constexpr int c = decltype(cc)::value;
-        static_for<0, 8>([&](auto ac) {
-            constexpr int j = 8 * c + decltype(ac)::value;
-            if constexpr (j < NACC) sc[decltype(ac)::value * 34 + lane] = acc[j];
-        });
-        __syncwarp();
-        const int n = 8 * c + qa;
-        if (qg < G && n < NACC) {
-            double ev = 0.0, od = 0.0;
-            const double2 *src = reinterpret_cast<const double2 *>(sc + qa * 34 + qg * S);
-            for (int q = 0; q < S / 2; q++) { const double2 v = src[q]; ev += v.x; od += v.y; }
-            hplan[(size_t)qg * LY::TOT + PH::value.off[T] + n] = make_double2(ev, od);
-        }
-        __syncwarp();
-    });
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-template <int MODEL, int L, int T>
-__device__ __forceinline__ void dispatch_tile(const int t, const Stage<MODEL, L> &st, const int warp, const int lane,
-                                              const int G, const int S, const int P, const int nv, const int rg,
-                                              const int RG)
+// ---- phase B: Gram matrix of one image's staged rows, one warp ------------------------------
+// Column c of [J r]: c < K intrinsic block, then 6 columns per chain element, then the residual.
+// Fragment layout of mma.m8n8k4.f64: lane l feeds A[i = l>>2][k = l&3] and B[k = l&3][j = l>>2], so
+// for G = R^T R both are R[k0 + (l&3)][8 b + (l>>2)]; it receives C[l>>2][2 (l&3) + {0,1}].
+template <int MODEL, int L>
+__device__ __forceinline__ void gram_image(const Stage<MODEL, L> &st, const int g, const int lane, const int P)
 {
-    if constexpr (T < PlanHolder<Layout<MODEL, L>::KD, L>::value.NT) {
-        if (t == T) run_tile<MODEL, L, T>(st, warp, lane, G, S, P, nv, rg, RG);
-        else dispatch_tile<MODEL, L, T + 1>(t, st, warp, lane, G, S, P, nv, rg, RG);
+    using LY = Layout<MODEL, L>;
+    constexpr int K = LY::K, D = LY::D, W = LY::W, NCB = LY::NCB, NTILE = NCB * (NCB + 1) / 2;
+    const int kr = lane & 3, ci = lane >> 2;
+    const double *ptr[NCB];
+    int stride[NCB];
+#pragma unroll
+    for (int b = 0; b < NCB; b++) {
+        const int c = 8 * b + ci;
+        if (c < K) { ptr[b] = st.Jas + ((size_t)g * 2 * P + kr) * K + c; stride[b] = 4 * K; }
+        else if (c < D) {
+            const int e = (c - K) / 6, q = (c - K) - 6 * e;
+            const double *base = st.Jes[0];
+#pragma unroll
+            for (int ee = 1; ee < L; ee++) if (e == ee) base = st.Jes[ee];
+            ptr[b] = base + ((size_t)g * 2 * P + kr) * 6 + q; stride[b] = 24;
+        }
+        else if (c == D) { ptr[b] = st.rs + (size_t)g * 2 * P + kr; stride[b] = 4; }
+        else { ptr[b] = nullptr; stride[b] = 0; }
     }
+    // two interleaved accumulator sets (even / odd k-steps) keep two independent MMA chains per tile
+    double acc[2][NTILE][2];
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+#pragma unroll
+        for (int t = 0; t < NTILE; t++) { acc[h][t][0] = 0.0; acc[h][t][1] = 0.0; }
+    const int rows = 2 * P;
+    const int nks = (rows + 3) / 4;
+    for (int ks = 0; ks < nks; ks += 2) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int k = 4 * (ks + h) + kr;
+            double x[NCB];
+#pragma unroll
+            for (int b = 0; b < NCB; b++) {
+                x[b] = (ptr[b] != nullptr && k < rows) ? ptr[b][0] : 0.0;
+                if (ptr[b] != nullptr) ptr[b] += stride[b];
+            }
+            int t = 0;
+#pragma unroll
+            for (int bi = 0; bi < NCB; bi++)
+#pragma unroll
+                for (int bj = bi; bj < NCB; bj++) { dmma_8x8x4(acc[h][t][0], acc[h][t][1], x[bi], x[bj]); t++; }
+        }
+    }
+    double *h = st.Hs + (size_t)g * round_up2(LY::NE);
+    int t = 0;
+#pragma unroll
+    for (int bi = 0; bi < NCB; bi++)
+#pragma unroll
+        for (int bj = bi; bj < NCB; bj++) {
+            const int i = 8 * bi + ci;
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const int j = 8 * bj + 2 * kr + q;
+                if (i <= j && j < W) h[pk(i, j, W)] = acc[0][t][q] + acc[1][t][q];
+            }
+            t++;
+        }
 }
 
 // ---- phase 0: one image's transform chain -> staged pose record ---------------------
@@ -439,21 +256,21 @@ __device__ __forceinline__ void chain_pose(const EvalArgs &args, const int img, 
 }
 
 // ---- the kernel -------------------------------------------------------------------
+// PCG = groups whose poses one prologue pass stages (PCG * G <= blockDim.x).
 template <int MODEL, int L>
-__global__ void __launch_bounds__(256, (L == 1 && Camera<MODEL>::K <= 6) ? 3 : 2)
-reproj_eval_kernel(const EvalArgs args, const int G, const int PCG, const int *__restrict__ entry_table)
+__global__ void __launch_bounds__(224, (L == 1 && Camera<MODEL>::K <= 6) ? 4 : 2)
+reproj_eval_kernel(const EvalArgs args, const int G, const int PCG)
 {
     using LY = Layout<MODEL, L>;
     using CAM = Camera<MODEL>;
     constexpr int K = LY::K;
-    constexpr int NT = PlanHolder<LY::KD, L>::value.NT;
+    constexpr int NEP = round_up2(LY::NE);
     extern __shared__ __align__(16) double smem[];
     const int P = args.P;
     const Stage<MODEL, L> st(smem, G, P, PCG);
     const int tid = threadIdx.x;
     const int n_groups = (args.n_img + G - 1) / G;
     const int warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
-    const int S = 32 / G;
 
     double intr[K];
 #pragma unroll
@@ -461,13 +278,8 @@ reproj_eval_kernel(const EvalArgs args, const int G, const int PCG, const int *_
     const typename CAM::Consts cc = CAM::prepare(intr);
     const bool first_direct = (args.inverse[0] == 0);   // R12 of element 0 is the identity
     double part[LY::NPART];                              // this CTA's sum of its images' blocks
-    int code[LY::NPART];                                 // packed entry -> plan-order slot (see Plan::entry_table)
 #pragma unroll
-    for (int q = 0; q < LY::NPART; q++) {
-        part[q] = 0.0;
-        const int e = tid + q * blockDim.x;
-        code[q] = (args.H && e < LY::NE) ? __ldg(entry_table + e) : 3;
-    }
+    for (int q = 0; q < LY::NPART; q++) part[q] = 0.0;
 
     for (int j0 = 0; (long long)blockIdx.x + (long long)j0 * gridDim.x < n_groups; j0 += PCG) {
         // ---- phase 0: poses of this CTA's next PCG groups, one thread per image ---------
@@ -491,11 +303,11 @@ reproj_eval_kernel(const EvalArgs args, const int G, const int PCG, const int *_
                 const int g = idx / P;
                 const int c = idx - g * P;
                 const int img = img0 + g;
-                const double *ps = pose_grp + (size_t)g * LY::POSE;
-                // issue the (streaming) observation load first: its DRAM latency hides behind the model math
+                // issue the (streaming) observation load first: its latency hides behind the model math
                 double2 ob;
                 asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];"
                              : "=d"(ob.x), "=d"(ob.y) : "l"(args.obs + ((size_t)img * P + c) * 2));
+                const double *ps = pose_grp + (size_t)g * LY::POSE;
                 const double bx = __ldg(args.board + 3 * c), by = __ldg(args.board + 3 * c + 1),
                              bz = __ldg(args.board + 3 * c + 2);
                 const double X0 = fma(ps[2], bz, fma(ps[1], by, fma(ps[0], bx, ps[9])));
@@ -566,13 +378,9 @@ reproj_eval_kernel(const EvalArgs args, const int G, const int PCG, const int *_
                 if (issued) bulk_commit();
             }
 
-            // ---- phase B: per-image normal-equation blocks -----------------------------
+            // ---- phase B: per-image normal-equation blocks, one warp per image ------------
             if (args.H) {
-                // NT tiles x RG row groups of work units; with RG = 2 each tile's rows are shared by two
-                // warps that fill separate copies of the blocks (summed below: two addends, deterministic)
-                const int RG = (nw >= 2 * NT && P >= 2) ? 2 : 1;
-                for (int u = warp; u < NT * RG; u += nw)
-                    dispatch_tile<MODEL, L, 0>(u % NT, st, warp, lane, G, S, P, nv, u / NT, RG);
+                for (int g = warp; g < nv; g += nw) gram_image<MODEL, L>(st, g, lane, P);
                 __syncthreads();
                 double *Hg = args.H + (size_t)img0 * LY::NE;
 #pragma unroll
@@ -580,15 +388,8 @@ reproj_eval_kernel(const EvalArgs args, const int G, const int PCG, const int *_
                     const int e = tid + q * blockDim.x;
                     if (e < LY::NE) {
                         double sum = 0.0;
-                        const int pos = code[q] >> 2, mode = code[q] & 3;
-                        const double2 *hp = reinterpret_cast<const double2 *>(st.Hs) + pos;
                         for (int g = 0; g < nv; g++) {
-                            double2 v2 = hp[(size_t)g * LY::TOT];
-                            if (RG == 2) {
-                                const double2 w2 = hp[(size_t)(G + g) * LY::TOT];
-                                v2.x += w2.x; v2.y += w2.y;
-                            }
-                            const double val = mode == 0 ? v2.x + v2.y : (mode == 1 ? v2.x : (mode == 2 ? v2.y : 0.0));
+                            const double val = st.Hs[(size_t)g * NEP + e];
                             Hg[(size_t)g * LY::NE + e] = val;
                             sum += val;
                         }
@@ -609,7 +410,6 @@ reproj_eval_kernel(const EvalArgs args, const int G, const int PCG, const int *_
     }
 }
 
-
 template <int MODEL, int L>
 cudaError_t launch_one(const EvalArgs &args, cudaStream_t stream, unsigned long long *launches, int *grid_out,
                        bool query_only)
@@ -620,20 +420,9 @@ cudaError_t launch_one(const EvalArgs &args, cudaStream_t stream, unsigned long 
     static int blocks_per_sm[64];
     static int sm_count[64];
     static int planned_threads[64];
-    static int *entry_table[64];
     int dev = 0;
     cudaGetDevice(&dev);
     dev &= 63;
-    if (!entry_table[dev] && !query_only) {
-        using LY = Layout<MODEL, L>;
-        static constexpr Plan<LY::KD, L> plan{};
-        std::vector<int> tab(LY::NE);
-        plan.entry_table(tab.data());
-        cudaError_t e = cudaMalloc(&entry_table[dev], sizeof(int) * LY::NE);
-        if (e != cudaSuccess) return e;
-        e = cudaMemcpy(entry_table[dev], tab.data(), sizeof(int) * LY::NE, cudaMemcpyHostToDevice);
-        if (e != cudaSuccess) return e;
-    }
     if (pl.smem > configured_bytes[dev] || planned_threads[dev] != pl.threads) {
         cudaError_t e = cudaFuncSetAttribute(reproj_eval_kernel<MODEL, L>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
@@ -652,7 +441,7 @@ cudaError_t launch_one(const EvalArgs &args, cudaStream_t stream, unsigned long 
     if (grid > n_groups) grid = n_groups;
     if (grid_out) *grid_out = grid;
     if (query_only || args.n_img <= 0) return cudaSuccess;
-    reproj_eval_kernel<MODEL, L><<<grid, pl.threads, (size_t)pl.smem, stream>>>(args, pl.G, pl.PCG, entry_table[dev]);
+    reproj_eval_kernel<MODEL, L><<<grid, pl.threads, (size_t)pl.smem, stream>>>(args, pl.G, pl.PCG);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }
