@@ -73,7 +73,7 @@ class ClockSampler:
             if probe.returncode != 0 or "not a valid field" in (probe.stdout + probe.stderr).lower():
                 fields = fields.replace("clocks_event_reasons", "clocks_throttle_reasons")
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={fields}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={fields}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -107,7 +107,8 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "window": "timed regions plus ~1 s of the same step run back to back right after them"}
 
 
 def measured_peak():
@@ -269,6 +270,15 @@ def run_ours(args):
         launches_per_step = (vg.launch_count() - l0) / args.steps
     cost, red = probs[(args.steps - 1) % args.sets].fetch_reduced()
     value = world * n_img * P / (step_ms * 1e-3)
+    # the timed region above lasts only tens of milliseconds; keep the same step running for about a
+    # second so that nvidia-smi (20 ms period) sees the clocks and throttle reasons under this load
+    with torch.cuda.stream(stream):
+        t_w0 = time.time()
+        while time.time() - t_w0 < 1.0:
+            for i in range(200):
+                probs[i % args.sets].evaluate_async()
+            torch.cuda.synchronize()
+        windows.append((t_w0, time.time()))
 
     # ---- leg 2: the dominant kernel alone (roofline), same buffers, launched back to back -------
     bufs = []
@@ -310,21 +320,31 @@ def run_ours(args):
     h2d = h_obs.numel() * 8 + h_xi.numel() * 8 + K * 8
     d2h = (ks + 1) * 8
 
-    def e2e_step(i):
-        Pm = probs[i % args.sets]
-        Pm.update_observations(ds_ids[i % args.sets], h_obs.data_ptr())
-        Pm.set_transform_ptr(tr_ids[i % args.sets], h_xi.data_ptr())
-        Pm.set_camera(cam_ids[i % args.sets], d["intr_init"])
+    # two steps in flight (each problem on its own stream): the upload of step i+1 overlaps the kernels of step i
+    for Pm in probs:
+        Pm.set_stream(None)
+
+    def e2e_issue(i):
+        k = i % args.sets
+        Pm = probs[k]
+        Pm.update_observations(ds_ids[k], h_obs.data_ptr())
+        Pm.update_poses(tr_ids[k], h_xi.data_ptr())
+        Pm.set_camera(cam_ids[k], d["intr_init"])
         Pm.evaluate_async()
-        return Pm.fetch_reduced()
-    n_e2e = max(10, min(args.steps, 100))
+
+    def e2e_fetch(i):
+        return probs[i % args.sets].fetch_reduced()
+    n_e2e = max(10, min(args.steps, 200))
     for i in range(3):
-        e2e_step(i)
+        e2e_issue(i); e2e_fetch(i)
     barrier()
     t_w0 = time.time()
     t0 = time.perf_counter()
-    for i in range(n_e2e):
-        c_e2e, _ = e2e_step(i)
+    e2e_issue(0)
+    for i in range(1, n_e2e):
+        e2e_issue(i)
+        c_e2e, _ = e2e_fetch(i - 1)
+    c_e2e, _ = e2e_fetch(n_e2e - 1)
     torch.cuda.synchronize()
     e2e_s = max_over_ranks((time.perf_counter() - t0) / n_e2e)
     windows.append((t_w0, time.time()))

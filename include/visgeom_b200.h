@@ -217,6 +217,10 @@ int vg_problem_set_transform(vg_problem *p, int transform, const double *values)
 /* replace the observations / poses of a dataset from (pinned) host memory -- the
  * per-step input upload of the end-to-end benchmark */
 int vg_problem_update_observations(vg_problem *p, int dataset, const double *obs);
+/* same for a sequence transform's poses (n x 6); both calls are asynchronous on the problem's
+ * stream: the host buffers must stay valid until the next call that waits (fetch / evaluate /
+ * solve / get_*) */
+int vg_problem_update_poses(vg_problem *p, int transform, const double *values);
 /* residuals of one dataset at the current parameters (writeImageResidual,
  * :1186-1213 needs err = -r and proj = r + obs), n_img x 2P doubles to host */
 int vg_problem_residuals(vg_problem *p, int dataset, double *r);

@@ -91,6 +91,7 @@ def lib() -> C.CDLL:
         L.vg_problem_get_transform.argtypes = [C.c_void_p, C.c_int, c_dp]
         L.vg_problem_set_transform.argtypes = [C.c_void_p, C.c_int, c_dp]
         L.vg_problem_update_observations.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.vg_problem_update_poses.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.vg_problem_residuals.argtypes = [C.c_void_p, C.c_int, c_dp]
         L.vg_solve_options_default.argtypes = [C.POINTER(SolveOptions)]
     _lib = L
@@ -309,6 +310,10 @@ class Problem:
     def set_transform_ptr(self, tid, host_ptr: int):
         """values read from a (pinned) host address"""
         _check(self.L.vg_problem_set_transform(self.h, tid, C.cast(host_ptr, c_dp)))
+
+    def update_poses(self, tid, host_ptr: int):
+        """asynchronous upload of a sequence transform's poses from a (pinned) host address"""
+        _check(self.L.vg_problem_update_poses(self.h, tid, host_ptr))
 
     def update_observations(self, dataset, host_ptr: int):
         _check(self.L.vg_problem_update_observations(self.h, dataset, host_ptr))

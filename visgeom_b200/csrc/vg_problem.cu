@@ -111,8 +111,11 @@ struct vg_problem {
     DatasetDesc *d_desc[2] = {nullptr, nullptr};
     std::vector<DatasetDesc> h_desc[2];
     int *d_pose_start = nullptr, *d_contrib_ds = nullptr, *d_contrib_img = nullptr;
-    int *d_pose_seq = nullptr, *d_pose_local = nullptr, *d_fail = nullptr, *d_acc_tab = nullptr;
-    std::vector<int> h_acc_tab;
+    int *d_pose_seq = nullptr, *d_pose_local = nullptr, *d_fail = nullptr;
+    std::vector<int> h_acc_tab;                 // offset of each dataset's cta_partial region
+    FinOut *d_fin_out = nullptr;
+    FinSrc *d_fin_src = nullptr;
+    int n_fin_out = 0;
     double **d_seq_ptr[2] = {nullptr, nullptr};
     double *d_scale = nullptr, *d_ws = nullptr, *d_partial = nullptr, *d_red = nullptr, *d_delta = nullptr;
     double *d_cta_partial = nullptr;
@@ -134,7 +137,7 @@ void free_prepared(vg_problem *p)
     auto F = [](auto *&ptr) { if (ptr) { cudaFree(ptr); ptr = nullptr; } };
     for (int s = 0; s < 2; s++) { F(p->d_slab[s]); F(p->d_desc[s]); F(p->d_seq_ptr[s]); }
     F(p->d_pose_start); F(p->d_contrib_ds); F(p->d_contrib_img); F(p->d_pose_seq); F(p->d_pose_local);
-    F(p->d_fail); F(p->d_acc_tab); F(p->d_cta_partial); F(p->d_scale); F(p->d_ws); F(p->d_partial); F(p->d_red); F(p->d_delta);
+    F(p->d_fail); F(p->d_fin_out); F(p->d_fin_src); F(p->d_cta_partial); F(p->d_scale); F(p->d_ws); F(p->d_partial); F(p->d_red); F(p->d_delta);
     if (p->h_red) { cudaFreeHost(p->h_red); p->h_red = nullptr; }
     if (p->h_up) { cudaFreeHost(p->h_up); p->h_up = nullptr; }
     for (auto &d : p->dss)
@@ -247,10 +250,16 @@ int prepare(vg_problem *p)
     std::vector<int> grids(p->dss.size() + 1, 0);
     for (size_t k = 0; k < p->dss.size(); k++)
         VG_CUDA(eval_grid_size(p->cams[p->dss[k].cam].model, p->dss[k].L, p->dss[k].n_img, p->dss[k].P, &grids[k]));
-    p->h_acc_tab.assign(2 * p->dss.size() + 2, 0);
-    shared_partial_table(p->h_desc[0].data(), grids.data(), (int)p->dss.size(), p->h_acc_tab.data());
-    VG_CUDA(upload_i(p->d_acc_tab, p->h_acc_tab));
-    p->cta_partial_doubles = shared_partial_doubles(p->h_desc[0].data(), grids.data(), (int)p->dss.size());
+    std::vector<FinOut> fin_out;
+    std::vector<FinSrc> fin_src;
+    build_finalize_tables(p->h_desc[0].data(), grids.data(), (int)p->dss.size(), Ks, p->h_acc_tab, fin_out, fin_src,
+                          &p->cta_partial_doubles);
+    p->n_fin_out = (int)fin_out.size();
+    VG_CUDA(cudaMalloc(&p->d_fin_out, sizeof(FinOut) * (fin_out.size() + 1)));
+    VG_CUDA(cudaMalloc(&p->d_fin_src, sizeof(FinSrc) * (fin_src.size() + 1)));
+    VG_CUDA(cudaMemcpy(p->d_fin_out, fin_out.data(), sizeof(FinOut) * fin_out.size(), cudaMemcpyHostToDevice));
+    if (!fin_src.empty())
+        VG_CUDA(cudaMemcpy(p->d_fin_src, fin_src.data(), sizeof(FinSrc) * fin_src.size(), cudaMemcpyHostToDevice));
     VG_CUDA(cudaMalloc(&p->d_cta_partial, sizeof(double) * p->cta_partial_doubles));
     VG_CUDA(cudaMalloc(&p->d_fail, sizeof(int)));
     VG_CUDA(cudaMemset(p->d_fail, 0, sizeof(int)));
@@ -304,8 +313,7 @@ int evaluate_set(vg_problem *p, int s, bool timed)
     }
     if (timed) VG_CUDA(cudaEventRecord(p->ev1, p->stream));
     SolverLaunch sl{p->stream, &launch_counter()};
-    cudaError_t e = launch_finalize_shared(p->d_desc[s], (int)p->dss.size(), p->Ks, p->d_cta_partial, p->d_acc_tab,
-                                           p->d_red, sl);
+    cudaError_t e = launch_finalize_shared(p->d_fin_out, p->d_fin_src, p->n_fin_out, p->d_cta_partial, p->d_red, sl);
     if (e != cudaSuccess) return fail_cuda(e, "finalize_shared");
     p->n_eval++;
     return VG_OK;
@@ -643,6 +651,18 @@ int vg_problem_update_observations(vg_problem *p, int dataset, const double *obs
     Ds &d = p->dss[dataset];
     VG_CUDA(cudaSetDevice(p->device));
     VG_CUDA(cudaMemcpyAsync(d.d_obs, obs, sizeof(double) * 2 * (size_t)d.P * d.n_img, cudaMemcpyHostToDevice, p->stream));
+    return VG_OK;
+}
+
+int vg_problem_update_poses(vg_problem *p, int transform, const double *values)
+{
+    if (!p || !values || transform < 0 || transform >= (int)p->trs.size()) return fail(VG_ERR_INVALID, "bad transform");
+    Tr &t = p->trs[transform];
+    if (t.is_global) return fail(VG_ERR_INVALID, "vg_problem_update_poses: not a sequence transform");
+    int rc = prepare(p);
+    if (rc) return rc;
+    VG_CUDA(cudaSetDevice(p->device));
+    VG_CUDA(cudaMemcpyAsync(t.dev[p->cur], values, sizeof(double) * 6 * t.n, cudaMemcpyHostToDevice, p->stream));
     return VG_OK;
 }
 

@@ -3,6 +3,8 @@
 // so results are bit-reproducible run to run for a fixed problem.
 #include "vg_solver_kernels.cuh"
 
+#include <vector>
+
 namespace vg {
 
 namespace {
@@ -16,37 +18,46 @@ constexpr int GRAM_POSES = 64;       // poses per block in gram_reduce
 constexpr int GRAM_THREADS = 224;    // >= Ks(Ks+1)/2 + Ks for Ks <= 18; larger Ks loops
 
 // ---- A, g_a, cost: fold the per-CTA block sums of the evaluation kernel -------------------
-// one block; datasets are folded in sequentially so that two datasets sharing a
-// camera add into the same entries in a fixed order
-__global__ void __launch_bounds__(ACC_THREADS)
-finalize_shared_kernel(const DatasetDesc *desc_all, int n_ds, int Ks, const double *partial,
-                       const int *partial_off, const int *n_blocks, double *red)
+// The fused evaluation kernel leaves one row of block sums per persistent CTA and dataset.  A
+// host-built table lists, for every entry of the reduced system (A_ij with i <= j, g_i, cost), the
+// (dataset, packed entry) sources that feed it.  One block per FIN_OUT outputs: every thread owns
+// CTA rows (one per thread in practice) and keeps FIN_OUT independent loads in flight -- the kernel
+// is pure memory latency -- then a fixed shuffle / shared-memory tree.  Deterministic.
+__global__ void __launch_bounds__(FIN_THREADS)
+finalize_shared_kernel(const FinOut *outs, const FinSrc *srcs, int n_out, const double *partial, double *red)
 {
-    double *A = red + red_off_A(Ks), *g = red + red_off_g(Ks), *cost = red + red_off_cost(Ks);
-    for (int i = threadIdx.x; i < red_off_model(Ks); i += blockDim.x) red[i] = 0.0;   // A, g_a, cost
+    __shared__ double wsum[FIN_THREADS / 32][FIN_OUT];
+    __shared__ FinOut so[FIN_OUT];
+    const int o0 = blockIdx.x * FIN_OUT;
+    if (threadIdx.x < FIN_OUT && o0 + threadIdx.x < n_out) so[threadIdx.x] = outs[o0 + threadIdx.x];
     __syncthreads();
-    for (int ds = 0; ds < n_ds; ds++) {
-        const DatasetDesc &d = desc_all[ds];
-        const double *pp = partial + partial_off[ds];
-        for (int e = threadIdx.x; e < d.ne; e += blockDim.x) {
-            // packed index -> (a,b)
-            int a = 0, rem = e;
-            while (rem >= d.W - a) { rem -= d.W - a; a++; }
-            const int b = a + rem;
-            const int ka = d.kind[a], kb = d.kind[b];
-            if (ka == COL_CONST || kb == COL_CONST || ka == COL_POSE || kb == COL_POSE) continue;
-            double s = 0.0;
-            for (int blk = 0; blk < n_blocks[ds]; blk++) s += pp[(size_t)blk * d.ne + e];
-            if (ka == COL_SHARED && kb == COL_SHARED) {
-                A[d.idx[a] * Ks + d.idx[b]] += s;
-                if (a != b) A[d.idx[b] * Ks + d.idx[a]] += s;
-            } else if (ka == COL_SHARED && kb == COL_RESID) {
-                g[d.idx[a]] += s;
-            } else if (ka == COL_RESID && kb == COL_RESID) {
-                cost[0] += 0.5 * s;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    double v[FIN_OUT];
+#pragma unroll
+    for (int q = 0; q < FIN_OUT; q++) {
+        v[q] = 0.0;
+        if (o0 + q < n_out) {
+            for (int si = so[q].src_begin; si < so[q].src_end; si++) {
+                const FinSrc sr = srcs[si];
+                for (int row = threadIdx.x; row < sr.nb; row += blockDim.x)
+                    v[q] += partial[(size_t)sr.off + (size_t)row * sr.ne + sr.e];
             }
         }
-        __syncthreads();
+    }
+#pragma unroll
+    for (int q = 0; q < FIN_OUT; q++) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], off);
+        if (lane == 0) wsum[warp][q] = v[q];
+    }
+    __syncthreads();
+    if (threadIdx.x < FIN_OUT && o0 + threadIdx.x < n_out) {
+        const int q = threadIdx.x;
+        double t = 0.0;
+        for (int w = 0; w < nw; w++) t += wsum[w][q];
+        t *= so[q].scale;
+        red[so[q].dst0] = t;
+        if (so[q].dst1 >= 0) red[so[q].dst1] = t;
     }
 }
 
@@ -302,30 +313,58 @@ __global__ void finalize_backsub_kernel(int Ks, int n_blocks, const double *part
 
 }  // namespace
 
-// The fused evaluation kernel leaves, per dataset, one row of ne block sums per persistent
-// CTA (EvalArgs::cta_partial).  h_tab = [offset(ds) | rows(ds)] in doubles / rows; d_tab is
-// the same table on the device.
-void shared_partial_table(const DatasetDesc *h_desc, const int *grids, int n_ds, int *h_tab)
+// Host side of finalize_shared: offsets of each dataset's cta_partial region and the output table.
+void build_finalize_tables(const DatasetDesc *h_desc, const int *grids, int n_ds, int Ks, std::vector<int> &offsets,
+                           std::vector<FinOut> &outs, std::vector<FinSrc> &srcs, size_t *partial_doubles)
 {
+    offsets.assign(n_ds + 1, 0);
     size_t off = 0;
+    for (int ds = 0; ds < n_ds; ds++) { offsets[ds] = (int)off; off += (size_t)grids[ds] * h_desc[ds].ne; }
+    offsets[n_ds] = (int)off;
+    *partial_doubles = off + 8;
+    const int n_out = Ks * (Ks + 1) / 2 + Ks + 1;
+    std::vector<std::vector<FinSrc>> per(n_out);
+    auto a_index = [&](int i, int j) { if (i > j) { const int t = i; i = j; j = t; } return i * Ks - i * (i - 1) / 2 + (j - i); };
     for (int ds = 0; ds < n_ds; ds++) {
-        h_tab[ds] = (int)off;
-        h_tab[n_ds + ds] = h_desc[ds].n_img > 0 ? grids[ds] : 0;
-        off += (size_t)grids[ds] * h_desc[ds].ne;
+        const DatasetDesc &d = h_desc[ds];
+        if (d.n_img <= 0) continue;
+        int e = 0;
+        for (int a = 0; a < d.W; a++)
+            for (int b = a; b < d.W; b++, e++) {
+                const int ka = d.kind[a], kb = d.kind[b];
+                int o = -1;
+                if (ka == COL_SHARED && kb == COL_SHARED) o = a_index(d.idx[a], d.idx[b]);
+                else if (ka == COL_SHARED && kb == COL_RESID) o = Ks * (Ks + 1) / 2 + d.idx[a];
+                else if (ka == COL_RESID && kb == COL_RESID) o = n_out - 1;
+                if (o >= 0) per[o].push_back(FinSrc{offsets[ds], d.ne, grids[ds], e});
+            }
     }
+    outs.clear(); srcs.clear();
+    int o = 0;
+    for (int i = 0; i < Ks; i++)
+        for (int j = i; j < Ks; j++, o++) {
+            FinOut f{red_off_A(Ks) + i * Ks + j, i == j ? -1 : red_off_A(Ks) + j * Ks + i, 1.0, (int)srcs.size(), 0};
+            for (auto &x : per[o]) srcs.push_back(x);
+            f.src_end = (int)srcs.size();
+            outs.push_back(f);
+        }
+    for (int i = 0; i < Ks; i++, o++) {
+        FinOut f{red_off_g(Ks) + i, -1, 1.0, (int)srcs.size(), 0};
+        for (auto &x : per[o]) srcs.push_back(x);
+        f.src_end = (int)srcs.size();
+        outs.push_back(f);
+    }
+    FinOut f{red_off_cost(Ks), -1, 0.5, (int)srcs.size(), 0};
+    for (auto &x : per[o]) srcs.push_back(x);
+    f.src_end = (int)srcs.size();
+    outs.push_back(f);
 }
 
-size_t shared_partial_doubles(const DatasetDesc *h_desc, const int *grids, int n_ds)
+cudaError_t launch_finalize_shared(const FinOut *d_outs, const FinSrc *d_srcs, int n_out, const double *partial,
+                                   double *red, SolverLaunch sl)
 {
-    size_t off = 0;
-    for (int ds = 0; ds < n_ds; ds++) off += (size_t)grids[ds] * h_desc[ds].ne;
-    return off + 8;
-}
-
-cudaError_t launch_finalize_shared(const DatasetDesc *d_desc, int n_ds, int Ks, const double *partial,
-                                   const int *d_tab, double *red, SolverLaunch sl)
-{
-    finalize_shared_kernel<<<1, ACC_THREADS, 0, sl.stream>>>(d_desc, n_ds, Ks, partial, d_tab, d_tab + n_ds, red);
+    const int blocks = (n_out + FIN_OUT - 1) / FIN_OUT;
+    finalize_shared_kernel<<<blocks, FIN_THREADS, 0, sl.stream>>>(d_outs, d_srcs, n_out, partial, red);
     if (sl.launches) (*sl.launches)++;
     return cudaGetLastError();
 }

@@ -17,6 +17,8 @@
 
 #include <cuda_runtime.h>
 
+#include <vector>
+
 namespace vg {
 
 constexpr int MAX_W = 41;          // 10 intrinsics + 5*6 + residual column
@@ -74,11 +76,16 @@ struct SolverLaunch {
 };
 
 // A, g_a, cost of all datasets -> red[A..cost]; partial is scratch of >= blocks*MAX_NE doubles
+// finalize_shared tables (built on the host once per problem)
+constexpr int FIN_THREADS = 640;
+constexpr int FIN_OUT = 8;
+struct FinSrc { int off, ne, nb, e; };                       // cta_partial offset, row stride, rows, packed entry
+struct FinOut { int dst0, dst1; double scale; int src_begin, src_end; };   // red[] targets (dst1 = mirror or -1)
 // grids[ds] = persistent CTAs of dataset ds' evaluation kernel = rows of its cta_partial region
-void shared_partial_table(const DatasetDesc *h_desc, const int *grids, int n_ds, int *h_tab /* 2*n_ds ints */);
-size_t shared_partial_doubles(const DatasetDesc *h_desc, const int *grids, int n_ds);
-cudaError_t launch_finalize_shared(const DatasetDesc *d_desc, int n_ds, int Ks, const double *partial,
-                                   const int *d_tab, double *red, SolverLaunch sl);
+void build_finalize_tables(const DatasetDesc *h_desc, const int *grids, int n_ds, int Ks, std::vector<int> &offsets,
+                           std::vector<FinOut> &outs, std::vector<FinSrc> &srcs, size_t *partial_doubles);
+cudaError_t launch_finalize_shared(const FinOut *d_outs, const FinSrc *d_srcs, int n_out, const double *partial,
+                                   double *red, SolverLaunch sl);
 
 // per-pose factorisation + Schur terms -> ws, red[S,v], red[gmax]
 cudaError_t launch_pose_schur(const DatasetDesc *d_desc, int n_pose, int Ks,
