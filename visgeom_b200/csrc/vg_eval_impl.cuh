@@ -95,7 +95,7 @@ template <int MODEL, int L> struct Layout {
     // doubles of shared memory: poses of PCG groups + staging of one group of G images + packed blocks
     __host__ __device__ static constexpr long long smem_doubles(int G, int P, int PCG)
     {
-        return (long long)PCG * G * POSE + (long long)G * 2 * P * (1 + K + 6 * L) + (long long)G * round_up2(NE);
+        return 2 + (long long)PCG * G * POSE + (long long)G * 2 * P * (1 + K + 6 * L) + (long long)G * round_up2(NE);
     }
 };
 
@@ -115,9 +115,10 @@ __device__ __forceinline__ void store_row(double *p, const double (&a)[N], bool 
 // Shared-memory view of the staged group
 template <int MODEL, int L> struct Stage {
     using LY = Layout<MODEL, L>;
-    double *pose, *rs, *Jas, *Jes[L], *Hs;
+    double *pose, *rs, *Jas, *Jes[L], *Hs, *zero;
     __device__ Stage(double *base, int G, int P, int PCG)
     {
+        zero = base;            base += 2;                 // two zeros for the Gram padding columns
         pose = base;            base += (size_t)PCG * G * LY::POSE;
         rs = base;              base += (size_t)G * 2 * P;
         Jas = base;             base += (size_t)G * 2 * P * LY::K;
@@ -144,6 +145,8 @@ __device__ __forceinline__ void gram_image(const Stage<MODEL, L> &st, const int 
     using LY = Layout<MODEL, L>;
     constexpr int K = LY::K, D = LY::D, W = LY::W, NCB = LY::NCB, NTILE = NCB * (NCB + 1) / 2;
     const int kr = lane & 3, ci = lane >> 2;
+    // per 8-column block: this lane's source pointer and its increment per k-step (4 rows); padding
+    // columns read a zero slot with increment 0, so the inner loop has no selects
     const double *ptr[NCB];
     int stride[NCB];
 #pragma unroll
@@ -158,7 +161,7 @@ __device__ __forceinline__ void gram_image(const Stage<MODEL, L> &st, const int 
             ptr[b] = base + ((size_t)g * 2 * P + kr) * 6 + q; stride[b] = 24;
         }
         else if (c == D) { ptr[b] = st.rs + (size_t)g * 2 * P + kr; stride[b] = 4; }
-        else { ptr[b] = nullptr; stride[b] = 0; }
+        else { ptr[b] = st.zero; stride[b] = 0; }
     }
     // two interleaved accumulator sets (even / odd k-steps) keep two independent MMA chains per tile
     double acc[2][NTILE][2];
@@ -167,24 +170,24 @@ __device__ __forceinline__ void gram_image(const Stage<MODEL, L> &st, const int 
 #pragma unroll
         for (int t = 0; t < NTILE; t++) { acc[h][t][0] = 0.0; acc[h][t][1] = 0.0; }
     const int rows = 2 * P;
-    const int nks = (rows + 3) / 4;
-    for (int ks = 0; ks < nks; ks += 2) {
+    const int nfull = rows >> 2;              // k-steps whose 4 rows all exist
+    auto kstep = [&](const int h, const bool guard) {
+        double x[NCB];
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int k = 4 * (ks + h) + kr;
-            double x[NCB];
-#pragma unroll
-            for (int b = 0; b < NCB; b++) {
-                x[b] = (ptr[b] != nullptr && k < rows) ? ptr[b][0] : 0.0;
-                if (ptr[b] != nullptr) ptr[b] += stride[b];
-            }
-            int t = 0;
-#pragma unroll
-            for (int bi = 0; bi < NCB; bi++)
-#pragma unroll
-                for (int bj = bi; bj < NCB; bj++) { dmma_8x8x4(acc[h][t][0], acc[h][t][1], x[bi], x[bj]); t++; }
+        for (int b = 0; b < NCB; b++) {
+            x[b] = guard ? 0.0 : ptr[b][0];
+            ptr[b] += stride[b];
         }
-    }
+        int t = 0;
+#pragma unroll
+        for (int bi = 0; bi < NCB; bi++)
+#pragma unroll
+            for (int bj = bi; bj < NCB; bj++) { dmma_8x8x4(acc[h][t][0], acc[h][t][1], x[bi], x[bj]); t++; }
+    };
+    int ks = 0;
+    for (; ks + 1 < nfull; ks += 2) { kstep(0, false); kstep(1, false); }
+    if (ks < nfull) { kstep(0, false); ks++; }
+    if (rows & 3) kstep(1, kr >= (rows & 3));   // ragged tail: rows beyond 2P contribute zeros
     double *h = st.Hs + (size_t)g * round_up2(LY::NE);
     int t = 0;
 #pragma unroll
@@ -271,6 +274,7 @@ reproj_eval_kernel(const EvalArgs args, const int G, const int PCG)
     const int tid = threadIdx.x;
     const int n_groups = (args.n_img + G - 1) / G;
     const int warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+    if (tid < 2) st.zero[tid] = 0.0;     // visible to everyone after the first __syncthreads below
 
     double intr[K];
 #pragma unroll
