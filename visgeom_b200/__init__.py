@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvisgeom_b200.so")
+_VARIANT = os.environ.get("VG_VARIANT", "")   # developer builds only (see build.py)
+LIB_PATH = os.path.join(_HERE, "libvisgeom_b200%s.so" % ("_" + _VARIANT if _VARIANT else ""))
 
 EUCM, UCM, MEI = 0, 1, 2
 TRANSFORM_DIRECT, TRANSFORM_INVERSE = 0, 1

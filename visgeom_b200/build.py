@@ -11,8 +11,11 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libvisgeom_b200.so")
-OBJ = os.path.join(HERE, "_obj")
+# developer variants (VG_VARIANT=phase: per-phase clock64 counters in the evaluation kernel) build next to
+# the product library and never replace it
+VARIANT = os.environ.get("VG_VARIANT", "")
+LIB = os.path.join(HERE, "libvisgeom_b200%s.so" % ("_" + VARIANT if VARIANT else ""))
+OBJ = os.path.join(HERE, "_obj" + ("_" + VARIANT if VARIANT else ""))
 
 SOURCES = ["vg_eval_eucm.cu", "vg_eval_ucm.cu", "vg_eval_mei.cu", "vg_eval.cu", "vg_api.cu", "vg_solver_kernels.cu",
            "vg_problem.cu"]
@@ -21,6 +24,8 @@ HEADERS = ["vg_math.cuh", "vg_eval.cuh", "vg_eval_impl.cuh", "vg_common.h", "vg_
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++"]
+if VARIANT == "phase":
+    FLAGS.append("-DVG_PHASE_CLOCKS")
 
 
 def _stale(target: str, deps: list[str]) -> bool:

@@ -2,6 +2,7 @@
 // (the kernels themselves: vg_eval_impl.cuh, instantiated per model in vg_eval_{eucm,ucm,mei}.cu).
 #include "vg_eval.cuh"
 
+
 namespace vg {
 
 constexpr int MODEL_EUCM = 0, MODEL_UCM = 1, MODEL_MEI = 2;

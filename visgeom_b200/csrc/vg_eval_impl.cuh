@@ -37,6 +37,17 @@
 
 namespace vg {
 
+#ifdef VG_PHASE_CLOCKS
+// developer build only (VG_VARIANT=phase): clock64 cycles per phase, summed over CTAs, as seen by
+// lane 0 of warp 0 (row 0: a normal-equation warp) and of the last warp (row 1)
+static __device__ unsigned long long g_phase_clocks[2][8];   // per translation unit (no -rdc)
+#define VG_PC_DECL long long pc_t = clock64(); unsigned long long pc_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define VG_PC(i) { const long long pc_n = clock64(); pc_acc[i] += (unsigned long long)(pc_n - pc_t); pc_t = pc_n; }
+#else
+#define VG_PC_DECL
+#define VG_PC(i)
+#endif
+
 struct LaunchPlan { int G, threads, PCG; long long smem; };
 bool plan_eval(int model, int L, int P, LaunchPlan *pl);
 
@@ -285,6 +296,7 @@ reproj_eval_kernel(const EvalArgs args, const int G, const int PCG)
 #pragma unroll
     for (int q = 0; q < LY::NPART; q++) part[q] = 0.0;
 
+    VG_PC_DECL
     for (int j0 = 0; (long long)blockIdx.x + (long long)j0 * gridDim.x < n_groups; j0 += PCG) {
         // ---- phase 0: poses of this CTA's next PCG groups, one thread per image ---------
         if (tid < PCG * G) {
@@ -294,6 +306,7 @@ reproj_eval_kernel(const EvalArgs args, const int G, const int PCG)
             if (grp < n_groups && img < args.n_img) chain_pose<L>(args, (int)img, st.pose + (size_t)tid * LY::POSE);
         }
         __syncthreads();
+        VG_PC(0)
 
         for (int j = 0; j < PCG; j++) {
             const long long grp = (long long)blockIdx.x + (long long)(j0 + j) * gridDim.x;
@@ -365,7 +378,9 @@ reproj_eval_kernel(const EvalArgs args, const int G, const int PCG)
                 }
             }
             fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the TMA engine
+            VG_PC(1)
             __syncthreads();
+            VG_PC(2)
 
             // ---- phase S: stream the Ceres-layout blocks out with TMA bulk copies -------
             bool issued = false;
@@ -384,8 +399,11 @@ reproj_eval_kernel(const EvalArgs args, const int G, const int PCG)
 
             // ---- phase B: per-image normal-equation blocks, one warp per image ------------
             if (args.H) {
+                VG_PC(3)
                 for (int g = warp; g < nv; g += nw) gram_image<MODEL, L>(st, g, lane, P);
+                VG_PC(4)
                 __syncthreads();
+                VG_PC(5)
                 double *Hg = args.H + (size_t)img0 * LY::NE;
 #pragma unroll
                 for (int q = 0; q < LY::NPART; q++) {
@@ -401,10 +419,16 @@ reproj_eval_kernel(const EvalArgs args, const int G, const int PCG)
                     }
                 }
             }
+            VG_PC(6)
             if (issued) bulk_wait_read_all();   // staging must outlive the TMA reads
             __syncthreads();                    // staging + Hs are free for the next group
+            VG_PC(7)
         }
     }
+#ifdef VG_PHASE_CLOCKS
+    if (lane == 0 && (warp == 0 || warp == nw - 1))
+        for (int i = 0; i < 8; i++) atomicAdd(&g_phase_clocks[warp == 0 ? 0 : 1][i], pc_acc[i]);
+#endif
     if (args.H && args.cta_partial) {
 #pragma unroll
         for (int q = 0; q < LY::NPART; q++) {
