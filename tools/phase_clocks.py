@@ -11,7 +11,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import synthdata as sd
 import visgeom_b200 as vg
 
-NAMES = ["0 pose+bar", "A corner", "A barrier", "S tma issue", "B gram", "B barrier", "H out", "tma wait+bar"]
+PHASED = True
+NAMES = [["0 pose+bar", "A corner", "A barrier", "S tma issue", "B gram", "B barrier", "H out", "tma wait+bar"]] * 2 if PHASED else [
+    ["pose", "obs wait", "corners", "tma issue", "gram", "H store", "tma read wait", "-"],
+    ["-", "-", "-", "-", "-", "-", "-", "-"]]
 
 
 def main():
@@ -45,12 +48,12 @@ def main():
         run()
     L.vg_debug_phase_clocks(out, 1)
     v = np.array(list(out), dtype=np.float64).reshape(2, 8) / reps
-    grid = 592
-    for w, nm in ((0, "warp 0 (gram warp)"), (1, "last warp")):
+    grid = 592 if PHASED else 148
+    for w, nm in ((0, "Gram warp 0"), (1, "last warp" if PHASED else "corner warp 0")):
         tot = v[w].sum()
         print(f"{nm}: {tot / grid:9.0f} cycles per CTA")
         for i in range(8):
-            print(f"   {NAMES[i]:14s} {v[w, i] / grid:9.0f} cycles/CTA  {100 * v[w, i] / tot:5.1f}%")
+            print(f"   {NAMES[w][i]:14s} {v[w, i] / grid:9.0f} cycles/CTA  {100 * v[w, i] / tot:5.1f}%")
 
 
 if __name__ == "__main__":

@@ -6,6 +6,12 @@
 namespace vg {
 
 constexpr int MAX_CHAIN = 5;
+constexpr int EVAL_REDUCE_GROUP = 16;
+
+// Tables of the fused shared-block reduction (built on the host once per problem): every entry of the reduced
+// system (A_ij with i <= j, g_i, cost) lists the (dataset, packed entry) sums that feed it.
+struct FinSrc { int off, ne, nb, e; };                       // offset of the dataset's sums, row stride, rows, packed entry
+struct FinOut { int dst0, dst1; double scale; int src_begin, src_end; };   // red[] targets (dst1 = mirror or -1)
 
 // One dataset = one camera + one board + n_img images sharing a transform chain.
 // All pointers are device memory.  Output pointers may be null.
@@ -22,6 +28,18 @@ struct EvalArgs {
     double *Je[MAX_CHAIN];          // n_img x 2P x 6
     double *H;                      // n_img x NE packed normal-equation blocks
     double *cta_partial;            // nullable: gridDim.x x NE, each CTA's sum of its images' blocks
+    // Fused reduction of cta_partial inside the same launch (nullable: the caller reduces cta_partial itself).
+    // The last CTA of every group of EVAL_REDUCE_GROUP rows sums its group into lvl1, the last of those sums lvl1
+    // into ds_sum (both in index order: deterministic); counters return to zero.  If red is set (last dataset of
+    // an evaluation) the same CTA then assembles the reduced system from all datasets' sums (fin_base).
+    unsigned int *tickets;          // 1 + ceil(rows / EVAL_REDUCE_GROUP) counters, zero between launches
+    double *lvl1;                   // ceil(rows / EVAL_REDUCE_GROUP) x NE
+    double *ds_sum;                 // NE
+    const FinOut *fin_outs;
+    const FinSrc *fin_srcs;
+    int n_fin_out;
+    const double *fin_base;         // all datasets' ds_sum regions
+    double *red;
     int n_img;
     int P;
 };

@@ -18,13 +18,13 @@
 //   S. store  : the staged blocks of the G images are contiguous in global memory, so one
 //               elected thread streams each region out with a TMA bulk copy
 //               (cp.async.bulk shared::cta -> global, SASS UBLKCP); no register round trip.
-//   B. normal : the per-image block [J r]^T [J r] is a small dense Gram matrix (2P rows x
-//               K+6L+1 columns): one warp per image runs it on the FP64 MMA path
-//               (mma.sync.m8n8k4.f64, 256 FMAs per instruction, fragments loaded straight
-//               from the staged rows), which removes the cross-lane reduction and ~6x of
-//               the instructions a per-lane FMA formulation needs.  The blocks leave through
-//               coalesced stores; their per-CTA sums (for the shared normal-equation block)
-//               stay in registers until the CTA ends.
+//   B. normal : the per-image block [J r]^T [J r] is a small Gram matrix (2P rows x K+6L+1
+//               columns): one warp per image runs it on the FP64 MMA path (mma.sync.m8n8k4.f64,
+//               256 FMAs per instruction, fragments loaded straight from the staged rows) by row
+//               parity (vg_gram.cuh: the structural zeros of the intrinsic rows are never
+//               multiplied: 2 MMA tiles per k-step for EUCM instead of 3, 3 instead of 6 for MEI).
+//               The group's packed blocks leave with one more TMA bulk copy; their per-CTA sums
+//               (for the shared normal-equation block) stay in registers until the CTA ends.
 // The kernel is HBM-write bound by design (224 B written per EUCM corner).  tcgen05/TMEM are
 // not applicable (no FP64 there); the only matrix-unit use is the legacy FP64 mma.sync above.
 #pragma once
@@ -41,11 +41,19 @@ namespace vg {
 // developer build only (VG_VARIANT=phase): clock64 cycles per phase, summed over CTAs, as seen by
 // lane 0 of warp 0 (row 0: a normal-equation warp) and of the last warp (row 1)
 static __device__ unsigned long long g_phase_clocks[2][8];   // per translation unit (no -rdc)
-#define VG_PC_DECL long long pc_t = clock64(); unsigned long long pc_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#define VG_PC(i) { const long long pc_n = clock64(); pc_acc[i] += (unsigned long long)(pc_n - pc_t); pc_t = pc_n; }
+__device__ __forceinline__ long long vg_clock()
+{
+    long long c;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(c) :: "memory");
+    return c;
+}
+#define VG_PC_DECL long long pc_t = vg_clock(); unsigned long long pc_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define VG_PC(i) { const long long pc_n = vg_clock(); pc_acc[i] += (unsigned long long)(pc_n - pc_t); pc_t = pc_n; }
+#define VG_PC_FLUSH(row) if (lane == 0) for (int i_ = 0; i_ < 8; i_++) atomicAdd(&g_phase_clocks[row][i_], pc_acc[i_]);
 #else
 #define VG_PC_DECL
 #define VG_PC(i)
+#define VG_PC_FLUSH(row)
 #endif
 
 struct LaunchPlan { int G, threads, PCG; long long smem; };
@@ -106,7 +114,10 @@ template <int MODEL, int L> struct Layout {
     // doubles of shared memory: poses of PCG groups + staging of one group of G images + packed blocks
     __host__ __device__ static constexpr long long smem_doubles(int G, int P, int PCG)
     {
-        return 2 + (long long)PCG * G * POSE + (long long)G * 2 * P * (1 + K + 6 * L) + (long long)G * round_up2(NE);
+        // + 64: the ragged last k-step of the Gram loop reads (and discards) up to three corners past an image
+        // ... + the observations of the CTA's next group (G x P x 2)
+        return 2 + (long long)PCG * G * POSE + (long long)G * 2 * P * (1 + K + 6 * L) + round_up2(G * NE) + 64 +
+               (long long)G * 2 * P;
     }
 };
 
@@ -126,7 +137,7 @@ __device__ __forceinline__ void store_row(double *p, const double (&a)[N], bool 
 // Shared-memory view of the staged group
 template <int MODEL, int L> struct Stage {
     using LY = Layout<MODEL, L>;
-    double *pose, *rs, *Jas, *Jes[L], *Hs, *zero;
+    double *pose, *rs, *Jas, *Jes[L], *Hs, *zero, *obuf;
     __device__ Stage(double *base, int G, int P, int PCG)
     {
         zero = base;            base += 2;                 // two zeros for the Gram padding columns
@@ -135,7 +146,8 @@ template <int MODEL, int L> struct Stage {
         Jas = base;             base += (size_t)G * 2 * P * LY::K;
 #pragma unroll
         for (int e = 0; e < L; e++) { Jes[e] = base; base += (size_t)G * 2 * P * 6; }
-        Hs = base;
+        Hs = base;              base += round_up2(G * LY::NE) + 64;
+        obuf = base;
     }
 };
 
@@ -144,6 +156,23 @@ __device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, const double 
 {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+}  // namespace
+}  // namespace vg
+#include "vg_gram.cuh"
+namespace vg {
+namespace {
+
+// Which Gram formulation an instantiation uses: the row-parity one when it saves at least two MMA tiles per
+// k-step over the dense one (MEI: 3 instead of 6), else the dense one (fewer fragment loads per k-step).
+#ifndef VG_GRAM_MODE
+#define VG_GRAM_MODE -1
+#endif
+template <int MODEL, int L> __host__ __device__ constexpr bool use_parity_gram()
+{
+    constexpr int dense = Layout<MODEL, L>::NCB * (Layout<MODEL, L>::NCB + 1) / 2;
+    return VG_GRAM_MODE < 0 ? dense - ParityGram<MODEL, L>::NTILE >= 2 : VG_GRAM_MODE > 0;
 }
 
 // ---- phase B: Gram matrix of one image's staged rows, one warp ------------------------------
@@ -199,7 +228,7 @@ __device__ __forceinline__ void gram_image(const Stage<MODEL, L> &st, const int 
     for (; ks + 1 < nfull; ks += 2) { kstep(0, false); kstep(1, false); }
     if (ks < nfull) { kstep(0, false); ks++; }
     if (rows & 3) kstep(1, kr >= (rows & 3));   // ragged tail: rows beyond 2P contribute zeros
-    double *h = st.Hs + (size_t)g * round_up2(LY::NE);
+    double *h = st.Hs + (size_t)g * LY::NE;
     int t = 0;
 #pragma unroll
     for (int bi = 0; bi < NCB; bi++)
@@ -269,6 +298,66 @@ __device__ __forceinline__ void chain_pose(const EvalArgs &args, const int img, 
     for (int i = 0; i < 3; i++) ps[9 + i] = tacc[i];
 }
 
+// ---- tail: fold the per-CTA block sums into the dataset's sum and (last dataset) the reduced system ----
+// Two-level "last CTA done" tree over the rows of cta_partial; every level adds its rows in index order, so the
+// result does not depend on which CTA happens to arrive last.  Replaces the separate reduction launch the
+// normal-equation build would otherwise need after every evaluation.
+// sum of p[r * stride], r in [r0, r1), added in index order; the (L2) loads of 16 rows are in flight together
+__device__ __forceinline__ double sum_rows_in_order(const double *p, const int stride, const int r0, const int r1)
+{
+    double s = 0.0;
+    for (int b = r0; b < r1; b += EVAL_REDUCE_GROUP) {
+        double v[EVAL_REDUCE_GROUP];
+#pragma unroll
+        for (int i = 0; i < EVAL_REDUCE_GROUP; i++) v[i] = b + i < r1 ? __ldcg(p + (size_t)(b + i) * stride) : 0.0;
+#pragma unroll
+        for (int i = 0; i < EVAL_REDUCE_GROUP; i++) s += v[i];
+    }
+    return s;
+}
+
+template <int NE>
+__device__ __forceinline__ void fused_reduce(const EvalArgs &args)
+{
+    __shared__ int s_last;
+    const int tid = threadIdx.x, rows = gridDim.x;
+    const int ngrp = (rows + EVAL_REDUCE_GROUP - 1) / EVAL_REDUCE_GROUP, grp = blockIdx.x / EVAL_REDUCE_GROUP;
+    const int r0 = grp * EVAL_REDUCE_GROUP, r1 = min(rows, r0 + EVAL_REDUCE_GROUP);
+    __threadfence();                       // this thread's part of the CTA's row is visible device-wide
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(args.tickets + 1 + grp, 1u) == (unsigned)(r1 - r0 - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int e = tid; e < NE; e += blockDim.x)
+        args.lvl1[(size_t)grp * NE + e] = sum_rows_in_order(args.cta_partial + e, NE, r0, r1);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        args.tickets[1 + grp] = 0;
+        s_last = atomicAdd(args.tickets, 1u) == (unsigned)(ngrp - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int e = tid; e < NE; e += blockDim.x) args.ds_sum[e] = sum_rows_in_order(args.lvl1 + e, NE, 0, ngrp);
+    if (tid == 0) args.tickets[0] = 0;
+    if (!args.red) return;
+    __threadfence();
+    __syncthreads();                       // this dataset's sums are complete; the earlier datasets' launches are
+    for (int o = tid; o < args.n_fin_out; o += blockDim.x) {
+        const FinOut f = args.fin_outs[o];
+        double v = 0.0;
+        for (int si = f.src_begin; si < f.src_end; si++) {
+            const FinSrc sr = args.fin_srcs[si];
+            v += __ldcg(args.fin_base + (size_t)sr.off + sr.e);
+        }
+        v *= f.scale;
+        args.red[f.dst0] = v;
+        if (f.dst1 >= 0) args.red[f.dst1] = v;
+    }
+}
+
 // ---- the kernel -------------------------------------------------------------------
 // PCG = groups whose poses one prologue pass stages (PCG * G <= blockDim.x).
 template <int MODEL, int L>
@@ -278,14 +367,16 @@ reproj_eval_kernel(const EvalArgs args, const int G, const int PCG)
     using LY = Layout<MODEL, L>;
     using CAM = Camera<MODEL>;
     constexpr int K = LY::K;
-    constexpr int NEP = round_up2(LY::NE);
     extern __shared__ __align__(16) double smem[];
     const int P = args.P;
     const Stage<MODEL, L> st(smem, G, P, PCG);
     const int tid = threadIdx.x;
     const int n_groups = (args.n_img + G - 1) / G;
-    const int warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
-    if (tid < 2) st.zero[tid] = 0.0;     // visible to everyone after the first __syncthreads below
+    // the warp index through a shuffle: provably warp-uniform (uniform datapath for the TMA operands)
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31, nw = blockDim.x >> 5;
+    if (tid < 2) st.zero[tid] = 0.0;
+    GramMap<MODEL, L> gmap;
+    if constexpr (use_parity_gram<MODEL, L>()) gram_map_init<MODEL, L>(gmap, lane);     // visible to everyone after the first __syncthreads below
 
     double intr[K];
 #pragma unroll
@@ -296,6 +387,18 @@ reproj_eval_kernel(const EvalArgs args, const int G, const int PCG)
 #pragma unroll
     for (int q = 0; q < LY::NPART; q++) part[q] = 0.0;
 
+    // Observations are fetched one group ahead into shared memory (cp.async, every thread the element it will
+    // itself consume): under the kernel's own store stream a global read takes longer than a corner pass.
+    auto fetch_obs = [&](const long long grp) {
+        if (grp < n_groups) {
+            const int i0 = (int)grp * G, n = min(G, args.n_img - i0) * P;
+            for (int idx = tid; idx < n; idx += blockDim.x)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(smem_u32(st.obuf + 2 * idx)),
+                             "l"(args.obs + ((size_t)i0 * P + idx) * 2) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    fetch_obs(blockIdx.x);
     VG_PC_DECL
     for (int j0 = 0; (long long)blockIdx.x + (long long)j0 * gridDim.x < n_groups; j0 += PCG) {
         // ---- phase 0: poses of this CTA's next PCG groups, one thread per image ---------
@@ -316,14 +419,11 @@ reproj_eval_kernel(const EvalArgs args, const int G, const int PCG)
             const double *pose_grp = st.pose + (size_t)j * G * LY::POSE;
 
             // ---- phase A: one thread per (image, corner) -------------------------------
+            asm volatile("cp.async.wait_group 0;" ::: "memory");     // this thread's own observations have landed
             for (int idx = tid; idx < nv * P; idx += blockDim.x) {
                 const int g = idx / P;
                 const int c = idx - g * P;
-                const int img = img0 + g;
-                // issue the (streaming) observation load first: its latency hides behind the model math
-                double2 ob;
-                asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];"
-                             : "=d"(ob.x), "=d"(ob.y) : "l"(args.obs + ((size_t)img * P + c) * 2));
+                const double2 ob = *reinterpret_cast<const double2 *>(st.obuf + 2 * idx);
                 const double *ps = pose_grp + (size_t)g * LY::POSE;
                 const double bx = __ldg(args.board + 3 * c), by = __ldg(args.board + 3 * c + 1),
                              bz = __ldg(args.board + 3 * c + 2);
@@ -377,6 +477,7 @@ reproj_eval_kernel(const EvalArgs args, const int G, const int PCG)
                     store_row<6>(st.Jes[e] + (row + 1) * 6, jv, true);
                 }
             }
+            fetch_obs(grp + gridDim.x);  // the next group's observations, into the elements just consumed
             fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the TMA engine
             VG_PC(1)
             __syncthreads();
@@ -400,19 +501,36 @@ reproj_eval_kernel(const EvalArgs args, const int G, const int PCG)
             // ---- phase B: per-image normal-equation blocks, one warp per image ------------
             if (args.H) {
                 VG_PC(3)
-                for (int g = warp; g < nv; g += nw) gram_image<MODEL, L>(st, g, lane, P);
+                for (int g = warp; g < nv; g += nw) {
+                    const double *Jes_g[L];
+#pragma unroll
+                    for (int e = 0; e < L; e++) Jes_g[e] = st.Jes[e] + (size_t)g * 2 * P * 6;
+                    if constexpr (use_parity_gram<MODEL, L>()) {
+                        GramFrag<MODEL, L> v;
+                        gram_slot_parity<MODEL, L>(st.rs + (size_t)g * 2 * P, st.Jas + (size_t)g * 2 * P * K, Jes_g, st.zero, lane, P, v);
+                        gram_frag_emit<MODEL, L>(v, gmap, st.Hs + (size_t)g * LY::NE, lane);
+                    } else {
+                        gram_image<MODEL, L>(st, g, lane, P);
+                    }
+                }
+                fence_proxy_async_smem();
                 VG_PC(4)
                 __syncthreads();
                 VG_PC(5)
+                // the group's packed blocks are contiguous in global memory: one more bulk copy (a ragged last
+                // group, whose byte count may not be a multiple of 16, goes through ordinary stores)
                 double *Hg = args.H + (size_t)img0 * LY::NE;
+                const size_t hbytes = (size_t)nv * LY::NE * 8;
+                const bool h_bulk = (hbytes & 15) == 0 && ((reinterpret_cast<uintptr_t>(Hg) & 15) == 0);
+                if (h_bulk && tid == 0) { bulk_store(Hg, st.Hs, (uint32_t)hbytes); bulk_commit(); issued = true; }
 #pragma unroll
                 for (int q = 0; q < LY::NPART; q++) {
                     const int e = tid + q * blockDim.x;
                     if (e < LY::NE) {
                         double sum = 0.0;
                         for (int g = 0; g < nv; g++) {
-                            const double val = st.Hs[(size_t)g * NEP + e];
-                            Hg[(size_t)g * LY::NE + e] = val;
+                            const double val = st.Hs[(size_t)g * LY::NE + e];
+                            if (!h_bulk) Hg[(size_t)g * LY::NE + e] = val;
                             sum += val;
                         }
                         part[q] += sum;
@@ -435,6 +553,7 @@ reproj_eval_kernel(const EvalArgs args, const int G, const int PCG)
             const int e = tid + q * blockDim.x;
             if (e < LY::NE) args.cta_partial[(size_t)blockIdx.x * LY::NE + e] = part[q];
         }
+        if (args.tickets) fused_reduce<LY::NE>(args);
     }
 }
 
@@ -473,6 +592,7 @@ cudaError_t launch_one(const EvalArgs &args, cudaStream_t stream, unsigned long 
     if (launches) (*launches)++;
     return cudaGetLastError();
 }
+
 
 template <int MODEL>
 cudaError_t launch_model(int L, const EvalArgs &a, cudaStream_t s, unsigned long long *n, int *grid, bool q)

@@ -119,6 +119,11 @@ struct vg_problem {
     double **d_seq_ptr[2] = {nullptr, nullptr};
     double *d_scale = nullptr, *d_ws = nullptr, *d_partial = nullptr, *d_red = nullptr, *d_delta = nullptr;
     double *d_cta_partial = nullptr;
+    // fused reduction (vg_eval.cuh): per dataset its tickets / level-1 rows, all datasets' sums, table offsets
+    unsigned int *d_tickets = nullptr;
+    double *d_lvl1 = nullptr, *d_ds_sum = nullptr;
+    std::vector<int> h_ticket_off, h_lvl1_off, h_sum_off;
+    int last_ds = -1;                           // the last dataset with images: its launch assembles d_red
     size_t partial_doubles = 0, cta_partial_doubles = 0;
     double *h_red = nullptr;                  // pinned
     double *h_up = nullptr;                   // pinned upload staging: [slab | delta_a]
@@ -137,7 +142,7 @@ void free_prepared(vg_problem *p)
     auto F = [](auto *&ptr) { if (ptr) { cudaFree(ptr); ptr = nullptr; } };
     for (int s = 0; s < 2; s++) { F(p->d_slab[s]); F(p->d_desc[s]); F(p->d_seq_ptr[s]); }
     F(p->d_pose_start); F(p->d_contrib_ds); F(p->d_contrib_img); F(p->d_pose_seq); F(p->d_pose_local);
-    F(p->d_fail); F(p->d_fin_out); F(p->d_fin_src); F(p->d_cta_partial); F(p->d_scale); F(p->d_ws); F(p->d_partial); F(p->d_red); F(p->d_delta);
+    F(p->d_fail); F(p->d_fin_out); F(p->d_fin_src); F(p->d_cta_partial); F(p->d_tickets); F(p->d_lvl1); F(p->d_ds_sum); F(p->d_scale); F(p->d_ws); F(p->d_partial); F(p->d_red); F(p->d_delta);
     if (p->h_red) { cudaFreeHost(p->h_red); p->h_red = nullptr; }
     if (p->h_up) { cudaFreeHost(p->h_up); p->h_up = nullptr; }
     for (auto &d : p->dss)
@@ -250,10 +255,30 @@ int prepare(vg_problem *p)
     std::vector<int> grids(p->dss.size() + 1, 0);
     for (size_t k = 0; k < p->dss.size(); k++)
         VG_CUDA(eval_grid_size(p->cams[p->dss[k].cam].model, p->dss[k].L, p->dss[k].n_img, p->dss[k].P, &grids[k]));
+    // cta_partial regions (one row per persistent CTA), tickets and level-1 rows of every dataset
+    const int n_ds = (int)p->dss.size();
+    p->h_acc_tab.assign(n_ds + 1, 0); p->h_ticket_off.assign(n_ds + 1, 0); p->h_lvl1_off.assign(n_ds + 1, 0);
+    p->last_ds = -1;
+    for (int k = 0; k < n_ds; k++) {
+        const int ne = p->h_desc[0][k].ne;
+        const int ngrp = (grids[k] + EVAL_REDUCE_GROUP - 1) / EVAL_REDUCE_GROUP;
+        p->h_acc_tab[k + 1] = p->h_acc_tab[k] + grids[k] * ne;
+        p->h_ticket_off[k + 1] = p->h_ticket_off[k] + 1 + ngrp;
+        p->h_lvl1_off[k + 1] = p->h_lvl1_off[k] + ngrp * ne;
+        if (p->dss[k].n_img > 0) p->last_ds = k;
+    }
+    p->cta_partial_doubles = (size_t)p->h_acc_tab[n_ds] + 8;
+    // the reduced system is assembled from one row of sums per dataset
+    std::vector<int> one_row(n_ds + 1, 1);
     std::vector<FinOut> fin_out;
     std::vector<FinSrc> fin_src;
-    build_finalize_tables(p->h_desc[0].data(), grids.data(), (int)p->dss.size(), Ks, p->h_acc_tab, fin_out, fin_src,
-                          &p->cta_partial_doubles);
+    size_t sum_doubles = 0;
+    build_finalize_tables(p->h_desc[0].data(), one_row.data(), n_ds, Ks, p->h_sum_off, fin_out, fin_src, &sum_doubles);
+    VG_CUDA(cudaMalloc(&p->d_tickets, sizeof(unsigned int) * (p->h_ticket_off[n_ds] + 1)));
+    VG_CUDA(cudaMemset(p->d_tickets, 0, sizeof(unsigned int) * (p->h_ticket_off[n_ds] + 1)));
+    VG_CUDA(cudaMalloc(&p->d_lvl1, sizeof(double) * (p->h_lvl1_off[n_ds] + 1)));
+    VG_CUDA(cudaMalloc(&p->d_ds_sum, sizeof(double) * sum_doubles));
+    VG_CUDA(cudaMemset(p->d_ds_sum, 0, sizeof(double) * sum_doubles));
     p->n_fin_out = (int)fin_out.size();
     VG_CUDA(cudaMalloc(&p->d_fin_out, sizeof(FinOut) * (fin_out.size() + 1)));
     VG_CUDA(cudaMalloc(&p->d_fin_src, sizeof(FinSrc) * (fin_src.size() + 1)));
@@ -306,15 +331,20 @@ int evaluate_set(vg_problem *p, int s, bool timed)
         a.r = p->materialize ? d.d_r : nullptr;
         a.Ja = p->materialize ? d.d_Ja : nullptr;
         a.H = d.d_H[s];
-        a.cta_partial = p->d_cta_partial + p->h_acc_tab[&d - p->dss.data()];
+        const int k = (int)(&d - p->dss.data());
+        a.cta_partial = p->d_cta_partial + p->h_acc_tab[k];
+        a.tickets = p->d_tickets + p->h_ticket_off[k];
+        a.lvl1 = p->d_lvl1 + p->h_lvl1_off[k];
+        a.ds_sum = p->d_ds_sum + p->h_sum_off[k];
+        if (k == p->last_ds) {      // the shared-block reduction -> d_red segment E is the tail of this launch
+            a.fin_outs = p->d_fin_out; a.fin_srcs = p->d_fin_src; a.n_fin_out = p->n_fin_out;
+            a.fin_base = p->d_ds_sum; a.red = p->d_red;
+        }
         a.n_img = d.n_img; a.P = d.P;
         cudaError_t e = launch_eval(p->cams[d.cam].model, d.L, a, p->stream, &launch_counter());
         if (e != cudaSuccess) return fail_cuda(e, "reproj_eval_kernel launch");
     }
     if (timed) VG_CUDA(cudaEventRecord(p->ev1, p->stream));
-    SolverLaunch sl{p->stream, &launch_counter()};
-    cudaError_t e = launch_finalize_shared(p->d_fin_out, p->d_fin_src, p->n_fin_out, p->d_cta_partial, p->d_red, sl);
-    if (e != cudaSuccess) return fail_cuda(e, "finalize_shared");
     p->n_eval++;
     return VG_OK;
 }

@@ -17,50 +17,6 @@ constexpr int POSE_THREADS = 128;
 constexpr int GRAM_POSES = 64;       // poses per block in gram_reduce
 constexpr int GRAM_THREADS = 224;    // >= Ks(Ks+1)/2 + Ks for Ks <= 18; larger Ks loops
 
-// ---- A, g_a, cost: fold the per-CTA block sums of the evaluation kernel -------------------
-// The fused evaluation kernel leaves one row of block sums per persistent CTA and dataset.  A
-// host-built table lists, for every entry of the reduced system (A_ij with i <= j, g_i, cost), the
-// (dataset, packed entry) sources that feed it.  One block per FIN_OUT outputs: every thread owns
-// CTA rows (one per thread in practice) and keeps FIN_OUT independent loads in flight -- the kernel
-// is pure memory latency -- then a fixed shuffle / shared-memory tree.  Deterministic.
-__global__ void __launch_bounds__(FIN_THREADS)
-finalize_shared_kernel(const FinOut *outs, const FinSrc *srcs, int n_out, const double *partial, double *red)
-{
-    __shared__ double wsum[FIN_THREADS / 32][FIN_OUT];
-    __shared__ FinOut so[FIN_OUT];
-    const int o0 = blockIdx.x * FIN_OUT;
-    if (threadIdx.x < FIN_OUT && o0 + threadIdx.x < n_out) so[threadIdx.x] = outs[o0 + threadIdx.x];
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    double v[FIN_OUT];
-#pragma unroll
-    for (int q = 0; q < FIN_OUT; q++) {
-        v[q] = 0.0;
-        if (o0 + q < n_out) {
-            for (int si = so[q].src_begin; si < so[q].src_end; si++) {
-                const FinSrc sr = srcs[si];
-                for (int row = threadIdx.x; row < sr.nb; row += blockDim.x)
-                    v[q] += partial[(size_t)sr.off + (size_t)row * sr.ne + sr.e];
-            }
-        }
-    }
-#pragma unroll
-    for (int q = 0; q < FIN_OUT; q++) {
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], off);
-        if (lane == 0) wsum[warp][q] = v[q];
-    }
-    __syncthreads();
-    if (threadIdx.x < FIN_OUT && o0 + threadIdx.x < n_out) {
-        const int q = threadIdx.x;
-        double t = 0.0;
-        for (int w = 0; w < nw; w++) t += wsum[w][q];
-        t *= so[q].scale;
-        red[so[q].dst0] = t;
-        if (so[q].dst1 >= 0) red[so[q].dst1] = t;
-    }
-}
-
 // ---- per-pose factorisation ------------------------------------------------------------
 // lower-triangular packed index (i >= j)
 __device__ __forceinline__ constexpr int lt(int i, int j) { return i * (i + 1) / 2 + j; }
@@ -313,7 +269,8 @@ __global__ void finalize_backsub_kernel(int Ks, int n_blocks, const double *part
 
 }  // namespace
 
-// Host side of finalize_shared: offsets of each dataset's cta_partial region and the output table.
+// Tables of the shared-block reduction (fused into the evaluation kernel): offsets of each dataset's sums
+// region and, per entry of the reduced system, its sources.
 void build_finalize_tables(const DatasetDesc *h_desc, const int *grids, int n_ds, int Ks, std::vector<int> &offsets,
                            std::vector<FinOut> &outs, std::vector<FinSrc> &srcs, size_t *partial_doubles)
 {
@@ -358,15 +315,6 @@ void build_finalize_tables(const DatasetDesc *h_desc, const int *grids, int n_ds
     for (auto &x : per[o]) srcs.push_back(x);
     f.src_end = (int)srcs.size();
     outs.push_back(f);
-}
-
-cudaError_t launch_finalize_shared(const FinOut *d_outs, const FinSrc *d_srcs, int n_out, const double *partial,
-                                   double *red, SolverLaunch sl)
-{
-    const int blocks = (n_out + FIN_OUT - 1) / FIN_OUT;
-    finalize_shared_kernel<<<blocks, FIN_THREADS, 0, sl.stream>>>(d_outs, d_srcs, n_out, partial, red);
-    if (sl.launches) (*sl.launches)++;
-    return cudaGetLastError();
 }
 
 size_t pose_scratch(int n_pose, int Ks)

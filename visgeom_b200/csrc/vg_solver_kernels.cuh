@@ -6,14 +6,15 @@
 // free intrinsics + free global transforms, Ks columns) plus one independent 6x6
 // block per free sequence pose.  Per evaluation the fused kernel (vg_eval.cu) leaves
 // one packed [J r]^T [J r] block per image; the kernels here
-//   finalize_shared   : fold the per-CTA block sums the evaluation kernel leaves into
-//                       A (Ks x Ks), g_a, cost (shared x shared / shared x residual / residual^2)
+//   (the fold of the evaluation kernel's per-CTA block sums into A (Ks x Ks), g_a and the cost is fused into
+//    that kernel's tail, vg_eval_impl.cuh: fused_reduce)
 //   pose_factor       : per pose gather C (6x6), E (Ks x 6), b; damp, Cholesky,
 //                       Z = L^-1 E^T, z = L^-1 b
 //   gram_reduce       : S_red = sum Z^T Z, v_red = sum Z^T z  (the Schur complement terms)
 //   pose_backsub      : delta_p = -L^-T (z + Z delta_a), candidate poses, model-decrease
 //                       and step-norm partial sums
 #pragma once
+#include "vg_eval.cuh"
 
 #include <cuda_runtime.h>
 
@@ -75,17 +76,10 @@ struct SolverLaunch {
     unsigned long long *launches;
 };
 
-// A, g_a, cost of all datasets -> red[A..cost]; partial is scratch of >= blocks*MAX_NE doubles
-// finalize_shared tables (built on the host once per problem)
-constexpr int FIN_THREADS = 640;
-constexpr int FIN_OUT = 8;
-struct FinSrc { int off, ne, nb, e; };                       // cta_partial offset, row stride, rows, packed entry
-struct FinOut { int dst0, dst1; double scale; int src_begin, src_end; };   // red[] targets (dst1 = mirror or -1)
-// grids[ds] = persistent CTAs of dataset ds' evaluation kernel = rows of its cta_partial region
-void build_finalize_tables(const DatasetDesc *h_desc, const int *grids, int n_ds, int Ks, std::vector<int> &offsets,
-                           std::vector<FinOut> &outs, std::vector<FinSrc> &srcs, size_t *partial_doubles);
-cudaError_t launch_finalize_shared(const FinOut *d_outs, const FinSrc *d_srcs, int n_out, const double *partial,
-                                   double *red, SolverLaunch sl);
+// Tables of the shared-block reduction fused into the evaluation kernel (vg_eval.cuh: FinOut / FinSrc).
+// rows[ds] = rows of dataset ds' sums region (1: the kernel leaves one reduced row per dataset)
+void build_finalize_tables(const DatasetDesc *h_desc, const int *rows, int n_ds, int Ks, std::vector<int> &offsets,
+                           std::vector<FinOut> &outs, std::vector<FinSrc> &srcs, size_t *sum_doubles);
 
 // per-pose factorisation + Schur terms -> ws, red[S,v], red[gmax]
 cudaError_t launch_pose_schur(const DatasetDesc *d_desc, int n_pose, int Ks,
