@@ -186,6 +186,26 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------------
+def lm_leg(make_problem, d, model_id, max_iter, threads=None):
+    """LM iterations/s (BASELINE.json's second metric) of one solve from the perturbed initial guess:
+    make_problem() -> an object with the visgeom_b200.Problem interface (the CUDA engine, or the oracle's
+    restatement of the Ceres trust-region loop on the host cores)."""
+    Pm = make_problem()
+    cam = Pm.add_camera(model_id, d["intr_init"])
+    tr = Pm.add_transform(d["xi_init"], is_global=False)
+    Pm.add_dataset(cam, d["board"], d["obs"], [tr], [0])
+    o = Pm.default_options() if hasattr(Pm, "default_options") else Pm.o.default_options()
+    o.max_num_iterations = max_iter
+    if threads is not None and hasattr(o, "threads"):
+        o.threads = threads
+    Pm.evaluate()            # device buffers allocated and inputs uploaded before the clock starts
+    t0 = time.perf_counter()
+    sm = Pm.solve(o)
+    dt = time.perf_counter() - t0
+    return dict(iterations=int(sm.iterations), seconds=dt, iters_per_s=sm.iterations / dt if dt > 0 else None,
+                final_cost=float(sm.final_cost), intrinsics=[float(x) for x in Pm.camera(cam)])
+
+
 class DevView:
     """__cuda_array_interface__ view of a raw device pointer (for torch.distributed)."""
     def __init__(self, ptr, n):
@@ -361,6 +381,14 @@ def run_ours(args):
             vg.eval_chain(model_id, d["intr_init"], d["board"], d["obs"], xs, [0], [0], want_H=True)
         full_value = n_img * P * reps / (time.perf_counter() - t0)
 
+    # ---- LM iterations/s: one vg_problem_solve of the whole C2 problem (host inputs, parameters back) --------
+    lm = None
+    if rank == 0 and world == 1:
+        lm_leg(lambda: vg.Problem(local), d, model_id, 3)          # warm-up (allocations, first launches)
+        t_w0 = time.time()
+        lm = lm_leg(lambda: vg.Problem(local), d, model_id, 25)
+        windows.append((t_w0, time.time()))
+
     sampler.stop()
     clocks = sampler.summary(windows)
     total_launches = vg.launch_count() - launches0
@@ -374,6 +402,16 @@ def run_ours(args):
         one = cpu_reference_leg(d, model_id, min(n_img, 2000), 3, 1, threads=1)
         cpu = {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": res["kind"], "sample": res["sample"],
                "single_thread_value": one["value"]}
+        # the same LM loop restated on the host (oracle/oracle_lm.c; Ceres itself is absent), on a bounded sample
+        from oracle import pyoracle
+        orc = pyoracle.Oracle()
+        n_lm = min(n_img, 2000)
+        d_lm = {k: (v[:n_lm] if k in ("obs", "xi_init") else v) for k, v in d.items()}
+        cpu_lm = lm_leg(lambda: pyoracle.OracleProblem(orc), d_lm, model_id, 4, threads=orc.max_threads())
+        cpu["lm"] = {"iters_per_s": cpu_lm["iters_per_s"], "images": n_lm, "iterations": cpu_lm["iterations"],
+                     "cores": orc.max_threads(),
+                     "iters_per_s_scaled_to_workload": cpu_lm["iters_per_s"] * n_lm / n_img if cpu_lm["iters_per_s"] else None,
+                     "kind": "port", "what": "oracle LM (restated Ceres trust-region loop), OpenMP evaluation"}
 
     if rank == 0:
         line = {
@@ -395,6 +433,11 @@ def run_ours(args):
                     "what": "vg_problem_* with pinned host inputs every step; result = cost + reduced normal equations"},
             "e2e_ceres_contract": {"value": full_value, "unit": UNIT,
                                    "what": "vg_eval_chain with host buffers: r, J_intr, J_pose and H copied back (PCIe bound)"},
+            "lm": None if lm is None else {"iters_per_s": lm["iters_per_s"], "iterations": lm["iterations"], "seconds": lm["seconds"],
+                                           "final_cost": lm["final_cost"], "intrinsics": lm["intrinsics"],
+                                           "what": "vg_problem_solve on the same workload from the perturbed initial guess "
+                                                   "(one LM iteration = evaluation + per-pose Schur elimination + shared solve + "
+                                                   "back-substitution + candidate evaluation)"},
             "gpu_launches": int(round(launches_per_step * args.steps)), "gpu_launches_per_step": launches_per_step,
             "gpu_launches_total": int(total_launches),
             "clocks": clocks,

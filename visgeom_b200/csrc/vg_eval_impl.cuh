@@ -316,6 +316,15 @@ __device__ __forceinline__ double sum_rows_in_order(const double *p, const int s
     return s;
 }
 
+// ticket with release + acquire ordering at device scope: the CTA barrier before it orders the other threads'
+// writes before this thread's release (cumulativity), the one after it their reads after the acquire
+__device__ __forceinline__ unsigned int take_ticket(unsigned int *counter)
+{
+    unsigned int old;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(counter) : "memory");
+    return old;
+}
+
 template <int NE>
 __device__ __forceinline__ void fused_reduce(const EvalArgs &args)
 {
@@ -323,23 +332,19 @@ __device__ __forceinline__ void fused_reduce(const EvalArgs &args)
     const int tid = threadIdx.x, rows = gridDim.x;
     const int ngrp = (rows + EVAL_REDUCE_GROUP - 1) / EVAL_REDUCE_GROUP, grp = blockIdx.x / EVAL_REDUCE_GROUP;
     const int r0 = grp * EVAL_REDUCE_GROUP, r1 = min(rows, r0 + EVAL_REDUCE_GROUP);
-    __threadfence();                       // this thread's part of the CTA's row is visible device-wide
-    __syncthreads();
-    if (tid == 0) s_last = atomicAdd(args.tickets + 1 + grp, 1u) == (unsigned)(r1 - r0 - 1);
+    __syncthreads();                       // the CTA's row of cta_partial is written
+    if (tid == 0) s_last = take_ticket(args.tickets + 1 + grp) == (unsigned)(r1 - r0 - 1);
     __syncthreads();
     if (!s_last) return;
-    __threadfence();
     for (int e = tid; e < NE; e += blockDim.x)
         args.lvl1[(size_t)grp * NE + e] = sum_rows_in_order(args.cta_partial + e, NE, r0, r1);
-    __threadfence();
     __syncthreads();
     if (tid == 0) {
         args.tickets[1 + grp] = 0;
-        s_last = atomicAdd(args.tickets, 1u) == (unsigned)(ngrp - 1);
+        s_last = take_ticket(args.tickets) == (unsigned)(ngrp - 1);
     }
     __syncthreads();
     if (!s_last) return;
-    __threadfence();
     for (int e = tid; e < NE; e += blockDim.x) args.ds_sum[e] = sum_rows_in_order(args.lvl1 + e, NE, 0, ngrp);
     if (tid == 0) args.tickets[0] = 0;
     if (!args.red) return;
