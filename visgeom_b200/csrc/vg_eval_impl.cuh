@@ -111,12 +111,19 @@ template <int MODEL, int L> struct Layout {
     static constexpr int NCB = (W + 7) / 8;       // 8-column blocks of the Gram matrix
     static constexpr int POSE = round_up2(12 + 21 * L);
     static constexpr int NPART = (NE + 95) / 96;  // per-thread slots of the per-CTA block sums
+    // per-lane output map of the parity Gram fragments: (iu, iv) per fragment element, bytes when they fit
+    using map_t = std::conditional_t<(NE <= 127), char2, short2>;
+    static constexpr int PNB = (K - 4 + 3 + 6 * L + 7) / 8;                   // 8-column blocks of the parity Gram
+    static constexpr int MAPD = (PNB * (PNB + 1) / 2 * 2 * 32 * (int)sizeof(map_t) + 7) / 8;   // doubles (upper bound)
+    static constexpr int TAIL = 64 > MAPD ? 64 : MAPD;
     // doubles of shared memory: poses of PCG groups + staging of one group of G images + packed blocks
     __host__ __device__ static constexpr long long smem_doubles(int G, int P, int PCG)
     {
-        // + 64: the ragged last k-step of the Gram loop reads (and discards) up to three corners past an image
+        // + TAIL: the per-lane output map of the Gram fragments (vg_gram.cuh: GramMap as short2 per element and
+        //   lane); the ragged last k-step of the Gram loop also reads (and discards) up to three corners past the
+        //   last image, into this area
         // ... + the observations of the CTA's next group (G x P x 2)
-        return 2 + (long long)PCG * G * POSE + (long long)G * 2 * P * (1 + K + 6 * L) + round_up2(G * NE) + 64 +
+        return 2 + (long long)PCG * G * POSE + (long long)G * 2 * P * (1 + K + 6 * L) + 2 + round_up2(G * NE) + TAIL +
                (long long)G * 2 * P;
     }
 };
@@ -138,15 +145,20 @@ __device__ __forceinline__ void store_row(double *p, const double (&a)[N], bool 
 template <int MODEL, int L> struct Stage {
     using LY = Layout<MODEL, L>;
     double *pose, *rs, *Jas, *Jes[L], *Hs, *zero, *obuf;
+    typename LY::map_t *map;
     __device__ Stage(double *base, int G, int P, int PCG)
     {
         zero = base;            base += 2;                 // two zeros for the Gram padding columns
         pose = base;            base += (size_t)PCG * G * LY::POSE;
         rs = base;              base += (size_t)G * 2 * P;
         Jas = base;             base += (size_t)G * 2 * P * LY::K;
+        // the chain blocks start 2 (mod 4) doubles after the intrinsic block: Gram fragment loads that mix both
+        // (vg_eval_impl.cuh: gram_image) then fall into distinct banks
+        base += ((size_t)G * 2 * P * LY::K) % 4 == 0 ? 2 : 0;
 #pragma unroll
         for (int e = 0; e < L; e++) { Jes[e] = base; base += (size_t)G * 2 * P * 6; }
-        Hs = base;              base += round_up2(G * LY::NE) + 64;
+        Hs = base;              base += round_up2(G * LY::NE);
+        map = reinterpret_cast<typename LY::map_t *>(base);     base += LY::TAIL;
         obuf = base;
     }
 };
@@ -185,49 +197,66 @@ __device__ __forceinline__ void gram_image(const Stage<MODEL, L> &st, const int 
     using LY = Layout<MODEL, L>;
     constexpr int K = LY::K, D = LY::D, W = LY::W, NCB = LY::NCB, NTILE = NCB * (NCB + 1) / 2;
     const int kr = lane & 3, ci = lane >> 2;
-    // per 8-column block: this lane's source pointer and its increment per k-step (4 rows); padding
-    // columns read a zero slot with increment 0, so the inner loop has no selects
+    // A k-step takes four rows of one parity (the u-rows, then the v-rows, of four consecutive corners): with the
+    // rows 16 K or 96 bytes apart the fragment loads of a half-warp then fall into distinct shared-memory banks
+    // (rows 4s..4s+3 would put lanes kr = 0 and kr = 3 on the same ones).
+    // Per 8-column block: this lane's source pointer (u-row of corner kr), the offset of the v-row below it and
+    // the increment per pair of k-steps (8 rows); padding columns read a zero slot with increment 0.
     const double *ptr[NCB];
-    int stride[NCB];
+    int dv[NCB], stride[NCB];
 #pragma unroll
     for (int b = 0; b < NCB; b++) {
         const int c = 8 * b + ci;
-        if (c < K) { ptr[b] = st.Jas + ((size_t)g * 2 * P + kr) * K + c; stride[b] = 4 * K; }
+        if (c < K) { ptr[b] = st.Jas + ((size_t)g * 2 * P + 2 * kr) * K + c; dv[b] = K; stride[b] = 8 * K; }
         else if (c < D) {
             const int e = (c - K) / 6, q = (c - K) - 6 * e;
             const double *base = st.Jes[0];
 #pragma unroll
             for (int ee = 1; ee < L; ee++) if (e == ee) base = st.Jes[ee];
-            ptr[b] = base + ((size_t)g * 2 * P + kr) * 6 + q; stride[b] = 24;
+            ptr[b] = base + ((size_t)g * 2 * P + 2 * kr) * 6 + q; dv[b] = 6; stride[b] = 48;
         }
-        else if (c == D) { ptr[b] = st.rs + (size_t)g * 2 * P + kr; stride[b] = 4; }
-        else { ptr[b] = st.zero; stride[b] = 0; }
+        else if (c == D) { ptr[b] = st.rs + (size_t)g * 2 * P + 2 * kr; dv[b] = 1; stride[b] = 8; }
+        else { ptr[b] = st.zero; dv[b] = 0; stride[b] = 0; }
     }
-    // two interleaved accumulator sets (even / odd k-steps) keep two independent MMA chains per tile
+    // two accumulator sets (u-rows / v-rows) keep two independent MMA chains per tile
     double acc[2][NTILE][2];
 #pragma unroll
     for (int h = 0; h < 2; h++)
 #pragma unroll
         for (int t = 0; t < NTILE; t++) { acc[h][t][0] = 0.0; acc[h][t][1] = 0.0; }
-    const int rows = 2 * P;
-    const int nfull = rows >> 2;              // k-steps whose 4 rows all exist
-    auto kstep = [&](const int h, const bool guard) {
-        double x[NCB];
-#pragma unroll
-        for (int b = 0; b < NCB; b++) {
-            x[b] = guard ? 0.0 : ptr[b][0];
-            ptr[b] += stride[b];
-        }
+    auto mma = [&](const int h, const double (&x)[NCB]) {
         int t = 0;
 #pragma unroll
         for (int bi = 0; bi < NCB; bi++)
 #pragma unroll
             for (int bj = bi; bj < NCB; bj++) { dmma_8x8x4(acc[h][t][0], acc[h][t][1], x[bi], x[bj]); t++; }
     };
-    int ks = 0;
-    for (; ks + 1 < nfull; ks += 2) { kstep(0, false); kstep(1, false); }
-    if (ks < nfull) { kstep(0, false); ks++; }
-    if (rows & 3) kstep(1, kr >= (rows & 3));   // ragged tail: rows beyond 2P contribute zeros
+    const int rows = 2 * P;
+    const int n8 = rows >> 3;                 // pairs of k-steps whose 8 rows all exist
+    for (int s = 0; s < n8; s++) {
+        double xu[NCB], xv[NCB];
+#pragma unroll
+        for (int b = 0; b < NCB; b++) {
+            xu[b] = ptr[b][0];
+            xv[b] = ptr[b][dv[b]];
+            ptr[b] += stride[b];
+        }
+        mma(0, xu);
+        mma(1, xv);
+    }
+    // the last 2, 4 or 6 rows: consecutive rows, those past the image contribute zeros
+    const int rem = rows & 7;
+    if (rem) {
+        double x[NCB];
+#pragma unroll
+        for (int b = 0; b < NCB; b++) x[b] = kr < rem ? ptr[b][-kr * dv[b]] : 0.0;
+        mma(0, x);
+        if (rem > 4) {
+#pragma unroll
+            for (int b = 0; b < NCB; b++) x[b] = 4 + kr < rem ? ptr[b][(4 - kr) * dv[b]] : 0.0;
+            mma(1, x);
+        }
+    }
     double *h = st.Hs + (size_t)g * LY::NE;
     int t = 0;
 #pragma unroll
@@ -365,8 +394,11 @@ __device__ __forceinline__ void fused_reduce(const EvalArgs &args)
 
 // ---- the kernel -------------------------------------------------------------------
 // PCG = groups whose poses one prologue pass stages (PCG * G <= blockDim.x).
+#ifndef VG_WIDE_BLOCKS
+#define VG_WIDE_BLOCKS 2
+#endif
 template <int MODEL, int L>
-__global__ void __launch_bounds__(224, (L == 1 && Camera<MODEL>::K <= 6) ? 4 : 2)
+__global__ void __launch_bounds__(224, (L == 1 && Camera<MODEL>::K <= 6) ? 4 : (L == 1 ? VG_WIDE_BLOCKS : 2))
 reproj_eval_kernel(const EvalArgs args, const int G, const int PCG)
 {
     using LY = Layout<MODEL, L>;
@@ -380,8 +412,19 @@ reproj_eval_kernel(const EvalArgs args, const int G, const int PCG)
     // the warp index through a shuffle: provably warp-uniform (uniform datapath for the TMA operands)
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31, nw = blockDim.x >> 5;
     if (tid < 2) st.zero[tid] = 0.0;
-    GramMap<MODEL, L> gmap;
-    if constexpr (use_parity_gram<MODEL, L>()) gram_map_init<MODEL, L>(gmap, lane);     // visible to everyone after the first __syncthreads below
+    // the output map of the Gram fragments is a function of the lane only: the first warp leaves it in shared
+    // memory (read back per image, so that it does not occupy registers during the corner phase)
+    if constexpr (use_parity_gram<MODEL, L>()) {
+        if (tid < 32) {
+            GramMap<MODEL, L> gm;
+            gram_map_init<MODEL, L>(gm, lane);
+#pragma unroll
+            for (int t = 0; t < ParityGram<MODEL, L>::NTILE; t++)
+#pragma unroll
+                for (int q = 0; q < 2; q++)
+                    st.map[(t * 2 + q) * 32 + lane] = typename LY::map_t{(decltype(LY::map_t::x))gm.iu[t][q], (decltype(LY::map_t::x))gm.iv[t][q]};
+        }
+    }     // visible to everyone after the first __syncthreads below
 
     double intr[K];
 #pragma unroll
@@ -513,7 +556,7 @@ reproj_eval_kernel(const EvalArgs args, const int G, const int PCG)
                     if constexpr (use_parity_gram<MODEL, L>()) {
                         GramFrag<MODEL, L> v;
                         gram_slot_parity<MODEL, L>(st.rs + (size_t)g * 2 * P, st.Jas + (size_t)g * 2 * P * K, Jes_g, st.zero, lane, P, v);
-                        gram_frag_emit<MODEL, L>(v, gmap, st.Hs + (size_t)g * LY::NE, lane);
+                        gram_frag_emit<MODEL, L, typename LY::map_t>(v, st.map, st.Hs + (size_t)g * LY::NE, lane);
                     } else {
                         gram_image<MODEL, L>(st, g, lane, P);
                     }

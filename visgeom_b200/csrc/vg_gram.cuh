@@ -109,9 +109,10 @@ __device__ __forceinline__ void gram_map_init(GramMap<MODEL, L> &m, const int la
     }
 }
 
-// write the fragments of one image into a packed upper-triangular block h (shared or global memory)
-template <int MODEL, int L>
-__device__ __forceinline__ void gram_frag_emit(const GramFrag<MODEL, L> &f, const GramMap<MODEL, L> &m, double *h,
+// write the fragments of one image into a packed upper-triangular block h; map: GramMap as (iu, iv) per fragment
+// element and lane (char2 or short2; -1: not stored)
+template <int MODEL, int L, typename MAP_T>
+__device__ __forceinline__ void gram_frag_emit(const GramFrag<MODEL, L> &f, const MAP_T *map, double *h,
                                                const int lane)
 {
     using PG = ParityGram<MODEL, L>;
@@ -120,7 +121,8 @@ __device__ __forceinline__ void gram_frag_emit(const GramFrag<MODEL, L> &f, cons
 #pragma unroll
         for (int q = 0; q < 2; q++) {
             // parity-independent entries (iu == iv) receive the sum from both stores
-            const int iu = m.iu[t][q], iv = m.iv[t][q];
+            const MAP_T m = map[(t * 2 + q) * 32 + lane];
+            const int iu = m.x, iv = m.y;
             const bool same = iu == iv;
             const double su = same ? f.v[0][t][q] + f.v[1][t][q] : f.v[0][t][q];
             const double sv = same ? su : f.v[1][t][q];
