@@ -1,0 +1,130 @@
+"""The calibration front end (vg_calib: JSON problem files -> GenericCameraCalibration mirror -> C ABI), the
+reference's `calib` tool (test/calibration/generic_calibration.cpp, unified_calibration.cpp:91-356,632-660).
+
+CPU part: the parsing / configuration errors the reference raises before any solve, and the loud failure
+without a GPU.  GPU part: whole problems against the oracle's LM solution of the same data."""
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import synthdata as sd  # noqa: E402
+import make_calib_problem as mk  # noqa: E402
+from visgeom_b200 import build as vg_build  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def cli():
+    vg_build.build()
+    return vg_build.build_cli()
+
+
+def run(cli, *args, cwd=None):
+    return subprocess.run([cli, *args], capture_output=True, text=True, cwd=cwd, timeout=600)
+
+
+def edit(path, fn):
+    prob = json.load(open(path))
+    fn(prob)
+    json.dump(prob, open(path, "w"))
+
+
+def test_config_errors_match_the_reference(cli, tmp_path):
+    path, _ = mk.write_mono(str(tmp_path / "a"), 4)
+    edit(path, lambda p: p["cameras"][0].update(type="pinhole"))
+    r = run(cli, path)
+    assert r.returncode == 1 and "invalid camera model name" in r.stderr                       # :177
+    path, _ = mk.write_mono(str(tmp_path / "b"), 4)
+    edit(path, lambda p: p["cameras"][0].update(value=[0.5, 1, 300, 300, 600]))
+    assert "invalid number of intrinsic parameters" in run(cli, path).stderr                   # :151
+    path, _ = mk.write_mono(str(tmp_path / "c"), 4)
+    edit(path, lambda p: p["transformations"][0].update(constant=True))
+    assert "is constant but there is no prior" in run(cli, path).stderr                        # :103
+    path, _ = mk.write_mono(str(tmp_path / "d"), 4)
+    edit(path, lambda p: p["transformations"].append({"name": "x2", "global": False, "constant": False, "prior": False})
+         or p["data"][0]["transform_chain"].append({"name": "x2", "direct": True}))
+    assert "not one sequences in a transform chain" in run(cli, path).stderr                   # :227
+    path, _ = mk.write_mono(str(tmp_path / "e"), 4)
+    edit(path, lambda p: p["data"][0].update(init="nope"))
+    assert "does not exist, impossible to initialize" in run(cli, path).stderr                 # :433
+    path, _ = mk.write_mono(str(tmp_path / "f"), 4)
+    edit(path, lambda p: p["data"][0].update(type="images"))
+    assert "checkerboard detector" in run(cli, path).stderr
+    assert "cannot open file" in run(cli, str(tmp_path / "missing.json")).stderr
+    assert run(cli).returncode == 2
+
+
+def test_fails_loudly_without_a_gpu(cli, tmp_path):
+    import visgeom_b200 as vg
+    if vg.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    path, _ = mk.write_mono(str(tmp_path), 4)
+    r = run(cli, path)
+    assert r.returncode == 1 and "no CUDA device" in r.stderr
+
+
+def parse_report(out):
+    intr, glob = {}, {}
+    sect = None
+    for line in out.splitlines():
+        if line.startswith("Intrinsic parameters"): sect = "i"; continue
+        if line.startswith("Local extrinsic"): sect = "l"; continue
+        if line.startswith("Global extrinsic"): sect = "g"; continue
+        m = re.match(r"^(\w+) : (.*)$", line)
+        if m and sect == "i": intr[m.group(1)] = np.array([float(x) for x in m.group(2).split()])
+        if m and sect == "g": glob[m.group(1)] = np.array([float(x) for x in m.group(2).split()])
+    return intr, glob
+
+
+@pytest.mark.gpu
+def test_mono_problem_matches_oracle(cli, tmp_path, oracle):
+    from oracle.pyoracle import OracleProblem
+    n = 24
+    path, d = mk.write_mono(str(tmp_path), n, skip=(5,))
+    r = run(cli, "--precision", "17", "--out", str(tmp_path) + "/", path)
+    assert r.returncode == 0, r.stderr
+    intr, _ = parse_report(r.stdout)
+    keep = [i for i in range(n) if i != 5]
+    O = OracleProblem(oracle)
+    cam = O.add_camera(sd.EUCM, d["intr_init"])
+    tr = O.add_transform(d["xi_init"][keep], is_global=False)
+    O.add_dataset(cam, d["board"], d["obs"][keep], [tr], [0])
+    O.solve()
+    rel = np.abs(intr["camera1"] - O.camera(cam)) / np.abs(O.camera(cam))
+    assert rel.max() < 1e-6, rel          # north_star: final intrinsics <= 1e-6 relative
+    # image_error_0.txt: err_u err_v proj_u proj_v tx..rz per corner of every image with a board
+    rows = np.loadtxt(str(tmp_path / "image_error_0.txt"))
+    assert rows.shape == (len(keep) * d["P"], 10)
+    obs = d["obs"][keep].reshape(-1, 2)
+    assert np.abs(rows[:, 0:2] + rows[:, 2:4] - obs).max() < 1e-9           # err = detected - projected
+    assert np.sqrt((rows[:, 0:2] ** 2).mean()) < 0.2                          # 0.1 px noise
+    assert np.abs(rows[:d["P"], 4:10] - O.transform(tr)[0]).max() < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prior", [True, False])
+def test_stereo_problem_matches_oracle(cli, tmp_path, oracle, prior):
+    from oracle.pyoracle import OracleProblem
+    path, s = mk.write_stereo(str(tmp_path), 40, prior=prior)
+    r = run(cli, "--precision", "17", "--out", str(tmp_path) + "/", path)
+    assert r.returncode == 0, r.stderr
+    intr, glob = parse_report(r.stdout)
+    O = OracleProblem(oracle)
+    c1 = O.add_camera(sd.EUCM, s["intr1_init"]); c2 = O.add_camera(sd.EUCM, s["intr2_init"])
+    tb = O.add_transform(s["xi_init"], is_global=False)
+    t12 = O.add_transform(s["xi12_init"], is_global=True)
+    O.add_dataset(c1, s["board"], s["obs1"], [tb], [0])
+    O.add_dataset(c2, s["board"], s["obs2"], [t12, tb], [1, 0])
+    O.solve()
+    for name, cid in (("camera1", c1), ("camera2", c2)):
+        rel = np.abs(intr[name] - O.camera(cid)) / np.abs(O.camera(cid))
+        assert rel.max() < 1e-6, (name, rel)
+    assert np.abs(glob["xiCam12"] - O.transform(t12)[0]).max() < 1e-6
+    assert os.path.exists(str(tmp_path / "image_error_1.txt"))

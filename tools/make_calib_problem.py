@@ -1,0 +1,75 @@
+"""Writes synthetic calibration problems in the reference's JSON format (README.md:36-223 of visgeom,
+dataset type "ir_data": pre-extracted corners, unified_calibration.cpp:234-277) for vg_calib / the tests.
+
+  python tools/make_calib_problem.py mono|stereo OUT_DIR [n_images]
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import synthdata as sd  # noqa: E402
+
+
+def _object(board, nx=9, ny=6):
+    return {"corner_ul": 0, "corner_ur": nx - 1, "corner_bl": nx * (ny - 1), "corner_br": nx * ny - 1,
+            "points": [[float(v) for v in p] for p in board]}
+
+
+def _dataset(camera, chain, init, data_file, board):
+    return {"type": "ir_data", "camera": camera,
+            "transform_chain": [{"name": n, "direct": bool(d)} for n, d in chain], "init": init,
+            "parameters": [], "image_width": sd.IMAGE_W, "image_height": sd.IMAGE_H, "data_file": data_file,
+            "object": _object(board)}
+
+
+def _points(obs_row):
+    return [[float(obs_row[2 * i]), float(obs_row[2 * i + 1])] for i in range(len(obs_row) // 2)]
+
+
+def write_mono(out_dir, n_img=20, model=sd.EUCM, seed=20241, skip=()):
+    """One camera, one per-image board pose initialised from the corners (init = the sequence).  Images in
+    `skip` carry no entry for the camera (no board extracted)."""
+    os.makedirs(out_dir, exist_ok=True)
+    d = sd.make_mono(model, n_img, seed=seed)
+    data_file = os.path.join(out_dir, "corners.json")
+    json.dump([[] if i in skip else [{"camera": "camera1", "points": _points(d["obs"][i])}] for i in range(n_img)],
+              open(data_file, "w"))
+    prob = {"transformations": [{"name": "xiCamBoard", "global": False, "constant": False, "prior": False}],
+            "cameras": [{"name": "camera1", "type": sd.MODEL_NAMES[model], "constant": False,
+                         "value": [float(v) for v in d["intr_init"]]}],
+            "data": [_dataset("camera1", [("xiCamBoard", True)], "xiCamBoard", data_file, d["board"])]}
+    path = os.path.join(out_dir, "problem.json")
+    json.dump(prob, open(path, "w"), indent=1)
+    return path, d
+
+
+def write_stereo(out_dir, n_pairs=20, seed=20244, prior=True):
+    """The layout of data/calib_stereo_example.json: camera1 sees the board through xiCamBoardStereo, camera2
+    through xiCam12^-1 o xiCamBoardStereo; xiCam12 is global, with a prior or (prior=False) initialised from the
+    second dataset (unified_calibration.cpp:497-511: first extracted image, then a solve over the dataset)."""
+    os.makedirs(out_dir, exist_ok=True)
+    s = sd.make_stereo(n_pairs, seed=seed)
+    data_file = os.path.join(out_dir, "corners.json")
+    json.dump([[{"camera": "camera1", "points": _points(s["obs1"][i])},
+                {"camera": "camera2", "points": _points(s["obs2"][i])}] for i in range(n_pairs)], open(data_file, "w"))
+    prob = {"transformations": [{"name": "xiCamBoardStereo", "global": False, "constant": False, "prior": False},
+                                ({"name": "xiCam12", "global": True, "constant": False, "prior": True,
+                                  "value": [float(v) for v in s["xi12_init"]]} if prior else
+                                 {"name": "xiCam12", "global": True, "constant": False, "prior": False})],
+            "cameras": [{"name": "camera1", "type": "eucm", "constant": False, "value": [float(v) for v in s["intr1_init"]]},
+                        {"name": "camera2", "type": "eucm", "constant": False, "value": [float(v) for v in s["intr2_init"]]}],
+            "data": [_dataset("camera1", [("xiCamBoardStereo", True)], "xiCamBoardStereo", data_file, s["board"]),
+                     _dataset("camera2", [("xiCam12", False), ("xiCamBoardStereo", True)], "none" if prior else "xiCam12",
+                              data_file, s["board"])]}
+    path = os.path.join(out_dir, "problem.json")
+    json.dump(prob, open(path, "w"), indent=1)
+    return path, s
+
+
+if __name__ == "__main__":
+    kind, out = sys.argv[1], sys.argv[2]
+    n = int(sys.argv[3]) if len(sys.argv) > 3 else 20
+    print((write_mono if kind == "mono" else write_stereo)(out, n)[0])

@@ -61,5 +61,24 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+CLI = os.path.join(HERE, "bin", "vg_calib")
+HOST = os.path.join(HERE, "host")
+INCLUDE = os.path.join(os.path.dirname(HERE), "include")
+
+
+def build_cli(force: bool = False) -> str:
+    """g++ -> visgeom_b200/bin/vg_calib: the reference's `calib` tool (JSON front end, host C++) over the C ABI."""
+    srcs = [os.path.join(HOST, f) for f in ("calibration.cpp", "calib_main.cpp")]
+    deps = srcs + [os.path.join(HOST, "json.hpp")] + [os.path.join(INCLUDE, "visgeom_b200", f)
+                                                      for f in ("calibration.hpp", "camera.hpp", "geometry.hpp")] + [LIB]
+    if force or _stale(CLI, deps):
+        os.makedirs(os.path.dirname(CLI), exist_ok=True)
+        subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-I" + INCLUDE, "-I" + HOST] + srcs +
+                              ["-o", CLI, "-L" + HERE, "-lvisgeom_b200", "-Wl,-rpath,$ORIGIN/.."])
+    return CLI
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if not VARIANT:
+        print(build_cli(force="--force" in sys.argv))

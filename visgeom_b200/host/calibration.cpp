@@ -1,0 +1,513 @@
+// calibration.cpp -- see include/visgeom_b200/calibration.hpp.  Host-side mirror of GenericCameraCalibration
+// (src/calibration/unified_calibration.cpp) over the C ABI of the CUDA engine.
+#include "visgeom_b200/calibration.hpp"
+
+#include <algorithm>
+#include <cstdio>
+#include <fstream>
+#include <iostream>
+#include <stdexcept>
+
+#include "json.hpp"
+
+namespace visgeom_b200 {
+
+using std::cout;
+using std::endl;
+using std::runtime_error;
+using std::string;
+using std::vector;
+
+namespace {
+
+// transformFromData, include/json.h:37-68
+Transf transformFromData(const vector<double> &v)
+{
+    if (v.size() == 3) return Transf(v[0], v[1], 0, 0, 0, v[2]);                 // x, y, theta
+    if (v.size() == 6) return Transf(v.data());                                   // angle-axis
+    if (v.size() == 7) return Transf(v[0], v[1], v[2], v[3], v[4], v[5], v[6]);   // quaternion
+    if (v.size() == 12) {                                                         // homogeneous 3x4
+        const Matrix3d R{{v[0], v[1], v[2], v[4], v[5], v[6], v[8], v[9], v[10]}};
+        return Transf(Vector3d(v[3], v[7], v[11]), R);
+    }
+    throw runtime_error("invalid trasformation format. must be 3, 6, or 12 values; " + std::to_string(v.size()) +
+                        " are given.");
+}
+
+void check(int rc, const char *what)
+{
+    if (rc < 0) throw runtime_error(string(what) + ": " + vg_last_error());
+}
+
+struct ProblemHandle {
+    vg_problem *p;
+    explicit ProblemHandle(int device) : p(vg_problem_create(device))
+    {
+        if (!p) throw runtime_error(string("vg_problem_create: ") + vg_last_error());
+    }
+    ~ProblemHandle() { vg_problem_destroy(p); }
+};
+
+}  // namespace
+
+GenericCameraCalibration::~GenericCameraCalibration()
+{
+    for (auto &x : cameraMap) delete x.second;
+}
+
+bool GenericCameraCalibration::addResiduals(const string &infoFileName)
+{
+    const json::Value root = json::read_json(infoFileName);
+    parseTransforms(root);
+    parseCameras(root);
+    parseData(root);
+    return true;
+}
+
+// unified_calibration.cpp:91-132
+void GenericCameraCalibration::parseTransforms(const json::Value &root)
+{
+    for (const json::Value &node : root.child("transformations").arr) {
+        const string name = node.getString("name");
+        TransformInfo &info = transformInfoMap[name] = TransformInfo();
+        info.global = node.getBool("global");
+        info.prior = node.getBool("prior");
+        info.constant = node.getBool("constant");
+        if (info.constant && !info.prior) throw runtime_error(name + " is constant but there is no prior");
+        if (info.global) {
+            globalTransformMap[name] = Array6d{};
+            if (info.prior) globalTransformMap[name] = transformFromData(node.child("value").numbers()).toArray();
+        } else {
+            sequenceTransformMap[name] = vector<Array6d>();
+            sequenceInitMap[name] = vector<bool>();
+            if (info.prior)
+                for (const json::Value &val : node.child("value").arr)
+                    sequenceTransformMap[name].push_back(transformFromData(val.numbers()).toArray());
+        }
+    }
+}
+
+// unified_calibration.cpp:134-180
+void GenericCameraCalibration::parseCameras(const json::Value &root)
+{
+    for (const json::Value &node : root.child("cameras").arr) {
+        const string name = node.getString("name");
+        cameraConstantMap[name] = node.getBool("constant");
+        vector<double> &intrinsicVec = intrinsicMap[name] = node.child("value").numbers();
+        const string cameraType = node.getString("type");
+        const size_t n = intrinsicVec.size();
+        if (cameraType == "eucm") {
+            cout << "Model : EUCM" << endl;
+            if (n != 6) throw runtime_error("invalid number of intrinsic parameters");
+            cameraMap[name] = new EnhancedCamera(intrinsicVec.data());
+        } else if (cameraType == "ucm") {
+            cout << "Model : UCM" << endl;
+            if (n != 5) throw runtime_error("invalid number of intrinsic parameters");
+            cameraMap[name] = new UnifiedCamera(intrinsicVec.data());
+        } else if (cameraType == "mei") {
+            cout << "Model : MEI" << endl;
+            if (n != 10) throw runtime_error("invalid number of intrinsic parameters");
+            cameraMap[name] = new MeiCamera(intrinsicVec.data());
+        } else {
+            throw runtime_error("invalid camera model name");
+        }
+    }
+}
+
+// unified_calibration.cpp:182-230
+void GenericCameraCalibration::initTransformChainInfo(ImageData &data, const json::Value &node)
+{
+    data.cameraName = node.getString("camera");
+    if (cameraMap.find(data.cameraName) == cameraMap.end()) throw runtime_error(data.cameraName + " : unknown camera");
+    for (const json::Value &flag : node.child("parameters").arr) {
+        const string &f = flag.str;
+        if (f == "do_not_solve") data.doNotSolve = true;
+        else if (f == "do_not_solve_global") data.doNotSolveGlobal = true;
+        else if (f == "check_extraction" || f == "improve_detection" || f == "show_outliers" || f == "user_guided" ||
+                 f == "save_outlire_images" || f == "draw_improved") { /* image / GUI options: nothing to do here */ }
+        else cout << "WARNING : UNKNOWN FLAG -- " << f << endl;
+    }
+    cout << "Camera : " << data.cameraName << endl;
+    cout << "Transformations : ";
+    for (const json::Value &t : node.child("transform_chain").arr) {
+        data.transNameVec.push_back(t.getString("name"));
+        cout << data.transNameVec.back();
+        if (t.getBool("direct")) data.transStatusVec.push_back(TRANSFORM_DIRECT);
+        else { data.transStatusVec.push_back(TRANSFORM_INVERSE); cout << "_inv"; }
+        cout << "   ";
+    }
+    int sequenceCount = 0;
+    for (const string &name : data.transNameVec) {
+        if (transformInfoMap.find(name) == transformInfoMap.end()) throw runtime_error(name + " has not been declared");
+        if (!transformInfoMap[name].global) sequenceCount++;
+    }
+    if (sequenceCount != 1) throw runtime_error("not one sequences in a transform chain");
+    if (data.transNameVec.size() > VG_MAX_CHAIN)
+        throw runtime_error("the transform chain is too long (5 transforms at max are supproted)");
+    cout << endl;
+}
+
+// unified_calibration.cpp:233-250
+void GenericCameraCalibration::initGridIR(ImageData &data, const json::Value &node)
+{
+    data.board.clear();
+    data.idxUL = node.getInt("object.corner_ul");
+    data.idxUR = node.getInt("object.corner_ur");
+    data.idxBL = node.getInt("object.corner_bl");
+    data.idxBR = node.getInt("object.corner_br");
+    for (const json::Value &x : node.child("object.points").arr) {
+        const vector<double> pt = x.numbers();
+        data.board.emplace_back(pt.at(0), pt.at(1), pt.at(2));
+    }
+}
+
+// unified_calibration.cpp:252-277
+void GenericCameraCalibration::readCorners(ImageData &data, const json::Value &node)
+{
+    data.imageWidth = node.getInt("image_width");
+    data.imageHeight = node.getInt("image_height");
+    const json::Value dataFile = json::read_json(node.getString("data_file"));
+    const string cameraID = node.getString("camera");
+    for (const json::Value &dataPoint : dataFile.arr) {
+        data.detectedCornersVec.emplace_back();
+        vector<Vector2d> &cornerVec = data.detectedCornersVec.back();
+        for (const json::Value &x : dataPoint.arr) {
+            if (x.getString("camera") == cameraID) {
+                for (const json::Value &y : x.child("points").arr) {
+                    const vector<double> pt = y.numbers();
+                    cornerVec.emplace_back(pt.at(0), pt.at(1));
+                }
+                break;
+            }
+        }
+        if (!cornerVec.empty() && cornerVec.size() != data.board.size())
+            throw runtime_error("an image has " + std::to_string(cornerVec.size()) + " points, the object " +
+                                std::to_string(data.board.size()));
+    }
+}
+
+Transf GenericCameraCalibration::getTransform(const string &name, int idx) const
+{
+    const auto g = globalTransformMap.find(name);
+    if (g != globalTransformMap.end()) return Transf(g->second.data());
+    return Transf(sequenceTransformMap.at(name).at(idx).data());
+}
+
+// unified_calibration.cpp:311-348: un-wind the chain around the transform being initialised
+Transf GenericCameraCalibration::getInitTransform(Transf xi, const string &initName, const ImageData &data, int transfIdx)
+{
+    const int n = (int)data.transNameVec.size();
+    for (int i = 0; i < n; i++) {
+        const string &name = data.transNameVec[i];
+        if (name == initName) break;
+        if (data.transStatusVec[i] == TRANSFORM_DIRECT) xi = getTransform(name, transfIdx).inverseCompose(xi);
+        else xi = getTransform(name, transfIdx).compose(xi);
+    }
+    for (int i = n - 1; i >= 0; i--) {
+        const string &name = data.transNameVec[i];
+        if (name == initName) {
+            if (data.transStatusVec[i] == TRANSFORM_INVERSE) xi = xi.inverse();
+            break;
+        }
+        if (data.transStatusVec[i] == TRANSFORM_DIRECT) xi = xi.composeInverse(getTransform(name, transfIdx));
+        else xi = xi.compose(getTransform(name, transfIdx));
+    }
+    return xi;
+}
+
+// closed-form part of estimateInitialGrid, unified_calibration.cpp:1066-1129: the four outer corners are
+// back-projected, scaled with the board's edge lengths and turned into a board frame
+Transf GenericCameraCalibration::estimateInitialGridGuess(const ImageData &data, int gridIdx) const
+{
+    const vector<Vector2d> &cornerVec = data.detectedCornersVec[gridIdx];
+    const ICamera *cam = cameraMap.at(data.cameraName);
+    Vector3d XUL, XUR, XBL, XBR;
+    cam->reconstructPoint(cornerVec[data.idxUL], XUL);
+    cam->reconstructPoint(cornerVec[data.idxUR], XUR);
+    cam->reconstructPoint(cornerVec[data.idxBL], XBL);
+    cam->reconstructPoint(cornerVec[data.idxBR], XBR);
+    XUL.normalize(); XUR.normalize(); XBR.normalize(); XBL.normalize();
+    const double scaleXU = (data.board[data.idxUR] - data.board[data.idxUL]).norm() / (XUR - XUL).norm();
+    const double scaleXB = (data.board[data.idxBR] - data.board[data.idxBL]).norm() / (XBR - XBL).norm();
+    const double scaleYL = (data.board[data.idxBL] - data.board[data.idxUL]).norm() / (XBL - XUL).norm();
+    const double scaleYR = (data.board[data.idxBR] - data.board[data.idxUR]).norm() / (XBR - XUR).norm();
+    const Vector3d pos = XUL * std::min(scaleXU, scaleYL);
+    const Vector3d posx = XUR * std::min(scaleXU, scaleYR);
+    const Vector3d posy = XBL * std::min(scaleXB, scaleYL);
+    Vector3d ex = posx - pos, ey = posy - pos;
+    ex.normalize();
+    ey = ey - ex * ex.dot(ey);      // make ey perpendicular
+    ey.normalize();
+    const Vector3d ez = ex.cross(ey);
+    return Transf(pos, Matrix3d::fromColumns(ex, ey, ez));
+}
+
+// The refinement part of estimateInitialGrid (unified_calibration.cpp:1131-1155), batched: the reference solves
+// one 6-parameter problem per image with the intrinsics constant; here all images of the dataset are the poses
+// of ONE problem on the GPU (they are independent: the Hessian is block diagonal).  Difference, stated: the
+// reference wraps each block in SoftLOneLoss(25), this solve uses the plain squared residual (an initial guess
+// for the global problem either way).
+void GenericCameraCalibration::refineInitialGrids(const ImageData &data, const vector<int> &idx, vector<Array6d> &xi) const
+{
+    if (idx.empty()) return;
+    const ICamera *cam = cameraMap.at(data.cameraName);
+    const int P = (int)data.board.size(), n = (int)idx.size();
+    vector<double> board(3 * (size_t)P), obs(2 * (size_t)P * n), poses(6 * (size_t)n);
+    for (int i = 0; i < P; i++) for (int k = 0; k < 3; k++) board[3 * i + k] = data.board[i][k];
+    for (int j = 0; j < n; j++) {
+        for (int i = 0; i < P; i++) for (int k = 0; k < 2; k++)
+            obs[((size_t)j * P + i) * 2 + k] = data.detectedCornersVec[idx[j]][i][k];
+        for (int k = 0; k < 6; k++) poses[6 * (size_t)j + k] = xi[j][k];
+    }
+    ProblemHandle h(device);
+    const int camId = vg_problem_add_camera(h.p, cam->model(), intrinsicMap.at(data.cameraName).data(), 1);
+    check(camId, "vg_problem_add_camera");
+    const int tr = vg_problem_add_transform(h.p, 0, 0, n, poses.data());
+    check(tr, "vg_problem_add_transform");
+    const int status = VG_TRANSFORM_DIRECT;
+    check(vg_problem_add_dataset(h.p, camId, P, board.data(), n, obs.data(), nullptr, 1, &tr, &status), "vg_problem_add_dataset");
+    vg_solve_options o;
+    vg_solve_options_default(&o);
+    o.max_num_iterations = 500;                // as the reference's per-image solve
+    o.function_tolerance = 1e-6; o.gradient_tolerance = 1e-10; o.parameter_tolerance = 1e-8;   // Ceres defaults
+    o.verbose = 0;
+    vg_solve_summary s;
+    check(vg_problem_solve(h.p, &o, &s), "vg_problem_solve (initial poses)");
+    check(vg_problem_get_transform(h.p, tr, poses.data()), "vg_problem_get_transform");
+    for (int j = 0; j < n; j++) for (int k = 0; k < 6; k++) xi[j][k] = poses[6 * (size_t)j + k];
+}
+
+// unified_calibration.cpp:358-427: a global transform initialised from one image is refined over all images
+// of the dataset with every other block constant (the reference uses SoftLOneLoss(1) there)
+void GenericCameraCalibration::initGlobalTransform(const ImageData &data, const string &name)
+{
+    const ICamera *cam = cameraMap.at(data.cameraName);
+    const int P = (int)data.board.size();
+    vector<int> seqIndex;
+    vector<double> board(3 * (size_t)P), obs;
+    for (int i = 0; i < P; i++) for (int k = 0; k < 3; k++) board[3 * i + k] = data.board[i][k];
+    for (size_t t = 0; t < data.detectedCornersVec.size(); t++) {
+        if (data.detectedCornersVec[t].empty()) continue;
+        seqIndex.push_back((int)t);
+        for (const Vector2d &c : data.detectedCornersVec[t]) { obs.push_back(c[0]); obs.push_back(c[1]); }
+    }
+    ProblemHandle h(device);
+    const int camId = vg_problem_add_camera(h.p, cam->model(), intrinsicMap.at(data.cameraName).data(), 1);
+    check(camId, "vg_problem_add_camera");
+    vector<int> ids, status;
+    int target = -1;
+    for (size_t i = 0; i < data.transNameVec.size(); i++) {
+        const string &tn = data.transNameVec[i];
+        int id;
+        if (transformInfoMap[tn].global) id = vg_problem_add_transform(h.p, 1, tn != name, 1, globalTransformMap[tn].data());
+        else {
+            const vector<Array6d> &seq = sequenceTransformMap[tn];
+            id = vg_problem_add_transform(h.p, 0, 1, (int)seq.size(), seq[0].data());
+        }
+        check(id, "vg_problem_add_transform");
+        if (tn == name) target = id;
+        ids.push_back(id);
+        status.push_back(data.transStatusVec[i]);
+    }
+    check(vg_problem_add_dataset(h.p, camId, P, board.data(), (int)seqIndex.size(), obs.data(), seqIndex.data(),
+                                 (int)ids.size(), ids.data(), status.data()), "vg_problem_add_dataset");
+    vg_solve_options o;
+    vg_solve_options_default(&o);
+    o.max_num_iterations = 500;
+    o.function_tolerance = 1e-6; o.gradient_tolerance = 1e-10; o.parameter_tolerance = 1e-8;
+    o.verbose = 1;
+    vg_solve_summary s;
+    check(vg_problem_solve(h.p, &o, &s), "vg_problem_solve (global transform)");
+    check(vg_problem_get_transform(h.p, target, globalTransformMap[name].data()), "vg_problem_get_transform");
+}
+
+// unified_calibration.cpp:429-512
+void GenericCameraCalibration::initTransforms(const ImageData &data, const string &initName)
+{
+    if (initName == "none") return;
+    if (transformInfoMap.find(initName) == transformInfoMap.end())
+        throw runtime_error(initName + " does not exist, impossible to initialize");
+    if (std::find(data.transNameVec.begin(), data.transNameVec.end(), initName) == data.transNameVec.end())
+        throw runtime_error(initName + " does not belong to the transform chain");
+    if (transformInfoMap[initName].prior) throw runtime_error(initName + " has a prior value");
+    transformInfoMap[initName].initialized = true;
+    for (const string &x : data.transNameVec)
+        if (!(transformInfoMap[x].prior ^ transformInfoMap[x].initialized))
+            throw runtime_error(x + " is not initialized. Cannot initialize more than one transform at a time");
+
+    const int nImg = (int)data.detectedCornersVec.size();
+    if (!transformInfoMap[initName].global) {
+        vector<Array6d> &seq = sequenceTransformMap[initName];
+        vector<bool> &done = sequenceInitMap[initName];
+        if (seq.empty()) { seq.assign(nImg, Array6d{0, 0, 1, 0, 0, 0}); done.assign(nImg, false); }
+        if ((int)seq.size() < nImg) throw runtime_error(initName + " : the sequence is shorter than the dataset");
+        vector<int> idx;
+        vector<Array6d> xi;
+        for (int t = 0; t < nImg; t++)
+            if (!data.detectedCornersVec[t].empty() && !done[t]) {
+                idx.push_back(t);
+                xi.push_back(estimateInitialGridGuess(data, t).toArray());
+            }
+        if (!data.doNotSolve) refineInitialGrids(data, idx, xi);
+        for (size_t j = 0; j < idx.size(); j++) {
+            seq[idx[j]] = getInitTransform(Transf(xi[j].data()), initName, data, idx[j]).toArray();
+            done[idx[j]] = true;
+        }
+    } else {
+        const int t = data.getFirstExtractedIdx();
+        if (t < 0) throw runtime_error(initName + " : no board extracted, impossible to initialize");
+        vector<Array6d> xi{estimateInitialGridGuess(data, t).toArray()};
+        if (!data.doNotSolve) refineInitialGrids(data, {t}, xi);
+        cout << "INITI VALUE IN CAMERA FRAME " << endl << Transf(xi[0].data()) << endl;
+        const Transf x = getInitTransform(Transf(xi[0].data()), initName, data, t);
+        cout << "INITI TRANSFORM " << endl << x << endl;
+        globalTransformMap[initName] = x.toArray();
+        if (nImg > 1 && !data.doNotSolve) initGlobalTransform(data, initName);
+    }
+}
+
+// unified_calibration.cpp:632-660 (+ the dataset types this engine does not take)
+void GenericCameraCalibration::parseData(const json::Value &root)
+{
+    for (const json::Value &node : root.child("data").arr) {
+        const string dataType = node.getString("type");
+        if (dataType == "ir_data") {
+            dataVec.emplace_back();
+            ImageData &data = dataVec.back();
+            initTransformChainInfo(data, node);
+            initGridIR(data, node);
+            readCorners(data, node);
+            initTransforms(data, node.getString("init"));
+        } else if (dataType == "images") {
+            throw runtime_error("dataset type \"images\" needs the checkerboard detector (OpenCV), which is outside this "
+                                "engine: extract the corners first and pass them as an \"ir_data\" dataset");
+        } else {
+            throw runtime_error("dataset type \"" + dataType + "\" is not supported by this engine (reprojection datasets only)");
+        }
+    }
+}
+
+// unified_calibration.cpp:1160-1183
+void GenericCameraCalibration::computeTransforms(const ImageData &data, vector<Transf> &transfVec) const
+{
+    transfVec.clear();
+    for (size_t t = 0; t < data.detectedCornersVec.size(); t++) {
+        Transf xi(0, 0, 0, 0, 0, 0);
+        for (size_t i = 0; i < data.transNameVec.size(); i++) {
+            const Transf x = getTransform(data.transNameVec[i], (int)t);
+            xi = data.transStatusVec[i] == TRANSFORM_DIRECT ? xi.compose(x) : xi.composeInverse(x);
+        }
+        transfVec.push_back(xi);
+    }
+}
+
+// unified_calibration.cpp:1186-1218: "err_u err_v   proj_u proj_v   tx ty tz rx ry rz" per corner, err = detected -
+// projected; both come from the engine's residuals (r = projected - detected)
+void GenericCameraCalibration::writeImageResidual(vg_problem *p, int dataset, const ImageData &data, const string &fileName) const
+{
+    vector<Transf> transfVec;
+    computeTransforms(data, transfVec);
+    const int P = (int)data.board.size();
+    int n = 0;
+    for (const auto &c : data.detectedCornersVec) if (!c.empty()) n++;
+    vector<double> r((size_t)n * 2 * P);
+    if (n) check(vg_problem_residuals(p, dataset, r.data()), "vg_problem_residuals");
+    std::ofstream f(fileName);
+    f.precision(cout.precision());      // the reference's default (6 digits) unless --precision asked for more
+    size_t row = 0;
+    for (size_t t = 0; t < transfVec.size(); t++) {
+        if (data.detectedCornersVec[t].empty()) continue;
+        for (int i = 0; i < P; i++, row++) {
+            const double ru = r[2 * row], rv = r[2 * row + 1];
+            const Vector2d &det = data.detectedCornersVec[t][i];
+            f << -ru << " " << -rv << "   " << det[0] + ru << " " << det[1] + rv << "   " << transfVec[t] << "\n";
+        }
+    }
+}
+
+// unified_calibration.cpp:39-89 with ceres::Problem / ceres::Solve replaced by the engine
+// (problem assembly: addGridResidualBlocks :514-630)
+bool GenericCameraCalibration::compute()
+{
+    ProblemHandle h(device);
+    std::map<string, int> camId, trId;
+    for (auto &x : cameraMap) {
+        const int id = vg_problem_add_camera(h.p, x.second->model(), intrinsicMap[x.first].data(), cameraConstantMap[x.first]);
+        check(id, "vg_problem_add_camera");
+        camId[x.first] = id;
+    }
+    for (auto &x : globalTransformMap) {
+        const int id = vg_problem_add_transform(h.p, 1, transformInfoMap[x.first].constant, 1, x.second.data());
+        check(id, "vg_problem_add_transform");
+        trId[x.first] = id;
+    }
+    for (auto &x : sequenceTransformMap) {
+        if (x.second.empty()) continue;
+        const int id = vg_problem_add_transform(h.p, 0, transformInfoMap[x.first].constant, (int)x.second.size(), x.second[0].data());
+        check(id, "vg_problem_add_transform");
+        trId[x.first] = id;
+    }
+    vector<int> dsId(dataVec.size(), -1);
+    for (size_t d = 0; d < dataVec.size(); d++) {
+        const ImageData &data = dataVec[d];
+        if (data.doNotSolveGlobal) continue;
+        const int P = (int)data.board.size();
+        vector<double> board(3 * (size_t)P), obs;
+        vector<int> seqIndex, ids, status;
+        for (int i = 0; i < P; i++) for (int k = 0; k < 3; k++) board[3 * i + k] = data.board[i][k];
+        for (size_t t = 0; t < data.detectedCornersVec.size(); t++) {
+            if (data.detectedCornersVec[t].empty()) continue;       // :520
+            seqIndex.push_back((int)t);
+            for (const Vector2d &c : data.detectedCornersVec[t]) { obs.push_back(c[0]); obs.push_back(c[1]); }
+        }
+        for (size_t i = 0; i < data.transNameVec.size(); i++) {
+            if (trId.find(data.transNameVec[i]) == trId.end())
+                throw runtime_error(data.transNameVec[i] + " has no values: give a prior or initialise it");
+            ids.push_back(trId[data.transNameVec[i]]);
+            status.push_back(data.transStatusVec[i]);
+        }
+        dsId[d] = vg_problem_add_dataset(h.p, camId[data.cameraName], P, board.data(), (int)seqIndex.size(), obs.data(),
+                                         seqIndex.data(), (int)ids.size(), ids.data(), status.data());
+        check(dsId[d], "vg_problem_add_dataset");
+    }
+
+    vg_solve_options o;
+    vg_solve_options_default(&o);      // max_num_iterations 1000, tolerances 1e-15 (:46-49)
+    o.verbose = 1;                     // minimizer_progress_to_stdout
+    check(vg_problem_solve(h.p, &o, &lastSummary), "vg_problem_solve");
+    static const char *why[] = {"function tolerance", "gradient tolerance", "parameter tolerance", "max iterations",
+                                "trust region radius", "failure"};
+    cout << "\nSolver Summary\n  iterations " << lastSummary.iterations << " (successful " << lastSummary.num_successful
+         << ", unsuccessful " << lastSummary.num_unsuccessful << ")\n  initial cost " << lastSummary.initial_cost
+         << "\n  final cost   " << lastSummary.final_cost << "\n  termination  " << why[lastSummary.termination]
+         << "\n  time total " << lastSummary.seconds_total << " s, in residual/Jacobian/normal-equation kernels "
+         << lastSummary.seconds_evaluate << " s (" << lastSummary.num_evaluations << " evaluations)\n" << endl;
+
+    // results back into the maps
+    for (auto &x : camId) check(vg_problem_get_camera(h.p, x.second, intrinsicMap[x.first].data()), "vg_problem_get_camera");
+    for (auto &x : globalTransformMap) check(vg_problem_get_transform(h.p, trId[x.first], x.second.data()), "vg_problem_get_transform");
+    for (auto &x : sequenceTransformMap)
+        if (!x.second.empty()) check(vg_problem_get_transform(h.p, trId[x.first], x.second[0].data()), "vg_problem_get_transform");
+    for (auto &x : cameraMap) x.second->setParameters(intrinsicMap[x.first].data());
+
+    cout << "Intrinsic parameters :" << endl;
+    for (auto &x : intrinsicMap) {
+        cout << x.first << " : ";
+        for (double v : x.second) cout << v << "  ";
+        cout << endl;
+    }
+    cout << "Local extrinsic parameters :" << endl;
+    for (auto &seq : sequenceTransformMap) {
+        cout << "Sequence : " << seq.first << endl;
+        int i = 0;
+        for (auto &x : seq.second) cout << i++ << " : " << Transf(x.data()) << endl;
+    }
+    cout << "Global extrinsic parameters :" << endl;
+    for (auto &x : globalTransformMap) cout << x.first << " : " << Transf(x.second.data()) << endl;
+
+    for (size_t d = 0; d < dataVec.size(); d++)
+        if (dsId[d] >= 0) writeImageResidual(h.p, dsId[d], dataVec[d], outputPrefix + "image_error_" + std::to_string(d) + ".txt");
+    return true;
+}
+
+}  // namespace visgeom_b200
