@@ -156,30 +156,51 @@ pose_factor_kernel(const DatasetDesc *desc_all, int n_pose, int Ks,
 __global__ void __launch_bounds__(GRAM_THREADS)
 gram_kernel(int n_pose, int Ks, const double *ws, double *partial)
 {
+    // thread = (entry t of the upper triangle of Z^T Z plus the Z^T z column, slice q of the block's poses);
+    // the slices of an entry are added in slice order afterwards, so the sum order is fixed
+    __shared__ double sh[GRAM_THREADS];
     const int npair = Ks * (Ks + 1) / 2 + Ks;
     const int p0 = blockIdx.x * GRAM_POSES, p1 = min(n_pose, p0 + GRAM_POSES);
     const int stride = pose_ws_stride(Ks);
-    for (int t = threadIdx.x; t < npair; t += blockDim.x) {
-        int a, b;   // b == Ks -> the z column
-        if (t < Ks * (Ks + 1) / 2) {
-            a = 0; int rem = t;
-            while (rem >= Ks - a) { rem -= Ks - a; a++; }
-            b = a + rem;
-        } else {
-            a = t - Ks * (Ks + 1) / 2; b = Ks;
-        }
+    const int Q = max(1, (int)blockDim.x / npair);
+    const int per = (GRAM_POSES + Q - 1) / Q;
+    for (int t0 = 0; t0 < npair; t0 += blockDim.x) {
+        const int q = Q > 1 ? threadIdx.x / npair : 0;
+        const int t = Q > 1 ? threadIdx.x - q * npair : t0 + threadIdx.x;
         double s = 0.0;
-        for (int p = p0; p < p1; p++) {
-            const double *w = ws + (size_t)p * stride;
-            const double *Z = w + 33, *z = w + 27;
+        const bool active = t < npair && q < Q;
+        if (active) {
+            int a, b;   // b == Ks -> the z column
+            if (t < Ks * (Ks + 1) / 2) {
+                a = 0; int rem = t;
+                while (rem >= Ks - a) { rem -= Ks - a; a++; }
+                b = a + rem;
+            } else {
+                a = t - Ks * (Ks + 1) / 2; b = Ks;
+            }
+            const int q0 = p0 + q * per, q1 = min(p1, q0 + per);
+            for (int p = q0; p < q1; p++) {
+                const double *w = ws + (size_t)p * stride;
+                const double *Z = w + 33, *z = w + 27;
 #pragma unroll
-            for (int k = 0; k < 6; k++) {
-                const double za = Z[k * Ks + a];
-                const double zb = (b < Ks) ? Z[k * Ks + b] : z[k];
-                s = fma(za, zb, s);
+                for (int k = 0; k < 6; k++) {
+                    const double za = Z[k * Ks + a];
+                    const double zb = (b < Ks) ? Z[k * Ks + b] : z[k];
+                    s = fma(za, zb, s);
+                }
             }
         }
-        partial[(size_t)blockIdx.x * npair + t] = s;
+        if (Q > 1) {
+            sh[threadIdx.x] = s;
+            __syncthreads();
+            if (threadIdx.x < npair) {
+                double tot = 0.0;
+                for (int qq = 0; qq < Q; qq++) tot += sh[qq * npair + threadIdx.x];
+                partial[(size_t)blockIdx.x * npair + threadIdx.x] = tot;
+            }
+            break;
+        }
+        if (active) partial[(size_t)blockIdx.x * npair + t] = s;
     }
 }
 
@@ -187,22 +208,41 @@ __global__ void __launch_bounds__(256)
 finalize_gram_kernel(int Ks, int n_blocks, const double *partial, int n_gmax, const double *partial_gmax,
                      double *red, int *fail_flag, int rank, int nranks)
 {
+    // thread = (entry t, slice q of the blocks); slices combined in slice order (fixed sum order)
+    __shared__ double sh[256];
     const int npair = Ks * (Ks + 1) / 2 + Ks;
     double *S = red + red_off_S(Ks), *v = red + red_off_v(Ks);
-    for (int t = threadIdx.x; t < npair; t += blockDim.x) {
+    const int Q = max(1, (int)blockDim.x / npair);
+    const int per = (n_blocks + Q - 1) / Q;
+    for (int t0 = 0; t0 < npair; t0 += blockDim.x) {
+        const int q = Q > 1 ? threadIdx.x / npair : 0;
+        const int t = Q > 1 ? threadIdx.x - q * npair : t0 + threadIdx.x;
         double s = 0.0;
-        for (int blk = 0; blk < n_blocks; blk++) s += partial[(size_t)blk * npair + t];
-        if (t < Ks * (Ks + 1) / 2) {
-            int a = 0, rem = t;
-            while (rem >= Ks - a) { rem -= Ks - a; a++; }
-            const int b = a + rem;
-            S[a * Ks + b] = s;
-            S[b * Ks + a] = s;
-        } else {
-            v[t - Ks * (Ks + 1) / 2] = s;
+        if (t < npair && q < Q) {
+            const int b0 = q * per, b1 = min(n_blocks, b0 + per);
+            for (int blk = b0; blk < b1; blk++) s += partial[(size_t)blk * npair + t];
         }
+        if (Q > 1) {
+            sh[threadIdx.x] = s;
+            __syncthreads();
+            s = 0.0;
+            if (threadIdx.x < npair)
+                for (int qq = 0; qq < Q; qq++) s += sh[qq * npair + threadIdx.x];
+        }
+        if (t < npair && (Q == 1 || threadIdx.x < npair)) {
+            if (t < Ks * (Ks + 1) / 2) {
+                int a = 0, rem = t;
+                while (rem >= Ks - a) { rem -= Ks - a; a++; }
+                const int b = a + rem;
+                S[a * Ks + b] = s;
+                S[b * Ks + a] = s;
+            } else {
+                v[t - Ks * (Ks + 1) / 2] = s;
+            }
+        }
+        if (Q > 1) break;
     }
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 32) {
         double m = 0.0;
         for (int i = 0; i < n_gmax; i++) m = fmax(m, partial_gmax[i]);
         for (int r = 0; r < nranks; r++) red[red_off_gmax(Ks) + r] = (r == rank) ? m : 0.0;
