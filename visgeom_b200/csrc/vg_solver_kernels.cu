@@ -13,22 +13,22 @@ __host__ __device__ inline int pk(int a, int b, int W) { return a * W - a * (a -
 __device__ __forceinline__ int pks(int a, int b, int W) { return a <= b ? pk(a, b, W) : pk(b, a, W); }
 
 constexpr int ACC_THREADS = 256;
-constexpr int POSE_THREADS = 128;
-constexpr int GRAM_POSES = 64;       // poses per block in gram_reduce
-constexpr int GRAM_THREADS = 224;    // >= Ks(Ks+1)/2 + Ks for Ks <= 18; larger Ks loops
+constexpr int POSE_THREADS = 128;     // pose_backsub
+constexpr int FACTOR_THREADS = 64;    // pose_factor: one pose per thread, >= one block per SM at 10 000 poses
 
 // ---- per-pose factorisation ------------------------------------------------------------
 // lower-triangular packed index (i >= j)
 __device__ __forceinline__ constexpr int lt(int i, int j) { return i * (i + 1) / 2 + j; }
 
-__device__ __forceinline__ void forward_subst(const double (&Lm)[21], double (&x)[6])
+// x <- L^-1 x; invd = reciprocals of L's diagonal (one division per pivot instead of one per solve)
+__device__ __forceinline__ void forward_subst(const double (&Lm)[21], const double (&invd)[6], double (&x)[6])
 {
 #pragma unroll
     for (int i = 0; i < 6; i++) {
         double s = x[i];
 #pragma unroll
         for (int k = 0; k < i; k++) s = fma(-Lm[lt(i, k)], x[k], s);
-        x[i] = s / Lm[lt(i, i)];
+        x[i] = s * invd[i];
     }
 }
 
@@ -43,12 +43,64 @@ __device__ __forceinline__ void backward_subst(const double (&Lm)[21], double (&
     }
 }
 
-__global__ void __launch_bounds__(POSE_THREADS)
+// ---- Schur complement terms: S_red = sum Z^T Z, v_red = sum Z^T z -----------------------
+// Tail of pose_factor: the block's poses (one per thread) are folded into one row of partial sums.
+// thread = (entry t of the upper triangle of Z^T Z plus the Z^T z column, slice q of the block's poses); the
+// slices of an entry are added in slice order afterwards, so the sum order is fixed.  sh: blockDim.x doubles.
+__device__ __forceinline__ void block_gram(int n_pose, int Ks, const double *ws, double *partial, double *sh)
+{
+    const int npair = Ks * (Ks + 1) / 2 + Ks;
+    const int p0 = blockIdx.x * blockDim.x, p1 = min(n_pose, p0 + (int)blockDim.x);
+    const int stride = pose_ws_stride(Ks);
+    const int Q = max(1, (int)blockDim.x / npair);
+    const int per = ((int)blockDim.x + Q - 1) / Q;
+    for (int t0 = 0; t0 < npair; t0 += blockDim.x) {
+        const int q = Q > 1 ? threadIdx.x / npair : 0;
+        const int t = Q > 1 ? threadIdx.x - q * npair : t0 + threadIdx.x;
+        double s = 0.0;
+        const bool active = t < npair && q < Q;
+        if (active) {
+            int a, b;   // b == Ks -> the z column
+            if (t < Ks * (Ks + 1) / 2) {
+                a = 0; int rem = t;
+                while (rem >= Ks - a) { rem -= Ks - a; a++; }
+                b = a + rem;
+            } else {
+                a = t - Ks * (Ks + 1) / 2; b = Ks;
+            }
+            const int q0 = p0 + q * per, q1 = min(p1, q0 + per);
+            for (int p = q0; p < q1; p++) {
+                const double *w = ws + (size_t)p * stride;
+                const double *Z = w + 33, *z = w + 27;
+#pragma unroll
+                for (int k = 0; k < 6; k++) {
+                    const double za = __ldcg(Z + k * Ks + a);
+                    const double zb = (b < Ks) ? __ldcg(Z + k * Ks + b) : __ldcg(z + k);
+                    s = fma(za, zb, s);
+                }
+            }
+        }
+        if (Q > 1) {
+            __syncthreads();
+            sh[threadIdx.x] = s;
+            __syncthreads();
+            if (threadIdx.x < npair) {
+                double tot = 0.0;
+                for (int qq = 0; qq < Q; qq++) tot += sh[qq * npair + threadIdx.x];
+                partial[(size_t)blockIdx.x * npair + threadIdx.x] = tot;
+            }
+            break;
+        }
+        if (active) partial[(size_t)blockIdx.x * npair + t] = s;
+    }
+}
+
+__global__ void __launch_bounds__(FACTOR_THREADS)
 pose_factor_kernel(const DatasetDesc *desc_all, int n_pose, int Ks,
                    const int *pose_start, const int *contrib_ds, const int *contrib_img,
-                   double *scale, LmConsts lm, double *ws, double *partial_gmax, int *fail_flag)
+                   double *scale, LmConsts lm, double *ws, double *partial_gmax, double *partial_gram, int *fail_flag)
 {
-    __shared__ double sh_max[POSE_THREADS];
+    __shared__ double sh_max[FACTOR_THREADS];
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     double gmax = 0.0;
     if (p < n_pose) {
@@ -70,7 +122,7 @@ pose_factor_kernel(const DatasetDesc *desc_all, int n_pose, int Ks,
             }
         }
         double *w = ws + (size_t)p * pose_ws_stride(Ks);
-        double Lm[21], lam[6];
+        double Lm[21], lam[6], invd[6] = {1.0, 1.0, 1.0, 1.0, 1.0, 1.0};
         bool empty = true;
 #pragma unroll
         for (int k = 0; k < 6; k++) {
@@ -111,6 +163,7 @@ pose_factor_kernel(const DatasetDesc *desc_all, int n_pose, int Ks,
                 s = sqrt(s);
                 Lm[lt(j, j)] = s;
                 const double inv = 1.0 / s;
+                invd[j] = inv;
 #pragma unroll
                 for (int i = j + 1; i < 6; i++) {
                     double t = Lm[lt(i, j)];
@@ -121,13 +174,15 @@ pose_factor_kernel(const DatasetDesc *desc_all, int n_pose, int Ks,
             }
         }
         if (!ok) atomicExch(fail_flag, 1);
-        forward_subst(Lm, b);   // z = L^-1 b
+        forward_subst(Lm, invd, b);   // z = L^-1 b
 #pragma unroll
         for (int i = 0; i < 21; i++) w[i] = Lm[i];
 #pragma unroll
         for (int k = 0; k < 6; k++) { w[21 + k] = lam[k]; w[27 + k] = b[k]; }
         double *Z = w + 33;     // 6 x Ks, row-major
-        for (int i = 0; i < 6 * Ks; i++) Z[i] = 0.0;
+        const bool single = (c1 - c0 == 1);      // one image observes this pose: every Z entry is written once
+        if (!single)
+            for (int i = 0; i < 6 * Ks; i++) Z[i] = 0.0;
         for (int c = c0; c < c1; c++) {
             const DatasetDesc &d = desc_all[contrib_ds[c]];
             const double *H = d.H + (size_t)contrib_img[c] * d.ne;
@@ -137,71 +192,32 @@ pose_factor_kernel(const DatasetDesc *desc_all, int n_pose, int Ks,
                 double e[6];
 #pragma unroll
                 for (int i = 0; i < 6; i++) e[i] = H[pks(col, pc + i, W)];
-                forward_subst(Lm, e);
+                forward_subst(Lm, invd, e);
+                if (single) {
 #pragma unroll
-                for (int i = 0; i < 6; i++) Z[i * Ks + sidx] += e[i];
+                    for (int i = 0; i < 6; i++) Z[i * Ks + sidx] = e[i];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 6; i++) Z[i * Ks + sidx] += e[i];
+                }
             }
+            if (single)      // shared columns this dataset does not touch
+                for (int sidx = 0; sidx < Ks; sidx++) {
+                    bool touched = false;
+                    for (int q = 0; q < d.n_sl; q++) touched = touched || d.sl_idx[q] == sidx;
+                    if (!touched)
+                        for (int i = 0; i < 6; i++) Z[i * Ks + sidx] = 0.0;
+                }
         }
     }
     sh_max[threadIdx.x] = gmax;
-    __syncthreads();
+    __syncthreads();          // also: this block's Z, z are written (read back below by other threads of the block)
     for (int off = blockDim.x / 2; off > 0; off >>= 1) {
         if (threadIdx.x < off) sh_max[threadIdx.x] = fmax(sh_max[threadIdx.x], sh_max[threadIdx.x + off]);
         __syncthreads();
     }
     if (threadIdx.x == 0) partial_gmax[blockIdx.x] = sh_max[0];
-}
-
-// ---- Schur complement terms: S_red = sum Z^T Z, v_red = sum Z^T z -----------------------
-__global__ void __launch_bounds__(GRAM_THREADS)
-gram_kernel(int n_pose, int Ks, const double *ws, double *partial)
-{
-    // thread = (entry t of the upper triangle of Z^T Z plus the Z^T z column, slice q of the block's poses);
-    // the slices of an entry are added in slice order afterwards, so the sum order is fixed
-    __shared__ double sh[GRAM_THREADS];
-    const int npair = Ks * (Ks + 1) / 2 + Ks;
-    const int p0 = blockIdx.x * GRAM_POSES, p1 = min(n_pose, p0 + GRAM_POSES);
-    const int stride = pose_ws_stride(Ks);
-    const int Q = max(1, (int)blockDim.x / npair);
-    const int per = (GRAM_POSES + Q - 1) / Q;
-    for (int t0 = 0; t0 < npair; t0 += blockDim.x) {
-        const int q = Q > 1 ? threadIdx.x / npair : 0;
-        const int t = Q > 1 ? threadIdx.x - q * npair : t0 + threadIdx.x;
-        double s = 0.0;
-        const bool active = t < npair && q < Q;
-        if (active) {
-            int a, b;   // b == Ks -> the z column
-            if (t < Ks * (Ks + 1) / 2) {
-                a = 0; int rem = t;
-                while (rem >= Ks - a) { rem -= Ks - a; a++; }
-                b = a + rem;
-            } else {
-                a = t - Ks * (Ks + 1) / 2; b = Ks;
-            }
-            const int q0 = p0 + q * per, q1 = min(p1, q0 + per);
-            for (int p = q0; p < q1; p++) {
-                const double *w = ws + (size_t)p * stride;
-                const double *Z = w + 33, *z = w + 27;
-#pragma unroll
-                for (int k = 0; k < 6; k++) {
-                    const double za = Z[k * Ks + a];
-                    const double zb = (b < Ks) ? Z[k * Ks + b] : z[k];
-                    s = fma(za, zb, s);
-                }
-            }
-        }
-        if (Q > 1) {
-            sh[threadIdx.x] = s;
-            __syncthreads();
-            if (threadIdx.x < npair) {
-                double tot = 0.0;
-                for (int qq = 0; qq < Q; qq++) tot += sh[qq * npair + threadIdx.x];
-                partial[(size_t)blockIdx.x * npair + threadIdx.x] = tot;
-            }
-            break;
-        }
-        if (active) partial[(size_t)blockIdx.x * npair + t] = s;
-    }
+    block_gram(n_pose, Ks, ws, partial_gram, sh_max);
 }
 
 __global__ void __launch_bounds__(256)
@@ -359,10 +375,9 @@ void build_finalize_tables(const DatasetDesc *h_desc, const int *grids, int n_ds
 
 size_t pose_scratch(int n_pose, int Ks)
 {
-    const size_t nb_pose = (n_pose + POSE_THREADS - 1) / POSE_THREADS;
-    const size_t nb_gram = (n_pose + GRAM_POSES - 1) / GRAM_POSES;
+    const size_t nb_pose = (n_pose + FACTOR_THREADS - 1) / FACTOR_THREADS;
     const size_t npair = (size_t)Ks * (Ks + 1) / 2 + Ks;
-    return nb_pose * 4 + nb_gram * npair + 16;
+    return nb_pose * 4 + nb_pose * npair + 16;
 }
 
 cudaError_t launch_pose_schur(const DatasetDesc *d_desc, int n_pose, int Ks,
@@ -370,18 +385,16 @@ cudaError_t launch_pose_schur(const DatasetDesc *d_desc, int n_pose, int Ks,
                               double *scale, LmConsts lm, double *ws, double *partial, size_t partial_doubles,
                               double *red, int *fail_flag, int rank, int nranks, SolverLaunch sl)
 {
-    const int nb_pose = (n_pose + POSE_THREADS - 1) / POSE_THREADS;
-    const int nb_gram = (n_pose + GRAM_POSES - 1) / GRAM_POSES;
+    const int nb_pose = (n_pose + FACTOR_THREADS - 1) / FACTOR_THREADS;
     if (pose_scratch(n_pose, Ks) > partial_doubles) return cudaErrorInvalidValue;
     double *p_gmax = partial;
     double *p_gram = partial + nb_pose;
     if (n_pose > 0) {
-        pose_factor_kernel<<<nb_pose, POSE_THREADS, 0, sl.stream>>>(d_desc, n_pose, Ks, pose_start, contrib_ds,
-                                                                   contrib_img, scale, lm, ws, p_gmax, fail_flag);
-        gram_kernel<<<nb_gram, GRAM_THREADS, 0, sl.stream>>>(n_pose, Ks, ws, p_gram);
-        if (sl.launches) (*sl.launches) += 2;
+        pose_factor_kernel<<<nb_pose, FACTOR_THREADS, 0, sl.stream>>>(d_desc, n_pose, Ks, pose_start, contrib_ds,
+                                                                     contrib_img, scale, lm, ws, p_gmax, p_gram, fail_flag);
+        if (sl.launches) (*sl.launches)++;
     }
-    finalize_gram_kernel<<<1, 256, 0, sl.stream>>>(Ks, n_pose > 0 ? nb_gram : 0, p_gram, n_pose > 0 ? nb_pose : 0, p_gmax,
+    finalize_gram_kernel<<<1, 256, 0, sl.stream>>>(Ks, n_pose > 0 ? nb_pose : 0, p_gram, n_pose > 0 ? nb_pose : 0, p_gmax,
                                                    red, fail_flag, rank, nranks);
     if (sl.launches) (*sl.launches)++;
     return cudaGetLastError();
