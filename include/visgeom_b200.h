@@ -150,6 +150,21 @@ typedef struct {
 
 void vg_solve_options_default(vg_solve_options *o);
 
+/* ---- inner level, the other functors of the global problem -------------------------------
+ * Batched over n independent blocks, host buffers, Ceres layouts (residual 6, Jacobians row-major 6 x 6).
+ *
+ * TransformationPrior(stiffness, xi_prior)::Evaluate(xi)   calib_cost_functions.h:83-108, .cpp:215-228
+ *   r = A (R e_t, R e_r), e = xi_prior^-1 o xi, A = diag(stiffness) with its rotation block times
+ *   interOmegaRot(prior rotation); the Jacobian the functor reports is A itself.  J nullable. */
+int vg_eval_transformation_prior(int n, const double *stiffness /* n x 6 */, const double *xi_prior /* n x 6 */,
+                                 const double *xi /* n x 6 */, double *r /* n x 6 */, double *J /* n x 36 */);
+/* OdometryPrior(errV, errW, lambda, odom1, odom2)::Evaluate(xi1, xi2)   calib_cost_functions.cpp:119-213
+ *   zeta_prior = odom1^-1 o odom2, r = A (zeta_prior^-1 o (xi1^-1 o xi2)); J1, J2 nullable. */
+int vg_eval_odometry_prior(int n, double errV, double errW, double lambda,
+                           const double *odom1 /* n x 6 */, const double *odom2 /* n x 6 */,
+                           const double *xi1 /* n x 6 */, const double *xi2 /* n x 6 */,
+                           double *r /* n x 6 */, double *J1 /* n x 36 */, double *J2 /* n x 36 */);
+
 /* device < 0 -> current device */
 vg_problem *vg_problem_create(int device);
 void vg_problem_destroy(vg_problem *p);
@@ -164,6 +179,20 @@ int vg_problem_set_bounds(vg_problem *p, int camera, int idx, double lower, doub
  * transforms; values n x 6 [t,r]; constant -> SetParameterBlockConstant (:604-610).
  * Returns transform id >= 0. */
 int vg_problem_add_transform(vg_problem *p, int is_global, int constant, int n, const double *values);
+
+/* addResiduals "transformation_prior", unified_calibration.cpp:808-829: a TransformationPrior block on element
+ * `index` of a transform (0 for a global one; the reference always takes element 0, unified_calibration.h:161-165).
+ * xi_prior NULL -> the element's value at the time of the call, which is what the reference passes (:826-827).
+ * Returns the block id >= 0. */
+int vg_problem_add_transformation_prior(vg_problem *p, int transform, int index, const double *stiffness /* 6 */,
+                                        const double *xi_prior /* 6 or NULL */);
+/* addResiduals "odometry", :742-807: one OdometryPrior block per pair of consecutive elements of a sequence
+ * transform, built from n = its length odometry readings (n x 6).  The pose part of the normal equations becomes
+ * block tridiagonal along that sequence.  Returns the number of blocks added. */
+int vg_problem_add_odometry(vg_problem *p, int transform, double errV, double errW, double lambda, int n,
+                            const double *odom /* n x 6 */);
+/* "anchor" (:803-806): SetParameterBlockConstant on ONE element of a sequence transform */
+int vg_problem_set_pose_constant(vg_problem *p, int transform, int index, int constant);
 
 /* addGridResidualBlocks, :514-568: one residual block per image of the dataset.
  * obs n_img x P x 2 (host).  seq_index (nullable -> identity) maps image i to the

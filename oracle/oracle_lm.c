@@ -23,7 +23,13 @@ typedef struct {
     int shared_off;   /* global & free */
     int pose_off;     /* sequence & free */
     double *values;
+    unsigned char *fixed;   /* per element: SetParameterBlockConstant on one element ("anchor", unified_calibration.cpp:803-806) */
 } tr_t;
+
+/* TransformationPrior block on element `index` of a transform (unified_calibration.cpp:808-829) */
+typedef struct { int tr, index; vgo_transformation_prior f; } tp_t;
+/* OdometryPrior block between elements i and i+1 of a sequence transform (unified_calibration.cpp:793-802) */
+typedef struct { int tr, i; vgo_odometry_prior f; } op_t;
 
 typedef struct {
     int cam, P, n_img, L, D, ne;
@@ -34,10 +40,12 @@ typedef struct {
 } ds_t;
 
 struct vgo_problem {
-    int n_cam, n_tr, n_ds;
+    int n_cam, n_tr, n_ds, n_tp, n_op, n_fixed;
     cam_t *cams;
     tr_t *trs;
     ds_t *dss;
+    tp_t *tps;
+    op_t *ops;
 };
 
 static double now_s(void)
@@ -73,7 +81,8 @@ vgo_problem *vgo_problem_create(void)
 void vgo_problem_destroy(vgo_problem *p)
 {
     if (!p) return;
-    for (int i = 0; i < p->n_tr; i++) free(p->trs[i].values);
+    for (int i = 0; i < p->n_tr; i++) { free(p->trs[i].values); free(p->trs[i].fixed); }
+    free(p->tps); free(p->ops);
     for (int i = 0; i < p->n_ds; i++) {
         free(p->dss[i].board); free(p->dss[i].obs); free(p->dss[i].seq_index); free(p->dss[i].H);
     }
@@ -112,7 +121,39 @@ int vgo_problem_add_transform(vgo_problem *p, int is_global, int constant, int n
     t->shared_off = t->pose_off = -1;
     t->values = (double *)malloc(sizeof(double) * 6 * (size_t)n);
     memcpy(t->values, values, sizeof(double) * 6 * (size_t)n);
+    t->fixed = (unsigned char *)calloc((size_t)n, 1);
     return p->n_tr++;
+}
+
+int vgo_problem_add_transformation_prior(vgo_problem *p, int tr, int index, const double *stiffness, const double *xi_prior)
+{
+    if (tr < 0 || tr >= p->n_tr || index < 0 || index >= p->trs[tr].n) return -1;
+    p->tps = (tp_t *)realloc(p->tps, sizeof(tp_t) * (size_t)(p->n_tp + 1));
+    tp_t *t = &p->tps[p->n_tp];
+    t->tr = tr; t->index = index;
+    /* the prior value is the transform's value when the block is created (calib_cost_functions.h:85-86) */
+    vgo_transformation_prior_init(&t->f, stiffness, xi_prior ? xi_prior : p->trs[tr].values + 6 * (size_t)index);
+    return p->n_tp++;
+}
+
+int vgo_problem_add_odometry(vgo_problem *p, int tr, double errV, double errW, double lambda, int n, const double *odom)
+{
+    if (tr < 0 || tr >= p->n_tr || p->trs[tr].is_global || n != p->trs[tr].n) return -1;
+    p->ops = (op_t *)realloc(p->ops, sizeof(op_t) * (size_t)(p->n_op + (n > 1 ? n - 1 : 0) + 1));
+    for (int i = 0; i + 1 < n; i++) {
+        op_t *e = &p->ops[p->n_op++];
+        e->tr = tr; e->i = i;
+        vgo_odometry_prior_init(&e->f, errV, errW, lambda, odom + 6 * (size_t)i, odom + 6 * (size_t)(i + 1));
+    }
+    return 0;
+}
+
+int vgo_problem_set_pose_constant(vgo_problem *p, int tr, int index, int constant)
+{
+    if (tr < 0 || tr >= p->n_tr || index < 0 || index >= p->trs[tr].n) return -1;
+    p->n_fixed += (constant ? 1 : 0) - (p->trs[tr].fixed[index] ? 1 : 0);
+    p->trs[tr].fixed[index] = constant ? 1 : 0;
+    return 0;
 }
 
 int vgo_problem_add_dataset(vgo_problem *p, int cam, int P, const double *board,
@@ -220,6 +261,7 @@ typedef struct {
     int Ks, n_pose;
     double *A, *ga;            /* Ks x Ks, Ks */
     double *C, *E, *b;         /* n_pose x 36, n_pose x Ks x 6, n_pose x 6 */
+    double *O;                 /* n_op x 36: block (pose of element i+1, pose of element i) of J^T J */
     double cost;
 } normal_eq;
 
@@ -247,6 +289,19 @@ static double evaluate_all(vgo_problem *p, int threads)
         ds_t *d = &p->dss[k];
         ds_eval(p, d, NULL, 1, threads);
         for (int i = 0; i < d->n_img; i++) cost += 0.5 * d->H[(size_t)i * d->ne + d->ne - 1];
+    }
+    for (int k = 0; k < p->n_tp; k++) {
+        const tp_t *t = &p->tps[k];
+        double r[6];
+        vgo_transformation_prior_eval(&t->f, p->trs[t->tr].values + 6 * (size_t)t->index, r, NULL);
+        for (int i = 0; i < 6; i++) cost += 0.5 * r[i] * r[i];
+    }
+    for (int k = 0; k < p->n_op; k++) {
+        const op_t *e = &p->ops[k];
+        const double *x = p->trs[e->tr].values + 6 * (size_t)e->i;
+        double r[6];
+        vgo_odometry_prior_eval(&e->f, x, x + 6, r, NULL, NULL);
+        for (int i = 0; i < 6; i++) cost += 0.5 * r[i] * r[i];
     }
     return cost;
 }
@@ -314,6 +369,144 @@ static void assemble(const vgo_problem *p, normal_eq *n)
             }
         }
     }
+    /* the 6-residual blocks: J^T J, J^T r and 1/2 r^T r of every prior (what Ceres forms from the functor's output) */
+    for (int k = 0; k < p->n_tp; k++) {
+        const tp_t *t = &p->tps[k];
+        const tr_t *tr = &p->trs[t->tr];
+        double r[6], J[36];
+        vgo_transformation_prior_eval(&t->f, tr->values + 6 * (size_t)t->index, r, J);
+        for (int i = 0; i < 6; i++) n->cost += 0.5 * r[i] * r[i];
+        for (int a = 0; a < 6; a++) {
+            double g = 0;
+            for (int i = 0; i < 6; i++) g += J[6 * i + a] * r[i];
+            for (int b2 = 0; b2 < 6; b2++) {
+                double h = 0;
+                for (int i = 0; i < 6; i++) h += J[6 * i + a] * J[6 * i + b2];
+                if (tr->shared_off >= 0) n->A[(tr->shared_off + a) * Ks + tr->shared_off + b2] += h;
+                else if (tr->pose_off >= 0) n->C[(size_t)(tr->pose_off + t->index) * 36 + 6 * a + b2] += h;
+            }
+            if (tr->shared_off >= 0) n->ga[tr->shared_off + a] += g;
+            else if (tr->pose_off >= 0) n->b[(size_t)(tr->pose_off + t->index) * 6 + a] += g;
+        }
+    }
+    for (int k = 0; k < p->n_op; k++) {
+        const op_t *e = &p->ops[k];
+        const tr_t *tr = &p->trs[e->tr];
+        const double *x = tr->values + 6 * (size_t)e->i;
+        double r[6], J1[36], J2[36];
+        vgo_odometry_prior_eval(&e->f, x, x + 6, r, J1, J2);
+        for (int i = 0; i < 6; i++) n->cost += 0.5 * r[i] * r[i];
+        memset(n->O + 36 * (size_t)k, 0, 36 * sizeof(double));
+        if (tr->pose_off < 0) continue;
+        const size_t q1 = (size_t)(tr->pose_off + e->i), q2 = q1 + 1;
+        for (int a = 0; a < 6; a++) {
+            double g1 = 0, g2 = 0;
+            for (int i = 0; i < 6; i++) { g1 += J1[6 * i + a] * r[i]; g2 += J2[6 * i + a] * r[i]; }
+            n->b[q1 * 6 + a] += g1; n->b[q2 * 6 + a] += g2;
+            for (int b2 = 0; b2 < 6; b2++) {
+                double h11 = 0, h22 = 0, h21 = 0;
+                for (int i = 0; i < 6; i++) {
+                    h11 += J1[6 * i + a] * J1[6 * i + b2];
+                    h22 += J2[6 * i + a] * J2[6 * i + b2];
+                    h21 += J2[6 * i + a] * J1[6 * i + b2];
+                }
+                n->C[q1 * 36 + 6 * a + b2] += h11;
+                n->C[q2 * 36 + 6 * a + b2] += h22;
+                n->O[36 * (size_t)k + 6 * a + b2] = h21;
+            }
+        }
+    }
+    /* constant elements of a free sequence: their columns leave the problem */
+    for (int i = 0; i < p->n_tr; i++) {
+        const tr_t *t = &p->trs[i];
+        if (t->pose_off < 0) continue;
+        for (int q = 0; q < t->n; q++) {
+            if (!t->fixed[q]) continue;
+            const size_t z = (size_t)(t->pose_off + q);
+            memset(n->C + z * 36, 0, 36 * sizeof(double));
+            memset(n->E + z * Ks * 6, 0, sizeof(double) * 6 * (size_t)Ks);
+            memset(n->b + z * 6, 0, 6 * sizeof(double));
+        }
+    }
+    for (int k = 0; k < p->n_op; k++) {
+        const op_t *e = &p->ops[k];
+        const tr_t *tr = &p->trs[e->tr];
+        if (tr->fixed[e->i] || tr->fixed[e->i + 1]) memset(n->O + 36 * (size_t)k, 0, 36 * sizeof(double));
+    }
+}
+
+static int chol(double *M, int n);
+static void chol_solve(const double *Lm, int n, double *x);
+static double clampd(double v, double lo, double hi);
+
+/* LM step of a problem whose pose blocks are coupled (odometry): the full (Ks + 6 n_pose) system is formed and
+ * factorised densely -- the same normal equations, no structure exploited (an independent route to the step the
+ * CUDA engine computes with a block-tridiagonal elimination).  Returns 1 and da, dp, model_change on success. */
+static int dense_step(const vgo_problem *p, const normal_eq *n, const double *scale_a, const double *scale_p,
+                      double radius, const vgo_solve_options *o, double *da, double *dp, double *model_change)
+{
+    const int Ks = n->Ks, NP = n->n_pose;
+    const size_t N = (size_t)Ks + 6 * (size_t)NP;
+    double *M = (double *)calloc(N * N + 1, sizeof(double));
+    double *Hm = (double *)calloc(N * N + 1, sizeof(double));
+    double *g = (double *)calloc(N + 1, sizeof(double));
+    double *d = (double *)calloc(N + 1, sizeof(double));
+    for (int i = 0; i < Ks; i++) {
+        for (int j = 0; j < Ks; j++) Hm[(size_t)i * N + j] = n->A[i * Ks + j];
+        g[i] = n->ga[i];
+    }
+    for (int q = 0; q < NP; q++) {
+        const size_t r0 = (size_t)Ks + 6 * (size_t)q;
+        for (int a = 0; a < 6; a++) {
+            for (int b2 = 0; b2 < 6; b2++) Hm[(r0 + a) * N + r0 + b2] = n->C[(size_t)q * 36 + 6 * a + b2];
+            for (int s2 = 0; s2 < Ks; s2++) {
+                const double e = n->E[((size_t)q * Ks + s2) * 6 + a];
+                Hm[(r0 + a) * N + s2] = e; Hm[(size_t)s2 * N + r0 + a] = e;
+            }
+            g[r0 + a] = n->b[(size_t)q * 6 + a];
+        }
+    }
+    for (int k = 0; k < p->n_op; k++) {
+        const op_t *e = &p->ops[k];
+        const tr_t *tr = &p->trs[e->tr];
+        if (tr->pose_off < 0) continue;
+        const size_t r1 = (size_t)Ks + 6 * (size_t)(tr->pose_off + e->i), r2 = r1 + 6;
+        for (int a = 0; a < 6; a++)
+            for (int b2 = 0; b2 < 6; b2++) {
+                const double h = n->O[36 * (size_t)k + 6 * a + b2];
+                Hm[(r2 + a) * N + r1 + b2] = h; Hm[(r1 + b2) * N + r2 + a] = h;
+            }
+    }
+    memcpy(M, Hm, sizeof(double) * N * N);
+    for (size_t j = 0; j < N; j++) {
+        const double sc = j < (size_t)Ks ? scale_a[j] : scale_p[j - (size_t)Ks];
+        const double s2 = sc * sc, hjj = Hm[j * N + j];
+        if (j >= (size_t)Ks) {
+            /* a pose nothing observes / a constant element: identity row, zero step */
+            const size_t q = (j - (size_t)Ks) / 6;
+            int empty = 1;
+            for (int k = 0; k < 6; k++) if (n->C[q * 36 + 7 * k] != 0.0) empty = 0;
+            if (empty) { M[j * N + j] = 1.0; continue; }
+        }
+        M[j * N + j] += clampd(s2 * hjj, o->min_lm_diagonal, o->max_lm_diagonal) / (radius * s2);
+    }
+    int ok = chol(M, (int)N) == 0;
+    if (ok) {
+        for (size_t j = 0; j < N; j++) d[j] = -g[j];
+        chol_solve(M, (int)N, d);
+        double gd = 0, dHd = 0;
+        for (size_t i = 0; i < N; i++) {
+            gd += g[i] * d[i];
+            double t = 0;
+            for (size_t j = 0; j < N; j++) t += Hm[i * N + j] * d[j];
+            dHd += d[i] * t;
+        }
+        *model_change = -gd - 0.5 * dHd;
+        memcpy(da, d, sizeof(double) * (size_t)Ks);
+        memcpy(dp, d + Ks, sizeof(double) * 6 * (size_t)NP);
+    }
+    free(M); free(Hm); free(g); free(d);
+    return ok;
 }
 
 /* in-place Cholesky of an n x n SPD matrix (row-major, lower); returns 0 on success */
@@ -389,6 +582,8 @@ int vgo_problem_solve(vgo_problem *p, const vgo_solve_options *o, vgo_solve_summ
     n.C = (double *)calloc(36 * (size_t)(NP + 1), sizeof(double));
     n.E = (double *)calloc(6 * (size_t)(Ks + 1) * (size_t)(NP + 1), sizeof(double));
     n.b = (double *)calloc(6 * (size_t)(NP + 1), sizeof(double));
+    n.O = (double *)calloc(36 * (size_t)(p->n_op + 1), sizeof(double));
+    const int coupled = p->n_op > 0 || p->n_fixed > 0;     /* pose blocks no longer independent / all free */
     double *scale_a = (double *)malloc(sizeof(double) * (size_t)(Ks + 1));
     double *scale_p = (double *)malloc(sizeof(double) * 6 * (size_t)(NP + 1));
     double *Lp = (double *)malloc(sizeof(double) * 36 * (size_t)(NP + 1));   /* chol factors */
@@ -444,6 +639,11 @@ int vgo_problem_solve(vgo_problem *p, const vgo_solve_options *o, vgo_solve_summ
 
         /* ---- LM step at the current radius ---- */
         int ok = 1;
+        double model_change = 0, step2 = 0, x2 = 0;
+        if (coupled) {
+            ok = dense_step(p, &n, scale_a, scale_p, radius, o, da, dp, &model_change);
+            if (ok && !(model_change > 0.0)) ok = 0;
+        } else {
         memcpy(S, n.A, sizeof(double) * (size_t)Ks * Ks);
         for (int j = 0; j < Ks; j++) {
             double s2 = scale_a[j] * scale_a[j];
@@ -483,7 +683,6 @@ int vgo_problem_solve(vgo_problem *p, const vgo_solve_options *o, vgo_solve_summ
             if (chol(S, Ks)) ok = 0;
             else { memcpy(da, rhs, sizeof(double) * (size_t)Ks); chol_solve(S, Ks, da); }
         }
-        double model_change = 0, step2 = 0, x2 = 0;
         if (ok) {
             /* back substitution + model cost change = -g^T d - 1/2 d^T H d */
             double gd = 0, dHd = 0;
@@ -518,6 +717,7 @@ int vgo_problem_solve(vgo_problem *p, const vgo_solve_options *o, vgo_solve_summ
             model_change = -gd - 0.5 * dHd;
             if (!(model_change > 0.0)) ok = 0;
         }
+        }
         if (!ok) {
             /* invalid step (Ceres: StepIsInvalid) */
             invalid_run++;
@@ -551,7 +751,7 @@ int vgo_problem_solve(vgo_problem *p, const vgo_solve_options *o, vgo_solve_summ
                 }
             } else if (t->pose_off >= 0) {
                 for (int q = 0; q < t->n; q++)
-                    for (int k = 0; k < 6; k++) {
+                    for (int k = 0; k < 6 && !t->fixed[q]; k++) {
                         double x = t->values[6 * q + k], dd = dp[6 * (size_t)(t->pose_off + q) + k];
                         x2 += x * x; step2 += dd * dd;
                         t->values[6 * q + k] = x + dd;
@@ -594,7 +794,7 @@ int vgo_problem_solve(vgo_problem *p, const vgo_solve_options *o, vgo_solve_summ
     sum->seconds_total = now_s() - t_start;
     sum->seconds_evaluate = t_eval;
     sum->num_evaluations = n_eval;
-    free(n.A); free(n.ga); free(n.C); free(n.E); free(n.b);
+    free(n.A); free(n.ga); free(n.C); free(n.E); free(n.b); free(n.O);
     free(scale_a); free(scale_p); free(Lp); free(S); free(rhs); free(da); free(dp); free(Y);
     return 0;
 }

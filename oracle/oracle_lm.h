@@ -66,6 +66,14 @@ int vgo_problem_add_transform(vgo_problem *p, int is_global, int constant, int n
 int vgo_problem_add_dataset(vgo_problem *p, int cam, int P, const double *board,
                             int n_img, const double *obs, const int *seq_index,
                             int chain_len, const int *transform_ids, const int *status);
+/* TransformationPrior on element `index` of a transform (0 for a global one); xi_prior NULL -> the element's
+ * current value, as unified_calibration.cpp:826-828 constructs it.  Returns the block id. */
+int vgo_problem_add_transformation_prior(vgo_problem *p, int tr, int index, const double *stiffness, const double *xi_prior);
+/* OdometryPrior between every pair of consecutive elements of a sequence transform, built from n odometry
+ * readings (unified_calibration.cpp:793-802) */
+int vgo_problem_add_odometry(vgo_problem *p, int tr, double errV, double errW, double lambda, int n, const double *odom);
+/* SetParameterBlockConstant on one element of a sequence ("anchor", unified_calibration.cpp:803-806) */
+int vgo_problem_set_pose_constant(vgo_problem *p, int tr, int index, int constant);
 int vgo_problem_solve(vgo_problem *p, const vgo_solve_options *o, vgo_solve_summary *s);
 int vgo_problem_get_camera(const vgo_problem *p, int cam, double *out);
 int vgo_problem_get_transform(const vgo_problem *p, int tr, double *out);

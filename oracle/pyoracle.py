@@ -95,10 +95,22 @@ class _Evaluator:
         return dict(r=r, J_intr=Ja, J_xi=Je, H=H)
 
 
+class TransformationPriorC(C.Structure):
+    _fields_ = [("xi_prior", C.c_double * 6), ("A", C.c_double * 36), ("R", C.c_double * 9)]
+
+
+class OdometryPriorC(C.Structure):
+    _fields_ = [("zeta_prior", C.c_double * 6), ("A", C.c_double * 36)]
+
+
 class Oracle(_Evaluator):
     def __init__(self):
         lib = C.CDLL(build())
         super().__init__(lib, "vgo")
+        lib.vgo_transformation_prior_init.argtypes = [C.POINTER(TransformationPriorC), c_dp, c_dp]
+        lib.vgo_transformation_prior_eval.argtypes = [C.POINTER(TransformationPriorC), c_dp, c_dp, c_dp]
+        lib.vgo_odometry_prior_init.argtypes = [C.POINTER(OdometryPriorC), C.c_double, C.c_double, C.c_double, c_dp, c_dp]
+        lib.vgo_odometry_prior_eval.argtypes = [C.POINTER(OdometryPriorC), c_dp, c_dp, c_dp, c_dp, c_dp]
         lib.vgo_max_threads.restype = C.c_int
         lib.vgo_lower_bound.restype = C.c_double
         lib.vgo_upper_bound.restype = C.c_double
@@ -119,6 +131,9 @@ class Oracle(_Evaluator):
         lib.vgo_problem_add_transform.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, c_dp]
         lib.vgo_problem_add_dataset.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp, C.c_int, c_dp, c_ip,
                                                 C.c_int, c_ip, c_ip]
+        lib.vgo_problem_add_transformation_prior.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp, c_dp]
+        lib.vgo_problem_add_odometry.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, c_dp]
+        lib.vgo_problem_set_pose_constant.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         lib.vgo_problem_solve.argtypes = [C.c_void_p, C.POINTER(SolveOptions), C.POINTER(SolveSummary)]
         lib.vgo_problem_get_camera.argtypes = [C.c_void_p, C.c_int, c_dp]
         lib.vgo_problem_get_transform.argtypes = [C.c_void_p, C.c_int, c_dp]
@@ -135,6 +150,23 @@ class Oracle(_Evaluator):
         o = SolveOptions()
         self.lib.vgo_solve_options_default(C.byref(o))
         return o
+
+    # ---- the prior functors (calib_cost_functions.h:64-108) ----
+    def transformation_prior(self, stiffness, xi_prior, xi):
+        """-> r (6), J (6, 6): TransformationPrior built from (stiffness, xi_prior), evaluated at xi."""
+        st = _f64(stiffness); xp = _f64(xi_prior); x = _f64(xi)
+        tp = TransformationPriorC(); r = np.zeros(6); J = np.zeros((6, 6))
+        self.lib.vgo_transformation_prior_init(C.byref(tp), _dp(st), _dp(xp))
+        self.lib.vgo_transformation_prior_eval(C.byref(tp), _dp(x), _dp(r), _dp(J))
+        return r, J
+
+    def odometry_prior(self, errV, errW, lam, odom1, odom2, xi1, xi2):
+        """-> r (6), J1, J2 (6, 6): OdometryPrior built from two odometry readings, evaluated at (xi1, xi2)."""
+        o1 = _f64(odom1); o2 = _f64(odom2); a = _f64(xi1); b = _f64(xi2)
+        op = OdometryPriorC(); r = np.zeros(6); J1 = np.zeros((6, 6)); J2 = np.zeros((6, 6))
+        self.lib.vgo_odometry_prior_init(C.byref(op), errV, errW, lam, _dp(o1), _dp(o2))
+        self.lib.vgo_odometry_prior_eval(C.byref(op), _dp(a), _dp(b), _dp(r), _dp(J1), _dp(J2))
+        return r, J1, J2
 
     # ---- small geometry helpers (for the unit tests of the restatement) ----
     def rotation_matrix(self, v):
@@ -223,6 +255,24 @@ class OracleProblem:
             raise ValueError(f"add_dataset failed: {did}")
         return did
 
+    def add_transformation_prior(self, transform, stiffness, index=0, xi_prior=None):
+        st = _f64(stiffness)
+        xp = None if xi_prior is None else _f64(xi_prior)
+        rc = self.lib.vgo_problem_add_transformation_prior(self.h, transform, index, _dp(st), None if xp is None else _dp(xp))
+        if rc < 0:
+            raise ValueError("add_transformation_prior failed")
+        return rc
+
+    def add_odometry(self, transform, errV, errW, lam, odom):
+        od = _f64(odom).reshape(-1, 6)
+        if self.lib.vgo_problem_add_odometry(self.h, transform, errV, errW, lam, od.shape[0], _dp(od)) < 0:
+            raise ValueError("add_odometry failed")
+        return od.shape[0] - 1
+
+    def set_pose_constant(self, transform, index, constant=True):
+        if self.lib.vgo_problem_set_pose_constant(self.h, transform, index, int(constant)) < 0:
+            raise ValueError("set_pose_constant failed")
+
     def solve(self, options=None):
         o = options or self.o.default_options()
         s = SolveSummary()
@@ -255,3 +305,17 @@ class Reference(_Evaluator):
         if path is None:
             raise FileNotFoundError("oracle/_ref/libvisgeom_ref.so not built (needs /root/reference)")
         super().__init__(C.CDLL(path), "vgref")
+        self.lib.vgref_transformation_prior.argtypes = [c_dp, c_dp, c_dp, c_dp, c_dp]
+        self.lib.vgref_odometry_prior.argtypes = [C.c_double, C.c_double, C.c_double, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]
+
+    def transformation_prior(self, stiffness, xi_prior, xi):
+        st = _f64(stiffness); xp = _f64(xi_prior); x = _f64(xi)
+        r = np.zeros(6); J = np.zeros((6, 6))
+        self.lib.vgref_transformation_prior(_dp(st), _dp(xp), _dp(x), _dp(r), _dp(J))
+        return r, J
+
+    def odometry_prior(self, errV, errW, lam, odom1, odom2, xi1, xi2):
+        o1 = _f64(odom1); o2 = _f64(odom2); a = _f64(xi1); b = _f64(xi2)
+        r = np.zeros(6); J1 = np.zeros((6, 6)); J2 = np.zeros((6, 6))
+        self.lib.vgref_odometry_prior(errV, errW, lam, _dp(o1), _dp(o2), _dp(a), _dp(b), _dp(r), _dp(J1), _dp(J2))
+        return r, J1, J2

@@ -120,4 +120,22 @@ double vgref_bound(int model, const double *intr, int idx, int upper)
     return upper ? cam->upperBound(idx) : cam->lowerBound(idx);
 }
 
+// the other residual types of the global problem (calib_cost_functions.h:64-108): constructed and evaluated
+// exactly as addResiduals does (unified_calibration.cpp:795-803, 827-828)
+void vgref_transformation_prior(const double *stiffness, const double *xi_prior, const double *xi, double *r, double *J)
+{
+    TransformationPrior cost(stiffness, xi_prior);
+    const double *params[1] = {xi};
+    double *jac[1] = {J};
+    cost.Evaluate(params, r, J ? jac : NULL);
+}
+void vgref_odometry_prior(double errV, double errW, double lambda, const double *odom1, const double *odom2,
+                          const double *xi1, const double *xi2, double *r, double *J1, double *J2)
+{
+    OdometryPrior cost(errV, errW, lambda, Transformation<double>(odom1), Transformation<double>(odom2));
+    const double *params[2] = {xi1, xi2};
+    double *jac[2] = {J1, J2};
+    cost.Evaluate(params, r, (J1 || J2) ? jac : NULL);
+}
+
 }  // extern "C"

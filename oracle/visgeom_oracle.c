@@ -753,6 +753,162 @@ int vgo_evaluate(int model, int P, const double *obs, const double *board,
     return 1;
 }
 
+/* ------------------------------------------------------------------ */
+/* 6x6 row-major helpers for the prior functors */
+static void mat6_mul(const double A[36], const double B[36], double C[36])
+{
+    for (int i = 0; i < 6; i++)
+        for (int j = 0; j < 6; j++) {
+            double s = A[6 * i] * B[j];
+            for (int k = 1; k < 6; k++) s += A[6 * i + k] * B[6 * k + j];
+            C[6 * i + j] = s;
+        }
+}
+
+static void mat6_vec(const double A[36], const double v[6], double o[6])
+{
+    for (int i = 0; i < 6; i++) {
+        double s = A[6 * i] * v[0];
+        for (int k = 1; k < 6; k++) s += A[6 * i + k] * v[k];
+        o[i] = s;
+    }
+}
+
+/* [[a, 0], [0, b]] with 3x3 blocks */
+static void blockdiag6(const double a[9], const double b[9], double M[36])
+{
+    memset(M, 0, 36 * sizeof(double));
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) { M[6 * i + j] = a[3 * i + j]; M[6 * (i + 3) + j + 3] = b[3 * i + j]; }
+}
+
+/* calib_cost_functions.h:85-98 */
+void vgo_transformation_prior_init(vgo_transformation_prior *tp, const double stiffness[6], const double xi_prior[6])
+{
+    memcpy(tp->xi_prior, xi_prior, 6 * sizeof(double));
+    memset(tp->A, 0, sizeof tp->A);
+    vgo_rotation_matrix(xi_prior + 3, tp->R);
+    for (int i = 0; i < 6; i++) tp->A[6 * i + i] = stiffness[i];
+    double M[9], D[9], DM[9];
+    vgo_inter_omega_rot(xi_prior + 3, M);
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) D[3 * i + j] = tp->A[6 * (i + 3) + j + 3];
+    mat3_mul(D, M, DM);                                     /* bottom-right = bottom-right * M, :95-96 */
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) tp->A[6 * (i + 3) + j + 3] = DM[3 * i + j];
+}
+
+/* calib_cost_functions.cpp:215-228 */
+void vgo_transformation_prior_eval(const vgo_transformation_prior *tp, const double xi[6], double r[6], double *J)
+{
+    double e[6], err[6];
+    vgo_inverse_compose(tp->xi_prior, xi, e);               /* :220 */
+    mat3_vec(tp->R, e, err);                                /* :221 */
+    mat3_vec(tp->R, e + 3, err + 3);                        /* :222 */
+    mat6_vec(tp->A, err, r);                                /* :223 */
+    if (J) memcpy(J, tp->A, 36 * sizeof(double));           /* :224-227: the Jacobian is A itself */
+}
+
+/* calib_cost_functions.cpp:119-173 */
+void vgo_odometry_prior_init(vgo_odometry_prior *op, double errV, double errW, double lambda,
+                             const double xi1[6], const double xi2[6])
+{
+    const double MIN_SIGMA_V = 0.01, MIN_SIGMA_W = 0.01, MIN_DELTA = 0.01, MIN_L = 0.01;
+    vgo_inverse_compose(xi1, xi2, op->zeta_prior);          /* :122 */
+    memset(op->A, 0, sizeof op->A);
+    const double delta = fmax(norm3(op->zeta_prior + 3), MIN_DELTA);
+    const double l = fmax(norm3(op->zeta_prior), MIN_L);
+    const double delta2 = delta / 2., l2 = l / 2.;
+    const double s = sin(delta2), c = cos(delta2);
+    const double dfdu[3][2] = { { c, l2 * s }, { -s, l2 * c }, { 0, 1 } };     /* :142-145 */
+    double Cu[2];
+    Cu[0] = fmax(errV * errV * l * l, MIN_SIGMA_V * MIN_SIGMA_V);              /* :147-151 */
+    Cu[1] = fmax(errW * errW * delta * delta, MIN_SIGMA_W * MIN_SIGMA_W);
+    /* Cx = dfdu Cu dfdu^T + lambda^2 I, evaluated left to right as (dfdu*Cu)*dfdu^T, :153 */
+    double Cx[9];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            const double a0 = dfdu[i][0] * Cu[0] + dfdu[i][1] * 0.;
+            const double a1 = dfdu[i][0] * 0. + dfdu[i][1] * Cu[1];
+            Cx[3 * i + j] = (a0 * dfdu[j][0] + a1 * dfdu[j][1]) + (lambda * lambda) * (i == j ? 1. : 0.);
+        }
+    /* 3x3 inverse by cofactors (what Eigen's fixed-size inverse computes), :154 */
+    double cof[3][3], inv[9];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+            cof[i][j] = Cx[3 * i1 + j1] * Cx[3 * i2 + j2] - Cx[3 * i1 + j2] * Cx[3 * i2 + j1];
+        }
+    const double det = Cx[0] * cof[0][0] + Cx[1] * cof[0][1] + Cx[2] * cof[0][2];
+    const double id = 1. / det;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) inv[3 * i + j] = cof[j][i] * id;
+    /* LLT, U = L^T, :155-156 */
+    double Lc[9] = { 0 };
+    for (int j = 0; j < 3; j++) {
+        double d = inv[3 * j + j];
+        for (int k = 0; k < j; k++) d -= Lc[3 * j + k] * Lc[3 * j + k];
+        Lc[3 * j + j] = sqrt(d);
+        for (int i = j + 1; i < 3; i++) {
+            double t = inv[3 * i + j];
+            for (int k = 0; k < j; k++) t -= Lc[3 * i + k] * Lc[3 * j + k];
+            Lc[3 * i + j] = t / Lc[3 * j + j];
+        }
+    }
+#define U_(i, j) Lc[3 * (j) + (i)]
+    op->A[0] = U_(0, 0); op->A[1] = U_(0, 1);               /* topLeftCorner<2,2>, :157 */
+    op->A[6] = U_(1, 0); op->A[7] = U_(1, 1);
+    op->A[5] = U_(0, 2); op->A[11] = U_(1, 2);              /* topRightCorner<2,1> of the 6x6: column 5, :158 */
+    op->A[14] = 1. / lambda;                                /* (2,2), :159 */
+    op->A[6 * 3 + 3] = 1. / lambda;                         /* B, :161-166 */
+    op->A[6 * 4 + 4] = 1. / lambda;
+    op->A[6 * 5 + 5] = U_(2, 2);
+#undef U_
+}
+
+/* calib_cost_functions.cpp:177-213 */
+void vgo_odometry_prior_eval(const vgo_odometry_prior *op, const double xi1[6], const double xi2[6],
+                             double r[6], double *J1, double *J2)
+{
+    double zeta[6], err[6];
+    vgo_inverse_compose(xi1, xi2, zeta);                    /* :182 */
+    vgo_inverse_compose(op->zeta_prior, zeta, err);         /* :187 */
+    mat6_vec(op->A, err, r);                                /* :188 */
+    if (J1) {                                               /* :193-203 */
+        double neg[3] = { -xi1[3], -xi1[4], -xi1[5] }, R10[9], M[9], R10M[9], Jb[36];
+        vgo_rotation_matrix(neg, R10);
+        vgo_inter_omega_rot(xi1 + 3, M);
+        mat3_mul(R10, M, R10M);
+        blockdiag6(R10, R10M, Jb);
+        /* zeta.screwTransfInv(), transformation.h:234-243 */
+        double nz[3] = { -zeta[3], -zeta[4], -zeta[5] }, Rz[9], th[9], Rth[9], TT[36];
+        vgo_rotation_matrix(nz, Rz);
+        hat3(zeta, th);
+        double nRz[9];
+        for (int i = 0; i < 9; i++) nRz[i] = -Rz[i];
+        mat3_mul(nRz, th, Rth);
+        memset(TT, 0, sizeof TT);
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) {
+                TT[6 * i + j] = Rz[3 * i + j];
+                TT[6 * i + j + 3] = Rth[3 * i + j];
+                TT[6 * (i + 3) + j + 3] = Rz[3 * i + j];
+            }
+        double nA[36], nATT[36];
+        for (int i = 0; i < 36; i++) nA[i] = -op->A[i];
+        mat6_mul(nA, TT, nATT);                             /* (-_A * TT) * J1, left to right */
+        mat6_mul(nATT, Jb, J1);
+    }
+    if (J2) {                                               /* :206-213 */
+        double neg[3] = { -xi2[3], -xi2[4], -xi2[5] }, R20[9], M[9], R20M[9], Jb[36];
+        vgo_rotation_matrix(neg, R20);
+        vgo_inter_omega_rot(xi2 + 3, M);
+        mat3_mul(R20, M, R20M);
+        blockdiag6(R20, R20M, Jb);
+        mat6_mul(op->A, Jb, J2);
+    }
+}
+
 int vgo_hessian_entries(int K, int chain_len)
 {
     int D = K + 6 * chain_len;

@@ -84,6 +84,30 @@ int vgo_evaluate_batch(int model, const double *intr, int n_img, int P,
                        double *r, double *J_intr, double *const *J_xi, double *H,
                        int threads);
 
+/* ---- the other residual types of the global problem ----
+ * TransformationPrior: calib_cost_functions.h:83-108 (ctor), calib_cost_functions.cpp:215-228 (Evaluate).
+ * 6 residuals on ONE transform; the Jacobian the functor hands Ceres is the constant matrix A. */
+typedef struct {
+    double xi_prior[6];
+    double A[36];            /* row-major (Matrix6drm) */
+    double R[9];             /* rotMat of the prior */
+} vgo_transformation_prior;
+void vgo_transformation_prior_init(vgo_transformation_prior *tp, const double stiffness[6], const double xi_prior[6]);
+/* r: 6 doubles; J: 36 doubles row-major or NULL */
+void vgo_transformation_prior_eval(const vgo_transformation_prior *tp, const double xi[6], double r[6], double *J);
+
+/* OdometryPrior: calib_cost_functions.h:64-81, calib_cost_functions.cpp:119-213.
+ * 6 residuals between two consecutive elements of a sequence transform. */
+typedef struct {
+    double zeta_prior[6];
+    double A[36];            /* row-major restatement of the column-major Matrix6d _A */
+} vgo_odometry_prior;
+void vgo_odometry_prior_init(vgo_odometry_prior *op, double errV, double errW, double lambda,
+                             const double xi1[6], const double xi2[6]);
+/* r: 6 doubles; J1, J2: 36 doubles row-major (Matrix6drm maps, .cpp:195,206) or NULL */
+void vgo_odometry_prior_eval(const vgo_odometry_prior *op, const double xi1[6], const double xi2[6],
+                             double r[6], double *J1, double *J2);
+
 int vgo_hessian_entries(int K, int chain_len);   /* (D+1)(D+2)/2 */
 int vgo_max_threads(void);
 

@@ -207,3 +207,71 @@ def make_stereo(n_pairs: int = 20, seed: int = 20244, noise_px: float = 0.1):
                 intr1_init=EUCM_GUESS.copy(), intr2_init=EUCM_GUESS.copy(),
                 xi12_gt=STEREO_GT.copy(), xi12_init=STEREO_PRIOR.copy(),
                 xi_gt=xi_gt, xi_init=np.ascontiguousarray(xi_init), width=IMAGE_W, height=IMAGE_H)
+
+
+# ---- odometry problem: a robot whose odometry couples consecutive poses -----------------------
+def _se3_mat(xi):
+    T = np.eye(4)
+    T[:3, :3] = rodrigues(np.asarray(xi)[None, 3:])[0]
+    T[:3, 3] = np.asarray(xi)[:3]
+    return T
+
+
+def _rotvec(R):
+    """log of a rotation matrix (angles well below pi here)."""
+    c = np.clip((np.trace(R) - 1.0) / 2.0, -1.0, 1.0)
+    th = np.arccos(c)
+    w = np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]])
+    return 0.5 * w if th < 1e-9 else w * (th / (2.0 * np.sin(th)))
+
+
+def _se3_vec(T):
+    return np.concatenate([T[:3, 3], _rotvec(T[:3, :3])])
+
+
+def make_odometry(n: int = 40, seed: int = 20246, noise_px: float = 0.1, odo_noise: float = 0.003,
+                  extra_unlinked: int = 0):
+    """A camera on a wheeled base looking at one fixed board (the use the reference's "odometry" +
+    "transformation_prior" datasets are made for, unified_calibration.cpp:742-829):
+        X_cam = xiBaseCam^-1 o xiOdom[i]^-1 o xiWorldBoard (X_board)
+    i.e. the chain [xiBaseCam INVERSE (global), xiOdom INVERSE (sequence), xiWorldBoard DIRECT (global)].
+    Returns GT / initial values, noisy observations and noisy odometry readings (n x 6)."""
+    board = make_board()
+    P = board.shape[0]
+    R_bc = np.array([[0.0, 0.0, 1.0], [-1.0, 0.0, 0.0], [0.0, -1.0, 0.0]])      # camera z along the base's x
+    tilt = rodrigues(np.array([[0.05, -0.03, 0.02]]))[0]
+    T_bc = np.eye(4); T_bc[:3, :3] = R_bc @ tilt; T_bc[:3, 3] = [0.10, 0.02, 0.30]
+    T_wB = np.eye(4); T_wB[:3, :3] = R_bc; T_wB[:3, 3] = [1.0, 0.4, 0.55]
+    # unicycle trajectory: speed and yaw rate from the counters, kept within +-0.2 m / +-0.35 rad
+    u = uniform(seed, 3, 2 * n).reshape(n, 2)
+    T = np.eye(4)
+    poses, x, th = [T.copy()], 0.0, 0.0
+    for i in range(n - 1):
+        v = 0.04 * (2.0 * u[i, 0] - 1.0) - 0.2 * x * 0.2
+        w = 0.08 * (2.0 * u[i, 1] - 1.0) - 0.2 * th * 0.2
+        T = T @ _se3_mat([v, 0.0, 0.0, 0.0, 0.0, w])
+        x, th = T[0, 3], np.arctan2(T[1, 0], T[0, 0])
+        poses.append(T.copy())
+    xi_odom_gt = np.array([_se3_vec(Tp) for Tp in poses])
+    # noisy odometry readings: the true increments perturbed, re-integrated
+    nz = normal(seed, 5, 6 * n).reshape(n, 6) * odo_noise
+    Tr = np.eye(4)
+    readings = [_se3_vec(Tr)]
+    for i in range(n - 1):
+        inc = np.linalg.inv(poses[i]) @ poses[i + 1]
+        Tr = Tr @ inc @ _se3_mat(nz[i] * np.array([1, 1, 0.2, 0.2, 0.2, 1]))
+        readings.append(_se3_vec(Tr))
+    odom = np.array(readings)
+    Xc = np.array([(np.linalg.inv(T_bc) @ np.linalg.inv(Tp) @ T_wB @ np.c_[board, np.ones(P)].T).T[:, :3] for Tp in poses])
+    uv, valid = project(EUCM, EUCM_GT_LEFT, Xc)
+    assert valid.all() and (uv[..., 0] > 0).all() and (uv[..., 0] < IMAGE_W).all() and (uv[..., 1] > 0).all() and (uv[..., 1] < IMAGE_H).all()
+    obs = uv.reshape(n, 2 * P) + noise_px * normal(seed, 7, n * 2 * P).reshape(n, 2 * P)
+    xi_bc_gt, xi_wB_gt = _se3_vec(T_bc), _se3_vec(T_wB)
+    pert = uniform(seed, 9, 12) * 2.0 - 1.0
+    scale = np.array([0.01, 0.01, 0.01, 0.01, 0.01, 0.01])
+    return dict(P=P, n_img=n, board=board, obs=np.ascontiguousarray(obs), obs_clean=np.ascontiguousarray(uv.reshape(n, 2 * P)),
+                intr_gt=EUCM_GT_LEFT.copy(), intr_init=EUCM_GT_LEFT * np.array([1.01, 0.99, 1.005, 0.995, 1.002, 0.998]),
+                xi_odom_gt=xi_odom_gt, odom=np.ascontiguousarray(odom), xi_odom_init=np.ascontiguousarray(odom.copy()),
+                xi_bc_gt=xi_bc_gt, xi_bc_init=xi_bc_gt + pert[:6] * scale,
+                xi_wB_gt=xi_wB_gt, xi_wB_init=xi_wB_gt + pert[6:] * scale,
+                status=[1, 1, 0], err_v=0.05, err_w=0.05, lam=0.01, width=IMAGE_W, height=IMAGE_H)

@@ -104,6 +104,41 @@ def main():
     path = os.path.join(HERE, "reference_vectors.npz")
     np.savez_compressed(path, **blob)
     print(f"wrote {path}: {len(blob)} arrays, {os.path.getsize(path) / 1024:.0f} KiB")
+    priors(ref, orc)
+
+
+def priors(ref, orc):
+    """TransformationPrior / OdometryPrior (calib_cost_functions.h:64-108, .cpp:119-228) evaluated by the reference
+    build on seeded inputs -> reference_priors.npz (a separate file: the vectors above stay byte-identical)."""
+    n = 48
+    u = sd.uniform(78, 1, 40 * n).reshape(n, 40) * 2 - 1
+    blob = {}
+    stiff = 0.5 + 50.0 * (u[:, 0:6] + 1)
+    xp = np.concatenate([u[:, 6:9] * 0.5, u[:, 9:12] * 1.2], axis=1)
+    xi = xp + u[:, 12:18] * 0.05
+    xp[::8, 3:] *= 1e-6                          # small-angle branches of interOmegaRot / the quaternion
+    xi[4::8] = xp[4::8]                          # zero error
+    xi[5::8, 3:] += 2.5 * u[5::8, 18:21]         # large relative rotation (angle wrap in toRotationVector)
+    r = np.zeros((n, 6)); J = np.zeros((n, 6, 6))
+    for i in range(n):
+        r[i], J[i] = ref.transformation_prior(stiff[i], xp[i], xi[i])
+    blob.update({"tp/stiffness": stiff, "tp/xi_prior": xp, "tp/xi": xi, "tp/r": r, "tp/J": J})
+    o1 = np.concatenate([u[:, 18:21], u[:, 21:24] * 0.7], axis=1)
+    inc = np.concatenate([u[:, 24:27] * 0.1, u[:, 27:30] * 0.06], axis=1)
+    inc[::6] *= 1e-3                             # below MIN_L / MIN_DELTA (.cpp:131-135)
+    inc[3::6, 3:] = 0
+    o2 = np.array([orc.compose(o1[i], inc[i]) for i in range(n)])
+    x1 = o1 + u[:, 30:36] * 0.01
+    x2 = o2 + u[:, 34:40] * 0.01
+    errV, errW, lam = 0.1, 0.05, 0.02
+    r = np.zeros((n, 6)); J1 = np.zeros((n, 6, 6)); J2 = np.zeros((n, 6, 6))
+    for i in range(n):
+        r[i], J1[i], J2[i] = ref.odometry_prior(errV, errW, lam, o1[i], o2[i], x1[i], x2[i])
+    blob.update({"op/params": np.array([errV, errW, lam]), "op/odom1": o1, "op/odom2": o2, "op/xi1": x1, "op/xi2": x2,
+                 "op/r": r, "op/J1": J1, "op/J2": J2})
+    path = os.path.join(HERE, "reference_priors.npz")
+    np.savez_compressed(path, **blob)
+    print(f"wrote {path}: {len(blob)} arrays, {os.path.getsize(path) / 1024:.0f} KiB")
 
 
 if __name__ == "__main__":

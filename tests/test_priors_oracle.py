@@ -1,0 +1,95 @@
+"""CPU: the oracle's restatement of TransformationPrior / OdometryPrior (calib_cost_functions.h:64-108,
+calib_cost_functions.cpp:119-228) against the committed vectors the REFERENCE build produced
+(tests/golden/make_golden.py -> reference_priors.npz), and the oracle LM's two linear-algebra routes
+(arrowhead elimination / dense factorisation) against each other."""
+import os
+
+import numpy as np
+import pytest
+
+import synthdata as sd
+from oracle.pyoracle import OracleProblem
+from util import assert_close
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_priors.npz"))
+PIN_RTOL = 1e-13
+
+
+def test_transformation_prior_matches_reference_vectors(oracle):
+    for i in range(len(GOLD["tp/xi"])):
+        r, J = oracle.transformation_prior(GOLD["tp/stiffness"][i], GOLD["tp/xi_prior"][i], GOLD["tp/xi"][i])
+        assert_close(r, GOLD["tp/r"][i], f"tp[{i}]: r", PIN_RTOL)
+        assert_close(J, GOLD["tp/J"][i], f"tp[{i}]: J", PIN_RTOL)
+
+
+def test_odometry_prior_matches_reference_vectors(oracle):
+    errV, errW, lam = GOLD["op/params"]
+    for i in range(len(GOLD["op/xi1"])):
+        r, J1, J2 = oracle.odometry_prior(errV, errW, lam, GOLD["op/odom1"][i], GOLD["op/odom2"][i],
+                                          GOLD["op/xi1"][i], GOLD["op/xi2"][i])
+        assert_close(r, GOLD["op/r"][i], f"op[{i}]: r", PIN_RTOL)
+        assert_close(J1, GOLD["op/J1"][i], f"op[{i}]: J1", PIN_RTOL)
+        assert_close(J2, GOLD["op/J2"][i], f"op[{i}]: J2", PIN_RTOL)
+
+
+def test_prior_residual_is_zero_at_the_prior(oracle):
+    xp = np.array([0.3, -0.2, 0.5, 0.4, -0.7, 0.2])
+    r, J = oracle.transformation_prior([3, 4, 5, 6, 7, 8], xp, xp)
+    assert np.abs(r).max() < 1e-14
+    assert np.allclose(np.diag(J)[:3], [3, 4, 5])
+    o1 = np.array([0.1, 0.2, 0.0, 0.0, 0.0, 0.3]); o2 = oracle.compose(o1, [0.05, 0, 0, 0, 0, 0.04])
+    r, _, _ = oracle.odometry_prior(0.1, 0.1, 0.01, o1, o2, o1, o2)
+    assert np.abs(r).max() < 1e-12
+
+
+def test_odometry_jacobian_of_the_second_pose_is_a_derivative(oracle):
+    """J2 = A blockdiag(R20, R20 M(r2)) is the derivative of the residual in the functor's own first-order model:
+    check it against central differences of r wrt xi2 where the prior error is small (the functor's Jacobians
+    are exact only at zero error, calib_cost_functions.cpp:190-213)."""
+    o1 = np.array([0.2, -0.1, 0.0, 0.02, -0.01, 0.4]); o2 = oracle.compose(o1, [0.06, 0.01, 0, 0, 0, 0.05])
+    _, _, J2 = oracle.odometry_prior(0.1, 0.1, 0.02, o1, o2, o1, o2)
+    fd = np.zeros((6, 6)); h = 1e-6
+    for k in range(6):
+        e = np.zeros(6); e[k] = h
+        rp, _, _ = oracle.odometry_prior(0.1, 0.1, 0.02, o1, o2, o1, o2 + e)
+        rm, _, _ = oracle.odometry_prior(0.1, 0.1, 0.02, o1, o2, o1, o2 - e)
+        fd[:, k] = (rp - rm) / (2 * h)
+    assert np.abs(fd - J2).max() <= 1e-5 * np.abs(J2).max()
+
+
+def test_dense_route_equals_arrowhead_route(oracle):
+    """A constant, unobserved extra element switches the oracle LM to its dense factorisation: the solution must
+    not change (the two routes solve the same normal equations)."""
+    d = sd.make_mono(sd.EUCM, 12, seed=77)
+    res = []
+    for extra in (False, True):
+        P = OracleProblem(oracle)
+        cam = P.add_camera(sd.EUCM, d["intr_init"])
+        xi = np.vstack([d["xi_init"], d["xi_init"][:1]]) if extra else d["xi_init"]
+        tr = P.add_transform(xi, is_global=False)
+        P.add_dataset(cam, d["board"], d["obs"], [tr], [0], seq_index=np.arange(12))
+        if extra:
+            P.set_pose_constant(tr, 12)
+        s = P.solve()
+        res.append((s.final_cost, P.camera(cam), P.transform(tr)[:12], s.iterations))
+    assert abs(res[0][0] - res[1][0]) <= 1e-10 * res[0][0]
+    assert np.abs(res[0][1] - res[1][1]).max() <= 1e-8 * np.abs(res[0][1]).max()
+    assert np.abs(res[0][2] - res[1][2]).max() <= 1e-8
+
+
+def test_odometry_problem_converges(oracle):
+    d = sd.make_odometry(24)
+    P = OracleProblem(oracle)
+    cam = P.add_camera(sd.EUCM, d["intr_gt"], constant=True)
+    bc = P.add_transform(d["xi_bc_init"], is_global=True)
+    od = P.add_transform(d["xi_odom_init"], is_global=False)
+    wB = P.add_transform(d["xi_wB_init"], is_global=True)
+    P.add_dataset(cam, d["board"], d["obs"], [bc, od, wB], d["status"])
+    assert P.add_odometry(od, d["err_v"], d["err_w"], d["lam"], d["odom"]) == 23
+    P.set_pose_constant(od, 0)
+    P.add_transformation_prior(bc, [10] * 6)
+    o = oracle.default_options(); o.max_num_iterations = 12
+    s = P.solve(o)
+    assert s.final_cost < 1e-2 * s.initial_cost
+    assert np.array_equal(P.transform(od)[0], d["xi_odom_init"][0])          # the anchor did not move
+    assert np.abs(P.transform(od) - d["xi_odom_gt"]).max() < np.abs(d["odom"] - d["xi_odom_gt"]).max()

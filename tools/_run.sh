@@ -1,5 +1,4 @@
 set -x
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python tools/lm_timing.py 2>&1 | tail -2
-python tools/lm_timing.py 10000 25 2>&1 | tail -1
-python bench.py > gpurun_out/bench_r1g.json 2> gpurun_out/bench_r1g.err; tail -c 900 gpurun_out/bench_r1g.json; tail -3 gpurun_out/bench_r1g.err
+python -m pytest tests/test_priors_gpu.py -q --tb=short 2>&1 | tail -60
+timeout 400 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_priors_gpu.py -x -q > gpurun_out/sanitizer_priors.log 2>&1; echo sanitizer rc=$?; tail -4 gpurun_out/sanitizer_priors.log
+python -m pytest tests -m gpu -q 2>&1 | tail -3

@@ -75,6 +75,12 @@ def lib() -> C.CDLL:
         L.vg_problem_add_transform.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, c_dp]
         L.vg_problem_add_dataset.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp, C.c_int, c_dp, c_ip,
                                              C.c_int, c_ip, c_ip]
+        L.vg_problem_add_transformation_prior.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp, c_dp]
+        L.vg_problem_add_odometry.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, c_dp]
+        L.vg_problem_set_pose_constant.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.vg_eval_transformation_prior.argtypes = [C.c_int, c_dp, c_dp, c_dp, c_dp, c_dp]
+        L.vg_eval_odometry_prior.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, c_dp, c_dp, c_dp, c_dp,
+                                             c_dp, c_dp, c_dp]
         L.vg_problem_set_allreduce.argtypes = [C.c_void_p, ALLREDUCE_FN, C.c_void_p, C.c_int, C.c_int]
         L.vg_problem_materialize_jacobians.argtypes = [C.c_void_p, C.c_int]
         L.vg_problem_device_buffer.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p),
@@ -163,6 +169,28 @@ def eval_chain(model, intr, board, obs, xi_list, status, is_global,
     return dict(r=r, J_intr=Ja, J_xi=Je, H=H)
 
 
+def eval_transformation_prior(stiffness, xi_prior, xi, want_J=True):
+    """Batched TransformationPrior::Evaluate (calib_cost_functions.cpp:215-228): inputs (n, 6) -> r (n, 6), J (n, 6, 6)."""
+    st = _f64(stiffness).reshape(-1, 6); xp = _f64(xi_prior).reshape(-1, 6); x = _f64(xi).reshape(-1, 6)
+    n = x.shape[0]
+    r = np.empty((n, 6)); J = np.empty((n, 6, 6)) if want_J else None
+    _check(lib().vg_eval_transformation_prior(n, _dp(st), _dp(xp), _dp(x), _dp(r), _dp(J) if want_J else None))
+    return r, J
+
+
+def eval_odometry_prior(errV, errW, lam, odom1, odom2, xi1, xi2, want_J=True):
+    """Batched OdometryPrior::Evaluate (calib_cost_functions.cpp:177-213): -> r (n, 6), J1, J2 (n, 6, 6)."""
+    o1 = _f64(odom1).reshape(-1, 6); o2 = _f64(odom2).reshape(-1, 6)
+    a = _f64(xi1).reshape(-1, 6); b = _f64(xi2).reshape(-1, 6)
+    n = a.shape[0]
+    r = np.empty((n, 6))
+    J1 = np.empty((n, 6, 6)) if want_J else None
+    J2 = np.empty((n, 6, 6)) if want_J else None
+    _check(lib().vg_eval_odometry_prior(n, errV, errW, lam, _dp(o1), _dp(o2), _dp(a), _dp(b), _dp(r),
+                                        _dp(J1) if want_J else None, _dp(J2) if want_J else None))
+    return r, J1, J2
+
+
 def eval_chain_dev(model, intr, board, obs, xi_list, status, is_global, n_img, P,
                    r=None, J_intr=None, J_xi=None, H=None, seq_index=None, stream=0):
     """Device-pointer variant: every array argument is an integer device address
@@ -229,6 +257,19 @@ class Problem:
             self.h, cam, board.shape[0], _dp(board), obs.shape[0], _dp(obs),
             None if si is None else si.ctypes.data_as(c_ip), len(ids),
             ids.ctypes.data_as(c_ip), st.ctypes.data_as(c_ip)))
+
+    def add_transformation_prior(self, transform, stiffness, index=0, xi_prior=None):
+        st = _f64(stiffness)
+        xp = None if xi_prior is None else _f64(xi_prior)
+        return _check(self.L.vg_problem_add_transformation_prior(self.h, transform, index, _dp(st),
+                                                                 None if xp is None else _dp(xp)))
+
+    def add_odometry(self, transform, errV, errW, lam, odom):
+        od = _f64(odom).reshape(-1, 6)
+        return _check(self.L.vg_problem_add_odometry(self.h, transform, errV, errW, lam, od.shape[0], _dp(od)))
+
+    def set_pose_constant(self, transform, index, constant=True):
+        _check(self.L.vg_problem_set_pose_constant(self.h, transform, index, int(constant)))
 
     def set_allreduce(self, fn, rank, nranks):
         """fn(buf_ptr:int, count:int, stream:int) -> None sums count doubles in place across ranks."""

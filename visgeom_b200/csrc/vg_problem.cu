@@ -10,6 +10,7 @@
 #include "vg_common.h"
 #include "vg_eval.cuh"
 #include "vg_solver_kernels.cuh"
+#include "vg_priors.cuh"
 
 #include <chrono>
 #include <cmath>
@@ -34,8 +35,14 @@ struct Tr {
     int glob_slot;                 // index among global transforms (slab position)
     int seq_slot;                  // index among sequence transforms
     std::vector<double> host;      // n x 6
+    std::vector<unsigned char> fixed;   // per element: constant ("anchor", unified_calibration.cpp:803-806)
     double *dev[2];                // sequences: device poses (set 0 / 1); constants alias one buffer
 };
+
+// TransformationPrior block (unified_calibration.cpp:808-829) and the OdometryPrior blocks of one "odometry"
+// dataset (:742-807)
+struct TPrior { int tr, index; double stiffness[6], xi_prior[6]; };
+struct Odom { int tr; double errV, errW, lambda; std::vector<double> odom; };
 
 struct Ds {
     int cam, P, n_img, L, D, W, ne;
@@ -96,6 +103,8 @@ struct vg_problem {
     std::vector<Cam> cams;
     std::vector<Tr> trs;
     std::vector<Ds> dss;
+    std::vector<TPrior> tps;
+    std::vector<Odom> odoms;
     int n_glob = 0, n_seq = 0;
     bool materialize = false;
 
@@ -130,6 +139,32 @@ struct vg_problem {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double eval_ms = 0;
     int n_eval = 0;
+    // prior blocks and coupled / constant sequence elements (vg_priors.cuh); all empty in a plain grid problem
+    int n_tp = 0, n_op = 0, n_tp_shared = 0, n_seg = 0;
+    double *d_tp_const = nullptr, *d_op_const = nullptr, *d_tp_out[2] = {nullptr, nullptr}, *d_op_out[2] = {nullptr, nullptr};
+    const double **d_tp_xi[2] = {nullptr, nullptr}, **d_op_xi[2] = {nullptr, nullptr};
+    int *d_tp_shared_rec = nullptr, *d_tp_shared_off = nullptr;
+    int *d_seg_start = nullptr, *d_seg_len = nullptr, *d_extra_start = nullptr, *d_extra_kind = nullptr, *d_extra_rec = nullptr,
+        *d_prev_edge = nullptr;
+    unsigned char *d_mask = nullptr, *d_fixed = nullptr;
+    double *d_chain_off = nullptr, *d_chain_w = nullptr;
+
+    PriorTables prior_tables(int s) const
+    {
+        PriorTables t;
+        t.n_tp = n_tp; t.n_op = n_op; t.tp_const = d_tp_const; t.op_const = d_op_const;
+        t.tp_xi = d_tp_xi[s]; t.op_xi = d_op_xi[s]; t.tp_out = d_tp_out[s]; t.op_out = d_op_out[s];
+        t.n_tp_shared = n_tp_shared; t.tp_shared_rec = d_tp_shared_rec; t.tp_shared_off = d_tp_shared_off;
+        return t;
+    }
+    ChainTables chain_tables(int s) const
+    {
+        ChainTables c;
+        c.n_seg = n_seg; c.seg_start = d_seg_start; c.seg_len = d_seg_len; c.mask = d_mask; c.fixed = d_fixed;
+        c.extra_start = d_extra_start; c.extra_kind = d_extra_kind; c.extra_rec = d_extra_rec; c.prev_edge = d_prev_edge;
+        c.tp_const = d_tp_const; c.tp_out = d_tp_out[s]; c.op_out = d_op_out[s]; c.off = d_chain_off; c.w = d_chain_w;
+        return c;
+    }
 
     double *cam_ptr(int set, int cam) const { return d_slab[set] + (size_t)cam * CAM_STRIDE; }
     double *glob_ptr(int set, int slot) const { return d_slab[set] + cams.size() * CAM_STRIDE + (size_t)slot * 6; }
@@ -143,6 +178,11 @@ void free_prepared(vg_problem *p)
     for (int s = 0; s < 2; s++) { F(p->d_slab[s]); F(p->d_desc[s]); F(p->d_seq_ptr[s]); }
     F(p->d_pose_start); F(p->d_contrib_ds); F(p->d_contrib_img); F(p->d_pose_seq); F(p->d_pose_local);
     F(p->d_fail); F(p->d_fin_out); F(p->d_fin_src); F(p->d_cta_partial); F(p->d_tickets); F(p->d_lvl1); F(p->d_ds_sum); F(p->d_scale); F(p->d_ws); F(p->d_partial); F(p->d_red); F(p->d_delta);
+    for (int s = 0; s < 2; s++) { F(p->d_tp_out[s]); F(p->d_op_out[s]); F(p->d_tp_xi[s]); F(p->d_op_xi[s]); }
+    F(p->d_tp_const); F(p->d_op_const); F(p->d_tp_shared_rec); F(p->d_tp_shared_off); F(p->d_seg_start); F(p->d_seg_len);
+    F(p->d_extra_start); F(p->d_extra_kind); F(p->d_extra_rec); F(p->d_prev_edge); F(p->d_mask); F(p->d_fixed);
+    F(p->d_chain_off); F(p->d_chain_w);
+    p->n_tp = p->n_op = p->n_tp_shared = p->n_seg = 0;
     if (p->h_red) { cudaFreeHost(p->h_red); p->h_red = nullptr; }
     if (p->h_up) { cudaFreeHost(p->h_up); p->h_up = nullptr; }
     for (auto &d : p->dss)
@@ -157,6 +197,111 @@ void fill_slab(const vg_problem *p, double *dst)
         memcpy(dst + c * CAM_STRIDE, p->cams[c].params, sizeof(double) * p->cams[c].K);
     for (const Tr &t : p->trs)
         if (t.is_global) memcpy(dst + p->cams.size() * CAM_STRIDE + (size_t)t.glob_slot * 6, t.host.data(), 48);
+}
+
+// prior records, the poses that gather them, and the segments the chain kernels walk
+int prepare_priors(vg_problem *p)
+{
+    const int NP = p->n_pose;
+    if (p->tps.empty() && p->odoms.empty()) {
+        bool any_fixed = false;
+        for (const Tr &t : p->trs)
+            if (t.pose_off >= 0)
+                for (unsigned char f : t.fixed) any_fixed = any_fixed || f;
+        if (!any_fixed) return VG_OK;
+    }
+    std::vector<double> tp_in, op_in;
+    std::vector<const double *> tp_xi[2], op_xi[2];
+    std::vector<int> sh_rec, sh_off, prev_edge(NP ? NP : 1, -1);
+    std::vector<std::vector<std::pair<int, int>>> extras(NP);
+    std::vector<unsigned char> mask(NP ? NP : 1, 0), fixed(NP ? NP : 1, 0), linked_next(NP ? NP : 1, 0);
+    for (const TPrior &tp : p->tps) {
+        const Tr &t = p->trs[tp.tr];
+        if (t.is_global && p->rank != 0) continue;       // shared blocks are counted once across ranks
+        const int rec = (int)tp_xi[0].size();
+        tp_in.insert(tp_in.end(), tp.stiffness, tp.stiffness + 6);
+        tp_in.insert(tp_in.end(), tp.xi_prior, tp.xi_prior + 6);
+        for (int s = 0; s < 2; s++)
+            tp_xi[s].push_back(t.is_global ? p->glob_ptr(s, t.glob_slot) : t.dev[s] + (size_t)6 * tp.index);
+        if (t.is_global) { if (t.shared_off >= 0) { sh_rec.push_back(rec); sh_off.push_back(t.shared_off); } }
+        else if (t.pose_off >= 0) extras[t.pose_off + tp.index].push_back({EXTRA_TP, rec});
+    }
+    for (const Odom &od : p->odoms) {
+        const Tr &t = p->trs[od.tr];
+        for (int i = 0; i + 1 < t.n; i++) {
+            const int e = (int)op_xi[0].size();
+            op_in.push_back(od.errV); op_in.push_back(od.errW); op_in.push_back(od.lambda);
+            op_in.insert(op_in.end(), od.odom.begin() + (size_t)6 * i, od.odom.begin() + (size_t)6 * (i + 2));
+            for (int s = 0; s < 2; s++) op_xi[s].push_back(t.dev[s] + (size_t)6 * i);
+            if (t.pose_off >= 0) {
+                const int q = t.pose_off + i;
+                extras[q].push_back({EXTRA_OP_FIRST, e});
+                extras[q + 1].push_back({EXTRA_OP_SECOND, e});
+                prev_edge[q + 1] = e;
+                linked_next[q] = 1;
+            }
+        }
+    }
+    p->n_tp = (int)tp_xi[0].size(); p->n_op = (int)op_xi[0].size(); p->n_tp_shared = (int)sh_rec.size();
+    for (const Tr &t : p->trs)
+        if (t.pose_off >= 0)
+            for (int i = 0; i < t.n; i++) fixed[t.pose_off + i] = t.fixed[i];
+    std::vector<int> extra_start(NP + 1, 0), extra_kind, extra_rec, seg_start, seg_len;
+    for (int q = 0; q < NP; q++) {
+        extra_start[q] = (int)extra_kind.size();
+        for (auto &x : extras[q]) { extra_kind.push_back(x.first); extra_rec.push_back(x.second); }
+        mask[q] = (!extras[q].empty() || fixed[q]) ? 1 : 0;
+    }
+    extra_start[NP] = (int)extra_kind.size();
+    for (int q = 0; q < NP; q++) {
+        if (!mask[q] || prev_edge[q] >= 0) continue;     // not a segment head
+        int len = 1;
+        while (linked_next[q + len - 1]) len++;
+        seg_start.push_back(q); seg_len.push_back(len);
+    }
+    p->n_seg = (int)seg_start.size();
+
+    auto up_d = [&](double *&dptr, const std::vector<double> &v, size_t min_n) -> cudaError_t {
+        cudaError_t e = cudaMalloc(&dptr, sizeof(double) * (v.size() > min_n ? v.size() : min_n));
+        if (e != cudaSuccess || v.empty()) return e;
+        return cudaMemcpy(dptr, v.data(), sizeof(double) * v.size(), cudaMemcpyHostToDevice);
+    };
+    auto up_i = [&](int *&dptr, const std::vector<int> &v) -> cudaError_t {
+        cudaError_t e = cudaMalloc(&dptr, sizeof(int) * (v.size() ? v.size() : 1));
+        if (e != cudaSuccess || v.empty()) return e;
+        return cudaMemcpy(dptr, v.data(), sizeof(int) * v.size(), cudaMemcpyHostToDevice);
+    };
+    auto up_b = [&](unsigned char *&dptr, const std::vector<unsigned char> &v) -> cudaError_t {
+        cudaError_t e = cudaMalloc(&dptr, v.size() ? v.size() : 1);
+        if (e != cudaSuccess || v.empty()) return e;
+        return cudaMemcpy(dptr, v.data(), v.size(), cudaMemcpyHostToDevice);
+    };
+    double *d_tp_in = nullptr, *d_op_in = nullptr;
+    VG_CUDA(up_d(d_tp_in, tp_in, 1)); VG_CUDA(up_d(d_op_in, op_in, 1));
+    VG_CUDA(cudaMalloc(&p->d_tp_const, sizeof(double) * TP_CONST * (size_t)(p->n_tp + 1)));
+    VG_CUDA(cudaMalloc(&p->d_op_const, sizeof(double) * OP_CONST * (size_t)(p->n_op + 1)));
+    for (int s = 0; s < 2; s++) {
+        VG_CUDA(cudaMalloc(&p->d_tp_out[s], sizeof(double) * TP_OUT * (size_t)(p->n_tp + 1)));
+        VG_CUDA(cudaMalloc(&p->d_op_out[s], sizeof(double) * OP_OUT * (size_t)(p->n_op + 1)));
+        VG_CUDA(cudaMalloc(&p->d_tp_xi[s], sizeof(double *) * (size_t)(p->n_tp + 1)));
+        VG_CUDA(cudaMalloc(&p->d_op_xi[s], sizeof(double *) * (size_t)(p->n_op + 1)));
+        if (p->n_tp) VG_CUDA(cudaMemcpy(p->d_tp_xi[s], tp_xi[s].data(), sizeof(double *) * p->n_tp, cudaMemcpyHostToDevice));
+        if (p->n_op) VG_CUDA(cudaMemcpy(p->d_op_xi[s], op_xi[s].data(), sizeof(double *) * p->n_op, cudaMemcpyHostToDevice));
+    }
+    VG_CUDA(up_i(p->d_tp_shared_rec, sh_rec)); VG_CUDA(up_i(p->d_tp_shared_off, sh_off));
+    VG_CUDA(up_i(p->d_seg_start, seg_start)); VG_CUDA(up_i(p->d_seg_len, seg_len));
+    VG_CUDA(up_i(p->d_extra_start, extra_start)); VG_CUDA(up_i(p->d_extra_kind, extra_kind)); VG_CUDA(up_i(p->d_extra_rec, extra_rec));
+    VG_CUDA(up_i(p->d_prev_edge, prev_edge));
+    VG_CUDA(up_b(p->d_mask, mask)); VG_CUDA(up_b(p->d_fixed, fixed));
+    VG_CUDA(cudaMalloc(&p->d_chain_off, sizeof(double) * 36 * (size_t)(NP ? NP : 1)));
+    VG_CUDA(cudaMalloc(&p->d_chain_w, sizeof(double) * 6 * (size_t)(NP ? NP : 1)));
+    VG_CUDA(cudaMemset(p->d_chain_off, 0, sizeof(double) * 36 * (size_t)(NP ? NP : 1)));
+    SolverLaunch sl{p->stream, &launch_counter()};
+    cudaError_t e = launch_prior_setup(p->n_tp, d_tp_in, p->d_tp_const, p->n_op, d_op_in, p->d_op_const, sl);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+    cudaFree(d_tp_in); cudaFree(d_op_in);
+    if (e != cudaSuccess) return fail_cuda(e, "prior setup");
+    return VG_OK;
 }
 
 // (re)build everything that depends on the problem structure
@@ -290,7 +435,11 @@ int prepare(vg_problem *p)
     VG_CUDA(cudaMemset(p->d_fail, 0, sizeof(int)));
     VG_CUDA(cudaMalloc(&p->d_scale, sizeof(double) * 6 * (size_t)(NP ? NP : 1)));
     VG_CUDA(cudaMalloc(&p->d_ws, sizeof(double) * (size_t)pose_ws_stride(Ks) * (NP ? NP : 1)));
-    p->partial_doubles = pose_scratch(NP, Ks) + 64;
+    {
+        int rc = prepare_priors(p);
+        if (rc) return rc;
+    }
+    p->partial_doubles = pose_scratch(NP, Ks, p->n_seg) + 3 * (size_t)pose_backsub_blocks(NP) + 64;
     VG_CUDA(cudaMalloc(&p->d_partial, sizeof(double) * p->partial_doubles));
     const int rs = red_size(Ks, p->nranks);
     VG_CUDA(cudaMalloc(&p->d_red, sizeof(double) * rs));
@@ -343,6 +492,13 @@ int evaluate_set(vg_problem *p, int s, bool timed)
         a.n_img = d.n_img; a.P = d.P;
         cudaError_t e = launch_eval(p->cams[d.cam].model, d.L, a, p->stream, &launch_counter());
         if (e != cudaSuccess) return fail_cuda(e, "reproj_eval_kernel launch");
+    }
+    if (p->n_tp + p->n_op > 0) {
+        // the 6-residual blocks: their normal-equation pieces, then cost and shared-block terms on top of d_red
+        if (p->last_ds < 0) VG_CUDA(cudaMemsetAsync(p->d_red, 0, sizeof(double) * red_off_model(p->Ks), p->stream));
+        SolverLaunch sl{p->stream, &launch_counter()};
+        cudaError_t e = launch_prior_eval(p->prior_tables(s), p->Ks, p->d_red, 1, nullptr, sl);
+        if (e != cudaSuccess) return fail_cuda(e, "prior_eval launch");
     }
     if (timed) VG_CUDA(cudaEventRecord(p->ev1, p->stream));
     p->n_eval++;
@@ -477,6 +633,7 @@ int vg_problem_add_transform(vg_problem *p, int is_global, int constant, int n, 
     t.shared_off = t.pose_off = -1;
     t.glob_slot = t.seq_slot = -1;
     t.host.assign(values, values + (size_t)6 * n);
+    t.fixed.assign(n, 0);
     t.dev[0] = t.dev[1] = nullptr;
     if (t.is_global) t.glob_slot = p->n_glob++;
     else {
@@ -539,6 +696,64 @@ int vg_problem_add_dataset(vg_problem *p, int camera, int P, const double *board
     }
     p->dss.push_back(d);
     return (int)p->dss.size() - 1;
+}
+
+int vg_problem_add_transformation_prior(vg_problem *p, int transform, int index, const double *stiffness, const double *xi_prior)
+{
+    if (!p || !stiffness) return fail(VG_ERR_INVALID, "null argument");
+    if (transform < 0 || transform >= (int)p->trs.size()) return fail(VG_ERR_INVALID, "unknown transform");
+    Tr &t = p->trs[transform];
+    if (index < 0 || index >= t.n) return fail(VG_ERR_INVALID, "vg_problem_add_transformation_prior: element index out of range");
+    if (!xi_prior && !t.is_global && p->prepared) {
+        // the prior defaults to the element's current value: fetch the sequence if a solve has moved it
+        std::vector<double> tmp((size_t)6 * t.n);
+        int rc = vg_problem_get_transform(p, transform, tmp.data());
+        if (rc) return rc;
+    }
+    cudaSetDevice(p->device);
+    free_prepared(p);
+    TPrior tp;
+    tp.tr = transform; tp.index = index;
+    memcpy(tp.stiffness, stiffness, 48);
+    memcpy(tp.xi_prior, xi_prior ? xi_prior : t.host.data() + (size_t)6 * index, 48);
+    p->tps.push_back(tp);
+    return (int)p->tps.size() - 1;
+}
+
+int vg_problem_add_odometry(vg_problem *p, int transform, double errV, double errW, double lambda, int n, const double *odom)
+{
+    if (!p || !odom) return fail(VG_ERR_INVALID, "null argument");
+    if (transform < 0 || transform >= (int)p->trs.size()) return fail(VG_ERR_INVALID, "unknown transform");
+    const Tr &t = p->trs[transform];
+    if (t.is_global) return fail(VG_ERR_INVALID, "the transform is global. Odometry must be a sequence");   // :752-755
+    if (n != t.n) return fail(VG_ERR_INVALID, "vg_problem_add_odometry: one odometry reading per sequence element expected");
+    if (!(lambda > 0.0)) return fail(VG_ERR_INVALID, "vg_problem_add_odometry: lambda must be positive");
+    for (const Odom &o : p->odoms)
+        if (o.tr == transform) return fail(VG_ERR_UNSUPPORTED, "the sequence already has odometry blocks");
+    cudaSetDevice(p->device);
+    free_prepared(p);
+    Odom od;
+    od.tr = transform; od.errV = errV; od.errW = errW; od.lambda = lambda;
+    od.odom.assign(odom, odom + (size_t)6 * n);
+    p->odoms.push_back(od);
+    return n - 1;
+}
+
+int vg_problem_set_pose_constant(vg_problem *p, int transform, int index, int constant)
+{
+    if (!p || transform < 0 || transform >= (int)p->trs.size()) return fail(VG_ERR_INVALID, "unknown transform");
+    Tr &t = p->trs[transform];
+    if (t.is_global) return fail(VG_ERR_INVALID, "vg_problem_set_pose_constant: not a sequence transform");
+    if (index < 0 || index >= t.n) return fail(VG_ERR_INVALID, "vg_problem_set_pose_constant: element index out of range");
+    if (p->prepared) {
+        std::vector<double> tmp((size_t)6 * t.n);
+        int rc = vg_problem_get_transform(p, transform, tmp.data());    // keep what a solve has reached
+        if (rc) return rc;
+    }
+    cudaSetDevice(p->device);
+    free_prepared(p);
+    t.fixed[index] = constant ? 1 : 0;
+    return VG_OK;
 }
 
 int vg_problem_set_allreduce(vg_problem *p, vg_allreduce_fn fn, void *ctx, int rank, int nranks)
@@ -786,9 +1001,14 @@ int vg_problem_solve(vg_problem *p, const vg_solve_options *opt, vg_solve_summar
     for (;;) {
         // per-pose damped factorisation + Schur terms at the current radius (also max |g_pose|)
         LmConsts lm{radius, o.min_lm_diagonal, o.max_lm_diagonal, init_scale ? 1 : 0, o.jacobi_scaling};
-        cudaError_t ce = launch_pose_schur(p->d_desc[p->cur], NP, Ks, p->d_pose_start, p->d_contrib_ds, p->d_contrib_img,
-                                           p->d_scale, lm, p->d_ws, p->d_partial, p->partial_doubles, p->d_red,
-                                           p->d_fail, p->rank, p->nranks, sl);
+        cudaError_t ce = cudaSuccess;
+        if (p->n_seg > 0)      // coupled / constant elements first: their rows of ws, max |g| per segment
+            ce = launch_chain_factor(p->d_desc[p->cur], Ks, p->d_pose_start, p->d_contrib_ds, p->d_contrib_img, p->d_scale, lm,
+                                     p->d_ws, p->chain_tables(p->cur), p->d_partial + pose_factor_blocks(NP), p->d_fail, sl);
+        if (ce == cudaSuccess)
+            ce = launch_pose_schur(p->d_desc[p->cur], NP, Ks, p->d_pose_start, p->d_contrib_ds, p->d_contrib_img,
+                                   p->d_scale, lm, p->d_ws, p->d_partial, p->partial_doubles, p->d_red,
+                                   p->d_fail, p->rank, p->nranks, sl, p->d_mask, p->n_seg);
         if (ce != cudaSuccess) return fail_cuda(ce, "pose_schur");
         init_scale = false;
         rc = fetch_segment(p, offS, segS);
@@ -852,7 +1072,13 @@ int vg_problem_solve(vg_problem *p, const vg_solve_options *opt, vg_solve_summar
             if (Ks) VG_CUDA(cudaMemcpyAsync(p->d_delta, p->h_up + p->slab_doubles, sizeof(double) * Ks, cudaMemcpyHostToDevice, p->stream));
             // candidate poses + model-decrease / norm partial sums, then the evaluation there
             ce = launch_pose_backsub(NP, Ks, p->d_delta, p->d_seq_ptr[p->cur], p->d_seq_ptr[cand], p->d_pose_seq,
-                                     p->d_pose_local, p->d_ws, p->d_partial, p->partial_doubles, p->d_red, sl);
+                                     p->d_pose_local, p->d_ws, p->d_partial, p->partial_doubles, p->d_red, sl, p->d_mask,
+                                     p->d_chain_w);
+            const int nb_b = pose_backsub_blocks(NP);
+            if (ce == cudaSuccess && p->n_seg > 0)
+                ce = launch_chain_backsub(Ks, p->d_seq_ptr[p->cur], p->d_seq_ptr[cand], p->d_pose_seq, p->d_pose_local, p->d_ws,
+                                          p->chain_tables(p->cur), p->d_partial + 3 * (size_t)nb_b, sl);
+            if (ce == cudaSuccess) ce = launch_finalize_backsub(Ks, nb_b + p->n_seg, p->d_partial, p->d_red, sl);
             if (ce != cudaSuccess) return fail_cuda(ce, "pose_backsub");
             rc = evaluate_set(p, cand, true);
             if (rc) return rc;

@@ -98,12 +98,14 @@ __device__ __forceinline__ void block_gram(int n_pose, int Ks, const double *ws,
 __global__ void __launch_bounds__(FACTOR_THREADS)
 pose_factor_kernel(const DatasetDesc *desc_all, int n_pose, int Ks,
                    const int *pose_start, const int *contrib_ds, const int *contrib_img,
-                   double *scale, LmConsts lm, double *ws, double *partial_gmax, double *partial_gram, int *fail_flag)
+                   double *scale, LmConsts lm, double *ws, double *partial_gmax, double *partial_gram, int *fail_flag,
+                   const unsigned char *chain_mask)
 {
     __shared__ double sh_max[FACTOR_THREADS];
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     double gmax = 0.0;
-    if (p < n_pose) {
+    // chain_mask: elements the chain kernels (vg_priors.cu) have already factorised into ws
+    if (p < n_pose && !(chain_mask && chain_mask[p])) {
         double C[21], b[6];
 #pragma unroll
         for (int i = 0; i < 21; i++) C[i] = 0.0;
@@ -271,11 +273,12 @@ finalize_gram_kernel(int Ks, int n_blocks, const double *partial, int n_gmax, co
 __global__ void __launch_bounds__(POSE_THREADS)
 pose_backsub_kernel(int n_pose, int Ks, const double *delta_a, const double *const *seq_cur,
                     double *const *seq_cand, const int *pose_seq, const int *pose_local,
-                    const double *ws, double *partial)
+                    const double *ws, double *partial, const unsigned char *chain_mask, double *chain_w)
 {
     __shared__ double sh[3][POSE_THREADS];
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     double m = 0.0, st2 = 0.0, x2 = 0.0;
+    const bool chained = p < n_pose && chain_mask && chain_mask[p];
     if (p < n_pose) {
         const double *w = ws + (size_t)p * pose_ws_stride(Ks);
         double Lm[21], wv[6];
@@ -289,17 +292,23 @@ pose_backsub_kernel(int n_pose, int Ks, const double *delta_a, const double *con
             wv[k] = s;
             m = fma(-0.5 * s, s, m);
         }
-        backward_subst(Lm, wv);   // wv = L^-T w ; delta = -wv
-        const double *cur = seq_cur[pose_seq[p]] + (size_t)pose_local[p] * 6;
-        double *cand = seq_cand[pose_seq[p]] + (size_t)pose_local[p] * 6;
+        if (chained) {
+            // coupled elements: the triangular solve runs along the segment (chain_backsub_kernel, vg_priors.cu)
 #pragma unroll
-        for (int k = 0; k < 6; k++) {
-            const double dlt = -wv[k];
-            const double x = cur[k];
-            cand[k] = x + dlt;
-            m = fma(-0.5 * w[21 + k] * dlt, dlt, m);
-            st2 = fma(dlt, dlt, st2);
-            x2 = fma(x, x, x2);
+            for (int k = 0; k < 6; k++) chain_w[(size_t)p * 6 + k] = wv[k];
+        } else {
+            backward_subst(Lm, wv);   // wv = L^-T w ; delta = -wv
+            const double *cur = seq_cur[pose_seq[p]] + (size_t)pose_local[p] * 6;
+            double *cand = seq_cand[pose_seq[p]] + (size_t)pose_local[p] * 6;
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                const double dlt = -wv[k];
+                const double x = cur[k];
+                cand[k] = x + dlt;
+                m = fma(-0.5 * w[21 + k] * dlt, dlt, m);
+                st2 = fma(dlt, dlt, st2);
+                x2 = fma(x, x, x2);
+            }
         }
     }
     sh[0][threadIdx.x] = m; sh[1][threadIdx.x] = st2; sh[2][threadIdx.x] = x2;
@@ -373,28 +382,34 @@ void build_finalize_tables(const DatasetDesc *h_desc, const int *grids, int n_ds
     outs.push_back(f);
 }
 
-size_t pose_scratch(int n_pose, int Ks)
+int pose_factor_blocks(int n_pose) { return (n_pose + FACTOR_THREADS - 1) / FACTOR_THREADS; }
+int pose_backsub_blocks(int n_pose) { return (n_pose + POSE_THREADS - 1) / POSE_THREADS; }
+
+size_t pose_scratch(int n_pose, int Ks, int n_seg)
 {
     const size_t nb_pose = (n_pose + FACTOR_THREADS - 1) / FACTOR_THREADS;
     const size_t npair = (size_t)Ks * (Ks + 1) / 2 + Ks;
-    return nb_pose * 4 + nb_pose * npair + 16;
+    return nb_pose * 4 + nb_pose * npair + 4 * (size_t)n_seg + 16;
 }
 
 cudaError_t launch_pose_schur(const DatasetDesc *d_desc, int n_pose, int Ks,
                               const int *pose_start, const int *contrib_ds, const int *contrib_img,
                               double *scale, LmConsts lm, double *ws, double *partial, size_t partial_doubles,
-                              double *red, int *fail_flag, int rank, int nranks, SolverLaunch sl)
+                              double *red, int *fail_flag, int rank, int nranks, SolverLaunch sl,
+                              const unsigned char *chain_mask, int n_seg)
 {
+    // partial: [max |g| of each block (nb_pose) | of each chain segment (n_seg, written by chain_factor) | gram rows]
     const int nb_pose = (n_pose + FACTOR_THREADS - 1) / FACTOR_THREADS;
-    if (pose_scratch(n_pose, Ks) > partial_doubles) return cudaErrorInvalidValue;
+    if (pose_scratch(n_pose, Ks, n_seg) > partial_doubles) return cudaErrorInvalidValue;
     double *p_gmax = partial;
-    double *p_gram = partial + nb_pose;
+    double *p_gram = partial + nb_pose + n_seg;
     if (n_pose > 0) {
         pose_factor_kernel<<<nb_pose, FACTOR_THREADS, 0, sl.stream>>>(d_desc, n_pose, Ks, pose_start, contrib_ds,
-                                                                     contrib_img, scale, lm, ws, p_gmax, p_gram, fail_flag);
+                                                                     contrib_img, scale, lm, ws, p_gmax, p_gram, fail_flag,
+                                                                     chain_mask);
         if (sl.launches) (*sl.launches)++;
     }
-    finalize_gram_kernel<<<1, 256, 0, sl.stream>>>(Ks, n_pose > 0 ? nb_pose : 0, p_gram, n_pose > 0 ? nb_pose : 0, p_gmax,
+    finalize_gram_kernel<<<1, 256, 0, sl.stream>>>(Ks, n_pose > 0 ? nb_pose : 0, p_gram, n_pose > 0 ? nb_pose + n_seg : 0, p_gmax,
                                                    red, fail_flag, rank, nranks);
     if (sl.launches) (*sl.launches)++;
     return cudaGetLastError();
@@ -404,16 +419,22 @@ cudaError_t launch_pose_backsub(int n_pose, int Ks, const double *delta_a,
                                 const double *const *seq_cur, double *const *seq_cand,
                                 const int *pose_seq, const int *pose_local,
                                 const double *ws, double *partial, size_t partial_doubles, double *red,
-                                SolverLaunch sl)
+                                SolverLaunch sl, const unsigned char *chain_mask, double *chain_w)
 {
     const int nb = (n_pose + POSE_THREADS - 1) / POSE_THREADS;
     if ((size_t)nb * 3 > partial_doubles) return cudaErrorInvalidValue;
     if (n_pose > 0) {
         pose_backsub_kernel<<<nb, POSE_THREADS, 0, sl.stream>>>(n_pose, Ks, delta_a, seq_cur, seq_cand, pose_seq,
-                                                                pose_local, ws, partial);
+                                                                pose_local, ws, partial, chain_mask, chain_w);
         if (sl.launches) (*sl.launches)++;
     }
-    finalize_backsub_kernel<<<1, 32, 0, sl.stream>>>(Ks, nb, partial, red);
+    return cudaGetLastError();
+}
+
+// sums the rows the back-substitution kernels left: one per pose_backsub block, then one per chain segment
+cudaError_t launch_finalize_backsub(int Ks, int n_rows, const double *partial, double *red, SolverLaunch sl)
+{
+    finalize_backsub_kernel<<<1, 32, 0, sl.stream>>>(Ks, n_rows, partial, red);
     if (sl.launches) (*sl.launches)++;
     return cudaGetLastError();
 }

@@ -85,9 +85,12 @@ void build_finalize_tables(const DatasetDesc *h_desc, const int *rows, int n_ds,
 cudaError_t launch_pose_schur(const DatasetDesc *d_desc, int n_pose, int Ks,
                               const int *pose_start, const int *contrib_ds, const int *contrib_img,
                               double *scale, LmConsts lm, double *ws, double *partial, size_t partial_doubles,
-                              double *red, int *fail_flag, int rank, int nranks, SolverLaunch sl);
+                              double *red, int *fail_flag, int rank, int nranks, SolverLaunch sl,
+                              const unsigned char *chain_mask = nullptr, int n_seg = 0);
 
-size_t pose_scratch(int n_pose, int Ks);                                 // doubles
+size_t pose_scratch(int n_pose, int Ks, int n_seg = 0);                  // doubles
+int pose_factor_blocks(int n_pose);                                      // blocks of pose_factor (slots of max |g|)
+int pose_backsub_blocks(int n_pose);                                     // blocks of pose_backsub (rows of 3 sums)
 
 // candidate poses and model / norm partial sums -> red[model..]
 // pose_ptr_cur/cand: per pose-list entry the device address of its 6 doubles is
@@ -96,6 +99,7 @@ cudaError_t launch_pose_backsub(int n_pose, int Ks, const double *delta_a,
                                 const double *const *seq_cur, double *const *seq_cand,
                                 const int *pose_seq, const int *pose_local,
                                 const double *ws, double *partial, size_t partial_doubles, double *red,
-                                SolverLaunch sl);
+                                SolverLaunch sl, const unsigned char *chain_mask = nullptr, double *chain_w = nullptr);
+cudaError_t launch_finalize_backsub(int Ks, int n_rows, const double *partial, double *red, SolverLaunch sl);
 
 }  // namespace vg
