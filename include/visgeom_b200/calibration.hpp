@@ -2,9 +2,10 @@
 // (include/calibration/unified_calibration.h, src/calibration/unified_calibration.cpp), running on the CUDA engine:
 // addResiduals() reads the reference's JSON problem files, compute() replaces ceres::Solve + the report.
 //
-// Supported dataset type: "ir_data" (pre-extracted corners, unified_calibration.cpp:234-277,648-660).  The
-// "images" type needs the checkerboard detector (OpenCV), which is outside this engine, and is rejected with a
-// message; so are the odometry / prior datasets.
+// Supported dataset types: "ir_data" (pre-extracted corners, unified_calibration.cpp:234-277,648-660), "odometry"
+// (OdometryPrior blocks between consecutive elements of a sequence, :742-807) and "transformation_prior" (:808-829).
+// The "images" type needs the checkerboard detector (OpenCV), which is outside this engine, and is rejected with a
+// message; so is "odometry_intrinsic" (wheel-odometry intrinsics as parameters, :661-741).
 #pragma once
 
 #include <map>
@@ -41,6 +42,20 @@ struct ImageData {
     }
 };
 
+// "odometry" dataset (unified_calibration.cpp:742-807)
+struct OdometryData {
+    std::string transformName;
+    double errV = 0, errW = 0, lambda = 0;
+    std::vector<Array6d> odometry;         // one reading per element of the sequence
+    bool anchor = false;                   // first element constant (:803-806)
+};
+
+// "transformation_prior" dataset (:808-829): the prior value is the transform's value when the block is created
+struct PriorData {
+    std::string transformName;
+    Array6d stiffness{}, prior{};
+};
+
 class GenericCameraCalibration {
 public:
     GenericCameraCalibration() {}
@@ -65,6 +80,8 @@ private:
     void parseTransforms(const json::Value &root);
     void parseCameras(const json::Value &root);
     void parseData(const json::Value &root);
+    void parseOdometry(const json::Value &node);
+    void parseTransformationPrior(const json::Value &node);
     void initTransformChainInfo(ImageData &data, const json::Value &node);
     void initGridIR(ImageData &data, const json::Value &node);
     void readCorners(ImageData &data, const json::Value &node);
@@ -85,6 +102,8 @@ private:
     std::map<std::string, std::vector<double>> intrinsicMap;
     std::map<std::string, bool> cameraConstantMap;
     std::vector<ImageData> dataVec;
+    std::vector<OdometryData> odometryVec;
+    std::vector<PriorData> priorVec;
     vg_solve_summary lastSummary{};
 };
 

@@ -59,6 +59,22 @@ def test_config_errors_match_the_reference(cli, tmp_path):
     assert "checkerboard detector" in run(cli, path).stderr
     assert "cannot open file" in run(cli, str(tmp_path / "missing.json")).stderr
     assert run(cli).returncode == 2
+    # the odometry / prior datasets (unified_calibration.cpp:742-829)
+    path, _ = mk.write_odometry(str(tmp_path / "g"), 5)
+    edit(path, lambda p: p["data"][0].update(transform="xiBaseCam"))
+    assert "is global. Odometry must be a sequence" in run(cli, path).stderr                   # :752-755
+    path, _ = mk.write_odometry(str(tmp_path / "h"), 5)
+    edit(path, lambda p: p["data"][2].update(transform="xiOdom"))
+    assert "must have a prior value" in run(cli, path).stderr                                  # :816-819
+    path, _ = mk.write_odometry(str(tmp_path / "i"), 5)
+    edit(path, lambda p: p["data"].insert(1, dict(p["data"][0])))
+    assert "has already been initialized" in run(cli, path).stderr                             # :781-784
+    path, _ = mk.write_odometry(str(tmp_path / "j"), 5)
+    edit(path, lambda p: p["data"][0].update(transform="nope"))
+    assert "has not been declared" in run(cli, path).stderr                                    # :747-750
+    path, _ = mk.write_odometry(str(tmp_path / "k"), 5)
+    edit(path, lambda p: p["data"][0].update(type="odometry_intrinsic"))
+    assert "is not supported by this engine" in run(cli, path).stderr
 
 
 def test_fails_loudly_without_a_gpu(cli, tmp_path):
@@ -128,3 +144,29 @@ def test_stereo_problem_matches_oracle(cli, tmp_path, oracle, prior):
         assert rel.max() < 1e-6, (name, rel)
     assert np.abs(glob["xiCam12"] - O.transform(t12)[0]).max() < 1e-6
     assert os.path.exists(str(tmp_path / "image_error_1.txt"))
+
+
+@pytest.mark.gpu
+def test_odometry_problem_matches_oracle(cli, tmp_path, oracle):
+    """"odometry" (init + anchor) and "transformation_prior" datasets next to a reprojection dataset."""
+    from oracle.pyoracle import OracleProblem
+    path, d = mk.write_odometry(str(tmp_path), 30)
+    r = run(cli, "--precision", "17", "--out", str(tmp_path) + "/", path)
+    assert r.returncode == 0, r.stderr
+    intr, glob = parse_report(r.stdout)
+    O = OracleProblem(oracle)
+    cam = O.add_camera(sd.EUCM, d["intr_init"])
+    bc = O.add_transform(d["xi_bc_init"], is_global=True)
+    od = O.add_transform(d["odom"], is_global=False)
+    wB = O.add_transform(d["xi_wB_init"], is_global=True)
+    O.add_dataset(cam, d["board"], d["obs"], [bc, od, wB], d["status"])
+    O.add_odometry(od, d["err_v"], d["err_w"], d["lam"], d["odom"])
+    O.set_pose_constant(od, 0)
+    O.add_transformation_prior(bc, [10, 10, 10, 20, 20, 20])
+    so = O.solve()
+    m = re.search(r"final cost\s+(\S+)", r.stdout)
+    assert abs(float(m.group(1)) - so.final_cost) <= 1e-6 * so.final_cost
+    rel = np.abs(intr["camera1"] - O.camera(cam)) / np.abs(O.camera(cam))
+    assert rel.max() < 1e-6, rel
+    assert np.abs(glob["xiBaseCam"] - O.transform(bc)[0]).max() < 1e-6
+    assert np.abs(glob["xiWorldBoard"] - O.transform(wB)[0]).max() < 1e-6

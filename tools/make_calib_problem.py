@@ -1,7 +1,7 @@
 """Writes synthetic calibration problems in the reference's JSON format (README.md:36-223 of visgeom,
 dataset type "ir_data": pre-extracted corners, unified_calibration.cpp:234-277) for vg_calib / the tests.
 
-  python tools/make_calib_problem.py mono|stereo OUT_DIR [n_images]
+  python tools/make_calib_problem.py mono|stereo|odometry OUT_DIR [n_images]
 """
 from __future__ import annotations
 
@@ -69,7 +69,32 @@ def write_stereo(out_dir, n_pairs=20, seed=20244, prior=True):
     return path, s
 
 
+def write_odometry(out_dir, n=30, seed=20246, anchor=True, prior=True):
+    """A camera on a wheeled base looking at one board (synthdata.make_odometry): the sequence xiOdom takes its
+    initial values from an "odometry" dataset (unified_calibration.cpp:742-807), the camera extrinsic carries a
+    "transformation_prior" (:808-829); the reprojection dataset's chain is
+    [xiBaseCam inverse, xiOdom inverse, xiWorldBoard direct]."""
+    os.makedirs(out_dir, exist_ok=True)
+    d = sd.make_odometry(n, seed=seed)
+    data_file = os.path.join(out_dir, "corners.json")
+    json.dump([[{"camera": "camera1", "points": _points(d["obs"][i])}] for i in range(n)], open(data_file, "w"))
+    fl = lambda v: [float(x) for x in v]
+    data = [{"type": "odometry", "transform": "xiOdom", "err_v": d["err_v"], "err_w": d["err_w"], "lambda": d["lam"],
+             "init": True, "anchor": bool(anchor), "value": [fl(x) for x in d["odom"]]},
+            _dataset("camera1", [("xiBaseCam", False), ("xiOdom", False), ("xiWorldBoard", True)], "none", data_file, d["board"])]
+    if prior:
+        data.append({"type": "transformation_prior", "transform": "xiBaseCam", "stiffness": [10, 10, 10, 20, 20, 20]})
+    prob = {"transformations": [{"name": "xiOdom", "global": False, "constant": False, "prior": False},
+                                {"name": "xiBaseCam", "global": True, "constant": False, "prior": True, "value": fl(d["xi_bc_init"])},
+                                {"name": "xiWorldBoard", "global": True, "constant": False, "prior": True, "value": fl(d["xi_wB_init"])}],
+            "cameras": [{"name": "camera1", "type": "eucm", "constant": False, "value": fl(d["intr_init"])}],
+            "data": data}
+    path = os.path.join(out_dir, "problem.json")
+    json.dump(prob, open(path, "w"), indent=1)
+    return path, d
+
+
 if __name__ == "__main__":
     kind, out = sys.argv[1], sys.argv[2]
     n = int(sys.argv[3]) if len(sys.argv) > 3 else 20
-    print((write_mono if kind == "mono" else write_stereo)(out, n)[0])
+    print({"mono": write_mono, "stereo": write_stereo, "odometry": write_odometry}[kind](out, n)[0])

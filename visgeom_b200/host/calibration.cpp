@@ -378,13 +378,60 @@ void GenericCameraCalibration::parseData(const json::Value &root)
             initGridIR(data, node);
             readCorners(data, node);
             initTransforms(data, node.getString("init"));
+        } else if (dataType == "odometry") {
+            parseOdometry(node);
+        } else if (dataType == "transformation_prior") {
+            parseTransformationPrior(node);
         } else if (dataType == "images") {
             throw runtime_error("dataset type \"images\" needs the checkerboard detector (OpenCV), which is outside this "
                                 "engine: extract the corners first and pass them as an \"ir_data\" dataset");
         } else {
-            throw runtime_error("dataset type \"" + dataType + "\" is not supported by this engine (reprojection datasets only)");
+            throw runtime_error("dataset type \"" + dataType + "\" is not supported by this engine");
         }
     }
+}
+
+// unified_calibration.cpp:742-807: odometry readings -> one OdometryPrior block per pair of consecutive elements
+void GenericCameraCalibration::parseOdometry(const json::Value &node)
+{
+    OdometryData od;
+    od.transformName = node.getString("transform");
+    const string &name = od.transformName;
+    if (transformInfoMap.find(name) == transformInfoMap.end()) throw runtime_error(name + " has not been declared");
+    if (transformInfoMap[name].global) throw runtime_error(name + " is global. Odometry must be a sequence");
+    od.errV = node.getDouble("err_v");        // relative error in speed
+    od.errW = node.getDouble("err_w");        // relative error in rotation
+    od.lambda = node.getDouble("lambda");
+    for (const json::Value &item : node.child("value").arr) od.odometry.push_back(transformFromData(item.numbers()).toArray());
+    if (node.getBool("init")) {               // use the odometry as initial values (:776-790)
+        cout << name << endl;
+        if (!sequenceTransformMap[name].empty()) throw runtime_error(name + " has already been initialized");
+        transformInfoMap[name].initialized = true;
+        sequenceTransformMap[name] = od.odometry;
+        sequenceInitMap[name].assign(od.odometry.size(), true);
+    }
+    od.anchor = node.getBool("anchor");
+    odometryVec.push_back(od);
+}
+
+// unified_calibration.cpp:808-829
+void GenericCameraCalibration::parseTransformationPrior(const json::Value &node)
+{
+    PriorData pr;
+    pr.transformName = node.getString("transform");
+    const string &name = pr.transformName;
+    if (transformInfoMap.find(name) == transformInfoMap.end()) throw runtime_error(name + " has not been declared");
+    if (!transformInfoMap[name].prior) throw runtime_error(name + " must have a prior value");
+    const vector<double> st = node.child("stiffness").numbers();
+    if (st.size() != 6) throw runtime_error(name + " : the stiffness must have 6 values");
+    for (int k = 0; k < 6; k++) pr.stiffness[k] = st[k];
+    // getTransformData(name): the global value, or the first element of a sequence (unified_calibration.h:161-165)
+    if (transformInfoMap[name].global) pr.prior = globalTransformMap[name];
+    else {
+        if (sequenceTransformMap[name].empty()) throw runtime_error(name + " has no values");
+        pr.prior = sequenceTransformMap[name][0];
+    }
+    priorVec.push_back(pr);
 }
 
 // unified_calibration.cpp:1160-1183
@@ -469,6 +516,22 @@ bool GenericCameraCalibration::compute()
         dsId[d] = vg_problem_add_dataset(h.p, camId[data.cameraName], P, board.data(), (int)seqIndex.size(), obs.data(),
                                          seqIndex.data(), (int)ids.size(), ids.data(), status.data());
         check(dsId[d], "vg_problem_add_dataset");
+    }
+
+    for (const PriorData &pr : priorVec) {
+        if (trId.find(pr.transformName) == trId.end()) throw runtime_error(pr.transformName + " has no values");
+        check(vg_problem_add_transformation_prior(h.p, trId[pr.transformName], 0, pr.stiffness.data(), pr.prior.data()),
+              "vg_problem_add_transformation_prior");
+    }
+    for (const OdometryData &od : odometryVec) {
+        if (trId.find(od.transformName) == trId.end())
+            throw runtime_error(od.transformName + " has no values: give a prior or initialise it");
+        if (od.odometry.size() != sequenceTransformMap[od.transformName].size())
+            throw runtime_error(od.transformName + " : " + std::to_string(od.odometry.size()) + " odometry readings for a sequence of " +
+                                std::to_string(sequenceTransformMap[od.transformName].size()) + " elements");
+        check(vg_problem_add_odometry(h.p, trId[od.transformName], od.errV, od.errW, od.lambda, (int)od.odometry.size(),
+                                      od.odometry[0].data()), "vg_problem_add_odometry");
+        if (od.anchor) check(vg_problem_set_pose_constant(h.p, trId[od.transformName], 0, 1), "vg_problem_set_pose_constant");
     }
 
     vg_solve_options o;
