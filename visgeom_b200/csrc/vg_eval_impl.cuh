@@ -28,6 +28,7 @@
 // The kernel is HBM-write bound by design (224 B written per EUCM corner).  tcgen05/TMEM are
 // not applicable (no FP64 there); the only matrix-unit use is the legacy FP64 mma.sync above.
 #pragma once
+#include <cstdlib>
 #include "vg_eval.cuh"
 #include "vg_math.cuh"
 
@@ -426,6 +427,12 @@ reproj_eval_kernel(const EvalArgs args, const int G, const int PCG)
         }
     }     // visible to everyone after the first __syncthreads below
 
+    // Programmatic dependent launch: the next kernel of the stream may take this CTA's SM slot as soon as it is
+    // free and run its own prologue (above) under this grid's tail; nothing of global memory is touched before
+    // the grids this launch depends on have completed and flushed.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
     double intr[K];
 #pragma unroll
     for (int i = 0; i < K; i++) intr[i] = __ldg(args.intr + i);
@@ -636,9 +643,17 @@ cudaError_t launch_one(const EvalArgs &args, cudaStream_t stream, unsigned long 
     if (grid > n_groups) grid = n_groups;
     if (grid_out) *grid_out = grid;
     if (query_only || args.n_img <= 0) return cudaSuccess;
-    reproj_eval_kernel<MODEL, L><<<grid, pl.threads, (size_t)pl.smem, stream>>>(args, pl.G, pl.PCG);
+    // launched with programmatic stream serialization (developer knob VG_PDL=0: plain launch)
+    static const bool pdl = [] { const char *e = getenv("VG_PDL"); return !(e && e[0] == '0'); }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(pl.threads); cfg.dynamicSmemBytes = (size_t)pl.smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, reproj_eval_kernel<MODEL, L>, args, pl.G, pl.PCG);
     if (launches) (*launches)++;
-    return cudaGetLastError();
+    return le != cudaSuccess ? le : cudaGetLastError();
 }
 
 
