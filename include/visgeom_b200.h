@@ -191,6 +191,10 @@ int vg_problem_add_transformation_prior(vg_problem *p, int transform, int index,
  * block tridiagonal along that sequence.  Returns the number of blocks added. */
 int vg_problem_add_odometry(vg_problem *p, int transform, double errV, double errW, double lambda, int n,
                             const double *odom /* n x 6 */);
+/* The LossFunction argument of AddResidualBlock for every block of a dataset: a > 0 -> SoftLOneLoss(a) (the
+ * initialisation solves use it, unified_calibration.cpp:379-404 with a = 1, :1143 with a = 25), 0 -> NULL (the
+ * global problem, :539-565).  Ceres applies the loss to the squared norm of the whole block, i.e. per image. */
+int vg_problem_set_loss(vg_problem *p, int dataset, double a);
 /* "anchor" (:803-806): SetParameterBlockConstant on ONE element of a sequence transform */
 int vg_problem_set_pose_constant(vg_problem *p, int transform, int index, int constant);
 

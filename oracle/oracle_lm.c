@@ -37,6 +37,7 @@ typedef struct {
     double *board, *obs;
     int *seq_index;
     double *H;        /* n_img x ne */
+    double loss_a;    /* SoftLOneLoss(a) on every block; 0: NULL loss */
 } ds_t;
 
 struct vgo_problem {
@@ -148,6 +149,13 @@ int vgo_problem_add_odometry(vgo_problem *p, int tr, double errV, double errW, d
     return 0;
 }
 
+int vgo_problem_set_loss(vgo_problem *p, int dataset, double a)
+{
+    if (dataset < 0 || dataset >= p->n_ds || !(a >= 0.0)) return -1;
+    p->dss[dataset].loss_a = a;
+    return 0;
+}
+
 int vgo_problem_set_pose_constant(vgo_problem *p, int tr, int index, int constant)
 {
     if (tr < 0 || tr >= p->n_tr || index < 0 || index >= p->trs[tr].n) return -1;
@@ -237,6 +245,23 @@ static void ds_gather_xi(const vgo_problem *p, const ds_t *d, double **seq_tmp,
     }
 }
 
+/* Ceres' SoftLOneLoss::Evaluate (loss_function.cc: sum = 1 + s c, tmp = sqrt(sum), rho = 2 b (tmp - 1),
+ * rho' = 1 / tmp, rho'' = -c rho' / (2 sum) < 0) followed by its Corrector (corrector.cc): with rho'' <= 0 the
+ * residuals and Jacobians of the block are scaled by sqrt(rho') and the block's cost is rho / 2.  On the packed
+ * [J r]^T [J r] block: every entry times rho', the last one (r^T r) replaced by rho. */
+static void apply_loss(ds_t *d)
+{
+    if (!(d->loss_a > 0.0)) return;
+    const double b = d->loss_a * d->loss_a;
+    for (int i = 0; i < d->n_img; i++) {
+        double *H = d->H + (size_t)i * d->ne;
+        const double tmp = sqrt(1.0 + H[d->ne - 1] / b);
+        const double rho1 = 1.0 / tmp;
+        for (int e = 0; e < d->ne - 1; e++) H[e] *= rho1;
+        H[d->ne - 1] = 2.0 * b * (tmp - 1.0);
+    }
+}
+
 static void ds_eval(const vgo_problem *p, ds_t *d, double *r, int with_H, int threads)
 {
     const double *xi[MAX_CHAIN];
@@ -246,6 +271,7 @@ static void ds_eval(const vgo_problem *p, ds_t *d, double *r, int with_H, int th
     vgo_evaluate_batch(p->cams[d->cam].model, p->cams[d->cam].params, d->n_img, d->P,
                        d->board, d->obs, d->L, d->status, is_global, xi,
                        r, NULL, NULL, with_H ? d->H : NULL, threads);
+    if (with_H) apply_loss(d);
     free(tmp);
 }
 

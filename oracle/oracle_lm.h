@@ -72,6 +72,8 @@ int vgo_problem_add_transformation_prior(vgo_problem *p, int tr, int index, cons
 /* OdometryPrior between every pair of consecutive elements of a sequence transform, built from n odometry
  * readings (unified_calibration.cpp:793-802) */
 int vgo_problem_add_odometry(vgo_problem *p, int tr, double errV, double errW, double lambda, int n, const double *odom);
+/* the LossFunction of every block of a dataset: SoftLOneLoss(a) for a > 0, NULL for 0 (unified_calibration.cpp:379,1143) */
+int vgo_problem_set_loss(vgo_problem *p, int dataset, double a);
 /* SetParameterBlockConstant on one element of a sequence ("anchor", unified_calibration.cpp:803-806) */
 int vgo_problem_set_pose_constant(vgo_problem *p, int tr, int index, int constant);
 int vgo_problem_solve(vgo_problem *p, const vgo_solve_options *o, vgo_solve_summary *s);

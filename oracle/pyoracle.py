@@ -134,6 +134,7 @@ class Oracle(_Evaluator):
         lib.vgo_problem_add_transformation_prior.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp, c_dp]
         lib.vgo_problem_add_odometry.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, c_dp]
         lib.vgo_problem_set_pose_constant.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        lib.vgo_problem_set_loss.argtypes = [C.c_void_p, C.c_int, C.c_double]
         lib.vgo_problem_solve.argtypes = [C.c_void_p, C.POINTER(SolveOptions), C.POINTER(SolveSummary)]
         lib.vgo_problem_get_camera.argtypes = [C.c_void_p, C.c_int, c_dp]
         lib.vgo_problem_get_transform.argtypes = [C.c_void_p, C.c_int, c_dp]
@@ -268,6 +269,10 @@ class OracleProblem:
         if self.lib.vgo_problem_add_odometry(self.h, transform, errV, errW, lam, od.shape[0], _dp(od)) < 0:
             raise ValueError("add_odometry failed")
         return od.shape[0] - 1
+
+    def set_loss(self, dataset, a):
+        if self.lib.vgo_problem_set_loss(self.h, dataset, float(a)) < 0:
+            raise ValueError("set_loss failed")
 
     def set_pose_constant(self, transform, index, constant=True):
         if self.lib.vgo_problem_set_pose_constant(self.h, transform, index, int(constant)) < 0:

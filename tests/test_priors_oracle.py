@@ -93,3 +93,28 @@ def test_odometry_problem_converges(oracle):
     assert s.final_cost < 1e-2 * s.initial_cost
     assert np.array_equal(P.transform(od)[0], d["xi_odom_init"][0])          # the anchor did not move
     assert np.abs(P.transform(od) - d["xi_odom_gt"]).max() < np.abs(d["odom"] - d["xi_odom_gt"]).max()
+
+
+def test_loss_matches_ceres_corrector_restated_in_numpy(oracle):
+    """SoftLOneLoss(a) + Ceres' Corrector on raw (r, J) in numpy against the oracle LM's cost, and the robustness it
+    buys: gross outliers in two images pull the squared-loss intrinsics away, the robust ones stay."""
+    d = sd.make_mono(sd.EUCM, 10, seed=5)
+    obs = d["obs"].copy(); obs[3, :20] += 40.0; obs[7, 30:60] -= 25.0
+    a = 2.0
+    o = oracle.evaluate_batch(sd.EUCM, d["intr_init"], d["board"], obs, [d["xi_init"]], [0], [0])
+    s = (o["r"] ** 2).sum(axis=1)
+    rho = 2 * a * a * (np.sqrt(1 + s / (a * a)) - 1)
+    P = OracleProblem(oracle)
+    cam = P.add_camera(sd.EUCM, d["intr_init"]); tr = P.add_transform(d["xi_init"], is_global=False)
+    ds = P.add_dataset(cam, d["board"], obs, [tr], [0])
+    P.set_loss(ds, a)
+    assert abs(P.evaluate() - 0.5 * rho.sum()) <= 1e-12 * rho.sum()
+    res = {}
+    for loss in (0.0, 1.0):
+        P = OracleProblem(oracle)
+        cam = P.add_camera(sd.EUCM, d["intr_init"]); tr = P.add_transform(d["xi_init"], is_global=False)
+        ds = P.add_dataset(cam, d["board"], obs, [tr], [0])
+        P.set_loss(ds, loss)
+        P.solve()
+        res[loss] = np.abs(P.camera(cam)[2:] - d["intr_gt"][2:]).max()
+    assert res[1.0] < 0.5 * res[0.0]

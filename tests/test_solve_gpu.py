@@ -186,3 +186,47 @@ def test_full_size_solve_properties(gpu):
     g = red[K * K:]
     A = red[:K * K].reshape(K, K)
     assert np.abs(g / np.sqrt(np.diag(A))).max() < 1e-6 * np.sqrt(2 * cost)
+
+
+def test_soft_l_one_loss_matches_oracle(gpu, oracle):
+    """SoftLOneLoss(a) on every block of a dataset (the initialisation solves, unified_calibration.cpp:379,1143):
+    cost, reduced system and the LM solution with gross outliers in two images, against the oracle (Ceres'
+    SoftLOneLoss + Corrector restated)."""
+    d = sd.make_mono(sd.EUCM, 30, seed=808)
+    obs = d["obs"].copy(); obs[3, :20] += 40.0; obs[17, 30:60] -= 25.0
+    for a in (1.0, 25.0):
+        G, O = gpu.Problem(), OracleProblem(oracle)
+        ids = []
+        for P in (G, O):
+            cam, tr, ds = build_mono(P, d, obs=obs)
+            P.set_loss(ds, a)
+            ids.append((cam, tr))
+        cost = G.evaluate()
+        assert abs(cost - O.evaluate()) <= 1e-11 * cost
+        og = G.default_options(); og.max_num_iterations = 6
+        oo = oracle.default_options(); oo.max_num_iterations = 6
+        sg, so = G.solve(og), O.solve(oo)
+        assert (sg.num_successful, sg.num_unsuccessful) == (so.num_successful, so.num_unsuccessful)
+        assert abs(sg.final_cost - so.final_cost) <= FINAL_RTOL * so.final_cost
+        assert rel(G.camera(ids[0][0]), O.camera(ids[1][0])) < FINAL_RTOL
+        assert np.abs(G.transform(ids[0][1]) - O.transform(ids[1][1])).max() < 1e-8
+    # loss off again: identical to a problem that never had one
+    G.set_loss(0, 0.0)
+    G2 = gpu.Problem(); build_mono(G2, d, obs=obs)
+    G2.set_camera(0, G.camera(0)); G2.set_transform(0, G.transform(0))
+    assert G.evaluate() == G2.evaluate()
+
+
+def test_poses_only_refinement_with_loss(gpu, oracle):
+    """estimateInitialGrid's solve (:1131-1155), batched: intrinsics constant, every pose free, SoftLOneLoss(25)."""
+    d = sd.make_mono(sd.UCM, 25, seed=909)
+    G, O = gpu.Problem(), OracleProblem(oracle)
+    ids = []
+    for P in (G, O):
+        cam, tr, ds = build_mono(P, d, intr=d["intr_gt"], constant_cam=True)
+        P.set_loss(ds, 25.0)
+        ids.append(tr)
+    sg, so = G.solve(), O.solve()
+    assert abs(sg.final_cost - so.final_cost) <= FINAL_RTOL * so.final_cost
+    assert np.abs(G.transform(ids[0]) - O.transform(ids[1])).max() < 1e-8
+    assert np.abs(G.transform(ids[0]) - d["xi_gt"]).max() < 5e-3

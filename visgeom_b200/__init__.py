@@ -78,6 +78,7 @@ def lib() -> C.CDLL:
         L.vg_problem_add_transformation_prior.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp, c_dp]
         L.vg_problem_add_odometry.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, c_dp]
         L.vg_problem_set_pose_constant.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.vg_problem_set_loss.argtypes = [C.c_void_p, C.c_int, C.c_double]
         L.vg_eval_transformation_prior.argtypes = [C.c_int, c_dp, c_dp, c_dp, c_dp, c_dp]
         L.vg_eval_odometry_prior.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, c_dp, c_dp, c_dp, c_dp,
                                              c_dp, c_dp, c_dp]
@@ -267,6 +268,10 @@ class Problem:
     def add_odometry(self, transform, errV, errW, lam, odom):
         od = _f64(odom).reshape(-1, 6)
         return _check(self.L.vg_problem_add_odometry(self.h, transform, errV, errW, lam, od.shape[0], _dp(od)))
+
+    def set_loss(self, dataset, a):
+        """SoftLOneLoss(a) on every block of the dataset (a = 0: no loss)."""
+        _check(self.L.vg_problem_set_loss(self.h, dataset, float(a)))
 
     def set_pose_constant(self, transform, index, constant=True):
         _check(self.L.vg_problem_set_pose_constant(self.h, transform, index, int(constant)))

@@ -40,6 +40,11 @@ struct EvalArgs {
     int n_fin_out;
     const double *fin_base;         // all datasets' ds_sum regions
     double *red;
+    // Robust loss on the block of an image (Ceres applies a LossFunction to the squared norm s of the whole residual
+    // block): 0 = none, else b = a^2 of SoftLOneLoss(a), rho(s) = 2 b (sqrt(1 + s / b) - 1).  rho'' < 0, so Ceres'
+    // corrector scales residuals and Jacobians by sqrt(rho'): the packed block leaves as rho' [J r]^T [J r] with
+    // rho(s) in its last entry; r / J outputs stay raw (what Evaluate returns).
+    double loss_b;
     int n_img;
     int P;
 };

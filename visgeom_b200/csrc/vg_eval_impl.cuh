@@ -567,6 +567,15 @@ reproj_eval_kernel(const EvalArgs args, const int G, const int PCG)
                     } else {
                         gram_image<MODEL, L>(st, g, lane, P);
                     }
+                    if (args.loss_b > 0.0) {       // SoftLOneLoss on this image's block (see EvalArgs::loss_b)
+                        double *Hg = st.Hs + (size_t)g * LY::NE;
+                        __syncwarp();
+                        const double q = sqrt(1.0 + Hg[LY::NE - 1] / args.loss_b);
+                        const double w = 1.0 / q;
+                        __syncwarp();
+                        for (int e = lane; e < LY::NE - 1; e += 32) Hg[e] *= w;
+                        if (lane == 0) Hg[LY::NE - 1] = 2.0 * args.loss_b * (q - 1.0);
+                    }
                 }
                 fence_proxy_async_smem();
                 VG_PC(4)

@@ -48,6 +48,7 @@ struct Ds {
     int cam, P, n_img, L, D, W, ne;
     int tr[VG_MAX_CHAIN], status[VG_MAX_CHAIN];
     int seq_tr;                    // transform id of the chain's sequence element
+    double loss_a;                 // SoftLOneLoss(a) on every block of the dataset; 0: none (NULL loss)
     std::vector<int> seq_index;
     bool identity_index;
     double *d_board, *d_obs;
@@ -490,6 +491,7 @@ int evaluate_set(vg_problem *p, int s, bool timed)
             a.fin_base = p->d_ds_sum; a.red = p->d_red;
         }
         a.n_img = d.n_img; a.P = d.P;
+        a.loss_b = d.loss_a * d.loss_a;
         cudaError_t e = launch_eval(p->cams[d.cam].model, d.L, a, p->stream, &launch_counter());
         if (e != cudaSuccess) return fail_cuda(e, "reproj_eval_kernel launch");
     }
@@ -737,6 +739,14 @@ int vg_problem_add_odometry(vg_problem *p, int transform, double errV, double er
     od.odom.assign(odom, odom + (size_t)6 * n);
     p->odoms.push_back(od);
     return n - 1;
+}
+
+int vg_problem_set_loss(vg_problem *p, int dataset, double a)
+{
+    if (!p || dataset < 0 || dataset >= (int)p->dss.size()) return fail(VG_ERR_INVALID, "bad dataset");
+    if (!(a >= 0.0)) return fail(VG_ERR_INVALID, "vg_problem_set_loss: the scale must be positive (0: no loss)");
+    p->dss[dataset].loss_a = a;        // a launch parameter: nothing prepared depends on it
+    return VG_OK;
 }
 
 int vg_problem_set_pose_constant(vg_problem *p, int transform, int index, int constant)

@@ -244,9 +244,9 @@ Transf GenericCameraCalibration::estimateInitialGridGuess(const ImageData &data,
 
 // The refinement part of estimateInitialGrid (unified_calibration.cpp:1131-1155), batched: the reference solves
 // one 6-parameter problem per image with the intrinsics constant; here all images of the dataset are the poses
-// of ONE problem on the GPU (they are independent: the Hessian is block diagonal).  Difference, stated: the
-// reference wraps each block in SoftLOneLoss(25), this solve uses the plain squared residual (an initial guess
-// for the global problem either way).
+// of ONE problem on the GPU (they are independent: the Hessian is block diagonal), each block under
+// SoftLOneLoss(25) as in the reference (:1143).  Difference, stated: one trust region for the batch instead of one
+// per image (the minima are the same).
 void GenericCameraCalibration::refineInitialGrids(const ImageData &data, const vector<int> &idx, vector<Array6d> &xi) const
 {
     if (idx.empty()) return;
@@ -265,7 +265,9 @@ void GenericCameraCalibration::refineInitialGrids(const ImageData &data, const v
     const int tr = vg_problem_add_transform(h.p, 0, 0, n, poses.data());
     check(tr, "vg_problem_add_transform");
     const int status = VG_TRANSFORM_DIRECT;
-    check(vg_problem_add_dataset(h.p, camId, P, board.data(), n, obs.data(), nullptr, 1, &tr, &status), "vg_problem_add_dataset");
+    const int ds = vg_problem_add_dataset(h.p, camId, P, board.data(), n, obs.data(), nullptr, 1, &tr, &status);
+    check(ds, "vg_problem_add_dataset");
+    check(vg_problem_set_loss(h.p, ds, 25.0), "vg_problem_set_loss");        // new SoftLOneLoss(25), :1143
     vg_solve_options o;
     vg_solve_options_default(&o);
     o.max_num_iterations = 500;                // as the reference's per-image solve
@@ -278,7 +280,7 @@ void GenericCameraCalibration::refineInitialGrids(const ImageData &data, const v
 }
 
 // unified_calibration.cpp:358-427: a global transform initialised from one image is refined over all images
-// of the dataset with every other block constant (the reference uses SoftLOneLoss(1) there)
+// of the dataset with every other block constant, every block under SoftLOneLoss(1) (:379-404)
 void GenericCameraCalibration::initGlobalTransform(const ImageData &data, const string &name)
 {
     const ICamera *cam = cameraMap.at(data.cameraName);
@@ -309,8 +311,10 @@ void GenericCameraCalibration::initGlobalTransform(const ImageData &data, const 
         ids.push_back(id);
         status.push_back(data.transStatusVec[i]);
     }
-    check(vg_problem_add_dataset(h.p, camId, P, board.data(), (int)seqIndex.size(), obs.data(), seqIndex.data(),
-                                 (int)ids.size(), ids.data(), status.data()), "vg_problem_add_dataset");
+    const int ds = vg_problem_add_dataset(h.p, camId, P, board.data(), (int)seqIndex.size(), obs.data(), seqIndex.data(),
+                                          (int)ids.size(), ids.data(), status.data());
+    check(ds, "vg_problem_add_dataset");
+    check(vg_problem_set_loss(h.p, ds, 1.0), "vg_problem_set_loss");         // new SoftLOneLoss(1), :379-404
     vg_solve_options o;
     vg_solve_options_default(&o);
     o.max_num_iterations = 500;
