@@ -1,5 +1,3 @@
 set -x
-python -m pytest tests -m gpu -q --tb=short 2>&1 | tail -30
-python tools/kernel_timing.py --modes full,normal 2>&1 | tail -2
-python tools/kernel_timing.py --model 2 --modes full 2>&1 | tail -1
-python tools/lm_timing.py 2>&1 | tail -1
+ncu --set full --clock-control none --import-source on -k regex:"pose_factor|pose_backsub" -s 6 -c 2 -o gpurun_out/prof_lm_r1i python tools/lm_timing.py > gpurun_out/ncu_lm.log 2>&1
+tail -2 gpurun_out/ncu_lm.log

@@ -15,6 +15,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -127,13 +128,21 @@ struct vg_problem {
     FinSrc *d_fin_src = nullptr;
     int n_fin_out = 0;
     double **d_seq_ptr[2] = {nullptr, nullptr};
-    double *d_scale = nullptr, *d_ws = nullptr, *d_partial = nullptr, *d_red = nullptr, *d_delta = nullptr;
+    double *d_scale = nullptr, *d_ws = nullptr, *d_partial = nullptr, *d_delta = nullptr;
+    // per parameter set: [segment E | segment S | reduced_solve's scalars | candidate slab] (vg_solver_kernels.cuh)
+    double *d_redbuf[2] = {nullptr, nullptr};
+    int red_doubles = 0;
+    // shared parameter j: its slab position and box bounds; Jacobi scaling of the shared block
+    int *d_sh_off = nullptr;
+    unsigned int *d_solver_tickets = nullptr;   // "last block done" counters of pose_factor / pose_backsub
+    double *d_sh_lo = nullptr, *d_sh_hi = nullptr, *d_scale_a = nullptr;
+    std::vector<int> h_sh_off;
     double *d_cta_partial = nullptr;
     // fused reduction (vg_eval.cuh): per dataset its tickets / level-1 rows, all datasets' sums, table offsets
     unsigned int *d_tickets = nullptr;
     double *d_lvl1 = nullptr, *d_ds_sum = nullptr;
     std::vector<int> h_ticket_off, h_lvl1_off, h_sum_off;
-    int last_ds = -1;                           // the last dataset with images: its launch assembles d_red
+    int last_ds = -1;                           // the last dataset with images: its launch assembles the reduced system
     size_t partial_doubles = 0, cta_partial_doubles = 0;
     double *h_red = nullptr;                  // pinned
     double *h_up = nullptr;                   // pinned upload staging: [slab | delta_a]
@@ -176,9 +185,18 @@ namespace {
 void free_prepared(vg_problem *p)
 {
     auto F = [](auto *&ptr) { if (ptr) { cudaFree(ptr); ptr = nullptr; } };
+    if (p->prepared) {
+        // the device holds the current sequence poses (a solve leaves them there): bring the host copies up to date
+        // before the buffers that say which set is current go away
+        for (Tr &t : p->trs)
+            if (!t.is_global && !t.constant)
+                cudaMemcpyAsync(t.host.data(), t.dev[p->cur], sizeof(double) * 6 * t.n, cudaMemcpyDeviceToHost, p->stream);
+        cudaStreamSynchronize(p->stream);
+    }
     for (int s = 0; s < 2; s++) { F(p->d_slab[s]); F(p->d_desc[s]); F(p->d_seq_ptr[s]); }
     F(p->d_pose_start); F(p->d_contrib_ds); F(p->d_contrib_img); F(p->d_pose_seq); F(p->d_pose_local);
-    F(p->d_fail); F(p->d_fin_out); F(p->d_fin_src); F(p->d_cta_partial); F(p->d_tickets); F(p->d_lvl1); F(p->d_ds_sum); F(p->d_scale); F(p->d_ws); F(p->d_partial); F(p->d_red); F(p->d_delta);
+    F(p->d_fail); F(p->d_fin_out); F(p->d_fin_src); F(p->d_cta_partial); F(p->d_tickets); F(p->d_lvl1); F(p->d_ds_sum); F(p->d_scale); F(p->d_ws); F(p->d_partial); F(p->d_redbuf[0]); F(p->d_redbuf[1]); F(p->d_delta);
+    F(p->d_solver_tickets); F(p->d_sh_off); F(p->d_sh_lo); F(p->d_sh_hi); F(p->d_scale_a);
     for (int s = 0; s < 2; s++) { F(p->d_tp_out[s]); F(p->d_op_out[s]); F(p->d_tp_xi[s]); F(p->d_op_xi[s]); }
     F(p->d_tp_const); F(p->d_op_const); F(p->d_tp_shared_rec); F(p->d_tp_shared_off); F(p->d_seg_start); F(p->d_seg_len);
     F(p->d_extra_start); F(p->d_extra_kind); F(p->d_extra_rec); F(p->d_prev_edge); F(p->d_mask); F(p->d_fixed);
@@ -442,10 +460,27 @@ int prepare(vg_problem *p)
     }
     p->partial_doubles = pose_scratch(NP, Ks, p->n_seg) + 3 * (size_t)pose_backsub_blocks(NP) + 64;
     VG_CUDA(cudaMalloc(&p->d_partial, sizeof(double) * p->partial_doubles));
-    const int rs = red_size(Ks, p->nranks);
-    VG_CUDA(cudaMalloc(&p->d_red, sizeof(double) * rs));
-    VG_CUDA(cudaMemset(p->d_red, 0, sizeof(double) * rs));
+    const int rs = p->red_doubles = red_size(Ks, p->nranks) + SOLVE_OUT + (int)p->slab_doubles;
+    for (int s = 0; s < 2; s++) {
+        VG_CUDA(cudaMalloc(&p->d_redbuf[s], sizeof(double) * rs));
+        VG_CUDA(cudaMemset(p->d_redbuf[s], 0, sizeof(double) * rs));
+    }
     VG_CUDA(cudaMallocHost(&p->h_red, sizeof(double) * rs));
+    // where each shared parameter lives in the slab (cameras first, then free globals: the order of shared_off)
+    p->h_sh_off.assign(Ks ? Ks : 1, 0);
+    for (size_t ci = 0; ci < p->cams.size(); ci++)
+        if (p->cams[ci].shared_off >= 0)
+            for (int k = 0; k < p->cams[ci].K; k++) p->h_sh_off[p->cams[ci].shared_off + k] = (int)(ci * CAM_STRIDE) + k;
+    for (const Tr &t : p->trs)
+        if (t.shared_off >= 0)
+            for (int k = 0; k < 6; k++) p->h_sh_off[t.shared_off + k] = (int)(p->cams.size() * CAM_STRIDE) + t.glob_slot * 6 + k;
+    VG_CUDA(cudaMalloc(&p->d_solver_tickets, 2 * sizeof(unsigned int)));
+    VG_CUDA(cudaMemset(p->d_solver_tickets, 0, 2 * sizeof(unsigned int)));
+    VG_CUDA(cudaMalloc(&p->d_sh_off, sizeof(int) * (Ks ? Ks : 1)));
+    VG_CUDA(cudaMemcpy(p->d_sh_off, p->h_sh_off.data(), sizeof(int) * (Ks ? Ks : 1), cudaMemcpyHostToDevice));
+    VG_CUDA(cudaMalloc(&p->d_sh_lo, sizeof(double) * (Ks ? Ks : 1)));
+    VG_CUDA(cudaMalloc(&p->d_sh_hi, sizeof(double) * (Ks ? Ks : 1)));
+    VG_CUDA(cudaMalloc(&p->d_scale_a, sizeof(double) * (Ks ? Ks : 1)));
     p->cur = 0;
     // both parameter sets start from the host values
     fill_slab(p, p->h_slab.data());
@@ -461,7 +496,7 @@ int prepare(vg_problem *p)
 }
 
 // fused residual + Jacobian + normal-equation kernels of every dataset at parameter set s,
-// then the shared-block reduction -> d_red segment E (A, g_a, cost)
+// then the shared-block reduction -> segment E (A, g_a, cost) of that set's reduction buffer
 int evaluate_set(vg_problem *p, int s, bool timed)
 {
     if (timed) VG_CUDA(cudaEventRecord(p->ev0, p->stream));
@@ -486,9 +521,9 @@ int evaluate_set(vg_problem *p, int s, bool timed)
         a.tickets = p->d_tickets + p->h_ticket_off[k];
         a.lvl1 = p->d_lvl1 + p->h_lvl1_off[k];
         a.ds_sum = p->d_ds_sum + p->h_sum_off[k];
-        if (k == p->last_ds) {      // the shared-block reduction -> d_red segment E is the tail of this launch
+        if (k == p->last_ds) {      // the shared-block reduction -> segment E is the tail of this launch
             a.fin_outs = p->d_fin_out; a.fin_srcs = p->d_fin_src; a.n_fin_out = p->n_fin_out;
-            a.fin_base = p->d_ds_sum; a.red = p->d_red;
+            a.fin_base = p->d_ds_sum; a.red = p->d_redbuf[s];
         }
         a.n_img = d.n_img; a.P = d.P;
         a.loss_b = d.loss_a * d.loss_a;
@@ -496,10 +531,10 @@ int evaluate_set(vg_problem *p, int s, bool timed)
         if (e != cudaSuccess) return fail_cuda(e, "reproj_eval_kernel launch");
     }
     if (p->n_tp + p->n_op > 0) {
-        // the 6-residual blocks: their normal-equation pieces, then cost and shared-block terms on top of d_red
-        if (p->last_ds < 0) VG_CUDA(cudaMemsetAsync(p->d_red, 0, sizeof(double) * red_off_model(p->Ks), p->stream));
+        // the 6-residual blocks: their normal-equation pieces, then cost and shared-block terms on top of the reduced system
+        if (p->last_ds < 0) VG_CUDA(cudaMemsetAsync(p->d_redbuf[s], 0, sizeof(double) * red_off_model(p->Ks), p->stream));
         SolverLaunch sl{p->stream, &launch_counter()};
-        cudaError_t e = launch_prior_eval(p->prior_tables(s), p->Ks, p->d_red, 1, nullptr, sl);
+        cudaError_t e = launch_prior_eval(p->prior_tables(s), p->Ks, p->d_redbuf[s], 1, nullptr, sl);
         if (e != cudaSuccess) return fail_cuda(e, "prior_eval launch");
     }
     if (timed) VG_CUDA(cudaEventRecord(p->ev1, p->stream));
@@ -507,14 +542,24 @@ int evaluate_set(vg_problem *p, int s, bool timed)
     return VG_OK;
 }
 
-// exchange a segment of the reduction buffer across ranks (if any) and fetch it
-int fetch_segment(vg_problem *p, int off, int count)
+// sum a segment of a set's reduction buffer across ranks (if any)
+int exchange_segment(vg_problem *p, int s, int off, int count)
 {
-    if (p->allreduce && p->nranks > 1) {
-        if (p->allreduce(p->allreduce_ctx, p->d_red + off, count, p->stream) != 0)
+    if (count > 0 && p->allreduce && p->nranks > 1) {
+        if (p->allreduce(p->allreduce_ctx, p->d_redbuf[s] + off, count, p->stream) != 0)
             return fail(VG_ERR_CUDA, "all-reduce callback failed");
     }
-    VG_CUDA(cudaMemcpyAsync(p->h_red + off, p->d_red + off, sizeof(double) * count, cudaMemcpyDeviceToHost, p->stream));
+    return VG_OK;
+}
+
+// exchange a segment across ranks and fetch `fetch` doubles from its start (>= count: what follows the segment
+// is local to the rank)
+int fetch_segment(vg_problem *p, int s, int off, int count, int fetch = 0)
+{
+    int rc = exchange_segment(p, s, off, count);
+    if (rc) return rc;
+    if (fetch < count) fetch = count;
+    VG_CUDA(cudaMemcpyAsync(p->h_red + off, p->d_redbuf[s] + off, sizeof(double) * fetch, cudaMemcpyDeviceToHost, p->stream));
     VG_CUDA(cudaStreamSynchronize(p->stream));
     return VG_OK;
 }
@@ -806,7 +851,7 @@ int vg_problem_evaluate_async(vg_problem *p)
     if (rc) return rc;
     if (p->allreduce && p->nranks > 1) {
         const int Ks = p->Ks;
-        if (p->allreduce(p->allreduce_ctx, p->d_red, red_off_model(Ks), p->stream) != 0)
+        if (p->allreduce(p->allreduce_ctx, p->d_redbuf[p->cur], red_off_model(Ks), p->stream) != 0)
             return fail(VG_ERR_CUDA, "all-reduce callback failed");
     }
     return VG_OK;
@@ -817,7 +862,7 @@ int vg_problem_fetch_reduced(vg_problem *p, double *cost, double *reduced)
     if (!p || !p->prepared) return fail(VG_ERR_INVALID, "nothing evaluated yet");
     VG_CUDA(cudaSetDevice(p->device));
     const int Ks = p->Ks, n = red_off_model(Ks);
-    VG_CUDA(cudaMemcpyAsync(p->h_red, p->d_red, sizeof(double) * n, cudaMemcpyDeviceToHost, p->stream));
+    VG_CUDA(cudaMemcpyAsync(p->h_red, p->d_redbuf[p->cur], sizeof(double) * n, cudaMemcpyDeviceToHost, p->stream));
     VG_CUDA(cudaStreamSynchronize(p->stream));
     if (cost) *cost = p->h_red[red_off_cost(Ks)];
     if (reduced) memcpy(reduced, p->h_red, sizeof(double) * (Ks * Ks + Ks));
@@ -930,7 +975,7 @@ int vg_problem_evaluate(vg_problem *p, double *cost, double *reduced)
     rc = evaluate_set(p, p->cur, false);
     if (rc) return rc;
     const int Ks = p->Ks;
-    rc = fetch_segment(p, 0, red_segE_size(Ks));
+    rc = fetch_segment(p, p->cur, 0, red_segE_size(Ks));
     if (rc) return rc;
     if (cost) *cost = p->h_red[red_off_cost(Ks)];
     if (reduced) memcpy(reduced, p->h_red, sizeof(double) * (Ks * Ks + Ks));
@@ -980,9 +1025,8 @@ int vg_problem_solve(vg_problem *p, const vg_solve_options *opt, vg_solve_summar
     p->eval_ms = 0; p->n_eval = 0;
     const int Ks = p->Ks, NP = p->n_pose;
     const int segE = red_segE_size(Ks), offS = red_off_S(Ks), segS = red_segS_size(Ks, p->nranks);
+    const int off_out = red_size(Ks, p->nranks), off_slab = off_out + SOLVE_OUT;
     SolverLaunch sl{p->stream, &launch_counter()};
-    std::vector<double> A(Ks * Ks), ga(Ks), S(Ks * Ks), rhs(Ks), da(Ks), scale_a(Ks, 1.0);
-    std::vector<double> cand_slab(p->slab_doubles);
     const size_t glob0 = p->cams.size() * CAM_STRIDE;
 
     auto collect_eval_time = [&]() {
@@ -990,122 +1034,125 @@ int vg_problem_solve(vg_problem *p, const vg_solve_options *opt, vg_solve_summar
         if (cudaEventElapsedTime(&ms, p->ev0, p->ev1) == cudaSuccess) p->eval_ms += ms;
     };
 
+    // box bounds of the shared parameters (cameras: the model's or vg_problem_set_bounds'; transforms: none)
+    {
+        std::vector<double> lo(Ks ? Ks : 1, -1e300), hi(Ks ? Ks : 1, 1e300);
+        for (const Cam &c : p->cams)
+            if (c.shared_off >= 0)
+                for (int k = 0; k < c.K; k++) { lo[c.shared_off + k] = c.lo[k]; hi[c.shared_off + k] = c.hi[k]; }
+        // h_up is pinned and at least 2 Ks doubles long; nothing else uses it while a solve runs
+        memcpy(p->h_up, lo.data(), sizeof(double) * Ks);
+        memcpy(p->h_up + Ks, hi.data(), sizeof(double) * Ks);
+        if (Ks) {
+            VG_CUDA(cudaMemcpyAsync(p->d_sh_lo, p->h_up, sizeof(double) * Ks, cudaMemcpyHostToDevice, p->stream));
+            VG_CUDA(cudaMemcpyAsync(p->d_sh_hi, p->h_up + Ks, sizeof(double) * Ks, cudaMemcpyHostToDevice, p->stream));
+        }
+    }
+
     // iteration 0: evaluate at the starting point
-    VG_CUDA(cudaMemsetAsync(p->d_red + red_off_model(Ks), 0, 3 * sizeof(double), p->stream));
+    for (int s_ = 0; s_ < 2; s_++)
+        VG_CUDA(cudaMemsetAsync(p->d_redbuf[s_] + red_off_model(Ks), 0, 3 * sizeof(double), p->stream));
     rc = evaluate_set(p, p->cur, true);
     if (rc) return rc;
-    rc = fetch_segment(p, 0, segE);
+    rc = fetch_segment(p, p->cur, 0, segE);
     if (rc) return rc;
     collect_eval_time();
     double cost = p->h_red[red_off_cost(Ks)];
-    memcpy(A.data(), p->h_red + red_off_A(Ks), sizeof(double) * Ks * Ks);
-    memcpy(ga.data(), p->h_red + red_off_g(Ks), sizeof(double) * Ks);
     sum->initial_cost = cost;
-    for (int j = 0; j < Ks; j++) scale_a[j] = o.jacobi_scaling ? 1.0 / (1.0 + std::sqrt(A[j * Ks + j])) : 1.0;
 
     double radius = o.initial_radius, decrease_factor = 2.0;
     int invalid_run = 0, iter = 0;
     bool init_scale = true;
     sum->termination = 3;
+    static const bool trace = getenv("VG_LM_TRACE") != nullptr;      // developer knob: host timeline of the loop
+    cudaEvent_t tev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (trace) for (auto &e : tev) cudaEventCreate(&e);
+    auto mark = [&](int i) { if (trace) cudaEventRecord(tev[i], p->stream); };
+    double t_iter = now_s();
+    if (trace) fprintf(stderr, "[vg lm] start + first evaluation: %.1f us\n", (t_iter - t_start) * 1e6);
 
     for (;;) {
-        // per-pose damped factorisation + Schur terms at the current radius (also max |g_pose|)
+        // One host synchronisation per iteration: the per-pose damped factorisation + Schur terms at the current
+        // radius, the reduced solve, the back-substitution and the candidate's evaluation are queued back to back;
+        // what the decisions below need comes back in one copy.  When the iteration or radius limit is already
+        // reached only the gradient test is still due (Ceres tests it first), so the step itself is not queued.
+        const bool limits = iter >= o.max_num_iterations || radius < o.min_radius;
+        const int cand = p->cur ^ 1;
         LmConsts lm{radius, o.min_lm_diagonal, o.max_lm_diagonal, init_scale ? 1 : 0, o.jacobi_scaling};
         cudaError_t ce = cudaSuccess;
+        mark(0);
         if (p->n_seg > 0)      // coupled / constant elements first: their rows of ws, max |g| per segment
             ce = launch_chain_factor(p->d_desc[p->cur], Ks, p->d_pose_start, p->d_contrib_ds, p->d_contrib_img, p->d_scale, lm,
                                      p->d_ws, p->chain_tables(p->cur), p->d_partial + pose_factor_blocks(NP), p->d_fail, sl);
+        // reduced system  (A + D_a - S_red) delta_a = -(g_a - v_red), candidate shared parameters Pi(x + delta_a): on one
+        // rank in the tail of the pose factorisation kernel, else in its own launch after the exchange of S_red, v_red
+        const SolveArgs sa{(int)p->slab_doubles, p->nranks, p->d_redbuf[p->cur], p->d_redbuf[cand], p->d_slab[p->cur],
+                           p->d_slab[cand], p->d_delta, p->d_sh_off, p->d_sh_lo, p->d_sh_hi, p->d_scale_a};
+        const bool fuse = p->nranks == 1 && NP > 0;
         if (ce == cudaSuccess)
             ce = launch_pose_schur(p->d_desc[p->cur], NP, Ks, p->d_pose_start, p->d_contrib_ds, p->d_contrib_img,
-                                   p->d_scale, lm, p->d_ws, p->d_partial, p->partial_doubles, p->d_red,
-                                   p->d_fail, p->rank, p->nranks, sl, p->d_mask, p->n_seg);
+                                   p->d_scale, lm, p->d_ws, p->d_partial, p->partial_doubles, p->d_redbuf[p->cur],
+                                   p->d_fail, p->rank, p->nranks, sl, p->d_mask, p->n_seg, fuse ? &sa : nullptr,
+                                   fuse ? p->d_solver_tickets : nullptr);
         if (ce != cudaSuccess) return fail_cuda(ce, "pose_schur");
+        mark(1);
+        if (!fuse) {
+            rc = exchange_segment(p, p->cur, offS, segS);
+            if (rc) return rc;
+            ce = launch_reduced_solve(Ks, sa, lm, sl);
+            if (ce != cudaSuccess) return fail_cuda(ce, "reduced_solve");
+        }
         init_scale = false;
-        rc = fetch_segment(p, offS, segS);
-        if (rc) return rc;
-        // gradient tolerance: max-norm of the projected gradient
-        double gmax = 0;
-        for (int r = 0; r < p->nranks; r++) gmax = std::fmax(gmax, p->h_red[red_off_gmax(Ks) + r]);
-        for (const Cam &c : p->cams) {
-            if (c.shared_off < 0) continue;
-            for (int k = 0; k < c.K; k++) {
-                const double x = c.params[k], g = ga[c.shared_off + k];
-                gmax = std::fmax(gmax, std::fabs(x - clampd(x - g, c.lo[k], c.hi[k])));
-            }
-        }
-        for (const Tr &t : p->trs)
-            if (t.shared_off >= 0)
-                for (int k = 0; k < 6; k++) gmax = std::fmax(gmax, std::fabs(ga[t.shared_off + k]));
-        if (gmax <= o.gradient_tolerance) { sum->termination = 1; break; }
-        if (iter >= o.max_num_iterations) { sum->termination = 3; break; }
-        if (radius < o.min_radius) { sum->termination = 4; break; }
-        iter++;
-
-        bool ok = p->h_red[red_off_fail(Ks)] == 0.0;
-        // reduced system  (A + D_a - S_red) delta_a = -(g_a - v_red)
-        if (ok && Ks > 0) {
-            for (int i = 0; i < Ks * Ks; i++) S[i] = A[i] - p->h_red[offS + i];
-            for (int j = 0; j < Ks; j++) {
-                const double s2 = scale_a[j] * scale_a[j];
-                S[j * Ks + j] += clampd(s2 * A[j * Ks + j], o.min_lm_diagonal, o.max_lm_diagonal) / (radius * s2);
-                rhs[j] = -(ga[j] - p->h_red[red_off_v(Ks) + j]);
-            }
-            if (chol(S, Ks)) ok = false;
-            else { da = rhs; chol_solve(S, Ks, da.data()); }
-        }
-        double model_change = 0, step2 = 0, x2 = 0, new_cost = 0;
-        const int cand = p->cur ^ 1;
-        if (ok) {
-            // candidate shared parameters = Pi(x + delta_a), uploaded together with delta_a
-            fill_slab(p, cand_slab.data());
-            for (size_t ci = 0; ci < p->cams.size(); ci++) {
-                const Cam &c = p->cams[ci];
-                if (c.shared_off < 0) continue;
-                for (int k = 0; k < c.K; k++) {
-                    const double x = c.params[k];
-                    const double xn = clampd(x + da[c.shared_off + k], c.lo[k], c.hi[k]);
-                    x2 += x * x; step2 += (xn - x) * (xn - x);
-                    cand_slab[ci * CAM_STRIDE + k] = xn;
-                }
-            }
-            for (const Tr &t : p->trs) {
-                if (t.shared_off < 0) continue;
-                for (int k = 0; k < 6; k++) {
-                    const double x = t.host[k], dd = da[t.shared_off + k];
-                    x2 += x * x; step2 += dd * dd;
-                    cand_slab[glob0 + (size_t)t.glob_slot * 6 + k] = x + dd;
-                }
-            }
-            memcpy(p->h_up, cand_slab.data(), p->slab_doubles * sizeof(double));
-            if (Ks) memcpy(p->h_up + p->slab_doubles, da.data(), sizeof(double) * Ks);
-            VG_CUDA(cudaMemcpyAsync(p->d_slab[cand], p->h_up, p->slab_doubles * sizeof(double), cudaMemcpyHostToDevice, p->stream));
-            if (Ks) VG_CUDA(cudaMemcpyAsync(p->d_delta, p->h_up + p->slab_doubles, sizeof(double) * Ks, cudaMemcpyHostToDevice, p->stream));
-            // candidate poses + model-decrease / norm partial sums, then the evaluation there
+        mark(2);
+        if (!limits) {
+            // candidate poses + model-decrease / norm partial sums (summed by the kernel's last block unless chain
+            // segments add rows of their own), then the evaluation there
+            const bool fuse_b = NP > 0 && p->n_seg == 0;
             ce = launch_pose_backsub(NP, Ks, p->d_delta, p->d_seq_ptr[p->cur], p->d_seq_ptr[cand], p->d_pose_seq,
-                                     p->d_pose_local, p->d_ws, p->d_partial, p->partial_doubles, p->d_red, sl, p->d_mask,
-                                     p->d_chain_w);
+                                     p->d_pose_local, p->d_ws, p->d_partial, p->partial_doubles, p->d_redbuf[cand], sl, p->d_mask,
+                                     p->d_chain_w, fuse_b ? p->d_solver_tickets + 1 : nullptr);
             const int nb_b = pose_backsub_blocks(NP);
             if (ce == cudaSuccess && p->n_seg > 0)
                 ce = launch_chain_backsub(Ks, p->d_seq_ptr[p->cur], p->d_seq_ptr[cand], p->d_pose_seq, p->d_pose_local, p->d_ws,
                                           p->chain_tables(p->cur), p->d_partial + 3 * (size_t)nb_b, sl);
-            if (ce == cudaSuccess) ce = launch_finalize_backsub(Ks, nb_b + p->n_seg, p->d_partial, p->d_red, sl);
+            if (ce == cudaSuccess && !fuse_b) ce = launch_finalize_backsub(Ks, nb_b + p->n_seg, p->d_partial, p->d_redbuf[cand], sl);
             if (ce != cudaSuccess) return fail_cuda(ce, "pose_backsub");
+            mark(3);
             rc = evaluate_set(p, cand, true);
             if (rc) return rc;
-            rc = fetch_segment(p, 0, segE);
-            if (rc) return rc;
-            collect_eval_time();
-            new_cost = p->h_red[red_off_cost(Ks)];
-            double gd = 0, dHd = 0;
-            for (int s_ = 0; s_ < Ks; s_++) {
-                gd += ga[s_] * da[s_];
-                double t = 0;
-                for (int s2 = 0; s2 < Ks; s2++) t += A[s_ * Ks + s2] * da[s2];
-                dHd += da[s_] * t;
+            mark(4);
+        }
+        const double t_queued = trace ? now_s() : 0.0;
+        rc = fetch_segment(p, cand, 0, limits ? 0 : segE, p->red_doubles);
+        if (rc) return rc;
+        if (trace) {
+            const double t_now = now_s();
+            fprintf(stderr, "[vg lm] iteration %d: queued in %.1f us, waited %.1f us\n", iter + 1, (t_queued - t_iter) * 1e6,
+                    (t_now - t_queued) * 1e6);
+            t_iter = t_now;
+            if (!limits) {
+                float a = 0, b = 0, c = 0, d = 0;
+                cudaEventElapsedTime(&a, tev[0], tev[1]); cudaEventElapsedTime(&b, tev[1], tev[2]);
+                cudaEventElapsedTime(&c, tev[2], tev[3]); cudaEventElapsedTime(&d, tev[3], tev[4]);
+                fprintf(stderr, "[vg lm]   device: pose factor + Schur terms %.1f us, reduced solve %.1f us, back-substitution %.1f us, "
+                        "evaluation %.1f us\n", a * 1e3, b * 1e3, c * 1e3, d * 1e3);
             }
-            model_change = -(gd + 0.5 * dHd + p->h_red[red_off_model(Ks)]);
-            step2 += p->h_red[red_off_model(Ks) + 1];
-            x2 += p->h_red[red_off_model(Ks) + 2];
+        }
+        const double *so = p->h_red + off_out;
+        // gradient tolerance: max-norm of the projected gradient at the current point
+        if (so[0] <= o.gradient_tolerance) { sum->termination = 1; break; }
+        if (iter >= o.max_num_iterations) { sum->termination = 3; break; }
+        if (radius < o.min_radius) { sum->termination = 4; break; }
+        iter++;
+        collect_eval_time();
+
+        bool ok = so[1] == 0.0 && so[2] != 0.0;      // every pose block and the reduced system factorised
+        double model_change = 0, step2 = 0, x2 = 0;
+        const double new_cost = p->h_red[red_off_cost(Ks)];
+        if (ok) {
+            model_change = -(so[3] + 0.5 * so[4] + p->h_red[red_off_model(Ks)]);
+            step2 = so[5] + p->h_red[red_off_model(Ks) + 1];
+            x2 = so[6] + p->h_red[red_off_model(Ks) + 2];
             if (!(model_change > 0.0)) ok = false;
         }
         if (!ok) {
@@ -1128,12 +1175,11 @@ int vg_problem_solve(vg_problem *p, const vg_solve_options *opt, vg_solve_summar
         if (rho > o.min_relative_decrease) {
             const double cost_change = cost - new_cost, old_cost = cost;
             p->cur = cand;
+            const double *cs = p->h_red + off_slab;     // the candidate slab reduced_solve left
             for (size_t ci = 0; ci < p->cams.size(); ci++)
-                memcpy(p->cams[ci].params, &cand_slab[ci * CAM_STRIDE], sizeof(double) * p->cams[ci].K);
+                memcpy(p->cams[ci].params, cs + ci * CAM_STRIDE, sizeof(double) * p->cams[ci].K);
             for (Tr &t : p->trs)
-                if (t.is_global) memcpy(t.host.data(), &cand_slab[glob0 + (size_t)t.glob_slot * 6], 48);
-            memcpy(A.data(), p->h_red + red_off_A(Ks), sizeof(double) * Ks * Ks);
-            memcpy(ga.data(), p->h_red + red_off_g(Ks), sizeof(double) * Ks);
+                if (t.is_global) memcpy(t.host.data(), cs + glob0 + (size_t)t.glob_slot * 6, 48);
             cost = new_cost;
             sum->num_successful++;
             radius = radius / std::fmax(1.0 / 3.0, 1.0 - std::pow(2.0 * rho - 1.0, 3.0));
@@ -1145,17 +1191,13 @@ int vg_problem_solve(vg_problem *p, const vg_solve_options *opt, vg_solve_summar
             radius /= decrease_factor; decrease_factor *= 2.0;
         }
     }
-    // the non-current set keeps stale candidates: bring the shared slab of both sets in line
-    fill_slab(p, p->h_slab.data());
-    for (int s_ = 0; s_ < 2; s_++)
-        VG_CUDA(cudaMemcpyAsync(p->d_slab[s_], p->h_slab.data(), p->slab_doubles * sizeof(double), cudaMemcpyHostToDevice, p->stream));
-    for (Tr &t : p->trs)
-        if (!t.is_global)
-            VG_CUDA(cudaMemcpyAsync(t.host.data(), t.dev[p->cur], sizeof(double) * 6 * t.n, cudaMemcpyDeviceToHost, p->stream));
-    VG_CUDA(cudaStreamSynchronize(p->stream));
+    // Nothing to copy back: the last fetch synchronised the stream; the candidate set's slab and poses are rewritten
+    // by every step before they are used; sequence poses stay on the device until vg_problem_get_transform asks for
+    // them (or the problem's structure changes: free_prepared).
     sum->iterations = iter;
     sum->final_cost = cost;
     sum->seconds_total = now_s() - t_start;
+    if (trace) fprintf(stderr, "[vg lm] epilogue: %.1f us\n", (now_s() - t_iter) * 1e6);
     sum->seconds_evaluate = p->eval_ms * 1e-3;
     sum->num_evaluations = p->n_eval;
     return VG_OK;

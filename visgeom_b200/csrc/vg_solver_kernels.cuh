@@ -71,6 +71,23 @@ __host__ __device__ inline int red_off_gmax(int Ks) { return red_off_fail(Ks) + 
 __host__ __device__ inline int red_segS_size(int Ks, int nranks) { return Ks * Ks + Ks + 1 + nranks; }
 __host__ __device__ inline int red_size(int Ks, int nranks) { return red_segE_size(Ks) + red_segS_size(Ks, nranks); }
 
+// after the two segments, per parameter set: what reduced_solve leaves for the host about the step TOWARDS this set
+//   [max |projected gradient| at the current point, failed pose factorisations, reduced Cholesky ok, g_a . delta_a,
+//    delta_a^T A delta_a, |step|^2 and |x|^2 over the shared parameters, spare] then a copy of the candidate slab
+constexpr int SOLVE_OUT = 8;
+
+// what the reduced solve reads and leaves (reduced_solve_kernel, or pose_factor's fused tail on one rank)
+struct SolveArgs {
+    int slab_n, nranks;
+    const double *red_cur;          // the current set's reduction buffer: A, g_a (segment E), S_red, v_red, max |g| (segment S)
+    double *red_cand;               // the candidate set's buffer: scalars + candidate slab go after its two segments
+    const double *slab_cur;
+    double *slab_cand, *delta_a;
+    const int *sh_off;              // slab position of shared parameter j
+    const double *sh_lo, *sh_hi;    // its box bounds
+    double *scale_a;                // Jacobi scaling of the shared block (written when lm.init_scale)
+};
+
 struct SolverLaunch {
     cudaStream_t stream;
     unsigned long long *launches;
@@ -86,7 +103,8 @@ cudaError_t launch_pose_schur(const DatasetDesc *d_desc, int n_pose, int Ks,
                               const int *pose_start, const int *contrib_ds, const int *contrib_img,
                               double *scale, LmConsts lm, double *ws, double *partial, size_t partial_doubles,
                               double *red, int *fail_flag, int rank, int nranks, SolverLaunch sl,
-                              const unsigned char *chain_mask = nullptr, int n_seg = 0);
+                              const unsigned char *chain_mask = nullptr, int n_seg = 0,
+                              const SolveArgs *fused = nullptr, unsigned int *ticket = nullptr);
 
 size_t pose_scratch(int n_pose, int Ks, int n_seg = 0);                  // doubles
 int pose_factor_blocks(int n_pose);                                      // blocks of pose_factor (slots of max |g|)
@@ -99,7 +117,10 @@ cudaError_t launch_pose_backsub(int n_pose, int Ks, const double *delta_a,
                                 const double *const *seq_cur, double *const *seq_cand,
                                 const int *pose_seq, const int *pose_local,
                                 const double *ws, double *partial, size_t partial_doubles, double *red,
-                                SolverLaunch sl, const unsigned char *chain_mask = nullptr, double *chain_w = nullptr);
+                                SolverLaunch sl, const unsigned char *chain_mask = nullptr, double *chain_w = nullptr,
+                                unsigned int *ticket = nullptr);   // ticket: the last block also sums the rows into red
+// reduced system of the current set -> delta_a, candidate slab, host scalars (red_cand tail)
+cudaError_t launch_reduced_solve(int Ks, const SolveArgs &sa, LmConsts lm, SolverLaunch sl);
 cudaError_t launch_finalize_backsub(int Ks, int n_rows, const double *partial, double *red, SolverLaunch sl);
 
 }  // namespace vg
