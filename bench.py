@@ -263,10 +263,39 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    state = {"nccl": os.environ.get("VG_BENCH_NCCL", "0") == "1"}
+
     def attach_allreduce(Pm):
-        """N > 1: the engine's cross-rank sum of the reduced normal equations goes through torch.distributed (NCCL)."""
-        if world == 1:
+        """N > 1: the cross-rank sum of the reduced normal equations.  Default: the engine's own exchange over peer
+        memory inside the kernel that assembles them (NVLink / NVSwitch; torch.distributed only carries the CUDA IPC
+        handles at set-up).  VG_BENCH_NCCL=1: an NCCL all-reduce per evaluation through a callback instead."""
+        if world == 1 or os.environ.get("VG_BENCH_NOCOLL") == "1":     # (diagnosis: ranks left unconnected)
             return
+        if not state["nccl"]:
+            ok = 1
+            try:
+                mine = torch.frombuffer(bytearray(Pm.peer_export()), dtype=torch.uint8).to(dev)
+            except vg.VisgeomError as e:
+                print(f"[bench] rank {rank}: peer_export failed ({e})", file=sys.stderr)
+                mine, ok = torch.zeros(64, dtype=torch.uint8, device=dev), 0
+            every = torch.empty(world * 64, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(every, mine)
+            if ok:
+                try:
+                    Pm.peer_connect(rank, world, bytes(every.cpu().numpy().tobytes()))
+                except vg.VisgeomError as e:
+                    print(f"[bench] rank {rank}: peer_connect failed ({e})", file=sys.stderr)
+                    ok = 0
+            flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 1:
+                return
+            # some rank could not map its peers (no P2P / IPC): every rank falls back to NCCL, for every problem
+            if rank == 0:
+                print("[bench] peer-memory exchange unavailable, using the NCCL all-reduce callback", file=sys.stderr)
+            state["nccl"] = True
+            if ok:
+                raise SystemExit("bench.py: inconsistent peer set-up")   # connected here but not elsewhere: cannot mix
         views, streams = {}, {}
 
         def allreduce(buf, count, strm):
@@ -453,8 +482,11 @@ def run_ours(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"monocular {args.model}, {world * n_img} synthetic images x {P} corners (9x6 board); "
                                    "step = fused residual + analytic Jacobian (Ceres layout, written to HBM) + per-image "
-                                   "J^T J/J^T r + shared-block reduction" + (" + NCCL all-reduce" if world > 1 else ""),
+                                   "J^T J/J^T r + shared-block reduction" +
+                                   ("" if world == 1 else " + NCCL all-reduce of the shared block" if state["nccl"] else
+                                    " + in-kernel exchange of the shared block over NVLink peer memory"),
                        "images_per_gpu": n_img, "corners_per_image": P, "model": None,
+                       "collective": None if world == 1 else ("nccl" if state["nccl"] else "peer-memory, fused into the evaluation kernel"),
                        "l2": f"{args.sets} rotating buffer sets, {args.sets * out_bytes / 1e6:.0f} MB of outputs in flight (> 126 MB L2)",
                        "cost_check": cost},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

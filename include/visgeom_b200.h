@@ -215,6 +215,16 @@ int vg_problem_add_dataset(vg_problem *p, int camera, int P, const double *board
 typedef int (*vg_allreduce_fn)(void *ctx, double *buf, int count, void *stream);
 int vg_problem_set_allreduce(vg_problem *p, vg_allreduce_fn fn, void *ctx, int rank, int nranks);
 
+/* The same sum over peer memory instead (GPUs of one NVLink / NVSwitch domain, one process per GPU): the kernel that
+ * assembles the reduced normal equations also exchanges them with the other ranks -- peer stores into every rank's
+ * inbox, a flag, a sum in rank order (bit-identical on every rank) -- with no collective launch and no host in the
+ * loop.  Each rank exports the CUDA IPC handle of its inbox (64 bytes), the application gathers the handles of all
+ * ranks (any transport) and hands the whole array to every rank.  Call before the first evaluation; every rank must
+ * then issue the same sequence of evaluations / solves on this problem. */
+#define VG_IPC_HANDLE_BYTES 64
+int vg_problem_peer_export(vg_problem *p, void *ipc_handle_out /* VG_IPC_HANDLE_BYTES */);
+int vg_problem_peer_connect(vg_problem *p, int rank, int nranks, const void *ipc_handles /* nranks x VG_IPC_HANDLE_BYTES */);
+
 /* When enabled, every evaluation also materialises r and all Jacobian blocks in
  * device memory in the Ceres layout (what GenericProjectionJac::Evaluate hands to
  * Ceres); the LM loop itself only needs the per-image normal-equation blocks and

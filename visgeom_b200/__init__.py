@@ -82,6 +82,8 @@ def lib() -> C.CDLL:
         L.vg_eval_transformation_prior.argtypes = [C.c_int, c_dp, c_dp, c_dp, c_dp, c_dp]
         L.vg_eval_odometry_prior.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, c_dp, c_dp, c_dp, c_dp,
                                              c_dp, c_dp, c_dp]
+        L.vg_problem_peer_export.argtypes = [C.c_void_p, C.c_void_p]
+        L.vg_problem_peer_connect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.vg_problem_set_allreduce.argtypes = [C.c_void_p, ALLREDUCE_FN, C.c_void_p, C.c_int, C.c_int]
         L.vg_problem_materialize_jacobians.argtypes = [C.c_void_p, C.c_int]
         L.vg_problem_device_buffer.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p),
@@ -275,6 +277,18 @@ class Problem:
 
     def set_pose_constant(self, transform, index, constant=True):
         _check(self.L.vg_problem_set_pose_constant(self.h, transform, index, int(constant)))
+
+    def peer_export(self) -> bytes:
+        """CUDA IPC handle (64 bytes) of this rank's inbox for the peer-memory exchange."""
+        buf = (C.c_ubyte * 64)()
+        _check(self.L.vg_problem_peer_export(self.h, buf))
+        return bytes(buf)
+
+    def peer_connect(self, rank, nranks, handles: bytes):
+        """handles: the nranks x 64 bytes every rank's peer_export() returned, in rank order."""
+        assert len(handles) == 64 * nranks
+        buf = (C.c_ubyte * len(handles)).from_buffer_copy(handles)
+        _check(self.L.vg_problem_peer_connect(self.h, rank, nranks, buf))
 
     def set_allreduce(self, fn, rank, nranks):
         """fn(buf_ptr:int, count:int, stream:int) -> None sums count doubles in place across ranks."""

@@ -3,6 +3,8 @@
 
 #include <cuda_runtime.h>
 
+#include "vg_peer.cuh"
+
 namespace vg {
 
 constexpr int MAX_CHAIN = 5;
@@ -45,6 +47,10 @@ struct EvalArgs {
     // corrector scales residuals and Jacobians by sqrt(rho'): the packed block leaves as rho' [J r]^T [J r] with
     // rho(s) in its last entry; r / J outputs stay raw (what Evaluate returns).
     double loss_b;
+    // Multi-GPU (vg_peer.cuh): the CTA that assembles the reduced system also sums its first peer_count doubles
+    // across the ranks over peer memory, in the same launch.  peer.n <= 1: nothing to exchange.
+    PeerCtx peer;
+    int peer_count;
     int n_img;
     int P;
 };

@@ -391,6 +391,8 @@ __device__ __forceinline__ void fused_reduce(const EvalArgs &args)
         args.red[f.dst0] = v;
         if (f.dst1 >= 0) args.red[f.dst1] = v;
     }
+    // several GPUs: the same CTA exchanges the reduced system with its peers over NVLink (vg_peer.cuh)
+    if (args.peer.n > 1) peer_allreduce(args.red, args.peer_count, args.peer);
 }
 
 // ---- the kernel -------------------------------------------------------------------

@@ -134,6 +134,13 @@ struct vg_problem {
     int red_doubles = 0;
     // shared parameter j: its slab position and box bounds; Jacobi scaling of the shared block
     int *d_sh_off = nullptr;
+    // peer-memory exchange (vg_peer.cuh): own inbox, every rank's inbox as mapped here, exchanges done so far
+    unsigned long long *d_inbox = nullptr;
+    unsigned long long **d_peer_ptrs = nullptr;
+    std::vector<void *> peer_opened;
+    bool peers = false, exchanged_in_kernel = false;
+    unsigned long long epoch = 0;
+    PeerCtx next_peer_ctx() { return PeerCtx{d_peer_ptrs, rank, nranks, ++epoch}; }
     unsigned int *d_solver_tickets = nullptr;   // "last block done" counters of pose_factor / pose_backsub
     double *d_sh_lo = nullptr, *d_sh_hi = nullptr, *d_scale_a = nullptr;
     std::vector<int> h_sh_off;
@@ -524,6 +531,11 @@ int evaluate_set(vg_problem *p, int s, bool timed)
         if (k == p->last_ds) {      // the shared-block reduction -> segment E is the tail of this launch
             a.fin_outs = p->d_fin_out; a.fin_srcs = p->d_fin_src; a.n_fin_out = p->n_fin_out;
             a.fin_base = p->d_ds_sum; a.red = p->d_redbuf[s];
+            if (p->peers && p->nranks > 1 && p->n_tp + p->n_op == 0) {
+                a.peer = p->next_peer_ctx();
+                a.peer_count = red_segE_size(p->Ks);
+                p->exchanged_in_kernel = true;
+            }
         }
         a.n_img = d.n_img; a.P = d.P;
         a.loss_b = d.loss_a * d.loss_a;
@@ -545,6 +557,16 @@ int evaluate_set(vg_problem *p, int s, bool timed)
 // sum a segment of a set's reduction buffer across ranks (if any)
 int exchange_segment(vg_problem *p, int s, int off, int count)
 {
+    if (count > 0 && p->peers && p->nranks > 1) {
+        // peer memory: segment E has usually been exchanged by the evaluation kernel itself
+        const bool done = off == 0 && p->exchanged_in_kernel;
+        p->exchanged_in_kernel = false;
+        if (done) return VG_OK;
+        SolverLaunch sl{p->stream, &launch_counter()};
+        cudaError_t e = launch_peer_exchange(p->d_redbuf[s] + off, count, p->next_peer_ctx(), sl);
+        if (e != cudaSuccess) return fail_cuda(e, "peer exchange");
+        return VG_OK;
+    }
     if (count > 0 && p->allreduce && p->nranks > 1) {
         if (p->allreduce(p->allreduce_ctx, p->d_redbuf[s] + off, count, p->stream) != 0)
             return fail(VG_ERR_CUDA, "all-reduce callback failed");
@@ -638,6 +660,8 @@ void vg_problem_destroy(vg_problem *p)
         cudaFree(d.d_r); cudaFree(d.d_Ja);
         for (int e = 0; e < VG_MAX_CHAIN; e++) cudaFree(d.d_Je[e]);
     }
+    for (void *q : p->peer_opened) cudaIpcCloseMemHandle(q);
+    cudaFree(p->d_peer_ptrs); cudaFree(p->d_inbox);
     cudaEventDestroy(p->ev0); cudaEventDestroy(p->ev1);
     cudaStreamDestroy(p->own_stream);
     delete p;
@@ -811,11 +835,51 @@ int vg_problem_set_pose_constant(vg_problem *p, int transform, int index, int co
     return VG_OK;
 }
 
+int vg_problem_peer_export(vg_problem *p, void *ipc_handle_out)
+{
+    if (!p || !ipc_handle_out) return fail(VG_ERR_INVALID, "null argument");
+    VG_CUDA(cudaSetDevice(p->device));
+    if (!p->d_inbox) {
+        VG_CUDA(cudaMalloc(&p->d_inbox, peer_inbox_bytes()));
+        VG_CUDA(cudaMemset(p->d_inbox, 0, peer_inbox_bytes()));
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == VG_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    VG_CUDA(cudaIpcGetMemHandle(&h, p->d_inbox));
+    memcpy(ipc_handle_out, &h, sizeof h);
+    return VG_OK;
+}
+
+int vg_problem_peer_connect(vg_problem *p, int rank, int nranks, const void *ipc_handles)
+{
+    if (!p || !ipc_handles || nranks < 1 || nranks > PEER_MAX_RANKS || rank < 0 || rank >= nranks)
+        return fail(VG_ERR_INVALID, "vg_problem_peer_connect: bad arguments");
+    if (!p->d_inbox) return fail(VG_ERR_INVALID, "vg_problem_peer_connect: call vg_problem_peer_export first");
+    if (p->peers) return fail(VG_ERR_INVALID, "vg_problem_peer_connect: already connected");
+    VG_CUDA(cudaSetDevice(p->device));
+    free_prepared(p);
+    std::vector<unsigned long long *> ptrs(nranks, nullptr);
+    for (int r = 0; r < nranks; r++) {
+        if (r == rank) { ptrs[r] = p->d_inbox; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const char *>(ipc_handles) + (size_t)r * sizeof h, sizeof h);
+        void *q = nullptr;
+        VG_CUDA(cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess));
+        p->peer_opened.push_back(q);
+        ptrs[r] = static_cast<unsigned long long *>(q);
+    }
+    VG_CUDA(cudaMalloc(&p->d_peer_ptrs, sizeof(unsigned long long *) * nranks));
+    VG_CUDA(cudaMemcpy(p->d_peer_ptrs, ptrs.data(), sizeof(unsigned long long *) * nranks, cudaMemcpyHostToDevice));
+    p->rank = rank; p->nranks = nranks; p->peers = true; p->epoch = 0;
+    return VG_OK;
+}
+
 int vg_problem_set_allreduce(vg_problem *p, vg_allreduce_fn fn, void *ctx, int rank, int nranks)
 {
     if (!p || nranks < 1 || rank < 0 || rank >= nranks) return fail(VG_ERR_INVALID, "vg_problem_set_allreduce: bad arguments");
     cudaSetDevice(p->device);
     free_prepared(p);
+    if (p->peers) return fail(VG_ERR_INVALID, "vg_problem_set_allreduce: the problem exchanges over peer memory already");
     p->allreduce = fn; p->allreduce_ctx = ctx; p->rank = rank; p->nranks = fn ? nranks : 1;
     if (!fn) p->rank = 0;
     return VG_OK;
@@ -849,12 +913,7 @@ int vg_problem_evaluate_async(vg_problem *p)
     VG_CUDA(cudaSetDevice(p->device));
     rc = evaluate_set(p, p->cur, false);
     if (rc) return rc;
-    if (p->allreduce && p->nranks > 1) {
-        const int Ks = p->Ks;
-        if (p->allreduce(p->allreduce_ctx, p->d_redbuf[p->cur], red_off_model(Ks), p->stream) != 0)
-            return fail(VG_ERR_CUDA, "all-reduce callback failed");
-    }
-    return VG_OK;
+    return exchange_segment(p, p->cur, 0, red_segE_size(p->Ks));
 }
 
 int vg_problem_fetch_reduced(vg_problem *p, double *cost, double *reduced)

@@ -514,6 +514,12 @@ pose_backsub_kernel(int n_pose, int Ks, const double *delta_a, const double *con
 
 
 
+// one block: a segment of the reduction buffer summed across the ranks over peer memory (vg_peer.cuh)
+__global__ void __launch_bounds__(256) peer_exchange_kernel(double *buf, int count, PeerCtx pc)
+{
+    peer_allreduce(buf, count, pc);
+}
+
 }  // namespace
 
 // Tables of the shared-block reduction (fused into the evaluation kernel): offsets of each dataset's sums
@@ -636,6 +642,14 @@ cudaError_t launch_reduced_solve(int Ks, const SolveArgs &sa, LmConsts lm, Solve
     const size_t smem = sizeof(double) * (2 * (size_t)Ks * Ks + 9 * (size_t)Ks + 1);
     if (smem > 40 * 1024) return cudaErrorInvalidValue;       // Ks <= 48
     reduced_solve_kernel<<<1, SOLVE_THREADS, smem, sl.stream>>>(Ks, sa, lm);
+    if (sl.launches) (*sl.launches)++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_peer_exchange(double *buf, int count, const PeerCtx &pc, SolverLaunch sl)
+{
+    if (count > PEER_SLOT_DOUBLES) return cudaErrorInvalidValue;
+    peer_exchange_kernel<<<1, 256, 0, sl.stream>>>(buf, count, pc);
     if (sl.launches) (*sl.launches)++;
     return cudaGetLastError();
 }

@@ -121,6 +121,8 @@ cudaError_t launch_pose_backsub(int n_pose, int Ks, const double *delta_a,
                                 unsigned int *ticket = nullptr);   // ticket: the last block also sums the rows into red
 // reduced system of the current set -> delta_a, candidate slab, host scalars (red_cand tail)
 cudaError_t launch_reduced_solve(int Ks, const SolveArgs &sa, LmConsts lm, SolverLaunch sl);
+// buf[0..count) <- its sum over the ranks, through the peers' inboxes (one block; vg_peer.cuh)
+cudaError_t launch_peer_exchange(double *buf, int count, const PeerCtx &pc, SolverLaunch sl);
 cudaError_t launch_finalize_backsub(int Ks, int n_rows, const double *partial, double *red, SolverLaunch sl);
 
 }  // namespace vg
