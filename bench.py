@@ -484,9 +484,10 @@ def run_ours(args):
                                    "step = fused residual + analytic Jacobian (Ceres layout, written to HBM) + per-image "
                                    "J^T J/J^T r + shared-block reduction" +
                                    ("" if world == 1 else " + NCCL all-reduce of the shared block" if state["nccl"] else
-                                    " + in-kernel exchange of the shared block over NVLink peer memory"),
+                                    " + exchange of the shared block over NVLink peer memory (posted by the kernel's tail, summed by the "
+                                    "head of the problem's next launch)"),
                        "images_per_gpu": n_img, "corners_per_image": P, "model": None,
-                       "collective": None if world == 1 else ("nccl" if state["nccl"] else "peer-memory, fused into the evaluation kernel"),
+                       "collective": None if world == 1 else ("nccl" if state["nccl"] else "peer-memory, fused into the evaluation kernel (post in the tail, collect in the next launch's head)"),
                        "l2": f"{args.sets} rotating buffer sets, {args.sets * out_bytes / 1e6:.0f} MB of outputs in flight (> 126 MB L2)",
                        "cost_check": cost},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

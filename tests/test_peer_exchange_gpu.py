@@ -47,6 +47,16 @@ def main():
       ca, ra = A.evaluate(want_reduced=True)
       assert abs(cs - ca) <= 1e-12 * ca, (cs, ca)
       assert np.abs(rs - ra).max() <= 1e-11 * np.abs(ra).max()
+  # deferred exchange: evaluate_async only posts, the next launch (or the fetch) forms the sum
+  for burst in (1, 2, 5):
+      for _ in range(burst):
+          S.evaluate_async()
+      cs, rs = S.fetch_reduced()
+      assert abs(cs - ca) <= 1e-12 * ca, (burst, cs, ca)
+      assert np.abs(rs - ra).max() <= 1e-11 * np.abs(ra).max()
+  S.evaluate_async()                         # posted, then a synchronous evaluation collects it first
+  cs, rs = S.evaluate(want_reduced=True)
+  assert abs(cs - ca) <= 1e-12 * ca and np.isfinite(rs).all()
   o = S.default_options(); o.max_num_iterations = 12
   ss, sa = S.solve(o), A.solve(o)
   # (the iteration counts may differ by one at the very end: the last trial steps change the cost by rounding noise)

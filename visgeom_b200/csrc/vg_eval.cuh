@@ -49,8 +49,15 @@ struct EvalArgs {
     double loss_b;
     // Multi-GPU (vg_peer.cuh): the CTA that assembles the reduced system also sums its first peer_count doubles
     // across the ranks over peer memory, in the same launch.  peer.n <= 1: nothing to exchange.
+    // peer_deferred: the tail only posts this rank's block; the sum is formed later -- by the head of this problem's
+    // next launch (collect / collect_buf: the exchange it still owes, and the buffer its sum belongs in) or by a
+    // one-block kernel when something needs it sooner.  collect_done: device word, the last exchange collected.
     PeerCtx peer;
     int peer_count;
+    int peer_deferred;
+    PeerCtx collect;
+    double *collect_buf;
+    unsigned long long *collect_done;
     int n_img;
     int P;
 };

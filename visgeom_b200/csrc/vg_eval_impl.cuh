@@ -378,6 +378,17 @@ __device__ __forceinline__ void fused_reduce(const EvalArgs &args)
     for (int e = tid; e < NE; e += blockDim.x) args.ds_sum[e] = sum_rows_in_order(args.lvl1 + e, NE, 0, ngrp);
     if (tid == 0) args.tickets[0] = 0;
     if (!args.red) return;
+    if (args.peer.n > 1 && args.peer_deferred && args.collect.n > 1) {
+        // the previous exchange must be collected (head of this launch) before its buffer is reused and before the
+        // next one is posted
+        if (tid == 0) {
+            unsigned long long seen;
+            do {
+                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(args.collect_done) : "memory");
+            } while (seen < args.collect.epoch);
+        }
+        __syncthreads();
+    }
     __threadfence();
     __syncthreads();                       // this dataset's sums are complete; the earlier datasets' launches are
     for (int o = tid; o < args.n_fin_out; o += blockDim.x) {
@@ -392,7 +403,10 @@ __device__ __forceinline__ void fused_reduce(const EvalArgs &args)
         if (f.dst1 >= 0) args.red[f.dst1] = v;
     }
     // several GPUs: the same CTA exchanges the reduced system with its peers over NVLink (vg_peer.cuh)
-    if (args.peer.n > 1) peer_allreduce(args.red, args.peer_count, args.peer);
+    if (args.peer.n > 1) {
+        if (args.peer_deferred) peer_post(args.red, args.peer_count, args.peer);
+        else peer_allreduce(args.red, args.peer_count, args.peer);
+    }
 }
 
 // ---- the kernel -------------------------------------------------------------------
@@ -434,6 +448,16 @@ reproj_eval_kernel(const EvalArgs args, const int G, const int PCG)
     // the grids this launch depends on have completed and flushed.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    // several GPUs, deferred exchange: the first CTA forms the sum of this problem's previous exchange, which has been
+    // crossing NVLink while the launches in between ran (vg_peer.cuh)
+    if (args.collect.n > 1 && blockIdx.x == 0) {
+        peer_collect(args.collect_buf, args.peer_count, args.collect);
+        __threadfence();
+        __syncthreads();
+        if (tid == 0)
+            asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(args.collect_done), "l"(args.collect.epoch) : "memory");
+    }
 
     double intr[K];
 #pragma unroll

@@ -10,8 +10,11 @@
 //   1. the CTA stores its block into slot[epoch & 1][my rank] of EVERY rank's inbox (peer stores over NVLink);
 //   2. thread i polls word pair i of every rank's slot in its OWN inbox until the tags match, and adds the values
 //      up in rank order -- every rank forms the same sum in the same order, bit-identical across ranks.
-// Two slot parities are enough: a rank starts exchange e + 2 only after it has finished e + 1, which needed every
-// peer's words of e + 1, and a peer writes those only after it has consumed exchange e.
+// Two slot parities are enough: a rank posts exchange e + 2 only after it has collected e + 1, which needed every
+// peer's words of e + 1, and a peer posts those only after it has collected exchange e.  The two steps need not
+// sit in the same kernel: a launch may post exchange e in its tail and leave the collection to the head of the
+// next launch (or to a one-block kernel), so that the NVLink round trip hides behind the next launch's work --
+// the rule above is all that has to hold (collect e - 1 before posting e).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -36,9 +39,13 @@ __device__ __forceinline__ unsigned long long *peer_slot(unsigned long long *inb
     return inbox + ((size_t)parity * PEER_MAX_RANKS + r) * 2 * PEER_SLOT_DOUBLES;
 }
 
-// buf[0..count) <- sum over ranks; called by every thread of ONE CTA, count <= PEER_SLOT_DOUBLES.
-// buf may have been written by this CTA just before (the barrier below orders it).
-__device__ __forceinline__ void peer_allreduce(double *buf, int count, const PeerCtx &pc)
+// A poll gives up after PEER_SPIN_LIMIT reads (seconds of waiting: a peer that never arrives -- a rank that died or
+// issued a different sequence of exchanges) and poisons the sum with NaN instead of hanging the GPU.
+constexpr long long PEER_SPIN_LIMIT = 1ll << 31;
+
+// step 1: this rank's block into every rank's inbox.  Called by every thread of ONE CTA, count <= PEER_SLOT_DOUBLES;
+// buf may have been written by this CTA just before (the barrier orders it).
+__device__ __forceinline__ void peer_post(const double *buf, int count, const PeerCtx &pc)
 {
     const int tid = threadIdx.x, nt = blockDim.x, parity = (int)(pc.epoch & 1ull);
     const unsigned long long tag = (pc.epoch & 0xffffffffull) << 32;
@@ -52,22 +59,40 @@ __device__ __forceinline__ void peer_allreduce(double *buf, int count, const Pee
             asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(dst + 1), "l"(w1) : "memory");
         }
     }
+}
+
+__device__ __forceinline__ unsigned long long peer_poll(const unsigned long long *src, unsigned long long tag)
+{
+    unsigned long long a = 0;
+    for (long long it = 0; it < PEER_SPIN_LIMIT; it++) {
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(a) : "l"(src) : "memory");
+        if ((a & 0xffffffff00000000ull) == tag) return a & 0xffffffffull;
+    }
+    return ~0ull;           // gave up
+}
+
+// step 2: buf[0..count) <- the sum over the ranks' blocks of exchange pc.epoch, in rank order
+__device__ __forceinline__ void peer_collect(double *buf, int count, const PeerCtx &pc)
+{
+    const int tid = threadIdx.x, nt = blockDim.x, parity = (int)(pc.epoch & 1ull);
+    const unsigned long long tag = (pc.epoch & 0xffffffffull) << 32;
     unsigned long long *mine = pc.inbox[pc.rank];
     for (int i = tid; i < count; i += nt) {
         double s = 0.0;
         for (int r = 0; r < pc.n; r++) {
             const unsigned long long *src = peer_slot(mine, parity, r) + 2 * i;
-            unsigned long long a, b;
-            do {
-                asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(a) : "l"(src) : "memory");
-            } while ((a & 0xffffffff00000000ull) != tag);
-            do {
-                asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(b) : "l"(src + 1) : "memory");
-            } while ((b & 0xffffffff00000000ull) != tag);
-            s += __longlong_as_double((long long)((a & 0xffffffffull) | (b << 32)));
+            const unsigned long long a = peer_poll(src, tag), b = peer_poll(src + 1, tag);
+            s += (a == ~0ull || b == ~0ull) ? __longlong_as_double(0x7ff8000000000000ll)
+                                            : __longlong_as_double((long long)(a | (b << 32)));
         }
         buf[i] = s;
     }
+}
+
+__device__ __forceinline__ void peer_allreduce(double *buf, int count, const PeerCtx &pc)
+{
+    peer_post(buf, count, pc);
+    peer_collect(buf, count, pc);
 }
 
 }  // namespace vg

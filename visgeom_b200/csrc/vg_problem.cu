@@ -140,6 +140,11 @@ struct vg_problem {
     std::vector<void *> peer_opened;
     bool peers = false, exchanged_in_kernel = false;
     unsigned long long epoch = 0;
+    // deferred exchange (vg_problem_evaluate_async): posted by an evaluation kernel, not collected yet
+    bool pending = false;
+    unsigned long long pending_epoch = 0;
+    int pending_set = 0;
+    unsigned long long *d_collect_done = nullptr;
     PeerCtx next_peer_ctx() { return PeerCtx{d_peer_ptrs, rank, nranks, ++epoch}; }
     unsigned int *d_solver_tickets = nullptr;   // "last block done" counters of pose_factor / pose_backsub
     double *d_sh_lo = nullptr, *d_sh_hi = nullptr, *d_scale_a = nullptr;
@@ -209,6 +214,7 @@ void free_prepared(vg_problem *p)
     F(p->d_extra_start); F(p->d_extra_kind); F(p->d_extra_rec); F(p->d_prev_edge); F(p->d_mask); F(p->d_fixed);
     F(p->d_chain_off); F(p->d_chain_w);
     p->n_tp = p->n_op = p->n_tp_shared = p->n_seg = 0;
+    p->pending = false;                 // an exchange posted but never asked for: its words are simply overwritten
     if (p->h_red) { cudaFreeHost(p->h_red); p->h_red = nullptr; }
     if (p->h_up) { cudaFreeHost(p->h_up); p->h_up = nullptr; }
     for (auto &d : p->dss)
@@ -504,8 +510,27 @@ int prepare(vg_problem *p)
 
 // fused residual + Jacobian + normal-equation kernels of every dataset at parameter set s,
 // then the shared-block reduction -> segment E (A, g_a, cost) of that set's reduction buffer
-int evaluate_set(vg_problem *p, int s, bool timed)
+// the sum of an exchange that an evaluation kernel posted and nothing has collected yet
+int flush_pending(vg_problem *p)
 {
+    if (!p->pending) return VG_OK;
+    p->pending = false;
+    SolverLaunch sl{p->stream, &launch_counter()};
+    const PeerCtx pc{p->d_peer_ptrs, p->rank, p->nranks, p->pending_epoch};
+    cudaError_t e = launch_peer_collect(p->d_redbuf[p->pending_set], red_segE_size(p->Ks), pc, p->d_collect_done, sl);
+    if (e != cudaSuccess) return fail_cuda(e, "peer collect");
+    return VG_OK;
+}
+
+// deferred: several GPUs over peer memory -- the kernel only posts its block, the sum is formed by this problem's
+// next launch (or by flush_pending when something needs it sooner), so the NVLink round trip is off the critical path
+int evaluate_set(vg_problem *p, int s, bool timed, bool deferred = false)
+{
+    deferred = deferred && p->peers && p->nranks > 1 && p->n_tp + p->n_op == 0 && p->last_ds >= 0;
+    if (!deferred) {
+        int rc = flush_pending(p);
+        if (rc) return rc;
+    }
     if (timed) VG_CUDA(cudaEventRecord(p->ev0, p->stream));
     for (Ds &d : p->dss) {
         EvalArgs a;
@@ -532,9 +557,20 @@ int evaluate_set(vg_problem *p, int s, bool timed)
             a.fin_outs = p->d_fin_out; a.fin_srcs = p->d_fin_src; a.n_fin_out = p->n_fin_out;
             a.fin_base = p->d_ds_sum; a.red = p->d_redbuf[s];
             if (p->peers && p->nranks > 1 && p->n_tp + p->n_op == 0) {
-                a.peer = p->next_peer_ctx();
                 a.peer_count = red_segE_size(p->Ks);
-                p->exchanged_in_kernel = true;
+                if (deferred) {
+                    a.peer_deferred = 1;
+                    if (p->pending) {
+                        a.collect = PeerCtx{p->d_peer_ptrs, p->rank, p->nranks, p->pending_epoch};
+                        a.collect_buf = p->d_redbuf[p->pending_set];
+                        a.collect_done = p->d_collect_done;
+                    }
+                    a.peer = p->next_peer_ctx();
+                    p->pending = true; p->pending_epoch = a.peer.epoch; p->pending_set = s;
+                } else {
+                    a.peer = p->next_peer_ctx();
+                    p->exchanged_in_kernel = true;
+                }
             }
         }
         a.n_img = d.n_img; a.P = d.P;
@@ -558,6 +594,8 @@ int evaluate_set(vg_problem *p, int s, bool timed)
 int exchange_segment(vg_problem *p, int s, int off, int count)
 {
     if (count > 0 && p->peers && p->nranks > 1) {
+        int rc = flush_pending(p);
+        if (rc) return rc;
         // peer memory: segment E has usually been exchanged by the evaluation kernel itself
         const bool done = off == 0 && p->exchanged_in_kernel;
         p->exchanged_in_kernel = false;
@@ -661,7 +699,7 @@ void vg_problem_destroy(vg_problem *p)
         for (int e = 0; e < VG_MAX_CHAIN; e++) cudaFree(d.d_Je[e]);
     }
     for (void *q : p->peer_opened) cudaIpcCloseMemHandle(q);
-    cudaFree(p->d_peer_ptrs); cudaFree(p->d_inbox);
+    cudaFree(p->d_peer_ptrs); cudaFree(p->d_inbox); cudaFree(p->d_collect_done);
     cudaEventDestroy(p->ev0); cudaEventDestroy(p->ev1);
     cudaStreamDestroy(p->own_stream);
     delete p;
@@ -868,6 +906,8 @@ int vg_problem_peer_connect(vg_problem *p, int rank, int nranks, const void *ipc
         p->peer_opened.push_back(q);
         ptrs[r] = static_cast<unsigned long long *>(q);
     }
+    VG_CUDA(cudaMalloc(&p->d_collect_done, sizeof(unsigned long long)));
+    VG_CUDA(cudaMemset(p->d_collect_done, 0, sizeof(unsigned long long)));
     VG_CUDA(cudaMalloc(&p->d_peer_ptrs, sizeof(unsigned long long *) * nranks));
     VG_CUDA(cudaMemcpy(p->d_peer_ptrs, ptrs.data(), sizeof(unsigned long long *) * nranks, cudaMemcpyHostToDevice));
     p->rank = rank; p->nranks = nranks; p->peers = true; p->epoch = 0;
@@ -911,8 +951,10 @@ int vg_problem_evaluate_async(vg_problem *p)
     int rc = prepare(p);
     if (rc) return rc;
     VG_CUDA(cudaSetDevice(p->device));
-    rc = evaluate_set(p, p->cur, false);
+    const bool deferred = p->peers && p->nranks > 1 && p->n_tp + p->n_op == 0 && p->last_ds >= 0;
+    rc = evaluate_set(p, p->cur, false, deferred);
     if (rc) return rc;
+    if (deferred) return VG_OK;          // posted; vg_problem_fetch_reduced (or the next evaluation) forms the sum
     return exchange_segment(p, p->cur, 0, red_segE_size(p->Ks));
 }
 
@@ -920,6 +962,10 @@ int vg_problem_fetch_reduced(vg_problem *p, double *cost, double *reduced)
 {
     if (!p || !p->prepared) return fail(VG_ERR_INVALID, "nothing evaluated yet");
     VG_CUDA(cudaSetDevice(p->device));
+    {
+        int rc = flush_pending(p);
+        if (rc) return rc;
+    }
     const int Ks = p->Ks, n = red_off_model(Ks);
     VG_CUDA(cudaMemcpyAsync(p->h_red, p->d_redbuf[p->cur], sizeof(double) * n, cudaMemcpyDeviceToHost, p->stream));
     VG_CUDA(cudaStreamSynchronize(p->stream));

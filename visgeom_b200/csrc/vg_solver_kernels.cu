@@ -520,6 +520,15 @@ __global__ void __launch_bounds__(256) peer_exchange_kernel(double *buf, int cou
     peer_allreduce(buf, count, pc);
 }
 
+// the second half alone: the sum of an exchange an evaluation kernel posted earlier
+__global__ void __launch_bounds__(256) peer_collect_kernel(double *buf, int count, PeerCtx pc, unsigned long long *done)
+{
+    peer_collect(buf, count, pc);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) *done = pc.epoch;
+}
+
 }  // namespace
 
 // Tables of the shared-block reduction (fused into the evaluation kernel): offsets of each dataset's sums
@@ -650,6 +659,14 @@ cudaError_t launch_peer_exchange(double *buf, int count, const PeerCtx &pc, Solv
 {
     if (count > PEER_SLOT_DOUBLES) return cudaErrorInvalidValue;
     peer_exchange_kernel<<<1, 256, 0, sl.stream>>>(buf, count, pc);
+    if (sl.launches) (*sl.launches)++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_peer_collect(double *buf, int count, const PeerCtx &pc, unsigned long long *done, SolverLaunch sl)
+{
+    if (count > PEER_SLOT_DOUBLES) return cudaErrorInvalidValue;
+    peer_collect_kernel<<<1, 256, 0, sl.stream>>>(buf, count, pc, done);
     if (sl.launches) (*sl.launches)++;
     return cudaGetLastError();
 }
