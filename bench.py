@@ -27,6 +27,11 @@ import sys
 import threading
 import time
 
+# The reference arm times the CPU path on ALL host threads; torchrun exports OMP_NUM_THREADS=1 to its workers, which
+# would pin the OpenMP runtime to one thread for the life of the process.  Decided before any library loads it.
+if "--impl" in sys.argv and "reference" in sys.argv:
+    os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -143,7 +148,9 @@ def cpu_reference_leg(d, model_id, n_img_step, steps, warmup, threads=None):
     except Exception:
         ev = pyoracle.Oracle()
     orc = pyoracle.Oracle()
-    threads = threads or orc.max_threads()
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which omp_get_max_threads obeys:
+    # the num_threads clause of the oracle's loop does not)
+    threads = threads or max(orc.max_threads(), len(os.sched_getaffinity(0)))
     K, P = d["K"], d["P"]
     n = n_img_step
     obs = np.ascontiguousarray(d["obs"][:n]); xi = np.ascontiguousarray(d["xi_init"][:n])
