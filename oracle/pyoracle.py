@@ -20,7 +20,7 @@ c_ip = C.POINTER(C.c_int)
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(_HERE, f) for f in ("visgeom_oracle.c", "oracle_lm.c", "visgeom_oracle.h", "oracle_lm.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("visgeom_oracle.c", "oracle_lm.c", "oracle_tuned.c", "visgeom_oracle.h", "oracle_lm.h")]
     if force or not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs):
         subprocess.check_call(["make", "-s", "-C", _HERE, "libvisgeom_oracle.so"])
     return _LIB
@@ -300,6 +300,17 @@ class OracleProblem:
         c = C.c_double()
         self.lib.vgo_problem_evaluate(self.h, threads, C.cast(C.byref(c), c_dp))
         return c.value
+
+
+class TunedOracle(_Evaluator):
+    """oracle_tuned.c: the same path with shared sub-expressions and no per-image allocation (CPU baseline only)."""
+
+    def __init__(self):
+        super().__init__(C.CDLL(build()), "vgo")
+        fn = self.lib.vgo_evaluate_batch_tuned
+        fn.restype = C.c_int
+        fn.argtypes = self._batch.argtypes
+        self._batch = fn
 
 
 class Reference(_Evaluator):

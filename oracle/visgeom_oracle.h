@@ -108,6 +108,15 @@ void vgo_odometry_prior_init(vgo_odometry_prior *op, double errV, double errW, d
 void vgo_odometry_prior_eval(const vgo_odometry_prior *op, const double xi1[6], const double xi2[6],
                              double r[6], double *J1, double *J2);
 
+/* The tuned CPU variant of the batched driver (oracle_tuned.c): same outputs, the chain composed once, no per-image
+ * allocation, one pass per corner sharing rho / eta between projection and both Jacobians. */
+int vgo_evaluate_batch_tuned(int model, const double *intr, int n_img, int P,
+                             const double *board, const double *obs,
+                             int chain_len, const int *status, const int *is_global,
+                             const double *const *xi,
+                             double *r, double *J_intr, double *const *J_xi, double *H,
+                             int threads);
+
 int vgo_hessian_entries(int K, int chain_len);   /* (D+1)(D+2)/2 */
 int vgo_max_threads(void);
 

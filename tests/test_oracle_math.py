@@ -6,6 +6,7 @@ import pytest
 
 import synthdata as sd
 from oracle.pyoracle import OracleProblem
+from util import assert_close, assert_close_hessian
 
 D, I = 0, 1
 
@@ -100,3 +101,24 @@ def test_synthetic_data_is_deterministic():
     assert d["board"].shape == (54, 3) and tuple(d["board"][10]) == (0.1, 0.1, 0.0)     # unified_calibration.cpp:286-292
     assert abs(float(d["obs"].sum()) - 1093379.0) < 1e6   # sanity, not a fingerprint
     assert np.isfinite(d["obs"]).all() and (d["obs"] > 0).all() and (d["obs"][:, 0::2] < 1280).all()
+
+
+@pytest.mark.parametrize("model", [sd.EUCM, sd.UCM, sd.MEI])
+def test_tuned_cpu_variant_equals_the_faithful_oracle(oracle, model):
+    """oracle_tuned.c (bench.py's second CPU baseline) produces the faithful restatement's outputs."""
+    from oracle.pyoracle import TunedOracle
+    from test_eval_gpu import make_chain
+    tuned = TunedOracle()
+    d = sd.make_mono(model, 40, seed=60 + model)
+    xi_fail = d["xi_init"].copy(); xi_fail[3, 2] = -0.05                     # behind the camera: sentinel rows
+    cases = [(model, d["intr_init"], d["board"], d["obs"], [xi_fail], [0], [0])]
+    st, gl = [1, 0, 1, 0, 0], [1, 0, 1, 1, 1]
+    cases.append((model, d["intr_gt"], d["board"], d["obs"], make_chain(oracle, d["xi_gt"], st, gl, seed=5), st, gl))
+    for args in cases:
+        a, b = oracle.evaluate_batch(*args, want_H=True), tuned.evaluate_batch(*args, want_H=True, threads=2)
+        assert ((a["r"] == 1e15) == (b["r"] == 1e15)).all()
+        assert_close(b["r"], a["r"], "r", 1e-12)
+        assert_close(b["J_intr"], a["J_intr"], "J_intr", 1e-12)
+        for x, y in zip(b["J_xi"], a["J_xi"]):
+            assert_close(x, y, "J_xi", 1e-12)
+        assert_close_hessian(b["H"], a["H"], "H", 1e-11)

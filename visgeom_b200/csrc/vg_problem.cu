@@ -157,7 +157,7 @@ struct vg_problem {
     int last_ds = -1;                           // the last dataset with images: its launch assembles the reduced system
     size_t partial_doubles = 0, cta_partial_doubles = 0;
     double *h_red = nullptr;                  // pinned
-    double *h_up = nullptr;                   // pinned upload staging: [slab | delta_a]
+    double *h_up = nullptr;                   // pinned upload staging (the shared parameters' bounds at the start of a solve)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double eval_ms = 0;
     int n_eval = 0;

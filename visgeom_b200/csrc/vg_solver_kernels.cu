@@ -13,7 +13,6 @@ namespace {
 __host__ __device__ inline int pk(int a, int b, int W) { return a * W - a * (a - 1) / 2 + (b - a); }
 __device__ __forceinline__ int pks(int a, int b, int W) { return a <= b ? pk(a, b, W) : pk(b, a, W); }
 
-constexpr int ACC_THREADS = 256;
 constexpr int SOLVE_THREADS = 256;
 // A pose is worked on by a group of 8 lanes: with one thread per pose 10 000 poses are 2 warps per SM, each
 // running ~5 000 dependent instructions -- pure issue latency (ncu: 3 % of the warp slots active, 34 us).  The
