@@ -1,4 +1,3 @@
 set -x
-python -m pytest tests/test_solve_gpu.py tests/test_priors_gpu.py -m gpu -q -x 2>&1 | tail -2
-python tools/lm_timing.py 2>&1 | tail -2
-VG_LM_TRACE=1 python tools/lm_timing.py 2>&1 | grep device | tail -2
+python -m pytest tests -m gpu -q 2>&1 | tail -2
+python bench.py > gpurun_out/bench_r1j.json 2> gpurun_out/bench_r1j.err; tail -c 300 gpurun_out/bench_r1j.json; tail -2 gpurun_out/bench_r1j.err
