@@ -68,6 +68,16 @@ def test_full_size_parity(gpu, oracle, model, n_img):
     assert (np.abs(Hf - gram) / (dscale[:, :, None] * dscale[:, None, :])).max() < 1e-12
 
 
+def test_stereo_full_size_parity(gpu, oracle):
+    """C4 at BASELINE.json's full size (5 000 stereo pairs = 540 000 corners): both cameras' blocks against the oracle,
+    the two-element chain [xiCam12 INVERSE (global), xiCamBoardStereo DIRECT (sequence)] included."""
+    s = sd.make_stereo(5000, seed=20244)
+    g, o = both(gpu, oracle, sd.EUCM, s["intr2_init"], s["board"], s["obs2"], [s["xi12_init"], s["xi_init"]], [I, D], [1, 0])
+    compare_eval(g, o, "C4 cam2")
+    g, o = both(gpu, oracle, sd.EUCM, s["intr1_init"], s["board"], s["obs1"], [s["xi_init"]], [D], [0])
+    compare_eval(g, o, "C4 cam1")
+
+
 def test_stereo_chain_parity(gpu, oracle):
     """C4: camera2 sees the board through [xiCam12 INVERSE (global), xiCamBoard DIRECT (sequence)]
     (data/calib_stereo_example.json:86-92)."""

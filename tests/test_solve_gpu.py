@@ -230,3 +230,26 @@ def test_poses_only_refinement_with_loss(gpu, oracle):
     assert abs(sg.final_cost - so.final_cost) <= FINAL_RTOL * so.final_cost
     assert np.abs(G.transform(ids[0]) - O.transform(ids[1])).max() < 1e-8
     assert np.abs(G.transform(ids[0]) - d["xi_gt"]).max() < 5e-3
+
+
+def test_stereo_full_size_solve(gpu, oracle):
+    """C4 at full size (5 000 pairs, 18 shared parameters + 5 000 poses): five LM iterations against the oracle LM (the
+    sixth is already at the minimum, where a trial step changes the cost by rounding noise only), then the engine
+    alone on to convergence (intrinsics of both cameras and the stereo extrinsic near the truth)."""
+    s = sd.make_stereo(5000, seed=20244)
+    G, O = gpu.Problem(), OracleProblem(oracle)
+    gi, oi = build_stereo(G, s), build_stereo(O, s)
+    og = G.default_options(); og.max_num_iterations = 5
+    oo = oracle.default_options(); oo.max_num_iterations = 5; oo.threads = oracle.max_threads()
+    sg, so = G.solve(og), O.solve(oo)
+    assert abs(sg.initial_cost - so.initial_cost) <= 1e-10 * so.initial_cost
+    assert (sg.num_successful, sg.num_unsuccessful) == (so.num_successful, so.num_unsuccessful) == (5, 0)
+    assert abs(sg.final_cost - so.final_cost) <= FINAL_RTOL * so.final_cost
+    for a, b in zip(gi[:2], oi[:2]):
+        assert rel(G.camera(a), O.camera(b)) < FINAL_RTOL
+    assert np.abs(G.transform(gi[2]) - O.transform(oi[2])).max() < 1e-8
+    assert np.abs(G.transform(gi[3]) - O.transform(oi[3])).max() < 1e-7
+    sg = G.solve()
+    assert sg.termination in (0, 1, 2)
+    assert rel(G.camera(gi[0])[2:], s["intr1_gt"][2:]) < 1e-3 and rel(G.camera(gi[1])[2:], s["intr2_gt"][2:]) < 1e-3
+    assert np.abs(G.transform(gi[2])[0] - s["xi12_gt"]).max() < 1e-3

@@ -39,9 +39,9 @@ __device__ __forceinline__ unsigned long long *peer_slot(unsigned long long *inb
     return inbox + ((size_t)parity * PEER_MAX_RANKS + r) * 2 * PEER_SLOT_DOUBLES;
 }
 
-// A poll gives up after PEER_SPIN_LIMIT reads (seconds of waiting: a peer that never arrives -- a rank that died or
+// A poll gives up after PEER_SPIN_LIMIT reads (ten seconds or more of waiting: a peer that never arrives -- a rank that died or
 // issued a different sequence of exchanges) and poisons the sum with NaN instead of hanging the GPU.
-constexpr long long PEER_SPIN_LIMIT = 1ll << 31;
+constexpr long long PEER_SPIN_LIMIT = 1ll << 25;
 
 // step 1: this rank's block into every rank's inbox.  Called by every thread of ONE CTA, count <= PEER_SLOT_DOUBLES;
 // buf may have been written by this CTA just before (the barrier orders it).
