@@ -165,6 +165,14 @@ int vg_eval_odometry_prior(int n, double errV, double errW, double lambda,
                            const double *xi1 /* n x 6 */, const double *xi2 /* n x 6 */,
                            double *r /* n x 6 */, double *J1 /* n x 36 */, double *J2 /* n x 36 */);
 
+/* TrajectoryVisualQuality::visualCov (trajectory_generation.cpp:185-206), batched over n camera poses:
+ * the covariance of a camera pose localised on the board, from dP/dX of the model at every board point:
+ *   [t, r] = camPose^-1 o xiBoard, X_i = R b_i + t, J_i = dpdx(X_i) [-I | hat(X_i)],
+ *   JtJ = sum J_i^T J_i, JtCJ = sum J_i^T S J_i with S = U of the Cholesky factorisation of diag(1 / feature_variance),
+ *   cov = JtCJ^-T JtJ JtCJ^-1   (6 x 6 row-major per pose). */
+int vg_visual_cov(int model, const double *intr, const double *xi_board /* 6 */, int P, const double *board /* P x 3 */,
+                  double feature_variance, int n, const double *cam_poses /* n x 6 */, double *cov /* n x 36 */);
+
 /* device < 0 -> current device */
 vg_problem *vg_problem_create(int device);
 void vg_problem_destroy(vg_problem *p);

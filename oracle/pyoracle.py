@@ -169,6 +169,15 @@ class Oracle(_Evaluator):
         self.lib.vgo_odometry_prior_eval(C.byref(op), _dp(a), _dp(b), _dp(r), _dp(J1), _dp(J2))
         return r, J1, J2
 
+    def visual_cov(self, model, intr, xi_board, board, feature_variance, cam_poses):
+        """TrajectoryVisualQuality::visualCov for n camera poses -> (n, 6, 6)."""
+        intr = _f64(intr); xb = _f64(xi_board); board = _f64(board); poses = _f64(cam_poses).reshape(-1, 6)
+        out = np.zeros((poses.shape[0], 6, 6))
+        self.lib.vgo_visual_cov.argtypes = [C.c_int, c_dp, c_dp, C.c_int, c_dp, C.c_double, C.c_int, c_dp, c_dp]
+        self.lib.vgo_visual_cov(model, _dp(intr), _dp(xb), board.shape[0], _dp(board), feature_variance, poses.shape[0],
+                                _dp(poses), _dp(out))
+        return out
+
     # ---- small geometry helpers (for the unit tests of the restatement) ----
     def rotation_matrix(self, v):
         v = _f64(v); R = np.zeros(9)
@@ -323,6 +332,14 @@ class Reference(_Evaluator):
         super().__init__(C.CDLL(path), "vgref")
         self.lib.vgref_transformation_prior.argtypes = [c_dp, c_dp, c_dp, c_dp, c_dp]
         self.lib.vgref_odometry_prior.argtypes = [C.c_double, C.c_double, C.c_double, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]
+
+    def visual_cov(self, model, intr, xi_board, nx, ny, step, feature_variance, cam_poses):
+        """The reference's own TrajectoryVisualQuality (built through its constructor) -> (n, 6, 6)."""
+        intr = _f64(intr); xb = _f64(xi_board); poses = _f64(cam_poses).reshape(-1, 6)
+        out = np.zeros((poses.shape[0], 6, 6))
+        self.lib.vgref_visual_cov.argtypes = [C.c_int, c_dp, c_dp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, c_dp, c_dp]
+        self.lib.vgref_visual_cov(model, _dp(intr), _dp(xb), nx, ny, step, feature_variance, poses.shape[0], _dp(poses), _dp(out))
+        return out
 
     def transformation_prior(self, stiffness, xi_prior, xi):
         st = _f64(stiffness); xp = _f64(xi_prior); x = _f64(xi)

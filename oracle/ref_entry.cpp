@@ -5,6 +5,7 @@
 // (calib_cost_functions.cpp:28-117) exactly as Ceres does: one functor per image, Evaluate
 // with all Jacobian blocks requested.  No reference source is copied into this repository.
 #include "calibration/calib_cost_functions.h"
+#include "calibration/trajectory_generation.h"
 #include "projection/eucm.h"
 #include "projection/ucm.h"
 #include "projection/mei.h"
@@ -136,6 +137,34 @@ void vgref_odometry_prior(double errV, double errW, double lambda, const double 
     const double *params[2] = {xi1, xi2};
     double *jac[2] = {J1, J2};
     cost.Evaluate(params, r, (J1 || J2) ? jac : NULL);
+}
+
+// TrajectoryVisualQuality::visualCov (trajectory_generation.cpp:185-206): the object is built through its own
+// constructor from an in-memory property tree (the keys it reads, :85-118), no trajectories attached
+static ptree leaf(double v) { ptree t; t.put_value(v); return t; }
+static ptree vec(const double *v, int n) { ptree t; for (int i = 0; i < n; i++) t.add_child("", leaf(v[i])); return t; }
+
+void vgref_visual_cov(int model, const double *intr, const double *xi_board, int nx, int ny, double step,
+                      double feature_variance, int n, const double *cam_poses, double *out)
+{
+    const double zero6[6] = {0, 0, 0, 0, 0, 0}, one6[6] = {1, 1, 1, 1, 1, 1};
+    ptree params, board;
+    params.add_child("xiBaseCam", vec(zero6, 6));
+    params.add_child("xiOrigBoard", vec(xi_board, 6));
+    params.add_child("turn_radius", leaf(1.0));
+    board.add_child("cols", leaf(nx)); board.add_child("rows", leaf(ny)); board.add_child("step", leaf(step));
+    params.add_child("board", board);
+    params.add_child("min_camera_dist", leaf(0.1));
+    params.add_child("min_margin", leaf(10.0));
+    params.add_child("min_cell_size", leaf(1.0));
+    params.add_child("prior_variance", vec(one6, 6));
+    params.add_child("feature_variance", leaf(feature_variance));
+    std::unique_ptr<ICamera> cam(make_camera(model, intr));
+    TrajectoryVisualQuality quality(vector<ITrajectory *>(), params, cam.get());
+    for (int k = 0; k < n; k++) {
+        Matrix6d C = quality.visualCov(Transformation<double>(cam_poses + 6 * k));
+        for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) out[36 * k + 6 * i + j] = C(i, j);
+    }
 }
 
 }  // extern "C"

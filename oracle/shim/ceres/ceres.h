@@ -29,7 +29,12 @@ public:
     }
 };
 template <typename F, int S = 4> class DynamicAutoDiffCostFunction;
-class FirstOrderFunction;
+class FirstOrderFunction {
+public:
+    virtual ~FirstOrderFunction() {}
+    virtual bool Evaluate(const double *parameters, double *cost, double *gradient) const = 0;
+    virtual int NumParameters() const = 0;
+};
 class LossFunction { public: virtual ~LossFunction() {} };
 class SoftLOneLoss;
 class CauchyLoss;

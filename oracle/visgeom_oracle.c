@@ -909,6 +909,75 @@ void vgo_odometry_prior_eval(const vgo_odometry_prior *op, const double xi1[6], 
     }
 }
 
+/* ------------------------------------------------------------------ */
+/* TrajectoryVisualQuality::visualCov, trajectory_generation.cpp:185-206: covariance of the camera pose
+ * localised on the board, from dP/dX of every board point.  feature_variance -> _ptStiffness = U of the Cholesky
+ * factorisation of diag(1 / variance) (:112-115).  out: 6 x 6 row-major per pose. */
+void vgo_visual_cov(int model, const double *intr, const double xi_board[6], int P, const double *board,
+                    double feature_variance, int n, const double *cam_poses, double *out)
+{
+    const double stiff = sqrt(1. / feature_variance);                 /* U(0,0) = U(1,1); U(0,1) = 0 */
+    for (int k = 0; k < n; k++) {
+        double xcb[6], R[9];
+        vgo_inverse_compose(cam_poses + 6 * (size_t)k, xi_board, xcb);  /* :187 */
+        vgo_rotation_matrix(xcb + 3, R);
+        double JtJ[36], JtCJ[36];
+        memset(JtJ, 0, sizeof JtJ); memset(JtCJ, 0, sizeof JtCJ);
+        for (int i = 0; i < P; i++) {
+            double X[3], o[3], pj[6], hx[9], d[2][6];
+            mat3_vec(R, board + 3 * i, o);
+            X[0] = o[0] + xcb[0]; X[1] = o[1] + xcb[1]; X[2] = o[2] + xcb[2];
+            vgo_projection_jacobian(model, intr, X, pj, pj + 3);       /* :195 (zero rows when the projection fails) */
+            hat3(X, hx);
+            for (int q = 0; q < 2; q++)                                 /* dpdx * [-I | hat(X)], :197-200 */
+                for (int j = 0; j < 3; j++) {
+                    d[q][j] = -pj[3 * q + j];
+                    d[q][3 + j] = pj[3 * q] * hx[j] + pj[3 * q + 1] * hx[3 + j] + pj[3 * q + 2] * hx[6 + j];
+                }
+            for (int a = 0; a < 6; a++)
+                for (int b = 0; b < 6; b++) {
+                    JtJ[6 * a + b] += d[0][a] * d[0][b] + d[1][a] * d[1][b];                        /* :201 */
+                    JtCJ[6 * a + b] += (d[0][a] * stiff) * d[0][b] + (d[1][a] * stiff) * d[1][b];   /* :202 */
+                }
+        }
+        /* JtCJ^-1 by LU with partial pivoting (Eigen's fixed-size inverse beyond 4x4), :204 */
+        double lu[6][6], inv[36];
+        int perm[6];
+        for (int i = 0; i < 6; i++) { perm[i] = i; for (int j = 0; j < 6; j++) lu[i][j] = JtCJ[6 * i + j]; }
+        for (int c = 0; c < 6; c++) {
+            int piv = c;
+            for (int i = c + 1; i < 6; i++) if (fabs(lu[i][c]) > fabs(lu[piv][c])) piv = i;
+            if (piv != c) {
+                for (int j = 0; j < 6; j++) { double t = lu[c][j]; lu[c][j] = lu[piv][j]; lu[piv][j] = t; }
+                int t = perm[c]; perm[c] = perm[piv]; perm[piv] = t;
+            }
+            for (int i = c + 1; i < 6; i++) {
+                lu[i][c] /= lu[c][c];
+                for (int j = c + 1; j < 6; j++) lu[i][j] -= lu[i][c] * lu[c][j];
+            }
+        }
+        for (int c = 0; c < 6; c++) {
+            double x[6];
+            for (int i = 0; i < 6; i++) {
+                double v = perm[i] == c ? 1. : 0.;
+                for (int j = 0; j < i; j++) v -= lu[i][j] * x[j];
+                x[i] = v;
+            }
+            for (int i = 5; i >= 0; i--) {
+                double v = x[i];
+                for (int j = i + 1; j < 6; j++) v -= lu[i][j] * x[j];
+                x[i] = v / lu[i][i];
+            }
+            for (int i = 0; i < 6; i++) inv[6 * i + c] = x[i];
+        }
+        /* inv^T * JtJ * inv, :205 */
+        double invT[36], tmp[36];
+        for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) invT[6 * i + j] = inv[6 * j + i];
+        mat6_mul(invT, JtJ, tmp);
+        mat6_mul(tmp, inv, out + 36 * (size_t)k);
+    }
+}
+
 int vgo_hessian_entries(int K, int chain_len)
 {
     int D = K + 6 * chain_len;

@@ -108,6 +108,11 @@ void vgo_odometry_prior_init(vgo_odometry_prior *op, double errV, double errW, d
 void vgo_odometry_prior_eval(const vgo_odometry_prior *op, const double xi1[6], const double xi2[6],
                              double r[6], double *J1, double *J2);
 
+/* TrajectoryVisualQuality::visualCov (trajectory_generation.cpp:185-206): 6 x 6 covariance of each camera pose
+ * localised on the board; cam_poses n x 6, out n x 36 row-major */
+void vgo_visual_cov(int model, const double *intr, const double xi_board[6], int P, const double *board,
+                    double feature_variance, int n, const double *cam_poses, double *out);
+
 /* The tuned CPU variant of the batched driver (oracle_tuned.c): same outputs, the chain composed once, no per-image
  * allocation, one pass per corner sharing rho / eta between projection and both Jacobians. */
 int vgo_evaluate_batch_tuned(int model, const double *intr, int n_img, int P,

@@ -105,6 +105,26 @@ def main():
     np.savez_compressed(path, **blob)
     print(f"wrote {path}: {len(blob)} arrays, {os.path.getsize(path) / 1024:.0f} KiB")
     priors(ref, orc)
+    visual_cov(ref, orc)
+
+
+def visual_cov(ref, orc):
+    """TrajectoryVisualQuality::visualCov (trajectory_generation.cpp:185-206) from the reference build, the object made by
+    its own constructor -> reference_visualcov.npz."""
+    blob = {}
+    xi_board = np.array([0.3, -0.2, 0.1, 0.1, -0.2, 0.3])
+    for model, name, intr in ((sd.EUCM, "eucm", sd.EUCM_GT_LEFT), (sd.UCM, "ucm", sd.UCM_GT), (sd.MEI, "mei", sd.MEI_GT)):
+        d = sd.make_mono(model, 16, seed=70 + model)
+        # camera poses such that camPose^-1 o xiBoard is a pose from which the whole board is visible
+        cam = np.array([orc.compose(xi_board, x, "compose_inverse") for x in d["xi_gt"]])
+        if model == sd.EUCM:      # a board seen edge-on, 36 of its 54 corners outside the model's domain: zero rows (eucm.h:141-150)
+            cam[-1] = orc.compose(xi_board, [0.3, -0.25, 0.02, 0, 1.9, 0], "compose_inverse")
+        blob[f"{name}/intr"] = np.asarray(intr); blob[f"{name}/cam_poses"] = cam
+        blob[f"{name}/cov"] = ref.visual_cov(model, intr, xi_board, 9, 6, 0.1, 0.25, cam)
+    blob["xi_board"] = xi_board; blob["board"] = sd.make_board(9, 6, 0.1); blob["feature_variance"] = np.array(0.25)
+    path = os.path.join(HERE, "reference_visualcov.npz")
+    np.savez_compressed(path, **blob)
+    print(f"wrote {path}: {len(blob)} arrays, {os.path.getsize(path) / 1024:.0f} KiB")
 
 
 def priors(ref, orc):

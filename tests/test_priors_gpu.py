@@ -205,3 +205,30 @@ def test_prior_api_errors(gpu):
     P.add_odometry(sq, 0.1, 0.1, 0.01, d["odom"])
     with pytest.raises(gpu.VisgeomError, match="already has odometry"):
         P.add_odometry(sq, 0.1, 0.1, 0.01, d["odom"])
+
+
+VCOV = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_visualcov.npz"))
+
+
+@pytest.mark.parametrize("model,name", [(sd.EUCM, "eucm"), (sd.UCM, "ucm"), (sd.MEI, "mei")])
+def test_visual_cov_matches_reference_and_oracle(gpu, oracle, model, name):
+    """TrajectoryVisualQuality::visualCov (trajectory_generation.cpp:185-206; SURVEY 8f-5) through vg_visual_cov: the
+    reference build's vectors (a pose with 36 of 54 corners outside the model's domain included), then 300 random
+    poses against the oracle.  Tolerance 1e-9 of each matrix's largest entry (the 6 x 6 inverse amplifies rounding
+    by the condition number of J^T J, ~1e3 here)."""
+    fv = float(VCOV["feature_variance"])
+    got = gpu.visual_cov(model, VCOV[f"{name}/intr"], VCOV["xi_board"], VCOV["board"], fv, VCOV[f"{name}/cam_poses"])
+    want = VCOV[f"{name}/cov"]
+    for k in range(len(want)):
+        assert np.isfinite(got[k]).all()
+        assert np.abs(got[k] - want[k]).max() <= 1e-9 * np.abs(want[k]).max(), (name, k)
+    d = sd.make_mono(model, 300, seed=4100 + model)
+    xi_board = np.array([-0.2, 0.4, 0.3, 0.3, 0.1, -0.4])
+    cam = np.array([oracle.compose(xi_board, x, "compose_inverse") for x in d["xi_gt"]])
+    got = gpu.visual_cov(model, d["intr_gt"], xi_board, d["board"], 0.04, cam)
+    want = oracle.visual_cov(model, d["intr_gt"], xi_board, d["board"], 0.04, cam)
+    rel_err = np.abs(got - want).max(axis=(1, 2)) / np.abs(want).max(axis=(1, 2))
+    assert rel_err.max() <= 1e-9, rel_err.max()
+    assert gpu.visual_cov(model, d["intr_gt"], xi_board, d["board"], 0.04, np.zeros((0, 6))).shape == (0, 6, 6)
+    with pytest.raises(gpu.VisgeomError, match="bad arguments"):
+        gpu.visual_cov(model, d["intr_gt"], xi_board, d["board"], -1.0, cam)

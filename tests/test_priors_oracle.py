@@ -118,3 +118,20 @@ def test_loss_matches_ceres_corrector_restated_in_numpy(oracle):
         P.solve()
         res[loss] = np.abs(P.camera(cam)[2:] - d["intr_gt"][2:]).max()
     assert res[1.0] < 0.5 * res[0.0]
+
+
+VCOV = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_visualcov.npz"))
+
+
+@pytest.mark.parametrize("model,name", [(sd.EUCM, "eucm"), (sd.UCM, "ucm"), (sd.MEI, "mei")])
+def test_visual_cov_matches_reference_vectors(oracle, model, name):
+    """TrajectoryVisualQuality::visualCov (trajectory_generation.cpp:185-206; SURVEY 8f-5): the oracle against the
+    reference build's own object (constructed through its constructor from an in-memory property tree)."""
+    got = oracle.visual_cov(model, VCOV[f"{name}/intr"], VCOV["xi_board"], VCOV["board"], float(VCOV["feature_variance"]),
+                            VCOV[f"{name}/cam_poses"])
+    want = VCOV[f"{name}/cov"]
+    for k in range(len(want)):
+        assert np.abs(got[k] - want[k]).max() <= 1e-11 * np.abs(want[k]).max()
+    # the covariance of a localisation is symmetric positive definite
+    w = np.linalg.eigvalsh((want[0] + want[0].T) / 2)
+    assert w[0] > 0

@@ -1,2 +1,2 @@
 set -x
-python -m pytest tests/test_solve_gpu.py tests/test_eval_gpu.py -m gpu -q --tb=short 2>&1 | tail -4
+python -m pytest tests/test_priors_gpu.py -m gpu -q --tb=short 2>&1 | tail -12

@@ -84,6 +84,7 @@ def lib() -> C.CDLL:
                                              c_dp, c_dp, c_dp]
         L.vg_problem_peer_export.argtypes = [C.c_void_p, C.c_void_p]
         L.vg_problem_peer_connect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.vg_visual_cov.argtypes = [C.c_int, c_dp, c_dp, C.c_int, c_dp, C.c_double, C.c_int, c_dp, c_dp]
         L.vg_problem_set_allreduce.argtypes = [C.c_void_p, ALLREDUCE_FN, C.c_void_p, C.c_int, C.c_int]
         L.vg_problem_materialize_jacobians.argtypes = [C.c_void_p, C.c_int]
         L.vg_problem_device_buffer.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p),
@@ -192,6 +193,15 @@ def eval_odometry_prior(errV, errW, lam, odom1, odom2, xi1, xi2, want_J=True):
     _check(lib().vg_eval_odometry_prior(n, errV, errW, lam, _dp(o1), _dp(o2), _dp(a), _dp(b), _dp(r),
                                         _dp(J1) if want_J else None, _dp(J2) if want_J else None))
     return r, J1, J2
+
+
+def visual_cov(model, intr, xi_board, board, feature_variance, cam_poses):
+    """TrajectoryVisualQuality::visualCov (trajectory_generation.cpp:185-206) for n camera poses -> (n, 6, 6)."""
+    intr = _f64(intr); xb = _f64(xi_board); board = _f64(board); poses = _f64(cam_poses).reshape(-1, 6)
+    out = np.empty((poses.shape[0], 6, 6))
+    _check(lib().vg_visual_cov(model, _dp(intr), _dp(xb), board.shape[0], _dp(board), float(feature_variance),
+                               poses.shape[0], _dp(poses), _dp(out)))
+    return out
 
 
 def eval_chain_dev(model, intr, board, obs, xi_list, status, is_global, n_img, P,

@@ -343,6 +343,108 @@ __global__ void op_functor_kernel(int n, double errV, double errW, double lambda
         for (int k = 0; k < 36; k++) J2_out[36 * (size_t)i + k] = J2[k];
 }
 
+
+// ---- TrajectoryVisualQuality::visualCov (trajectory_generation.cpp:185-206) ----------------------
+// One warp per camera pose: the lanes take the board points (X = R b + t with [t, r] = camPose^-1 o xiBoard, the
+// model's dP/dX, rows dpdx [-I | hat(X)]), J^T J is summed over the lanes in a fixed order, lane 0 inverts
+// J^T C J = stiffness * J^T J by LU with partial pivoting and forms inv^T J^T J inv.
+template <int MODEL>
+__global__ void __launch_bounds__(128) visual_cov_kernel(const double *intr_g, const double *xi_board, int P, const double *board,
+                                                          double stiffness, int n, const double *cam_poses, double *cov)
+{
+    using CAM = Camera<MODEL>;
+    constexpr int K = CAM::K;
+    const int lane = threadIdx.x & 31, pose = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (pose >= n) return;
+    double intr[K];
+#pragma unroll
+    for (int i = 0; i < K; i++) intr[i] = intr_g[i];
+    const typename CAM::Consts cc = CAM::prepare(intr);
+    double xcb[6], R[9], M[9];
+    se3_inverse_compose(cam_poses + 6 * (size_t)pose, xi_board, xcb);
+    rodrigues_and_left_jacobian(xcb[3], xcb[4], xcb[5], R, M);
+    double acc[21];
+#pragma unroll
+    for (int i = 0; i < 21; i++) acc[i] = 0.0;
+    for (int i = lane; i < P; i += 32) {
+        const double bx = board[3 * i], by = board[3 * i + 1], bz = board[3 * i + 2];
+        const double X[3] = {fma(R[0], bx, fma(R[1], by, R[2] * bz)) + xcb[0], fma(R[3], bx, fma(R[4], by, R[5] * bz)) + xcb[1],
+                             fma(R[6], bx, fma(R[7], by, R[8] * bz)) + xcb[2]};
+        double u, v, Pu[3], Pv[3], Ju[K], Jv[K];
+        const bool ok = CAM::eval(intr, cc, X[0], X[1], X[2], u, v, Pu, Pv, Ju, Jv);
+        double d[2][6];
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const double *Pq = q ? Pv : Pu;
+            const double p0 = ok ? Pq[0] : 0.0, p1 = ok ? Pq[1] : 0.0, p2 = ok ? Pq[2] : 0.0;   // zero rows on a failed projection
+            d[q][0] = -p0; d[q][1] = -p1; d[q][2] = -p2;
+            // P hat(X): columns (p1 X2 - p2 X1, p2 X0 - p0 X2, p0 X1 - p1 X0)
+            d[q][3] = p1 * X[2] - p2 * X[1];
+            d[q][4] = p2 * X[0] - p0 * X[2];
+            d[q][5] = p0 * X[1] - p1 * X[0];
+        }
+#pragma unroll
+        for (int a = 0; a < 6; a++)
+#pragma unroll
+            for (int b = 0; b <= a; b++) acc[lt(a, b)] += fma(d[0][a], d[0][b], d[1][a] * d[1][b]);
+    }
+    // lanes combined in a fixed (butterfly) order
+#pragma unroll
+    for (int i = 0; i < 21; i++)
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
+    if (lane != 0) return;
+    double JtJ[36], lu[36], inv[36];
+#pragma unroll
+    for (int a = 0; a < 6; a++)
+#pragma unroll
+        for (int b = 0; b < 6; b++) {
+            JtJ[6 * a + b] = acc[a >= b ? lt(a, b) : lt(b, a)];
+            lu[6 * a + b] = stiffness * JtJ[6 * a + b];
+        }
+    int perm[6] = {0, 1, 2, 3, 4, 5};
+    for (int c = 0; c < 6; c++) {
+        int piv = c;
+        for (int i = c + 1; i < 6; i++) if (fabs(lu[6 * i + c]) > fabs(lu[6 * piv + c])) piv = i;
+        if (piv != c) {
+            for (int j = 0; j < 6; j++) { const double t = lu[6 * c + j]; lu[6 * c + j] = lu[6 * piv + j]; lu[6 * piv + j] = t; }
+            const int t = perm[c]; perm[c] = perm[piv]; perm[piv] = t;
+        }
+        for (int i = c + 1; i < 6; i++) {
+            lu[6 * i + c] /= lu[6 * c + c];
+            for (int j = c + 1; j < 6; j++) lu[6 * i + j] = fma(-lu[6 * i + c], lu[6 * c + j], lu[6 * i + j]);
+        }
+    }
+    for (int c = 0; c < 6; c++) {
+        double x[6];
+        for (int i = 0; i < 6; i++) {
+            double s = perm[i] == c ? 1.0 : 0.0;
+            for (int j = 0; j < i; j++) s = fma(-lu[6 * i + j], x[j], s);
+            x[i] = s;
+        }
+        for (int i = 5; i >= 0; i--) {
+            double s = x[i];
+            for (int j = i + 1; j < 6; j++) s = fma(-lu[6 * i + j], x[j], s);
+            x[i] = s / lu[6 * i + i];
+        }
+        for (int i = 0; i < 6; i++) inv[6 * i + c] = x[i];
+    }
+    double tmp[36];
+    for (int a = 0; a < 6; a++)
+        for (int b = 0; b < 6; b++) {
+            double s = 0.0;
+            for (int k = 0; k < 6; k++) s = fma(inv[6 * k + a], JtJ[6 * k + b], s);
+            tmp[6 * a + b] = s;
+        }
+    double *out = cov + 36 * (size_t)pose;
+    for (int a = 0; a < 6; a++)
+        for (int b = 0; b < 6; b++) {
+            double s = 0.0;
+            for (int k = 0; k < 6; k++) s = fma(tmp[6 * a + k], inv[6 * k + b], s);
+            out[6 * a + b] = s;
+        }
+}
+
 // ---- block-tridiagonal pose elimination --------------------------------------------------------------------
 // One warp per segment (a run of consecutive sequence elements linked by odometry blocks, or a single element
 // that carries a prior / is constant).  The 6x6 work of an element is done by every lane (same values, no
@@ -656,6 +758,29 @@ int vg_eval_odometry_prior(int n, double errV, double errW, double lambda, const
     VG_CUDA(dr.down(r, 6 * m));
     if (J1) VG_CUDA(j1.down(J1, 36 * m));
     if (J2) VG_CUDA(j2.down(J2, 36 * m));
+    return VG_OK;
+}
+
+int vg_visual_cov(int model, const double *intr, const double *xi_board, int P, const double *board, double feature_variance,
+                  int n, const double *cam_poses, double *cov)
+{
+    const int K = vg_model_num_params(model);
+    if (K < 0) return K;
+    if (n < 0 || P < 1 || !intr || !xi_board || !board || !(feature_variance > 0.0) || (n > 0 && (!cam_poses || !cov)))
+        return fail(VG_ERR_INVALID, "vg_visual_cov: bad arguments");
+    int rc = have_device();
+    if (rc || n == 0) return rc;
+    DevBuf di, dx, db, dp, dc;
+    VG_CUDA(di.up(intr, (size_t)K)); VG_CUDA(dx.up(xi_board, 6)); VG_CUDA(db.up(board, 3 * (size_t)P));
+    VG_CUDA(dp.up(cam_poses, 6 * (size_t)n)); VG_CUDA(dc.alloc(36 * (size_t)n));
+    const double stiffness = std::sqrt(1.0 / feature_variance);      // U of the Cholesky factorisation of diag(1 / variance), :112-115
+    const int blocks = (n + 3) / 4;
+    if (model == VG_MODEL_EUCM) visual_cov_kernel<MODEL_EUCM><<<blocks, 128>>>(di.p, dx.p, P, db.p, stiffness, n, dp.p, dc.p);
+    else if (model == VG_MODEL_UCM) visual_cov_kernel<MODEL_UCM><<<blocks, 128>>>(di.p, dx.p, P, db.p, stiffness, n, dp.p, dc.p);
+    else visual_cov_kernel<MODEL_MEI><<<blocks, 128>>>(di.p, dx.p, P, db.p, stiffness, n, dp.p, dc.p);
+    launch_counter()++;
+    VG_CUDA(cudaGetLastError());
+    VG_CUDA(dc.down(cov, 36 * (size_t)n));
     return VG_OK;
 }
 
