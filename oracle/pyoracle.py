@@ -28,8 +28,8 @@ def build(force: bool = False) -> str:
 
 def build_ref(force: bool = False):
     """Compile the reference's own sources against oracle/shim (only where /root/reference exists)."""
-    if os.path.isdir("/root/reference/include") and (force or not os.path.exists(_REF)):
-        subprocess.check_call(["make", "-s", "-C", _HERE, "ref"])
+    if os.path.isdir("/root/reference/include"):        # make decides whether anything is stale
+        subprocess.check_call(["make", "-s", "-C", _HERE] + (["-B"] if force else []) + ["ref"])
     return _REF if os.path.exists(_REF) else None
 
 
