@@ -7,7 +7,8 @@ Jacobian blocks (Ceres layout, materialised in memory), plus the J^T J / J^T r
 normal-equation build and its reduction to the shared (intrinsic) block -- what one
 Ceres evaluation of the reference costs (calib_cost_functions.cpp:28-117 driven by
 ceres::Solve, unified_calibration.cpp:53).  With N > 1 GPUs every rank owns its own
-images (weak scaling) and the reduced block is summed with one NCCL all-reduce.
+images (weak scaling) and the reduced block is summed across the ranks by the evaluation
+kernel itself over NVLink peer memory (VG_BENCH_NCCL=1: one NCCL all-reduce per step).
 
 Workload at N=1: BASELINE.json configs[1] -- monocular EUCM, 10 000 synthetic images
 x 54 corners (9x6 board), fp64.
