@@ -1,2 +1,2 @@
-set -x
-python -m pytest tests/test_priors_gpu.py -m gpu -q --tb=short 2>&1 | tail -12
+python -m pytest tests -m gpu -q 2>&1 | tail -2
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
