@@ -44,6 +44,14 @@ def test_no_cpu_fallback(vg):
         vg.eval_chain(sd.EUCM, d["intr_init"], d["board"], d["obs"], [d["xi_init"]], [0], [0])
     with pytest.raises(vg.VisgeomError, match="no CUDA device"):
         vg.Problem()
+    # the prior functors and visualCov have no CPU path either
+    x = np.zeros((2, 6)); x[:, 2] = 1.0
+    with pytest.raises(vg.VisgeomError, match="no CUDA device"):
+        vg.eval_transformation_prior(np.ones((2, 6)), x, x)
+    with pytest.raises(vg.VisgeomError, match="no CUDA device"):
+        vg.eval_odometry_prior(0.1, 0.1, 0.01, x, x, x, x)
+    with pytest.raises(vg.VisgeomError, match="no CUDA device"):
+        vg.visual_cov(sd.EUCM, d["intr_init"], x[0], d["board"], 0.25, x)
 
 
 def test_product_does_not_touch_the_oracle():
