@@ -35,6 +35,7 @@ struct ImageData {
     int idxUL = 0, idxUR = 0, idxBL = 0, idxBR = 0;
     int imageWidth = 0, imageHeight = 0;
     bool doNotSolve = false, doNotSolveGlobal = false;
+    bool showOutliers = false;      // "show_outliers": the textual part of the reference's outlier report (no image windows here)
     int getFirstExtractedIdx() const
     {
         for (size_t i = 0; i < detectedCornersVec.size(); i++) if (!detectedCornersVec[i].empty()) return (int)i;

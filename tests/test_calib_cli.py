@@ -170,3 +170,19 @@ def test_odometry_problem_matches_oracle(cli, tmp_path, oracle):
     assert rel.max() < 1e-6, rel
     assert np.abs(glob["xiBaseCam"] - O.transform(bc)[0]).max() < 1e-6
     assert np.abs(glob["xiWorldBoard"] - O.transform(wB)[0]).max() < 1e-6
+
+
+@pytest.mark.gpu
+def test_show_outliers_report(cli, tmp_path):
+    """"show_outliers" (unified_calibration.cpp:1217-1272): the textual part of the report -- a sample is listed when
+    one of its corners is off by 3.6 sigma or a pixel."""
+    path, d = mk.write_mono(str(tmp_path), 12)
+    corners = json.load(open(str(tmp_path / "corners.json")))
+    corners[4][0]["points"][10][0] += 6.0            # one gross outlier in image 4
+    json.dump(corners, open(str(tmp_path / "corners.json"), "w"))
+    edit(path, lambda p: p["data"][0].update(parameters=["show_outliers"]))
+    r = run(cli, "--out", str(tmp_path) + "/", path)
+    assert r.returncode == 0, r.stderr
+    assert "Sample #4" in r.stdout and "standard deviation : " in r.stdout
+    m = re.search(r"err : (\S+)", r.stdout)
+    assert m and float(m.group(1)) > 3.0

@@ -1,2 +1,1 @@
-python -m pytest tests -m gpu -q 2>&1 | tail -2
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+python -m pytest tests/test_calib_cli.py -m gpu -q --tb=short 2>&1 | tail -12

@@ -3,6 +3,7 @@
 #include "visgeom_b200/calibration.hpp"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <fstream>
 #include <iostream>
@@ -123,7 +124,8 @@ void GenericCameraCalibration::initTransformChainInfo(ImageData &data, const jso
         const string &f = flag.str;
         if (f == "do_not_solve") data.doNotSolve = true;
         else if (f == "do_not_solve_global") data.doNotSolveGlobal = true;
-        else if (f == "check_extraction" || f == "improve_detection" || f == "show_outliers" || f == "user_guided" ||
+        else if (f == "show_outliers") data.showOutliers = true;
+        else if (f == "check_extraction" || f == "improve_detection" || f == "user_guided" ||
                  f == "save_outlire_images" || f == "draw_improved") { /* image / GUI options: nothing to do here */ }
         else cout << "WARNING : UNKNOWN FLAG -- " << f << endl;
     }
@@ -468,10 +470,28 @@ void GenericCameraCalibration::writeImageResidual(vg_problem *p, int dataset, co
     size_t row = 0;
     for (size_t t = 0; t < transfVec.size(); t++) {
         if (data.detectedCornersVec[t].empty()) continue;
+        const size_t row0 = row;
+        double stdAcc = 0;
         for (int i = 0; i < P; i++, row++) {
             const double ru = r[2 * row], rv = r[2 * row + 1];
             const Vector2d &det = data.detectedCornersVec[t][i];
             f << -ru << " " << -rv << "   " << det[0] + ru << " " << det[1] + rv << "   " << transfVec[t] << "\n";
+            stdAcc += ru * ru + rv * rv;
+        }
+        if (!data.showOutliers) continue;
+        // :1217-1232, 1234-1272 without the image: a corner is an outlier when its error reaches 3.6 sigma or one pixel
+        const double sigma = std::sqrt(stdAcc / (P - 2));
+        bool header = false;
+        for (int i = 0; i < P; i++) {
+            const double ru = r[2 * (row0 + i)], rv = r[2 * (row0 + i) + 1];
+            const double errNorm = std::sqrt(ru * ru + rv * rv);
+            if (errNorm < 3.6 * sigma && errNorm < 1.) continue;
+            if (!header) {
+                cout << "Sample #" << t << endl << transfVec[t] << endl << "standard deviation : " << sigma << endl;
+                header = true;
+            }
+            const Vector2d &det = data.detectedCornersVec[t][i];
+            cout << det[0] + ru << " " << det[1] + rv << "   err : " << errNorm << endl;
         }
     }
 }
