@@ -66,3 +66,106 @@ def test_camera_objects_match_reference_vectors(probe, model, name, intr):
     b = GOLD[f"probe/bounds_{name}"]
     out = probe([f"bounds {model} {len(intr)} {fmt(intr)} {i}" for i in range(len(intr))])
     assert np.array_equal(np.array(out), b)
+
+
+# ---- the initialisation half of the front end, on the host alone ("do_not_solve") ------------------------------------
+import json
+import sys
+
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import make_calib_problem as mk  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def calib_probe(tmp_path_factory, vg):
+    exe = str(tmp_path_factory.mktemp("calib") / "calib_probe")
+    lib_dir = os.path.join(ROOT, "visgeom_b200")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "include"),
+                           "-I" + os.path.join(lib_dir, "host"), os.path.join(ROOT, "tests", "calib_probe.cpp"),
+                           os.path.join(lib_dir, "host", "calibration.cpp"), "-o", exe, "-L" + lib_dir, "-lvisgeom_b200",
+                           "-Wl,-rpath," + lib_dir])
+
+    def run(path):
+        r = subprocess.run([exe, path], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stderr
+        seq, glob, lines, i = {}, {}, r.stdout.splitlines(), 0
+        while i < len(lines):
+            w = lines[i].split()
+            if w and w[0] == "SEQ":
+                n = int(w[2])
+                seq[w[1]] = np.array([[float(x) for x in lines[i + 1 + k].split()] for k in range(n)])
+                i += 1 + n
+            elif w and w[0] == "GLOBAL":
+                glob[w[1]] = np.array([float(x) for x in lines[i + 1].split()])
+                i += 2
+            else:
+                i += 1
+        return seq, glob
+    return run
+
+
+def initial_grid(oracle, model, intr, board, corners, nx=9, ny=6):
+    """estimateInitialGrid's closed form (unified_calibration.cpp:1066-1130) restated in numpy on top of the oracle's
+    reconstructPoint: four outer corners back-projected, scaled by the board's edge lengths, an orthonormal basis."""
+    iUL, iUR, iBL, iBR = 0, nx - 1, nx * (ny - 1), nx * ny - 1
+    X = {}
+    for k, i in (("UL", iUL), ("UR", iUR), ("BL", iBL), ("BR", iBR)):
+        v, ok = oracle.reconstruct(model, intr, corners[i])
+        assert ok
+        X[k] = v / np.linalg.norm(v)
+    n = np.linalg.norm
+    sXU = n(board[iUR] - board[iUL]) / n(X["UR"] - X["UL"]); sXB = n(board[iBR] - board[iBL]) / n(X["BR"] - X["BL"])
+    sYL = n(board[iBL] - board[iUL]) / n(X["BL"] - X["UL"]); sYR = n(board[iBR] - board[iUR]) / n(X["BR"] - X["UR"])
+    pos = X["UL"] * min(sXU, sYL)
+    ex = X["UR"] * min(sXU, sYR) - pos
+    ey = X["BL"] * min(sXB, sYL) - pos
+    ex /= n(ex)
+    ey = ey - ex * ex.dot(ey)
+    ey /= n(ey)
+    R = np.stack([ex, ey, np.cross(ex, ey)], axis=1)
+    w = np.sqrt(1 + np.trace(R)) / 2                     # rotationVector(R): quaternion.h:52-59, then :84-98
+    q = np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]]) / (4 * w)
+    s = n(q)
+    return np.r_[pos, q / s * 2 * np.arctan2(s, w)]
+
+
+def test_initial_poses_follow_the_reference_closed_form(calib_probe, oracle, tmp_path):
+    path, d = mk.write_mono(str(tmp_path / "m"), 8, skip=(2,))
+    prob = json.load(open(path)); prob["data"][0]["parameters"] = ["do_not_solve"]; json.dump(prob, open(path, "w"))
+    seq, _ = calib_probe(path)
+    got = seq["xiCamBoard"]
+    assert got.shape == (8, 6)
+    for t in range(8):
+        if t == 2:
+            assert np.array_equal(got[t], [0, 0, 1, 0, 0, 0])           # no board extracted: the default stays (:456)
+            continue
+        want = initial_grid(oracle, sd.EUCM, d["intr_init"], d["board"], d["obs"][t].reshape(-1, 2))
+        assert np.abs(got[t] - want).max() < 1e-12
+    # with the true intrinsics the closed form is a starting point near the true poses (it scales the four corner rays by
+    # edge-length ratios, which is only approximate for a tilted board -- the solve that follows refines it)
+    prob["cameras"][0]["value"] = [float(v) for v in d["intr_gt"]]; json.dump(prob, open(path, "w"))
+    got = calib_probe(path)[0]["xiCamBoard"]
+    keep = [t for t in range(8) if t != 2]
+    assert np.abs(got[keep, 3:] - d["xi_gt"][keep, 3:]).max() < 0.5
+    assert np.abs(got[keep, :3] - d["xi_gt"][keep, :3]).max() < 0.25
+
+
+def test_global_transform_is_unwound_from_the_chain(calib_probe, oracle, tmp_path):
+    """Stereo layout without a prior on xiCam12: camera1's dataset initialises the board poses, camera2's dataset
+    initialises xiCam12 from its first image through getInitTransform (:311-348): chain [xiCam12 INVERSE, board DIRECT]
+    -> xiCam12 = (xi_cam2<-board o xi_cam1<-board^-1)^-1."""
+    path, s = mk.write_stereo(str(tmp_path / "s"), 5, prior=False)
+    prob = json.load(open(path))
+    for ds in prob["data"]:
+        ds["parameters"] = ["do_not_solve"]
+    json.dump(prob, open(path, "w"))
+    seq, glob = calib_probe(path)
+    b1 = seq["xiCamBoardStereo"]
+    for t in range(5):
+        want = initial_grid(oracle, sd.EUCM, s["intr1_init"], s["board"], s["obs1"][t].reshape(-1, 2))
+        assert np.abs(b1[t] - want).max() < 1e-12
+    g2 = initial_grid(oracle, sd.EUCM, s["intr2_init"], s["board"], s["obs2"][0].reshape(-1, 2))
+    x = oracle.compose(g2, b1[0], "compose_inverse")                     # xi o board^-1
+    R = oracle.rotation_matrix(-x[3:])
+    want = np.r_[-(R @ x[:3]), -x[3:]]                                   # Transformation::inverse, transformation.h:112-119
+    assert np.abs(glob["xiCam12"] - want).max() < 1e-12
