@@ -169,3 +169,33 @@ def test_global_transform_is_unwound_from_the_chain(calib_probe, oracle, tmp_pat
     R = oracle.rotation_matrix(-x[3:])
     want = np.r_[-(R @ x[:3]), -x[3:]]                                   # Transformation::inverse, transformation.h:112-119
     assert np.abs(glob["xiCam12"] - want).max() < 1e-12
+
+
+def test_json_reader_errors_and_value_forms(calib_probe, tmp_path):
+    """The Boost.PropertyTree reader the reference uses is replaced by visgeom_b200/host/json.hpp: numbers may come as
+    strings (ptree stores everything as text) and with exponents; malformed input, a missing key (ptree's wording) and
+    a missing file are reported."""
+    path, d = mk.write_mono(str(tmp_path / "j"), 3)
+    prob = json.load(open(path))
+    prob["data"][0]["parameters"] = ["do_not_solve"]
+    json.dump(prob, open(path, "w"))
+    base = calib_probe(path)[0]["xiCamBoard"]
+    prob["cameras"][0]["value"] = [str(v) for v in prob["cameras"][0]["value"]]       # numbers as strings
+    prob["cameras"][0]["value"][2] = "3.0e2"                                             # 300 with an exponent
+    p2 = tmp_path / "strings.json"
+    p2.write_text(json.dumps(prob))
+    assert np.array_equal(calib_probe(str(p2))[0]["xiCamBoard"], base)
+
+    def error_of(text):
+        p = tmp_path / "bad.json"
+        p.write_text(text)
+        with pytest.raises(AssertionError) as e:
+            calib_probe(str(p))
+        return str(e.value)
+    good = json.dumps(prob)
+    assert "JSON: " in error_of(good[:len(good) // 2])                                   # truncated
+    assert "JSON: " in error_of(good.replace(":", "=", 1))
+    del prob["cameras"][0]["type"]
+    assert "No such node (type)" in error_of(json.dumps(prob))
+    with pytest.raises(AssertionError, match="cannot open file"):
+        calib_probe(str(tmp_path / "missing.json"))
