@@ -46,6 +46,23 @@ P_CORNERS = 54
 ALGO_BYTES_PER_IMAGE = {"eucm": 54 * 224 + 680, "ucm": 54 * 208 + 632, "mei": 54 * 288 + 872}
 
 
+def out_bytes_per_image(model):
+    K = sd.NUM_PARAMS[{"eucm": sd.EUCM, "ucm": sd.UCM, "mei": sd.MEI}[model]]
+    W = K + 7
+    return 2 * P_CORNERS * 8 * (1 + K + 6) + W * (W + 1) // 2 * 8
+
+
+def bench_config(args):
+    """The workload both arms run (identical dict in the CUDA arm and in --impl reference)."""
+    n, P = args.images_per_gpu, P_CORNERS
+    return {"workload": f"monocular {args.model}, {args.gpus * n} synthetic images x {P} corners (9x6 board); step = residual + "
+                        "analytic Jacobian (Ceres layout, materialised) + per-image J^T J / J^T r + shared-block reduction",
+            "camera_model": args.model, "images_total": args.gpus * n, "images_per_gpu": n, "corners_per_image": P,
+            "sharding": "one global dataset (synthdata.make_mono, seed 20242), contiguous image range per GPU",
+            "l2": f"CUDA arm: {args.sets} rotating buffer sets, {args.sets * n * out_bytes_per_image(args.model) / 1e6:.0f} MB of "
+                  "outputs in flight (> 126 MB L2)"}
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -56,6 +73,8 @@ def parse_args():
     ap.add_argument("--model", default="eucm", choices=["eucm", "ucm", "mei"])
     ap.add_argument("--sets", type=int, default=4, help="rotating buffer sets (working set > L2)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline leg")
+    ap.add_argument("--c5-images-per-gpu", type=int, default=25000,
+                    help="at --gpus 8 the C5 workload (200 000 images) is measured too; 0 disables")
     return ap.parse_args()
 
 
@@ -194,14 +213,14 @@ def run_reference(args):
     budget_s = 150.0
     per_step = max(200, min(n_img, int(rate * budget_s / max(1, args.steps + args.warmup) / d["P"])))
     res = cpu_reference_leg(d, model_id, per_step, args.steps, args.warmup)
-    total_imgs = n_img * args.gpus
     line = {
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * res["seconds"] / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"monocular {args.model}, {total_imgs} synthetic images x {d['P']} corners (9x6 board), "
-                               f"residual + analytic Jacobian + normal-equation build per step",
-                   "images_per_step": per_step, "cpu_threads": res["cores"]},
+        "config": bench_config(args),
+        "details": {"images_per_step": per_step, "cpu_threads": res["cores"],
+                    "what": "the reference's own calib_cost_functions.cpp + headers (oracle/_ref), OpenMP over images; "
+                            "each step a bounded sample of the workload"},
         "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": res["kind"], "sample": res["sample"]},
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -240,6 +259,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from visgeom_b200 import build as vg_build
+    from visgeom_b200.sharding import shard_range
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -254,13 +274,13 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     model_id = {"eucm": sd.EUCM, "ucm": sd.UCM, "mei": sd.MEI}[args.model]
-    n_img, P = args.images_per_gpu, P_CORNERS
-    d = sd.make_mono(model_id, n_img, seed=20242 + rank)
-    K = d["K"]
+    P = P_CORNERS
+    K = sd.NUM_PARAMS[model_id]
     stream = torch.cuda.Stream(device=dev)
     sampler = ClockSampler(local)
     windows = []
     launches0 = vg.launch_count()
+    failures = []
 
     def barrier():
         torch.cuda.synchronize()
@@ -281,7 +301,7 @@ def run_ours(args):
         """N > 1: the cross-rank sum of the reduced normal equations.  Default: the engine's own exchange over peer
         memory inside the kernel that assembles them (NVLink / NVSwitch; torch.distributed only carries the CUDA IPC
         handles at set-up).  VG_BENCH_NCCL=1: an NCCL all-reduce per evaluation through a callback instead."""
-        if world == 1 or os.environ.get("VG_BENCH_NOCOLL") == "1":     # (diagnosis: ranks left unconnected)
+        if world == 1:
             return
         if not state["nccl"]:
             ok = 1
@@ -322,86 +342,163 @@ def run_ours(args):
                 dist.all_reduce(t)
         Pm.set_allreduce(allreduce, rank, world)
 
-    def make_gpu_problem():
-        Pm = vg.Problem(local)
-        attach_allreduce(Pm)
-        return Pm
-
-    # ---- NSETS problems (own device buffers each) sharing one stream: working set > L2 -------
-    probs, ds_ids, tr_ids, cam_ids = [], [], [], []
-    for s in range(args.sets):
+    def new_problem(d, connect=True, materialize=False):
         Pm = vg.Problem(local)
         cam = Pm.add_camera(model_id, d["intr_init"])
         tr = Pm.add_transform(d["xi_init"], is_global=False)
         ds = Pm.add_dataset(cam, d["board"], d["obs"], [tr], [0])
-        Pm.materialize_jacobians(True)
-        Pm.set_stream(stream.cuda_stream)
-        attach_allreduce(Pm)
-        probs.append(Pm); ds_ids.append(ds); tr_ids.append(tr); cam_ids.append(cam)
-    ks = probs[0].evaluate(want_reduced=True)[1].size
-    out_bytes = n_img * (2 * P * 8 * (1 + K + 6) + vg.hessian_entries(model_id, 1) * 8)
+        if materialize:
+            Pm.materialize_jacobians(True)
+        if connect:
+            attach_allreduce(Pm)
+        return Pm, cam, tr, ds
+
+    def shard_of(d_all, n_total):
+        lo, hi = shard_range(n_total, rank, world)
+        d = dict(d_all)
+        d["obs"] = np.ascontiguousarray(d_all["obs"][lo:hi]); d["xi_init"] = np.ascontiguousarray(d_all["xi_init"][lo:hi])
+        d["n_img"] = hi - lo
+        return d
+
+    peak, peak_src = measured_peak()
+
+    def exchange_check(d, d_all):
+        """N > 1, outside every timed region: what the in-kernel peer exchange produced (deferred mode: posted by the
+        kernel's tail, collected by the next launch / the fetch; synchronous mode: posted and collected by the same
+        CTA) against (i) an NCCL all-reduce of every rank's LOCAL reduced block and (ii) one GPU evaluating the whole
+        global dataset."""
+        loc, *_ = new_problem(d, connect=False)
+        c_loc, r_loc = loc.evaluate(want_reduced=True)
+        t = torch.from_numpy(np.concatenate([[c_loc], r_loc.ravel()])).to(dev)
+        dist.all_reduce(t)
+        want = t.cpu().numpy()
+        res = {"modes": {}, "transport": "nccl callback" if state["nccl"] else "peer memory, in kernel"}
+        worst, identical = 0.0, True
+        for mode in ("deferred", "synchronous"):
+            ex, *_ = new_problem(d)
+            for rep in range(3):             # the third exchange reuses a slot parity
+                if mode == "deferred":
+                    ex.evaluate_async()
+                    c, r = ex.fetch_reduced()
+                else:
+                    c, r = ex.evaluate(want_reduced=True)
+            got = np.concatenate([[c], r.ravel()])
+            rel = float(np.abs(got - want).max() / np.abs(want).max())
+            mine = torch.from_numpy(got.copy()).to(dev)
+            every = torch.empty(world * mine.numel(), dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(every, mine)
+            ev = every.cpu().numpy().reshape(world, -1)
+            same = bool((ev.view(np.uint64) == ev.view(np.uint64)[0]).all())
+            res["modes"][mode] = {"max_rel_vs_nccl_allreduce_of_local_blocks": rel, "bit_identical_across_ranks": same}
+            worst, identical = max(worst, rel), identical and same
+            ex.close()
+        res["max_rel"], res["bit_identical_across_ranks"] = worst, identical
+        # (ii) the same images on ONE GPU (rank 0): the N-GPU problem is a sharding of one dataset
+        g_rel = None
+        if rank == 0:
+            glob, *_ = new_problem(d_all, connect=False)
+            c_g, r_g = glob.evaluate(want_reduced=True)
+            full = np.concatenate([[c_g], r_g.ravel()])
+            g_rel = float(np.abs(full - want).max() / np.abs(full).max())
+            res["global_cost_one_gpu"], res["global_cost_n_gpus"] = float(c_g), float(want[0])
+            glob.close()
+        res["max_rel_vs_one_gpu_on_all_images"] = g_rel
+        loc.close()
+        ok = worst <= 1e-12 and identical and (g_rel is None or g_rel <= 1e-12)
+        res["ok"] = bool(ok)
+        if not ok:
+            failures.append(f"exchange check failed: {res}")
+        return res
+
+    def measure(n_img, steps, warmup, with_check):
+        """device-resident step, the kernel alone and (N > 1) the exchange check for n_img images per GPU"""
+        n_total = world * n_img
+        d_all = sd.make_mono(model_id, n_total, seed=20242)
+        d = shard_of(d_all, n_total)
+        # ---- NSETS problems (own device buffers each) sharing one stream: working set > L2 -------
+        probs, ds_ids, tr_ids, cam_ids = [], [], [], []
+        for s_ in range(args.sets):
+            Pm, cam, tr, ds = new_problem(d, materialize=True)
+            Pm.set_stream(stream.cuda_stream)
+            probs.append(Pm); ds_ids.append(ds); tr_ids.append(tr); cam_ids.append(cam)
+        ks = probs[0].evaluate(want_reduced=True)[1].size
+        # ---- leg 1: device-resident steps (value) ---------------------------------------------------
+        with torch.cuda.stream(stream):
+            for i in range(warmup):
+                probs[i % args.sets].evaluate_async()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0 = vg.launch_count()
+            t_w0 = time.time()
+            e0.record(stream)
+            for i in range(steps):
+                probs[i % args.sets].evaluate_async()
+            e1.record(stream)
+            barrier()
+            windows.append((t_w0, time.time()))
+            step_ms = max_over_ranks(e0.elapsed_time(e1) / steps)
+            launches_per_step = (vg.launch_count() - l0) / steps
+        cost, red = probs[(steps - 1) % args.sets].fetch_reduced()
+        # the timed region above lasts only tens of milliseconds; keep the same step running for about a
+        # second so that nvidia-smi (20 ms period) sees the clocks and throttle reasons under this load
+        with torch.cuda.stream(stream):
+            t_w0 = time.time()
+            while time.time() - t_w0 < 1.0:
+                for i in range(200):
+                    probs[i % args.sets].evaluate_async()
+                torch.cuda.synchronize()
+            windows.append((t_w0, time.time()))
+        barrier()
+        # ---- leg 2: the dominant kernel alone (roofline), same buffers, launched back to back -------
+        bufs = []
+        for s_ in range(args.sets):
+            Pm = probs[s_]
+            bufs.append(dict(obs=Pm.device_buffer(ds_ids[s_], -1)[0], r=Pm.device_buffer(ds_ids[s_], 0)[0],
+                             Ja=Pm.device_buffer(ds_ids[s_], 1)[0], Je=Pm.device_buffer(ds_ids[s_], 2)[0],
+                             H=Pm.device_buffer(ds_ids[s_], -2)[0]))
+        t_intr = torch.from_numpy(d["intr_init"]).to(dev)
+        t_board = torch.from_numpy(d["board"]).to(dev)
+        t_xi = torch.from_numpy(d["xi_init"]).to(dev)
+
+        def kernel_only(s_):
+            b = bufs[s_]
+            vg.eval_chain_dev(model_id, t_intr.data_ptr(), t_board.data_ptr(), b["obs"], [t_xi.data_ptr()], [0], [0],
+                              n_img, P, r=b["r"], J_intr=b["Ja"], J_xi=[b["Je"]], H=b["H"], stream=stream.cuda_stream)
+        with torch.cuda.stream(stream):
+            for i in range(max(3, warmup)):
+                kernel_only(i % args.sets)
+            torch.cuda.synchronize()
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t_w0 = time.time()
+            k0.record(stream)
+            for i in range(steps):
+                kernel_only(i % args.sets)
+            k1.record(stream)
+            torch.cuda.synchronize()
+            windows.append((t_w0, time.time()))
+            kernel_us = k0.elapsed_time(k1) * 1e3 / steps
+        algo_bytes = ALGO_BYTES_PER_IMAGE[args.model] * n_img
+        achieved = algo_bytes / (kernel_us * 1e-6) / 1e9
+        step_gbs = algo_bytes / (step_ms * 1e-3) / 1e9
+        out = {"value": n_total * P / (step_ms * 1e-3), "ms_per_step": step_ms, "images_per_gpu": n_img, "images_total": n_total,
+               "launches_per_step": launches_per_step, "cost": cost, "shared_block_doubles": int(ks),
+               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                            "traffic": recorded_traffic(args.model, n_img),
+                            "traffic_note": "bytes per launch from profiles/traffic.json (ncu --set full); below the algorithmic "
+                                            "bytes when the 126 MB L2 still holds part of the outputs as the kernel ends",
+                            "kernel": "reproj_eval_kernel", "kernel_us": kernel_us,
+                            "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src,
+                            # the same bytes over the whole device-timed step (kernel + fused reduction tail + exchange)
+                            "step_achieved": step_gbs, "step_frac": step_gbs / peak}}
+        if world > 1 and with_check:
+            out["exchange_check"] = exchange_check(d, d_all)
+        return out, d, probs, (ds_ids, tr_ids, cam_ids)
+
     sampler.start()
     time.sleep(0.3)
-
-    # ---- leg 1: device-resident steps (value) ---------------------------------------------------
-    with torch.cuda.stream(stream):
-        for i in range(args.warmup):
-            probs[i % args.sets].evaluate_async()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = vg.launch_count()
-        t_w0 = time.time()
-        e0.record(stream)
-        for i in range(args.steps):
-            probs[i % args.sets].evaluate_async()
-        e1.record(stream)
-        barrier()
-        windows.append((t_w0, time.time()))
-        step_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
-        launches_per_step = (vg.launch_count() - l0) / args.steps
-    cost, red = probs[(args.steps - 1) % args.sets].fetch_reduced()
-    value = world * n_img * P / (step_ms * 1e-3)
-    # the timed region above lasts only tens of milliseconds; keep the same step running for about a
-    # second so that nvidia-smi (20 ms period) sees the clocks and throttle reasons under this load
-    with torch.cuda.stream(stream):
-        t_w0 = time.time()
-        while time.time() - t_w0 < 1.0:
-            for i in range(200):
-                probs[i % args.sets].evaluate_async()
-            torch.cuda.synchronize()
-        windows.append((t_w0, time.time()))
-
-    # ---- leg 2: the dominant kernel alone (roofline), same buffers, launched back to back -------
-    bufs = []
-    for s in range(args.sets):
-        Pm = probs[s]
-        bufs.append(dict(obs=Pm.device_buffer(ds_ids[s], -1)[0], r=Pm.device_buffer(ds_ids[s], 0)[0],
-                         Ja=Pm.device_buffer(ds_ids[s], 1)[0], Je=Pm.device_buffer(ds_ids[s], 2)[0],
-                         H=Pm.device_buffer(ds_ids[s], -2)[0]))
-    t_intr = torch.from_numpy(d["intr_init"]).to(dev)
-    t_board = torch.from_numpy(d["board"]).to(dev)
-    t_xi = torch.from_numpy(d["xi_init"]).to(dev)
-
-    def kernel_only(s):
-        b = bufs[s]
-        vg.eval_chain_dev(model_id, t_intr.data_ptr(), t_board.data_ptr(), b["obs"], [t_xi.data_ptr()], [0], [0],
-                          n_img, P, r=b["r"], J_intr=b["Ja"], J_xi=[b["Je"]], H=b["H"], stream=stream.cuda_stream)
-    with torch.cuda.stream(stream):
-        for i in range(max(3, args.warmup)):
-            kernel_only(i % args.sets)
-        torch.cuda.synchronize()
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t_w0 = time.time()
-        k0.record(stream)
-        for i in range(args.steps):
-            kernel_only(i % args.sets)
-        k1.record(stream)
-        torch.cuda.synchronize()
-        windows.append((t_w0, time.time()))
-        kernel_us = k0.elapsed_time(k1) * 1e3 / args.steps
-    peak, peak_src = measured_peak()
-    algo_bytes = ALGO_BYTES_PER_IMAGE[args.model] * n_img
-    achieved = algo_bytes / (kernel_us * 1e-6) / 1e9
+    n_img = args.images_per_gpu
+    main, d, probs, (ds_ids, tr_ids, cam_ids) = measure(n_img, args.steps, args.warmup, True)
+    ks = main["shared_block_doubles"]
 
     # ---- leg 3: end to end through the problem API with HOST buffers ---------------------------
     # per step: pinned host -> device copy of that step's observations, poses and intrinsics, the same
@@ -440,6 +537,9 @@ def run_ours(args):
     e2e_s = max_over_ranks((time.perf_counter() - t0) / n_e2e)
     windows.append((t_w0, time.time()))
     e2e_value = world * n_img * P / e2e_s
+    for Pm in probs:
+        Pm.close()
+    probs = []
 
     # the inner (Ceres cost-function) contract end to end: r and every Jacobian block back on the host
     full_value = None
@@ -452,8 +552,12 @@ def run_ours(args):
             vg.eval_chain(model_id, d["intr_init"], d["board"], d["obs"], xs, [0], [0], want_H=True)
         full_value = n_img * P * reps / (time.perf_counter() - t0)
 
-    # ---- LM iterations/s: one vg_problem_solve of the whole C2 problem (host inputs, parameters back) --------
-    # With N GPUs every rank solves the one problem made of all ranks' images (its own shard + the all-reduces).
+    # ---- LM iterations/s: one vg_problem_solve of the whole problem (host inputs, parameters back) --------
+    # With N GPUs every rank solves the one problem made of all ranks' images (its own shard + the exchanges).
+    def make_gpu_problem():
+        Pm = vg.Problem(local)
+        attach_allreduce(Pm)
+        return Pm
     barrier()
     lm_leg(make_gpu_problem, d, model_id, 3)          # warm-up (allocations, first launches)
     barrier()
@@ -462,6 +566,32 @@ def run_ours(args):
     windows.append((t_w0, time.time()))
     lm["seconds"] = max_over_ranks(lm["seconds"])
     lm["iters_per_s"] = lm["iterations"] / lm["seconds"]
+    if world > 1:
+        # every rank must have walked the same trajectory to the same parameters, bit for bit
+        mine = torch.tensor(lm["intrinsics"] + [lm["final_cost"]], dtype=torch.float64, device=dev)
+        every = torch.empty(world * mine.numel(), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(every, mine)
+        ev = every.cpu().numpy().reshape(world, -1)
+        lm["bit_identical_across_ranks"] = bool((ev.view(np.uint64) == ev.view(np.uint64)[0]).all())
+        if not lm["bit_identical_across_ranks"] or not np.isfinite(ev).all():
+            failures.append("LM: ranks disagree on the solution")
+
+    # ---- C5 (BASELINE.json configs[4]): 200 000 images over 8 GPUs, 25 000 per GPU ----------------------
+    c5 = None
+    if (world == 8 or os.environ.get("VG_BENCH_C5") == "1") and args.c5_images_per_gpu > 0 and args.c5_images_per_gpu != n_img:
+        barrier()
+        c5, d5, probs5, _ = measure(args.c5_images_per_gpu, max(10, args.steps), max(3, args.warmup), True)
+        for Pm in probs5:
+            Pm.close()
+        barrier()
+        lm_leg(make_gpu_problem, d5, model_id, 3)
+        barrier()
+        lm5 = lm_leg(make_gpu_problem, d5, model_id, 25)
+        lm5["seconds"] = max_over_ranks(lm5["seconds"])
+        c5["lm"] = {"iters_per_s": lm5["iterations"] / lm5["seconds"], "iterations": lm5["iterations"],
+                    "final_cost": lm5["final_cost"], "intrinsics": lm5["intrinsics"]}
+        c5["workload"] = (f"monocular {args.model}, {c5['images_total']} synthetic images x {P} corners over {world} GPUs "
+                          f"({c5['images_per_gpu']} per GPU): BASELINE.json configs[4]")
 
     sampler.stop()
     clocks = sampler.summary(windows)
@@ -489,29 +619,21 @@ def run_ours(args):
         cpu["lm"] = {"iters_per_s": cpu_lm["iters_per_s"], "images": n_lm, "iterations": cpu_lm["iterations"],
                      "cores": orc.max_threads(),
                      "iters_per_s_scaled_to_workload": cpu_lm["iters_per_s"] * n_lm / n_img if cpu_lm["iters_per_s"] else None,
-                     "kind": "port", "what": "oracle LM (restated Ceres trust-region loop), OpenMP evaluation"}
+                     "kind": "port", "what": "oracle LM (restated Ceres trust-region loop, not Ceres itself), OpenMP evaluation"}
 
     if rank == 0:
+        collective = None if world == 1 else ("nccl all-reduce callback" if state["nccl"] else
+                                              "peer memory over NVLink, fused into the evaluation kernel (posted by the "
+                                              "kernel's tail, summed by the head of the problem's next launch)")
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"monocular {args.model}, {world * n_img} synthetic images x {P} corners (9x6 board); "
-                                   "step = fused residual + analytic Jacobian (Ceres layout, written to HBM) + per-image "
-                                   "J^T J/J^T r + shared-block reduction" +
-                                   ("" if world == 1 else " + NCCL all-reduce of the shared block" if state["nccl"] else
-                                    " + exchange of the shared block over NVLink peer memory (posted by the kernel's tail, summed by the "
-                                    "head of the problem's next launch)"),
-                       "images_per_gpu": n_img, "corners_per_image": P, "model": None,
-                       "collective": None if world == 1 else ("nccl" if state["nccl"] else "peer-memory, fused into the evaluation kernel (post in the tail, collect in the next launch's head)"),
-                       "l2": f"{args.sets} rotating buffer sets, {args.sets * out_bytes / 1e6:.0f} MB of outputs in flight (> 126 MB L2)",
-                       "cost_check": cost},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": recorded_traffic(args.model, n_img),
-                         "traffic_note": "bytes per launch from profiles/traffic.json (ncu --set full); below the algorithmic "
-                                         "bytes because the 126 MB L2 still holds part of the ~120 MB of outputs when the kernel ends",
-                         "kernel": "reproj_eval_kernel", "kernel_us": kernel_us,
-                         "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src},
+            "config": bench_config(args),
+            "details": {"collective": collective, "cost_check": main["cost"],
+                        "solver_parity": "LM parity is pinned against a restatement of Ceres' trust-region loop "
+                                         "(oracle/oracle_lm.c) and scipy, not against Ceres itself (absent here)"},
+            "roofline": main["roofline"],
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s * 1e3,
@@ -520,18 +642,30 @@ def run_ours(args):
                                    "what": "vg_eval_chain with host buffers: r, J_intr, J_pose and H copied back (PCIe bound)"},
             "lm": None if lm is None else {"iters_per_s": lm["iters_per_s"], "iterations": lm["iterations"], "seconds": lm["seconds"],
                                            "final_cost": lm["final_cost"], "intrinsics": lm["intrinsics"],
+                                           "bit_identical_across_ranks": lm.get("bit_identical_across_ranks"),
                                            "what": "vg_problem_solve on the same workload from the perturbed initial guess "
                                                    "(one LM iteration = evaluation + per-pose Schur elimination + shared solve + "
                                                    "back-substitution + candidate evaluation)"},
-            "gpu_launches": int(round(launches_per_step * args.steps)), "gpu_launches_per_step": launches_per_step,
+            "gpu_launches": int(round(main["launches_per_step"] * args.steps)), "gpu_launches_per_step": main["launches_per_step"],
             "gpu_launches_total": int(total_launches),
             "clocks": clocks,
         }
-        del line["config"]["model"]
+        if "exchange_check" in main:
+            line["exchange_check"] = main["exchange_check"]
+        if c5 is not None:
+            line["c5"] = c5
+        if failures:
+            line["failures"] = failures
         print(json.dumps(line), flush=True)
     if world > 1:
+        bad = torch.tensor([len(failures)], dtype=torch.int32, device=dev)
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
         dist.barrier()
         dist.destroy_process_group()
+        if int(bad.item()):
+            raise SystemExit(3)
+    elif failures:
+        raise SystemExit(3)
 
 
 def main():

@@ -12,9 +12,7 @@ import synthdata as sd
 import visgeom_b200 as vg
 
 PHASED = True
-NAMES = [["0 pose+bar", "A corner", "A barrier", "S tma issue", "B gram", "B barrier", "H out", "tma wait+bar"]] * 2 if PHASED else [
-    ["pose", "obs wait", "corners", "tma issue", "gram", "H store", "tma read wait", "-"],
-    ["-", "-", "-", "-", "-", "-", "-", "-"]]
+NAMES = [["A corner", "H wait+fence", "B2 barrier", "S/B tma,gram", "B3 barrier", "H out", "-", "-"]] * 2
 
 
 def main():
@@ -49,7 +47,7 @@ def main():
     L.vg_debug_phase_clocks(out, 1)
     v = np.array(list(out), dtype=np.float64).reshape(2, 8) / reps
     grid = 592 if PHASED else 148
-    for w, nm in ((0, "Gram warp 0"), (1, "last warp" if PHASED else "corner warp 0")):
+    for w, nm in ((0, "warp 0 (Gram)"), (1, "last warp (TMA issue, poses)")):
         tot = v[w].sum()
         print(f"{nm}: {tot / grid:9.0f} cycles per CTA")
         for i in range(8):

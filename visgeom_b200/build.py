@@ -19,7 +19,9 @@ OBJ = os.path.join(HERE, "_obj" + ("_" + VARIANT if VARIANT else ""))
 
 SOURCES = ["vg_eval_eucm.cu", "vg_eval_ucm.cu", "vg_eval_mei.cu", "vg_eval.cu", "vg_api.cu", "vg_solver_kernels.cu",
            "vg_problem.cu", "vg_priors.cu"]
-HEADERS = ["vg_math.cuh", "vg_eval.cuh", "vg_eval_impl.cuh", "vg_gram.cuh", "vg_common.h", "vg_solver_kernels.cuh", "vg_priors.cuh", "../../include/visgeom_b200.h"]
+# every header of csrc/ is a dependency of every object (a stale object with a mismatched cross-rank protocol or
+# argument struct would load silently)
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + ["../../include/visgeom_b200.h"]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

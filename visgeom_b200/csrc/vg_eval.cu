@@ -2,6 +2,8 @@
 // (the kernels themselves: vg_eval_impl.cuh, instantiated per model in vg_eval_{eucm,ucm,mei}.cu).
 #include "vg_eval.cuh"
 
+#include <cstdlib>
+
 
 namespace vg {
 
@@ -26,7 +28,7 @@ static long long smem_any(int model, int L, int G, int P, int PCG)
 }
 
 // G images per group (G*P <= 256 so that one corner pass covers a group; at most 8: one
-// normal-equation warp per image), PCG groups per pose prologue (about 6 KB of pose records).
+// normal-equation warp per image), PCG groups per pose prologue (about 4.5 KB of pose records).
 bool plan_eval(int model, int L, int P, LaunchPlan *pl)
 {
     if (P < 1 || L < 1 || L > MAX_CHAIN) return false;
@@ -37,8 +39,10 @@ bool plan_eval(int model, int L, int P, LaunchPlan *pl)
         int t = ((G * P + 31) / 32) * 32;
         if (t < 96) t = 96;
         if (t > 224) t = 224;   // __launch_bounds__ of the kernel
-        int pcg = (6 * 1024) / (pose_doubles * 8 * G);
-        if (pcg * G > t) pcg = t / G;
+        int pcg = 5632 / (pose_doubles * 8 * G);
+        if (pcg * G > 32) pcg = 32 / G;     // one warp restages a batch of poses (G <= 4)
+        static const int pcg_env = [] { const char *e = getenv("VG_PCG"); return e ? atoi(e) : 0; }();   // developer knob
+        if (pcg_env > 0 && pcg_env * G <= 32) pcg = pcg_env;
         if (pcg < 1) pcg = 1;
         long long b = smem_any(model, L, G, P, pcg);
         if (b < 0) return false;

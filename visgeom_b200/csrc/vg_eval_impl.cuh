@@ -29,6 +29,7 @@
 // not applicable (no FP64 there); the only matrix-unit use is the legacy FP64 mma.sync above.
 #pragma once
 #include <cstdlib>
+#include <cstring>
 #include "vg_eval.cuh"
 #include "vg_math.cuh"
 
@@ -50,15 +51,24 @@ __device__ __forceinline__ long long vg_clock()
 }
 #define VG_PC_DECL long long pc_t = vg_clock(); unsigned long long pc_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #define VG_PC(i) { const long long pc_n = vg_clock(); pc_acc[i] += (unsigned long long)(pc_n - pc_t); pc_t = pc_n; }
-#define VG_PC_FLUSH(row) if (lane == 0) for (int i_ = 0; i_ < 8; i_++) atomicAdd(&g_phase_clocks[row][i_], pc_acc[i_]);
+#define VG_PC_FLUSH_ALL if (lane == 0 && (warp == 0 || warp == nw - 1)) for (int i_ = 0; i_ < 8; i_++) atomicAdd(&g_phase_clocks[warp == 0 ? 0 : 1][i_], pc_acc[i_]);
 #else
 #define VG_PC_DECL
 #define VG_PC(i)
-#define VG_PC_FLUSH(row)
+#define VG_PC_FLUSH_ALL
 #endif
 
 struct LaunchPlan { int G, threads, PCG; long long smem; };
 bool plan_eval(int model, int L, int P, LaunchPlan *pl);
+// the launch plan's sizes as functions of the board (shared with plan_eval, vg_eval.cu; shared-memory limits may
+// still lower them there -- launch_one checks before it picks a kernel with the board compiled in)
+__host__ __device__ constexpr int plan_group(int P) { return 4 * P <= 224 ? 4 : (2 * P <= 224 ? 2 : 1); }
+__host__ __device__ constexpr int plan_pcg(int pose_doubles, int G)
+{
+    int pcg = 5632 / (pose_doubles * 8 * G);
+    if (pcg * G > 32) pcg = 32 / G;
+    return pcg < 1 ? 1 : pcg;
+}
 
 namespace {
 
@@ -116,7 +126,8 @@ template <int MODEL, int L> struct Layout {
     using map_t = std::conditional_t<(NE <= 127), char2, short2>;
     static constexpr int PNB = (K - 4 + 3 + 6 * L + 7) / 8;                   // 8-column blocks of the parity Gram
     static constexpr int MAPD = (PNB * (PNB + 1) / 2 * 2 * 32 * (int)sizeof(map_t) + 7) / 8;   // doubles (upper bound)
-    static constexpr int TAIL = 64 > MAPD ? 64 : MAPD;
+    static constexpr int TAIL = MAPD;
+    static constexpr int CAMD = 14;               // intrinsics (<= 10) + Camera::Consts (<= 4) in shared memory
     // doubles of shared memory: poses of PCG groups + staging of one group of G images + packed blocks
     __host__ __device__ static constexpr long long smem_doubles(int G, int P, int PCG)
     {
@@ -124,7 +135,8 @@ template <int MODEL, int L> struct Layout {
         //   lane); the ragged last k-step of the Gram loop also reads (and discards) up to three corners past the
         //   last image, into this area
         // ... + the observations of the CTA's next group (G x P x 2)
-        return 2 + (long long)PCG * G * POSE + (long long)G * 2 * P * (1 + K + 6 * L) + 2 + round_up2(G * NE) + TAIL +
+        // ... + the camera's parameters and constants (CAMD)
+        return 2 + CAMD + (long long)PCG * G * POSE + (long long)G * 2 * P * (1 + K + 6 * L) + 2 + round_up2(G * NE) + TAIL +
                (long long)G * 2 * P;
     }
 };
@@ -145,11 +157,12 @@ __device__ __forceinline__ void store_row(double *p, const double (&a)[N], bool 
 // Shared-memory view of the staged group
 template <int MODEL, int L> struct Stage {
     using LY = Layout<MODEL, L>;
-    double *pose, *rs, *Jas, *Jes[L], *Hs, *zero, *obuf;
+    double *pose, *rs, *Jas, *Jes[L], *Hs, *zero, *obuf, *cam;
     typename LY::map_t *map;
     __device__ Stage(double *base, int G, int P, int PCG)
     {
         zero = base;            base += 2;                 // two zeros for the Gram padding columns
+        cam = base;             base += LY::CAMD;          // intrinsics, then the model's per-launch constants
         pose = base;            base += (size_t)PCG * G * LY::POSE;
         rs = base;              base += (size_t)G * 2 * P;
         Jas = base;             base += (size_t)G * 2 * P * LY::K;
@@ -192,6 +205,8 @@ template <int MODEL, int L> __host__ __device__ constexpr bool use_parity_gram()
 // Column c of [J r]: c < K intrinsic block, then 6 columns per chain element, then the residual.
 // Fragment layout of mma.m8n8k4.f64: lane l feeds A[i = l>>2][k = l&3] and B[k = l&3][j = l>>2], so
 // for G = R^T R both are R[k0 + (l&3)][8 b + (l>>2)]; it receives C[l>>2][2 (l&3) + {0,1}].
+// (Splitting an image's tiles over several warps was measured and lost: the phase is bound by the FP64 pipe of
+// the warp's SM sub-partition, 16 cycles per DMMA, and a CTA's images already sit on all four of them.)
 template <int MODEL, int L>
 __device__ __forceinline__ void gram_image(const Stage<MODEL, L> &st, const int g, const int lane, const int P)
 {
@@ -356,7 +371,7 @@ __device__ __forceinline__ unsigned int take_ticket(unsigned int *counter)
 }
 
 template <int NE>
-__device__ __forceinline__ void fused_reduce(const EvalArgs &args)
+__device__ __forceinline__ void fused_reduce(const EvalArgs &args, double *scratch, const int scratch_cap)
 {
     __shared__ int s_last;
     const int tid = threadIdx.x, rows = gridDim.x;
@@ -405,29 +420,81 @@ __device__ __forceinline__ void fused_reduce(const EvalArgs &args)
     // several GPUs: the same CTA exchanges the reduced system with its peers over NVLink (vg_peer.cuh)
     if (args.peer.n > 1) {
         if (args.peer_deferred) peer_post(args.red, args.peer_count, args.peer);
-        else peer_allreduce(args.red, args.peer_count, args.peer);
+        else peer_allreduce(args.red, args.peer_count, args.peer, scratch, scratch_cap);
+    }
+}
+
+// ---- phase A stores ---------------------------------------------------------------------
+// A corner's two rows (u, v) of a block are 2 N contiguous doubles, the corners of a warp 2 N doubles apart.  Written
+// row by row with 16-byte stores, lanes l and l + 4 of a quarter-warp would hit the same banks when N / 2 is odd
+// (96-byte and 160-byte corner strides: only the even 16-byte bank groups are used).  The lanes with bit 2 set
+// therefore store their v-row first and their u-row second: the quarter-warp then covers all eight bank groups in
+// every store instruction.  N odd (UCM): the 2 N doubles go out as N 16-byte stores across the row boundary (corner
+// stride N x 16 bytes, N odd: conflict free as it is).
+template <int N>
+__device__ __forceinline__ void store_pair(double *p, const double (&a)[N], const double (&b)[N], const bool hi)
+{
+    if constexpr ((N & 1) == 0) {
+        double *pf = p + (hi ? N : 0), *ps = p + (hi ? 0 : N);
+#pragma unroll
+        for (int i = 0; i < N; i += 2)
+            *reinterpret_cast<double2 *>(pf + i) = make_double2(hi ? b[i] : a[i], hi ? b[i + 1] : a[i + 1]);
+#pragma unroll
+        for (int i = 0; i < N; i += 2)
+            *reinterpret_cast<double2 *>(ps + i) = make_double2(hi ? a[i] : b[i], hi ? a[i + 1] : b[i + 1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i + 1 < N; i += 2) *reinterpret_cast<double2 *>(p + i) = make_double2(a[i], a[i + 1]);
+        *reinterpret_cast<double2 *>(p + N - 1) = make_double2(a[N - 1], b[0]);
+#pragma unroll
+        for (int i = 1; i + 1 < N; i += 2) *reinterpret_cast<double2 *>(p + N + i) = make_double2(b[i], b[i + 1]);
     }
 }
 
 // ---- the kernel -------------------------------------------------------------------
-// PCG = groups whose poses one prologue pass stages (PCG * G <= blockDim.x).
+// CTA b owns the image groups b, b + gridDim.x, ... (static, hence deterministic); a group is G consecutive images,
+// PCG groups share one batch of staged poses (PCG * G <= 32: one warp restages them).  Per group, two CTA barriers:
+//   A   corner phase: camera model, residual / Jacobian rows -> staging area
+//   B2
+//   S   the last warp: TMA bulk stores of the staged blocks; the poses of the next batch when this group is the last of
+//       its batch; then it waits until the copies have read the staging area -- all of it while the other warps are
+//       in the Gram phase, so nobody waits for these
+//   B   one warp per image: Gram matrix on the FP64 MMA path
+//   B3
+//   H   packed blocks: TMA bulk store (its read is awaited before the next B2), per-CTA running sums
+// (Measured and rejected on the way, see DESIGN.md: contiguous image ranges per CTA, an mbarrier in place of a
+// barrier for "staging free", an image's Gram tiles spread over several warps.)
 #ifndef VG_WIDE_BLOCKS
 #define VG_WIDE_BLOCKS 2
 #endif
-template <int MODEL, int L>
+// developer switches (A/B builds through VG_EXTRA_FLAGS; the defaults are the product)
+#ifndef VG_SWAP_STORES
+#define VG_SWAP_STORES 1      // store_pair's bank-conflict-free order
+#endif
+#ifndef VG_CAM_SMEM
+#define VG_CAM_SMEM 1         // camera parameters read from shared memory in the corner phase (0: kept in registers)
+#endif
+// PC > 0: the board's point count is compiled in (with the images per group and the pose batch the launch plan picks
+// for it: plan_group / plan_pcg), so that the index arithmetic of the corner phase and every shared-memory offset
+// are constants; PC == 0: any board, sizes at run time.
+template <int MODEL, int L, int PC>
 __global__ void __launch_bounds__(224, (L == 1 && Camera<MODEL>::K <= 6) ? 4 : (L == 1 ? VG_WIDE_BLOCKS : 2))
-reproj_eval_kernel(const EvalArgs args, const int G, const int PCG)
+reproj_eval_kernel(const EvalArgs args, const int G_rt, const int PCG_rt)
 {
     using LY = Layout<MODEL, L>;
     using CAM = Camera<MODEL>;
     constexpr int K = LY::K;
     extern __shared__ __align__(16) double smem[];
-    const int P = args.P;
+    const int P = PC ? PC : args.P;
+    const int G = PC ? plan_group(PC) : G_rt;
+    const int PCG = PC ? plan_pcg(LY::POSE, plan_group(PC)) : PCG_rt;
     const Stage<MODEL, L> st(smem, G, P, PCG);
     const int tid = threadIdx.x;
-    const int n_groups = (args.n_img + G - 1) / G;
     // the warp index through a shuffle: provably warp-uniform (uniform datapath for the TMA operands)
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31, nw = blockDim.x >> 5;
+    const int T0 = (nw - 1) * 32;              // the one thread that issues (and waits for) every TMA copy
+    const int ngw = nw - 1;                    // warps 0 .. ngw-1 take the Gram phase (nw >= 3: launch plan)
+    const bool hi = VG_SWAP_STORES && (tid & 4) != 0;            // store_pair: this lane writes its v-row first
     if (tid < 2) st.zero[tid] = 0.0;
     // the output map of the Gram fragments is a function of the lane only: the first warp leaves it in shared
     // memory (read back per image, so that it does not occupy registers during the corner phase)
@@ -443,26 +510,50 @@ reproj_eval_kernel(const EvalArgs args, const int G, const int PCG)
         }
     }     // visible to everyone after the first __syncthreads below
 
+    // this CTA's groups
+    const int n_groups_all = (args.n_img + G - 1) / G;
+    const int my_groups = n_groups_all > (int)blockIdx.x ? (n_groups_all - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    auto group_first = [&](const int gi) { return (int)(((long long)blockIdx.x + (long long)gi * gridDim.x) * G); };
+    // poses of a batch of PCG groups starting at group gi0: thread t takes image (t % G) of group gi0 + t / G
+    auto stage_poses = [&](const int gi0, const int t) {
+        const int j = t / G, gq = t - j * G;
+        if (j < PCG && gi0 + j < my_groups) {
+            const int img = group_first(gi0 + j) + gq;
+            if (img < args.n_img) chain_pose<L>(args, img, st.pose + (size_t)t * LY::POSE);
+        }
+    };
+
     // Programmatic dependent launch: the next kernel of the stream may take this CTA's SM slot as soon as it is
     // free and run its own prologue (above) under this grid's tail; nothing of global memory is touched before
     // the grids this launch depends on have completed and flushed.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
-    // several GPUs, deferred exchange: the first CTA forms the sum of this problem's previous exchange, which has been
-    // crossing NVLink while the launches in between ran (vg_peer.cuh)
-    if (args.collect.n > 1 && blockIdx.x == 0) {
-        peer_collect(args.collect_buf, args.peer_count, args.collect);
+    // several GPUs, deferred exchange: one CTA (the last: it has the fewest groups) forms the sum of this problem's
+    // previous exchange, which has been crossing NVLink while the launches in between ran (vg_peer.cuh)
+    if (args.collect.n > 1 && blockIdx.x == gridDim.x - 1) {
+        peer_collect(args.collect_buf, args.peer_count, args.collect, st.rs, G * 2 * P * (1 + K + 6 * L));
         __threadfence();
         __syncthreads();
         if (tid == 0)
             asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(args.collect_done), "l"(args.collect.epoch) : "memory");
     }
 
+    // the camera's parameters and constants wait in shared memory: read where the corner phase needs them, they do
+    // not occupy registers during the Gram phase
+#if VG_CAM_SMEM
+    if (tid == 0) {
+        double intr[K];
+#pragma unroll
+        for (int i = 0; i < K; i++) { intr[i] = __ldg(args.intr + i); st.cam[i] = intr[i]; }
+        CAM::save(CAM::prepare(intr), st.cam + K);
+    }
+#else
     double intr[K];
 #pragma unroll
     for (int i = 0; i < K; i++) intr[i] = __ldg(args.intr + i);
     const typename CAM::Consts cc = CAM::prepare(intr);
+#endif
     const bool first_direct = (args.inverse[0] == 0);   // R12 of element 0 is the identity
     double part[LY::NPART];                              // this CTA's sum of its images' blocks
 #pragma unroll
@@ -470,104 +561,125 @@ reproj_eval_kernel(const EvalArgs args, const int G, const int PCG)
 
     // Observations are fetched one group ahead into shared memory (cp.async, every thread the element it will
     // itself consume): under the kernel's own store stream a global read takes longer than a corner pass.
-    auto fetch_obs = [&](const long long grp) {
-        if (grp < n_groups) {
-            const int i0 = (int)grp * G, n = min(G, args.n_img - i0) * P;
+    auto fetch_obs = [&](const int gi) {
+        if (gi < my_groups) {
+            const int i0 = group_first(gi), n = min(G, args.n_img - i0) * P;
             for (int idx = tid; idx < n; idx += blockDim.x)
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(smem_u32(st.obuf + 2 * idx)),
                              "l"(args.obs + ((size_t)i0 * P + idx) * 2) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    fetch_obs(blockIdx.x);
+    fetch_obs(0);
+    // poses of the first PCG groups: one thread per image
+    if (tid < PCG * G) stage_poses(0, tid);
+    __syncthreads();
     VG_PC_DECL
-    for (int j0 = 0; (long long)blockIdx.x + (long long)j0 * gridDim.x < n_groups; j0 += PCG) {
-        // ---- phase 0: poses of this CTA's next PCG groups, one thread per image ---------
-        if (tid < PCG * G) {
-            const int j = tid / G, gi = tid - j * G;
-            const long long grp = (long long)blockIdx.x + (long long)(j0 + j) * gridDim.x;
-            const long long img = grp * G + gi;
-            if (grp < n_groups && img < args.n_img) chain_pose<L>(args, (int)img, st.pose + (size_t)tid * LY::POSE);
-        }
-        __syncthreads();
-        VG_PC(0)
 
-        for (int j = 0; j < PCG; j++) {
-            const long long grp = (long long)blockIdx.x + (long long)(j0 + j) * gridDim.x;
-            if (grp >= n_groups) break;
-            const int img0 = (int)grp * G;
-            const int nv = min(G, args.n_img - img0);
-            const double *pose_grp = st.pose + (size_t)j * G * LY::POSE;
-
-            // ---- phase A: one thread per (image, corner) -------------------------------
-            asm volatile("cp.async.wait_group 0;" ::: "memory");     // this thread's own observations have landed
-            for (int idx = tid; idx < nv * P; idx += blockDim.x) {
-                const int g = idx / P;
-                const int c = idx - g * P;
-                const double2 ob = *reinterpret_cast<const double2 *>(st.obuf + 2 * idx);
-                const double *ps = pose_grp + (size_t)g * LY::POSE;
-                const double bx = __ldg(args.board + 3 * c), by = __ldg(args.board + 3 * c + 1),
-                             bz = __ldg(args.board + 3 * c + 2);
-                const double X0 = fma(ps[2], bz, fma(ps[1], by, fma(ps[0], bx, ps[9])));
-                const double X1 = fma(ps[5], bz, fma(ps[4], by, fma(ps[3], bx, ps[10])));
-                const double X2 = fma(ps[8], bz, fma(ps[7], by, fma(ps[6], bx, ps[11])));
-                double u, v, Pu[3], Pv[3], Ju[K], Jv[K];
-                const bool ok = CAM::eval(intr, cc, X0, X1, X2, u, v, Pu, Pv, Ju, Jv);
-                double2 res;
-                if (ok) {
-                    res.x = u - ob.x;
-                    res.y = v - ob.y;
-                } else {
-                    res.x = DOUBLE_BIG;
-                    res.y = DOUBLE_BIG;
+    // ---- A: one thread per (image, corner) -- the camera model, then the rows into the staging area -----------
+    // When a group fits one pass over the CTA (always, unless the board has more points than the CTA threads) a
+    // thread keeps its (image, corner) pair and its board point for the whole launch.
+    const bool single_pass = G * P <= (int)blockDim.x;
+    const int g_t = tid / P, c_t = tid - g_t * P;
+    double bx_t = 0.0, by_t = 0.0, bz_t = 0.0;
+    if (single_pass && tid < G * P) {
+        bx_t = __ldg(args.board + 3 * c_t); by_t = __ldg(args.board + 3 * c_t + 1); bz_t = __ldg(args.board + 3 * c_t + 2);
+    }
+    const double *pose_base = st.pose;          // the current group's pose records
+    auto corner = [&](const int idx, const int g, const int c, const double bx, const double by, const double bz) {
+        const double *ps = pose_base + (size_t)g * LY::POSE;
+#if VG_CAM_SMEM
+        double intr[K];
 #pragma unroll
-                    for (int i = 0; i < 3; i++) { Pu[i] = 0.0; Pv[i] = 0.0; }
+        for (int i = 0; i < K; i++) intr[i] = st.cam[i];
+        const typename CAM::Consts cc = CAM::load(intr, st.cam + K);
+#endif
+        const double2 ob = *reinterpret_cast<const double2 *>(st.obuf + 2 * idx);
+        const double X0 = fma(ps[2], bz, fma(ps[1], by, fma(ps[0], bx, ps[9])));
+        const double X1 = fma(ps[5], bz, fma(ps[4], by, fma(ps[3], bx, ps[10])));
+        const double X2 = fma(ps[8], bz, fma(ps[7], by, fma(ps[6], bx, ps[11])));
+        double u, v, Pu[3], Pv[3], Ju[K], Jv[K];
+        const bool ok = CAM::eval(intr, cc, X0, X1, X2, u, v, Pu, Pv, Ju, Jv);
+        // rows into the staging area, in exactly the Ceres block layout
+        const size_t row = (size_t)g * 2 * P + 2 * c;
+        *reinterpret_cast<double2 *>(st.rs + row) = make_double2(u - ob.x, v - ob.y);
+        store_pair<K>(st.Jas + row * K, Ju, Jv, hi);
+        // rows of dP/dX in the order this lane stores them (see store_pair)
+        double Pa[3], Pb[3];
 #pragma unroll
-                    for (int i = 0; i < K; i++) { Ju[i] = 0.0; Jv[i] = 0.0; }
-                }
-                const size_t row = (size_t)g * 2 * P + 2 * c;
-                *reinterpret_cast<double2 *>(st.rs + row) = res;
-                store_row<K>(st.Jas + row * K, Ju, (K % 2) == 0);
-                store_row<K>(st.Jas + (row + 1) * K, Jv, (K % 2) == 0);
+        for (int q = 0; q < 3; q++) { Pa[q] = hi ? Pv[q] : Pu[q]; Pb[q] = hi ? Pu[q] : Pv[q]; }
+        const int ra = hi ? 6 : 0, rb = hi ? 0 : 6;
 #pragma unroll
-                for (int e = 0; e < L; e++) {
-                    const double *pe = ps + 12 + 21 * e;
-                    const double w0 = X0 - pe[18], w1 = X1 - pe[19], w2 = X2 - pe[20];
-                    // (w x p)^T M12  ==  -p^T hat(w) M12   (jacobian.h:165,170)
-                    const double cu0 = w1 * Pu[2] - w2 * Pu[1], cu1 = w2 * Pu[0] - w0 * Pu[2],
-                                 cu2 = w0 * Pu[1] - w1 * Pu[0];
-                    const double cv0 = w1 * Pv[2] - w2 * Pv[1], cv1 = w2 * Pv[0] - w0 * Pv[2],
-                                 cv2 = w0 * Pv[1] - w1 * Pv[0];
-                    double ju[6], jv[6];
-                    if (e == 0 && first_direct) {
+        for (int e = 0; e < L; e++) {
+            const double *pe = ps + 12 + 21 * e;
+            const double w0 = X0 - pe[18], w1 = X1 - pe[19], w2 = X2 - pe[20];
+            // (w x p)^T M12  ==  -p^T hat(w) M12   (jacobian.h:165,170)
+            const double ca0 = w1 * Pa[2] - w2 * Pa[1], ca1 = w2 * Pa[0] - w0 * Pa[2],
+                         ca2 = w0 * Pa[1] - w1 * Pa[0];
+            const double cb0 = w1 * Pb[2] - w2 * Pb[1], cb1 = w2 * Pb[0] - w0 * Pb[2],
+                         cb2 = w0 * Pb[1] - w1 * Pb[0];
+            double ja[6], jb_[6];
+            if (e == 0 && first_direct) {
 #pragma unroll
-                        for (int q = 0; q < 3; q++) { ju[q] = Pu[q]; jv[q] = Pv[q]; }
-                    } else {
+                for (int q = 0; q < 3; q++) { ja[q] = Pa[q]; jb_[q] = Pb[q]; }
+            } else {
 #pragma unroll
-                        for (int q = 0; q < 3; q++) {
-                            ju[q] = fma(Pu[2], pe[6 + q], fma(Pu[1], pe[3 + q], Pu[0] * pe[q]));
-                            jv[q] = fma(Pv[2], pe[6 + q], fma(Pv[1], pe[3 + q], Pv[0] * pe[q]));
-                        }
-                    }
-#pragma unroll
-                    for (int q = 0; q < 3; q++) {
-                        ju[3 + q] = fma(cu2, pe[15 + q], fma(cu1, pe[12 + q], cu0 * pe[9 + q]));
-                        jv[3 + q] = fma(cv2, pe[15 + q], fma(cv1, pe[12 + q], cv0 * pe[9 + q]));
-                    }
-                    store_row<6>(st.Jes[e] + row * 6, ju, true);
-                    store_row<6>(st.Jes[e] + (row + 1) * 6, jv, true);
+                for (int q = 0; q < 3; q++) {
+                    ja[q] = fma(Pa[2], pe[6 + q], fma(Pa[1], pe[3 + q], Pa[0] * pe[q]));
+                    jb_[q] = fma(Pb[2], pe[6 + q], fma(Pb[1], pe[3 + q], Pb[0] * pe[q]));
                 }
             }
-            fetch_obs(grp + gridDim.x);  // the next group's observations, into the elements just consumed
-            fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the TMA engine
-            VG_PC(1)
-            __syncthreads();
-            VG_PC(2)
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                ja[3 + q] = fma(ca2, pe[15 + q], fma(ca1, pe[12 + q], ca0 * pe[9 + q]));
+                jb_[3 + q] = fma(cb2, pe[15 + q], fma(cb1, pe[12 + q], cb0 * pe[9 + q]));
+            }
+            double *pj = st.Jes[e] + row * 6;
+            store_row<6>(pj + ra, ja, true);
+            store_row<6>(pj + rb, jb_, true);
+        }
+        if (!ok) {
+            // failed projection (rare): the 1e15 sentinel and zero Jacobian rows over what was just written
+            // (calib_cost_functions.cpp:66-70, eucm.h:141-150,198-206)
+            *reinterpret_cast<double2 *>(st.rs + row) = make_double2(DOUBLE_BIG, DOUBLE_BIG);
+            for (int i = 0; i < 2 * K; i++) st.Jas[row * K + i] = 0.0;
+#pragma unroll
+            for (int e = 0; e < L; e++)
+                for (int i = 0; i < 12; i++) st.Jes[e][row * 6 + i] = 0.0;
+        }
+    };
 
-            // ---- phase S: stream the Ceres-layout blocks out with TMA bulk copies -------
-            bool issued = false;
-            if (tid == 0) {
+    for (int gi = 0; gi < my_groups; gi++) {
+        const int jb = gi % PCG;
+        const int img0 = group_first(gi);
+        const int nv = min(G, args.n_img - img0);
+        const int ncorn = nv * P;
+        pose_base = st.pose + (size_t)jb * G * LY::POSE;
+
+        asm volatile("cp.async.wait_group 0;" ::: "memory");     // this thread's own observations have landed
+        if (single_pass) {
+            if (tid < ncorn) corner(tid, g_t, c_t, bx_t, by_t, bz_t);
+        } else {
+            for (int idx = tid; idx < ncorn; idx += blockDim.x) {
+                const int g = idx / P, c = idx - g * P;
+                corner(idx, g, c, __ldg(args.board + 3 * c), __ldg(args.board + 3 * c + 1), __ldg(args.board + 3 * c + 2));
+            }
+        }
+        VG_PC(0)
+        // the previous group's packed blocks must have been read before this group's Gram phase rewrites them
+        if (tid == T0) bulk_wait_read_all();
+        fetch_obs(gi + 1);          // the next group's observations, into the elements just consumed
+        fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the TMA engine
+        VG_PC(1)
+        __syncthreads();            // ---- B2
+        VG_PC(2)
+
+        const bool restage = jb == PCG - 1 && gi + 1 < my_groups;
+        if (warp == nw - 1) {
+            // ---- S: the Ceres-layout blocks leave with TMA bulk copies; next batch of poses; staging area read ----
+            if (lane == 0) {
                 const size_t rows = (size_t)nv * 2 * P;
+                bool issued = false;
                 if (args.r) { bulk_store_chunked(args.r + (size_t)img0 * 2 * P, st.rs, rows * 8); issued = true; }
                 if (args.Ja) { bulk_store_chunked(args.Ja + (size_t)img0 * 2 * P * K, st.Jas, rows * K * 8); issued = true; }
 #pragma unroll
@@ -578,81 +690,77 @@ reproj_eval_kernel(const EvalArgs args, const int G, const int PCG)
                     }
                 if (issued) bulk_commit();
             }
-
-            // ---- phase B: per-image normal-equation blocks, one warp per image ------------
-            if (args.H) {
-                VG_PC(3)
-                for (int g = warp; g < nv; g += nw) {
+            // every warp has left the corner phase of this batch's last group: its pose records are free
+            if (restage) stage_poses(gi + 1, lane);
+            if (lane == 0) bulk_wait_read_all();      // the next corner phase may overwrite the staging area
+        }
+        // ---- B: per-image normal-equation blocks, one warp per image -----------------------------------
+        if (args.H) {
+            for (int g = warp; g < nv && warp < ngw; g += ngw) {
+                if constexpr (use_parity_gram<MODEL, L>()) {
                     const double *Jes_g[L];
 #pragma unroll
                     for (int e = 0; e < L; e++) Jes_g[e] = st.Jes[e] + (size_t)g * 2 * P * 6;
-                    if constexpr (use_parity_gram<MODEL, L>()) {
-                        GramFrag<MODEL, L> v;
-                        gram_slot_parity<MODEL, L>(st.rs + (size_t)g * 2 * P, st.Jas + (size_t)g * 2 * P * K, Jes_g, st.zero, lane, P, v);
-                        gram_frag_emit<MODEL, L, typename LY::map_t>(v, st.map, st.Hs + (size_t)g * LY::NE, lane);
-                    } else {
-                        gram_image<MODEL, L>(st, g, lane, P);
-                    }
-                    if (args.loss_b > 0.0) {       // SoftLOneLoss on this image's block (see EvalArgs::loss_b)
-                        double *Hg = st.Hs + (size_t)g * LY::NE;
-                        __syncwarp();
-                        const double q = sqrt(1.0 + Hg[LY::NE - 1] / args.loss_b);
-                        const double w = 1.0 / q;
-                        __syncwarp();
-                        for (int e = lane; e < LY::NE - 1; e += 32) Hg[e] *= w;
-                        if (lane == 0) Hg[LY::NE - 1] = 2.0 * args.loss_b * (q - 1.0);
-                    }
+                    GramFrag<MODEL, L> v;
+                    gram_slot_parity<MODEL, L>(st.rs + (size_t)g * 2 * P, st.Jas + (size_t)g * 2 * P * K, Jes_g, st.zero, lane, P, v);
+                    gram_frag_emit<MODEL, L, typename LY::map_t>(v, st.map, st.Hs + (size_t)g * LY::NE, lane);
+                } else {
+                    gram_image<MODEL, L>(st, g, lane, P);
                 }
-                fence_proxy_async_smem();
-                VG_PC(4)
-                __syncthreads();
-                VG_PC(5)
-                // the group's packed blocks are contiguous in global memory: one more bulk copy (a ragged last
-                // group, whose byte count may not be a multiple of 16, goes through ordinary stores)
-                double *Hg = args.H + (size_t)img0 * LY::NE;
-                const size_t hbytes = (size_t)nv * LY::NE * 8;
-                const bool h_bulk = (hbytes & 15) == 0 && ((reinterpret_cast<uintptr_t>(Hg) & 15) == 0);
-                if (h_bulk && tid == 0) { bulk_store(Hg, st.Hs, (uint32_t)hbytes); bulk_commit(); issued = true; }
-#pragma unroll
-                for (int q = 0; q < LY::NPART; q++) {
-                    const int e = tid + q * blockDim.x;
-                    if (e < LY::NE) {
-                        double sum = 0.0;
-                        for (int g = 0; g < nv; g++) {
-                            const double val = st.Hs[(size_t)g * LY::NE + e];
-                            if (!h_bulk) Hg[(size_t)g * LY::NE + e] = val;
-                            sum += val;
-                        }
-                        part[q] += sum;
-                    }
+                if (args.loss_b > 0.0) {       // SoftLOneLoss on this image's block (see EvalArgs::loss_b)
+                    double *Hg = st.Hs + (size_t)g * LY::NE;
+                    __syncwarp();
+                    const double q = sqrt(1.0 + Hg[LY::NE - 1] / args.loss_b);
+                    const double w = 1.0 / q;
+                    __syncwarp();
+                    for (int e = lane; e < LY::NE - 1; e += 32) Hg[e] *= w;
+                    if (lane == 0) Hg[LY::NE - 1] = 2.0 * args.loss_b * (q - 1.0);
                 }
             }
-            VG_PC(6)
-            if (issued) bulk_wait_read_all();   // staging must outlive the TMA reads
-            __syncthreads();                    // staging + Hs are free for the next group
-            VG_PC(7)
+            fence_proxy_async_smem();
         }
+        VG_PC(3)
+        __syncthreads();            // ---- B3: packed blocks complete, staging area read, next poses staged
+        VG_PC(4)
+        if (args.H) {
+            // the group's packed blocks are contiguous in global memory: one more bulk copy (a ragged last
+            // group, whose byte count may not be a multiple of 16, goes through ordinary stores)
+            double *Hg = args.H + (size_t)img0 * LY::NE;
+            const size_t hbytes = (size_t)nv * LY::NE * 8;
+            const bool h_bulk = (hbytes & 15) == 0 && ((reinterpret_cast<uintptr_t>(Hg) & 15) == 0);
+            if (h_bulk && tid == T0) { bulk_store(Hg, st.Hs, (uint32_t)hbytes); bulk_commit(); }
+#pragma unroll
+            for (int q = 0; q < LY::NPART; q++) {
+                const int e = tid + q * blockDim.x;
+                if (e < LY::NE) {
+                    double sum = 0.0;
+                    for (int g = 0; g < nv; g++) {
+                        const double val = st.Hs[(size_t)g * LY::NE + e];
+                        if (!h_bulk) Hg[(size_t)g * LY::NE + e] = val;
+                        sum += val;
+                    }
+                    part[q] += sum;
+                }
+            }
+        }
+        VG_PC(5)
     }
-#ifdef VG_PHASE_CLOCKS
-    if (lane == 0 && (warp == 0 || warp == nw - 1))
-        for (int i = 0; i < 8; i++) atomicAdd(&g_phase_clocks[warp == 0 ? 0 : 1][i], pc_acc[i]);
-#endif
+    if (tid == T0) bulk_wait_read_all();        // shared memory must outlive the TMA reads
+    VG_PC_FLUSH_ALL
     if (args.H && args.cta_partial) {
 #pragma unroll
         for (int q = 0; q < LY::NPART; q++) {
             const int e = tid + q * blockDim.x;
             if (e < LY::NE) args.cta_partial[(size_t)blockIdx.x * LY::NE + e] = part[q];
         }
-        if (args.tickets) fused_reduce<LY::NE>(args);
+        if (args.tickets) fused_reduce<LY::NE>(args, st.rs, G * 2 * P * (1 + K + 6 * L));
     }
 }
 
-template <int MODEL, int L>
-cudaError_t launch_one(const EvalArgs &args, cudaStream_t stream, unsigned long long *launches, int *grid_out,
-                       bool query_only)
+template <int MODEL, int L, int PC>
+cudaError_t launch_fixed(const EvalArgs &args, const LaunchPlan &pl, cudaStream_t stream, unsigned long long *launches,
+                         int *grid_out, bool query_only)
 {
-    LaunchPlan pl;
-    if (!plan_eval(MODEL, L, args.P, &pl)) return cudaErrorInvalidValue;
     static int configured_bytes[64];    // per instantiation and device; zero-initialised
     static int blocks_per_sm[64];
     static int sm_count[64];
@@ -661,12 +769,12 @@ cudaError_t launch_one(const EvalArgs &args, cudaStream_t stream, unsigned long 
     cudaGetDevice(&dev);
     dev &= 63;
     if (pl.smem > configured_bytes[dev] || planned_threads[dev] != pl.threads) {
-        cudaError_t e = cudaFuncSetAttribute(reproj_eval_kernel<MODEL, L>,
+        cudaError_t e = cudaFuncSetAttribute(reproj_eval_kernel<MODEL, L, PC>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
         if (e != cudaSuccess) return e;
         configured_bytes[dev] = (int)pl.smem;
         planned_threads[dev] = pl.threads;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[dev], reproj_eval_kernel<MODEL, L>,
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[dev], reproj_eval_kernel<MODEL, L, PC>,
                                                           pl.threads, (size_t)pl.smem);
         if (e != cudaSuccess) return e;
         e = cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
@@ -686,11 +794,28 @@ cudaError_t launch_one(const EvalArgs &args, cudaStream_t stream, unsigned long 
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-    const cudaError_t le = cudaLaunchKernelEx(&cfg, reproj_eval_kernel<MODEL, L>, args, pl.G, pl.PCG);
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, reproj_eval_kernel<MODEL, L, PC>, args, pl.G, pl.PCG);
     if (launches) (*launches)++;
     return le != cudaSuccess ? le : cudaGetLastError();
 }
 
+// boards with a kernel of their own (the 9 x 6 board of every BASELINE configuration), for chains of one or two
+// transforms; anything else runs the run-time-sized kernel
+template <int MODEL, int L>
+cudaError_t launch_one(const EvalArgs &args, cudaStream_t stream, unsigned long long *launches, int *grid_out,
+                       bool query_only)
+{
+    LaunchPlan pl;
+    if (!plan_eval(MODEL, L, args.P, &pl)) return cudaErrorInvalidValue;
+#ifndef VG_NO_FIXED_BOARD
+    if constexpr (L <= 2) {
+        constexpr int PC = 54;
+        if (args.P == PC && pl.G == plan_group(PC) && pl.PCG == plan_pcg(Layout<MODEL, L>::POSE, plan_group(PC)))
+            return launch_fixed<MODEL, L, PC>(args, pl, stream, launches, grid_out, query_only);
+    }
+#endif
+    return launch_fixed<MODEL, L, 0>(args, pl, stream, launches, grid_out, query_only);
+}
 
 template <int MODEL>
 cudaError_t launch_model(int L, const EvalArgs &a, cudaStream_t s, unsigned long long *n, int *grid, bool q)

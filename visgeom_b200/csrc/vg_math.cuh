@@ -115,6 +115,7 @@ template <int MODEL> struct Camera;
 template <> struct Camera<MODEL_EUCM> {
     static constexpr int K = 6;
     struct Consts { double gamma, ab, hemi; bool hemi_test; };
+    static constexpr int NCONST = 3;      // doubles of Consts a kernel may park in shared memory (save / load)
     __device__ __forceinline__ static Consts prepare(const double (&p)[K])
     {
         Consts c;
@@ -122,6 +123,14 @@ template <> struct Camera<MODEL_EUCM> {
         c.ab = p[0] * p[1];
         c.hemi_test = p[0] > 0.5;                                  // eucm.h:49
         c.hemi = (p[0] - 1.0) / (p[0] + p[0] - 1.0);               // eucm.h:52
+        return c;
+    }
+    __device__ __forceinline__ static void save(const Consts &c, double *d) { d[0] = c.gamma; d[1] = c.ab; d[2] = c.hemi; }
+    __device__ __forceinline__ static Consts load(const double (&p)[K], const double *d)
+    {
+        Consts c;
+        c.gamma = d[0]; c.ab = d[1]; c.hemi = d[2];
+        c.hemi_test = p[0] > 0.5;
         return c;
     }
     __device__ __forceinline__ static bool eval(const double (&p)[K], const Consts &cc, const double x, const double y,
@@ -199,7 +208,10 @@ __device__ __forceinline__ void unified_normalise(const double xi, const double 
 template <> struct Camera<MODEL_UCM> {
     static constexpr int K = 5;
     struct Consts {};
+    static constexpr int NCONST = 0;
     __device__ __forceinline__ static Consts prepare(const double (&)[K]) { return Consts(); }
+    __device__ __forceinline__ static void save(const Consts &, double *) {}
+    __device__ __forceinline__ static Consts load(const double (&)[K], const double *) { return Consts(); }
     __device__ __forceinline__ static bool eval(const double (&p)[K], const Consts &, const double x, const double y, const double z,
                                                 double &u, double &v, double (&Pu)[3], double (&Pv)[3],
                                                 double (&Ju)[K], double (&Jv)[K])
@@ -221,7 +233,10 @@ template <> struct Camera<MODEL_UCM> {
 template <> struct Camera<MODEL_MEI> {
     static constexpr int K = 10;
     struct Consts {};
+    static constexpr int NCONST = 0;
     __device__ __forceinline__ static Consts prepare(const double (&)[K]) { return Consts(); }
+    __device__ __forceinline__ static void save(const Consts &, double *) {}
+    __device__ __forceinline__ static Consts load(const double (&)[K], const double *) { return Consts(); }
     __device__ __forceinline__ static bool eval(const double (&p)[K], const Consts &, const double x, const double y, const double z,
                                                 double &u, double &v, double (&Pu)[3], double (&Pv)[3],
                                                 double (&Ju)[K], double (&Jv)[K])

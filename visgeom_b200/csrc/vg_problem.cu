@@ -353,6 +353,12 @@ int prepare(vg_problem *p)
     p->Ks = off;
     p->n_pose = po;
     const int Ks = p->Ks, NP = p->n_pose;
+    // limits of the shared block (the reference has none; these are the engine's): the reduced solve keeps
+    // 2 Ks^2 + 9 Ks doubles in 40 KB of shared memory, a rank's slot of the peer exchange holds PEER_SLOT_DOUBLES
+    if (sizeof(double) * (2 * (size_t)Ks * Ks + 9 * (size_t)Ks + 1) > 40 * 1024)
+        return fail(VG_ERR_UNSUPPORTED, "too many free shared parameters (cameras + global transforms): at most 48 are supported");
+    if (red_size(Ks, p->nranks) > PEER_SLOT_DOUBLES)
+        return fail(VG_ERR_UNSUPPORTED, "the shared block does not fit a peer-exchange slot");
 
     p->slab_doubles = p->cams.size() * CAM_STRIDE + (size_t)p->n_glob * 6 + 2;
     p->h_slab.assign(p->slab_doubles, 0.0);
@@ -578,9 +584,12 @@ int evaluate_set(vg_problem *p, int s, bool timed, bool deferred = false)
         cudaError_t e = launch_eval(p->cams[d.cam].model, d.L, a, p->stream, &launch_counter());
         if (e != cudaSuccess) return fail_cuda(e, "reproj_eval_kernel launch");
     }
+    // no dataset with images on this rank (fewer images than ranks, or a problem of prior blocks only): nothing has
+    // written segment E, and what it holds is the cross-rank SUM of this set's previous evaluation -- it must not be
+    // contributed again
+    if (p->last_ds < 0) VG_CUDA(cudaMemsetAsync(p->d_redbuf[s], 0, sizeof(double) * red_off_model(p->Ks), p->stream));
     if (p->n_tp + p->n_op > 0) {
         // the 6-residual blocks: their normal-equation pieces, then cost and shared-block terms on top of the reduced system
-        if (p->last_ds < 0) VG_CUDA(cudaMemsetAsync(p->d_redbuf[s], 0, sizeof(double) * red_off_model(p->Ks), p->stream));
         SolverLaunch sl{p->stream, &launch_counter()};
         cudaError_t e = launch_prior_eval(p->prior_tables(s), p->Ks, p->d_redbuf[s], 1, nullptr, sl);
         if (e != cudaSuccess) return fail_cuda(e, "prior_eval launch");

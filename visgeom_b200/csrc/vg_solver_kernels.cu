@@ -185,6 +185,7 @@ __device__ __forceinline__ void block_gram(int n_pose, int Ks, const double *ws,
     const int npair = Ks * (Ks + 1) / 2 + Ks;
     const int p0 = blockIdx.x * FACTOR_POSES, p1 = min(n_pose, p0 + FACTOR_POSES);
     const int stride = pose_ws_stride(Ks);
+    if (npair == 0) return;                       // no free shared parameter (poses-only refinement)
     const int Q = max(1, (int)blockDim.x / npair);
     const int per = (FACTOR_POSES + Q - 1) / Q;
     for (int t0 = 0; t0 < npair; t0 += blockDim.x) {
@@ -239,7 +240,7 @@ __device__ __forceinline__ void finalize_gram_body(int Ks, int n_blocks, const d
     // thread = (entry t, slice q of the blocks); slices combined in slice order (fixed sum order)
     const int npair = Ks * (Ks + 1) / 2 + Ks;
     double *S = red + red_off_S(Ks), *v = red + red_off_v(Ks);
-    const int Q = max(1, (int)blockDim.x / npair);
+    const int Q = npair > 0 ? max(1, (int)blockDim.x / npair) : 1;
     const int per = (n_blocks + Q - 1) / Q;
     for (int t0 = 0; t0 < npair; t0 += blockDim.x) {
         const int q = Q > 1 ? threadIdx.x / npair : 0;
@@ -516,13 +517,15 @@ pose_backsub_kernel(int n_pose, int Ks, const double *delta_a, const double *con
 // one block: a segment of the reduction buffer summed across the ranks over peer memory (vg_peer.cuh)
 __global__ void __launch_bounds__(256) peer_exchange_kernel(double *buf, int count, PeerCtx pc)
 {
-    peer_allreduce(buf, count, pc);
+    __shared__ double scratch[2048];
+    peer_allreduce(buf, count, pc, scratch, 2048);
 }
 
 // the second half alone: the sum of an exchange an evaluation kernel posted earlier
 __global__ void __launch_bounds__(256) peer_collect_kernel(double *buf, int count, PeerCtx pc, unsigned long long *done)
 {
-    peer_collect(buf, count, pc);
+    __shared__ double scratch[2048];
+    peer_collect(buf, count, pc, scratch, 2048);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) *done = pc.epoch;
