@@ -53,9 +53,10 @@ def test_mono_parity(gpu, oracle, model, n_img):
         compare_eval(g, o, f"mono model={model} n={n_img}")
 
 
-@pytest.mark.parametrize("model,n_img", [(sd.EUCM, 10000), (sd.MEI, 10000)])
+@pytest.mark.parametrize("model,n_img", [(sd.EUCM, 10000), (sd.MEI, 10000), (sd.UCM, 10000), (sd.EUCM, 25000)])
 def test_full_size_parity(gpu, oracle, model, n_img):
-    """C2 / C3 at BASELINE.json's full size, every output element against the oracle."""
+    """C2 / C3 at BASELINE.json's full size, UCM at the same size and C5's per-GPU shard (25 000 images): every
+    output element against the oracle."""
     d = sd.make_mono(model, n_img, seed=20242 + model)
     g, o = both(gpu, oracle, model, d["intr_init"], d["board"], d["obs"], [d["xi_init"]], [D], [0])
     compare_eval(g, o, f"full model={model}")

@@ -188,6 +188,24 @@ def test_full_size_solve_properties(gpu):
     assert np.abs(g / np.sqrt(np.diag(A))).max() < 1e-6 * np.sqrt(2 * cost)
 
 
+def test_full_size_solve_matches_oracle_lm(gpu, oracle):
+    """C2 at full size: the first five LM iterations (accept / reject sequence, cost, shared parameters and every
+    pose) against the oracle's restatement of the Ceres loop, all host threads; the sixth iteration is already at the
+    minimum, where a trial step changes the cost by rounding noise only.  The engine takes its two-launch step for
+    the plain structure here (vg_solver_fast.cu); VG_LM_NOFAST=1 runs the general kernels on the same case."""
+    d = sd.make_mono(sd.EUCM, 10000, seed=20242)
+    G, O = gpu.Problem(), OracleProblem(oracle)
+    (gc, gt, _), (oc, ot, _) = build_mono(G, d), build_mono(O, d)
+    og = G.default_options(); og.max_num_iterations = 5
+    oo = oracle.default_options(); oo.max_num_iterations = 5; oo.threads = oracle.max_threads()
+    sg, so = G.solve(og), O.solve(oo)
+    assert abs(sg.initial_cost - so.initial_cost) <= 1e-10 * so.initial_cost
+    assert (sg.num_successful, sg.num_unsuccessful) == (so.num_successful, so.num_unsuccessful)
+    assert abs(sg.final_cost - so.final_cost) <= FINAL_RTOL * so.final_cost
+    assert rel(G.camera(gc), O.camera(oc)) < FINAL_RTOL
+    assert np.abs(G.transform(gt) - O.transform(ot)).max() < 1e-8
+
+
 def test_soft_l_one_loss_matches_oracle(gpu, oracle):
     """SoftLOneLoss(a) on every block of a dataset (the initialisation solves, unified_calibration.cpp:379,1143):
     cost, reduced system and the LM solution with gross outliers in two images, against the oracle (Ceres'

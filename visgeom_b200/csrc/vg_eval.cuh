@@ -8,12 +8,14 @@
 namespace vg {
 
 constexpr int MAX_CHAIN = 5;
-constexpr int EVAL_REDUCE_GROUP = 16;
+constexpr int EVAL_REDUCE_GROUP = 24;     // rows per first-level group of the fused reduction (592 CTAs: 25 groups)
 
 // Tables of the fused shared-block reduction (built on the host once per problem): every entry of the reduced
 // system (A_ij with i <= j, g_i, cost) lists the (dataset, packed entry) sums that feed it.
 struct FinSrc { int off, ne, nb, e; };                       // offset of the dataset's sums, row stride, rows, packed entry
 struct FinOut { int dst0, dst1; double scale; int src_begin, src_end; };   // red[] targets (dst1 = mirror or -1)
+// The same assembly seen from the one dataset that feeds it alone: where entry e of its sums goes (dst0 < 0: nowhere)
+struct EMapEntry { int dst0, dst1; double scale; };
 
 // One dataset = one camera + one board + n_img images sharing a transform chain.
 // All pointers are device memory.  Output pointers may be null.
@@ -41,7 +43,14 @@ struct EvalArgs {
     const FinSrc *fin_srcs;
     int n_fin_out;
     const double *fin_base;         // all datasets' ds_sum regions
+    const EMapEntry *emap;          // nullable: NE entries, set when this dataset is the only source of every entry of red
     double *red;
+    // nullable: host-mapped words the CTA that assembled red also leaves red[host_index] and (after it) host_seq in,
+    // for a host that polls instead of synchronising the stream (vg_problem_solve)
+    double *host_value;
+    unsigned long long *host_flag;
+    unsigned long long host_seq;
+    int host_index;
     // Robust loss on the block of an image (Ceres applies a LossFunction to the squared norm s of the whole residual
     // block): 0 = none, else b = a^2 of SoftLOneLoss(a), rho(s) = 2 b (sqrt(1 + s / b) - 1).  rho'' < 0, so Ceres'
     // corrector scales residuals and Jacobians by sqrt(rho'): the packed block leaves as rho' [J r]^T [J r] with

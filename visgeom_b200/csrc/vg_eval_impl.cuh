@@ -351,12 +351,13 @@ __device__ __forceinline__ void chain_pose(const EvalArgs &args, const int img, 
 __device__ __forceinline__ double sum_rows_in_order(const double *p, const int stride, const int r0, const int r1)
 {
     double s = 0.0;
-    for (int b = r0; b < r1; b += EVAL_REDUCE_GROUP) {
-        double v[EVAL_REDUCE_GROUP];
+    constexpr int ROW_BATCH = 16;
+    for (int b = r0; b < r1; b += ROW_BATCH) {
+        double v[ROW_BATCH];
 #pragma unroll
-        for (int i = 0; i < EVAL_REDUCE_GROUP; i++) v[i] = b + i < r1 ? __ldcg(p + (size_t)(b + i) * stride) : 0.0;
+        for (int i = 0; i < ROW_BATCH; i++) v[i] = b + i < r1 ? __ldcg(p + (size_t)(b + i) * stride) : 0.0;
 #pragma unroll
-        for (int i = 0; i < EVAL_REDUCE_GROUP; i++) s += v[i];
+        for (int i = 0; i < ROW_BATCH; i++) s += v[i];
     }
     return s;
 }
@@ -370,6 +371,33 @@ __device__ __forceinline__ unsigned int take_ticket(unsigned int *counter)
     return old;
 }
 
+// dst[e] = sum of src[r * NE + e], r in [r0, r1), for every entry e.  With NE <= blockDim / 2 a thread is an (entry,
+// slice of the rows) pair -- half as many dependent batches of L2 loads per thread -- and the slices of an entry are
+// added up in slice order through shared memory (sh: blockDim doubles); fixed order either way.
+// Returns (threads tid < NE, when 2 NE <= blockDim) the entry the thread stored.
+template <int NE>
+__device__ __forceinline__ double reduce_rows(const double *src, const int r0, const int r1, double *dst, double *sh)
+{
+    const int tid = threadIdx.x, nt = blockDim.x;
+    double t = 0.0;
+    if (2 * NE <= nt) {
+        const int S = nt / NE, q = tid / NE, e = tid - q * NE;
+        const int per = (r1 - r0 + S - 1) / S;
+        if (q < S) {
+            const int a = r0 + q * per, b = min(r1, a + per);
+            sh[tid] = sum_rows_in_order(src + e, NE, a, b);
+        }
+        __syncthreads();
+        if (tid < NE) {
+            for (int k = 0; k < S; k++) t += sh[k * NE + tid];
+            dst[tid] = t;
+        }
+    } else {
+        for (int e = tid; e < NE; e += nt) dst[e] = sum_rows_in_order(src + e, NE, r0, r1);
+    }
+    return t;
+}
+
 template <int NE>
 __device__ __forceinline__ void fused_reduce(const EvalArgs &args, double *scratch, const int scratch_cap)
 {
@@ -377,12 +405,11 @@ __device__ __forceinline__ void fused_reduce(const EvalArgs &args, double *scrat
     const int tid = threadIdx.x, rows = gridDim.x;
     const int ngrp = (rows + EVAL_REDUCE_GROUP - 1) / EVAL_REDUCE_GROUP, grp = blockIdx.x / EVAL_REDUCE_GROUP;
     const int r0 = grp * EVAL_REDUCE_GROUP, r1 = min(rows, r0 + EVAL_REDUCE_GROUP);
-    __syncthreads();                       // the CTA's row of cta_partial is written
+    __syncthreads();                       // the CTA's row of cta_partial is written; the staging area (scratch) is free
     if (tid == 0) s_last = take_ticket(args.tickets + 1 + grp) == (unsigned)(r1 - r0 - 1);
     __syncthreads();
     if (!s_last) return;
-    for (int e = tid; e < NE; e += blockDim.x)
-        args.lvl1[(size_t)grp * NE + e] = sum_rows_in_order(args.cta_partial + e, NE, r0, r1);
+    reduce_rows<NE>(args.cta_partial, r0, r1, args.lvl1 + (size_t)grp * NE, scratch);
     __syncthreads();
     if (tid == 0) {
         args.tickets[1 + grp] = 0;
@@ -390,7 +417,12 @@ __device__ __forceinline__ void fused_reduce(const EvalArgs &args, double *scrat
     }
     __syncthreads();
     if (!s_last) return;
-    for (int e = tid; e < NE; e += blockDim.x) args.ds_sum[e] = sum_rows_in_order(args.lvl1 + e, NE, 0, ngrp);
+    // one dataset feeding the reduced system alone: entry e of its sums goes straight to its place (emap), without the
+    // round trips of the table-driven assembly below
+    const bool direct = args.red && args.emap && 2 * NE <= (int)blockDim.x;
+    EMapEntry em{-1, -1, 0.0};
+    if (direct && tid < NE) em = args.emap[tid];
+    const double mine = reduce_rows<NE>(args.lvl1, 0, ngrp, args.ds_sum, scratch);
     if (tid == 0) args.tickets[0] = 0;
     if (!args.red) return;
     if (args.peer.n > 1 && args.peer_deferred && args.collect.n > 1) {
@@ -404,6 +436,13 @@ __device__ __forceinline__ void fused_reduce(const EvalArgs &args, double *scrat
         }
         __syncthreads();
     }
+    if (direct) {
+        if (em.dst0 >= 0) {
+            const double v = mine * em.scale;
+            args.red[em.dst0] = v;
+            if (em.dst1 >= 0) args.red[em.dst1] = v;
+        }
+    } else {
     __threadfence();
     __syncthreads();                       // this dataset's sums are complete; the earlier datasets' launches are
     for (int o = tid; o < args.n_fin_out; o += blockDim.x) {
@@ -417,10 +456,19 @@ __device__ __forceinline__ void fused_reduce(const EvalArgs &args, double *scrat
         args.red[f.dst0] = v;
         if (f.dst1 >= 0) args.red[f.dst1] = v;
     }
+    }
     // several GPUs: the same CTA exchanges the reduced system with its peers over NVLink (vg_peer.cuh)
     if (args.peer.n > 1) {
         if (args.peer_deferred) peer_post(args.red, args.peer_count, args.peer);
         else peer_allreduce(args.red, args.peer_count, args.peer, scratch, scratch_cap);
+    }
+    if (args.host_flag) {
+        __syncthreads();
+        if (tid == 0) {
+            *args.host_value = *reinterpret_cast<volatile double *>(args.red + args.host_index);
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(args.host_flag), "l"(args.host_seq) : "memory");
+        }
     }
 }
 

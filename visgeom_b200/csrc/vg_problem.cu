@@ -12,6 +12,7 @@
 #include "vg_solver_kernels.cuh"
 #include "vg_priors.cuh"
 
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -126,6 +127,7 @@ struct vg_problem {
     std::vector<int> h_acc_tab;                 // offset of each dataset's cta_partial region
     FinOut *d_fin_out = nullptr;
     FinSrc *d_fin_src = nullptr;
+    EMapEntry *d_emap = nullptr;                // direct assembly from the last dataset's sums (vg_eval.cuh), or null
     int n_fin_out = 0;
     double **d_seq_ptr[2] = {nullptr, nullptr};
     double *d_scale = nullptr, *d_ws = nullptr, *d_partial = nullptr, *d_delta = nullptr;
@@ -147,6 +149,14 @@ struct vg_problem {
     unsigned long long *d_collect_done = nullptr;
     PeerCtx next_peer_ctx() { return PeerCtx{d_peer_ptrs, rank, nranks, ++epoch}; }
     unsigned int *d_solver_tickets = nullptr;   // "last block done" counters of pose_factor / pose_backsub
+    // the plain structure's two-launch step (vg_solver_fast.cu): dataset / sequence it applies to, or -1
+    int fast_ds = -1, fast_tr = -1;
+    double *d_fast_scratch = nullptr;
+    unsigned int *d_fast_tickets = nullptr;
+    // host-mapped words the step's kernels leave their scalars in, and the flag the host polls (no copy, no stream sync)
+    double *h_poll = nullptr;
+    unsigned long long poll_seq = 0;            // != 0: the next evaluation's last launch posts cost + flag
+    unsigned long long poll_counter = 0;
     double *d_sh_lo = nullptr, *d_sh_hi = nullptr, *d_scale_a = nullptr;
     std::vector<int> h_sh_off;
     double *d_cta_partial = nullptr;
@@ -207,8 +217,8 @@ void free_prepared(vg_problem *p)
     }
     for (int s = 0; s < 2; s++) { F(p->d_slab[s]); F(p->d_desc[s]); F(p->d_seq_ptr[s]); }
     F(p->d_pose_start); F(p->d_contrib_ds); F(p->d_contrib_img); F(p->d_pose_seq); F(p->d_pose_local);
-    F(p->d_fail); F(p->d_fin_out); F(p->d_fin_src); F(p->d_cta_partial); F(p->d_tickets); F(p->d_lvl1); F(p->d_ds_sum); F(p->d_scale); F(p->d_ws); F(p->d_partial); F(p->d_redbuf[0]); F(p->d_redbuf[1]); F(p->d_delta);
-    F(p->d_solver_tickets); F(p->d_sh_off); F(p->d_sh_lo); F(p->d_sh_hi); F(p->d_scale_a);
+    F(p->d_fail); F(p->d_fin_out); F(p->d_fin_src); F(p->d_emap); F(p->d_cta_partial); F(p->d_tickets); F(p->d_lvl1); F(p->d_ds_sum); F(p->d_scale); F(p->d_ws); F(p->d_partial); F(p->d_redbuf[0]); F(p->d_redbuf[1]); F(p->d_delta);
+    F(p->d_solver_tickets); F(p->d_fast_scratch); F(p->d_fast_tickets); F(p->d_sh_off); F(p->d_sh_lo); F(p->d_sh_hi); F(p->d_scale_a);
     for (int s = 0; s < 2; s++) { F(p->d_tp_out[s]); F(p->d_op_out[s]); F(p->d_tp_xi[s]); F(p->d_op_xi[s]); }
     F(p->d_tp_const); F(p->d_op_const); F(p->d_tp_shared_rec); F(p->d_tp_shared_off); F(p->d_seg_start); F(p->d_seg_len);
     F(p->d_extra_start); F(p->d_extra_kind); F(p->d_extra_rec); F(p->d_prev_edge); F(p->d_mask); F(p->d_fixed);
@@ -217,6 +227,7 @@ void free_prepared(vg_problem *p)
     p->pending = false;                 // an exchange posted but never asked for: its words are simply overwritten
     if (p->h_red) { cudaFreeHost(p->h_red); p->h_red = nullptr; }
     if (p->h_up) { cudaFreeHost(p->h_up); p->h_up = nullptr; }
+    if (p->h_poll) { cudaFreeHost(p->h_poll); p->h_poll = nullptr; }
     for (auto &d : p->dss)
         for (int s = 0; s < 2; s++) F(d.d_H[s]);
     p->prepared = false;
@@ -468,6 +479,23 @@ int prepare(vg_problem *p)
     VG_CUDA(cudaMemcpy(p->d_fin_out, fin_out.data(), sizeof(FinOut) * fin_out.size(), cudaMemcpyHostToDevice));
     if (!fin_src.empty())
         VG_CUDA(cudaMemcpy(p->d_fin_src, fin_src.data(), sizeof(FinSrc) * fin_src.size(), cudaMemcpyHostToDevice));
+    // when every entry of the reduced system has exactly one source and all of them lie in the last dataset's sums,
+    // that dataset's launch writes them straight from its reduction
+    if (p->last_ds >= 0) {
+        const int ne = p->h_desc[0][p->last_ds].ne;
+        std::vector<EMapEntry> emap(ne, EMapEntry{-1, -1, 0.0});
+        bool ok = true;
+        for (const FinOut &f : fin_out) {
+            if (f.src_end - f.src_begin != 1) { ok = false; break; }
+            const FinSrc &sr = fin_src[f.src_begin];
+            if (sr.off != p->h_sum_off[p->last_ds] || sr.e < 0 || sr.e >= ne || emap[sr.e].dst0 >= 0) { ok = false; break; }
+            emap[sr.e] = EMapEntry{f.dst0, f.dst1, f.scale};
+        }
+        if (ok) {
+            VG_CUDA(cudaMalloc(&p->d_emap, sizeof(EMapEntry) * ne));
+            VG_CUDA(cudaMemcpy(p->d_emap, emap.data(), sizeof(EMapEntry) * ne, cudaMemcpyHostToDevice));
+        }
+    }
     VG_CUDA(cudaMalloc(&p->d_cta_partial, sizeof(double) * p->cta_partial_doubles));
     VG_CUDA(cudaMalloc(&p->d_fail, sizeof(int)));
     VG_CUDA(cudaMemset(p->d_fail, 0, sizeof(int)));
@@ -500,6 +528,30 @@ int prepare(vg_problem *p)
     VG_CUDA(cudaMalloc(&p->d_sh_lo, sizeof(double) * (Ks ? Ks : 1)));
     VG_CUDA(cudaMalloc(&p->d_sh_hi, sizeof(double) * (Ks ? Ks : 1)));
     VG_CUDA(cudaMalloc(&p->d_scale_a, sizeof(double) * (Ks ? Ks : 1)));
+    // the plain structure (see vg_solver_kernels.cuh): its step runs in two launches
+    p->fast_ds = p->fast_tr = -1;
+    if (p->nranks == 1 && p->n_seg == 0 && p->n_tp + p->n_op == 0 && Ks >= 1 && Ks <= FAST_MAX_KS && NP > 0) {
+        int n_free_seq = 0, tr_id = -1, n_ds_img = 0, ds_id = -1;
+        for (size_t i = 0; i < p->trs.size(); i++)
+            if (p->trs[i].pose_off >= 0) { n_free_seq++; tr_id = (int)i; }
+        for (size_t k = 0; k < p->dss.size(); k++)
+            if (p->dss[k].n_img > 0) { n_ds_img++; ds_id = (int)k; }
+        if (n_free_seq == 1 && n_ds_img == 1) {
+            const Ds &d = p->dss[ds_id];
+            const Tr &t = p->trs[tr_id];
+            bool ok = d.seq_tr == tr_id && d.identity_index && d.n_img == t.n && t.n == NP && t.pose_off == 0 &&
+                      p->h_desc[0][ds_id].pose_col >= 0 && p->h_desc[0][ds_id].n_sl <= FAST_MAX_KS;
+            for (unsigned char f : t.fixed) ok = ok && !f;
+            if (ok) { p->fast_ds = ds_id; p->fast_tr = tr_id; }
+        }
+    }
+    if (p->fast_ds >= 0) {
+        VG_CUDA(cudaMalloc(&p->d_fast_scratch, sizeof(double) * fast_scratch(NP, Ks)));
+        VG_CUDA(cudaMalloc(&p->d_fast_tickets, sizeof(unsigned int) * (fast_groups(NP) + 2)));
+        VG_CUDA(cudaMemset(p->d_fast_tickets, 0, sizeof(unsigned int) * (fast_groups(NP) + 2)));
+        VG_CUDA(cudaHostAlloc(&p->h_poll, sizeof(double) * (FAST_HOST_SLAB + p->slab_doubles + 2), cudaHostAllocMapped));
+        memset(p->h_poll, 0, sizeof(double) * (FAST_HOST_SLAB + p->slab_doubles + 2));
+    }
     p->cur = 0;
     // both parameter sets start from the host values
     fill_slab(p, p->h_slab.data());
@@ -561,7 +613,13 @@ int evaluate_set(vg_problem *p, int s, bool timed, bool deferred = false)
         a.ds_sum = p->d_ds_sum + p->h_sum_off[k];
         if (k == p->last_ds) {      // the shared-block reduction -> segment E is the tail of this launch
             a.fin_outs = p->d_fin_out; a.fin_srcs = p->d_fin_src; a.n_fin_out = p->n_fin_out;
-            a.fin_base = p->d_ds_sum; a.red = p->d_redbuf[s];
+            a.fin_base = p->d_ds_sum; a.red = p->d_redbuf[s]; a.emap = p->d_emap;
+            if (p->poll_seq) {
+                a.host_value = p->h_poll + 11;
+                a.host_flag = reinterpret_cast<unsigned long long *>(p->h_poll + 12);
+                a.host_seq = p->poll_seq; a.host_index = red_off_cost(p->Ks);
+                p->poll_seq = 0;
+            }
             if (p->peers && p->nranks > 1 && p->n_tp + p->n_op == 0) {
                 a.peer_count = red_segE_size(p->Ks);
                 if (deferred) {
@@ -1192,9 +1250,34 @@ int vg_problem_solve(vg_problem *p, const vg_solve_options *opt, vg_solve_summar
         // reached only the gradient test is still due (Ceres tests it first), so the step itself is not queued.
         const bool limits = iter >= o.max_num_iterations || radius < o.min_radius;
         const int cand = p->cur ^ 1;
+        unsigned long long polled = 0;          // != 0: this iteration's results arrive through p->h_poll
         LmConsts lm{radius, o.min_lm_diagonal, o.max_lm_diagonal, init_scale ? 1 : 0, o.jacobi_scaling};
         cudaError_t ce = cudaSuccess;
         mark(0);
+        static const bool nofast = getenv("VG_LM_NOFAST") != nullptr;   // developer knob: the general kernels everywhere
+        if (p->fast_ds >= 0 && !nofast) {
+            // the plain structure: factorisation + Schur terms, then reduced solve + back-substitution, two launches
+            const SolveArgs sa{(int)p->slab_doubles, p->nranks, p->d_redbuf[p->cur], p->d_redbuf[cand], p->d_slab[p->cur],
+                               p->d_slab[cand], p->d_delta, p->d_sh_off, p->d_sh_lo, p->d_sh_hi, p->d_scale_a};
+            const DatasetDesc &hd = p->h_desc[p->cur][p->fast_ds];
+            FastDesc fd;
+            memset(&fd, 0, sizeof fd);
+            fd.H = hd.H; fd.ne = hd.ne; fd.W = hd.W; fd.pose_col = hd.pose_col; fd.n_sl = hd.n_sl;
+            for (int q = 0; q < hd.n_sl; q++) { fd.sl_col[q] = hd.sl_col[q]; fd.sl_idx[q] = hd.sl_idx[q]; }
+            const Tr &ft = p->trs[p->fast_tr];
+            ce = launch_fast_step(fd, NP, Ks, p->d_scale, lm, p->d_ws, p->d_fast_scratch, p->d_fast_tickets, p->d_fail, sa,
+                                  ft.dev[p->cur], ft.dev[cand], !limits, sl, trace ? tev[1] : nullptr, p->h_poll);
+            if (ce != cudaSuccess) return fail_cuda(ce, "fast LM step");
+            init_scale = false;
+            mark(2); mark(3);
+            if (!limits) {
+                static const bool nopoll = getenv("VG_LM_NOPOLL") != nullptr;     // developer knob: copy + stream sync instead
+                if (!nopoll && !trace) { p->poll_seq = ++p->poll_counter; polled = p->poll_seq; }
+                rc = evaluate_set(p, cand, !polled);
+                if (rc) return rc;
+            }
+            mark(4);
+        } else {
         if (p->n_seg > 0)      // coupled / constant elements first: their rows of ws, max |g| per segment
             ce = launch_chain_factor(p->d_desc[p->cur], Ks, p->d_pose_start, p->d_contrib_ds, p->d_contrib_img, p->d_scale, lm,
                                      p->d_ws, p->chain_tables(p->cur), p->d_partial + pose_factor_blocks(NP), p->d_fail, sl);
@@ -1202,7 +1285,8 @@ int vg_problem_solve(vg_problem *p, const vg_solve_options *opt, vg_solve_summar
         // rank in the tail of the pose factorisation kernel, else in its own launch after the exchange of S_red, v_red
         const SolveArgs sa{(int)p->slab_doubles, p->nranks, p->d_redbuf[p->cur], p->d_redbuf[cand], p->d_slab[p->cur],
                            p->d_slab[cand], p->d_delta, p->d_sh_off, p->d_sh_lo, p->d_sh_hi, p->d_scale_a};
-        const bool fuse = p->nranks == 1 && NP > 0;
+        static const bool nofuse = getenv("VG_LM_NOFUSE") != nullptr;   // developer knob: the tail kernels on their own
+        const bool fuse = p->nranks == 1 && NP > 0 && !nofuse;
         if (ce == cudaSuccess)
             ce = launch_pose_schur(p->d_desc[p->cur], NP, Ks, p->d_pose_start, p->d_contrib_ds, p->d_contrib_img,
                                    p->d_scale, lm, p->d_ws, p->d_partial, p->partial_doubles, p->d_redbuf[p->cur],
@@ -1236,9 +1320,35 @@ int vg_problem_solve(vg_problem *p, const vg_solve_options *opt, vg_solve_summar
             if (rc) return rc;
             mark(4);
         }
+        }
         const double t_queued = trace ? now_s() : 0.0;
-        rc = fetch_segment(p, cand, 0, limits ? 0 : segE, p->red_doubles);
-        if (rc) return rc;
+        if (polled) {
+            // the kernels wrote what the decisions below read straight into host-mapped memory; the evaluation's last
+            // CTA raised the flag after its cost (a finished stream without the flag cannot happen: copy as a last resort)
+            volatile unsigned long long *flag = reinterpret_cast<volatile unsigned long long *>(p->h_poll + 12);
+            bool seen = false;
+            for (unsigned long long spins = 1; !(seen = *flag == polled); spins++) {
+                if ((spins & 0xFFF) == 0) {
+                    const cudaError_t qe = cudaStreamQuery(p->stream);
+                    if (qe == cudaSuccess) { seen = *flag == polled; break; }
+                    if (qe != cudaErrorNotReady) return fail_cuda(qe, "LM step");
+                }
+            }
+            if (seen) {
+                std::atomic_thread_fence(std::memory_order_acquire);
+                const double *hp = p->h_poll;
+                for (int i = 0; i < SOLVE_OUT; i++) p->h_red[off_out + i] = hp[i];
+                for (int i = 0; i < 3; i++) p->h_red[red_off_model(Ks) + i] = hp[8 + i];
+                p->h_red[red_off_cost(Ks)] = hp[11];
+                for (size_t i = 0; i < p->slab_doubles; i++) p->h_red[off_slab + i] = hp[FAST_HOST_SLAB + i];
+            } else {
+                polled = 0;
+            }
+        }
+        if (!polled) {
+            rc = fetch_segment(p, cand, 0, limits ? 0 : segE, p->red_doubles);
+            if (rc) return rc;
+        }
         if (trace) {
             const double t_now = now_s();
             fprintf(stderr, "[vg lm] iteration %d: queued in %.1f us, waited %.1f us\n", iter + 1, (t_queued - t_iter) * 1e6,
@@ -1258,7 +1368,7 @@ int vg_problem_solve(vg_problem *p, const vg_solve_options *opt, vg_solve_summar
         if (iter >= o.max_num_iterations) { sum->termination = 3; break; }
         if (radius < o.min_radius) { sum->termination = 4; break; }
         iter++;
-        collect_eval_time();
+        if (!polled) collect_eval_time();      // (a polled iteration records no events: seconds_evaluate covers the others)
 
         bool ok = so[1] == 0.0 && so[2] != 0.0;      // every pose block and the reduced system factorised
         double model_change = 0, step2 = 0, x2 = 0;

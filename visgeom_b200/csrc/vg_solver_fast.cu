@@ -1,0 +1,550 @@
+// vg_solver_fast.cu -- the Levenberg-Marquardt step for the plain calibration structure: one rank, one dataset
+// whose image i is the only block that touches free pose i (every monocular configuration), no coupled or constant
+// sequence elements, at most FAST_MAX_KS free shared parameters.  Same arithmetic as vg_solver_kernels.cu
+// (pose_factor / finalize_gram / reduced_solve / pose_backsub, i.e. the elimination Ceres performs inside
+// ceres::Solve, unified_calibration.cpp:39-53) in two launches without a serial tail:
+//   fast_factor   32 poses per block: the block's packed blocks arrive with one coalesced pass (no gather through the
+//                 pose list), damped 6x6 Cholesky, Z = L^-1 E^T, z = L^-1 b, the block's Schur terms from shared
+//                 memory; the last block of every group of FAST_GROUP blocks folds the group's rows into one
+//   fast_backsub  every block first adds the few group rows up and solves the small reduced system itself (a few
+//                 hundred flops, redundantly: nobody waits for a last block), then back-substitutes its poses;
+//                 block 0 also leaves the candidate shared parameters and the scalars of the accept / reject decision
+// Reciprocals and square roots are the hardware seed + Newton steps of vg_math.cuh (1-2 ulp): the IEEE division /
+// square-root sequences were half of the instructions of these latency-bound kernels.
+// All sums have a fixed order: bit-reproducible run to run.
+#include "vg_solver_kernels.cuh"
+#include "vg_math.cuh"
+
+#include <cstring>
+
+namespace vg {
+
+namespace {
+
+__host__ __device__ inline int pk(int a, int b, int W) { return a * W - a * (a - 1) / 2 + (b - a); }
+__device__ __forceinline__ int pks(int a, int b, int W) { return a <= b ? pk(a, b, W) : pk(b, a, W); }
+__device__ __forceinline__ constexpr int lt(int i, int j) { return i * (i + 1) / 2 + j; }
+
+constexpr int LANES = 8;                    // lanes per pose
+constexpr int F_THREADS = 256, F_POSES = F_THREADS / LANES;
+constexpr int B_THREADS = 128, B_POSES = B_THREADS / LANES;
+
+__device__ __forceinline__ double sum_rows_batched(const double *p, const size_t stride, const int r0, const int r1, const int rstep)
+{
+    constexpr int B = 24;
+    double s = 0.0;
+    for (int b = r0; b < r1; b += B * rstep) {
+        double v[B];
+#pragma unroll
+        for (int i = 0; i < B; i++) v[i] = b + i * rstep < r1 ? __ldcg(p + (size_t)(b + i * rstep) * stride) : 0.0;
+#pragma unroll
+        for (int i = 0; i < B; i++) s += v[i];
+    }
+    return s;
+}
+
+// max of p[r * stride], r in [r0, r1): every load in flight before the first comparison
+__device__ __forceinline__ double max_rows_batched(const double *p, const size_t stride, const int r0, const int r1)
+{
+    constexpr int B = 16;
+    double m = 0.0;
+    for (int b = r0; b < r1; b += B) {
+        double v[B];
+#pragma unroll
+        for (int i = 0; i < B; i++) v[i] = b + i < r1 ? __ldcg(p + (size_t)(b + i) * stride) : 0.0;
+#pragma unroll
+        for (int i = 0; i < B; i++) m = fmax(m, v[i]);
+    }
+    return m;
+}
+
+__device__ __forceinline__ unsigned int take_ticket(unsigned int *counter)
+{
+    unsigned int old;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(counter) : "memory");
+    return old;
+}
+
+// entry t of a row of Schur terms -> (a, b): t < Ks (Ks + 1) / 2 the upper triangle of Z^T Z row by row, then Z^T z
+__device__ __forceinline__ void pair_of(int t, int Ks, int &a, int &b)
+{
+    const int ntri = Ks * (Ks + 1) / 2;
+    if (t < ntri) {
+        a = 0;
+        int rem = t;
+        while (rem >= Ks - a) { rem -= Ks - a; a++; }
+        b = a + rem;
+    } else {
+        a = t - ntri; b = Ks;
+    }
+}
+
+// ---- factorisation -----------------------------------------------------------------------------
+// dynamic shared memory: [packed blocks of the block's poses: F_POSES x ne | Z, z of them: F_POSES x (6 Ks + 6)]
+// WC / PCC > 0: the block width and the pose block's first column are compiled in (every index into a packed block is
+// then a constant): the three camera models with a chain of one transform; 0: read from the descriptor.
+template <int WC, int PCC>
+__global__ void __launch_bounds__(F_THREADS)
+fast_factor_kernel(const FastDesc d, const int n_pose, const int Ks, double *scale, const LmConsts lm, double *ws,
+                   double *rows, double *grp_rows, double *gmax_rows, unsigned int *tickets, int *fail_flag)
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");       // (programmatic dependent launch: see launch_fast_step)
+    extern __shared__ double sm[];
+    __shared__ int s_lc[FAST_MAX_KS + 1];
+    __shared__ double s_red[F_THREADS];
+    __shared__ int s_last;
+    const int tid = threadIdx.x, sub = tid & (LANES - 1), lp = tid / LANES;
+    const int p0 = blockIdx.x * F_POSES, np = min(F_POSES, n_pose - p0), p = p0 + lp;
+    const int W = WC ? WC : d.W, pc = WC ? PCC : d.pose_col, ne = WC ? WC * (WC + 1) / 2 : d.ne;
+    double *Hs = sm, *zs = sm + (size_t)F_POSES * ne;
+    const int zstride = 6 * Ks + 6, npair = Ks * (Ks + 1) / 2 + Ks;
+    // local column of shared parameter j (the residual column for j == Ks); -1: the dataset does not touch it
+    if (tid <= Ks) {
+        int lc = tid == Ks ? W - 1 : -1;
+#pragma unroll
+        for (int q = 0; q < FAST_MAX_KS; q++)
+            if (q < d.n_sl && d.sl_idx[q] == tid) lc = d.sl_col[q];
+        s_lc[tid] = lc;
+    }
+    // the Jacobi scaling of this thread's pose (not at iteration 0, when it is computed below): in flight with the blocks
+    double scl[6] = {1.0, 1.0, 1.0, 1.0, 1.0, 1.0};
+    if (!lm.init_scale && p < n_pose) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) scl[k] = __ldg(scale + (size_t)p * 6 + k);
+    }
+    {
+        const double *src = d.H + (size_t)p0 * ne;
+        for (int i = tid; i < np * ne; i += F_THREADS) Hs[i] = __ldcs(src + i);
+    }
+    __syncthreads();
+    double gmax = 0.0;
+    if (p < n_pose) {
+        const double *Hp = Hs + (size_t)lp * ne;
+        double Lm[21];
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+#pragma unroll
+            for (int j = 0; j <= i; j++) Lm[lt(i, j)] = Hp[pk(pc + j, pc + i, W)];
+        double *w = ws + (size_t)p * pose_ws_stride(Ks);
+        double lam[6], invd[6] = {1.0, 1.0, 1.0, 1.0, 1.0, 1.0};
+        bool empty = true;
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            const double ckk = Lm[lt(k, k)];
+            if (ckk != 0.0) empty = false;
+            double sc;
+            if (lm.init_scale) {
+                sc = lm.jacobi_scaling ? fast_rcp(1.0 + (ckk > 0.0 ? ckk * fast_rsqrt(ckk) : 0.0)) : 1.0;
+                if (sub == 0) scale[(size_t)p * 6 + k] = sc;
+            } else {
+                sc = scl[k];
+            }
+            const double s2 = sc * sc;
+            lam[k] = fmin(fmax(s2 * ckk, lm.min_diag), lm.max_diag) * fast_rcp(lm.radius * s2);
+        }
+        bool ok = true;
+        if (empty) {
+            // a pose nothing observes: identity factor, zero step
+#pragma unroll
+            for (int i = 0; i < 6; i++)
+#pragma unroll
+                for (int j = 0; j <= i; j++) Lm[lt(i, j)] = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+            for (int k = 0; k < 6; k++) lam[k] = 0.0;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 6; k++) Lm[lt(k, k)] += lam[k];
+#pragma unroll
+            for (int j = 0; j < 6; j++) {
+                double s = Lm[lt(j, j)];
+#pragma unroll
+                for (int k = 0; k < j; k++) s = fma(-Lm[lt(j, k)], Lm[lt(j, k)], s);
+                if (!(s > 0.0)) { ok = false; s = 1.0; }
+                const double inv = fast_rsqrt(s);
+                Lm[lt(j, j)] = s * inv;
+                invd[j] = inv;
+#pragma unroll
+                for (int i = j + 1; i < 6; i++) {
+                    double t = Lm[lt(i, j)];
+#pragma unroll
+                    for (int k = 0; k < j; k++) t = fma(-Lm[lt(i, k)], Lm[lt(j, k)], t);
+                    Lm[lt(i, j)] = t * inv;
+                }
+            }
+        }
+        if (sub == 0) {
+            if (!ok) atomicExch(fail_flag, 1);
+            // (the diagonal of the stored factor holds the RECIPROCALS of L's diagonal: all fast_backsub needs of it)
+#pragma unroll
+            for (int i = 0; i < 6; i++)
+#pragma unroll
+                for (int j = 0; j <= i; j++) w[lt(i, j)] = i == j ? invd[i] : Lm[lt(i, j)];
+#pragma unroll
+            for (int k = 0; k < 6; k++) w[21 + k] = lam[k];
+        }
+        double *zrow = zs + (size_t)lp * zstride;
+        // the group's lanes take the columns: col < Ks -> column col of E^T (Z = L^-1 E^T), col == Ks -> the gradient
+        for (int col = sub; col <= Ks; col += LANES) {
+            const int lc = s_lc[col];
+            double e[6];
+#pragma unroll
+            for (int i = 0; i < 6; i++) e[i] = lc >= 0 ? Hp[pks(lc, pc + i, W)] : 0.0;
+            if (col == Ks) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) gmax = fmax(gmax, fabs(e[k]));
+            }
+#pragma unroll
+            for (int i = 0; i < 6; i++) {           // e <- L^-1 e
+                double s = e[i];
+#pragma unroll
+                for (int k = 0; k < i; k++) s = fma(-Lm[lt(i, k)], e[k], s);
+                e[i] = s * invd[i];
+            }
+            if (col == Ks) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) { w[27 + k] = e[k]; zrow[6 * Ks + k] = e[k]; }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 6; k++) { w[33 + k * Ks + col] = e[k]; zrow[k * Ks + col] = e[k]; }
+            }
+        }
+    }
+    // max |g| of the block
+    for (int off = 16; off > 0; off >>= 1) gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, off));
+    if ((tid & 31) == 0) s_red[tid >> 5] = gmax;
+    __syncthreads();                          // also: the block's Z, z are in shared memory
+    if (tid == 0) {
+        double m = 0.0;
+        for (int i = 0; i < F_THREADS / 32; i++) m = fmax(m, s_red[i]);
+        gmax_rows[blockIdx.x] = m;
+    }
+    __syncthreads();
+    // the block's row of Schur terms: thread = (entry t, slice q of the block's poses), slices added in slice order
+    if (npair > 0) {
+        const int Q = max(1, F_THREADS / npair), per = (F_POSES + Q - 1) / Q;
+        for (int t0 = 0; t0 < npair; t0 += F_THREADS) {
+            const int q = Q > 1 ? tid / npair : 0;
+            const int t = Q > 1 ? tid - q * npair : t0 + tid;
+            double s = 0.0;
+            if (t < npair && q < Q) {
+                int a, b;
+                pair_of(t, Ks, a, b);
+                const int q0 = q * per, q1 = min(np, q0 + per);
+                for (int l = q0; l < q1; l++) {
+                    const double *Z = zs + (size_t)l * zstride, *z = Z + 6 * Ks;
+#pragma unroll
+                    for (int k = 0; k < 6; k++) s = fma(Z[k * Ks + a], (b < Ks) ? Z[k * Ks + b] : z[k], s);
+                }
+            }
+            if (Q > 1) {
+                s_red[tid] = s;
+                __syncthreads();
+                if (tid < npair) {
+                    double tot = 0.0;
+                    for (int qq = 0; qq < Q; qq++) tot += s_red[qq * npair + tid];
+                    rows[(size_t)blockIdx.x * npair + tid] = tot;
+                }
+                break;
+            }
+            if (t < npair) rows[(size_t)blockIdx.x * npair + t] = s;
+        }
+    }
+    // the last block of the group folds the group's rows (and its max |g|) into one
+    const int grp = blockIdx.x / FAST_GROUP, b0 = grp * FAST_GROUP, b1 = min((int)gridDim.x, b0 + FAST_GROUP);
+    __syncthreads();
+    if (tid == 0) s_last = take_ticket(tickets + grp) == (unsigned)(b1 - b0 - 1);
+    __syncthreads();
+    if (!s_last) return;
+    for (int t = tid; t < npair; t += F_THREADS) grp_rows[(size_t)grp * (npair + 1) + t] = sum_rows_batched(rows + t, npair, b0, b1, 1);
+    if (tid == F_THREADS - 1) {
+        grp_rows[(size_t)grp * (npair + 1) + npair] = max_rows_batched(gmax_rows, 1, b0, b1);
+        tickets[grp] = 0;
+    }
+}
+
+// ---- reduced solve + back substitution ------------------------------------------------------------
+// static shared memory of the small solve: Ks <= FAST_MAX_KS
+struct SolveSm {
+    double S[FAST_MAX_KS * FAST_MAX_KS], A[FAST_MAX_KS * FAST_MAX_KS], Sred[FAST_MAX_KS * FAST_MAX_KS];
+    double rhs[FAST_MAX_KS], da[FAST_MAX_KS], g[FAST_MAX_KS], v[FAST_MAX_KS], xs[FAST_MAX_KS], lo[FAST_MAX_KS], hi[FAST_MAX_KS],
+        sc[FAST_MAX_KS], xn[FAST_MAX_KS], Ad[FAST_MAX_KS];
+    double gmax;
+    int ok;
+};
+
+__global__ void __launch_bounds__(B_THREADS, 6)       // every block of a C2-sized problem resident at once
+fast_backsub_kernel(const int n_pose, const int Ks, const int n_grp, const double *grp_rows, const SolveArgs sa,
+                    const LmConsts lm, const double *seq_cur, double *seq_cand, const double *ws, double *partial,
+                    unsigned int *ticket, int *fail_flag, double *host_out)
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // this lane's part of its pose's rows, in flight while the block solves the reduced system: lane k < 6 takes
+    // z_k, row k of Z, the factor and its own component of the pose
+    const int sub = threadIdx.x & (LANES - 1);
+    const int p = blockIdx.x * B_POSES + threadIdx.x / LANES;
+    const bool active = p < n_pose && sub < 6;
+    const double *w = ws + (size_t)(p < n_pose ? p : 0) * pose_ws_stride(Ks);
+    double zk = 0.0, lamk = 0.0, xk = 0.0, Zr[FAST_MAX_KS];
+#pragma unroll
+    for (int a = 0; a < FAST_MAX_KS; a++) Zr[a] = 0.0;
+    if (active) {
+        zk = __ldcg(w + 27 + sub); lamk = __ldcg(w + 21 + sub); xk = __ldcg(seq_cur + (size_t)p * 6 + sub);
+#pragma unroll
+        for (int a = 0; a < FAST_MAX_KS; a++) if (a < Ks) Zr[a] = __ldcg(w + 33 + sub * Ks + a);
+    }
+    __shared__ SolveSm q;
+    __shared__ double sh[3][B_THREADS / 32];
+    __shared__ int s_last;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int npair = Ks * (Ks + 1) / 2 + Ks, ntri = Ks * (Ks + 1) / 2;
+    const double *A = sa.red_cur + red_off_A(Ks), *ga = sa.red_cur + red_off_g(Ks);
+    // ---- the reduced system, by every block ----
+    for (int t = tid; t <= npair; t += B_THREADS) {
+        if (t < npair) {
+            const double s = sum_rows_batched(grp_rows + t, npair + 1, 0, n_grp, 1);
+            if (t < ntri) {
+                int a, b;
+                pair_of(t, Ks, a, b);
+                q.Sred[a * Ks + b] = s;
+                q.Sred[b * Ks + a] = s;
+            } else {
+                q.v[t - ntri] = s;
+            }
+        } else {
+            q.gmax = max_rows_batched(grp_rows + npair, npair + 1, 0, n_grp);
+        }
+    }
+    for (int i = tid; i < Ks * Ks; i += B_THREADS) q.A[i] = __ldcg(A + i);
+    for (int j = tid; j < Ks; j += B_THREADS) {
+        q.g[j] = __ldcg(ga + j);
+        q.xs[j] = sa.slab_cur[sa.sh_off[j]];
+        q.lo[j] = sa.sh_lo[j]; q.hi[j] = sa.sh_hi[j];
+        q.sc[j] = lm.init_scale ? 0.0 : sa.scale_a[j];
+    }
+    __syncthreads();
+    if (tid < 32) {
+        // one warp, right-looking Cholesky in shared memory (Ks <= FAST_MAX_KS < 32): warp-level syncs only
+        for (int j = lane; j < Ks; j += 32) {
+            const double ajj = q.A[j * Ks + j];
+            const double sc = lm.init_scale ? (lm.jacobi_scaling ? fast_rcp(1.0 + (ajj > 0.0 ? ajj * fast_rsqrt(ajj) : 0.0)) : 1.0) : q.sc[j];
+            q.sc[j] = sc;
+            const double s2 = sc * sc;
+            for (int k = 0; k < Ks; k++)
+                q.S[j * Ks + k] = q.A[j * Ks + k] - q.Sred[j * Ks + k] +
+                                  (k == j ? fmin(fmax(s2 * ajj, lm.min_diag), lm.max_diag) * fast_rcp(lm.radius * s2) : 0.0);
+            q.rhs[j] = -(q.g[j] - q.v[j]);
+        }
+        if (lane == 0) q.ok = 1;
+        __syncwarp();
+        for (int j = 0; j < Ks; j++) {
+            double piv = q.S[j * Ks + j];
+            if (!(piv > 0.0)) { if (lane == 0) q.ok = 0; piv = 1.0; }
+            const double inv = fast_rsqrt(piv);
+            __syncwarp();
+            if (lane == 0) q.S[j * Ks + j] = inv;               // the reciprocal of the pivot: what the substitutions need
+            for (int i = j + 1 + lane; i < Ks; i += 32) q.S[i * Ks + j] *= inv;
+            __syncwarp();
+            const int m = Ks - j - 1;
+            for (int e = lane; e < m * m; e += 32) {
+                const int i = j + 1 + e / m, k = j + 1 + e % m;
+                if (k <= i) q.S[i * Ks + k] = fma(-q.S[i * Ks + j], q.S[k * Ks + j], q.S[i * Ks + k]);
+            }
+            __syncwarp();
+        }
+        if (lane == 0) {
+            for (int i = 0; i < Ks; i++) {
+                double s = q.rhs[i];
+                for (int k = 0; k < i; k++) s = fma(-q.S[i * Ks + k], q.da[k], s);
+                q.da[i] = s * q.S[i * Ks + i];
+            }
+            for (int i = Ks - 1; i >= 0; i--) {
+                double s = q.da[i];
+                for (int k = i + 1; k < Ks; k++) s = fma(-q.S[k * Ks + i], q.da[k], s);
+                q.da[i] = s * q.S[i * Ks + i];
+            }
+            if (!q.ok)
+                for (int i = 0; i < Ks; i++) q.da[i] = 0.0;
+        }
+    }
+    __syncthreads();
+    // ---- block 0: what the reduced solve leaves for the host and for the candidate's evaluation ----
+    if (blockIdx.x == 0) {
+        double *out = sa.red_cand + red_size(Ks, sa.nranks);
+        for (int i = tid; i < sa.slab_n; i += B_THREADS) {       // constants and padding carry over
+            const double x = sa.slab_cur[i];
+            sa.slab_cand[i] = x;
+            out[SOLVE_OUT + i] = x;
+        }
+        __syncthreads();
+        for (int j = tid; j < Ks; j += B_THREADS) {
+            double t = 0.0;
+            for (int k = 0; k < Ks; k++) t = fma(q.A[j * Ks + k], q.da[k], t);
+            q.Ad[j] = t;
+            sa.delta_a[j] = q.da[j];
+            if (lm.init_scale) sa.scale_a[j] = q.sc[j];
+            const double xn = fmin(fmax(q.xs[j] + q.da[j], q.lo[j]), q.hi[j]);      // box bounds by projection
+            q.xn[j] = xn;
+            sa.slab_cand[sa.sh_off[j]] = xn;
+            out[SOLVE_OUT + sa.sh_off[j]] = xn;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double gd = 0.0, dHd = 0.0, step2 = 0.0, x2 = 0.0, gmax = q.gmax;
+            for (int j = 0; j < Ks; j++) {
+                gd = fma(q.g[j], q.da[j], gd);
+                dHd = fma(q.da[j], q.Ad[j], dHd);
+                x2 = fma(q.xs[j], q.xs[j], x2);
+                step2 = fma(q.xn[j] - q.xs[j], q.xn[j] - q.xs[j], step2);
+                gmax = fmax(gmax, fabs(q.xs[j] - fmin(fmax(q.xs[j] - q.g[j], q.lo[j]), q.hi[j])));
+            }
+            const double failed = (double)atomicExch(fail_flag, 0);
+            out[0] = gmax;
+            out[1] = failed;
+            out[2] = (double)q.ok;
+            out[3] = gd; out[4] = dHd; out[5] = step2; out[6] = x2; out[7] = 0.0;
+        }
+    }
+    // ---- back substitution: lane k < 6 of a pose's group: w_k = z_k + Z_k . delta_a, delta = -L^-T w ----
+    double m = 0.0, st2 = 0.0, x2 = 0.0, wk = 0.0;
+    if (active) {
+        double s = zk;
+#pragma unroll
+        for (int a = 0; a < FAST_MAX_KS; a++) if (a < Ks) s = fma(Zr[a], q.da[a], s);
+        wk = s;
+        m = -0.5 * s * s;
+    }
+    double wv[6];
+#pragma unroll
+    for (int j = 0; j < 6; j++) wv[j] = __shfl_sync(0xffffffffu, wk, (lane & ~(LANES - 1)) + j);
+    if (active) {
+        double Lm[21];
+#pragma unroll
+        for (int i = 0; i < 21; i++) Lm[i] = __ldcg(w + i);
+#pragma unroll
+        for (int i = 5; i >= 0; i--) {              // wv <- L^-T wv
+            double s = wv[i];
+#pragma unroll
+            for (int k = i + 1; k < 6; k++) s = fma(-Lm[lt(k, i)], wv[k], s);
+            wv[i] = s * Lm[lt(i, i)];           // (reciprocal diagonal, see fast_factor)
+        }
+        double yk = 0.0;
+#pragma unroll
+        for (int j = 0; j < 6; j++) yk = (j == sub) ? wv[j] : yk;
+        const double dlt = -yk;
+        seq_cand[(size_t)p * 6 + sub] = xk + dlt;
+        m = fma(-0.5 * lamk * dlt, dlt, m);
+        st2 = dlt * dlt;
+        x2 = xk * xk;
+    }
+    // block sums in a fixed order: lanes of a warp through shuffles (xor tree), warps in index order
+    for (int off = 16; off > 0; off >>= 1) {
+        m += __shfl_xor_sync(0xffffffffu, m, off);
+        st2 += __shfl_xor_sync(0xffffffffu, st2, off);
+        x2 += __shfl_xor_sync(0xffffffffu, x2, off);
+    }
+    if (lane == 0) { sh[0][tid >> 5] = m; sh[1][tid >> 5] = st2; sh[2][tid >> 5] = x2; }
+    __syncthreads();
+    if (tid < 3) {
+        double s = 0.0;
+        for (int i = 0; i < B_THREADS / 32; i++) s += sh[tid][i];
+        partial[(size_t)blockIdx.x * 3 + tid] = s;
+    }
+    // the last block adds the rows up
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = take_ticket(ticket) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    if (tid == 0) *ticket = 0;
+    const int qn = tid >> 5;
+    if (qn < 3) {
+        const double s = sum_rows_batched(partial + qn, 3, lane, gridDim.x, 32);
+        double tot = 0.0;
+        for (int l = 0; l < 32; l++) tot += __shfl_sync(0xffffffffu, s, l);
+        if (lane == 0) {
+            sa.red_cand[red_off_model(Ks) + qn] = tot;
+            if (host_out) host_out[8 + qn] = tot;
+        }
+    }
+    // a polling host (no copy, no stream sync): block 0's scalars and the candidate slab, straight into host-mapped memory.
+    // Done here, by the block that finishes last, so that no block waits on a fence behind writes that cross PCIe.
+    if (host_out) {
+        const double *out = sa.red_cand + red_size(Ks, sa.nranks);
+        for (int i = tid; i < SOLVE_OUT + sa.slab_n; i += B_THREADS)
+            host_out[i < SOLVE_OUT ? i : FAST_HOST_SLAB + (i - SOLVE_OUT)] = __ldcg(out + i);
+    }
+}
+
+}  // namespace
+
+int fast_factor_blocks(int n_pose) { return (n_pose + F_POSES - 1) / F_POSES; }
+int fast_groups(int n_pose) { return (fast_factor_blocks(n_pose) + FAST_GROUP - 1) / FAST_GROUP; }
+int fast_backsub_blocks(int n_pose) { return (n_pose + B_POSES - 1) / B_POSES; }
+
+size_t fast_scratch(int n_pose, int Ks)
+{
+    const size_t npair = (size_t)Ks * (Ks + 1) / 2 + Ks;
+    return (size_t)fast_factor_blocks(n_pose) * (npair + 1) + (size_t)fast_groups(n_pose) * (npair + 1) +
+           3 * (size_t)fast_backsub_blocks(n_pose) + 16;
+}
+
+template <int WC, int PCC>
+static cudaError_t launch_factor(const FastDesc &d, int n_pose, int Ks, double *scale, const LmConsts &lm, double *ws, double *rows,
+                                 double *grp_rows, double *gmax_rows, unsigned int *tickets, int *fail_flag, size_t smem,
+                                 cudaStream_t stream)
+{
+    static size_t configured[64];           // per instantiation and device; zero-initialised
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (smem > configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(fast_factor_kernel<WC, PCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured[dev] = smem;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(fast_factor_blocks(n_pose)); cfg.blockDim = dim3(F_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, fast_factor_kernel<WC, PCC>, d, n_pose, Ks, scale, lm, ws, rows, grp_rows, gmax_rows, tickets,
+                              fail_flag);
+}
+
+cudaError_t launch_fast_step(const FastDesc &d, int n_pose, int Ks, double *scale, LmConsts lm, double *ws, double *scratch,
+                             unsigned int *tickets, int *fail_flag, const SolveArgs &sa, const double *seq_cur,
+                             double *seq_cand, bool backsub, SolverLaunch sl, cudaEvent_t between, double *host_out)
+{
+    if (Ks < 1 || Ks > FAST_MAX_KS || n_pose < 1 || sa.nranks != 1) return cudaErrorInvalidValue;
+    const int nb = fast_factor_blocks(n_pose), ng = fast_groups(n_pose), npair = Ks * (Ks + 1) / 2 + Ks;
+    double *rows = scratch, *gmax_rows = rows + (size_t)nb * npair, *grp_rows = gmax_rows + nb,
+           *partial = grp_rows + (size_t)ng * (npair + 1);
+    const size_t smem = sizeof(double) * ((size_t)F_POSES * d.ne + (size_t)F_POSES * (6 * Ks + 6));
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    // Both kernels are launched with programmatic stream serialization (they start with griddepcontrol.wait): their
+    // launch latency hides under the tail of the kernel before them.
+    cudaError_t e;
+    if (d.W == 13 && d.pose_col == 6) e = launch_factor<13, 6>(d, n_pose, Ks, scale, lm, ws, rows, grp_rows, gmax_rows, tickets, fail_flag, smem, sl.stream);
+    else if (d.W == 12 && d.pose_col == 5) e = launch_factor<12, 5>(d, n_pose, Ks, scale, lm, ws, rows, grp_rows, gmax_rows, tickets, fail_flag, smem, sl.stream);
+    else if (d.W == 17 && d.pose_col == 10) e = launch_factor<17, 10>(d, n_pose, Ks, scale, lm, ws, rows, grp_rows, gmax_rows, tickets, fail_flag, smem, sl.stream);
+    else e = launch_factor<0, 0>(d, n_pose, Ks, scale, lm, ws, rows, grp_rows, gmax_rows, tickets, fail_flag, smem, sl.stream);
+    if (sl.launches) (*sl.launches)++;
+    if (e != cudaSuccess) return e;
+    if (between) cudaEventRecord(between, sl.stream);
+    // (backsub == false: only the gradient test is still due -- the kernel still leaves the scalars; the candidate
+    // poses it writes are never looked at)
+    (void)backsub;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(fast_backsub_blocks(n_pose)); cfg.blockDim = dim3(B_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = sl.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = between ? 0 : 1;
+    e = cudaLaunchKernelEx(&cfg, fast_backsub_kernel, n_pose, Ks, ng, (const double *)grp_rows, sa, lm, seq_cur, seq_cand,
+                           (const double *)ws, partial, tickets + ng, fail_flag, host_out);
+    if (sl.launches) (*sl.launches)++;
+    return e != cudaSuccess ? e : cudaGetLastError();
+}
+
+}  // namespace vg

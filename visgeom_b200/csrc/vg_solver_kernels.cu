@@ -23,6 +23,23 @@ constexpr int BACK_POSES = POSE_THREADS / POSE_LANES;
 constexpr int FACTOR_THREADS = 256;   // pose_factor: 32 poses per block
 constexpr int FACTOR_POSES = FACTOR_THREADS / POSE_LANES;
 
+// sum of p[r * stride], r in [r0, r1) step rstep, added in index order; the (L2) loads of 16 rows are in flight together
+// (a plain `s += __ldcg(..)` loop issues one load per round trip: the block that finishes last would spend tens of
+// microseconds on a few hundred rows)
+__device__ __forceinline__ double sum_rows_batched(const double *p, const size_t stride, const int r0, const int r1, const int rstep)
+{
+    constexpr int B = 16;
+    double s = 0.0;
+    for (int b = r0; b < r1; b += B * rstep) {
+        double v[B];
+#pragma unroll
+        for (int i = 0; i < B; i++) v[i] = b + i * rstep < r1 ? __ldcg(p + (size_t)(b + i * rstep) * stride) : 0.0;
+#pragma unroll
+        for (int i = 0; i < B; i++) s += v[i];
+    }
+    return s;
+}
+
 // ---- per-pose factorisation ------------------------------------------------------------
 // lower-triangular packed index (i >= j)
 __device__ __forceinline__ constexpr int lt(int i, int j) { return i * (i + 1) / 2 + j; }
@@ -180,7 +197,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS) reduced_solve_kernel(int Ks, So
 // Tail of pose_factor: the block's poses are folded into one row of partial sums.
 // thread = (entry t of the upper triangle of Z^T Z plus the Z^T z column, slice q of the block's poses); the
 // slices of an entry are added in slice order afterwards, so the sum order is fixed.  sh: blockDim.x doubles.
-__device__ __forceinline__ void block_gram(int n_pose, int Ks, const double *ws, double *partial, double *sh)
+// zs (nullable): this block's Z and z in shared memory, (6 Ks + 6) doubles per pose [Z row-major 6 x Ks | z], left
+// there by the factorisation above -- the block's own rows do not come back through L2
+__device__ __forceinline__ void block_gram(int n_pose, int Ks, const double *ws, double *partial, double *sh, const double *zs)
 {
     const int npair = Ks * (Ks + 1) / 2 + Ks;
     const int p0 = blockIdx.x * FACTOR_POSES, p1 = min(n_pose, p0 + FACTOR_POSES);
@@ -204,13 +223,19 @@ __device__ __forceinline__ void block_gram(int n_pose, int Ks, const double *ws,
             }
             const int q0 = p0 + q * per, q1 = min(p1, q0 + per);
             for (int p = q0; p < q1; p++) {
-                const double *w = ws + (size_t)p * stride;
-                const double *Z = w + 33, *z = w + 27;
+                if (zs) {
+                    const double *Z = zs + (size_t)(p - p0) * (6 * Ks + 6), *z = Z + 6 * Ks;
 #pragma unroll
-                for (int k = 0; k < 6; k++) {
-                    const double za = __ldcg(Z + k * Ks + a);
-                    const double zb = (b < Ks) ? __ldcg(Z + k * Ks + b) : __ldcg(z + k);
-                    s = fma(za, zb, s);
+                    for (int k = 0; k < 6; k++) s = fma(Z[k * Ks + a], (b < Ks) ? Z[k * Ks + b] : z[k], s);
+                } else {
+                    const double *w = ws + (size_t)p * stride;
+                    const double *Z = w + 33, *z = w + 27;
+#pragma unroll
+                    for (int k = 0; k < 6; k++) {
+                        const double za = __ldcg(Z + k * Ks + a);
+                        const double zb = (b < Ks) ? __ldcg(Z + k * Ks + b) : __ldcg(z + k);
+                        s = fma(za, zb, s);
+                    }
                 }
             }
         }
@@ -248,7 +273,7 @@ __device__ __forceinline__ void finalize_gram_body(int Ks, int n_blocks, const d
         double s = 0.0;
         if (t < npair && q < Q) {
             const int b0 = q * per, b1 = min(n_blocks, b0 + per);
-            for (int blk = b0; blk < b1; blk++) s += __ldcg(partial + (size_t)blk * npair + t);
+            s = sum_rows_batched(partial + t, npair, b0, b1, 1);
         }
         if (Q > 1) {
             sh[threadIdx.x] = s;
@@ -273,7 +298,13 @@ __device__ __forceinline__ void finalize_gram_body(int Ks, int n_blocks, const d
     if (threadIdx.x >= blockDim.x - 32) {        // the last warp: max |g| over the blocks' / segments' slots
         const int lane = threadIdx.x & 31;
         double m = 0.0;
-        for (int i = lane; i < n_gmax; i += 32) m = fmax(m, __ldcg(partial_gmax + i));
+        for (int i0 = lane; i0 < n_gmax; i0 += 32 * 8) {
+            double v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = i0 + 32 * k < n_gmax ? __ldcg(partial_gmax + i0 + 32 * k) : 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) m = fmax(m, v[k]);
+        }
         for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
         if (lane == 0) {
             for (int r = 0; r < nranks; r++) red[red_off_gmax(Ks) + r] = (r == rank) ? m : 0.0;
@@ -294,9 +325,12 @@ __global__ void __launch_bounds__(FACTOR_THREADS)
 pose_factor_kernel(const DatasetDesc *desc_all, int n_pose, int Ks,
                    const int *pose_start, const int *contrib_ds, const int *contrib_img,
                    double *scale, LmConsts lm, double *ws, double *partial_gmax, double *partial_gram, int *fail_flag,
-                   const unsigned char *chain_mask, FusedTail ft)
+                   const unsigned char *chain_mask, FusedTail ft, int z_smem)
 {
     __shared__ double sh_max[FACTOR_THREADS];
+    extern __shared__ double dyn_sm[];
+    double *zs = z_smem ? dyn_sm : nullptr;       // (the fused tail reuses the same bytes after block_gram)
+    double *zrow = zs ? zs + (size_t)(threadIdx.x / POSE_LANES) * (6 * Ks + 6) : nullptr;
     const int sub = threadIdx.x & (POSE_LANES - 1);
     const int p = blockIdx.x * FACTOR_POSES + threadIdx.x / POSE_LANES;
     double gmax = 0.0;
@@ -395,12 +429,16 @@ pose_factor_kernel(const DatasetDesc *desc_all, int n_pose, int Ks,
             forward_subst(Lm, invd, e);
             if (col == Ks) {
 #pragma unroll
-                for (int k = 0; k < 6; k++) w[27 + k] = e[k];           // z = L^-1 b
+                for (int k = 0; k < 6; k++) { w[27 + k] = e[k]; if (zrow) zrow[6 * Ks + k] = e[k]; }   // z = L^-1 b
             } else {
 #pragma unroll
-                for (int k = 0; k < 6; k++) w[33 + k * Ks + col] = e[k];
+                for (int k = 0; k < 6; k++) { w[33 + k * Ks + col] = e[k]; if (zrow) zrow[k * Ks + col] = e[k]; }
             }
         }
+    } else if (zrow && p < n_pose) {
+        // an element the chain kernels factorised: its rows of ws are complete in global memory
+        const double *w = ws + (size_t)p * pose_ws_stride(Ks);
+        for (int i = sub; i < 6 * Ks + 6; i += POSE_LANES) zrow[i] = i < 6 * Ks ? __ldcg(w + 33 + i) : __ldcg(w + 27 + (i - 6 * Ks));
     }
     sh_max[threadIdx.x] = gmax;
     __syncthreads();          // also: this block's Z, z are written (read back below by other threads of the block)
@@ -409,7 +447,7 @@ pose_factor_kernel(const DatasetDesc *desc_all, int n_pose, int Ks,
         __syncthreads();
     }
     if (threadIdx.x == 0) partial_gmax[blockIdx.x] = sh_max[0];
-    block_gram(n_pose, Ks, ws, partial_gram, sh_max);
+    block_gram(n_pose, Ks, ws, partial_gram, sh_max, zs);
     if (!ft.ticket) return;
     // Fused tail (one rank): the block that finishes last combines every block's row and solves the reduced
     // system, instead of two more single-block launches after this one.
@@ -424,7 +462,6 @@ pose_factor_kernel(const DatasetDesc *desc_all, int n_pose, int Ks,
     finalize_gram_body(Ks, gridDim.x, partial_gram, ft.n_gmax, partial_gmax, ft.red, fail_flag, 0, 1, sh_max);
     __threadfence();
     __syncthreads();
-    extern __shared__ double dyn_sm[];
     reduced_solve_body(Ks, ft.solve, lm, dyn_sm);
 }
 
@@ -434,8 +471,7 @@ __device__ __forceinline__ void finalize_backsub_body(int Ks, int n_blocks, cons
 {
     const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (q >= 3) return;
-    double s = 0.0;
-    for (int blk = lane; blk < n_blocks; blk += 32) s += __ldcg(partial + (size_t)blk * 3 + q);
+    const double s = sum_rows_batched(partial + q, 3, lane, n_blocks, 32);
     double tot = 0.0;
     for (int l = 0; l < 32; l++) tot += __shfl_sync(0xffffffffu, s, l);
     if (lane == 0) red[red_off_model(Ks) + q] = tot;
@@ -611,10 +647,14 @@ cudaError_t launch_pose_schur(const DatasetDesc *d_desc, int n_pose, int Ks,
         if (smem > 40 * 1024) return cudaErrorInvalidValue;
         ft.ticket = ticket; ft.n_gmax = nb_pose + n_seg; ft.red = red; ft.solve = *fused;
     }
+    // the block's Z, z rows in shared memory for its Schur terms (when they fit the default 48 KB with the rest)
+    const size_t zbytes = sizeof(double) * FACTOR_POSES * (6 * (size_t)Ks + 6);
+    const int z_smem = zbytes <= 40 * 1024 ? 1 : 0;
+    if (z_smem && zbytes > smem) smem = zbytes;
     if (n_pose > 0) {
         pose_factor_kernel<<<nb_pose, FACTOR_THREADS, smem, sl.stream>>>(d_desc, n_pose, Ks, pose_start, contrib_ds,
                                                                         contrib_img, scale, lm, ws, p_gmax, p_gram, fail_flag,
-                                                                        chain_mask, ft);
+                                                                        chain_mask, ft, z_smem);
         if (sl.launches) (*sl.launches)++;
     }
     if (ft.ticket) return cudaGetLastError();
