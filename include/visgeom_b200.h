@@ -34,6 +34,8 @@ extern "C" {
 #define VG_ERR_NOMEM       -3
 #define VG_ERR_UNSUPPORTED -4   /* e.g. board too large for one CTA's shared memory */
 #define VG_ERR_NUMERIC     -5   /* linear solve failed repeatedly */
+#define VG_ERR_PEER        -6   /* a rank of the peer-memory exchange never posted its block (died, or issued a different
+                                   sequence of evaluations): the sums of that exchange are NaN */
 
 /* camera models: include/projection/eucm.h, ucm.h, mei.h; parameter order as there:
  * EUCM [alpha,beta,fu,fv,u0,v0]  UCM [xi,fu,fv,u0,v0]  MEI [xi,k1..k5,fu,fv,u0,v0] */
@@ -232,6 +234,14 @@ int vg_problem_set_allreduce(vg_problem *p, vg_allreduce_fn fn, void *ctx, int r
 #define VG_IPC_HANDLE_BYTES 64
 int vg_problem_peer_export(vg_problem *p, void *ipc_handle_out /* VG_IPC_HANDLE_BYTES */);
 int vg_problem_peer_connect(vg_problem *p, int rank, int nranks, const void *ipc_handles /* nranks x VG_IPC_HANDLE_BYTES */);
+/* The same for problems that live in ONE process (one host thread driving several GPUs, or several problems sharing a
+ * GPU): every problem reports the device address of its inbox, and is handed the addresses of all of them in rank
+ * order.  Devices other than the problem's own must be peer-accessible (cudaDeviceEnablePeerAccess is attempted). */
+int vg_problem_peer_inbox(vg_problem *p, void **inbox_out, int *device_out);
+int vg_problem_peer_connect_local(vg_problem *p, int rank, int nranks, void *const *inboxes, const int *devices);
+/* A collect gives up after `polls` reads of a word that never arrives (0: the default, more than ten seconds); the
+ * call that next synchronises with the device then returns VG_ERR_PEER. */
+int vg_problem_set_peer_timeout(vg_problem *p, long long polls);
 
 /* When enabled, every evaluation also materialises r and all Jacobian blocks in
  * device memory in the Ceres layout (what GenericProjectionJac::Evaluate hands to
@@ -275,6 +285,22 @@ int vg_problem_update_poses(vg_problem *p, int transform, const double *values);
 /* residuals of one dataset at the current parameters (writeImageResidual,
  * :1186-1213 needs err = -r and proj = r + obs), n_img x 2P doubles to host */
 int vg_problem_residuals(vg_problem *p, int dataset, double *r);
+
+/* ---- the ICamera point API, batched (include/projection/generic_camera.h:36-113) -------------------------------------
+ * What a visgeom caller does with a camera object outside the calibration functor: projectPoint (:39),
+ * projectionJacobian (:46), intrinsicJacobian (:50), reconstructPoint (:36) and the *PointCloud loops around them
+ * (:64-113), for n points in one launch.  Layouts: X n x 3, uv n x 2; dPdX n x 6 = [du/dX (3), dv/dX (3)] per point
+ * (the two arrays projectionJacobian fills); dPdintr n x 2K = [du/dintr (K), dv/dintr (K)] (intrinsicJacobian);
+ * ok n bytes = the bool the reference's calls return.  A failed point (EUCM only: eucm.h:46-54, :100) keeps the
+ * caller's uv / X entry and gets zero Jacobians.  Any output pointer may be NULL.  _dev: device pointers, asynchronous
+ * on `stream`. */
+int vg_project_points(int model, const double *intr, long long n, const double *X, double *uv, double *dPdX,
+                      double *dPdintr, unsigned char *ok);
+int vg_project_points_dev(int model, const double *intr, long long n, const double *X, double *uv, double *dPdX,
+                          double *dPdintr, unsigned char *ok, void *stream);
+int vg_reconstruct_points(int model, const double *intr, long long n, const double *uv, double *X, unsigned char *ok);
+int vg_reconstruct_points_dev(int model, const double *intr, long long n, const double *uv, double *X, unsigned char *ok,
+                              void *stream);
 
 #ifdef __cplusplus
 }

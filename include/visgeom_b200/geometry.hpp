@@ -9,6 +9,7 @@
 #include <array>
 #include <cmath>
 #include <ostream>
+#include <vector>
 
 namespace visgeom_b200 {
 
@@ -40,6 +41,9 @@ struct Vector2d {
     double &operator[](int i) { return v[i]; }
     double operator[](int i) const { return v[i]; }
 };
+
+using Vector2dVec = std::vector<Vector2d>;       // include/eigen.h:80-81
+using Vector3dVec = std::vector<Vector3d>;
 
 struct Matrix3d {
     double m[9];   // row-major

@@ -115,6 +115,25 @@ int vgref_reconstruct(int model, const double *intr, const double *uv, double *X
     X[0] = Xv(0); X[1] = Xv(1); X[2] = Xv(2);
     return ok ? 1 : 0;
 }
+// the ICamera calls a visgeom user makes on a camera object (generic_camera.h:39-50): bit 0 projectPoint, bit 1
+// projectionJacobian, bit 2 intrinsicJacobian returned true.  Outputs are zeroed first: the reference leaves them
+// untouched on some failure paths.
+int vgref_project_point(int model, const double *intr, const double *X, double *uv, double *dudx, double *dvdx,
+                        double *dudalpha, double *dvdalpha)
+{
+    std::unique_ptr<ICamera> cam(make_camera(model, intr));
+    const int K = cam->numParams();
+    Vector3d Xv(X[0], X[1], X[2]);
+    Vector2d p(0, 0);
+    for (int i = 0; i < 3; i++) dudx[i] = dvdx[i] = 0;
+    for (int i = 0; i < K; i++) dudalpha[i] = dvdalpha[i] = 0;
+    int flags = 0;
+    if (cam->projectPoint(Xv, p)) flags |= 1;
+    uv[0] = p(0); uv[1] = p(1);
+    if (cam->projectionJacobian(Xv, dudx, dvdx)) flags |= 2;
+    if (cam->intrinsicJacobian(Xv, dudalpha, dvdalpha)) flags |= 4;
+    return flags;
+}
 double vgref_bound(int model, const double *intr, int idx, int upper)
 {
     std::unique_ptr<ICamera> cam(make_camera(model, intr));

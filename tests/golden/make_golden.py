@@ -106,6 +106,48 @@ def main():
     print(f"wrote {path}: {len(blob)} arrays, {os.path.getsize(path) / 1024:.0f} KiB")
     priors(ref, orc)
     visual_cov(ref, orc)
+    camera_api(ref)
+
+
+def camera_points(model, seed, n=160):
+    """3D points around the camera of a synthetic calibration: mostly in front, some beside and behind it (EUCM's
+    eta < 1e-3 and hemisphere rejections, eucm.h:46-54), some on the optical axis."""
+    u = sd.uniform(seed, 3, 3 * n).reshape(n, 3)
+    X = np.stack([(2 * u[:, 0] - 1) * 1.5, (2 * u[:, 1] - 1) * 1.0, 0.2 + 1.3 * u[:, 2]], axis=1)
+    X[n // 2: n // 2 + 20, 2] *= -1.0                     # behind the camera
+    X[n // 2 + 20: n // 2 + 30, 2] = -0.3 * np.abs(X[n // 2 + 20: n // 2 + 30, 0])   # far off axis, slightly behind
+    X[-4:, :2] = 0.0                                      # on the axis
+    return np.ascontiguousarray(X)
+
+
+def camera_api(ref):
+    """ICamera::projectPoint / projectionJacobian / intrinsicJacobian / reconstructPoint of the reference's three
+    camera classes on seeded point sets -> reference_camera.npz."""
+    lib = ref.lib
+    blob = {}
+    cams = ((sd.EUCM, sd.EUCM_GT_LEFT, "eucm"), (sd.EUCM, np.array([0.4, 1.2, 300.0, 310.0, 640.0, 400.0]), "eucm_a04"),
+            (sd.UCM, sd.UCM_GT, "ucm"), (sd.MEI, sd.MEI_GT, "mei"))
+    for model, intr, name in cams:
+        intr = np.ascontiguousarray(intr, dtype=np.float64)
+        K = len(intr)
+        X = camera_points(model, 3000 + K + len(name))
+        n = len(X)
+        uv = np.zeros((n, 2)); dpdx = np.zeros((n, 6)); dpda = np.zeros((n, 2 * K)); flags = np.zeros(n, dtype=np.int32)
+        for i in range(n):
+            flags[i] = lib.vgref_project_point(model, dp(intr), dp(X[i]), dp(uv[i]), dp(dpdx[i, :3]), dp(dpdx[i, 3:]),
+                                               dp(dpda[i, :K]), dp(dpda[i, K:]))
+        # back-projection of the projected points (and of a few raw pixels far from the centre)
+        px = np.concatenate([uv[flags & 1 == 1][:40], [[5.0, 5.0], [1275.0, 795.0], [640.0, 400.0], [2500.0, -900.0]]])
+        Xr = np.zeros((len(px), 3)); okr = np.zeros(len(px), dtype=np.int32)
+        for i in range(len(px)):
+            q = np.ascontiguousarray(px[i])
+            okr[i] = lib.vgref_reconstruct(model, dp(intr), dp(q), dp(Xr[i]))
+        blob[f"{name}/model"] = np.array(model); blob[f"{name}/intr"] = intr; blob[f"{name}/X"] = X
+        blob[f"{name}/uv"] = uv; blob[f"{name}/dPdX"] = dpdx; blob[f"{name}/dPdintr"] = dpda; blob[f"{name}/flags"] = flags
+        blob[f"{name}/px"] = px; blob[f"{name}/Xrec"] = Xr; blob[f"{name}/rec_ok"] = okr
+    path = os.path.join(HERE, "reference_camera.npz")
+    np.savez_compressed(path, **blob)
+    print(f"wrote {path}: {len(blob)} arrays, {os.path.getsize(path) / 1024:.0f} KiB")
 
 
 def visual_cov(ref, orc):

@@ -5,6 +5,9 @@
 //   quat t0 t1 t2 qx qy qz qw    -> 6 numbers: Transformation(x, y, z, qx, qy, qz, qw).toArray()
 //   reconstruct M n p0..p(n-1) u v -> ok X Y Z
 //   bounds M n p0..p(n-1) idx    -> lower upper
+//   project M n p0..p(n-1) m X0 Y0 Z0 ..  (GPU) -> per point: ok u v dudx(3) dvdx(3) dudalpha(n) dvdalpha(n) through the
+//                                  single-point virtuals, then "cloud" all_ok and per point: mask u v via projectPointCloud,
+//                                  then per point: mask X Y Z via reconstructPointCloud of those image points
 #include <cstdio>
 #include <iostream>
 #include <memory>
@@ -63,6 +66,37 @@ int main()
                 const bool ok = copy->reconstructPoint(Vector2d(u, v), X);
                 printf("%d %.17g %.17g %.17g\n", ok ? 1 : 0, X[0], X[1], X[2]);
             }
+        } else if (cmd == "project") {
+            int model, n, m;
+            std::cin >> model >> n;
+            std::vector<double> p(n);
+            for (double &x : p) std::cin >> x;
+            std::cin >> m;
+            Vector3dVec X(m);
+            for (auto &x : X) std::cin >> x[0] >> x[1] >> x[2];
+            std::unique_ptr<ICamera> cam(make(model, p.data()));
+            for (int i = 0; i < m; i++) {
+                Vector2d uv(-7, -7);
+                std::vector<double> ju(3), jv(3), au(n), av(n);
+                const bool ok = cam->projectPoint(X[i], uv);
+                const bool okj = cam->projectionJacobian(X[i], ju.data(), jv.data());
+                const bool oka = cam->intrinsicJacobian(X[i], au.data(), av.data());
+                printf("%d %.17g %.17g", (ok ? 1 : 0) | (okj ? 2 : 0) | (oka ? 4 : 0), uv[0], uv[1]);
+                for (double x : ju) printf(" %.17g", x);
+                for (double x : jv) printf(" %.17g", x);
+                for (double x : au) printf(" %.17g", x);
+                for (double x : av) printf(" %.17g", x);
+                printf("\n");
+            }
+            Vector2dVec uv;
+            std::vector<bool> mask;
+            const bool all = cam->projectPointCloud(X, uv, mask);
+            printf("%d\n", all ? 1 : 0);
+            for (int i = 0; i < m; i++) printf("%d %.17g %.17g\n", mask[i] ? 1 : 0, uv[i][0], uv[i][1]);
+            Vector3dVec back;
+            std::vector<bool> rmask;
+            cam->reconstructPointCloud(uv, back, rmask);
+            for (int i = 0; i < m; i++) printf("%d %.17g %.17g %.17g\n", rmask[i] ? 1 : 0, back[i][0], back[i][1], back[i][2]);
         } else {
             fprintf(stderr, "unknown command %s\n", cmd.c_str());
             return 2;

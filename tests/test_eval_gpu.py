@@ -182,3 +182,42 @@ def test_deterministic(gpu):
     b = gpu.eval_chain(*args, want_H=True)
     for k in ("r", "J_intr", "H"):
         assert (a[k] == b[k]).all()
+
+
+def test_concurrent_host_calls(gpu, oracle):
+    """vg_eval_chain from four host threads at once (Ceres evaluates residual blocks from num_threads threads; every
+    calling thread owns its streams, pinned slots and device workspace): each thread's outputs against the oracle, on
+    problems of different models and sizes, repeated so that the calls really overlap."""
+    import threading
+    jobs = []
+    for t, (model, n_img) in enumerate([(sd.EUCM, 700), (sd.MEI, 450), (sd.UCM, 900), (sd.EUCM, 33)]):
+        d = sd.make_mono(model, n_img, seed=600 + t)
+        want = oracle.evaluate_batch(model, d["intr_init"], d["board"], d["obs"], [d["xi_init"]], [D], [0], want_H=True)
+        jobs.append((model, d, want))
+    errors = []
+
+    def work(model, d, want):
+        try:
+            for _ in range(6):
+                g = gpu.eval_chain(model, d["intr_init"], d["board"], d["obs"], [d["xi_init"]], [D], [0], want_H=True)
+                compare_eval(g, want, f"thread model={model}")
+        except Exception as e:       # noqa: BLE001 -- reported below, in the main thread
+            errors.append(repr(e))
+    threads = [threading.Thread(target=work, args=j) for j in jobs]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+
+
+def test_host_call_chunking(gpu, oracle, monkeypatch):
+    """The chunked host path (chunk boundaries, the ragged last chunk, helper copy threads, a stereo chain whose global
+    element lives in the fixed inputs): 3 000 images cut into many small chunks, every element against the oracle."""
+    s = sd.make_stereo(3000, seed=611)
+    args = (sd.EUCM, s["intr2_init"], s["board"], s["obs2"], [s["xi12_init"], s["xi_init"]], [I, D], [1, 0])
+    g = gpu.eval_chain(*args, want_H=True)
+    o = oracle.evaluate_batch(*args, want_H=True, threads=8)
+    compare_eval(g, o, "chunked stereo")
+    g2 = gpu.eval_chain(*args, want_H=True, want_J=False)
+    assert (g2["r"] == g["r"]).all() and (g2["H"] == g["H"]).all()

@@ -91,3 +91,59 @@ def test_peer_exchange_matches_single_gpu(gpu, tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
                        capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0 and "peer exchange ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def _two_local_ranks(gpu, d, n):
+    """Two problems of this process on device 0, connected as ranks 0 / 1 of one exchange group through the addresses
+    of their inboxes (vg_problem_peer_connect_local): the protocol itself needs no second GPU."""
+    import synthdata as sd
+    probs = []
+    for r in range(2):
+        lo, hi = r * n // 2, (r + 1) * n // 2
+        P = gpu.Problem(0)
+        cam = P.add_camera(sd.EUCM, d["intr_init"])
+        tr = P.add_transform(d["xi_init"][lo:hi], is_global=False)
+        P.add_dataset(cam, d["board"], d["obs"][lo:hi], [tr], [0])
+        probs.append(P)
+    inboxes = [P.peer_inbox() for P in probs]
+    for r, P in enumerate(probs):
+        P.peer_connect_local(r, inboxes)
+    return probs
+
+
+def test_local_ranks_deferred_exchange_on_one_gpu(gpu):
+    """Deferred mode (the kernel's tail posts, the next launch or the fetch collects) with both ranks driven from one
+    host thread on one GPU: sums equal to the single problem holding all the images, bit-identical on both ranks."""
+    import numpy as np
+    import synthdata as sd
+    n = 90
+    d = sd.make_mono(sd.EUCM, n, seed=2027)
+    A = gpu.Problem(0)
+    cam = A.add_camera(sd.EUCM, d["intr_init"])
+    tr = A.add_transform(d["xi_init"], is_global=False)
+    A.add_dataset(cam, d["board"], d["obs"], [tr], [0])
+    ca, ra = A.evaluate(want_reduced=True)
+    P0, P1 = _two_local_ranks(gpu, d, n)
+    for burst in (1, 3, 2):                       # slot parities reused, collection by the next launch's head
+        for _ in range(burst):
+            P0.evaluate_async(); P1.evaluate_async()
+        (c0, r0), (c1, r1) = P0.fetch_reduced(), P1.fetch_reduced()
+        assert abs(c0 - ca) <= 1e-12 * ca and np.abs(r0 - ra).max() <= 1e-11 * np.abs(ra).max()
+        assert c0 == c1 and (r0 == r1).all()
+
+
+def test_missing_rank_is_reported_not_nan(gpu):
+    """A rank that never posts: the collect gives up after the configured number of polls and the next call that
+    synchronises returns VG_ERR_PEER (-6) with a message, instead of handing NaN sums to the LM loop."""
+    import synthdata as sd
+    n = 40
+    d = sd.make_mono(sd.EUCM, n, seed=2028)
+    P0, P1 = _two_local_ranks(gpu, d, n)
+    P0.set_peer_timeout(20000)                    # a few milliseconds of polling
+    P0.evaluate_async()                           # rank 1 never evaluates
+    with pytest.raises(gpu.VisgeomError, match=r"error -6: peer exchange 1 timed out on rank 0"):
+        P0.fetch_reduced()
+    # the exchange group is out of step from here on, as after any lost rank; a fresh pair works
+    Q0, Q1 = _two_local_ranks(gpu, d, n)
+    Q0.evaluate_async(); Q1.evaluate_async()
+    assert Q0.fetch_reduced()[0] == Q1.fetch_reduced()[0]

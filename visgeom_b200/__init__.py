@@ -66,6 +66,12 @@ def lib() -> C.CDLL:
     L.vg_eval_chain_dev.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                     c_ip, c_ip, C.POINTER(C.c_void_p), C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]
+    c_up = C.POINTER(C.c_ubyte)
+    L.vg_project_points.argtypes = [C.c_int, c_dp, C.c_longlong, c_dp, c_dp, c_dp, c_dp, c_up]
+    L.vg_reconstruct_points.argtypes = [C.c_int, c_dp, C.c_longlong, c_dp, c_dp, c_up]
+    L.vg_project_points_dev.argtypes = [C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p]
+    L.vg_reconstruct_points_dev.argtypes = [C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     if hasattr(L, "vg_problem_create"):
         L.vg_problem_create.restype = C.c_void_p
         L.vg_problem_create.argtypes = [C.c_int]
@@ -84,6 +90,9 @@ def lib() -> C.CDLL:
                                              c_dp, c_dp, c_dp]
         L.vg_problem_peer_export.argtypes = [C.c_void_p, C.c_void_p]
         L.vg_problem_peer_connect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.vg_problem_peer_inbox.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), c_ip]
+        L.vg_problem_peer_connect_local.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), c_ip]
+        L.vg_problem_set_peer_timeout.argtypes = [C.c_void_p, C.c_longlong]
         L.vg_visual_cov.argtypes = [C.c_int, c_dp, c_dp, C.c_int, c_dp, C.c_double, C.c_int, c_dp, c_dp]
         L.vg_problem_set_allreduce.argtypes = [C.c_void_p, ALLREDUCE_FN, C.c_void_p, C.c_int, C.c_int]
         L.vg_problem_materialize_jacobians.argtypes = [C.c_void_p, C.c_int]
@@ -145,11 +154,13 @@ def model_bounds(model: int):
 
 
 def eval_chain(model, intr, board, obs, xi_list, status, is_global,
-               want_r=True, want_J=True, want_H=False):
+               want_r=True, want_J=True, want_H=False, out=None):
     """Batched GenericProjectionJac::Evaluate through the host-buffer C ABI.
 
     obs (n_img, 2P); xi_list[e] is (n_img, 6) for a sequence or (6,) for a global
     transform.  Returns dict(r, J_intr, J_xi[], H) of numpy arrays (Ceres layout).
+    out: a dict a previous call returned -- its arrays are written again instead of allocating new ones (Ceres keeps
+    its residual / Jacobian buffers across evaluations too).
     """
     K = _check(lib().vg_model_num_params(model))       # "invalid camera model name" comes from the library
     intr = _f64(intr); board = _f64(board); obs = _f64(obs)
@@ -161,10 +172,14 @@ def eval_chain(model, intr, board, obs, xi_list, status, is_global,
     st = np.ascontiguousarray(status, dtype=np.int32)
     ig = np.ascontiguousarray(is_global, dtype=np.int32)
     xi_ptrs = (c_dp * Lc)(*[_dp(x) for x in xis])
-    r = np.empty((n_img, 2 * P)) if want_r else None
-    Ja = np.empty((n_img, 2 * P, K)) if want_J else None
-    Je = [np.empty((n_img, 2 * P, 6)) for _ in range(Lc)] if want_J else None
-    H = np.empty((n_img, hessian_entries(model, Lc))) if want_H else None
+    if out is not None:
+        r, Ja, Je, H = out["r"], out["J_intr"], out["J_xi"], out["H"]
+        assert (r is not None) == want_r and (Ja is not None) == want_J and (H is not None) == want_H
+    else:
+        r = np.empty((n_img, 2 * P)) if want_r else None
+        Ja = np.empty((n_img, 2 * P, K)) if want_J else None
+        Je = [np.empty((n_img, 2 * P, 6)) for _ in range(Lc)] if want_J else None
+        H = np.empty((n_img, hessian_entries(model, Lc))) if want_H else None
     je_ptrs = (c_dp * Lc)(*[_dp(j) for j in Je]) if want_J else None
     _check(lib().vg_eval_chain(model, _dp(intr), n_img, P, _dp(board), _dp(obs), Lc,
                                st.ctypes.data_as(c_ip), ig.ctypes.data_as(c_ip), xi_ptrs,
@@ -216,6 +231,36 @@ def eval_chain_dev(model, intr, board, obs, xi_list, status, is_global, n_img, P
     _check(lib().vg_eval_chain_dev(model, intr, n_img, P, board, obs, Lc,
                                    st.ctypes.data_as(c_ip), ig.ctypes.data_as(c_ip), xi_ptrs,
                                    seq_index, r, J_intr, je_ptrs, H, stream))
+
+
+def project_points(model, intr, X, want_jacobians=True, uv_init=None):
+    """ICamera::projectPointCloud + projectionJacobian + intrinsicJacobian for n points (vg_project_points).
+    Returns uv (n,2), ok (n,) bool, dPdX (n,2,3), dPdintr (n,2,K)."""
+    L = lib()
+    intr, X = _f64(intr), _f64(X).reshape(-1, 3)
+    n, K = X.shape[0], NUM_PARAMS[model]
+    uv = np.zeros((n, 2)) if uv_init is None else _f64(uv_init).copy()
+    ok = np.zeros(n, dtype=np.uint8)
+    dx = np.zeros((n, 2, 3)) if want_jacobians else None
+    da = np.zeros((n, 2, K)) if want_jacobians else None
+    nul = C.cast(None, c_dp)
+    _check(L.vg_project_points(model, intr.ctypes.data_as(c_dp), n, X.ctypes.data_as(c_dp), uv.ctypes.data_as(c_dp),
+                               dx.ctypes.data_as(c_dp) if want_jacobians else nul,
+                               da.ctypes.data_as(c_dp) if want_jacobians else nul,
+                               ok.ctypes.data_as(C.POINTER(C.c_ubyte))))
+    return uv, ok.astype(bool), dx, da
+
+
+def reconstruct_points(model, intr, uv, X_init=None):
+    """ICamera::reconstructPointCloud for n image points (vg_reconstruct_points): X (n,3), ok (n,) bool."""
+    L = lib()
+    intr, uv = _f64(intr), _f64(uv).reshape(-1, 2)
+    n = uv.shape[0]
+    X = np.zeros((n, 3)) if X_init is None else _f64(X_init).copy()
+    ok = np.zeros(n, dtype=np.uint8)
+    _check(L.vg_reconstruct_points(model, intr.ctypes.data_as(c_dp), n, uv.ctypes.data_as(c_dp), X.ctypes.data_as(c_dp),
+                                   ok.ctypes.data_as(C.POINTER(C.c_ubyte))))
+    return X, ok.astype(bool)
 
 
 class Problem:
@@ -299,6 +344,22 @@ class Problem:
         assert len(handles) == 64 * nranks
         buf = (C.c_ubyte * len(handles)).from_buffer_copy(handles)
         _check(self.L.vg_problem_peer_connect(self.h, rank, nranks, buf))
+
+    def peer_inbox(self):
+        """(device address of this problem's inbox, its device): for problems of one process (peer_connect_local)."""
+        ptr, dev = C.c_void_p(), C.c_int()
+        _check(self.L.vg_problem_peer_inbox(self.h, C.byref(ptr), C.byref(dev)))
+        return ptr.value, dev.value
+
+    def peer_connect_local(self, rank, inboxes):
+        """inboxes: every rank's peer_inbox() in rank order (same process)."""
+        n = len(inboxes)
+        ptrs = (C.c_void_p * n)(*[i[0] for i in inboxes])
+        devs = (C.c_int * n)(*[i[1] for i in inboxes])
+        _check(self.L.vg_problem_peer_connect_local(self.h, rank, n, ptrs, devs))
+
+    def set_peer_timeout(self, polls):
+        _check(self.L.vg_problem_set_peer_timeout(self.h, int(polls)))
 
     def set_allreduce(self, fn, rank, nranks):
         """fn(buf_ptr:int, count:int, stream:int) -> None sums count doubles in place across ranks."""

@@ -23,9 +23,7 @@ int fail_cuda(cudaError_t e, const char *where)
 }
 unsigned long long &launch_counter() { return g_launches; }
 
-static char *g_ws = nullptr;
-static size_t g_ws_bytes = 0;
-static int g_ws_dev = -1;
+void release_host_ctx();     // vg_host.cu: the calling thread's streams, pinned slots and device workspace
 
 static int model_K(int model)
 {
@@ -87,12 +85,9 @@ int vg_hessian_entries(int model, int chain_len)
     return W * (W + 1) / 2;
 }
 
-unsigned long long vg_launch_count(void) { return g_launches; }
+unsigned long long vg_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
-void vg_release_workspace(void)
-{
-    if (g_ws) { cudaFree(g_ws); g_ws = nullptr; g_ws_bytes = 0; g_ws_dev = -1; }
-}
+void vg_release_workspace(void) { release_host_ctx(); }
 
 static int check_eval_args(int model, int n_img, int P, int chain_len, const void *intr, const void *board,
                            const void *obs, const int *status, const int *is_global, const void *xi)
@@ -135,68 +130,6 @@ int vg_eval_chain_dev(int model, const double *intr, int n_img, int P,
     cudaError_t e = launch_eval(model, chain_len, a, static_cast<cudaStream_t>(stream), &g_launches);
     if (e != cudaSuccess) return fail_cuda(e, "reproj_eval_kernel launch");
     return VG_OK;
-}
-
-int vg_eval_chain(int model, const double *intr, int n_img, int P,
-                  const double *board, const double *obs,
-                  int chain_len, const int *status, const int *is_global,
-                  const double *const *xi,
-                  double *r, double *J_intr, double *const *J_xi, double *H)
-{
-    int rc = check_eval_args(model, n_img, P, chain_len, intr, board, obs, status, is_global, xi);
-    if (rc) return rc;
-    if (vg_device_count() < 1) return fail(VG_ERR_CUDA, "no CUDA device: this engine has no CPU path");
-    const int K = model_K(model);
-    const size_t rows = (size_t)n_img * 2 * P;
-    const int ne = vg_hessian_entries(model, chain_len);
-    // one device slab: inputs then outputs, every piece 256-byte aligned
-    struct Piece { size_t off, bytes; };
-    size_t total = 0;
-    auto reserve = [&](size_t bytes) { Piece p{total, bytes}; total += (bytes + 255) & ~size_t(255); return p; };
-    Piece p_intr = reserve(K * 8), p_board = reserve((size_t)P * 24), p_obs = reserve(rows * 8);
-    Piece p_xi[VG_MAX_CHAIN], p_je[VG_MAX_CHAIN];
-    for (int e = 0; e < chain_len; e++) p_xi[e] = reserve(is_global[e] ? 48 : (size_t)n_img * 48);
-    Piece p_r = reserve(r ? rows * 8 : 0), p_ja = reserve(J_intr ? rows * K * 8 : 0);
-    for (int e = 0; e < chain_len; e++) p_je[e] = reserve((J_xi && J_xi[e]) ? rows * 48 : 0);
-    Piece p_h = reserve(H ? (size_t)n_img * ne * 8 : 0);
-    // grow-only device workspace kept between calls (released by vg_release_workspace)
-    int dev = 0;
-    VG_CUDA(cudaGetDevice(&dev));
-    if (g_ws && (g_ws_dev != dev || g_ws_bytes < total)) { cudaFree(g_ws); g_ws = nullptr; g_ws_bytes = 0; }
-    if (!g_ws) {
-        VG_CUDA(cudaMalloc(&g_ws, total ? total : 256));
-        g_ws_bytes = total ? total : 256;
-        g_ws_dev = dev;
-    }
-    char *d = g_ws;
-    cudaStream_t st = nullptr;
-    auto cleanup = [&](int code) { return code; };
-#define VG_TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cleanup(fail_cuda(e__, #call)); } while (0)
-    VG_TRY(cudaMemcpyAsync(d + p_intr.off, intr, p_intr.bytes, cudaMemcpyHostToDevice, st));
-    VG_TRY(cudaMemcpyAsync(d + p_board.off, board, p_board.bytes, cudaMemcpyHostToDevice, st));
-    if (rows) VG_TRY(cudaMemcpyAsync(d + p_obs.off, obs, p_obs.bytes, cudaMemcpyHostToDevice, st));
-    const double *dxi[VG_MAX_CHAIN];
-    double *dje[VG_MAX_CHAIN];
-    for (int e = 0; e < chain_len; e++) {
-        if (p_xi[e].bytes) VG_TRY(cudaMemcpyAsync(d + p_xi[e].off, xi[e], p_xi[e].bytes, cudaMemcpyHostToDevice, st));
-        dxi[e] = reinterpret_cast<const double *>(d + p_xi[e].off);
-        dje[e] = p_je[e].bytes ? reinterpret_cast<double *>(d + p_je[e].off) : nullptr;
-    }
-    rc = vg_eval_chain_dev(model, reinterpret_cast<const double *>(d + p_intr.off), n_img, P,
-                           reinterpret_cast<const double *>(d + p_board.off),
-                           reinterpret_cast<const double *>(d + p_obs.off), chain_len, status, is_global, dxi,
-                           nullptr, p_r.bytes ? reinterpret_cast<double *>(d + p_r.off) : nullptr,
-                           p_ja.bytes ? reinterpret_cast<double *>(d + p_ja.off) : nullptr, dje,
-                           p_h.bytes ? reinterpret_cast<double *>(d + p_h.off) : nullptr, st);
-    if (rc) return cleanup(rc);
-    if (p_r.bytes) VG_TRY(cudaMemcpyAsync(r, d + p_r.off, p_r.bytes, cudaMemcpyDeviceToHost, st));
-    if (p_ja.bytes) VG_TRY(cudaMemcpyAsync(J_intr, d + p_ja.off, p_ja.bytes, cudaMemcpyDeviceToHost, st));
-    for (int e = 0; e < chain_len; e++)
-        if (p_je[e].bytes) VG_TRY(cudaMemcpyAsync(J_xi[e], d + p_je[e].off, p_je[e].bytes, cudaMemcpyDeviceToHost, st));
-    if (p_h.bytes) VG_TRY(cudaMemcpyAsync(H, d + p_h.off, p_h.bytes, cudaMemcpyDeviceToHost, st));
-    VG_TRY(cudaStreamSynchronize(st));
-#undef VG_TRY
-    return cleanup(VG_OK);
 }
 
 }  // extern "C"

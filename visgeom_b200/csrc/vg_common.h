@@ -13,6 +13,10 @@ void set_error(const std::string &msg);
 int fail(int code, const std::string &msg);
 int fail_cuda(cudaError_t e, const char *where);
 unsigned long long &launch_counter();
+#ifndef VG_COUNT_LAUNCH_DEFINED
+#define VG_COUNT_LAUNCH_DEFINED
+inline void count_launch(unsigned long long *c) { __atomic_fetch_add(c, 1ull, __ATOMIC_RELAXED); }   // several host threads
+#endif
 
 #define VG_CUDA(call)                                              \
     do {                                                           \

@@ -7,6 +7,12 @@
 
 namespace vg {
 
+// the library-wide launch counter (vg_launch_count) may be bumped from several host threads at once
+#ifndef VG_COUNT_LAUNCH_DEFINED
+#define VG_COUNT_LAUNCH_DEFINED
+inline void count_launch(unsigned long long *c) { __atomic_fetch_add(c, 1ull, __ATOMIC_RELAXED); }
+#endif
+
 constexpr int MAX_CHAIN = 5;
 constexpr int EVAL_REDUCE_GROUP = 24;     // rows per first-level group of the fused reduction (592 CTAs: 25 groups)
 

@@ -843,7 +843,7 @@ cudaError_t launch_fixed(const EvalArgs &args, const LaunchPlan &pl, cudaStream_
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
     const cudaError_t le = cudaLaunchKernelEx(&cfg, reproj_eval_kernel<MODEL, L, PC>, args, pl.G, pl.PCG);
-    if (launches) (*launches)++;
+    if (launches) count_launch(launches);
     return le != cudaSuccess ? le : cudaGetLastError();
 }
 

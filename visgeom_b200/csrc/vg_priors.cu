@@ -658,7 +658,7 @@ cudaError_t launch_prior_setup(int n_tp, const double *tp_in, double *tp_const, 
     const int n = n_tp + n_op;
     if (n <= 0) return cudaSuccess;
     prior_setup_kernel<<<(n + 63) / 64, 64, 0, sl.stream>>>(n_tp, tp_in, tp_const, n_op, op_in, op_const);
-    if (sl.launches) (*sl.launches)++;
+    if (sl.launches) count_launch(sl.launches);
     return cudaGetLastError();
 }
 
@@ -679,7 +679,7 @@ cudaError_t launch_chain_factor(const DatasetDesc *d_desc, int Ks, const int *po
     if (c.n_seg <= 0) return cudaSuccess;
     chain_factor_kernel<<<(c.n_seg + CHAIN_WARPS - 1) / CHAIN_WARPS, CHAIN_WARPS * 32, 0, sl.stream>>>(
         d_desc, Ks, pose_start, contrib_ds, contrib_img, scale, lm, ws, c, seg_gmax, fail_flag);
-    if (sl.launches) (*sl.launches)++;
+    if (sl.launches) count_launch(sl.launches);
     return cudaGetLastError();
 }
 
@@ -689,7 +689,7 @@ cudaError_t launch_chain_backsub(int Ks, const double *const *seq_cur, double *c
 {
     if (c.n_seg <= 0) return cudaSuccess;
     chain_backsub_kernel<<<(c.n_seg + 31) / 32, 32, 0, sl.stream>>>(Ks, seq_cur, seq_cand, pose_seq, pose_local, ws, c, seg_partial);
-    if (sl.launches) (*sl.launches)++;
+    if (sl.launches) count_launch(sl.launches);
     return cudaGetLastError();
 }
 
@@ -733,7 +733,7 @@ int vg_eval_transformation_prior(int n, const double *stiffness, const double *x
     VG_CUDA(dr.alloc(6 * m));
     if (J) VG_CUDA(dj.alloc(36 * m));
     tp_functor_kernel<<<(n + 63) / 64, 64>>>(n, ds.p, dp.p, dx.p, dr.p, J ? dj.p : nullptr);
-    launch_counter()++;
+    count_launch(&launch_counter());
     VG_CUDA(cudaGetLastError());
     VG_CUDA(dr.down(r, 6 * m));
     if (J) VG_CUDA(dj.down(J, 36 * m));
@@ -753,7 +753,7 @@ int vg_eval_odometry_prior(int n, double errV, double errW, double lambda, const
     if (J1) VG_CUDA(j1.alloc(36 * m));
     if (J2) VG_CUDA(j2.alloc(36 * m));
     op_functor_kernel<<<(n + 63) / 64, 64>>>(n, errV, errW, lambda, o1.p, o2.p, x1.p, x2.p, dr.p, J1 ? j1.p : nullptr, J2 ? j2.p : nullptr);
-    launch_counter()++;
+    count_launch(&launch_counter());
     VG_CUDA(cudaGetLastError());
     VG_CUDA(dr.down(r, 6 * m));
     if (J1) VG_CUDA(j1.down(J1, 36 * m));
@@ -778,7 +778,7 @@ int vg_visual_cov(int model, const double *intr, const double *xi_board, int P, 
     if (model == VG_MODEL_EUCM) visual_cov_kernel<MODEL_EUCM><<<blocks, 128>>>(di.p, dx.p, P, db.p, stiffness, n, dp.p, dc.p);
     else if (model == VG_MODEL_UCM) visual_cov_kernel<MODEL_UCM><<<blocks, 128>>>(di.p, dx.p, P, db.p, stiffness, n, dp.p, dc.p);
     else visual_cov_kernel<MODEL_MEI><<<blocks, 128>>>(di.p, dx.p, P, db.p, stiffness, n, dp.p, dc.p);
-    launch_counter()++;
+    count_launch(&launch_counter());
     VG_CUDA(cudaGetLastError());
     VG_CUDA(dc.down(cov, 36 * (size_t)n));
     return VG_OK;

@@ -18,6 +18,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <vector>
 
 using namespace vg;
@@ -147,7 +148,10 @@ struct vg_problem {
     unsigned long long pending_epoch = 0;
     int pending_set = 0;
     unsigned long long *d_collect_done = nullptr;
-    PeerCtx next_peer_ctx() { return PeerCtx{d_peer_ptrs, rank, nranks, ++epoch}; }
+    unsigned long long *h_peer_fail = nullptr;  // host-mapped: the number of an exchange whose collect gave up (vg_peer.cuh)
+    long long peer_spin_limit = 0;
+    PeerCtx peer_ctx(unsigned long long e) const { return PeerCtx{d_peer_ptrs, rank, nranks, e, h_peer_fail, peer_spin_limit}; }
+    PeerCtx next_peer_ctx() { return peer_ctx(++epoch); }
     unsigned int *d_solver_tickets = nullptr;   // "last block done" counters of pose_factor / pose_backsub
     // the plain structure's two-launch step (vg_solver_fast.cu): dataset / sequence it applies to, or -1
     int fast_ds = -1, fast_tr = -1;
@@ -566,6 +570,17 @@ int prepare(vg_problem *p)
     return VG_OK;
 }
 
+// after a synchronisation with the device: did a collect give up on a rank that never posted?
+int check_peer_fail(vg_problem *p)
+{
+    if (!p->h_peer_fail) return VG_OK;
+    const unsigned long long e = *reinterpret_cast<volatile unsigned long long *>(p->h_peer_fail);
+    if (!e) return VG_OK;
+    *p->h_peer_fail = 0;
+    return fail(VG_ERR_PEER, "peer exchange " + std::to_string(e) + " timed out on rank " + std::to_string(p->rank) +
+                                 ": a rank never posted its block (it died, or issued a different sequence of evaluations)");
+}
+
 // fused residual + Jacobian + normal-equation kernels of every dataset at parameter set s,
 // then the shared-block reduction -> segment E (A, g_a, cost) of that set's reduction buffer
 // the sum of an exchange that an evaluation kernel posted and nothing has collected yet
@@ -574,7 +589,7 @@ int flush_pending(vg_problem *p)
     if (!p->pending) return VG_OK;
     p->pending = false;
     SolverLaunch sl{p->stream, &launch_counter()};
-    const PeerCtx pc{p->d_peer_ptrs, p->rank, p->nranks, p->pending_epoch};
+    const PeerCtx pc = p->peer_ctx(p->pending_epoch);
     cudaError_t e = launch_peer_collect(p->d_redbuf[p->pending_set], red_segE_size(p->Ks), pc, p->d_collect_done, sl);
     if (e != cudaSuccess) return fail_cuda(e, "peer collect");
     return VG_OK;
@@ -625,7 +640,7 @@ int evaluate_set(vg_problem *p, int s, bool timed, bool deferred = false)
                 if (deferred) {
                     a.peer_deferred = 1;
                     if (p->pending) {
-                        a.collect = PeerCtx{p->d_peer_ptrs, p->rank, p->nranks, p->pending_epoch};
+                        a.collect = p->peer_ctx(p->pending_epoch);
                         a.collect_buf = p->d_redbuf[p->pending_set];
                         a.collect_done = p->d_collect_done;
                     }
@@ -688,7 +703,7 @@ int fetch_segment(vg_problem *p, int s, int off, int count, int fetch = 0)
     if (fetch < count) fetch = count;
     VG_CUDA(cudaMemcpyAsync(p->h_red + off, p->d_redbuf[s] + off, sizeof(double) * fetch, cudaMemcpyDeviceToHost, p->stream));
     VG_CUDA(cudaStreamSynchronize(p->stream));
-    return VG_OK;
+    return check_peer_fail(p);
 }
 
 int ensure_materialized(vg_problem *p)
@@ -767,6 +782,7 @@ void vg_problem_destroy(vg_problem *p)
     }
     for (void *q : p->peer_opened) cudaIpcCloseMemHandle(q);
     cudaFree(p->d_peer_ptrs); cudaFree(p->d_inbox); cudaFree(p->d_collect_done);
+    if (p->h_peer_fail) cudaFreeHost(p->h_peer_fail);
     cudaEventDestroy(p->ev0); cudaEventDestroy(p->ev1);
     cudaStreamDestroy(p->own_stream);
     delete p;
@@ -940,6 +956,18 @@ int vg_problem_set_pose_constant(vg_problem *p, int transform, int index, int co
     return VG_OK;
 }
 
+static int finish_peer_connect(vg_problem *p, int rank, int nranks, const std::vector<unsigned long long *> &ptrs)
+{
+    VG_CUDA(cudaMalloc(&p->d_collect_done, sizeof(unsigned long long)));
+    VG_CUDA(cudaMemset(p->d_collect_done, 0, sizeof(unsigned long long)));
+    VG_CUDA(cudaMalloc(&p->d_peer_ptrs, sizeof(unsigned long long *) * nranks));
+    VG_CUDA(cudaMemcpy(p->d_peer_ptrs, ptrs.data(), sizeof(unsigned long long *) * nranks, cudaMemcpyHostToDevice));
+    VG_CUDA(cudaHostAlloc(&p->h_peer_fail, sizeof(unsigned long long), cudaHostAllocMapped));
+    *p->h_peer_fail = 0;
+    p->rank = rank; p->nranks = nranks; p->peers = true; p->epoch = 0;
+    return VG_OK;
+}
+
 int vg_problem_peer_export(vg_problem *p, void *ipc_handle_out)
 {
     if (!p || !ipc_handle_out) return fail(VG_ERR_INVALID, "null argument");
@@ -973,11 +1001,47 @@ int vg_problem_peer_connect(vg_problem *p, int rank, int nranks, const void *ipc
         p->peer_opened.push_back(q);
         ptrs[r] = static_cast<unsigned long long *>(q);
     }
-    VG_CUDA(cudaMalloc(&p->d_collect_done, sizeof(unsigned long long)));
-    VG_CUDA(cudaMemset(p->d_collect_done, 0, sizeof(unsigned long long)));
-    VG_CUDA(cudaMalloc(&p->d_peer_ptrs, sizeof(unsigned long long *) * nranks));
-    VG_CUDA(cudaMemcpy(p->d_peer_ptrs, ptrs.data(), sizeof(unsigned long long *) * nranks, cudaMemcpyHostToDevice));
-    p->rank = rank; p->nranks = nranks; p->peers = true; p->epoch = 0;
+    return finish_peer_connect(p, rank, nranks, ptrs);
+}
+
+int vg_problem_peer_inbox(vg_problem *p, void **inbox_out, int *device_out)
+{
+    if (!p || !inbox_out) return fail(VG_ERR_INVALID, "null argument");
+    VG_CUDA(cudaSetDevice(p->device));
+    if (!p->d_inbox) {
+        VG_CUDA(cudaMalloc(&p->d_inbox, peer_inbox_bytes()));
+        VG_CUDA(cudaMemset(p->d_inbox, 0, peer_inbox_bytes()));
+    }
+    *inbox_out = p->d_inbox;
+    if (device_out) *device_out = p->device;
+    return VG_OK;
+}
+
+int vg_problem_peer_connect_local(vg_problem *p, int rank, int nranks, void *const *inboxes, const int *devices)
+{
+    if (!p || !inboxes || nranks < 1 || nranks > PEER_MAX_RANKS || rank < 0 || rank >= nranks)
+        return fail(VG_ERR_INVALID, "vg_problem_peer_connect_local: bad arguments");
+    if (!p->d_inbox || inboxes[rank] != p->d_inbox) return fail(VG_ERR_INVALID, "vg_problem_peer_connect_local: inboxes[rank] is not this problem's inbox");
+    if (p->peers) return fail(VG_ERR_INVALID, "vg_problem_peer_connect_local: already connected");
+    VG_CUDA(cudaSetDevice(p->device));
+    free_prepared(p);
+    std::vector<unsigned long long *> ptrs(nranks, nullptr);
+    for (int r = 0; r < nranks; r++) {
+        if (!inboxes[r]) return fail(VG_ERR_INVALID, "vg_problem_peer_connect_local: null inbox");
+        if (devices && devices[r] != p->device) {
+            const cudaError_t e = cudaDeviceEnablePeerAccess(devices[r], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail_cuda(e, "cudaDeviceEnablePeerAccess");
+            cudaGetLastError();
+        }
+        ptrs[r] = static_cast<unsigned long long *>(inboxes[r]);
+    }
+    return finish_peer_connect(p, rank, nranks, ptrs);
+}
+
+int vg_problem_set_peer_timeout(vg_problem *p, long long polls)
+{
+    if (!p || polls < 0) return fail(VG_ERR_INVALID, "vg_problem_set_peer_timeout: bad arguments");
+    p->peer_spin_limit = polls;
     return VG_OK;
 }
 
@@ -1036,6 +1100,10 @@ int vg_problem_fetch_reduced(vg_problem *p, double *cost, double *reduced)
     const int Ks = p->Ks, n = red_off_model(Ks);
     VG_CUDA(cudaMemcpyAsync(p->h_red, p->d_redbuf[p->cur], sizeof(double) * n, cudaMemcpyDeviceToHost, p->stream));
     VG_CUDA(cudaStreamSynchronize(p->stream));
+    {
+        int rc = check_peer_fail(p);
+        if (rc) return rc;
+    }
     if (cost) *cost = p->h_red[red_off_cost(Ks)];
     if (reduced) memcpy(reduced, p->h_red, sizeof(double) * (Ks * Ks + Ks));
     return VG_OK;

@@ -529,7 +529,7 @@ cudaError_t launch_fast_step(const FastDesc &d, int n_pose, int Ks, double *scal
     else if (d.W == 12 && d.pose_col == 5) e = launch_factor<12, 5>(d, n_pose, Ks, scale, lm, ws, rows, grp_rows, gmax_rows, tickets, fail_flag, smem, sl.stream);
     else if (d.W == 17 && d.pose_col == 10) e = launch_factor<17, 10>(d, n_pose, Ks, scale, lm, ws, rows, grp_rows, gmax_rows, tickets, fail_flag, smem, sl.stream);
     else e = launch_factor<0, 0>(d, n_pose, Ks, scale, lm, ws, rows, grp_rows, gmax_rows, tickets, fail_flag, smem, sl.stream);
-    if (sl.launches) (*sl.launches)++;
+    if (sl.launches) count_launch(sl.launches);
     if (e != cudaSuccess) return e;
     if (between) cudaEventRecord(between, sl.stream);
     // (backsub == false: only the gradient test is still due -- the kernel still leaves the scalars; the candidate
@@ -543,7 +543,7 @@ cudaError_t launch_fast_step(const FastDesc &d, int n_pose, int Ks, double *scal
     cfg.attrs = attr; cfg.numAttrs = between ? 0 : 1;
     e = cudaLaunchKernelEx(&cfg, fast_backsub_kernel, n_pose, Ks, ng, (const double *)grp_rows, sa, lm, seq_cur, seq_cand,
                            (const double *)ws, partial, tickets + ng, fail_flag, host_out);
-    if (sl.launches) (*sl.launches)++;
+    if (sl.launches) count_launch(sl.launches);
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 

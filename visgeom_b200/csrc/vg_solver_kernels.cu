@@ -655,12 +655,12 @@ cudaError_t launch_pose_schur(const DatasetDesc *d_desc, int n_pose, int Ks,
         pose_factor_kernel<<<nb_pose, FACTOR_THREADS, smem, sl.stream>>>(d_desc, n_pose, Ks, pose_start, contrib_ds,
                                                                         contrib_img, scale, lm, ws, p_gmax, p_gram, fail_flag,
                                                                         chain_mask, ft, z_smem);
-        if (sl.launches) (*sl.launches)++;
+        if (sl.launches) count_launch(sl.launches);
     }
     if (ft.ticket) return cudaGetLastError();
     finalize_gram_kernel<<<1, FIN_THREADS, 0, sl.stream>>>(Ks, n_pose > 0 ? nb_pose : 0, p_gram, n_pose > 0 ? nb_pose + n_seg : 0, p_gmax,
                                                    red, fail_flag, rank, nranks);
-    if (sl.launches) (*sl.launches)++;
+    if (sl.launches) count_launch(sl.launches);
     return cudaGetLastError();
 }
 
@@ -675,7 +675,7 @@ cudaError_t launch_pose_backsub(int n_pose, int Ks, const double *delta_a,
     if (n_pose > 0) {
         pose_backsub_kernel<<<nb, POSE_THREADS, 0, sl.stream>>>(n_pose, Ks, delta_a, seq_cur, seq_cand, pose_seq,
                                                                 pose_local, ws, partial, chain_mask, chain_w, ticket, red);
-        if (sl.launches) (*sl.launches)++;
+        if (sl.launches) count_launch(sl.launches);
     }
     return cudaGetLastError();
 }
@@ -684,7 +684,7 @@ cudaError_t launch_pose_backsub(int n_pose, int Ks, const double *delta_a,
 cudaError_t launch_finalize_backsub(int Ks, int n_rows, const double *partial, double *red, SolverLaunch sl)
 {
     finalize_backsub_kernel<<<1, 96, 0, sl.stream>>>(Ks, n_rows, partial, red);
-    if (sl.launches) (*sl.launches)++;
+    if (sl.launches) count_launch(sl.launches);
     return cudaGetLastError();
 }
 
@@ -693,7 +693,7 @@ cudaError_t launch_reduced_solve(int Ks, const SolveArgs &sa, LmConsts lm, Solve
     const size_t smem = sizeof(double) * (2 * (size_t)Ks * Ks + 9 * (size_t)Ks + 1);
     if (smem > 40 * 1024) return cudaErrorInvalidValue;       // Ks <= 48
     reduced_solve_kernel<<<1, SOLVE_THREADS, smem, sl.stream>>>(Ks, sa, lm);
-    if (sl.launches) (*sl.launches)++;
+    if (sl.launches) count_launch(sl.launches);
     return cudaGetLastError();
 }
 
@@ -701,7 +701,7 @@ cudaError_t launch_peer_exchange(double *buf, int count, const PeerCtx &pc, Solv
 {
     if (count > PEER_SLOT_DOUBLES) return cudaErrorInvalidValue;
     peer_exchange_kernel<<<1, 256, 0, sl.stream>>>(buf, count, pc);
-    if (sl.launches) (*sl.launches)++;
+    if (sl.launches) count_launch(sl.launches);
     return cudaGetLastError();
 }
 
@@ -709,7 +709,7 @@ cudaError_t launch_peer_collect(double *buf, int count, const PeerCtx &pc, unsig
 {
     if (count > PEER_SLOT_DOUBLES) return cudaErrorInvalidValue;
     peer_collect_kernel<<<1, 256, 0, sl.stream>>>(buf, count, pc, done);
-    if (sl.launches) (*sl.launches)++;
+    if (sl.launches) count_launch(sl.launches);
     return cudaGetLastError();
 }
 
