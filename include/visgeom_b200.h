@@ -302,6 +302,21 @@ int vg_reconstruct_points(int model, const double *intr, long long n, const doub
 int vg_reconstruct_points_dev(int model, const double *intr, long long n, const double *uv, double *X, unsigned char *ok,
                               void *stream);
 
+/* ---- checkerboard detector, first stage (src/calibration/corner_detector.cpp:262-329) ------------------------------
+ * CornerDetector::computeResponse for n_img 8-bit images of width x height (row-major, one after the other): the two
+ * Gaussian blurs (cv::GaussianBlur of an 8-bit image: OpenCV's bit-exact fixed-point path), the sharp gradient maps
+ * _gradx, _grady, _imgrad and the saddle response _resp (all float, one value per pixel, zero on the one-pixel border),
+ * avg = _avgVal (mean of the responses kept, :318) and count of them per image.  sigma1 / sigma2 are computeResponse's
+ * arguments (detectPattern calls it with 0.7 and 1.4, 2, 1: :229-233); filter sizes 3 and 1 + 2 ceil(sigma2).  Every
+ * float equals the CPU restatement's bit for bit; avg is summed in a different, fixed order (last-bit differences).
+ * avg / count may be NULL.  The later stages of the detector (candidate selection, graph weaving, sub-pixel refinement,
+ * :223-260, :47-198) are not built yet: "images" datasets are still rejected by the front end. */
+int vg_corner_response(const unsigned char *img, int n_img, int width, int height, double sigma1, double sigma2,
+                       float *resp, float *gradx, float *grady, float *imgrad, double *avg, long long *count);
+int vg_corner_response_dev(const unsigned char *img, int n_img, int width, int height, double sigma1, double sigma2,
+                           float *resp, float *gradx, float *grady, float *imgrad, double *avg, long long *count,
+                           void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,7 +20,8 @@ c_ip = C.POINTER(C.c_int)
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(_HERE, f) for f in ("visgeom_oracle.c", "oracle_lm.c", "oracle_tuned.c", "visgeom_oracle.h", "oracle_lm.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("visgeom_oracle.c", "oracle_lm.c", "oracle_tuned.c", "corner_oracle.c", "visgeom_oracle.h",
+                                               "oracle_lm.h")]
     if force or not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs):
         subprocess.check_call(["make", "-s", "-C", _HERE, "libvisgeom_oracle.so"])
     return _LIB
@@ -209,6 +210,29 @@ class Oracle(_Evaluator):
         params = _f64(params); X = _f64(X); du = np.zeros(K); dv = np.zeros(K)
         ok = self.lib.vgo_intrinsic_jacobian(model, _dp(params), _dp(X), _dp(du), _dp(dv))
         return np.stack([du, dv]), bool(ok)
+
+    def gaussian_blur_u8(self, img, n, sigma):
+        """cv::GaussianBlur(img, Size(n, n), sigma, sigma) for an 8-bit image (corner_oracle.c)."""
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        out = np.empty_like(img)
+        up = C.POINTER(C.c_ubyte)
+        self.lib.vgo_gaussian_blur_u8.argtypes = [up, C.c_int, C.c_int, C.c_int, C.c_double, up]
+        self.lib.vgo_gaussian_blur_u8(img.ctypes.data_as(up), img.shape[1], img.shape[0], n, float(sigma), out.ctypes.data_as(up))
+        return out
+
+    def corner_response(self, img, sigma1, sigma2):
+        """CornerDetector::computeResponse (corner_detector.cpp:262-329): dict(resp, gradx, grady, imgrad, avg, count)."""
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        h, w = img.shape
+        fp = C.POINTER(C.c_float)
+        outs = [np.empty((h, w), dtype=np.float32) for _ in range(4)]
+        avg = C.c_double()
+        self.lib.vgo_corner_response.restype = C.c_long
+        self.lib.vgo_corner_response.argtypes = [C.POINTER(C.c_ubyte), C.c_int, C.c_int, C.c_double, C.c_double, fp, fp, fp, fp,
+                                                 C.POINTER(C.c_double)]
+        cnt = self.lib.vgo_corner_response(img.ctypes.data_as(C.POINTER(C.c_ubyte)), w, h, float(sigma1), float(sigma2),
+                                           *[o.ctypes.data_as(fp) for o in outs], C.byref(avg))
+        return dict(resp=outs[0], gradx=outs[1], grady=outs[2], imgrad=outs[3], avg=avg.value, count=int(cnt))
 
     def reconstruct(self, model, params, uv):
         params = _f64(params); uv = _f64(uv); X = np.zeros(3)

@@ -275,3 +275,54 @@ def make_odometry(n: int = 40, seed: int = 20246, noise_px: float = 0.1, odo_noi
                 xi_bc_gt=xi_bc_gt, xi_bc_init=xi_bc_gt + pert[:6] * scale,
                 xi_wB_gt=xi_wB_gt, xi_wB_init=xi_wB_gt + pert[6:] * scale,
                 status=[1, 1, 0], err_v=0.05, err_w=0.05, lam=0.01, width=IMAGE_W, height=IMAGE_H)
+
+
+# ---- synthetic board IMAGES (input of the corner detector) -----------------------------------------
+def render_board_image(width: int = 320, height: int = 240, seed: int = 20250, nx: int = 9, ny: int = 6,
+                       model: int = EUCM, supersample: int = 3, noise: float = 2.0):
+    """An 8-bit image of the (nx+1) x (ny+1)-square checkerboard whose inner corners are the calibration board,
+    seen through a camera model scaled to the image size, with a lighting gradient and sensor noise.  Ray casting per
+    sub-pixel (back-projection of the pixel, intersection with the board plane), box-filtered: the edges are
+    anti-aliased as a real sensor would see them.  Returns (image uint8 (H, W), true corner positions (P, 2))."""
+    board = make_board(nx, ny, 0.1)
+    sc = width / IMAGE_W
+    intr = np.array({EUCM: EUCM_GT_LEFT, UCM: UCM_GT, MEI: MEI_GT}[model], dtype=np.float64).copy()
+    intr[-4:] *= sc
+    intr[-1] = intr[-1] / sc * (height / IMAGE_H)
+    intr[-3] = intr[-3] / sc * (height / IMAGE_H)
+    u = uniform(seed, 21, 6)
+    rv = (2 * u[:3] - 1) * np.array([0.35, 0.35, 0.5])
+    centre = board.mean(axis=0)
+    R = rodrigues(rv[None])[0]
+    t = np.array([(2 * u[3] - 1) * 0.12, (2 * u[4] - 1) * 0.08, 0.75 + 0.35 * u[5]]) - R @ centre
+    uv, _ = project(model, intr, board @ R.T + t)
+    ss = supersample
+    ys, xs = np.meshgrid((np.arange(height * ss) + 0.5) / ss - 0.5, (np.arange(width * ss) + 0.5) / ss - 0.5, indexing="ij")
+    # pixel -> ray (pinhole approximation of the inverse is not enough for a fisheye: invert EUCM in closed form)
+    xn, yn = (xs - intr[-2]) / intr[-4], (ys - intr[-1]) / intr[-3]
+    if model == EUCM:
+        a, b = intr[0], intr[1]
+        r2 = xn * xn + yn * yn
+        det = np.maximum(1 - (2 * a - 1) * b * r2, 0.0)
+        zn = (1 - a * a * b * r2) / ((1 - a) + a * np.sqrt(det))
+    else:
+        xi = intr[0]
+        r2 = xn * xn + yn * yn
+        g = np.sqrt(np.maximum(1 + r2 * (1 - xi * xi), 0.0))
+        en, ed = -g - xi * r2, xi * xi * r2 - 1
+        zn = ed / (ed + xi * en)
+    ray = np.stack([xn, yn, zn], axis=-1)
+    # intersection with the board plane: points R Xb + t, normal n = R e_z
+    n = R[:, 2]
+    lam = (n @ t) / np.maximum(ray @ n, 1e-9)
+    Xb = (ray * lam[..., None] - t) @ R                    # board coordinates
+    sq = 0.1
+    ix, iy = np.floor(Xb[..., 0] / sq + 1.0), np.floor(Xb[..., 1] / sq + 1.0)       # squares -1 .. nx, -1 .. ny
+    inside = (ix >= 0) & (ix <= nx) & (iy >= 0) & (iy <= ny) & (lam > 0)
+    dark = ((ix + iy) % 2 == 0) & inside
+    val = np.where(dark, 35.0, np.where(inside, 215.0, 120.0))
+    val = val.reshape(height, ss, width, ss).mean(axis=(1, 3))
+    light = 0.85 + 0.3 * (np.arange(width)[None, :] / width) * (0.5 + np.arange(height)[:, None] / height)
+    nz = normal(seed, 23, width * height).reshape(height, width) * noise
+    img = np.clip(np.rint(val * light + nz), 0, 255).astype(np.uint8)
+    return img, uv

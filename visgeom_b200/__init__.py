@@ -72,6 +72,11 @@ def lib() -> C.CDLL:
     L.vg_project_points_dev.argtypes = [C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p]
     L.vg_reconstruct_points_dev.argtypes = [C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    c_fp = C.POINTER(C.c_float)
+    L.vg_corner_response.argtypes = [c_up, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, c_fp, c_fp, c_fp, c_fp, c_dp,
+                                     C.POINTER(C.c_longlong)]
+    L.vg_corner_response_dev.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     if hasattr(L, "vg_problem_create"):
         L.vg_problem_create.restype = C.c_void_p
         L.vg_problem_create.argtypes = [C.c_int]
@@ -261,6 +266,25 @@ def reconstruct_points(model, intr, uv, X_init=None):
     _check(L.vg_reconstruct_points(model, intr.ctypes.data_as(c_dp), n, uv.ctypes.data_as(c_dp), X.ctypes.data_as(c_dp),
                                    ok.ctypes.data_as(C.POINTER(C.c_ubyte))))
     return X, ok.astype(bool)
+
+
+def corner_response(imgs, sigma1=0.7, sigma2=1.4):
+    """CornerDetector::computeResponse for a batch of 8-bit images (n, H, W) or one (H, W) (vg_corner_response).
+    Returns dict(resp, gradx, grady, imgrad: float32 arrays of the input's shape; avg (n,), count (n,))."""
+    L = lib()
+    a = np.ascontiguousarray(imgs, dtype=np.uint8)
+    single = a.ndim == 2
+    b = a[None] if single else a
+    n, h, w = b.shape
+    outs = [np.empty((n, h, w), dtype=np.float32) for _ in range(4)]
+    avg = np.empty(n); cnt = np.empty(n, dtype=np.int64)
+    fp = C.POINTER(C.c_float)
+    _check(L.vg_corner_response(b.ctypes.data_as(C.POINTER(C.c_ubyte)), n, w, h, float(sigma1), float(sigma2),
+                                *[o.ctypes.data_as(fp) for o in outs], avg.ctypes.data_as(c_dp),
+                                cnt.ctypes.data_as(C.POINTER(C.c_longlong))))
+    if single:
+        outs = [o[0] for o in outs]
+    return dict(resp=outs[0], gradx=outs[1], grady=outs[2], imgrad=outs[3], avg=avg, count=cnt)
 
 
 class Problem:
