@@ -286,6 +286,18 @@ int vg_problem_update_poses(vg_problem *p, int transform, const double *values);
  * :1186-1213 needs err = -r and proj = r + obs), n_img x 2P doubles to host */
 int vg_problem_residuals(vg_problem *p, int dataset, double *r);
 
+/* ---- per-image initialisation solves (unified_calibration.cpp:1131-1155) ---------------------------------------------
+ * estimateInitialGrid's refinement, for n_img images at once but as n_img INDEPENDENT problems: image i's board pose
+ * poses[6 i .. 6 i + 5] = [t, r] (camera <- board, a single DIRECT transform) is the only free block of its own
+ * Levenberg-Marquardt solve -- camera constant (:1145), the block under SoftLOneLoss(loss_a) (:1143; 0: no loss), own
+ * trust region, own accept / reject, own termination -- one warp per image, no host synchronisation in the loop.
+ * opt: NULL = vg_solve_options_default (the calibration's 1e-15 tolerances); the reference's per-image solve runs
+ * with Ceres' defaults (function 1e-6, gradient 1e-10, parameter 1e-8) and max_num_iterations = 500 (:1148).
+ * iterations / final_cost / termination (vg_solve_summary's codes): n_img entries each, may be NULL. */
+int vg_refine_poses(int model, const double *intr, int n_img, int P, const double *board, const double *obs,
+                    double *poses, double loss_a, const vg_solve_options *opt, int *iterations, double *final_cost,
+                    int *termination);
+
 /* ---- the ICamera point API, batched (include/projection/generic_camera.h:36-113) -------------------------------------
  * What a visgeom caller does with a camera object outside the calibration functor: projectPoint (:39),
  * projectionJacobian (:46), intrinsicJacobian (:50), reconstructPoint (:36) and the *PointCloud loops around them

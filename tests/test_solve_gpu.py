@@ -271,3 +271,31 @@ def test_stereo_full_size_solve(gpu, oracle):
     assert sg.termination in (0, 1, 2)
     assert rel(G.camera(gi[0])[2:], s["intr1_gt"][2:]) < 1e-3 and rel(G.camera(gi[1])[2:], s["intr2_gt"][2:]) < 1e-3
     assert np.abs(G.transform(gi[2])[0] - s["xi12_gt"]).max() < 1e-3
+
+
+def test_per_image_refinement_matches_oracle_one_problem_per_image(gpu, oracle):
+    """vg_refine_poses (estimateInitialGrid's solve, unified_calibration.cpp:1131-1155): every image is its own problem
+    -- camera constant, SoftLOneLoss(25), Ceres' default tolerances, 500 iterations -- so each image's pose, cost and
+    iteration count is held against the oracle LM solving that image ALONE.  Two images carry gross outliers, one starts
+    far away: their trust regions must not disturb the others'."""
+    d = sd.make_mono(sd.EUCM, 40, seed=1212)
+    obs = d["obs"].copy(); obs[5, :30] += 60.0; obs[11, 40:80] -= 35.0
+    xi0 = d["xi_init"].copy(); xi0[7] += np.array([0.08, -0.06, 0.1, 0.1, -0.08, 0.05])
+    o = gpu.SolveOptions(); gpu.lib().vg_solve_options_default(o)
+    o.max_num_iterations = 500; o.function_tolerance = 1e-6; o.gradient_tolerance = 1e-10; o.parameter_tolerance = 1e-8
+    x, it, cost, term = gpu.refine_poses(sd.EUCM, d["intr_gt"], d["board"], obs, xi0, 25.0, o)
+    for i in range(d["n_img"]):
+        O = OracleProblem(oracle)
+        cam = O.add_camera(sd.EUCM, d["intr_gt"], constant=True)
+        tr = O.add_transform(xi0[i:i + 1], is_global=False)
+        ds = O.add_dataset(cam, d["board"], obs[i:i + 1], [tr], [D])
+        O.set_loss(ds, 25.0)
+        oo = oracle.default_options()
+        oo.max_num_iterations = 500; oo.function_tolerance = 1e-6; oo.gradient_tolerance = 1e-10; oo.parameter_tolerance = 1e-8
+        so = O.solve(oo)
+        assert abs(cost[i] - so.final_cost) <= 1e-9 * max(1.0, so.final_cost), (i, cost[i], so.final_cost)
+        assert np.abs(x[i] - O.transform(tr)[0]).max() < 1e-8, i
+        assert it[i] == so.iterations and term[i] == so.termination, (i, it[i], so.iterations, term[i], so.termination)
+    # the clean images end next to the ground truth
+    clean = [i for i in range(d["n_img"]) if i not in (5, 11)]
+    assert np.abs(x[clean] - d["xi_gt"][clean]).max() < 5e-3

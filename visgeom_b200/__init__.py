@@ -77,6 +77,8 @@ def lib() -> C.CDLL:
                                      C.POINTER(C.c_longlong)]
     L.vg_corner_response_dev.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.vg_refine_poses.argtypes = [C.c_int, c_dp, C.c_int, C.c_int, c_dp, c_dp, c_dp, C.c_double, C.POINTER(SolveOptions), c_ip,
+                                  c_dp, c_ip]
     if hasattr(L, "vg_problem_create"):
         L.vg_problem_create.restype = C.c_void_p
         L.vg_problem_create.argtypes = [C.c_int]
@@ -266,6 +268,20 @@ def reconstruct_points(model, intr, uv, X_init=None):
     _check(L.vg_reconstruct_points(model, intr.ctypes.data_as(c_dp), n, uv.ctypes.data_as(c_dp), X.ctypes.data_as(c_dp),
                                    ok.ctypes.data_as(C.POINTER(C.c_ubyte))))
     return X, ok.astype(bool)
+
+
+def refine_poses(model, intr, board, obs, poses, loss_a=25.0, options=None):
+    """estimateInitialGrid's refinement as independent per-image solves (vg_refine_poses): returns
+    (poses (n, 6), iterations (n,), final_cost (n,), termination (n,))."""
+    L = lib()
+    intr, board, obs = _f64(intr), _f64(board), _f64(obs)
+    x = _f64(poses).copy().reshape(-1, 6)
+    n, P = x.shape[0], board.shape[0]
+    it = np.zeros(n, dtype=np.int32); term = np.zeros(n, dtype=np.int32); cost = np.zeros(n)
+    _check(L.vg_refine_poses(model, _dp(intr), n, P, _dp(board), _dp(obs), _dp(x), float(loss_a),
+                             C.byref(options) if options is not None else None, it.ctypes.data_as(c_ip), _dp(cost),
+                             term.ctypes.data_as(c_ip)))
+    return x, it, cost, term
 
 
 def corner_response(imgs, sigma1=0.7, sigma2=1.4):

@@ -18,7 +18,7 @@ LIB = os.path.join(HERE, "libvisgeom_b200%s.so" % ("_" + VARIANT if VARIANT else
 OBJ = os.path.join(HERE, "_obj" + ("_" + VARIANT if VARIANT else ""))
 
 SOURCES = ["vg_eval_eucm.cu", "vg_eval_ucm.cu", "vg_eval_mei.cu", "vg_eval.cu", "vg_api.cu", "vg_solver_kernels.cu",
-           "vg_problem.cu", "vg_priors.cu", "vg_solver_fast.cu", "vg_project.cu", "vg_host.cu", "vg_corner.cu"]
+           "vg_problem.cu", "vg_priors.cu", "vg_solver_fast.cu", "vg_project.cu", "vg_host.cu", "vg_corner.cu", "vg_refine.cu"]
 # every header of csrc/ is a dependency of every object (a stale object with a mismatched cross-rank protocol or
 # argument struct would load silently)
 HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + ["../../include/visgeom_b200.h"]

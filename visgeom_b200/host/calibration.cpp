@@ -246,9 +246,8 @@ Transf GenericCameraCalibration::estimateInitialGridGuess(const ImageData &data,
 
 // The refinement part of estimateInitialGrid (unified_calibration.cpp:1131-1155), batched: the reference solves
 // one 6-parameter problem per image with the intrinsics constant; here all images of the dataset are the poses
-// of ONE problem on the GPU (they are independent: the Hessian is block diagonal), each block under
-// SoftLOneLoss(25) as in the reference (:1143).  Difference, stated: one trust region for the batch instead of one
-// per image (the minima are the same).
+// at once on the GPU but as independent problems, one per image as in the reference (own trust region, own accept /
+// reject, own termination; vg_refine_poses), each block under SoftLOneLoss(25) (:1143).
 void GenericCameraCalibration::refineInitialGrids(const ImageData &data, const vector<int> &idx, vector<Array6d> &xi) const
 {
     if (idx.empty()) return;
@@ -261,23 +260,13 @@ void GenericCameraCalibration::refineInitialGrids(const ImageData &data, const v
             obs[((size_t)j * P + i) * 2 + k] = data.detectedCornersVec[idx[j]][i][k];
         for (int k = 0; k < 6; k++) poses[6 * (size_t)j + k] = xi[j][k];
     }
-    ProblemHandle h(device);
-    const int camId = vg_problem_add_camera(h.p, cam->model(), intrinsicMap.at(data.cameraName).data(), 1);
-    check(camId, "vg_problem_add_camera");
-    const int tr = vg_problem_add_transform(h.p, 0, 0, n, poses.data());
-    check(tr, "vg_problem_add_transform");
-    const int status = VG_TRANSFORM_DIRECT;
-    const int ds = vg_problem_add_dataset(h.p, camId, P, board.data(), n, obs.data(), nullptr, 1, &tr, &status);
-    check(ds, "vg_problem_add_dataset");
-    check(vg_problem_set_loss(h.p, ds, 25.0), "vg_problem_set_loss");        // new SoftLOneLoss(25), :1143
     vg_solve_options o;
     vg_solve_options_default(&o);
-    o.max_num_iterations = 500;                // as the reference's per-image solve
-    o.function_tolerance = 1e-6; o.gradient_tolerance = 1e-10; o.parameter_tolerance = 1e-8;   // Ceres defaults
-    o.verbose = 0;
-    vg_solve_summary s;
-    check(vg_problem_solve(h.p, &o, &s), "vg_problem_solve (initial poses)");
-    check(vg_problem_get_transform(h.p, tr, poses.data()), "vg_problem_get_transform");
+    o.max_num_iterations = 500;                // :1148
+    o.function_tolerance = 1e-6; o.gradient_tolerance = 1e-10; o.parameter_tolerance = 1e-8;   // Ceres defaults (:1146-1150 set nothing else)
+    // one independent problem per image, as the reference builds them: camera constant, SoftLOneLoss(25) (:1143-1145)
+    check(vg_refine_poses(cam->model(), intrinsicMap.at(data.cameraName).data(), n, P, board.data(), obs.data(), poses.data(),
+                          25.0, &o, nullptr, nullptr, nullptr), "vg_refine_poses (initial poses)");
     for (int j = 0; j < n; j++) for (int k = 0; k < 6; k++) xi[j][k] = poses[6 * (size_t)j + k];
 }
 
