@@ -51,12 +51,12 @@ struct EvalArgs {
     const double *fin_base;         // all datasets' ds_sum regions
     const EMapEntry *emap;          // nullable: NE entries, set when this dataset is the only source of every entry of red
     double *red;
-    // nullable: host-mapped words the CTA that assembled red also leaves red[host_index] and (after it) host_seq in,
-    // for a host that polls instead of synchronising the stream (vg_problem_solve)
+    // nullable: host-mapped words the CTA that assembled (and exchanged) red also leaves red[host_index .. + host_count)
+    // and, after them, host_seq in, for a host that polls instead of synchronising the stream (vg_problem_solve)
     double *host_value;
     unsigned long long *host_flag;
     unsigned long long host_seq;
-    int host_index;
+    int host_index, host_count;
     // Robust loss on the block of an image (Ceres applies a LossFunction to the squared norm s of the whole residual
     // block): 0 = none, else b = a^2 of SoftLOneLoss(a), rho(s) = 2 b (sqrt(1 + s / b) - 1).  rho'' < 0, so Ceres'
     // corrector scales residuals and Jacobians by sqrt(rho'): the packed block leaves as rho' [J r]^T [J r] with

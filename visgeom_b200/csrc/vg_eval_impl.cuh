@@ -465,7 +465,8 @@ __device__ __forceinline__ void fused_reduce(const EvalArgs &args, double *scrat
     if (args.host_flag) {
         __syncthreads();
         if (tid == 0) {
-            *args.host_value = *reinterpret_cast<volatile double *>(args.red + args.host_index);
+            for (int i = 0; i < args.host_count; i++)
+                args.host_value[i] = *reinterpret_cast<volatile double *>(args.red + args.host_index + i);
             __threadfence_system();
             asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(args.host_flag), "l"(args.host_seq) : "memory");
         }

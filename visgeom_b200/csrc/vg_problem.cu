@@ -158,6 +158,7 @@ struct vg_problem {
     double *d_fast_scratch = nullptr;
     unsigned int *d_fast_tickets = nullptr;
     // host-mapped words the step's kernels leave their scalars in, and the flag the host polls (no copy, no stream sync)
+    double *d_agree = nullptr;                  // several ranks: do all of them have the plain structure? (one exchange per solve)
     double *h_poll = nullptr;
     unsigned long long poll_seq = 0;            // != 0: the next evaluation's last launch posts cost + flag
     unsigned long long poll_counter = 0;
@@ -222,7 +223,7 @@ void free_prepared(vg_problem *p)
     for (int s = 0; s < 2; s++) { F(p->d_slab[s]); F(p->d_desc[s]); F(p->d_seq_ptr[s]); }
     F(p->d_pose_start); F(p->d_contrib_ds); F(p->d_contrib_img); F(p->d_pose_seq); F(p->d_pose_local);
     F(p->d_fail); F(p->d_fin_out); F(p->d_fin_src); F(p->d_emap); F(p->d_cta_partial); F(p->d_tickets); F(p->d_lvl1); F(p->d_ds_sum); F(p->d_scale); F(p->d_ws); F(p->d_partial); F(p->d_redbuf[0]); F(p->d_redbuf[1]); F(p->d_delta);
-    F(p->d_solver_tickets); F(p->d_fast_scratch); F(p->d_fast_tickets); F(p->d_sh_off); F(p->d_sh_lo); F(p->d_sh_hi); F(p->d_scale_a);
+    F(p->d_solver_tickets); F(p->d_fast_scratch); F(p->d_fast_tickets); F(p->d_agree); F(p->d_sh_off); F(p->d_sh_lo); F(p->d_sh_hi); F(p->d_scale_a);
     for (int s = 0; s < 2; s++) { F(p->d_tp_out[s]); F(p->d_op_out[s]); F(p->d_tp_xi[s]); F(p->d_op_xi[s]); }
     F(p->d_tp_const); F(p->d_op_const); F(p->d_tp_shared_rec); F(p->d_tp_shared_off); F(p->d_seg_start); F(p->d_seg_len);
     F(p->d_extra_start); F(p->d_extra_kind); F(p->d_extra_rec); F(p->d_prev_edge); F(p->d_mask); F(p->d_fixed);
@@ -534,7 +535,7 @@ int prepare(vg_problem *p)
     VG_CUDA(cudaMalloc(&p->d_scale_a, sizeof(double) * (Ks ? Ks : 1)));
     // the plain structure (see vg_solver_kernels.cuh): its step runs in two launches
     p->fast_ds = p->fast_tr = -1;
-    if (p->nranks == 1 && p->n_seg == 0 && p->n_tp + p->n_op == 0 && Ks >= 1 && Ks <= FAST_MAX_KS && NP > 0) {
+    if ((p->nranks == 1 || p->peers) && p->n_seg == 0 && p->n_tp + p->n_op == 0 && Ks >= 1 && Ks <= FAST_MAX_KS && NP > 0) {
         int n_free_seq = 0, tr_id = -1, n_ds_img = 0, ds_id = -1;
         for (size_t i = 0; i < p->trs.size(); i++)
             if (p->trs[i].pose_off >= 0) { n_free_seq++; tr_id = (int)i; }
@@ -549,6 +550,7 @@ int prepare(vg_problem *p)
             if (ok) { p->fast_ds = ds_id; p->fast_tr = tr_id; }
         }
     }
+    if (p->peers && p->nranks > 1) VG_CUDA(cudaMalloc(&p->d_agree, 2 * sizeof(double)));
     if (p->fast_ds >= 0) {
         VG_CUDA(cudaMalloc(&p->d_fast_scratch, sizeof(double) * fast_scratch(NP, Ks)));
         VG_CUDA(cudaMalloc(&p->d_fast_tickets, sizeof(unsigned int) * (fast_groups(NP) + 2)));
@@ -630,9 +632,9 @@ int evaluate_set(vg_problem *p, int s, bool timed, bool deferred = false)
             a.fin_outs = p->d_fin_out; a.fin_srcs = p->d_fin_src; a.n_fin_out = p->n_fin_out;
             a.fin_base = p->d_ds_sum; a.red = p->d_redbuf[s]; a.emap = p->d_emap;
             if (p->poll_seq) {
-                a.host_value = p->h_poll + 11;
-                a.host_flag = reinterpret_cast<unsigned long long *>(p->h_poll + 12);
-                a.host_seq = p->poll_seq; a.host_index = red_off_cost(p->Ks);
+                a.host_value = p->h_poll + FAST_HOST_EVAL;
+                a.host_flag = reinterpret_cast<unsigned long long *>(p->h_poll + FAST_HOST_FLAG);
+                a.host_seq = p->poll_seq; a.host_index = red_off_cost(p->Ks); a.host_count = 4;   // cost, model, step^2, x^2
                 p->poll_seq = 0;
             }
             if (p->peers && p->nranks > 1 && p->n_tp + p->n_op == 0) {
@@ -1289,6 +1291,22 @@ int vg_problem_solve(vg_problem *p, const vg_solve_options *opt, vg_solve_summar
         }
     }
 
+    // several ranks: the two-launch step only if EVERY rank's share has the plain structure (the ranks must issue the same
+    // sequence of exchanges): one exchange of a flag per solve
+    bool fast_everywhere = p->fast_ds >= 0;
+    if (p->peers && p->nranks > 1) {
+        const double mine = p->fast_ds >= 0 ? 1.0 : 0.0;
+        VG_CUDA(cudaMemcpyAsync(p->d_agree, &mine, sizeof(double), cudaMemcpyHostToDevice, p->stream));
+        VG_CUDA(cudaStreamSynchronize(p->stream));
+        cudaError_t ae = launch_peer_exchange(p->d_agree, 1, p->next_peer_ctx(), sl);
+        if (ae != cudaSuccess) return fail_cuda(ae, "peer exchange");
+        double all = 0.0;
+        VG_CUDA(cudaMemcpyAsync(&all, p->d_agree, sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        VG_CUDA(cudaStreamSynchronize(p->stream));
+        rc = check_peer_fail(p);
+        if (rc) return rc;
+        fast_everywhere = all == (double)p->nranks;
+    }
     // iteration 0: evaluate at the starting point
     for (int s_ = 0; s_ < 2; s_++)
         VG_CUDA(cudaMemsetAsync(p->d_redbuf[s_] + red_off_model(Ks), 0, 3 * sizeof(double), p->stream));
@@ -1323,7 +1341,7 @@ int vg_problem_solve(vg_problem *p, const vg_solve_options *opt, vg_solve_summar
         cudaError_t ce = cudaSuccess;
         mark(0);
         static const bool nofast = getenv("VG_LM_NOFAST") != nullptr;   // developer knob: the general kernels everywhere
-        if (p->fast_ds >= 0 && !nofast) {
+        if (fast_everywhere && !nofast) {
             // the plain structure: factorisation + Schur terms, then reduced solve + back-substitution, two launches
             const SolveArgs sa{(int)p->slab_doubles, p->nranks, p->d_redbuf[p->cur], p->d_redbuf[cand], p->d_slab[p->cur],
                                p->d_slab[cand], p->d_delta, p->d_sh_off, p->d_sh_lo, p->d_sh_hi, p->d_scale_a};
@@ -1333,8 +1351,11 @@ int vg_problem_solve(vg_problem *p, const vg_solve_options *opt, vg_solve_summar
             fd.H = hd.H; fd.ne = hd.ne; fd.W = hd.W; fd.pose_col = hd.pose_col; fd.n_sl = hd.n_sl;
             for (int q = 0; q < hd.n_sl; q++) { fd.sl_col[q] = hd.sl_col[q]; fd.sl_idx[q] = hd.sl_idx[q]; }
             const Tr &ft = p->trs[p->fast_tr];
+            PeerCtx pcx;
+            const PeerCtx *pcp = nullptr;
+            if (p->peers && p->nranks > 1) { pcx = p->next_peer_ctx(); pcp = &pcx; }
             ce = launch_fast_step(fd, NP, Ks, p->d_scale, lm, p->d_ws, p->d_fast_scratch, p->d_fast_tickets, p->d_fail, sa,
-                                  ft.dev[p->cur], ft.dev[cand], !limits, sl, trace ? tev[1] : nullptr, p->h_poll);
+                                  ft.dev[p->cur], ft.dev[cand], !limits, sl, trace ? tev[1] : nullptr, p->h_poll, pcp);
             if (ce != cudaSuccess) return fail_cuda(ce, "fast LM step");
             init_scale = false;
             mark(2); mark(3);
@@ -1393,7 +1414,7 @@ int vg_problem_solve(vg_problem *p, const vg_solve_options *opt, vg_solve_summar
         if (polled) {
             // the kernels wrote what the decisions below read straight into host-mapped memory; the evaluation's last
             // CTA raised the flag after its cost (a finished stream without the flag cannot happen: copy as a last resort)
-            volatile unsigned long long *flag = reinterpret_cast<volatile unsigned long long *>(p->h_poll + 12);
+            volatile unsigned long long *flag = reinterpret_cast<volatile unsigned long long *>(p->h_poll + FAST_HOST_FLAG);
             bool seen = false;
             for (unsigned long long spins = 1; !(seen = *flag == polled); spins++) {
                 if ((spins & 0xFFF) == 0) {
@@ -1402,12 +1423,12 @@ int vg_problem_solve(vg_problem *p, const vg_solve_options *opt, vg_solve_summar
                     if (qe != cudaErrorNotReady) return fail_cuda(qe, "LM step");
                 }
             }
+            p->exchanged_in_kernel = false;      // (segment E was summed across the ranks by the evaluation kernel itself)
             if (seen) {
                 std::atomic_thread_fence(std::memory_order_acquire);
                 const double *hp = p->h_poll;
                 for (int i = 0; i < SOLVE_OUT; i++) p->h_red[off_out + i] = hp[i];
-                for (int i = 0; i < 3; i++) p->h_red[red_off_model(Ks) + i] = hp[8 + i];
-                p->h_red[red_off_cost(Ks)] = hp[11];
+                for (int i = 0; i < 4; i++) p->h_red[red_off_cost(Ks) + i] = hp[FAST_HOST_EVAL + i];
                 for (size_t i = 0; i < p->slab_doubles; i++) p->h_red[off_slab + i] = hp[FAST_HOST_SLAB + i];
             } else {
                 polled = 0;

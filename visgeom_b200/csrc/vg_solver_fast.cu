@@ -275,7 +275,7 @@ struct SolveSm {
 __global__ void __launch_bounds__(B_THREADS, 6)       // every block of a C2-sized problem resident at once
 fast_backsub_kernel(const int n_pose, const int Ks, const int n_grp, const double *grp_rows, const SolveArgs sa,
                     const LmConsts lm, const double *seq_cur, double *seq_cand, const double *ws, double *partial,
-                    unsigned int *ticket, int *fail_flag, double *host_out)
+                    unsigned int *ticket, int *fail_flag, double *host_out, const double *fail_src)
 {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     // this lane's part of its pose's rows, in flight while the block solves the reduced system: lane k < 6 takes
@@ -397,7 +397,8 @@ fast_backsub_kernel(const int n_pose, const int Ks, const int n_grp, const doubl
                 step2 = fma(q.xn[j] - q.xs[j], q.xn[j] - q.xs[j], step2);
                 gmax = fmax(gmax, fabs(q.xs[j] - fmin(fmax(q.xs[j] - q.g[j], q.lo[j]), q.hi[j])));
             }
-            const double failed = (double)atomicExch(fail_flag, 0);
+            // failed pose factorisations: this rank's flag, or (several ranks) the count the exchange summed
+            const double failed = fail_src ? __ldcg(fail_src) : (double)atomicExch(fail_flag, 0);
             out[0] = gmax;
             out[1] = failed;
             out[2] = (double)q.ok;
@@ -461,10 +462,7 @@ fast_backsub_kernel(const int n_pose, const int Ks, const int n_grp, const doubl
         const double s = sum_rows_batched(partial + qn, 3, lane, gridDim.x, 32);
         double tot = 0.0;
         for (int l = 0; l < 32; l++) tot += __shfl_sync(0xffffffffu, s, l);
-        if (lane == 0) {
-            sa.red_cand[red_off_model(Ks) + qn] = tot;
-            if (host_out) host_out[8 + qn] = tot;
-        }
+        if (lane == 0) sa.red_cand[red_off_model(Ks) + qn] = tot;       // (summed across the ranks by the candidate's evaluation)
     }
     // a polling host (no copy, no stream sync): block 0's scalars and the candidate slab, straight into host-mapped memory.
     // Done here, by the block that finishes last, so that no block waits on a fence behind writes that cross PCIe.
@@ -472,6 +470,33 @@ fast_backsub_kernel(const int n_pose, const int Ks, const int n_grp, const doubl
         const double *out = sa.red_cand + red_size(Ks, sa.nranks);
         for (int i = tid; i < SOLVE_OUT + sa.slab_n; i += B_THREADS)
             host_out[i < SOLVE_OUT ? i : FAST_HOST_SLAB + (i - SOLVE_OUT)] = __ldcg(out + i);
+    }
+}
+
+// several ranks: this rank's Schur terms (its group rows folded into one), its max |g| and its failed factorisations
+// summed / gathered across the ranks over peer memory (vg_peer.cuh) -> one row [S, v (npair) | max |g| | failures] that
+// fast_backsub reads as if it were a single group row.  One block.
+__global__ void __launch_bounds__(256)
+fast_exchange_kernel(const int Ks, const int n_grp, const double *grp_rows, double *xbuf, double *row_out, int *fail_flag,
+                     const PeerCtx pc)
+{
+    __shared__ double scratch[2048];
+    const int tid = threadIdx.x, npair = Ks * (Ks + 1) / 2 + Ks;
+    for (int t = tid; t < npair; t += blockDim.x) xbuf[t] = sum_rows_batched(grp_rows + t, npair + 1, 0, n_grp, 1);
+    if (tid == blockDim.x - 1) {
+        const double m = max_rows_batched(grp_rows + npair, npair + 1, 0, n_grp);
+        for (int r = 0; r < pc.n; r++) xbuf[npair + r] = r == pc.rank ? m : 0.0;
+        xbuf[npair + pc.n] = (double)atomicExch(fail_flag, 0);
+    }
+    __syncthreads();
+    peer_allreduce(xbuf, npair + pc.n + 1, pc, scratch, 2048);
+    __syncthreads();
+    for (int t = tid; t < npair; t += blockDim.x) row_out[t] = xbuf[t];
+    if (tid == 0) {
+        double m = 0.0;
+        for (int r = 0; r < pc.n; r++) m = fmax(m, xbuf[npair + r]);
+        row_out[npair] = m;
+        row_out[npair + 1] = xbuf[npair + pc.n];
     }
 }
 
@@ -485,7 +510,7 @@ size_t fast_scratch(int n_pose, int Ks)
 {
     const size_t npair = (size_t)Ks * (Ks + 1) / 2 + Ks;
     return (size_t)fast_factor_blocks(n_pose) * (npair + 1) + (size_t)fast_groups(n_pose) * (npair + 1) +
-           3 * (size_t)fast_backsub_blocks(n_pose) + 16;
+           3 * (size_t)fast_backsub_blocks(n_pose) + 2 * (npair + PEER_MAX_RANKS + 4) + 16;
 }
 
 template <int WC, int PCC>
@@ -514,12 +539,14 @@ static cudaError_t launch_factor(const FastDesc &d, int n_pose, int Ks, double *
 
 cudaError_t launch_fast_step(const FastDesc &d, int n_pose, int Ks, double *scale, LmConsts lm, double *ws, double *scratch,
                              unsigned int *tickets, int *fail_flag, const SolveArgs &sa, const double *seq_cur,
-                             double *seq_cand, bool backsub, SolverLaunch sl, cudaEvent_t between, double *host_out)
+                             double *seq_cand, bool backsub, SolverLaunch sl, cudaEvent_t between, double *host_out,
+                             const PeerCtx *peer)
 {
-    if (Ks < 1 || Ks > FAST_MAX_KS || n_pose < 1 || sa.nranks != 1) return cudaErrorInvalidValue;
+    if (Ks < 1 || Ks > FAST_MAX_KS || n_pose < 1 || (sa.nranks != 1 && !peer)) return cudaErrorInvalidValue;
     const int nb = fast_factor_blocks(n_pose), ng = fast_groups(n_pose), npair = Ks * (Ks + 1) / 2 + Ks;
     double *rows = scratch, *gmax_rows = rows + (size_t)nb * npair, *grp_rows = gmax_rows + nb,
-           *partial = grp_rows + (size_t)ng * (npair + 1);
+           *partial = grp_rows + (size_t)ng * (npair + 1), *xbuf = partial + 3 * (size_t)fast_backsub_blocks(n_pose),
+           *xrow = xbuf + (npair + PEER_MAX_RANKS + 4);
     const size_t smem = sizeof(double) * ((size_t)F_POSES * d.ne + (size_t)F_POSES * (6 * Ks + 6));
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     // Both kernels are launched with programmatic stream serialization (they start with griddepcontrol.wait): their
@@ -532,6 +559,15 @@ cudaError_t launch_fast_step(const FastDesc &d, int n_pose, int Ks, double *scal
     if (sl.launches) count_launch(sl.launches);
     if (e != cudaSuccess) return e;
     if (between) cudaEventRecord(between, sl.stream);
+    const double *rows_in = grp_rows, *fail_src = nullptr;
+    int n_rows_in = ng;
+    if (peer && peer->n > 1) {
+        fast_exchange_kernel<<<1, 256, 0, sl.stream>>>(Ks, ng, grp_rows, xbuf, xrow, fail_flag, *peer);
+        if (sl.launches) count_launch(sl.launches);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        rows_in = xrow; n_rows_in = 1; fail_src = xrow + npair + 1;
+    }
     // (backsub == false: only the gradient test is still due -- the kernel still leaves the scalars; the candidate
     // poses it writes are never looked at)
     (void)backsub;
@@ -541,8 +577,8 @@ cudaError_t launch_fast_step(const FastDesc &d, int n_pose, int Ks, double *scal
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = between ? 0 : 1;
-    e = cudaLaunchKernelEx(&cfg, fast_backsub_kernel, n_pose, Ks, ng, (const double *)grp_rows, sa, lm, seq_cur, seq_cand,
-                           (const double *)ws, partial, tickets + ng, fail_flag, host_out);
+    e = cudaLaunchKernelEx(&cfg, fast_backsub_kernel, n_pose, Ks, n_rows_in, rows_in, sa, lm, seq_cur, seq_cand,
+                           (const double *)ws, partial, tickets + ng, fail_flag, host_out, fail_src);
     if (sl.launches) count_launch(sl.launches);
     return e != cudaSuccess ? e : cudaGetLastError();
 }

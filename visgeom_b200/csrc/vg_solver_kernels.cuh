@@ -128,11 +128,13 @@ cudaError_t launch_peer_collect(double *buf, int count, const PeerCtx &pc, unsig
 cudaError_t launch_finalize_backsub(int Ks, int n_rows, const double *partial, double *red, SolverLaunch sl);
 
 // ---- the plain structure's step in two launches (vg_solver_fast.cu) ------------------------------------------
-// one rank, ONE dataset whose image i is the only block of free pose i (identity image -> element map, every element of
+// one rank (or several over peer memory, every rank with this structure), ONE dataset whose image i is the only block of free pose i (identity image -> element map, every element of
 // the one free sequence observed and free), no prior / odometry blocks, 1 <= Ks <= FAST_MAX_KS
 constexpr int FAST_MAX_KS = 12;
 constexpr int FAST_GROUP = 20;       // blocks of fast_factor whose rows one of them folds
-constexpr int FAST_HOST_SLAB = 16;   // host_out: [scalars 0..7 | model sums 8..10 | cost 11 | .. | candidate slab from here]
+// host-mapped words of the polled step: [reduced solve's scalars 0..7 | 16..19: cost and the three model / norm sums, as
+// the candidate's evaluation left them after its exchange | 24: its flag | candidate slab from FAST_HOST_SLAB]
+constexpr int FAST_HOST_EVAL = 16, FAST_HOST_FLAG = 24, FAST_HOST_SLAB = 32;
 struct FastDesc {
     const double *H;                 // n_pose x ne packed blocks (the set being factorised)
     int ne, W, pose_col, n_sl;
@@ -145,6 +147,6 @@ int fast_groups(int n_pose);                  // tickets needed: fast_groups + 1
 cudaError_t launch_fast_step(const FastDesc &d, int n_pose, int Ks, double *scale, LmConsts lm, double *ws, double *scratch,
                              unsigned int *tickets, int *fail_flag, const SolveArgs &sa, const double *seq_cur,
                              double *seq_cand, bool backsub, SolverLaunch sl, cudaEvent_t between = nullptr,
-                             double *host_out = nullptr);   // host_out: host-mapped doubles, see FAST_HOST_SLAB
+                             double *host_out = nullptr, const PeerCtx *peer = nullptr);   // peer: several ranks, see fast_exchange   // host_out: host-mapped doubles, see FAST_HOST_SLAB
 
 }  // namespace vg
