@@ -293,6 +293,20 @@ __device__ __forceinline__ void gram_image(const Stage<MODEL, L> &st, const int 
 template <int L>
 __device__ __forceinline__ void chain_pose(const EvalArgs &args, const int img, double *ps)
 {
+    if (L == 1 && !args.inverse[0]) {
+        // one DIRECT element (every monocular dataset): R12 = I, M12 = J_l(r), t13 = t -- no products needed; this is
+        // the latency every CTA pays before its first corner phase
+        const int sidx = args.seq_index ? args.seq_index[img] : img;
+        const double *x = args.xi[0] + (size_t)sidx * args.xi_stride[0];
+        const double t0 = x[0], t1 = x[1], t2 = x[2];
+        double Re[9], Jl[9];
+        rodrigues_and_left_jacobian(x[3], x[4], x[5], Re, Jl);
+#pragma unroll
+        for (int i = 0; i < 9; i++) { ps[i] = Re[i]; ps[12 + i] = i % 4 == 0 ? 1.0 : 0.0; ps[21 + i] = Jl[i]; }
+        ps[9] = t0; ps[10] = t1; ps[11] = t2;
+        ps[30] = t0; ps[31] = t1; ps[32] = t2;
+        return;
+    }
     double Racc[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     double tacc[3] = {0, 0, 0};
     const int sidx = args.seq_index ? args.seq_index[img] : img;
@@ -591,7 +605,7 @@ reproj_eval_kernel(const EvalArgs args, const int G_rt, const int PCG_rt)
     // the camera's parameters and constants wait in shared memory: read where the corner phase needs them, they do
     // not occupy registers during the Gram phase
 #if VG_CAM_SMEM
-    if (tid == 0) {
+    if (tid == 32) {        // (not thread 0: that one stages a pose at the same time)
         double intr[K];
 #pragma unroll
         for (int i = 0; i < K; i++) { intr[i] = __ldg(args.intr + i); st.cam[i] = intr[i]; }
