@@ -69,7 +69,8 @@ struct EvalArgs {
     // one-block kernel when something needs it sooner.  collect_done: device word, the last exchange collected.
     PeerCtx peer;
     int peer_count;
-    int peer_deferred;
+    int peer_deferred;                  // 1: the tail posts; 2: nobody posts here -- the collecting head (collect_post) does
+    int collect_post;                   // the head posts collect_buf (this rank's block of that exchange) before it collects
     PeerCtx collect;
     double *collect_buf;
     unsigned long long *collect_done;

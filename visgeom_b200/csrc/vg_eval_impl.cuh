@@ -412,6 +412,20 @@ __device__ __forceinline__ double reduce_rows(const double *src, const int r0, c
     return t;
 }
 
+// The deferred exchange this launch owes (one CTA, at its head): post this rank's block if the launch that produced it
+// left that to us, form the sum, publish "collected".  Out of line: one CTA in one launch out of many runs it, and
+// inlined it costs the kernel's main loop registers.
+__device__ __noinline__ void head_exchange(double *buf, int count, PeerCtx pc, int post, unsigned long long *done,
+                                           double *scratch, int cap)
+{
+    if (post) peer_post(buf, count, pc);
+    peer_collect(buf, count, pc, scratch, cap);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0)
+        asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(done), "l"(pc.epoch) : "memory");
+}
+
 template <int NE>
 __device__ __forceinline__ void fused_reduce(const EvalArgs &args, double *scratch, const int scratch_cap)
 {
@@ -473,8 +487,10 @@ __device__ __forceinline__ void fused_reduce(const EvalArgs &args, double *scrat
     }
     // several GPUs: the same CTA exchanges the reduced system with its peers over NVLink (vg_peer.cuh)
     if (args.peer.n > 1) {
-        if (args.peer_deferred) peer_post(args.red, args.peer_count, args.peer);
-        else peer_allreduce(args.red, args.peer_count, args.peer, scratch, scratch_cap);
+        if (args.peer_deferred == 1) peer_post(args.red, args.peer_count, args.peer);
+        else if (!args.peer_deferred) peer_allreduce(args.red, args.peer_count, args.peer, scratch, scratch_cap);
+        // (peer_deferred == 2: the block stays in args.red; this problem's next launch posts it from its head, so that
+        // not even the remote stores' round trip -- which the END of a grid has to wait for -- is paid by a step)
     }
     if (args.host_flag) {
         __syncthreads();
@@ -594,13 +610,9 @@ reproj_eval_kernel(const EvalArgs args, const int G_rt, const int PCG_rt)
 
     // several GPUs, deferred exchange: one CTA (the last: it has the fewest groups) forms the sum of this problem's
     // previous exchange, which has been crossing NVLink while the launches in between ran (vg_peer.cuh)
-    if (args.collect.n > 1 && blockIdx.x == gridDim.x - 1) {
-        peer_collect(args.collect_buf, args.peer_count, args.collect, st.rs, G * 2 * P * (1 + K + 6 * L));
-        __threadfence();
-        __syncthreads();
-        if (tid == 0)
-            asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(args.collect_done), "l"(args.collect.epoch) : "memory");
-    }
+    if (args.collect.n > 1 && blockIdx.x == gridDim.x - 1)
+        head_exchange(args.collect_buf, args.peer_count, args.collect, args.collect_post, args.collect_done, st.rs,
+                      G * 2 * P * (1 + K + 6 * L));
 
     // the camera's parameters and constants wait in shared memory: read where the corner phase needs them, they do
     // not occupy registers during the Gram phase

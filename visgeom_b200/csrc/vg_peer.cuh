@@ -15,7 +15,10 @@
 // peer's words of e + 1, and a peer posts those only after it has collected exchange e.  The two steps need not
 // sit in the same kernel: a launch may post exchange e in its tail and leave the collection to the head of the
 // next launch (or to a one-block kernel), so that the NVLink round trip hides behind the next launch's work --
-// the rule above is all that has to hold (collect e - 1 before posting e).
+// the rule above is all that has to hold (collect e - 1 before posting e).  With one process per rank (all ranks
+// issue the same sequence of calls) even the posting moves to the head of the next launch: a grid cannot end before
+// its remote stores are acknowledged, so a tail that posts pays one NVLink round trip per step (measured: 1.1 us
+// of a 33 us step on two GPUs).
 #pragma once
 #include <cuda_runtime.h>
 

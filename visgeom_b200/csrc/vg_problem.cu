@@ -142,6 +142,10 @@ struct vg_problem {
     unsigned long long **d_peer_ptrs = nullptr;
     std::vector<void *> peer_opened;
     bool peers = false, exchanged_in_kernel = false;
+    // one process per rank (IPC handles): a deferred exchange is posted by the head of the problem's NEXT launch (or by the
+    // fetch), which every rank issues as well; ranks of one process (connect_local, possibly driven from one thread
+    // that fetches them one after the other) post in the tail of the launch itself
+    bool post_at_head = false;
     unsigned long long epoch = 0;
     // deferred exchange (vg_problem_evaluate_async): posted by an evaluation kernel, not collected yet
     bool pending = false;
@@ -592,7 +596,7 @@ int flush_pending(vg_problem *p)
     p->pending = false;
     SolverLaunch sl{p->stream, &launch_counter()};
     const PeerCtx pc = p->peer_ctx(p->pending_epoch);
-    cudaError_t e = launch_peer_collect(p->d_redbuf[p->pending_set], red_segE_size(p->Ks), pc, p->d_collect_done, sl);
+    cudaError_t e = launch_peer_collect(p->d_redbuf[p->pending_set], red_segE_size(p->Ks), pc, p->d_collect_done, p->post_at_head, sl);
     if (e != cudaSuccess) return fail_cuda(e, "peer collect");
     return VG_OK;
 }
@@ -640,8 +644,9 @@ int evaluate_set(vg_problem *p, int s, bool timed, bool deferred = false)
             if (p->peers && p->nranks > 1 && p->n_tp + p->n_op == 0) {
                 a.peer_count = red_segE_size(p->Ks);
                 if (deferred) {
-                    a.peer_deferred = 1;
+                    a.peer_deferred = p->post_at_head ? 2 : 1;
                     if (p->pending) {
+                        a.collect_post = p->post_at_head ? 1 : 0;
                         a.collect = p->peer_ctx(p->pending_epoch);
                         a.collect_buf = p->d_redbuf[p->pending_set];
                         a.collect_done = p->d_collect_done;
@@ -1003,6 +1008,7 @@ int vg_problem_peer_connect(vg_problem *p, int rank, int nranks, const void *ipc
         p->peer_opened.push_back(q);
         ptrs[r] = static_cast<unsigned long long *>(q);
     }
+    p->post_at_head = getenv("VG_PEER_POST_TAIL") == nullptr;      // (developer knob: the tail posts, as between local ranks)
     return finish_peer_connect(p, rank, nranks, ptrs);
 }
 

@@ -558,9 +558,10 @@ __global__ void __launch_bounds__(256) peer_exchange_kernel(double *buf, int cou
 }
 
 // the second half alone: the sum of an exchange an evaluation kernel posted earlier
-__global__ void __launch_bounds__(256) peer_collect_kernel(double *buf, int count, PeerCtx pc, unsigned long long *done)
+__global__ void __launch_bounds__(256) peer_collect_kernel(double *buf, int count, PeerCtx pc, unsigned long long *done, int post)
 {
     __shared__ double scratch[2048];
+    if (post) peer_post(buf, count, pc);          // (an evaluation that left the posting to its successor)
     peer_collect(buf, count, pc, scratch, 2048);
     __threadfence();
     __syncthreads();
@@ -705,10 +706,10 @@ cudaError_t launch_peer_exchange(double *buf, int count, const PeerCtx &pc, Solv
     return cudaGetLastError();
 }
 
-cudaError_t launch_peer_collect(double *buf, int count, const PeerCtx &pc, unsigned long long *done, SolverLaunch sl)
+cudaError_t launch_peer_collect(double *buf, int count, const PeerCtx &pc, unsigned long long *done, bool post, SolverLaunch sl)
 {
     if (count > PEER_SLOT_DOUBLES) return cudaErrorInvalidValue;
-    peer_collect_kernel<<<1, 256, 0, sl.stream>>>(buf, count, pc, done);
+    peer_collect_kernel<<<1, 256, 0, sl.stream>>>(buf, count, pc, done, post ? 1 : 0);
     if (sl.launches) count_launch(sl.launches);
     return cudaGetLastError();
 }

@@ -124,7 +124,8 @@ cudaError_t launch_reduced_solve(int Ks, const SolveArgs &sa, LmConsts lm, Solve
 // buf[0..count) <- its sum over the ranks, through the peers' inboxes (one block; vg_peer.cuh)
 cudaError_t launch_peer_exchange(double *buf, int count, const PeerCtx &pc, SolverLaunch sl);
 // the collection half of an exchange an evaluation kernel has posted; *done <- its number
-cudaError_t launch_peer_collect(double *buf, int count, const PeerCtx &pc, unsigned long long *done, SolverLaunch sl);
+// post: buf still holds this rank's own block of that exchange (nobody posted it yet): post it, then collect
+cudaError_t launch_peer_collect(double *buf, int count, const PeerCtx &pc, unsigned long long *done, bool post, SolverLaunch sl);
 cudaError_t launch_finalize_backsub(int Ks, int n_rows, const double *partial, double *red, SolverLaunch sl);
 
 // ---- the plain structure's step in two launches (vg_solver_fast.cu) ------------------------------------------
