@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include "vg_peer.cuh"
+#include "vg_lm_dev.cuh"
 
 namespace vg {
 
@@ -76,6 +77,15 @@ struct EvalArgs {
     unsigned long long *collect_done;
     int n_img;
     int P;
+    // The LM loop's decision on the device (vg_lm_dev.cuh).  lm_mode 1: this is the solve's first evaluation -- the
+    // thread that finishes red[] records the cost; 2: a candidate's evaluation -- every CTA leaves at once when the solve
+    // is over (or only the gradient test is due), the packed blocks go to H or H_alt (LmState::hcur), and the finishing
+    // thread decides.  lm_so: the reduced solve's scalars about this step (SOLVE_OUT); red + host_index: cost and the
+    // three pose sums.
+    int lm_mode;
+    LmState *lm;
+    const double *lm_so;
+    double *H_alt;
 };
 
 // returns cudaError_t of the launch (cudaSuccess, or cudaErrorInvalidValue for an

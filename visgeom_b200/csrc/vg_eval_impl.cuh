@@ -412,6 +412,94 @@ __device__ __forceinline__ double reduce_rows(const double *src, const int r0, c
     return t;
 }
 
+// ---- the LM loop's decision, by the thread that finished the evaluation (vg_lm_dev.cuh) ---------------------------
+// The same tests in the same order as vg_problem_solve's host loop (Ceres' trust-region minimizer: gradient tolerance
+// at the current point, iteration / radius limits, step validity, parameter tolerance, rho, radius update, function
+// tolerance).  mode 1: first evaluation (records the cost); 2: a candidate's evaluation; limits_pass: only the
+// gradient test was due (nothing was evaluated).  ev = [cost, model decrease, |step|^2, |x|^2 over the poses] as the
+// evaluation's exchange left them, so = the reduced solve's scalars (SOLVE_OUT).  Out of line: one thread per launch.
+__device__ __noinline__ void lm_decide(LmState *st, const double *so, const double *ev, const int mode, const int limits_pass)
+{
+    // everything the decision reads, in flight together (one round trip to L2 instead of one per branch taken)
+    const LmOptions o = st->opt;
+    const double cost0 = st->cost, radius0 = st->radius, dec0 = st->decrease_factor;
+    const int iter0 = st->iter, inv0 = st->invalid_run, ns0 = st->num_successful, nu0 = st->num_unsuccessful, hcur0 = st->hcur;
+    const unsigned long long r = st->records, epoch0 = st->epoch;
+    double sv[7], e4[4];
+#pragma unroll
+    for (int i = 0; i < 7; i++) sv[i] = (mode == 2) ? __ldcg(so + i) : 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) e4[i] = __ldcg(ev + i);
+
+    double cost = cost0, radius = radius0, dec = dec0, new_cost = 0.0, rho = 0.0, step_norm = 0.0, gmax = 0.0;
+    int done = 0, accepted = 0, valid = 0, iter = iter0, inv = inv0, ns = ns0, nu = nu0;
+    if (mode == 1) {
+        cost = e4[0];
+    } else {
+        gmax = sv[0];
+        if (gmax <= o.gradient_tolerance) done = 1 + 1;
+        else if (iter >= o.max_num_iterations) done = 1 + 3;
+        else if (radius < o.min_radius) done = 1 + 4;
+        else {
+            iter++;
+            bool ok = sv[1] == 0.0 && sv[2] != 0.0;      // every pose block and the reduced system factorised
+            double model_change = 0.0, step2 = 0.0, x2 = 0.0;
+            new_cost = e4[0];
+            if (ok) {
+                model_change = -(sv[3] + 0.5 * sv[4] + e4[1]);
+                step2 = sv[5] + e4[2];
+                x2 = sv[6] + e4[3];
+                if (!(model_change > 0.0)) ok = false;
+            }
+            step_norm = sqrt(step2);
+            if (!ok) {
+                // invalid step (linear solve failed or the model predicts no decrease)
+                nu++;
+                if (++inv >= o.max_consecutive_invalid) done = 1 + 5;
+                else { radius /= dec; dec *= 2.0; }
+            } else {
+                valid = 1;
+                inv = 0;
+                if (step_norm <= o.parameter_tolerance * (sqrt(x2) + o.parameter_tolerance)) {
+                    done = 1 + 2;             // candidate discarded, as Ceres stops before taking the step
+                } else {
+                    rho = (cost - new_cost) / model_change;
+                    if (rho > o.min_relative_decrease) {
+                        const double cost_change = cost - new_cost, old_cost = cost, t = 2.0 * rho - 1.0;
+                        accepted = 1;
+                        cost = new_cost;
+                        ns++;
+                        radius = radius / fmax(1.0 / 3.0, 1.0 - t * t * t);
+                        if (radius > o.max_radius) radius = o.max_radius;
+                        dec = 2.0;
+                        if (fabs(cost_change) <= o.function_tolerance * old_cost) done = 1 + 0;
+                    } else {
+                        nu++;
+                        radius /= dec; dec *= 2.0;
+                    }
+                }
+            }
+        }
+    }
+    const int hcur = hcur0 ^ accepted;        // the next factorisation reads the packed blocks where this evaluation left them
+    const unsigned long long epoch = epoch0 + (mode == 2 ? (limits_pass ? 1 : 2) : 0);    // (several ranks: exchanges used)
+    st->done = done;
+    st->limits = !done && (iter >= o.max_num_iterations || radius < o.min_radius);
+    st->migrate = accepted;                   // ... and copies the candidate's poses and slab over
+    st->hcur = hcur;
+    if (mode == 2) st->init_scale = 0;
+    st->iter = iter; st->invalid_run = inv; st->num_successful = ns; st->num_unsuccessful = nu;
+    st->radius = radius; st->decrease_factor = dec; st->cost = cost;
+    st->epoch = epoch;
+    st->records = r + 1;
+    LmRecord *rec = &st->rec;
+    rec->seq = r + 1;
+    rec->iter = iter; rec->done = done; rec->accepted = accepted; rec->valid = valid;
+    rec->num_successful = ns; rec->num_unsuccessful = nu; rec->migrate = accepted; rec->hcur = hcur; rec->epoch = epoch;
+    rec->cost = cost; rec->radius = radius; rec->prev_cost = cost0; rec->prev_radius = radius0;
+    rec->new_cost = new_cost; rec->rho = rho; rec->step_norm = step_norm; rec->gmax = gmax;
+}
+
 // The deferred exchange this launch owes (one CTA, at its head): post this rank's block if the launch that produced it
 // left that to us, form the sum, publish "collected".  Out of line: one CTA in one launch out of many runs it, and
 // inlined it costs the kernel's main loop registers.
@@ -488,7 +576,12 @@ __device__ __forceinline__ void fused_reduce(const EvalArgs &args, double *scrat
     // several GPUs: the same CTA exchanges the reduced system with its peers over NVLink (vg_peer.cuh)
     if (args.peer.n > 1) {
         if (args.peer_deferred == 1) peer_post(args.red, args.peer_count, args.peer);
-        else if (!args.peer_deferred) peer_allreduce(args.red, args.peer_count, args.peer, scratch, scratch_cap);
+        else if (!args.peer_deferred) {
+            PeerCtx pc = args.peer;
+            // (the LM loop on the device numbers its exchanges itself: launches queued past the end of a solve use none)
+            if (args.lm_mode == 2) pc.epoch = *reinterpret_cast<volatile unsigned long long *>(&args.lm->epoch) + 1;
+            peer_allreduce(args.red, args.peer_count, pc, scratch, scratch_cap);
+        }
         // (peer_deferred == 2: the block stays in args.red; this problem's next launch posts it from its head, so that
         // not even the remote stores' round trip -- which the END of a grid has to wait for -- is paid by a step)
     }
@@ -500,6 +593,14 @@ __device__ __forceinline__ void fused_reduce(const EvalArgs &args, double *scrat
             __threadfence_system();
             asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(args.host_flag), "l"(args.host_seq) : "memory");
         }
+    }
+    if (args.lm_mode) {
+        __threadfence();
+        __syncthreads();
+#ifdef VG_LM_STAMPS
+        if (args.lm_mode == 2) { VG_LM_STAMP(args.lm, 2, 1) }
+#endif
+        if (tid == 0) lm_decide(args.lm, args.lm_so, args.red + args.host_index, args.lm_mode, 0);
     }
 }
 
@@ -607,6 +708,16 @@ reproj_eval_kernel(const EvalArgs args, const int G_rt, const int PCG_rt)
     // the grids this launch depends on have completed and flushed.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    // the LM loop on the device: the solve is over (launch queued ahead of the decision), or only the gradient test is due
+    if (args.lm_mode == 2) {
+        const int dn = *reinterpret_cast<volatile int *>(&args.lm->done), lim = *reinterpret_cast<volatile int *>(&args.lm->limits);
+        if (dn | lim) {
+            if (!dn && blockIdx.x == 0 && tid == 0) lm_decide(args.lm, args.lm_so, args.red + args.host_index, 2, 1);
+            return;
+        }
+        VG_LM_STAMP(args.lm, 2, 0)
+    }
 
     // several GPUs, deferred exchange: one CTA (the last: it has the fewest groups) forms the sum of this problem's
     // previous exchange, which has been crossing NVLink while the launches in between ran (vg_peer.cuh)
@@ -800,7 +911,13 @@ reproj_eval_kernel(const EvalArgs args, const int G_rt, const int PCG_rt)
         if (args.H) {
             // the group's packed blocks are contiguous in global memory: one more bulk copy (a ragged last
             // group, whose byte count may not be a multiple of 16, goes through ordinary stores)
-            double *Hg = args.H + (size_t)img0 * LY::NE;
+            double *Hb = args.H;
+            if (args.lm_mode == 2) {        // candidates alternate between the two buffers (LmState::hcur)
+                int hc;
+                asm volatile("ld.global.ca.s32 %0, [%1];" : "=r"(hc) : "l"(&args.lm->hcur));
+                if (hc) Hb = args.H_alt;
+            }
+            double *Hg = Hb + (size_t)img0 * LY::NE;
             const size_t hbytes = (size_t)nv * LY::NE * 8;
             const bool h_bulk = (hbytes & 15) == 0 && ((reinterpret_cast<uintptr_t>(Hg) & 15) == 0);
             if (h_bulk && tid == T0) { bulk_store(Hg, st.Hs, (uint32_t)hbytes); bulk_commit(); }

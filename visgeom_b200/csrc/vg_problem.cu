@@ -166,6 +166,13 @@ struct vg_problem {
     double *h_poll = nullptr;
     unsigned long long poll_seq = 0;            // != 0: the next evaluation's last launch posts cost + flag
     unsigned long long poll_counter = 0;
+    // the LM loop's control state on the device (vg_lm_dev.cuh): state, its pinned upload staging, the host-mapped ring of
+    // records the host watches and the host-mapped copy of the final shared-parameter slab
+    LmState *d_lm = nullptr, *h_lm_stage = nullptr;
+    LmRecord *h_lm_ring = nullptr;
+    double *h_lm_final = nullptr;
+    unsigned long long lm_seq_base = 0;
+    int lm_eval_mode = 0, lm_set_a = 0;         // != 0: the next evaluate_set is part of that loop (EvalArgs::lm_mode)
     double *d_sh_lo = nullptr, *d_sh_hi = nullptr, *d_scale_a = nullptr;
     std::vector<int> h_sh_off;
     double *d_cta_partial = nullptr;
@@ -237,6 +244,10 @@ void free_prepared(vg_problem *p)
     if (p->h_red) { cudaFreeHost(p->h_red); p->h_red = nullptr; }
     if (p->h_up) { cudaFreeHost(p->h_up); p->h_up = nullptr; }
     if (p->h_poll) { cudaFreeHost(p->h_poll); p->h_poll = nullptr; }
+    if (p->h_lm_stage) { cudaFreeHost(p->h_lm_stage); p->h_lm_stage = nullptr; }
+    if (p->h_lm_ring) { cudaFreeHost(p->h_lm_ring); p->h_lm_ring = nullptr; }
+    if (p->h_lm_final) { cudaFreeHost(p->h_lm_final); p->h_lm_final = nullptr; }
+    F(p->d_lm);
     for (auto &d : p->dss)
         for (int s = 0; s < 2; s++) F(d.d_H[s]);
     p->prepared = false;
@@ -561,6 +572,11 @@ int prepare(vg_problem *p)
         VG_CUDA(cudaMemset(p->d_fast_tickets, 0, sizeof(unsigned int) * (fast_groups(NP) + 2)));
         VG_CUDA(cudaHostAlloc(&p->h_poll, sizeof(double) * (FAST_HOST_SLAB + p->slab_doubles + 2), cudaHostAllocMapped));
         memset(p->h_poll, 0, sizeof(double) * (FAST_HOST_SLAB + p->slab_doubles + 2));
+        VG_CUDA(cudaMalloc(&p->d_lm, sizeof(LmState)));
+        VG_CUDA(cudaHostAlloc(&p->h_lm_stage, sizeof(LmState), cudaHostAllocDefault));
+        VG_CUDA(cudaHostAlloc(&p->h_lm_ring, sizeof(LmRecord) * LM_RING, cudaHostAllocMapped));
+        memset(p->h_lm_ring, 0, sizeof(LmRecord) * LM_RING);
+        VG_CUDA(cudaHostAlloc(&p->h_lm_final, sizeof(double) * (p->slab_doubles + 2), cudaHostAllocMapped));
     }
     p->cur = 0;
     // both parameter sets start from the host values
@@ -640,6 +656,14 @@ int evaluate_set(vg_problem *p, int s, bool timed, bool deferred = false)
                 a.host_flag = reinterpret_cast<unsigned long long *>(p->h_poll + FAST_HOST_FLAG);
                 a.host_seq = p->poll_seq; a.host_index = red_off_cost(p->Ks); a.host_count = 4;   // cost, model, step^2, x^2
                 p->poll_seq = 0;
+            }
+            if (p->lm_eval_mode) {
+                // part of the LM loop that runs on the device (solve_on_device): s is set A (mode 1) or set C (mode 2)
+                const int sa_ = p->lm_set_a, sc_ = sa_ ^ 1;
+                a.lm_mode = p->lm_eval_mode; a.lm = p->d_lm;
+                a.lm_so = p->d_redbuf[sc_] + red_size(p->Ks, p->nranks);
+                a.H_alt = d.d_H[sa_];
+                a.host_index = red_off_cost(p->Ks);
             }
             if (p->peers && p->nranks > 1 && p->n_tp + p->n_op == 0) {
                 a.peer_count = red_segE_size(p->Ks);
@@ -1260,6 +1284,163 @@ int vg_problem_residuals(vg_problem *p, int dataset, double *r)
     return VG_OK;
 }
 
+// The LM loop of the plain structure with its control state on the device (vg_lm_dev.cuh): the host queues the passes
+// (factorisation + Schur terms, reduced solve + back-substitution, the candidate's evaluation whose last thread takes the
+// decision), one pass ahead of the last record it has seen, and never waits for the stream.
+static int solve_on_device(vg_problem *p, const vg_solve_options &o, vg_solve_summary *sum, const double t_start)
+{
+    const int Ks = p->Ks, NP = p->n_pose, A = p->cur, C = A ^ 1;
+    SolverLaunch sl{p->stream, &launch_counter()};
+    const bool multi = p->peers && p->nranks > 1;
+    const unsigned long long base = p->lm_seq_base;
+    LmState &s0 = *p->h_lm_stage;
+    memset(&s0, 0, sizeof s0);
+    s0.limits = (0 >= o.max_num_iterations || o.initial_radius < o.min_radius) ? 1 : 0;
+    s0.init_scale = 1;
+    s0.records = base; s0.published = base;
+    s0.epoch = p->epoch + 2;                 // (the first evaluation's exchange takes p->epoch + 1)
+    s0.radius = o.initial_radius; s0.decrease_factor = 2.0;
+    s0.opt = LmOptions{o.gradient_tolerance, o.function_tolerance, o.parameter_tolerance, o.min_relative_decrease, o.min_radius,
+                       o.max_radius, o.max_num_iterations, o.max_consecutive_invalid};
+#ifdef VG_LM_STAMPS
+    for (auto &row : s0.stamp) for (int k = 0; k < 6; k++) row[k] = (k & 1) ? 0ull : ~0ull;
+#endif
+    VG_CUDA(cudaMemcpyAsync(p->d_lm, &s0, sizeof s0, cudaMemcpyHostToDevice, p->stream));
+    for (int s_ = 0; s_ < 2; s_++)
+        VG_CUDA(cudaMemsetAsync(p->d_redbuf[s_] + red_off_model(Ks), 0, 3 * sizeof(double), p->stream));
+    p->lm_set_a = A;
+    p->lm_eval_mode = 1;
+    int rc = evaluate_set(p, A, false);
+    p->lm_eval_mode = 0;
+    if (rc) return rc;
+
+    const SolveArgs sa{(int)p->slab_doubles, p->nranks, p->d_redbuf[A], p->d_redbuf[C], p->d_slab[A], p->d_slab[C], p->d_delta,
+                       p->d_sh_off, p->d_sh_lo, p->d_sh_hi, p->d_scale_a};
+    const DatasetDesc &hd = p->h_desc[A][p->fast_ds];
+    FastDesc fd;
+    memset(&fd, 0, sizeof fd);
+    fd.H = hd.H; fd.ne = hd.ne; fd.W = hd.W; fd.pose_col = hd.pose_col; fd.n_sl = hd.n_sl;
+    for (int q = 0; q < hd.n_sl; q++) { fd.sl_col[q] = hd.sl_col[q]; fd.sl_idx[q] = hd.sl_idx[q]; }
+    const Tr &ft = p->trs[p->fast_tr];
+    Ds &fds = p->dss[p->fast_ds];
+    const FastLm flm{p->d_lm, fds.d_H[C], ft.dev[A], ft.dev[C], p->d_slab[A], p->d_slab[C], (int)p->slab_doubles,
+                     p->d_redbuf[A], p->d_redbuf[C], red_segE_size(Ks), p->h_lm_ring, p->h_lm_final};
+    const LmConsts lm{o.initial_radius, o.min_lm_diagonal, o.max_lm_diagonal, 1, o.jacobi_scaling};   // (radius, init_scale: LmState's)
+    const long long max_passes = (long long)o.max_num_iterations + 1;     // every pass ends the solve or counts an iteration
+    long long queued = 0;
+    auto queue_pass = [&]() -> int {
+        PeerCtx pcx;
+        const PeerCtx *pcp = nullptr;
+        if (multi) { pcx = p->peer_ctx(0); pcp = &pcx; }          // (exchange numbers: LmState::epoch)
+        cudaError_t ce = launch_fast_step(fd, NP, Ks, p->d_scale, lm, p->d_ws, p->d_fast_scratch, p->d_fast_tickets, p->d_fail, sa,
+                                          ft.dev[A], ft.dev[C], true, sl, nullptr, nullptr, pcp, &flm);
+        if (ce != cudaSuccess) return fail_cuda(ce, "fast LM step");
+        p->lm_eval_mode = 2;
+        const int r = evaluate_set(p, C, false);
+        p->lm_eval_mode = 0;
+        queued++;
+        return r;
+    };
+    static const bool tl = getenv("VG_LM_TIMELINE") != nullptr;      // developer knob: when the host saw and did what
+    std::vector<double> t_seen, t_queued;
+    if (tl) fprintf(stderr, "[vg lm] setup + first evaluation queued at %.1f us\n", (now_s() - t_start) * 1e6);
+    rc = queue_pass();
+    if (rc) return rc;
+    if (tl) fprintf(stderr, "[vg lm] pass 1 queued at %.1f us\n", (now_s() - t_start) * 1e6);
+
+    LmRecord rec;
+    memset(&rec, 0, sizeof rec);
+    for (long long n = 0;; n++) {
+        // record n: the first evaluation (n = 0), then the decision of pass n
+        const unsigned long long want = base + (unsigned long long)n + 1;
+        volatile unsigned long long *seq = &p->h_lm_ring[(base + (unsigned long long)n) % LM_RING].seq;
+        for (unsigned long long spins = 1; *seq != want; spins++) {
+            if ((spins & 0x3FFF) == 0) {
+                const cudaError_t qe = cudaStreamQuery(p->stream);
+                if (qe == cudaSuccess) {
+                    if (*seq == want) break;
+                    return fail(VG_ERR_CUDA, "LM loop on the device: the stream drained without a decision");
+                }
+                if (qe != cudaErrorNotReady) return fail_cuda(qe, "LM step");
+            }
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+        memcpy(&rec, const_cast<const LmRecord *>(&p->h_lm_ring[(base + (unsigned long long)n) % LM_RING]), sizeof rec);
+        if (n == 0) {
+            sum->initial_cost = rec.cost;
+        } else if (o.verbose && rec.valid && !(rec.done == 1 + 2)) {
+            printf("%4d  cost %.12e  new %.12e  rho %.3e  radius %.3e  |step| %.3e\n", rec.iter, rec.prev_cost, rec.new_cost,
+                   rec.rho, rec.prev_radius, rec.step_norm);
+        }
+        if (tl) t_seen.push_back((now_s() - t_start) * 1e6);
+        if (rec.done) break;
+        // pass n + 1 is queued (and possibly running); queue pass n + 2 behind it
+        // (a pass queued past the end of the solve only publishes the last record; max_passes + 1 passes cannot all run)
+        if (queued > max_passes + 1) return fail(VG_ERR_CUDA, "LM loop on the device: no termination within the iteration limit");
+        rc = queue_pass();
+        if (rc) return rc;
+        if (tl) t_queued.push_back((now_s() - t_start) * 1e6);
+    }
+    if (tl)
+        for (size_t i = 0; i < t_seen.size(); i++)
+            fprintf(stderr, "[vg lm] record %zu seen at %.1f us, next pass queued by %.1f us\n", i, t_seen[i],
+                    i < t_queued.size() ? t_queued[i] : 0.0);
+#ifdef VG_LM_STAMPS
+    {
+        cudaStreamSynchronize(p->stream);
+        cudaMemcpy(&s0, p->d_lm, sizeof s0, cudaMemcpyDeviceToHost);
+        const char *nm[3] = {"factor", "backsub", "eval"};
+        unsigned long long prev_end = 0;
+        for (long long r_ = 1; r_ <= rec.iter && r_ < 64; r_++) {
+            const unsigned long long *w = s0.stamp[(base + r_) & 63];
+            fprintf(stderr, "[vg lm] pass %lld:", r_);
+            for (int k = 0; k < 3; k++) {
+                fprintf(stderr, "  gap %.1f %s %.1f", prev_end ? (double)(long long)(w[2 * k] - prev_end) * 1e-3 : 0.0, nm[k],
+                        (double)(long long)(w[2 * k + 1] - w[2 * k]) * 1e-3);
+                prev_end = w[2 * k + 1];
+            }
+            fprintf(stderr, "  (us)\n");
+        }
+        for (int k = 0; k < 2; k++) {
+            fprintf(stderr, "[vg lm] %s, block 10, since the kernel's first block started:", nm[k]);
+            const unsigned long long t0 = s0.stamp[(base + rec.iter) & 63][2 * k];
+            for (int i = 0; i < 5; i++) fprintf(stderr, " %.1f", (double)(long long)(s0.phase[k][i] - t0) * 1e-3);
+            fprintf(stderr, "  end %.1f (us)\n", (double)(long long)(s0.stamp[(base + rec.iter) & 63][2 * k + 1] - t0) * 1e-3);
+        }
+    }
+#endif
+    p->lm_seq_base = base + LM_RING * ((unsigned long long)queued / LM_RING + 2);
+    p->exchanged_in_kernel = false;
+    if (multi) p->epoch = rec.epoch - 1;
+    // where the final point lives: set C if the last pass accepted its candidate (nothing has copied it over), else A;
+    // its packed blocks in the buffer the evaluations alternated to
+    const int fin = rec.migrate ? C : A, hset = rec.hcur ? C : A;
+    if (hset != fin)
+        VG_CUDA(cudaMemcpyAsync(fds.d_H[fin], fds.d_H[hset], sizeof(double) * (size_t)fds.n_img * fds.ne, cudaMemcpyDeviceToDevice, p->stream));
+    p->cur = fin;
+    {
+        const size_t glob0 = p->cams.size() * CAM_STRIDE;
+        const double *cs = p->h_lm_final;
+        if (rec.num_successful > 0) {
+            for (size_t ci = 0; ci < p->cams.size(); ci++)
+                memcpy(p->cams[ci].params, cs + ci * CAM_STRIDE, sizeof(double) * p->cams[ci].K);
+            for (Tr &t : p->trs)
+                if (t.is_global) memcpy(t.host.data(), cs + glob0 + (size_t)t.glob_slot * 6, 48);
+        }
+    }
+    rc = check_peer_fail(p);
+    if (rc) return rc;
+    sum->iterations = rec.iter;
+    sum->final_cost = rec.cost;
+    sum->termination = rec.done - 1;
+    sum->num_successful = rec.num_successful;
+    sum->num_unsuccessful = rec.num_unsuccessful;
+    sum->seconds_total = now_s() - t_start;
+    sum->seconds_evaluate = 0.0;             // (no events between the launches of this loop)
+    sum->num_evaluations = rec.iter + 1;
+    return VG_OK;
+}
+
 int vg_problem_solve(vg_problem *p, const vg_solve_options *opt, vg_solve_summary *sum)
 {
     if (!p || !sum) return fail(VG_ERR_INVALID, "null argument");
@@ -1313,6 +1494,10 @@ int vg_problem_solve(vg_problem *p, const vg_solve_options *opt, vg_solve_summar
         if (rc) return rc;
         fast_everywhere = all == (double)p->nranks;
     }
+    // the plain structure: the whole loop with its decisions on the device (developer knobs: VG_LM_HOSTLOOP -- the host
+    // decides every iteration, as for every other structure; VG_LM_NOFAST -- the general kernels; VG_LM_TRACE)
+    if (fast_everywhere && !getenv("VG_LM_HOSTLOOP") && !getenv("VG_LM_NOFAST") && !getenv("VG_LM_TRACE") && !getenv("VG_LM_BLIND"))
+        return solve_on_device(p, o, sum, t_start);
     // iteration 0: evaluate at the starting point
     for (int s_ = 0; s_ < 2; s_++)
         VG_CUDA(cudaMemsetAsync(p->d_redbuf[s_] + red_off_model(Ks), 0, 3 * sizeof(double), p->stream));
@@ -1347,6 +1532,13 @@ int vg_problem_solve(vg_problem *p, const vg_solve_options *opt, vg_solve_summar
         cudaError_t ce = cudaSuccess;
         mark(0);
         static const bool nofast = getenv("VG_LM_NOFAST") != nullptr;   // developer knob: the general kernels everywhere
+        // developer knob VG_LM_BLIND=M: the third iteration's launches are queued M times over without waiting for anything
+        // in between (the same step, recomputed): device time of an iteration with the host out of the loop
+        static const int blind = getenv("VG_LM_BLIND") ? atoi(getenv("VG_LM_BLIND")) : 0;
+        const int reps = (blind > 1 && iter == 2 && fast_everywhere) ? blind : 1;
+        cudaEvent_t bev[2] = {nullptr, nullptr};
+        if (reps > 1) { cudaEventCreate(&bev[0]); cudaEventCreate(&bev[1]); cudaEventRecord(bev[0], p->stream); }
+        for (int rep = 0; rep < reps; rep++)
         if (fast_everywhere && !nofast) {
             // the plain structure: factorisation + Schur terms, then reduced solve + back-substitution, two launches
             const SolveArgs sa{(int)p->slab_doubles, p->nranks, p->d_redbuf[p->cur], p->d_redbuf[cand], p->d_slab[p->cur],
@@ -1367,11 +1559,12 @@ int vg_problem_solve(vg_problem *p, const vg_solve_options *opt, vg_solve_summar
             mark(2); mark(3);
             if (!limits) {
                 static const bool nopoll = getenv("VG_LM_NOPOLL") != nullptr;     // developer knob: copy + stream sync instead
-                if (!nopoll && !trace) { p->poll_seq = ++p->poll_counter; polled = p->poll_seq; }
-                rc = evaluate_set(p, cand, !polled);
+                if (!nopoll && !trace && rep == reps - 1) { p->poll_seq = ++p->poll_counter; polled = p->poll_seq; }
+                rc = evaluate_set(p, cand, !polled && reps == 1);
                 if (rc) return rc;
             }
             mark(4);
+            if (reps > 1 && rep == reps - 2) cudaEventRecord(bev[1], p->stream);
         } else {
         if (p->n_seg > 0)      // coupled / constant elements first: their rows of ws, max |g| per segment
             ce = launch_chain_factor(p->d_desc[p->cur], Ks, p->d_pose_start, p->d_contrib_ds, p->d_contrib_img, p->d_scale, lm,
@@ -1415,6 +1608,14 @@ int vg_problem_solve(vg_problem *p, const vg_solve_options *opt, vg_solve_summar
             if (rc) return rc;
             mark(4);
         }
+        }
+        if (reps > 1) {
+            cudaEventSynchronize(bev[1]);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, bev[0], bev[1]);
+            fprintf(stderr, "[vg lm] blind: %d iterations queued back to back: %.2f us each on the device\n", reps - 1,
+                    ms * 1e3 / (reps - 1));
+            cudaEventDestroy(bev[0]); cudaEventDestroy(bev[1]);
         }
         const double t_queued = trace ? now_s() : 0.0;
         if (polled) {

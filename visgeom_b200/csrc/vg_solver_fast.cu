@@ -16,6 +16,7 @@
 #include "vg_math.cuh"
 
 #include <cstring>
+#include <type_traits>
 
 namespace vg {
 
@@ -24,6 +25,18 @@ namespace {
 __host__ __device__ inline int pk(int a, int b, int W) { return a * W - a * (a - 1) / 2 + (b - a); }
 __device__ __forceinline__ int pks(int a, int b, int W) { return a <= b ? pk(a, b, W) : pk(b, a, W); }
 __device__ __forceinline__ constexpr int lt(int i, int j) { return i * (i + 1) / 2 + j; }
+
+// loops whose indices must be compile-time constants (register arrays: a loop the compiler declines to unroll would send
+// the whole array to local memory -- which is what "#pragma unroll" on the 6x6 Cholesky below used to end in)
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F &&f)
+{
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
+}
+#define VG_IDX(c) decltype(c)::value
 
 constexpr int LANES = 8;                    // lanes per pose
 constexpr int F_THREADS = 256, F_POSES = F_THREADS / LANES;
@@ -85,10 +98,59 @@ __device__ __forceinline__ void pair_of(int t, int Ks, int &a, int &b)
 // then a constant): the three camera models with a chain of one transform; 0: read from the descriptor.
 template <int WC, int PCC>
 __global__ void __launch_bounds__(F_THREADS)
-fast_factor_kernel(const FastDesc d, const int n_pose, const int Ks, double *scale, const LmConsts lm, double *ws,
-                   double *rows, double *grp_rows, double *gmax_rows, unsigned int *tickets, int *fail_flag)
+fast_factor_kernel(const FastDesc d, const int n_pose, const int Ks, double *scale, const LmConsts lm_in, double *ws,
+                   double *rows, double *grp_rows, double *gmax_rows, unsigned int *tickets, int *fail_flag, const FastLm flm)
 {
     asm volatile("griddepcontrol.wait;" ::: "memory");       // (programmatic dependent launch: see launch_fast_step)
+    LmConsts lm = lm_in;
+    const double *Hsrc = d.H;
+    const int nblk = flm.st ? (int)gridDim.x - 1 : (int)gridDim.x;      // (with the loop's state on the device: one extra block)
+    if (flm.st) {
+        // the loop's state is on the device (vg_lm_dev.cuh): over -> nothing to do; else radius and buffers from there,
+        // and an accepted candidate's poses, slab and reduced system become the current ones
+        LmState *st = flm.st;
+        const int4 f = __ldcg(reinterpret_cast<const int4 *>(st));           // done, limits, migrate, hcur
+        const int isc = __ldcg(&st->init_scale);
+        const double rad = __ldcg(&st->radius);
+        if ((int)blockIdx.x == nblk) {
+            // the extra block: the previous launch's decision goes to the host ring from here -- writes that cross PCIe,
+            // and the fence behind them, under this kernel's own work instead of at the end of the evaluation
+            if (threadIdx.x < 32) {
+                const unsigned long long rcd = __ldcg(&st->records), pub = __ldcg(&st->published);
+                if (pub < rcd) {
+                    const int lane = threadIdx.x;
+                    const unsigned long long *src = reinterpret_cast<const unsigned long long *>(&st->rec);
+                    unsigned long long *dst = reinterpret_cast<unsigned long long *>(flm.ring + ((rcd - 1) % LM_RING));
+                    for (int i = 1 + lane; i < (int)(sizeof(LmRecord) / 8); i += 32) dst[i] = __ldcg(src + i);
+                    if (f.x) {          // the solve is over: the final shared parameters (set C if the last step was accepted)
+                        const double *sl = f.z ? flm.slab_c : flm.slab_a;
+                        for (int i = lane; i < flm.slab_n; i += 32) flm.final_out[i] = __ldcg(sl + i);
+                    }
+                    __threadfence_system();
+                    __syncwarp();
+                    if (lane == 0) {
+                        asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(dst), "l"(rcd) : "memory");
+                        st->published = rcd;
+                    }
+                }
+            }
+            return;
+        }
+        if (f.x) return;
+        VG_LM_STAMP(st, 0, 0)
+        VG_LM_PHASE(st, 0, 0)
+        lm.radius = rad;
+        lm.init_scale = isc;
+        if (f.w) Hsrc = flm.H_alt;
+        if (f.z) {
+            const int q0 = blockIdx.x * F_POSES * 6, qn = min(F_POSES, n_pose - (int)blockIdx.x * F_POSES) * 6;
+            for (int i = threadIdx.x; i < qn; i += F_THREADS) flm.pose_a[q0 + i] = __ldcg(flm.pose_c + q0 + i);
+            if (blockIdx.x == 0) {
+                for (int i = threadIdx.x; i < flm.slab_n; i += F_THREADS) flm.slab_a[i] = __ldcg(flm.slab_c + i);
+                for (int i = threadIdx.x; i < flm.red_n; i += F_THREADS) flm.red_a[i] = __ldcg(flm.red_c + i);
+            }
+        }
+    }
     extern __shared__ double sm[];
     __shared__ int s_lc[FAST_MAX_KS + 1];
     __shared__ double s_red[F_THREADS];
@@ -113,23 +175,26 @@ fast_factor_kernel(const FastDesc d, const int n_pose, const int Ks, double *sca
         for (int k = 0; k < 6; k++) scl[k] = __ldg(scale + (size_t)p * 6 + k);
     }
     {
-        const double *src = d.H + (size_t)p0 * ne;
+        const double *src = Hsrc + (size_t)p0 * ne;
         for (int i = tid; i < np * ne; i += F_THREADS) Hs[i] = __ldcs(src + i);
     }
     __syncthreads();
+    VG_LM_PHASE(flm.st, 0, 1)
     double gmax = 0.0;
     if (p < n_pose) {
         const double *Hp = Hs + (size_t)lp * ne;
         double Lm[21];
-#pragma unroll
-        for (int i = 0; i < 6; i++)
-#pragma unroll
-            for (int j = 0; j <= i; j++) Lm[lt(i, j)] = Hp[pk(pc + j, pc + i, W)];
+        static_for<0, 6>([&](auto ic) {
+            static_for<0, VG_IDX(ic) + 1>([&](auto jc) {
+                constexpr int i = VG_IDX(ic), j = VG_IDX(jc);
+                Lm[lt(i, j)] = Hp[pk(pc + j, pc + i, W)];
+            });
+        });
         double *w = ws + (size_t)p * pose_ws_stride(Ks);
         double lam[6], invd[6] = {1.0, 1.0, 1.0, 1.0, 1.0, 1.0};
         bool empty = true;
-#pragma unroll
-        for (int k = 0; k < 6; k++) {
+        static_for<0, 6>([&](auto kc) {
+            constexpr int k = VG_IDX(kc);
             const double ckk = Lm[lt(k, k)];
             if (ckk != 0.0) empty = false;
             double sc;
@@ -141,71 +206,63 @@ fast_factor_kernel(const FastDesc d, const int n_pose, const int Ks, double *sca
             }
             const double s2 = sc * sc;
             lam[k] = fmin(fmax(s2 * ckk, lm.min_diag), lm.max_diag) * fast_rcp(lm.radius * s2);
-        }
+        });
         bool ok = true;
         if (empty) {
             // a pose nothing observes: identity factor, zero step
-#pragma unroll
-            for (int i = 0; i < 6; i++)
-#pragma unroll
-                for (int j = 0; j <= i; j++) Lm[lt(i, j)] = (i == j) ? 1.0 : 0.0;
-#pragma unroll
-            for (int k = 0; k < 6; k++) lam[k] = 0.0;
+            static_for<0, 6>([&](auto ic) {
+                static_for<0, VG_IDX(ic) + 1>([&](auto jc) {
+                    constexpr int i = VG_IDX(ic), j = VG_IDX(jc);
+                    Lm[lt(i, j)] = (i == j) ? 1.0 : 0.0;
+                });
+                lam[VG_IDX(ic)] = 0.0;
+            });
         } else {
-#pragma unroll
-            for (int k = 0; k < 6; k++) Lm[lt(k, k)] += lam[k];
-#pragma unroll
-            for (int j = 0; j < 6; j++) {
+            static_for<0, 6>([&](auto kc) { Lm[lt(VG_IDX(kc), VG_IDX(kc))] += lam[VG_IDX(kc)]; });
+            static_for<0, 6>([&](auto jc) {
+                constexpr int j = VG_IDX(jc);
                 double s = Lm[lt(j, j)];
-#pragma unroll
-                for (int k = 0; k < j; k++) s = fma(-Lm[lt(j, k)], Lm[lt(j, k)], s);
+                static_for<0, j>([&](auto kc) { s = fma(-Lm[lt(j, VG_IDX(kc))], Lm[lt(j, VG_IDX(kc))], s); });
                 if (!(s > 0.0)) { ok = false; s = 1.0; }
                 const double inv = fast_rsqrt(s);
                 Lm[lt(j, j)] = s * inv;
                 invd[j] = inv;
-#pragma unroll
-                for (int i = j + 1; i < 6; i++) {
+                static_for<j + 1, 6>([&](auto ic) {
+                    constexpr int i = VG_IDX(ic);
                     double t = Lm[lt(i, j)];
-#pragma unroll
-                    for (int k = 0; k < j; k++) t = fma(-Lm[lt(i, k)], Lm[lt(j, k)], t);
+                    static_for<0, j>([&](auto kc) { t = fma(-Lm[lt(i, VG_IDX(kc))], Lm[lt(j, VG_IDX(kc))], t); });
                     Lm[lt(i, j)] = t * inv;
-                }
-            }
+                });
+            });
         }
         if (sub == 0) {
             if (!ok) atomicExch(fail_flag, 1);
             // (the diagonal of the stored factor holds the RECIPROCALS of L's diagonal: all fast_backsub needs of it)
-#pragma unroll
-            for (int i = 0; i < 6; i++)
-#pragma unroll
-                for (int j = 0; j <= i; j++) w[lt(i, j)] = i == j ? invd[i] : Lm[lt(i, j)];
-#pragma unroll
-            for (int k = 0; k < 6; k++) w[21 + k] = lam[k];
+            static_for<0, 6>([&](auto ic) {
+                static_for<0, VG_IDX(ic) + 1>([&](auto jc) {
+                    constexpr int i = VG_IDX(ic), j = VG_IDX(jc);
+                    w[lt(i, j)] = i == j ? invd[i] : Lm[lt(i, j)];
+                });
+                w[21 + VG_IDX(ic)] = lam[VG_IDX(ic)];
+            });
         }
         double *zrow = zs + (size_t)lp * zstride;
         // the group's lanes take the columns: col < Ks -> column col of E^T (Z = L^-1 E^T), col == Ks -> the gradient
         for (int col = sub; col <= Ks; col += LANES) {
             const int lc = s_lc[col];
             double e[6];
-#pragma unroll
-            for (int i = 0; i < 6; i++) e[i] = lc >= 0 ? Hp[pks(lc, pc + i, W)] : 0.0;
-            if (col == Ks) {
-#pragma unroll
-                for (int k = 0; k < 6; k++) gmax = fmax(gmax, fabs(e[k]));
-            }
-#pragma unroll
-            for (int i = 0; i < 6; i++) {           // e <- L^-1 e
+            static_for<0, 6>([&](auto ic) { e[VG_IDX(ic)] = lc >= 0 ? Hp[pks(lc, pc + VG_IDX(ic), W)] : 0.0; });
+            if (col == Ks) static_for<0, 6>([&](auto kc) { gmax = fmax(gmax, fabs(e[VG_IDX(kc)])); });
+            static_for<0, 6>([&](auto ic) {           // e <- L^-1 e
+                constexpr int i = VG_IDX(ic);
                 double s = e[i];
-#pragma unroll
-                for (int k = 0; k < i; k++) s = fma(-Lm[lt(i, k)], e[k], s);
+                static_for<0, i>([&](auto kc) { s = fma(-Lm[lt(i, VG_IDX(kc))], e[VG_IDX(kc)], s); });
                 e[i] = s * invd[i];
-            }
+            });
             if (col == Ks) {
-#pragma unroll
-                for (int k = 0; k < 6; k++) { w[27 + k] = e[k]; zrow[6 * Ks + k] = e[k]; }
+                static_for<0, 6>([&](auto kc) { w[27 + VG_IDX(kc)] = e[VG_IDX(kc)]; zrow[6 * Ks + VG_IDX(kc)] = e[VG_IDX(kc)]; });
             } else {
-#pragma unroll
-                for (int k = 0; k < 6; k++) { w[33 + k * Ks + col] = e[k]; zrow[k * Ks + col] = e[k]; }
+                static_for<0, 6>([&](auto kc) { w[33 + VG_IDX(kc) * Ks + col] = e[VG_IDX(kc)]; zrow[VG_IDX(kc) * Ks + col] = e[VG_IDX(kc)]; });
             }
         }
     }
@@ -213,6 +270,7 @@ fast_factor_kernel(const FastDesc d, const int n_pose, const int Ks, double *sca
     for (int off = 16; off > 0; off >>= 1) gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, off));
     if ((tid & 31) == 0) s_red[tid >> 5] = gmax;
     __syncthreads();                          // also: the block's Z, z are in shared memory
+    VG_LM_PHASE(flm.st, 0, 2)
     if (tid == 0) {
         double m = 0.0;
         for (int i = 0; i < F_THREADS / 32; i++) m = fmax(m, s_red[i]);
@@ -250,16 +308,21 @@ fast_factor_kernel(const FastDesc d, const int n_pose, const int Ks, double *sca
         }
     }
     // the last block of the group folds the group's rows (and its max |g|) into one
-    const int grp = blockIdx.x / FAST_GROUP, b0 = grp * FAST_GROUP, b1 = min((int)gridDim.x, b0 + FAST_GROUP);
+    const int grp = blockIdx.x / FAST_GROUP, b0 = grp * FAST_GROUP, b1 = min(nblk, b0 + FAST_GROUP);
     __syncthreads();
+    VG_LM_PHASE(flm.st, 0, 3)
     if (tid == 0) s_last = take_ticket(tickets + grp) == (unsigned)(b1 - b0 - 1);
     __syncthreads();
+    VG_LM_PHASE(flm.st, 0, 4)
+    VG_LM_STAMP(flm.st, 0, 1)
     if (!s_last) return;
     for (int t = tid; t < npair; t += F_THREADS) grp_rows[(size_t)grp * (npair + 1) + t] = sum_rows_batched(rows + t, npair, b0, b1, 1);
     if (tid == F_THREADS - 1) {
         grp_rows[(size_t)grp * (npair + 1) + npair] = max_rows_batched(gmax_rows, 1, b0, b1);
         tickets[grp] = 0;
     }
+    __syncthreads();
+    VG_LM_STAMP(flm.st, 0, 1)
 }
 
 // ---- reduced solve + back substitution ------------------------------------------------------------
@@ -272,25 +335,36 @@ struct SolveSm {
     int ok;
 };
 
+template <int KSC>                                    // Ks <= KSC: what the register arrays over the shared parameters are unrolled to
 __global__ void __launch_bounds__(B_THREADS, 6)       // every block of a C2-sized problem resident at once
 fast_backsub_kernel(const int n_pose, const int Ks, const int n_grp, const double *grp_rows, const SolveArgs sa,
-                    const LmConsts lm, const double *seq_cur, double *seq_cand, const double *ws, double *partial,
-                    unsigned int *ticket, int *fail_flag, double *host_out, const double *fail_src)
+                    const LmConsts lm_in, const double *seq_cur, double *seq_cand, const double *ws, double *partial,
+                    unsigned int *ticket, int *fail_flag, double *host_out, const double *fail_src, const LmState *st)
 {
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    LmConsts lm = lm_in;
+    if (st) {                                   // the loop's state on the device (vg_lm_dev.cuh)
+        const int dn = __ldcg(&st->done), isc = __ldcg(&st->init_scale);
+        const double rad = __ldcg(&st->radius);
+        if (dn) return;
+        lm.radius = rad;
+        lm.init_scale = isc;
+        VG_LM_STAMP(const_cast<LmState *>(st), 1, 0)
+        VG_LM_PHASE(const_cast<LmState *>(st), 1, 0)
+    }
     // this lane's part of its pose's rows, in flight while the block solves the reduced system: lane k < 6 takes
     // z_k, row k of Z, the factor and its own component of the pose
     const int sub = threadIdx.x & (LANES - 1);
     const int p = blockIdx.x * B_POSES + threadIdx.x / LANES;
     const bool active = p < n_pose && sub < 6;
     const double *w = ws + (size_t)(p < n_pose ? p : 0) * pose_ws_stride(Ks);
-    double zk = 0.0, lamk = 0.0, xk = 0.0, Zr[FAST_MAX_KS];
+    double zk = 0.0, lamk = 0.0, xk = 0.0, Zr[KSC];
 #pragma unroll
-    for (int a = 0; a < FAST_MAX_KS; a++) Zr[a] = 0.0;
+    for (int a = 0; a < KSC; a++) Zr[a] = 0.0;
     if (active) {
         zk = __ldcg(w + 27 + sub); lamk = __ldcg(w + 21 + sub); xk = __ldcg(seq_cur + (size_t)p * 6 + sub);
 #pragma unroll
-        for (int a = 0; a < FAST_MAX_KS; a++) if (a < Ks) Zr[a] = __ldcg(w + 33 + sub * Ks + a);
+        for (int a = 0; a < KSC; a++) if (a < Ks) Zr[a] = __ldcg(w + 33 + sub * Ks + a);
     }
     __shared__ SolveSm q;
     __shared__ double sh[3][B_THREADS / 32];
@@ -322,51 +396,81 @@ fast_backsub_kernel(const int n_pose, const int Ks, const int n_grp, const doubl
         q.sc[j] = lm.init_scale ? 0.0 : sa.scale_a[j];
     }
     __syncthreads();
+    VG_LM_PHASE(const_cast<LmState *>(st), 1, 1)
     if (tid < 32) {
-        // one warp, right-looking Cholesky in shared memory (Ks <= FAST_MAX_KS < 32): warp-level syncs only
-        for (int j = lane; j < Ks; j += 32) {
-            const double ajj = q.A[j * Ks + j];
-            const double sc = lm.init_scale ? (lm.jacobi_scaling ? fast_rcp(1.0 + (ajj > 0.0 ? ajj * fast_rsqrt(ajj) : 0.0)) : 1.0) : q.sc[j];
-            q.sc[j] = sc;
+        // One warp, lane j = row j of the reduced system in registers: right-looking Cholesky and the two substitutions
+        // through shuffles (the same operations in the same order as reduced_solve_kernel's; Ks <= KSC < 32).
+        constexpr unsigned FULL = 0xffffffffu;
+        const int j = lane;
+        const bool row = j < Ks;
+        double Srow[KSC], rhs = 0.0;
+        {
+            const double ajj = row ? q.A[j * Ks + j] : 1.0;
+            const double sc = lm.init_scale ? (lm.jacobi_scaling ? fast_rcp(1.0 + (ajj > 0.0 ? ajj * fast_rsqrt(ajj) : 0.0)) : 1.0)
+                                            : (row ? q.sc[j] : 1.0);
+            if (row) q.sc[j] = sc;
             const double s2 = sc * sc;
-            for (int k = 0; k < Ks; k++)
-                q.S[j * Ks + k] = q.A[j * Ks + k] - q.Sred[j * Ks + k] +
-                                  (k == j ? fmin(fmax(s2 * ajj, lm.min_diag), lm.max_diag) * fast_rcp(lm.radius * s2) : 0.0);
-            q.rhs[j] = -(q.g[j] - q.v[j]);
+            const double damp = fmin(fmax(s2 * ajj, lm.min_diag), lm.max_diag) * fast_rcp(lm.radius * s2);
+#pragma unroll
+            for (int k = 0; k < KSC; k++)
+                Srow[k] = (row && k < Ks) ? q.A[j * Ks + k] - q.Sred[j * Ks + k] + (k == j ? damp : 0.0) : 0.0;
+            if (row) rhs = -(q.g[j] - q.v[j]);
         }
-        if (lane == 0) q.ok = 1;
-        __syncwarp();
-        for (int j = 0; j < Ks; j++) {
-            double piv = q.S[j * Ks + j];
-            if (!(piv > 0.0)) { if (lane == 0) q.ok = 0; piv = 1.0; }
-            const double inv = fast_rsqrt(piv);
-            __syncwarp();
-            if (lane == 0) q.S[j * Ks + j] = inv;               // the reciprocal of the pivot: what the substitutions need
-            for (int i = j + 1 + lane; i < Ks; i += 32) q.S[i * Ks + j] *= inv;
-            __syncwarp();
-            const int m = Ks - j - 1;
-            for (int e = lane; e < m * m; e += 32) {
-                const int i = j + 1 + e / m, k = j + 1 + e % m;
-                if (k <= i) q.S[i * Ks + k] = fma(-q.S[i * Ks + j], q.S[k * Ks + j], q.S[i * Ks + k]);
+        bool ok = true;
+#pragma unroll
+        for (int c = 0; c < KSC; c++) {
+            if (c < Ks) {
+                double piv = __shfl_sync(FULL, Srow[c], c);
+                if (!(piv > 0.0)) { ok = false; piv = 1.0; }
+                const double inv = fast_rsqrt(piv);
+                const double lic = Srow[c] * inv;                   // L_jc (rows j > c)
+#pragma unroll
+                for (int k = c + 1; k < KSC; k++) {
+                    if (k < Ks) {
+                        const double lkc = __shfl_sync(FULL, lic, k);
+                        Srow[k] = fma(-lic, lkc, Srow[k]);
+                    }
+                }
+                Srow[c] = (j == c) ? inv : lic;                     // the diagonal holds the reciprocal of the pivot
             }
-            __syncwarp();
+        }
+        // L y = rhs, column by column: lane c's entry is final when its turn comes
+        double y = rhs;
+#pragma unroll
+        for (int c = 0; c < KSC; c++) {
+            if (c < Ks) {
+                const double yc = __shfl_sync(FULL, y * Srow[c], c);
+                if (j == c) y = yc;
+                else if (j > c) y = fma(-Srow[c], yc, y);
+            }
+        }
+        // L^T x = y: lane j needs column j of L -- through shared memory, once
+#pragma unroll
+        for (int k = 0; k < KSC; k++)
+            if (row && k <= j) q.S[j * Ks + k] = Srow[k];
+        __syncwarp();
+        double Lt[KSC], x[KSC];
+#pragma unroll
+        for (int k = 0; k < KSC; k++) { Lt[k] = (row && k > j && k < Ks) ? q.S[k * Ks + j] : 0.0; x[k] = 0.0; }
+#pragma unroll
+        for (int i = KSC - 1; i >= 0; i--) {
+            if (i < Ks) {
+                double t = y;
+#pragma unroll
+                for (int k = i + 1; k < KSC; k++)
+                    if (k < Ks) t = fma(-Lt[k], x[k], t);
+                x[i] = __shfl_sync(FULL, t * Srow[i], i);            // (lane i's own value is the one that counts)
+            }
         }
         if (lane == 0) {
-            for (int i = 0; i < Ks; i++) {
-                double s = q.rhs[i];
-                for (int k = 0; k < i; k++) s = fma(-q.S[i * Ks + k], q.da[k], s);
-                q.da[i] = s * q.S[i * Ks + i];
-            }
-            for (int i = Ks - 1; i >= 0; i--) {
-                double s = q.da[i];
-                for (int k = i + 1; k < Ks; k++) s = fma(-q.S[k * Ks + i], q.da[k], s);
-                q.da[i] = s * q.S[i * Ks + i];
-            }
-            if (!q.ok)
-                for (int i = 0; i < Ks; i++) q.da[i] = 0.0;
+            q.ok = ok ? 1 : 0;
+#pragma unroll
+            for (int k = 0; k < KSC; k++)
+                if (k < Ks) q.da[k] = ok ? x[k] : 0.0;
         }
     }
     __syncthreads();
+    VG_LM_PHASE(const_cast<LmState *>(st), 1, 2)
     // ---- block 0: what the reduced solve leaves for the host and for the candidate's evaluation ----
     if (blockIdx.x == 0) {
         double *out = sa.red_cand + red_size(Ks, sa.nranks);
@@ -410,7 +514,7 @@ fast_backsub_kernel(const int n_pose, const int Ks, const int n_grp, const doubl
     if (active) {
         double s = zk;
 #pragma unroll
-        for (int a = 0; a < FAST_MAX_KS; a++) if (a < Ks) s = fma(Zr[a], q.da[a], s);
+        for (int a = 0; a < KSC; a++) if (a < Ks) s = fma(Zr[a], q.da[a], s);
         wk = s;
         m = -0.5 * s * s;
     }
@@ -445,6 +549,7 @@ fast_backsub_kernel(const int n_pose, const int Ks, const int n_grp, const doubl
     }
     if (lane == 0) { sh[0][tid >> 5] = m; sh[1][tid >> 5] = st2; sh[2][tid >> 5] = x2; }
     __syncthreads();
+    VG_LM_PHASE(const_cast<LmState *>(st), 1, 3)
     if (tid < 3) {
         double s = 0.0;
         for (int i = 0; i < B_THREADS / 32; i++) s += sh[tid][i];
@@ -455,6 +560,8 @@ fast_backsub_kernel(const int n_pose, const int Ks, const int n_grp, const doubl
     __syncthreads();
     if (tid == 0) s_last = take_ticket(ticket) == gridDim.x - 1;
     __syncthreads();
+    VG_LM_PHASE(const_cast<LmState *>(st), 1, 4)
+    VG_LM_STAMP(const_cast<LmState *>(st), 1, 1)
     if (!s_last) return;
     if (tid == 0) *ticket = 0;
     const int qn = tid >> 5;
@@ -471,6 +578,8 @@ fast_backsub_kernel(const int n_pose, const int Ks, const int n_grp, const doubl
         for (int i = tid; i < SOLVE_OUT + sa.slab_n; i += B_THREADS)
             host_out[i < SOLVE_OUT ? i : FAST_HOST_SLAB + (i - SOLVE_OUT)] = __ldcg(out + i);
     }
+    __syncthreads();
+    VG_LM_STAMP(const_cast<LmState *>(st), 1, 1)
 }
 
 // several ranks: this rank's Schur terms (its group rows folded into one), its max |g| and its failed factorisations
@@ -478,8 +587,15 @@ fast_backsub_kernel(const int n_pose, const int Ks, const int n_grp, const doubl
 // fast_backsub reads as if it were a single group row.  One block.
 __global__ void __launch_bounds__(256)
 fast_exchange_kernel(const int Ks, const int n_grp, const double *grp_rows, double *xbuf, double *row_out, int *fail_flag,
-                     const PeerCtx pc)
+                     const PeerCtx pc_in, const LmState *st)
 {
+    PeerCtx pc = pc_in;
+    if (st) {                                   // (every rank takes the same decisions: all of them leave, or none)
+        const int dn = __ldcg(&st->done);
+        const unsigned long long ep = __ldcg(&st->epoch);
+        if (dn) return;
+        pc.epoch = ep;
+    }
     __shared__ double scratch[2048];
     const int tid = threadIdx.x, npair = Ks * (Ks + 1) / 2 + Ks;
     for (int t = tid; t < npair; t += blockDim.x) xbuf[t] = sum_rows_batched(grp_rows + t, npair + 1, 0, n_grp, 1);
@@ -516,7 +632,7 @@ size_t fast_scratch(int n_pose, int Ks)
 template <int WC, int PCC>
 static cudaError_t launch_factor(const FastDesc &d, int n_pose, int Ks, double *scale, const LmConsts &lm, double *ws, double *rows,
                                  double *grp_rows, double *gmax_rows, unsigned int *tickets, int *fail_flag, size_t smem,
-                                 cudaStream_t stream)
+                                 cudaStream_t stream, const FastLm &flm)
 {
     static size_t configured[64];           // per instantiation and device; zero-initialised
     int dev = 0;
@@ -528,20 +644,23 @@ static cudaError_t launch_factor(const FastDesc &d, int n_pose, int Ks, double *
         configured[dev] = smem;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(fast_factor_blocks(n_pose)); cfg.blockDim = dim3(F_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cfg.gridDim = dim3(fast_factor_blocks(n_pose) + (flm.st ? 1 : 0)); cfg.blockDim = dim3(F_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, fast_factor_kernel<WC, PCC>, d, n_pose, Ks, scale, lm, ws, rows, grp_rows, gmax_rows, tickets,
-                              fail_flag);
+                              fail_flag, flm);
 }
 
 cudaError_t launch_fast_step(const FastDesc &d, int n_pose, int Ks, double *scale, LmConsts lm, double *ws, double *scratch,
                              unsigned int *tickets, int *fail_flag, const SolveArgs &sa, const double *seq_cur,
                              double *seq_cand, bool backsub, SolverLaunch sl, cudaEvent_t between, double *host_out,
-                             const PeerCtx *peer)
+                             const PeerCtx *peer, const FastLm *flm_in)
 {
+    FastLm flm;
+    memset(&flm, 0, sizeof flm);
+    if (flm_in) flm = *flm_in;
     if (Ks < 1 || Ks > FAST_MAX_KS || n_pose < 1 || (sa.nranks != 1 && !peer)) return cudaErrorInvalidValue;
     const int nb = fast_factor_blocks(n_pose), ng = fast_groups(n_pose), npair = Ks * (Ks + 1) / 2 + Ks;
     double *rows = scratch, *gmax_rows = rows + (size_t)nb * npair, *grp_rows = gmax_rows + nb,
@@ -552,17 +671,17 @@ cudaError_t launch_fast_step(const FastDesc &d, int n_pose, int Ks, double *scal
     // Both kernels are launched with programmatic stream serialization (they start with griddepcontrol.wait): their
     // launch latency hides under the tail of the kernel before them.
     cudaError_t e;
-    if (d.W == 13 && d.pose_col == 6) e = launch_factor<13, 6>(d, n_pose, Ks, scale, lm, ws, rows, grp_rows, gmax_rows, tickets, fail_flag, smem, sl.stream);
-    else if (d.W == 12 && d.pose_col == 5) e = launch_factor<12, 5>(d, n_pose, Ks, scale, lm, ws, rows, grp_rows, gmax_rows, tickets, fail_flag, smem, sl.stream);
-    else if (d.W == 17 && d.pose_col == 10) e = launch_factor<17, 10>(d, n_pose, Ks, scale, lm, ws, rows, grp_rows, gmax_rows, tickets, fail_flag, smem, sl.stream);
-    else e = launch_factor<0, 0>(d, n_pose, Ks, scale, lm, ws, rows, grp_rows, gmax_rows, tickets, fail_flag, smem, sl.stream);
+    if (d.W == 13 && d.pose_col == 6) e = launch_factor<13, 6>(d, n_pose, Ks, scale, lm, ws, rows, grp_rows, gmax_rows, tickets, fail_flag, smem, sl.stream, flm);
+    else if (d.W == 12 && d.pose_col == 5) e = launch_factor<12, 5>(d, n_pose, Ks, scale, lm, ws, rows, grp_rows, gmax_rows, tickets, fail_flag, smem, sl.stream, flm);
+    else if (d.W == 17 && d.pose_col == 10) e = launch_factor<17, 10>(d, n_pose, Ks, scale, lm, ws, rows, grp_rows, gmax_rows, tickets, fail_flag, smem, sl.stream, flm);
+    else e = launch_factor<0, 0>(d, n_pose, Ks, scale, lm, ws, rows, grp_rows, gmax_rows, tickets, fail_flag, smem, sl.stream, flm);
     if (sl.launches) count_launch(sl.launches);
     if (e != cudaSuccess) return e;
     if (between) cudaEventRecord(between, sl.stream);
     const double *rows_in = grp_rows, *fail_src = nullptr;
     int n_rows_in = ng;
     if (peer && peer->n > 1) {
-        fast_exchange_kernel<<<1, 256, 0, sl.stream>>>(Ks, ng, grp_rows, xbuf, xrow, fail_flag, *peer);
+        fast_exchange_kernel<<<1, 256, 0, sl.stream>>>(Ks, ng, grp_rows, xbuf, xrow, fail_flag, *peer, (const LmState *)flm.st);
         if (sl.launches) count_launch(sl.launches);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
@@ -577,8 +696,12 @@ cudaError_t launch_fast_step(const FastDesc &d, int n_pose, int Ks, double *scal
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = between ? 0 : 1;
-    e = cudaLaunchKernelEx(&cfg, fast_backsub_kernel, n_pose, Ks, n_rows_in, rows_in, sa, lm, seq_cur, seq_cand,
-                           (const double *)ws, partial, tickets + ng, fail_flag, host_out, fail_src);
+    if (Ks <= 6)
+        e = cudaLaunchKernelEx(&cfg, fast_backsub_kernel<6>, n_pose, Ks, n_rows_in, rows_in, sa, lm, seq_cur, seq_cand,
+                               (const double *)ws, partial, tickets + ng, fail_flag, host_out, fail_src, (const LmState *)flm.st);
+    else
+        e = cudaLaunchKernelEx(&cfg, fast_backsub_kernel<FAST_MAX_KS>, n_pose, Ks, n_rows_in, rows_in, sa, lm, seq_cur, seq_cand,
+                               (const double *)ws, partial, tickets + ng, fail_flag, host_out, fail_src, (const LmState *)flm.st);
     if (sl.launches) count_launch(sl.launches);
     return e != cudaSuccess ? e : cudaGetLastError();
 }

@@ -136,6 +136,17 @@ constexpr int FAST_GROUP = 20;       // blocks of fast_factor whose rows one of 
 // host-mapped words of the polled step: [reduced solve's scalars 0..7 | 16..19: cost and the three model / norm sums, as
 // the candidate's evaluation left them after its exchange | 24: its flag | candidate slab from FAST_HOST_SLAB]
 constexpr int FAST_HOST_EVAL = 16, FAST_HOST_FLAG = 24, FAST_HOST_SLAB = 32;
+// the LM loop's state on the device (vg_lm_dev.cuh): what the step's kernels read instead of host-supplied values, and what
+// the factorisation copies over when the previous candidate was accepted (set C -> set A)
+struct FastLm {
+    LmState *st;                     // null: the host drives the loop (radius etc. from LmConsts)
+    const double *H_alt;             // the other H buffer (LmState::hcur == 1: factorise this one)
+    double *pose_a; const double *pose_c;     // n_pose x 6
+    double *slab_a; const double *slab_c; int slab_n;
+    double *red_a; const double *red_c; int red_n;      // segment E of the reduction buffers
+    LmRecord *ring;                  // host-mapped ring of records (LM_RING entries) and, at the end of the solve, the final
+    double *final_out;               // shared-parameter slab: published by one extra block of the factorisation kernel
+};
 struct FastDesc {
     const double *H;                 // n_pose x ne packed blocks (the set being factorised)
     int ne, W, pose_col, n_sl;
@@ -148,6 +159,8 @@ int fast_groups(int n_pose);                  // tickets needed: fast_groups + 1
 cudaError_t launch_fast_step(const FastDesc &d, int n_pose, int Ks, double *scale, LmConsts lm, double *ws, double *scratch,
                              unsigned int *tickets, int *fail_flag, const SolveArgs &sa, const double *seq_cur,
                              double *seq_cand, bool backsub, SolverLaunch sl, cudaEvent_t between = nullptr,
-                             double *host_out = nullptr, const PeerCtx *peer = nullptr);   // peer: several ranks, see fast_exchange   // host_out: host-mapped doubles, see FAST_HOST_SLAB
+                             double *host_out = nullptr, const PeerCtx *peer = nullptr, const FastLm *flm = nullptr);
+// host_out: host-mapped doubles, see FAST_HOST_SLAB; peer: several ranks, see fast_exchange; flm: the loop's state lives
+// on the device (seq_cur / sa's "current" members = set A, the candidate ones = set C)
 
 }  // namespace vg
