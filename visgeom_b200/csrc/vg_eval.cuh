@@ -83,6 +83,8 @@ struct EvalArgs {
     // thread decides.  lm_so: the reduced solve's scalars about this step (SOLVE_OUT); red + host_index: cost and the
     // three pose sums.
     int lm_mode;
+    int lm_partial_rows;            // mode 2: rows of lm_partial = [model decrease, |step|^2, |x|^2] per block of the
+    const double *lm_partial;       // back-substitution; the last CTA adds them up at its head -> red[host_index + 1 .. + 3]
     LmState *lm;
     const double *lm_so;
     double *H_alt;

@@ -500,6 +500,28 @@ __device__ __noinline__ void lm_decide(LmState *st, const double *so, const doub
     rec->new_cost = new_cost; rec->rho = rho; rec->step_norm = step_norm; rec->gmax = gmax;
 }
 
+// The three sums over the poses the decision needs (model decrease, |step|^2, |x|^2): one row per block of the
+// back-substitution kernel, added up here -- by one CTA at the head of the candidate's evaluation, under everybody
+// else's work -- instead of by that kernel's last block on the way to this launch.  Rows lane, lane + 32, ... per lane,
+// lanes in order: the order fast_backsub's own tail uses.
+__device__ __noinline__ void lm_model_sums(const double *partial, const int rows, double *dst)
+{
+    const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (q >= 3) return;
+    constexpr int B = 24;
+    double s = 0.0;
+    for (int b = lane; b < rows; b += B * 32) {
+        double v[B];
+#pragma unroll
+        for (int i = 0; i < B; i++) v[i] = b + i * 32 < rows ? __ldcg(partial + (size_t)(b + i * 32) * 3 + q) : 0.0;
+#pragma unroll
+        for (int i = 0; i < B; i++) s += v[i];
+    }
+    double tot = 0.0;
+    for (int l = 0; l < 32; l++) tot += __shfl_sync(0xffffffffu, s, l);
+    if (lane == 0) dst[q] = tot;
+}
+
 // The deferred exchange this launch owes (one CTA, at its head): post this rank's block if the launch that produced it
 // left that to us, form the sum, publish "collected".  Out of line: one CTA in one launch out of many runs it, and
 // inlined it costs the kernel's main loop registers.
@@ -717,6 +739,7 @@ reproj_eval_kernel(const EvalArgs args, const int G_rt, const int PCG_rt)
             return;
         }
         VG_LM_STAMP(args.lm, 2, 0)
+        if (blockIdx.x == gridDim.x - 1) lm_model_sums(args.lm_partial, args.lm_partial_rows, args.red + args.host_index + 1);
     }
 
     // several GPUs, deferred exchange: one CTA (the last: it has the fewest groups) forms the sum of this problem's

@@ -54,6 +54,7 @@ struct LmState {
     // developer build: %globaltimer at the start (min over blocks) and end (max) of the three kernels of each pass
     unsigned long long stamp[64][6];
     unsigned long long phase[2][10];        // block 10's way through fast_factor / fast_backsub, latest pass
+    long long clk[16];                      // clock64 inside the reduced solve (block 10, warp 0)
 #endif
 };
 
@@ -70,8 +71,13 @@ struct LmState {
         unsigned long long t_;                                                                                          \
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                                          \
         (st)->phase[k][i] = t_;                                                                                         \
-    }
+    }                                                                                                                   \
+    __syncwarp();
+#define VG_LM_CLK(st, i)                                                                                                \
+    if ((st) && threadIdx.x == 0 && blockIdx.x == 10) (st)->clk[i] = clock64();                                         \
+    __syncwarp();
 #else
+#define VG_LM_CLK(st, i)
 #define VG_LM_STAMP(st, k, is_end)
 #define VG_LM_PHASE(st, k, i)
 #endif

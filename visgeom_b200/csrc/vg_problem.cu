@@ -174,6 +174,8 @@ struct vg_problem {
     unsigned long long lm_seq_base = 0;
     int lm_eval_mode = 0, lm_set_a = 0;         // != 0: the next evaluate_set is part of that loop (EvalArgs::lm_mode)
     double *d_sh_lo = nullptr, *d_sh_hi = nullptr, *d_scale_a = nullptr;
+    bool bounds_on_device = false;              // d_sh_lo / d_sh_hi hold what h_up holds
+    FastShared fast_shared;                     // the same and the slab positions, by value, for the fast step's kernels (Ks <= FAST_MAX_KS)
     std::vector<int> h_sh_off;
     double *d_cta_partial = nullptr;
     // fused reduction (vg_eval.cuh): per dataset its tickets / level-1 rows, all datasets' sums, table offsets
@@ -395,6 +397,7 @@ int prepare(vg_problem *p)
     p->h_slab.assign(p->slab_doubles, 0.0);
     for (int s = 0; s < 2; s++) VG_CUDA(cudaMalloc(&p->d_slab[s], p->slab_doubles * sizeof(double)));
     VG_CUDA(cudaMallocHost(&p->h_up, (p->slab_doubles + Ks + 2) * sizeof(double)));
+    p->bounds_on_device = false;
     VG_CUDA(cudaMalloc(&p->d_delta, (Ks + 2) * sizeof(double)));
 
     // dataset descriptors (one per parameter set: they differ in the H pointer)
@@ -664,6 +667,8 @@ int evaluate_set(vg_problem *p, int s, bool timed, bool deferred = false)
                 a.lm_so = p->d_redbuf[sc_] + red_size(p->Ks, p->nranks);
                 a.H_alt = d.d_H[sa_];
                 a.host_index = red_off_cost(p->Ks);
+                a.lm_partial = fast_partial_rows(p->d_fast_scratch, p->n_pose, p->Ks);
+                a.lm_partial_rows = fast_backsub_blocks(p->n_pose);
             }
             if (p->peers && p->nranks > 1 && p->n_tp + p->n_op == 0) {
                 a.peer_count = red_segE_size(p->Ks);
@@ -1306,8 +1311,9 @@ static int solve_on_device(vg_problem *p, const vg_solve_options &o, vg_solve_su
     for (auto &row : s0.stamp) for (int k = 0; k < 6; k++) row[k] = (k & 1) ? 0ull : ~0ull;
 #endif
     VG_CUDA(cudaMemcpyAsync(p->d_lm, &s0, sizeof s0, cudaMemcpyHostToDevice, p->stream));
-    for (int s_ = 0; s_ < 2; s_++)
-        VG_CUDA(cudaMemsetAsync(p->d_redbuf[s_] + red_off_model(Ks), 0, 3 * sizeof(double), p->stream));
+    // (several ranks: the first evaluation's exchange sums segment E in place, the three pose sums of set A included --
+    // never read, but they must not pile up from solve to solve)
+    if (multi) VG_CUDA(cudaMemsetAsync(p->d_redbuf[A] + red_off_model(Ks), 0, 3 * sizeof(double), p->stream));
     p->lm_set_a = A;
     p->lm_eval_mode = 1;
     int rc = evaluate_set(p, A, false);
@@ -1333,7 +1339,7 @@ static int solve_on_device(vg_problem *p, const vg_solve_options &o, vg_solve_su
         const PeerCtx *pcp = nullptr;
         if (multi) { pcx = p->peer_ctx(0); pcp = &pcx; }          // (exchange numbers: LmState::epoch)
         cudaError_t ce = launch_fast_step(fd, NP, Ks, p->d_scale, lm, p->d_ws, p->d_fast_scratch, p->d_fast_tickets, p->d_fail, sa,
-                                          ft.dev[A], ft.dev[C], true, sl, nullptr, nullptr, pcp, &flm);
+                                          ft.dev[A], ft.dev[C], true, sl, nullptr, nullptr, pcp, &flm, p->fast_shared);
         if (ce != cudaSuccess) return fail_cuda(ce, "fast LM step");
         p->lm_eval_mode = 2;
         const int r = evaluate_set(p, C, false);
@@ -1401,10 +1407,13 @@ static int solve_on_device(vg_problem *p, const vg_solve_options &o, vg_solve_su
             }
             fprintf(stderr, "  (us)\n");
         }
+        fprintf(stderr, "[vg lm] clock64 in the reduced solve:");
+        for (int i = 1; i < 14; i++) fprintf(stderr, " %lld", s0.clk[i] - s0.clk[i - 1]);
+        fprintf(stderr, "\n");
         for (int k = 0; k < 2; k++) {
             fprintf(stderr, "[vg lm] %s, block 10, since the kernel's first block started:", nm[k]);
             const unsigned long long t0 = s0.stamp[(base + rec.iter) & 63][2 * k];
-            for (int i = 0; i < 5; i++) fprintf(stderr, " %.1f", (double)(long long)(s0.phase[k][i] - t0) * 1e-3);
+            for (int i = 0; i < 10; i++) fprintf(stderr, " %.1f", (double)(long long)(s0.phase[k][i] - t0) * 1e-3);
             fprintf(stderr, "  end %.1f (us)\n", (double)(long long)(s0.stamp[(base + rec.iter) & 63][2 * k + 1] - t0) * 1e-3);
         }
     }
@@ -1469,10 +1478,20 @@ int vg_problem_solve(vg_problem *p, const vg_solve_options *opt, vg_solve_summar
         for (const Cam &c : p->cams)
             if (c.shared_off >= 0)
                 for (int k = 0; k < c.K; k++) { lo[c.shared_off + k] = c.lo[k]; hi[c.shared_off + k] = c.hi[k]; }
-        // h_up is pinned and at least 2 Ks doubles long; nothing else uses it while a solve runs
-        memcpy(p->h_up, lo.data(), sizeof(double) * Ks);
-        memcpy(p->h_up + Ks, hi.data(), sizeof(double) * Ks);
-        if (Ks) {
+        // h_up is pinned and at least 2 Ks doubles long; nothing else uses it while a solve runs; it keeps what the device
+        // has (prepare() clears bounds_on_device)
+        if (Ks <= FAST_MAX_KS) {
+            memset(&p->fast_shared, 0, sizeof p->fast_shared);
+            for (int j = 0; j < Ks; j++) { p->fast_shared.off[j] = p->h_sh_off[j]; p->fast_shared.lo[j] = lo[j]; p->fast_shared.hi[j] = hi[j]; }
+        }
+        const bool same = p->bounds_on_device && memcmp(p->h_up, lo.data(), sizeof(double) * Ks) == 0 &&
+                          memcmp(p->h_up + Ks, hi.data(), sizeof(double) * Ks) == 0;
+        if (!same) {
+            memcpy(p->h_up, lo.data(), sizeof(double) * Ks);
+            memcpy(p->h_up + Ks, hi.data(), sizeof(double) * Ks);
+        }
+        if (Ks && !same) {
+            p->bounds_on_device = true;
             VG_CUDA(cudaMemcpyAsync(p->d_sh_lo, p->h_up, sizeof(double) * Ks, cudaMemcpyHostToDevice, p->stream));
             VG_CUDA(cudaMemcpyAsync(p->d_sh_hi, p->h_up + Ks, sizeof(double) * Ks, cudaMemcpyHostToDevice, p->stream));
         }
@@ -1553,7 +1572,8 @@ int vg_problem_solve(vg_problem *p, const vg_solve_options *opt, vg_solve_summar
             const PeerCtx *pcp = nullptr;
             if (p->peers && p->nranks > 1) { pcx = p->next_peer_ctx(); pcp = &pcx; }
             ce = launch_fast_step(fd, NP, Ks, p->d_scale, lm, p->d_ws, p->d_fast_scratch, p->d_fast_tickets, p->d_fail, sa,
-                                  ft.dev[p->cur], ft.dev[cand], !limits, sl, trace ? tev[1] : nullptr, p->h_poll, pcp);
+                                  ft.dev[p->cur], ft.dev[cand], !limits, sl, trace ? tev[1] : nullptr, p->h_poll, pcp, nullptr,
+                                  p->fast_shared);
             if (ce != cudaSuccess) return fail_cuda(ce, "fast LM step");
             init_scale = false;
             mark(2); mark(3);

@@ -339,18 +339,18 @@ template <int KSC>                                    // Ks <= KSC: what the reg
 __global__ void __launch_bounds__(B_THREADS, 6)       // every block of a C2-sized problem resident at once
 fast_backsub_kernel(const int n_pose, const int Ks, const int n_grp, const double *grp_rows, const SolveArgs sa,
                     const LmConsts lm_in, const double *seq_cur, double *seq_cand, const double *ws, double *partial,
-                    unsigned int *ticket, int *fail_flag, double *host_out, const double *fail_src, const LmState *st)
+                    unsigned int *ticket, int *fail_flag, double *host_out, const double *fail_src, const LmState *st,
+                    const FastShared fs)
 {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     LmConsts lm = lm_in;
-    if (st) {                                   // the loop's state on the device (vg_lm_dev.cuh)
-        const int dn = __ldcg(&st->done), isc = __ldcg(&st->init_scale);
-        const double rad = __ldcg(&st->radius);
-        if (dn) return;
-        lm.radius = rad;
-        lm.init_scale = isc;
-        VG_LM_STAMP(const_cast<LmState *>(st), 1, 0)
-        VG_LM_PHASE(const_cast<LmState *>(st), 1, 0)
+    // the loop's state on the device (vg_lm_dev.cuh): in flight with everything else this block reads first; nothing is
+    // written before "done" has been looked at
+    int st_done = 0;
+    if (st) {
+        st_done = __ldcg(&st->done);
+        lm.init_scale = __ldcg(&st->init_scale);
+        lm.radius = __ldcg(&st->radius);
     }
     // this lane's part of its pose's rows, in flight while the block solves the reduced system: lane k < 6 takes
     // z_k, row k of Z, the factor and its own component of the pose
@@ -372,7 +372,8 @@ fast_backsub_kernel(const int n_pose, const int Ks, const int n_grp, const doubl
     const int tid = threadIdx.x, lane = tid & 31;
     const int npair = Ks * (Ks + 1) / 2 + Ks, ntri = Ks * (Ks + 1) / 2;
     const double *A = sa.red_cur + red_off_A(Ks), *ga = sa.red_cur + red_off_g(Ks);
-    // ---- the reduced system, by every block ----
+    // ---- the reduced system, by every block: the three kinds of loads on different threads (for the usual sizes), so that
+    // their round trips to L2 overlap instead of following one another ----
     for (int t = tid; t <= npair; t += B_THREADS) {
         if (t < npair) {
             const double s = sum_rows_batched(grp_rows + t, npair + 1, 0, n_grp, 1);
@@ -388,13 +389,17 @@ fast_backsub_kernel(const int n_pose, const int Ks, const int n_grp, const doubl
             q.gmax = max_rows_batched(grp_rows + npair, npair + 1, 0, n_grp);
         }
     }
-    for (int i = tid; i < Ks * Ks; i += B_THREADS) q.A[i] = __ldcg(A + i);
-    for (int j = tid; j < Ks; j += B_THREADS) {
-        q.g[j] = __ldcg(ga + j);
-        q.xs[j] = sa.slab_cur[sa.sh_off[j]];
-        q.lo[j] = sa.sh_lo[j]; q.hi[j] = sa.sh_hi[j];
-        q.sc[j] = lm.init_scale ? 0.0 : sa.scale_a[j];
+    for (int i = (tid + 3 * B_THREADS / 4) % B_THREADS; i < Ks * Ks; i += B_THREADS) q.A[i] = __ldcg(A + i);       // from thread 32 on
+    for (int j = (tid + B_THREADS / 4) % B_THREADS; j < Ks; j += B_THREADS) {                                   // from thread 96 on
+        const double gj = __ldcg(ga + j), xj = __ldcg(sa.slab_cur + fs.off[j]), sj = __ldcg(sa.scale_a + j);
+        q.g[j] = gj;
+        q.xs[j] = xj;
+        q.lo[j] = fs.lo[j]; q.hi[j] = fs.hi[j];
+        q.sc[j] = lm.init_scale ? 0.0 : sj;
     }
+    if (st_done) return;
+    VG_LM_STAMP(const_cast<LmState *>(st), 1, 0)
+    VG_LM_PHASE(const_cast<LmState *>(st), 1, 0)
     __syncthreads();
     VG_LM_PHASE(const_cast<LmState *>(st), 1, 1)
     if (tid < 32) {
@@ -416,6 +421,7 @@ fast_backsub_kernel(const int n_pose, const int Ks, const int n_grp, const doubl
                 Srow[k] = (row && k < Ks) ? q.A[j * Ks + k] - q.Sred[j * Ks + k] + (k == j ? damp : 0.0) : 0.0;
             if (row) rhs = -(q.g[j] - q.v[j]);
         }
+        VG_LM_PHASE(const_cast<LmState *>(st), 1, 5)
         bool ok = true;
 #pragma unroll
         for (int c = 0; c < KSC; c++) {
@@ -434,6 +440,7 @@ fast_backsub_kernel(const int n_pose, const int Ks, const int n_grp, const doubl
                 Srow[c] = (j == c) ? inv : lic;                     // the diagonal holds the reciprocal of the pivot
             }
         }
+        VG_LM_PHASE(const_cast<LmState *>(st), 1, 6)
         // L y = rhs, column by column: lane c's entry is final when its turn comes
         double y = rhs;
 #pragma unroll
@@ -444,6 +451,7 @@ fast_backsub_kernel(const int n_pose, const int Ks, const int n_grp, const doubl
                 else if (j > c) y = fma(-Srow[c], yc, y);
             }
         }
+        VG_LM_PHASE(const_cast<LmState *>(st), 1, 7)
         // L^T x = y: lane j needs column j of L -- through shared memory, once
 #pragma unroll
         for (int k = 0; k < KSC; k++)
@@ -462,6 +470,7 @@ fast_backsub_kernel(const int n_pose, const int Ks, const int n_grp, const doubl
                 x[i] = __shfl_sync(FULL, t * Srow[i], i);            // (lane i's own value is the one that counts)
             }
         }
+        VG_LM_PHASE(const_cast<LmState *>(st), 1, 8)
         if (lane == 0) {
             q.ok = ok ? 1 : 0;
 #pragma unroll
@@ -555,6 +564,8 @@ fast_backsub_kernel(const int n_pose, const int Ks, const int n_grp, const doubl
         for (int i = 0; i < B_THREADS / 32; i++) s += sh[tid][i];
         partial[(size_t)blockIdx.x * 3 + tid] = s;
     }
+    // (the loop's state on the device: the candidate's evaluation adds the rows up at its head, vg_eval_impl.cuh)
+    if (st) return;
     // the last block adds the rows up
     __threadfence();
     __syncthreads();
@@ -622,6 +633,14 @@ int fast_factor_blocks(int n_pose) { return (n_pose + F_POSES - 1) / F_POSES; }
 int fast_groups(int n_pose) { return (fast_factor_blocks(n_pose) + FAST_GROUP - 1) / FAST_GROUP; }
 int fast_backsub_blocks(int n_pose) { return (n_pose + B_POSES - 1) / B_POSES; }
 
+// where launch_fast_step keeps the back-substitution's rows of three sums inside its scratch
+const double *fast_partial_rows(const double *scratch, int n_pose, int Ks)
+{
+    const size_t npair = (size_t)Ks * (Ks + 1) / 2 + Ks;
+    const size_t nb = fast_factor_blocks(n_pose), ng = fast_groups(n_pose);
+    return scratch + nb * npair + nb + ng * (npair + 1);
+}
+
 size_t fast_scratch(int n_pose, int Ks)
 {
     const size_t npair = (size_t)Ks * (Ks + 1) / 2 + Ks;
@@ -656,7 +675,7 @@ static cudaError_t launch_factor(const FastDesc &d, int n_pose, int Ks, double *
 cudaError_t launch_fast_step(const FastDesc &d, int n_pose, int Ks, double *scale, LmConsts lm, double *ws, double *scratch,
                              unsigned int *tickets, int *fail_flag, const SolveArgs &sa, const double *seq_cur,
                              double *seq_cand, bool backsub, SolverLaunch sl, cudaEvent_t between, double *host_out,
-                             const PeerCtx *peer, const FastLm *flm_in)
+                             const PeerCtx *peer, const FastLm *flm_in, const FastShared &fs)
 {
     FastLm flm;
     memset(&flm, 0, sizeof flm);
@@ -698,10 +717,10 @@ cudaError_t launch_fast_step(const FastDesc &d, int n_pose, int Ks, double *scal
     cfg.attrs = attr; cfg.numAttrs = between ? 0 : 1;
     if (Ks <= 6)
         e = cudaLaunchKernelEx(&cfg, fast_backsub_kernel<6>, n_pose, Ks, n_rows_in, rows_in, sa, lm, seq_cur, seq_cand,
-                               (const double *)ws, partial, tickets + ng, fail_flag, host_out, fail_src, (const LmState *)flm.st);
+                               (const double *)ws, partial, tickets + ng, fail_flag, host_out, fail_src, (const LmState *)flm.st, fs);
     else
         e = cudaLaunchKernelEx(&cfg, fast_backsub_kernel<FAST_MAX_KS>, n_pose, Ks, n_rows_in, rows_in, sa, lm, seq_cur, seq_cand,
-                               (const double *)ws, partial, tickets + ng, fail_flag, host_out, fail_src, (const LmState *)flm.st);
+                               (const double *)ws, partial, tickets + ng, fail_flag, host_out, fail_src, (const LmState *)flm.st, fs);
     if (sl.launches) count_launch(sl.launches);
     return e != cudaSuccess ? e : cudaGetLastError();
 }

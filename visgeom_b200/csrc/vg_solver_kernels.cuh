@@ -147,19 +147,27 @@ struct FastLm {
     LmRecord *ring;                  // host-mapped ring of records (LM_RING entries) and, at the end of the solve, the final
     double *final_out;               // shared-parameter slab: published by one extra block of the factorisation kernel
 };
+// the shared parameters' slab positions and box bounds, by value (what SolveArgs::sh_off / sh_lo / sh_hi point to)
+struct FastShared {
+    int off[FAST_MAX_KS];
+    double lo[FAST_MAX_KS], hi[FAST_MAX_KS];
+};
 struct FastDesc {
     const double *H;                 // n_pose x ne packed blocks (the set being factorised)
     int ne, W, pose_col, n_sl;
     int sl_col[FAST_MAX_KS], sl_idx[FAST_MAX_KS];
 };
 size_t fast_scratch(int n_pose, int Ks);      // doubles
+int fast_factor_blocks(int n_pose);
+int fast_backsub_blocks(int n_pose);
 int fast_groups(int n_pose);                  // tickets needed: fast_groups + 1
 // factorisation + Schur terms, then reduced solve + back-substitution: leaves exactly what launch_pose_schur (fused
 // tail) + launch_pose_backsub (fused finalize) leave
+const double *fast_partial_rows(const double *scratch, int n_pose, int Ks);     // rows of [model decrease, |step|^2, |x|^2]
 cudaError_t launch_fast_step(const FastDesc &d, int n_pose, int Ks, double *scale, LmConsts lm, double *ws, double *scratch,
                              unsigned int *tickets, int *fail_flag, const SolveArgs &sa, const double *seq_cur,
-                             double *seq_cand, bool backsub, SolverLaunch sl, cudaEvent_t between = nullptr,
-                             double *host_out = nullptr, const PeerCtx *peer = nullptr, const FastLm *flm = nullptr);
+                             double *seq_cand, bool backsub, SolverLaunch sl, cudaEvent_t between,
+                             double *host_out, const PeerCtx *peer, const FastLm *flm, const FastShared &fs);
 // host_out: host-mapped doubles, see FAST_HOST_SLAB; peer: several ranks, see fast_exchange; flm: the loop's state lives
 // on the device (seq_cur / sa's "current" members = set A, the candidate ones = set C)
 
