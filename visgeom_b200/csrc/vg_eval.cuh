@@ -86,6 +86,8 @@ struct EvalArgs {
     int lm_partial_rows;            // mode 2: rows of lm_partial = [model decrease, |step|^2, |x|^2] per block of the
     const double *lm_partial;       // back-substitution; the last CTA adds them up at its head -> red[host_index + 1 .. + 3]
     LmState *lm;
+    const LmState *lm_init;         // mode 1: the loop's initial state in host-mapped memory; block 0 copies it to *lm under
+                                    // the kernel's own work (no upload in front of the solve's first launch)
     const double *lm_so;
     double *H_alt;
 };

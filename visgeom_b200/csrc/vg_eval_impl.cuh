@@ -536,7 +536,7 @@ __device__ __noinline__ void head_exchange(double *buf, int count, PeerCtx pc, i
         asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(done), "l"(pc.epoch) : "memory");
 }
 
-template <int NE>
+template <int NE, bool LMD>
 __device__ __forceinline__ void fused_reduce(const EvalArgs &args, double *scratch, const int scratch_cap)
 {
     __shared__ int s_last;
@@ -601,7 +601,7 @@ __device__ __forceinline__ void fused_reduce(const EvalArgs &args, double *scrat
         else if (!args.peer_deferred) {
             PeerCtx pc = args.peer;
             // (the LM loop on the device numbers its exchanges itself: launches queued past the end of a solve use none)
-            if (args.lm_mode == 2) pc.epoch = *reinterpret_cast<volatile unsigned long long *>(&args.lm->epoch) + 1;
+            if (LMD && args.lm_mode == 2) pc.epoch = *reinterpret_cast<volatile unsigned long long *>(&args.lm->epoch) + 1;
             peer_allreduce(args.red, args.peer_count, pc, scratch, scratch_cap);
         }
         // (peer_deferred == 2: the block stays in args.red; this problem's next launch posts it from its head, so that
@@ -616,7 +616,7 @@ __device__ __forceinline__ void fused_reduce(const EvalArgs &args, double *scrat
             asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(args.host_flag), "l"(args.host_seq) : "memory");
         }
     }
-    if (args.lm_mode) {
+    if (LMD && args.lm_mode) {
         __threadfence();
         __syncthreads();
 #ifdef VG_LM_STAMPS
@@ -679,7 +679,9 @@ __device__ __forceinline__ void store_pair(double *p, const double (&a)[N], cons
 // PC > 0: the board's point count is compiled in (with the images per group and the pose batch the launch plan picks
 // for it: plan_group / plan_pcg), so that the index arithmetic of the corner phase and every shared-memory offset
 // are constants; PC == 0: any board, sizes at run time.
-template <int MODEL, int L, int PC>
+// LMD: the instantiation that takes part in the LM loop whose control state lives on the device (EvalArgs::lm_mode, chains
+// of one transform only); the ordinary one carries none of that code.
+template <int MODEL, int L, int PC, bool LMD = false>
 __global__ void __launch_bounds__(224, (L == 1 && Camera<MODEL>::K <= 6) ? 4 : (L == 1 ? VG_WIDE_BLOCKS : 2))
 reproj_eval_kernel(const EvalArgs args, const int G_rt, const int PCG_rt)
 {
@@ -731,15 +733,22 @@ reproj_eval_kernel(const EvalArgs args, const int G_rt, const int PCG_rt)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
-    // the LM loop on the device: the solve is over (launch queued ahead of the decision), or only the gradient test is due
-    if (args.lm_mode == 2) {
+    // the LM loop on the device (vg_lm_dev.cuh).  A candidate's evaluation (mode 2): is the solve over (this launch was queued
+    // ahead of the decision), or is only the gradient test due?  The two words are in flight while the prologue below
+    // reads its inputs; they are looked at before anything is written.  The first evaluation (mode 1): block 0 brings the
+    // loop's initial state over from host-mapped memory.
+    __shared__ int s_lm_skip;                  // (bit 0: done, bit 1: limits; through shared memory: no register lives that long)
+    if (LMD && args.lm_mode == 2 && tid == 33) {
         const int dn = *reinterpret_cast<volatile int *>(&args.lm->done), lim = *reinterpret_cast<volatile int *>(&args.lm->limits);
-        if (dn | lim) {
-            if (!dn && blockIdx.x == 0 && tid == 0) lm_decide(args.lm, args.lm_so, args.red + args.host_index, 2, 1);
-            return;
-        }
-        VG_LM_STAMP(args.lm, 2, 0)
-        if (blockIdx.x == gridDim.x - 1) lm_model_sums(args.lm_partial, args.lm_partial_rows, args.red + args.host_index + 1);
+        s_lm_skip = (dn ? 1 : 0) | (lim ? 2 : 0);
+    }
+    // (the pose sums of the step, by the CTA with the fewest groups: before the prologue, while few registers are live
+    // across the call; harmless when the solve turns out to be over)
+    if (LMD && args.lm_mode == 2 && blockIdx.x == gridDim.x - 1)
+        lm_model_sums(args.lm_partial, args.lm_partial_rows, args.red + args.host_index + 1);
+    if (LMD && args.lm_mode == 1 && blockIdx.x == 0 && tid >= 64 && tid < 64 + (int)(sizeof(LmState) / 8)) {
+        const unsigned long long v = *(reinterpret_cast<const volatile unsigned long long *>(args.lm_init) + (tid - 64));
+        reinterpret_cast<unsigned long long *>(args.lm)[tid - 64] = v;
     }
 
     // several GPUs, deferred exchange: one CTA (the last: it has the fewest groups) forms the sum of this problem's
@@ -783,6 +792,15 @@ reproj_eval_kernel(const EvalArgs args, const int G_rt, const int PCG_rt)
     // poses of the first PCG groups: one thread per image
     if (tid < PCG * G) stage_poses(0, tid);
     __syncthreads();
+    if (LMD && args.lm_mode == 2) {
+        const int skip = s_lm_skip;
+        if (skip) {
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            if (!(skip & 1) && blockIdx.x == 0 && tid == 0) lm_decide(args.lm, args.lm_so, args.red + args.host_index, 2, 1);
+            return;
+        }
+        VG_LM_STAMP(args.lm, 2, 0)
+    }
     VG_PC_DECL
 
     // ---- A: one thread per (image, corner) -- the camera model, then the rows into the staging area -----------
@@ -935,7 +953,7 @@ reproj_eval_kernel(const EvalArgs args, const int G_rt, const int PCG_rt)
             // the group's packed blocks are contiguous in global memory: one more bulk copy (a ragged last
             // group, whose byte count may not be a multiple of 16, goes through ordinary stores)
             double *Hb = args.H;
-            if (args.lm_mode == 2) {        // candidates alternate between the two buffers (LmState::hcur)
+            if (LMD && args.lm_mode == 2) {        // candidates alternate between the two buffers (LmState::hcur)
                 int hc;
                 asm volatile("ld.global.ca.s32 %0, [%1];" : "=r"(hc) : "l"(&args.lm->hcur));
                 if (hc) Hb = args.H_alt;
@@ -968,11 +986,11 @@ reproj_eval_kernel(const EvalArgs args, const int G_rt, const int PCG_rt)
             const int e = tid + q * blockDim.x;
             if (e < LY::NE) args.cta_partial[(size_t)blockIdx.x * LY::NE + e] = part[q];
         }
-        if (args.tickets) fused_reduce<LY::NE>(args, st.rs, G * 2 * P * (1 + K + 6 * L));
+        if (args.tickets) fused_reduce<LY::NE, LMD>(args, st.rs, G * 2 * P * (1 + K + 6 * L));
     }
 }
 
-template <int MODEL, int L, int PC>
+template <int MODEL, int L, int PC, bool LMD = false>
 cudaError_t launch_fixed(const EvalArgs &args, const LaunchPlan &pl, cudaStream_t stream, unsigned long long *launches,
                          int *grid_out, bool query_only)
 {
@@ -984,12 +1002,12 @@ cudaError_t launch_fixed(const EvalArgs &args, const LaunchPlan &pl, cudaStream_
     cudaGetDevice(&dev);
     dev &= 63;
     if (pl.smem > configured_bytes[dev] || planned_threads[dev] != pl.threads) {
-        cudaError_t e = cudaFuncSetAttribute(reproj_eval_kernel<MODEL, L, PC>,
+        cudaError_t e = cudaFuncSetAttribute(reproj_eval_kernel<MODEL, L, PC, LMD>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
         if (e != cudaSuccess) return e;
         configured_bytes[dev] = (int)pl.smem;
         planned_threads[dev] = pl.threads;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[dev], reproj_eval_kernel<MODEL, L, PC>,
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[dev], reproj_eval_kernel<MODEL, L, PC, LMD>,
                                                           pl.threads, (size_t)pl.smem);
         if (e != cudaSuccess) return e;
         e = cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
@@ -1009,7 +1027,7 @@ cudaError_t launch_fixed(const EvalArgs &args, const LaunchPlan &pl, cudaStream_
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-    const cudaError_t le = cudaLaunchKernelEx(&cfg, reproj_eval_kernel<MODEL, L, PC>, args, pl.G, pl.PCG);
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, reproj_eval_kernel<MODEL, L, PC, LMD>, args, pl.G, pl.PCG);
     if (launches) count_launch(launches);
     return le != cudaSuccess ? le : cudaGetLastError();
 }
@@ -1025,10 +1043,17 @@ cudaError_t launch_one(const EvalArgs &args, cudaStream_t stream, unsigned long 
 #ifndef VG_NO_FIXED_BOARD
     if constexpr (L <= 2) {
         constexpr int PC = 54;
-        if (args.P == PC && pl.G == plan_group(PC) && pl.PCG == plan_pcg(Layout<MODEL, L>::POSE, plan_group(PC)))
+        if (args.P == PC && pl.G == plan_group(PC) && pl.PCG == plan_pcg(Layout<MODEL, L>::POSE, plan_group(PC))) {
+            if constexpr (L == 1)
+                if (args.lm_mode) return launch_fixed<MODEL, L, PC, true>(args, pl, stream, launches, grid_out, query_only);
             return launch_fixed<MODEL, L, PC>(args, pl, stream, launches, grid_out, query_only);
+        }
     }
 #endif
+    if (args.lm_mode) {
+        if constexpr (L == 1) return launch_fixed<MODEL, L, 0, true>(args, pl, stream, launches, grid_out, query_only);
+        return cudaErrorInvalidValue;
+    }
     return launch_fixed<MODEL, L, 0>(args, pl, stream, launches, grid_out, query_only);
 }
 

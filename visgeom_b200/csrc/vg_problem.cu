@@ -576,7 +576,7 @@ int prepare(vg_problem *p)
         VG_CUDA(cudaHostAlloc(&p->h_poll, sizeof(double) * (FAST_HOST_SLAB + p->slab_doubles + 2), cudaHostAllocMapped));
         memset(p->h_poll, 0, sizeof(double) * (FAST_HOST_SLAB + p->slab_doubles + 2));
         VG_CUDA(cudaMalloc(&p->d_lm, sizeof(LmState)));
-        VG_CUDA(cudaHostAlloc(&p->h_lm_stage, sizeof(LmState), cudaHostAllocDefault));
+        VG_CUDA(cudaHostAlloc(&p->h_lm_stage, sizeof(LmState), cudaHostAllocMapped));
         VG_CUDA(cudaHostAlloc(&p->h_lm_ring, sizeof(LmRecord) * LM_RING, cudaHostAllocMapped));
         memset(p->h_lm_ring, 0, sizeof(LmRecord) * LM_RING);
         VG_CUDA(cudaHostAlloc(&p->h_lm_final, sizeof(double) * (p->slab_doubles + 2), cudaHostAllocMapped));
@@ -663,7 +663,7 @@ int evaluate_set(vg_problem *p, int s, bool timed, bool deferred = false)
             if (p->lm_eval_mode) {
                 // part of the LM loop that runs on the device (solve_on_device): s is set A (mode 1) or set C (mode 2)
                 const int sa_ = p->lm_set_a, sc_ = sa_ ^ 1;
-                a.lm_mode = p->lm_eval_mode; a.lm = p->d_lm;
+                a.lm_mode = p->lm_eval_mode; a.lm = p->d_lm; a.lm_init = p->h_lm_stage;
                 a.lm_so = p->d_redbuf[sc_] + red_size(p->Ks, p->nranks);
                 a.H_alt = d.d_H[sa_];
                 a.host_index = red_off_cost(p->Ks);
@@ -1310,7 +1310,8 @@ static int solve_on_device(vg_problem *p, const vg_solve_options &o, vg_solve_su
 #ifdef VG_LM_STAMPS
     for (auto &row : s0.stamp) for (int k = 0; k < 6; k++) row[k] = (k & 1) ? 0ull : ~0ull;
 #endif
-    VG_CUDA(cudaMemcpyAsync(p->d_lm, &s0, sizeof s0, cudaMemcpyHostToDevice, p->stream));
+    // (no upload: block 0 of the first evaluation fetches *h_lm_stage itself, EvalArgs::lm_init)
+    std::atomic_thread_fence(std::memory_order_release);
     // (several ranks: the first evaluation's exchange sums segment E in place, the three pose sums of set A included --
     // never read, but they must not pile up from solve to solve)
     if (multi) VG_CUDA(cudaMemsetAsync(p->d_redbuf[A] + red_off_model(Ks), 0, 3 * sizeof(double), p->stream));
