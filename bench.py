@@ -525,21 +525,28 @@ def run_ours(args):
 
     def e2e_fetch(i):
         return probs[i % args.sets].fetch_reduced()
-    n_e2e = max(10, min(args.steps, 200))
+    # (at least 200 steps: the leg is timed on the host clock, and with 20 of them -- 3.5 ms -- a single NVML query of the
+    # clock sampler, which can hold submissions up for a millisecond, moved the figure by a third from run to run)
+    n_e2e = max(args.steps, 200)
     for i in range(3):
         e2e_issue(i); e2e_fetch(i)
     barrier()
     t_w0 = time.time()
     t0 = time.perf_counter()
     e2e_issue(0)
+    e2e_trace = [] if os.environ.get("VG_BENCH_E2E_TRACE") else None      # developer knob: host time every 20 steps
     for i in range(1, n_e2e):
         e2e_issue(i)
         c_e2e, _ = e2e_fetch(i - 1)
+        if e2e_trace is not None and i % 20 == 0:
+            e2e_trace.append(round((time.perf_counter() - t0) * 1e6))
     c_e2e, _ = e2e_fetch(n_e2e - 1)
     torch.cuda.synchronize()
     e2e_s = max_over_ranks((time.perf_counter() - t0) / n_e2e)
     windows.append((t_w0, time.time()))
     e2e_value = world * n_img * P / e2e_s
+    if e2e_trace:
+        print("e2e host clock every 20 steps (us):", e2e_trace, file=sys.stderr)
     for Pm in probs:
         Pm.close()
     probs = []
@@ -567,10 +574,18 @@ def run_ours(args):
     lm_leg(make_gpu_problem, d, model_id, 3)          # warm-up (allocations, first launches)
     barrier()
     t_w0 = time.time()
-    lm = lm_leg(make_gpu_problem, d, model_id, 25)
+    # five solves of the same problem (fresh handles), the median reported: a solve lasts half a millisecond on the host
+    # clock, and one NVML query of the clock sampler landing inside it would otherwise decide the figure
+    lm_runs = []
+    for _ in range(5):
+        barrier()
+        r_ = lm_leg(make_gpu_problem, d, model_id, 25)
+        r_["seconds"] = max_over_ranks(r_["seconds"])
+        r_["iters_per_s"] = r_["iterations"] / r_["seconds"]
+        lm_runs.append(r_)
     windows.append((t_w0, time.time()))
-    lm["seconds"] = max_over_ranks(lm["seconds"])
-    lm["iters_per_s"] = lm["iterations"] / lm["seconds"]
+    lm = sorted(lm_runs, key=lambda r_: r_["iters_per_s"])[len(lm_runs) // 2]
+    lm["runs_iters_per_s"] = [r_["iters_per_s"] for r_ in lm_runs]
     if world > 1:
         # every rank must have walked the same trajectory to the same parameters, bit for bit
         mine = torch.tensor(lm["intrinsics"] + [lm["final_cost"]], dtype=torch.float64, device=dev)
@@ -641,15 +656,17 @@ def run_ours(args):
             "roofline": main["roofline"],
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_s * 1e3,
-                    "what": "vg_problem_* with pinned host inputs every step; result = cost + reduced normal equations"},
+                    "ms_per_step": e2e_s * 1e3, "steps": n_e2e,
+                    "what": "vg_problem_* with pinned host inputs every step (two steps in flight: the upload of one overlaps "
+                            "the kernel of the other); result = cost + reduced normal equations; host clock"},
             "e2e_ceres_contract": {"value": full_value, "unit": UNIT,
                                    "what": "vg_eval_chain with host (pageable) buffers: observations and poses up, r, J_intr, "
                                            "J_pose and H back (~12 KB per image: PCIe bound), chunked over two streams"},
             "lm": None if lm is None else {"iters_per_s": lm["iters_per_s"], "iterations": lm["iterations"], "seconds": lm["seconds"],
                                            "final_cost": lm["final_cost"], "intrinsics": lm["intrinsics"],
                                            "bit_identical_across_ranks": lm.get("bit_identical_across_ranks"),
-                                           "what": "vg_problem_solve on the same workload from the perturbed initial guess "
+                                           "runs_iters_per_s": lm.get("runs_iters_per_s"),
+                                           "what": "median of five vg_problem_solve runs on the same workload from the perturbed initial guess "
                                                    "(one LM iteration = evaluation + per-pose Schur elimination + shared solve + "
                                                    "back-substitution + candidate evaluation)"},
             "gpu_launches": int(round(main["launches_per_step"] * args.steps)), "gpu_launches_per_step": main["launches_per_step"],

@@ -15,7 +15,22 @@
 
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 namespace vg {
+
+// loops whose indices must be compile-time constants (register arrays: a loop the compiler declines to unroll would send
+// the whole array to local memory -- which is what "#pragma unroll" on the 6x6 Cholesky below used to end in)
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F &&f)
+{
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
+}
+#define VG_IDX(c) decltype(c)::value
+
 
 constexpr int MODEL_EUCM = 0;
 constexpr int MODEL_UCM = 1;

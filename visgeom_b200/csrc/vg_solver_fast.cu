@@ -26,17 +26,6 @@ __host__ __device__ inline int pk(int a, int b, int W) { return a * W - a * (a -
 __device__ __forceinline__ int pks(int a, int b, int W) { return a <= b ? pk(a, b, W) : pk(b, a, W); }
 __device__ __forceinline__ constexpr int lt(int i, int j) { return i * (i + 1) / 2 + j; }
 
-// loops whose indices must be compile-time constants (register arrays: a loop the compiler declines to unroll would send
-// the whole array to local memory -- which is what "#pragma unroll" on the 6x6 Cholesky below used to end in)
-template <int I, int N, class F>
-__device__ __forceinline__ void static_for(F &&f)
-{
-    if constexpr (I < N) {
-        f(std::integral_constant<int, I>{});
-        static_for<I + 1, N>(f);
-    }
-}
-#define VG_IDX(c) decltype(c)::value
 
 constexpr int LANES = 8;                    // lanes per pose
 constexpr int F_THREADS = 256, F_POSES = F_THREADS / LANES;

@@ -2,6 +2,7 @@
 // (per-block partials in a fixed layout, then one block summing them in index order),
 // so results are bit-reproducible run to run for a fixed problem.
 #include "vg_solver_kernels.cuh"
+#include "vg_math.cuh"
 
 #include <cstring>
 #include <vector>
@@ -47,24 +48,22 @@ __device__ __forceinline__ constexpr int lt(int i, int j) { return i * (i + 1) /
 // x <- L^-1 x; invd = reciprocals of L's diagonal (one division per pivot instead of one per solve)
 __device__ __forceinline__ void forward_subst(const double (&Lm)[21], const double (&invd)[6], double (&x)[6])
 {
-#pragma unroll
-    for (int i = 0; i < 6; i++) {
+    static_for<0, 6>([&](auto ic) {
+        constexpr int i = VG_IDX(ic);
         double s = x[i];
-#pragma unroll
-        for (int k = 0; k < i; k++) s = fma(-Lm[lt(i, k)], x[k], s);
+        static_for<0, i>([&](auto kc) { s = fma(-Lm[lt(i, VG_IDX(kc))], x[VG_IDX(kc)], s); });
         x[i] = s * invd[i];
-    }
+    });
 }
 
 __device__ __forceinline__ void backward_subst(const double (&Lm)[21], double (&x)[6])
 {
-#pragma unroll
-    for (int i = 5; i >= 0; i--) {
+    static_for<0, 6>([&](auto rc) {
+        constexpr int i = 5 - VG_IDX(rc);
         double s = x[i];
-#pragma unroll
-        for (int k = i + 1; k < 6; k++) s = fma(-Lm[lt(k, i)], x[k], s);
+        static_for<i + 1, 6>([&](auto kc) { s = fma(-Lm[lt(VG_IDX(kc), i)], x[VG_IDX(kc)], s); });
         x[i] = s / Lm[lt(i, i)];
-    }
+    });
 }
 
 // ---- reduced (shared-block) system on the device ----------------------------------------------------------
@@ -378,25 +377,23 @@ pose_factor_kernel(const DatasetDesc *desc_all, int n_pose, int Ks,
         } else {
 #pragma unroll
             for (int k = 0; k < 6; k++) Lm[lt(k, k)] += lam[k];
-            // Cholesky, in place
-#pragma unroll
-            for (int j = 0; j < 6; j++) {
+            // Cholesky, in place (compile-time indices: a loop left rolled would send Lm to local memory)
+            static_for<0, 6>([&](auto jc) {
+                constexpr int j = VG_IDX(jc);
                 double s = Lm[lt(j, j)];
-#pragma unroll
-                for (int k = 0; k < j; k++) s = fma(-Lm[lt(j, k)], Lm[lt(j, k)], s);
+                static_for<0, j>([&](auto kc) { s = fma(-Lm[lt(j, VG_IDX(kc))], Lm[lt(j, VG_IDX(kc))], s); });
                 if (!(s > 0.0)) { ok = false; s = 1.0; }
                 s = sqrt(s);
                 Lm[lt(j, j)] = s;
                 const double inv = 1.0 / s;
                 invd[j] = inv;
-#pragma unroll
-                for (int i = j + 1; i < 6; i++) {
+                static_for<j + 1, 6>([&](auto ic) {
+                    constexpr int i = VG_IDX(ic);
                     double t = Lm[lt(i, j)];
-#pragma unroll
-                    for (int k = 0; k < j; k++) t = fma(-Lm[lt(i, k)], Lm[lt(j, k)], t);
+                    static_for<0, j>([&](auto kc) { t = fma(-Lm[lt(i, VG_IDX(kc))], Lm[lt(j, VG_IDX(kc))], t); });
                     Lm[lt(i, j)] = t * inv;
-                }
-            }
+                });
+            });
         }
         if (sub == 0) {
             if (!ok) atomicExch(fail_flag, 1);
