@@ -1,6 +1,7 @@
 // Stand-in for the few Ceres declarations visgeom's include/ceres.h and
 // include/calibration/calib_cost_functions.h name.  TEST INFRASTRUCTURE ONLY (see oracle/shim/Eigen/Eigen).
-// Only the CostFunction interface is functional: the LM solver itself is restated in oracle/oracle_lm.c.
+// The CostFunction / FirstOrderFunction interfaces are functional; the LM solver itself is restated in
+// oracle/oracle_lm.c, the line-search GradientProblemSolver in gradient_solver.h.
 #ifndef VISGEOM_ORACLE_CERES_SHIM
 #define VISGEOM_ORACLE_CERES_SHIM
 #include <vector>
@@ -40,9 +41,7 @@ class SoftLOneLoss;
 class CauchyLoss;
 class Problem;
 class Solver;
-class GradientProblem;
-class GradientProblemSolver;
-template <typename G> class BiCubicInterpolator;
 void Solve();
 }  // namespace ceres
+#include "gradient_solver.h"   // BiCubicInterpolator, GradientProblem, GradientProblemSolver (restated, see there)
 #endif
