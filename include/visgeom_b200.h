@@ -321,13 +321,41 @@ int vg_reconstruct_points_dev(int model, const double *intr, long long n, const 
  * avg = _avgVal (mean of the responses kept, :318) and count of them per image.  sigma1 / sigma2 are computeResponse's
  * arguments (detectPattern calls it with 0.7 and 1.4, 2, 1: :229-233); filter sizes 3 and 1 + 2 ceil(sigma2).  Every
  * float equals the CPU restatement's bit for bit; avg is summed in a different, fixed order (last-bit differences).
- * avg / count may be NULL.  The later stages of the detector (candidate selection, graph weaving, sub-pixel refinement,
- * :223-260, :47-198) are not built yet: "images" datasets are still rejected by the front end. */
+ * avg / count may be NULL. */
 int vg_corner_response(const unsigned char *img, int n_img, int width, int height, double sigma1, double sigma2,
                        float *resp, float *gradx, float *grady, float *imgrad, double *avg, long long *count);
 int vg_corner_response_dev(const unsigned char *img, int n_img, int width, int height, double sigma1, double sigma2,
                            float *resp, float *gradx, float *grady, float *imgrad, double *avg, long long *count,
                            void *stream);
+
+/* ---- checkerboard detector (src/calibration/corner_detector.cpp:223-260; include/calibration/corner_detector.h:49-60) --
+ * CornerDetector(Nx, Ny, 3, improve).setImage(img) + detectPattern(ptVec) for n_img 8-bit images of width x height (row
+ * major, one after the other), as GenericCameraCalibration::extractGridProjections runs it per image
+ * (unified_calibration.cpp:995,1031-1033).  found[i] = detectPattern's return value; corners + i * Nx * Ny * 2 = ptVec
+ * (u, v per corner, board order) when found.  The scales 1.4 / 2 / 1 are tried in turn per image (:225-245).  On the
+ * GPU: blurs, gradients, response (:262-329), the scan for local maxima (:494-534) and, with improve != 0, the sub-pixel
+ * refinement (:162-198: SubpixelCorner minimised with ceres::GradientProblemSolver's defaults, one warp per corner);
+ * on host threads, one image each: candidate tests, the flood-fill graph and the pattern search (:331-492, :536-1076).
+ * Integer corner positions equal the reference's exactly; refined positions to a tolerance (the minimiser is a
+ * restatement of Ceres' line search). */
+int vg_detect_pattern(const unsigned char *img, int n_img, int width, int height, int Nx, int Ny, int improve,
+                      double *corners, unsigned char *found);
+/* The host stages of one scale on their own (no GPU needed): image, its two blurred copies (_src1, _src2), the local
+ * maxima of the response (value, u v) in any order, INIT_RADIUS -> candidates in the order constructGraph numbers them
+ * (cand, at most cand_cap; n_cand = how many there are), the grid (Nx Ny integer corners), initPoin's start values
+ * (5 per corner, :1261-1298) and improveCorners' radMax per corner (:164-175).  Outputs may be NULL.  Returns 1 when the
+ * pattern was found, 0 when not, a negative error code otherwise. */
+int vg_detector_host_stages(const unsigned char *img, const unsigned char *s1, const unsigned char *s2, int width, int height,
+                            const float *max_val, const int *max_uv, int n_max, int Nx, int Ny, int init_radius, int *cand,
+                            int cand_cap, int *n_cand, int *grid, double *start, double *reach);
+/* SubpixelCorner(gradu, gradv, prior_i, 7, length_i).Evaluate(params_i) (:47-100) for n parameter vectors (5 doubles
+ * each) on one pair of gradient maps: cost[n], gradient[5 n].  Host buffers. */
+int vg_subpixel_evaluate(const float *gradx, const float *grady, int width, int height, int n, const double *prior,
+                         const double *length, const double *params, double *cost, double *gradient);
+/* improveCorners' minimisation alone (:176-196) for n corners on one pair of gradient maps: start = initPoin's values,
+ * refined[2 n] = the minimiser's u, v; iterations may be NULL. */
+int vg_subpixel_refine(const float *gradx, const float *grady, int width, int height, int n, const double *prior,
+                       const double *length, const double *start, double *refined, int *iterations);
 
 #ifdef __cplusplus
 }

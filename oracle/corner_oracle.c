@@ -12,8 +12,9 @@
  * with the rounding error carried from tap to tap and the centre tap taking what is left of 256
  * (getGaussianKernelFixedPoint_ED), border BORDER_REFLECT_101, both passes in integers, one rounding at the end:
  * (sum + 2^15) >> 16.  Pinned bit for bit against cv2 4.13 (the python wheel of this container) by
- * tests/golden/make_corner_golden.py -> tests/golden/corner_response.npz.  The stencil part has no such anchor: the
- * reference's own code needs OpenCV C++ to compile (absent), so it is pinned on this restatement only. */
+ * tests/golden/make_corner_golden.py -> tests/golden/corner_response.npz.  The stencil part is pinned on the
+ * reference's own corner_detector.cpp compiled against an OpenCV stand-in (oracle/_ref/libvisgeom_refdet.so, whose
+ * GaussianBlur is the function below): tests/test_detector_oracle.py, fixtures tests/golden/detector.npz. */
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -97,7 +98,9 @@ long vgo_corner_response(const uint8_t *img, int width, int height, double sigma
             const double iuu = S2(v, u - 1) + S2(v, u + 1) - 2 * S2(v, u);
             const double ivv = S2(v - 1, u) + S2(v + 1, u) - 2 * S2(v, u);
             const double iuv = (S2(v - 1, u - 1) + S2(v + 1, u + 1) - S2(v + 1, u - 1) - S2(v - 1, u + 1)) / 4;
-            const double gx = (S2(v, u + 1) - S2(v, u - 1)) / 2, gy = (S2(v + 1, u) - S2(v - 1, u)) / 2;
+            /* :304-305 divide two 8-bit pixels' difference by the int 2 * HSIZE: an INTEGER division (towards zero) */
+            const double gx = (double)(((int)s2[(size_t)v * width + u + 1] - (int)s2[(size_t)v * width + u - 1]) / 2);
+            const double gy = (double)(((int)s2[(size_t)(v + 1) * width + u] - (int)s2[(size_t)(v - 1) * width + u]) / 2);
             const double gsq = gx * gx + gy * gy;
             const double val = -iuu * ivv + iuv * iuv - 0.001 * (gsq * gsq);
             if (val > 0.01) {

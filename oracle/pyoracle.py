@@ -376,3 +376,77 @@ class Reference(_Evaluator):
         r = np.zeros(6); J1 = np.zeros((6, 6)); J2 = np.zeros((6, 6))
         self.lib.vgref_odometry_prior(errV, errW, lam, _dp(o1), _dp(o2), _dp(a), _dp(b), _dp(r), _dp(J1), _dp(J2))
         return r, J1, J2
+
+
+class ReferenceDetector:
+    """The reference's own checkerboard detector (src/calibration/corner_detector.cpp compiled where it lies against the
+    OpenCV / Ceres stand-ins of oracle/shim -> oracle/_ref/libvisgeom_refdet.so; see ref_entry_detector.cpp).
+    exact=True loads the -O0 twin, which runs detectPattern as written (improveCorners through initPoin)."""
+
+    def __init__(self, exact: bool = False):
+        build_ref()
+        path = os.path.join(_HERE, "_ref", "libvisgeom_refdet_O0.so" if exact else "libvisgeom_refdet.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path + " not built (needs /root/reference)")
+        self.exact = exact
+        self.lib = C.CDLL(path)
+        vp = C.c_void_p
+        self.lib.vgref_detect_pattern.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]
+        self.lib.vgref_detector_stages.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, vp, vp, vp, vp,
+                                                   C.c_int, vp, vp, vp]
+        self.lib.vgref_subpixel_evaluate.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_int, C.c_double, vp, vp, vp]
+        self.lib.vgref_subpixel_solve.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_int, C.c_double, vp, vp]
+        self.lib.vgref_detector_maps.argtypes = [vp, C.c_int, C.c_int, C.c_double, vp, vp, vp, vp, vp, vp]
+
+    @staticmethod
+    def _p(a):
+        return a.ctypes.data_as(C.c_void_p)
+
+    def detect_pattern(self, img, nx=9, ny=6, improve=True):
+        """detectPattern -> (found, corners (nx ny, 2), start values (nx ny, 5) or None, iterations or None)."""
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        h, w = img.shape
+        c = np.zeros((nx * ny, 2)); init = np.zeros((nx * ny, 5)); it = np.zeros(nx * ny, dtype=np.int32)
+        own = 0 if self.exact else 1
+        ok = self.lib.vgref_detect_pattern(self._p(img), w, h, nx, ny, int(bool(improve)), own, self._p(c), self._p(init), self._p(it))
+        return bool(ok), c, (init if own and improve else None), (it if own and improve else None)
+
+    def stages(self, img, sigma2, nx=9, ny=6, cap=4096):
+        """One scale of detectPattern: candidates in graph order, arcs (per candidate: neighbours, signs), pattern."""
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        h, w = img.shape
+        pts = np.zeros((cap, 2), dtype=np.int32); n_arcs = np.zeros(cap, dtype=np.int32)
+        arc_cap = 16 * cap
+        arcs = np.zeros(arc_cap, dtype=np.int32); sign = np.zeros(arc_cap, dtype=np.int32)
+        pattern = np.zeros(nx * ny + 8, dtype=np.int32); n_pat = C.c_int(0); avg = C.c_double(0)
+        n = self.lib.vgref_detector_stages(self._p(img), w, h, nx, ny, float(sigma2), cap, self._p(pts), self._p(n_arcs), self._p(arcs),
+                                           self._p(sign), arc_cap, self._p(pattern), C.addressof(n_pat), C.addressof(avg))
+        n = min(n, cap)
+        tot = int(n_arcs[:n].sum())
+        return dict(cand=pts[:n].copy(), n_arcs=n_arcs[:n].copy(), arcs=arcs[:tot].copy(), sign=sign[:tot].copy(),
+                    pattern=pattern[:n_pat.value].copy(), avg=avg.value)
+
+    def maps(self, img, sigma2):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        h, w = img.shape
+        f = [np.zeros((h, w), dtype=np.float32) for _ in range(4)]
+        s = [np.zeros((h, w), dtype=np.uint8) for _ in range(2)]
+        self.lib.vgref_detector_maps(self._p(img), w, h, float(sigma2), *[self._p(a) for a in f + s])
+        return dict(resp=f[0], gradx=f[1], grady=f[2], imgrad=f[3], s1=s[0], s2=s[1])
+
+    def subpixel_evaluate(self, gradx, grady, prior, length, params, steps=7):
+        gx = np.ascontiguousarray(gradx, dtype=np.float32); gy = np.ascontiguousarray(grady, dtype=np.float32)
+        h, w = gx.shape
+        pr = _f64(prior); x = _f64(params)
+        cost = C.c_double(0); g = np.zeros(5)
+        self.lib.vgref_subpixel_evaluate(self._p(gx), self._p(gy), w, h, self._p(pr), steps, float(length), self._p(x),
+                                         C.addressof(cost), self._p(g))
+        return cost.value, g
+
+    def subpixel_solve(self, gradx, grady, prior, length, start, steps=7):
+        gx = np.ascontiguousarray(gradx, dtype=np.float32); gy = np.ascontiguousarray(grady, dtype=np.float32)
+        h, w = gx.shape
+        pr = _f64(prior); x = _f64(start).copy()
+        cost = C.c_double(0)
+        it = self.lib.vgref_subpixel_solve(self._p(gx), self._p(gy), w, h, self._p(pr), steps, float(length), self._p(x), C.addressof(cost))
+        return x, it, cost.value

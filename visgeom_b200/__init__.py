@@ -77,6 +77,14 @@ def lib() -> C.CDLL:
                                      C.POINTER(C.c_longlong)]
     L.vg_corner_response_dev.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.vg_detect_pattern.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.vg_detector_host_stages.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                          C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p]
+    L.vg_subpixel_evaluate.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p]
+    L.vg_subpixel_refine.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]
     L.vg_refine_poses.argtypes = [C.c_int, c_dp, C.c_int, C.c_int, c_dp, c_dp, c_dp, C.c_double, C.POINTER(SolveOptions), c_ip,
                                   c_dp, c_ip]
     if hasattr(L, "vg_problem_create"):
@@ -301,6 +309,67 @@ def corner_response(imgs, sigma1=0.7, sigma2=1.4):
     if single:
         outs = [o[0] for o in outs]
     return dict(resp=outs[0], gradx=outs[1], grady=outs[2], imgrad=outs[3], avg=avg, count=cnt)
+
+
+def _vp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def detect_pattern(imgs, nx=9, ny=6, improve=True):
+    """CornerDetector(nx, ny, 3, improve).detectPattern for a batch of 8-bit images (n, H, W) or one (H, W)
+    (vg_detect_pattern).  Returns (found (n,) bool, corners (n, nx ny, 2)); rows of images without a pattern are NaN."""
+    L = lib()
+    a = np.ascontiguousarray(imgs, dtype=np.uint8)
+    single = a.ndim == 2
+    b = a[None] if single else a
+    n, h, w = b.shape
+    corners = np.full((n, nx * ny, 2), np.nan)
+    found = np.zeros(n, dtype=np.uint8)
+    _check(L.vg_detect_pattern(_vp(b), n, w, h, nx, ny, int(bool(improve)), _vp(corners), _vp(found)))
+    corners[found == 0] = np.nan
+    return (bool(found[0]), corners[0]) if single else (found.astype(bool), corners)
+
+
+def detector_host_stages(img, s1, s2, max_val, max_uv, init_radius, nx=9, ny=6, cap=4096):
+    """The detector's host stages of one scale (vg_detector_host_stages; no GPU needed)."""
+    L = lib()
+    img = np.ascontiguousarray(img, dtype=np.uint8); s1 = np.ascontiguousarray(s1, dtype=np.uint8)
+    s2 = np.ascontiguousarray(s2, dtype=np.uint8)
+    h, w = img.shape
+    mv = np.ascontiguousarray(max_val, dtype=np.float32); muv = np.ascontiguousarray(max_uv, dtype=np.int32).reshape(-1, 2)
+    cand = np.zeros((cap, 2), dtype=np.int32); n_cand = C.c_int(0)
+    grid = np.zeros((nx * ny, 2), dtype=np.int32); start = np.zeros((nx * ny, 5)); reach = np.zeros(nx * ny)
+    rc = L.vg_detector_host_stages(_vp(img), _vp(s1), _vp(s2), w, h, _vp(mv), _vp(muv), len(mv), nx, ny, int(init_radius), _vp(cand),
+                                   cap, C.addressof(n_cand), _vp(grid), _vp(start), _vp(reach))
+    if rc < 0:
+        _check(rc)
+    return dict(found=rc == 1, cand=cand[:min(cap, n_cand.value)].copy(), grid=grid, start=start, reach=reach)
+
+
+def subpixel_evaluate(gradx, grady, prior, length, params):
+    """SubpixelCorner::Evaluate for n parameter vectors (vg_subpixel_evaluate) -> (cost (n,), gradient (n, 5))."""
+    L = lib()
+    gx = np.ascontiguousarray(gradx, dtype=np.float32); gy = np.ascontiguousarray(grady, dtype=np.float32)
+    h, w = gx.shape
+    x = np.ascontiguousarray(params, dtype=np.float64).reshape(-1, 5); n = x.shape[0]
+    pr = np.ascontiguousarray(np.broadcast_to(np.asarray(prior, dtype=np.float64).reshape(-1, 2), (n, 2)))
+    ln = np.ascontiguousarray(np.broadcast_to(np.asarray(length, dtype=np.float64).reshape(-1), (n,)))
+    cost = np.zeros(n); g = np.zeros((n, 5))
+    _check(L.vg_subpixel_evaluate(_vp(gx), _vp(gy), w, h, n, _vp(pr), _vp(ln), _vp(x), _vp(cost), _vp(g)))
+    return cost, g
+
+
+def subpixel_refine(gradx, grady, prior, length, start):
+    """improveCorners' minimisation for n corners (vg_subpixel_refine) -> (refined (n, 2), iterations (n,))."""
+    L = lib()
+    gx = np.ascontiguousarray(gradx, dtype=np.float32); gy = np.ascontiguousarray(grady, dtype=np.float32)
+    h, w = gx.shape
+    x = np.ascontiguousarray(start, dtype=np.float64).reshape(-1, 5); n = x.shape[0]
+    pr = np.ascontiguousarray(np.asarray(prior, dtype=np.float64).reshape(n, 2))
+    ln = np.ascontiguousarray(np.asarray(length, dtype=np.float64).reshape(n))
+    out = np.zeros((n, 2)); it = np.zeros(n, dtype=np.int32)
+    _check(L.vg_subpixel_refine(_vp(gx), _vp(gy), w, h, n, _vp(pr), _vp(ln), _vp(x), _vp(out), _vp(it)))
+    return out, it
 
 
 class Problem:

@@ -18,10 +18,10 @@ LIB = os.path.join(HERE, "libvisgeom_b200%s.so" % ("_" + VARIANT if VARIANT else
 OBJ = os.path.join(HERE, "_obj" + ("_" + VARIANT if VARIANT else ""))
 
 SOURCES = ["vg_eval_eucm.cu", "vg_eval_ucm.cu", "vg_eval_mei.cu", "vg_eval.cu", "vg_api.cu", "vg_solver_kernels.cu",
-           "vg_problem.cu", "vg_priors.cu", "vg_solver_fast.cu", "vg_project.cu", "vg_host.cu", "vg_corner.cu", "vg_refine.cu"]
+           "vg_problem.cu", "vg_priors.cu", "vg_solver_fast.cu", "vg_project.cu", "vg_host.cu", "vg_corner.cu", "vg_refine.cu", "vg_detector.cu"]
 # every header of csrc/ is a dependency of every object (a stale object with a mismatched cross-rank protocol or
 # argument struct would load silently)
-HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + ["../../include/visgeom_b200.h"]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".hpp"))) + ["../../include/visgeom_b200.h"]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -29,6 +29,8 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
 if VARIANT.startswith("phase"):
     FLAGS.append("-DVG_PHASE_CLOCKS")
 FLAGS += os.environ.get("VG_EXTRA_FLAGS", "").split()
+# the detector's refinement rounds operation by operation like the reference's host code (see vg_detector.cu)
+FILE_FLAGS = {"vg_detector.cu": ["-fmad=false"]}
 
 
 def _stale(target: str, deps: list[str]) -> bool:
@@ -49,7 +51,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(OBJ, s.replace(".cu", ".o"))
         objs.append(obj)
         if force or _stale(obj, [src] + hdrs):
-            cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            cmd = [NVCC] + FLAGS + FILE_FLAGS.get(s, []) + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
             procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for cmd, p in procs:
         out, _ = p.communicate()

@@ -9,6 +9,7 @@
 // round-to-nearest intrinsics (no FMA contraction), so every float written equals the CPU restatement's bit for bit;
 // only the mean is summed in a different (fixed) order.  Batched over images (grid.z).  No CPU path.
 #include "vg_common.h"
+#include "vg_detector.cuh"
 
 #include <cmath>
 #include <cstdint>
@@ -37,8 +38,8 @@ template <int R2>
 __global__ void __launch_bounds__(32 * WARPS)
 corner_response_kernel(const unsigned char *__restrict__ img, const int W, const int H, const Taps t1, const Taps t2,
                        float *__restrict__ resp, float *__restrict__ gradx, float *__restrict__ grady,
-                       float *__restrict__ imgrad, double *__restrict__ part_acc, unsigned int *__restrict__ part_cnt,
-                       const int warps_x, const int strips_y)
+                       float *__restrict__ imgrad, unsigned char *__restrict__ s1out, unsigned char *__restrict__ s2out,
+                       double *__restrict__ part_acc, unsigned int *__restrict__ part_cnt, const int warps_x, const int strips_y)
 {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long long wid = (long long)blockIdx.x * WARPS + wib;          // warp index inside the image
@@ -112,14 +113,15 @@ corner_response_kernel(const unsigned char *__restrict__ img, const int W, const
             f_gy = __double2float_rn(__dmul_rn(gys, 0.01));
             f_mag = __double2float_rn(__dmul_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(gxs, gxs), __dmul_rn(gys, gys))), 0.01));
             // saddle response of the wider blur (:297-309).  -Iuu Ivv + Iuv^2 is a multiple of 1/16 below 2^21 and
-            // |grad|^4 = (n / 4)^2 with n < 2^18: both exact in integers, hence exact as doubles; what is rounded is
+            // |grad|^4 = n^2 with n < 2^15: both exact in integers, hence exact as doubles; what is rounded is
             // 0.001 * q and the final subtraction, as in the reference
             const int iuu = s2l[1] + s2r[1] - 2 * s2c[1], ivv = s2c[0] + s2c[2] - 2 * s2c[1];
             const int iuv4 = s2l[0] + s2r[2] - s2l[2] - s2r[0];
-            const int gx2 = s2r[1] - s2l[1], gy2 = s2c[2] - s2c[0];
+            // the reference divides the pixel differences by the int 2 (:304-305): integer division, towards zero
+            const int gx2 = (s2r[1] - s2l[1]) / 2, gy2 = (s2c[2] - s2c[0]) / 2;
             const long long n = (long long)gx2 * gx2 + (long long)gy2 * gy2;
             const double sdet = (double)(iuv4 * iuv4 - 16 * iuu * ivv) * 0.0625;
-            const double q = (double)(n * n) * 0.0625;
+            const double q = (double)(n * n);
             const double val = __dsub_rn(sdet, __dmul_rn(0.001, q));
             if (val > 0.01) {
                 f_resp = __double2float_rn(val);
@@ -127,7 +129,10 @@ corner_response_kernel(const unsigned char *__restrict__ img, const int W, const
                 cnt++;
             }
         }
-        resp[idx] = f_resp; gradx[idx] = f_gx; grady[idx] = f_gy; imgrad[idx] = f_mag;
+        resp[idx] = f_resp; gradx[idx] = f_gx; grady[idx] = f_gy;
+        if (imgrad) imgrad[idx] = f_mag;
+        // the detector's host stages work from the two blurred images (vg_detector.cu); defined on the border too
+        if (s1out) { s1out[idx] = (unsigned char)s1c[1]; s2out[idx] = (unsigned char)s2c[1]; }
     }
     // the strip's sum and count in a fixed order
     for (int off = 16; off > 0; off >>= 1) {
@@ -190,14 +195,15 @@ bool gaussian_taps(int n, double sigma, Taps *t)
 
 using namespace vg;
 
-extern "C" {
-
-int vg_corner_response_dev(const unsigned char *img, int n_img, int width, int height, double sigma1, double sigma2,
-                           float *resp, float *gradx, float *grady, float *imgrad, double *avg, long long *count, void *stream)
+// computeResponse for the detector pipeline (vg_detector.cu): imgrad may be NULL (not written), s1 / s2 receive the
+// two blurred 8-bit images when given
+int vg::corner_response_launch(const unsigned char *img, int n_img, int width, int height, double sigma1, double sigma2,
+                               float *resp, float *gradx, float *grady, float *imgrad, unsigned char *s1, unsigned char *s2,
+                               double *avg, long long *count, void *stream)
 {
     if (n_img < 0 || width < 3 || height < 3) return fail(VG_ERR_INVALID, "vg_corner_response: bad image size");
     if (n_img == 0) return VG_OK;
-    if (!img || !resp || !gradx || !grady || !imgrad) return fail(VG_ERR_INVALID, "null argument");
+    if (!img || !resp || !gradx || !grady || (!s1) != (!s2)) return fail(VG_ERR_INVALID, "null argument");
     Taps t1, t2;
     // FILTER_SIZE_1 = 3, FILTER_SIZE_2 = 1 + 2 ceil(SIGMA_2)  (corner_detector.cpp:265,269)
     if (!gaussian_taps(3, sigma1, &t1) || !gaussian_taps(1 + 2 * (int)std::ceil(sigma2), sigma2, &t2))
@@ -219,7 +225,7 @@ int vg_corner_response_dev(const unsigned char *img, int n_img, int width, int h
     double *part_acc = reinterpret_cast<double *>(scratch.p);
     unsigned int *part_cnt = reinterpret_cast<unsigned int *>(scratch.p + n_part * sizeof(double));
 #define VG_CORNER_LAUNCH(R) corner_response_kernel<R><<<grid, 32 * WARPS, 0, st>>>(img, width, height, t1, t2, resp, gradx, grady, imgrad, \
-                                                                                   part_acc, part_cnt, warps_x, strips_y)
+                                                                                   s1, s2, part_acc, part_cnt, warps_x, strips_y)
     switch (t2.r) {
     case 1: VG_CORNER_LAUNCH(1); break;
     case 2: VG_CORNER_LAUNCH(2); break;
@@ -235,6 +241,16 @@ int vg_corner_response_dev(const unsigned char *img, int n_img, int width, int h
         e = cudaGetLastError();
     }
     return e == cudaSuccess ? VG_OK : fail_cuda(e, "corner_response_kernel launch");
+}
+
+extern "C" {
+
+int vg_corner_response_dev(const unsigned char *img, int n_img, int width, int height, double sigma1, double sigma2,
+                           float *resp, float *gradx, float *grady, float *imgrad, double *avg, long long *count, void *stream)
+{
+    if (n_img > 0 && !imgrad) return fail(VG_ERR_INVALID, "null argument");
+    return corner_response_launch(img, n_img, width, height, sigma1, sigma2, resp, gradx, grady, imgrad, nullptr, nullptr, avg,
+                                  count, stream);
 }
 
 int vg_corner_response(const unsigned char *img, int n_img, int width, int height, double sigma1, double sigma2,
