@@ -51,3 +51,23 @@ def assert_close_hessian(got, want, name, rtol=RTOL):
     worst = float(rel.max()) if rel.size else 0.0
     assert worst <= rtol, f"{name}: max scaled err {worst:.3e} > {rtol:.1e}"
     return worst
+
+
+def local_maxima_np(resp, avg, R):
+    """numpy statement of selectCandidates' scan (corner_detector.cpp:494-534) -> (values (n,), uv (n, 2)) in scan order."""
+    h, w = resp.shape
+    if h <= 2 * R or w <= 2 * R:
+        return np.zeros(0, np.float32), np.zeros((0, 2), np.int32)
+    c = resp[R:h - R, R:w - R]
+    ok = np.ones(c.shape, bool)
+    if np.isfinite(avg):
+        ok &= ~(c.astype(np.float64) < avg)
+    for j in range(-R, R + 1):
+        for i in range(-R, R + 1):
+            if (i == 0 and j == 0) or i * i + j * j > R * R + 1:
+                continue
+            nb = resp[R + j:h - R + j, R + i:w - R + i]
+            later = i > 0 or (i == 0 and j > 0)
+            ok &= ~((c < nb) | ((c == nb) & (not later)))
+    vs, us = np.nonzero(ok)
+    return c[vs, us].astype(np.float32), np.stack([us + R, vs + R], 1).astype(np.int32)

@@ -195,11 +195,17 @@ bool gaussian_taps(int n, double sigma, Taps *t)
 
 using namespace vg;
 
+size_t vg::corner_response_work_bytes(int n_img, int width, int height)
+{
+    const size_t tiles = (size_t)((width + COLS - 1) / COLS) * ((height + STRIP - 1) / STRIP);
+    return tiles * n_img * (sizeof(double) + sizeof(unsigned int));
+}
+
 // computeResponse for the detector pipeline (vg_detector.cu): imgrad may be NULL (not written), s1 / s2 receive the
 // two blurred 8-bit images when given
 int vg::corner_response_launch(const unsigned char *img, int n_img, int width, int height, double sigma1, double sigma2,
                                float *resp, float *gradx, float *grady, float *imgrad, unsigned char *s1, unsigned char *s2,
-                               double *avg, long long *count, void *stream)
+                               double *avg, long long *count, void *stream, void *work, size_t work_bytes)
 {
     if (n_img < 0 || width < 3 || height < 3) return fail(VG_ERR_INVALID, "vg_corner_response: bad image size");
     if (n_img == 0) return VG_OK;
@@ -212,18 +218,24 @@ int vg::corner_response_launch(const unsigned char *img, int n_img, int width, i
     const int warps_x = (width + COLS - 1) / COLS, strips_y = (height + STRIP - 1) / STRIP;
     const int tiles = warps_x * strips_y;
     const dim3 grid((tiles + WARPS - 1) / WARPS, n_img);
-    // per-strip partial sums: a grow-only scratch of the calling thread (work queued on one stream at a time per thread)
+    // per-strip partial sums: the caller's work area, else a grow-only scratch of the calling thread (work queued on one
+    // stream at a time per thread)
     static thread_local struct { int dev = -1; char *p = nullptr; size_t bytes = 0; } scratch;
-    int dev = 0;
-    VG_CUDA(cudaGetDevice(&dev));
     const size_t n_part = (size_t)tiles * n_img, need = n_part * (sizeof(double) + sizeof(unsigned int));
-    if (scratch.dev != dev || scratch.bytes < need) {
-        if (scratch.p) { cudaDeviceSynchronize(); cudaFree(scratch.p); scratch.p = nullptr; scratch.bytes = 0; }
-        VG_CUDA(cudaMalloc(&scratch.p, need));
-        scratch.bytes = need; scratch.dev = dev;
+    char *area = static_cast<char *>(work);
+    if (area && work_bytes < need) return fail(VG_ERR_INVALID, "vg_corner_response: work area too small");
+    if (!area) {
+        int dev = 0;
+        VG_CUDA(cudaGetDevice(&dev));
+        if (scratch.dev != dev || scratch.bytes < need) {
+            if (scratch.p) { cudaDeviceSynchronize(); cudaFree(scratch.p); scratch.p = nullptr; scratch.bytes = 0; }
+            VG_CUDA(cudaMalloc(&scratch.p, need));
+            scratch.bytes = need; scratch.dev = dev;
+        }
+        area = scratch.p;
     }
-    double *part_acc = reinterpret_cast<double *>(scratch.p);
-    unsigned int *part_cnt = reinterpret_cast<unsigned int *>(scratch.p + n_part * sizeof(double));
+    double *part_acc = reinterpret_cast<double *>(area);
+    unsigned int *part_cnt = reinterpret_cast<unsigned int *>(area + n_part * sizeof(double));
 #define VG_CORNER_LAUNCH(R) corner_response_kernel<R><<<grid, 32 * WARPS, 0, st>>>(img, width, height, t1, t2, resp, gradx, grady, imgrad, \
                                                                                    s1, s2, part_acc, part_cnt, warps_x, strips_y)
     switch (t2.r) {
@@ -250,7 +262,7 @@ int vg_corner_response_dev(const unsigned char *img, int n_img, int width, int h
 {
     if (n_img > 0 && !imgrad) return fail(VG_ERR_INVALID, "null argument");
     return corner_response_launch(img, n_img, width, height, sigma1, sigma2, resp, gradx, grady, imgrad, nullptr, nullptr, avg,
-                                  count, stream);
+                                  count, stream, nullptr, 0);
 }
 
 int vg_corner_response(const unsigned char *img, int n_img, int width, int height, double sigma1, double sigma2,

@@ -16,6 +16,8 @@
 #include "vg_detector_host.hpp"
 
 #include <atomic>
+#include <mutex>
+#include <string>
 #include <thread>
 
 namespace vg {
@@ -317,33 +319,191 @@ subpixel_evaluate_kernel(const float *__restrict__ gradx, const float *__restric
 }
 
 // ---- pipeline ---------------------------------------------------------------------------------------------------------
-struct DeviceBuffers {
+// Images go through in passes of a few images.  A pass = upload, response + scan on the GPU, the blurred images and the
+// maxima back, the host stages (one image per thread), the refinement of the grids found (while that pass's gradient
+// maps are still on the device), results out.  LANES passes are in flight at once, each on its own stream and buffers
+// and driven by its own host thread, so the copies and kernels of one pass run under the host stages of the others.
+// Buffers are kept between calls (grow only).
+constexpr int LANES = 3;
+
+struct Lane {
     unsigned char *img = nullptr, *s1 = nullptr, *s2 = nullptr;
     float *resp = nullptr, *gradx = nullptr, *grady = nullptr;
     double *avg = nullptr, *refined = nullptr;
     unsigned int *count = nullptr;
     det::Maximum *maxima = nullptr;
     RefineJob *jobs = nullptr;
-    unsigned char *h_s1 = nullptr, *h_s2 = nullptr;     // pinned
-    det::Maximum *h_maxima = nullptr;                   // pinned
-    ~DeviceBuffers()
+    void *work = nullptr;                // the response kernel's partial sums
+    size_t work_bytes = 0;
+    unsigned char *h_img = nullptr, *h_s1 = nullptr, *h_s2 = nullptr;     // pinned
+    det::Maximum *h_maxima = nullptr;                                     // pinned
+    unsigned int *h_count = nullptr;                                      // pinned
+    RefineJob *h_jobs = nullptr;                                          // pinned
+    double *h_refined = nullptr;                                          // pinned
+    cudaStream_t st = nullptr;
+    size_t pixels = 0, corners = 0;      // capacity: pixels of a pass, corners of a pass
+    int images = 0, cap = 0, dev = -1;   // images of a pass, maxima kept per image
+
+    void release()
     {
         cudaFree(img); cudaFree(s1); cudaFree(s2); cudaFree(resp); cudaFree(gradx); cudaFree(grady); cudaFree(avg);
-        cudaFree(refined); cudaFree(count); cudaFree(maxima); cudaFree(jobs);
-        cudaFreeHost(h_s1); cudaFreeHost(h_s2); cudaFreeHost(h_maxima);
+        cudaFree(refined); cudaFree(count); cudaFree(maxima); cudaFree(jobs); cudaFree(work);
+        work = nullptr; work_bytes = 0;
+        cudaFreeHost(h_img); cudaFreeHost(h_s1); cudaFreeHost(h_s2); cudaFreeHost(h_maxima); cudaFreeHost(h_count);
+        cudaFreeHost(h_jobs); cudaFreeHost(h_refined);
+        img = s1 = s2 = h_img = h_s1 = h_s2 = nullptr; resp = gradx = grady = nullptr; avg = refined = h_refined = nullptr;
+        count = h_count = nullptr; maxima = h_maxima = nullptr; jobs = h_jobs = nullptr;
+        pixels = corners = 0; images = cap = 0;
+    }
+    cudaError_t reserve_maxima(const int images_, const int cap_)
+    {
+        cudaFree(maxima); cudaFreeHost(h_maxima);
+        maxima = h_maxima = nullptr;
+        cudaError_t e = cudaMalloc(&maxima, sizeof(det::Maximum) * (size_t)cap_ * images_);
+        if (e == cudaSuccess) e = cudaMallocHost(&h_maxima, sizeof(det::Maximum) * (size_t)cap_ * images_);
+        cap = cap_;
+        return e;
+    }
+    cudaError_t reserve(const int device, const int W, const int H, const int images_, const int P, const int cap_)
+    {
+        const size_t N = (size_t)W * H, wb = corner_response_work_bytes(images_, W, H);
+        if (dev == device && pixels >= N * images_ && images >= images_ && corners >= (size_t)P * images_ && cap >= cap_ && st &&
+            work_bytes >= wb)
+            return cudaSuccess;
+        if (st) cudaStreamSynchronize(st);
+        release();
+        dev = device;
+        cudaError_t e = st ? cudaSuccess : cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+        const size_t px = N * images_, nc = (size_t)P * images_;
+        if (e == cudaSuccess) e = cudaMalloc(&img, px);
+        if (e == cudaSuccess) e = cudaMalloc(&s1, px);
+        if (e == cudaSuccess) e = cudaMalloc(&s2, px);
+        if (e == cudaSuccess) e = cudaMalloc(&resp, px * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&gradx, px * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&grady, px * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&avg, sizeof(double) * images_);
+        if (e == cudaSuccess) e = cudaMalloc(&count, sizeof(unsigned int) * images_);
+        if (e == cudaSuccess) e = cudaMalloc(&jobs, sizeof(RefineJob) * nc);
+        if (e == cudaSuccess) e = cudaMalloc(&refined, sizeof(double) * 2 * nc);
+        if (e == cudaSuccess) e = cudaMalloc(&work, wb);
+        if (e == cudaSuccess) work_bytes = wb;
+        if (e == cudaSuccess) e = cudaMallocHost(&h_img, px);
+        if (e == cudaSuccess) e = cudaMallocHost(&h_s1, px);
+        if (e == cudaSuccess) e = cudaMallocHost(&h_s2, px);
+        if (e == cudaSuccess) e = cudaMallocHost(&h_count, sizeof(unsigned int) * images_);
+        if (e == cudaSuccess) e = cudaMallocHost(&h_jobs, sizeof(RefineJob) * nc);
+        if (e == cudaSuccess) e = cudaMallocHost(&h_refined, sizeof(double) * 2 * nc);
+        if (e == cudaSuccess) e = reserve_maxima(images_, cap_);
+        if (e == cudaSuccess) { pixels = px; corners = nc; images = images_; }
+        return e;
     }
 };
 
-template <typename Fn> void parallel_for(const int n, Fn fn)
+struct Pipeline {
+    std::mutex mu;                      // one vg_detect_pattern at a time per process
+    Lane lane[LANES];
+};
+Pipeline &pipeline() { static Pipeline p; return p; }
+
+template <typename Fn> void parallel_for(const int n, const int threads, Fn fn)
 {
-    const int hw = (int)std::thread::hardware_concurrency();
-    const int nt = std::max(1, std::min(n, hw > 0 ? hw : 4));
+    const int nt = std::max(1, std::min(n, threads));
     if (nt == 1) { for (int i = 0; i < n; i++) fn(i); return; }
     std::atomic<int> next(0);
     std::vector<std::thread> pool;
     for (int t = 0; t < nt; t++)
         pool.emplace_back([&] { for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) fn(i); });
     for (auto &th : pool) th.join();
+}
+
+struct Request {
+    const unsigned char *img;
+    int width, height, Nx, Ny, improve;
+    double *corners;
+    unsigned char *found;
+    int host_threads;
+};
+
+#define DET_CUDA(call)                                                                                      \
+    do {                                                                                                    \
+        cudaError_t e__ = (call);                                                                           \
+        if (e__ != cudaSuccess) return std::string("CUDA error in " #call ": ") + cudaGetErrorString(e__);  \
+    } while (0)
+
+// one pass: the images `ids` (indices into the request) at one scale; the ones without a pattern are appended to `still`
+std::string run_pass(Lane &B, const Request &q, const int *ids, const int np, const double sigma2, std::vector<int> &still)
+{
+    const int W = q.width, H = q.height, P = q.Nx * q.Ny;
+    const size_t N = (size_t)W * H;
+    const int R = (int)std::round(1.5 * sigma2);                    // INIT_RADIUS (:231)
+    cudaStream_t st = B.st;
+    // staged through pinned memory: the caller's pageable pages would serialise the lanes inside the driver
+    for (int i = 0; i < np; i++) std::memcpy(B.h_img + (size_t)i * N, q.img + (size_t)ids[i] * N, N);
+    DET_CUDA(cudaMemcpyAsync(B.img, B.h_img, N * np, cudaMemcpyHostToDevice, st));
+    if (corner_response_launch(B.img, np, W, H, 0.7, sigma2, B.resp, B.gradx, B.grady, nullptr, B.s1, B.s2, B.avg, nullptr, st,
+                               B.work, B.work_bytes))
+        return vg_last_error();
+    DET_CUDA(cudaMemcpyAsync(B.h_s1, B.s1, N * np, cudaMemcpyDeviceToHost, st));
+    DET_CUDA(cudaMemcpyAsync(B.h_s2, B.s2, N * np, cudaMemcpyDeviceToHost, st));
+    for (;;) {
+        DET_CUDA(cudaMemsetAsync(B.count, 0, sizeof(unsigned int) * np, st));
+        const dim3 grid((W + 31) / 32, (H + 7) / 8, np);
+        local_maxima_kernel<<<grid, 256, 0, st>>>(B.resp, B.avg, W, H, R, B.maxima, B.count, B.cap);
+        count_launch(&launch_counter());
+        DET_CUDA(cudaGetLastError());
+        DET_CUDA(cudaMemcpyAsync(B.h_count, B.count, sizeof(unsigned int) * np, cudaMemcpyDeviceToHost, st));
+        DET_CUDA(cudaStreamSynchronize(st));
+        const unsigned int most = *std::max_element(B.h_count, B.h_count + np);
+        if (most <= (unsigned)B.cap) break;
+        DET_CUDA(B.reserve_maxima(B.images, (int)most));           // a noisy image: room for the longest list, again
+    }
+    for (int i = 0; i < np; i++)
+        if (B.h_count[i])
+            DET_CUDA(cudaMemcpyAsync(B.h_maxima + (size_t)i * B.cap, B.maxima + (size_t)i * B.cap,
+                                     sizeof(det::Maximum) * B.h_count[i], cudaMemcpyDeviceToHost, st));
+    DET_CUDA(cudaStreamSynchronize(st));
+    // host stages, one image per thread
+    std::vector<std::vector<det::Pt>> grids(np);
+    std::vector<unsigned char> job_ok((size_t)np * P, 0);
+    std::vector<RefineJob> jobs((size_t)np * P);
+    parallel_for(np, q.host_threads, [&](const int i) {
+        const det::Frame F{B.h_img + (size_t)i * N, B.h_s1 + (size_t)i * N, B.h_s2 + (size_t)i * N, W, H};
+        std::vector<det::Maximum> mx(B.h_maxima + (size_t)i * B.cap, B.h_maxima + (size_t)i * B.cap + B.h_count[i]);
+        grids[i] = det::detect_at_scale(F, mx, q.Nx, q.Ny, R);
+        if ((int)grids[i].size() != P || !q.improve) return;
+        std::vector<double> reach(P);
+        det::refinement_reach(grids[i], q.Nx, reach.data());
+        for (int k = 0; k < P; k++) {
+            RefineJob &J = jobs[(size_t)i * P + k];
+            J.prior[0] = grids[i][k].u; J.prior[1] = grids[i][k].v;
+            J.reach = reach[k];
+            J.img = i; J.pad = 0;
+            job_ok[(size_t)i * P + k] = det::init_point(F, grids[i][k], R, J.x) ? 1 : 0;
+        }
+    });
+    // results; refinement of the grids found, while this pass's gradient maps are on the device
+    std::vector<size_t> where;                                      // slot in q.corners of each packed job
+    int nj = 0;
+    for (int i = 0; i < np; i++) {
+        if ((int)grids[i].size() != P) { still.push_back(ids[i]); continue; }
+        q.found[ids[i]] = 1;
+        for (int k = 0; k < P; k++) {
+            const size_t slot = ((size_t)ids[i] * P + k) * 2;
+            q.corners[slot] = grids[i][k].u; q.corners[slot + 1] = grids[i][k].v;
+            if (q.improve && job_ok[(size_t)i * P + k]) { B.h_jobs[nj++] = jobs[(size_t)i * P + k]; where.push_back(slot); }
+        }
+    }
+    if (nj) {
+        DET_CUDA(cudaMemcpyAsync(B.jobs, B.h_jobs, sizeof(RefineJob) * nj, cudaMemcpyHostToDevice, st));
+        subpixel_refine_kernel<<<(nj + REFINE_WARPS - 1) / REFINE_WARPS, 32 * REFINE_WARPS, 0, st>>>(B.gradx, B.grady, W, H, B.jobs, nj,
+                                                                                                     B.refined, nullptr);
+        count_launch(&launch_counter());
+        DET_CUDA(cudaGetLastError());
+        DET_CUDA(cudaMemcpyAsync(B.h_refined, B.refined, sizeof(double) * 2 * nj, cudaMemcpyDeviceToHost, st));
+        DET_CUDA(cudaStreamSynchronize(st));
+        for (int j = 0; j < nj; j++) { q.corners[where[j]] = B.h_refined[2 * j]; q.corners[where[j] + 1] = B.h_refined[2 * j + 1]; }
+    }
+    return std::string();
 }
 
 }  // namespace
@@ -366,111 +526,50 @@ int vg_detect_pattern(const unsigned char *img, int n_img, int width, int height
     if (!img || !corners || !found) return fail(VG_ERR_INVALID, "null argument");
     const size_t N = (size_t)width * height;
     const int P = Nx * Ny;
-    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_img, ((size_t)768 << 20) / (15 * N)));
-    int cap = (int)std::min<size_t>(N / 4 + 16, 1u << 16);          // maxima kept per image; grown on overflow
-    DeviceBuffers B;
-    cudaStream_t st = nullptr;
-    VG_CUDA(cudaMalloc(&B.img, N * chunk));
-    VG_CUDA(cudaMalloc(&B.s1, N * chunk));
-    VG_CUDA(cudaMalloc(&B.s2, N * chunk));
-    VG_CUDA(cudaMalloc(&B.resp, N * chunk * sizeof(float)));
-    VG_CUDA(cudaMalloc(&B.gradx, N * chunk * sizeof(float)));
-    VG_CUDA(cudaMalloc(&B.grady, N * chunk * sizeof(float)));
-    VG_CUDA(cudaMalloc(&B.avg, sizeof(double) * chunk));
-    VG_CUDA(cudaMalloc(&B.count, sizeof(unsigned int) * chunk));
-    VG_CUDA(cudaMalloc(&B.maxima, sizeof(det::Maximum) * (size_t)cap * chunk));
-    VG_CUDA(cudaMalloc(&B.jobs, sizeof(RefineJob) * (size_t)P * chunk));
-    VG_CUDA(cudaMalloc(&B.refined, sizeof(double) * 2 * (size_t)P * chunk));
-    VG_CUDA(cudaMallocHost(&B.h_s1, N * chunk));
-    VG_CUDA(cudaMallocHost(&B.h_s2, N * chunk));
-    VG_CUDA(cudaMallocHost(&B.h_maxima, sizeof(det::Maximum) * (size_t)cap * chunk));
+    // images per pass: about 8 MB of pixels (8 images of 1280 x 800); VG_DETECT_CHUNK overrides (developer knob, tests)
+    size_t per_pass = std::max<size_t>(1, ((size_t)8 << 20) / N);
+    if (const char *e = std::getenv("VG_DETECT_CHUNK")) per_pass = (size_t)std::max(1, std::atoi(e));
+    const int chunk = (int)std::min<size_t>((size_t)n_img, per_pass);
+    const int cap = (int)std::min<size_t>(N / 4 + 16, 1u << 15);    // maxima kept per image; grown on overflow
+    const int hw = std::max(1, (int)std::thread::hardware_concurrency());
+    int dev = 0;
+    VG_CUDA(cudaGetDevice(&dev));
+    Pipeline &pl = pipeline();
+    std::lock_guard<std::mutex> lock(pl.mu);
+    const int lanes = std::max(1, std::min(LANES, (n_img + chunk - 1) / chunk));
+    for (int l = 0; l < lanes; l++) VG_CUDA(pl.lane[l].reserve(dev, width, height, chunk, P, cap));
+    const Request q{img, width, height, Nx, Ny, improve, corners, found, hw};
+    std::vector<int> pending(n_img);
+    for (int i = 0; i < n_img; i++) { pending[i] = i; found[i] = 0; }
     static const double SIGMA[3] = {1.4, 2, 1};                     // detectPattern's scales (:225)
-    std::vector<unsigned int> h_count(chunk);
-    std::vector<RefineJob> h_jobs;
-    std::vector<double> h_refined;
-    for (int c0 = 0; c0 < n_img; c0 += chunk) {
-        const int nc = std::min(chunk, n_img - c0);
-        std::vector<int> pending(nc);
-        for (int i = 0; i < nc; i++) { pending[i] = c0 + i; found[c0 + i] = 0; }
-        for (int scale = 0; scale < 3 && !pending.empty(); scale++) {
-            const int np = (int)pending.size();
-            const int R = (int)std::round(1.5 * SIGMA[scale]);      // INIT_RADIUS (:231)
-            if (scale == 0) VG_CUDA(cudaMemcpyAsync(B.img, img + (size_t)c0 * N, N * nc, cudaMemcpyHostToDevice, st));
-            else
-                for (int i = 0; i < np; i++)
-                    VG_CUDA(cudaMemcpyAsync(B.img + (size_t)i * N, img + (size_t)pending[i] * N, N, cudaMemcpyHostToDevice, st));
-            const int rc = corner_response_launch(B.img, np, width, height, 0.7, SIGMA[scale], B.resp, B.gradx, B.grady, nullptr,
-                                                  B.s1, B.s2, B.avg, nullptr, st);
-            if (rc) return rc;
-            for (;;) {
-                VG_CUDA(cudaMemsetAsync(B.count, 0, sizeof(unsigned int) * np, st));
-                const dim3 grid((width + 31) / 32, (height + 7) / 8, np);
-                local_maxima_kernel<<<grid, 256, 0, st>>>(B.resp, B.avg, width, height, R, B.maxima, B.count, cap);
-                count_launch(&launch_counter());
-                VG_CUDA(cudaGetLastError());
-                VG_CUDA(cudaMemcpyAsync(h_count.data(), B.count, sizeof(unsigned int) * np, cudaMemcpyDeviceToHost, st));
-                VG_CUDA(cudaStreamSynchronize(st));
-                const unsigned int most = *std::max_element(h_count.begin(), h_count.begin() + np);
-                if (most <= (unsigned)cap) break;
-                cap = (int)most;                                    // a noisy image: every list gets room for the longest one
-                cudaFree(B.maxima); B.maxima = nullptr;
-                cudaFreeHost(B.h_maxima); B.h_maxima = nullptr;
-                VG_CUDA(cudaMalloc(&B.maxima, sizeof(det::Maximum) * (size_t)cap * chunk));
-                VG_CUDA(cudaMallocHost(&B.h_maxima, sizeof(det::Maximum) * (size_t)cap * chunk));
+    for (int scale = 0; scale < 3 && !pending.empty(); scale++) {
+        const int np = (int)pending.size(), passes = (np + chunk - 1) / chunk;
+        std::atomic<int> next(0);
+        std::mutex out_mu;
+        std::vector<int> still;
+        std::string error;
+        auto drive = [&](const int l) {
+            cudaSetDevice(dev);
+            for (int b = next.fetch_add(1); b < passes; b = next.fetch_add(1)) {
+                std::vector<int> mine;
+                const std::string err = run_pass(pl.lane[l], q, pending.data() + (size_t)b * chunk, std::min(chunk, np - b * chunk),
+                                                 SIGMA[scale], mine);
+                std::lock_guard<std::mutex> g(out_mu);
+                if (!err.empty() && error.empty()) error = err;
+                still.insert(still.end(), mine.begin(), mine.end());
+                if (!err.empty()) return;
             }
-            VG_CUDA(cudaMemcpyAsync(B.h_s1, B.s1, N * np, cudaMemcpyDeviceToHost, st));
-            VG_CUDA(cudaMemcpyAsync(B.h_s2, B.s2, N * np, cudaMemcpyDeviceToHost, st));
-            for (int i = 0; i < np; i++)
-                if (h_count[i])
-                    VG_CUDA(cudaMemcpyAsync(B.h_maxima + (size_t)i * cap, B.maxima + (size_t)i * cap,
-                                            sizeof(det::Maximum) * h_count[i], cudaMemcpyDeviceToHost, st));
-            VG_CUDA(cudaStreamSynchronize(st));
-            // host stages, one image per thread
-            std::vector<std::vector<det::Pt>> grids(np);
-            h_jobs.assign((size_t)np * P, RefineJob());
-            std::vector<unsigned char> job_ok((size_t)np * P, 0);
-            parallel_for(np, [&](const int i) {
-                const det::Frame F{img + (size_t)pending[i] * N, B.h_s1 + (size_t)i * N, B.h_s2 + (size_t)i * N, width, height};
-                std::vector<det::Maximum> mx(B.h_maxima + (size_t)i * cap, B.h_maxima + (size_t)i * cap + h_count[i]);
-                grids[i] = det::detect_at_scale(F, mx, Nx, Ny, R);
-                if ((int)grids[i].size() != P || !improve) return;
-                std::vector<double> reach(P);
-                det::refinement_reach(grids[i], Nx, reach.data());
-                for (int k = 0; k < P; k++) {
-                    RefineJob &J = h_jobs[(size_t)i * P + k];
-                    J.prior[0] = grids[i][k].u; J.prior[1] = grids[i][k].v;
-                    J.reach = reach[k];
-                    J.img = i;
-                    job_ok[(size_t)i * P + k] = det::init_point(F, grids[i][k], R, J.x) ? 1 : 0;
-                }
-            });
-            // refinement of the grids found at this scale, while this scale's gradient maps are on the device
-            std::vector<int> still;
-            std::vector<RefineJob> packed;
-            std::vector<size_t> where;                              // corner slot in `corners` of each packed job
-            for (int i = 0; i < np; i++) {
-                if ((int)grids[i].size() != P) { still.push_back(pending[i]); continue; }
-                found[pending[i]] = 1;
-                for (int k = 0; k < P; k++) {
-                    const size_t slot = ((size_t)pending[i] * P + k) * 2;
-                    corners[slot] = grids[i][k].u; corners[slot + 1] = grids[i][k].v;
-                    if (improve && job_ok[(size_t)i * P + k]) { packed.push_back(h_jobs[(size_t)i * P + k]); where.push_back(slot); }
-                }
-            }
-            if (!packed.empty()) {
-                const int nj = (int)packed.size();
-                VG_CUDA(cudaMemcpyAsync(B.jobs, packed.data(), sizeof(RefineJob) * nj, cudaMemcpyHostToDevice, st));
-                subpixel_refine_kernel<<<(nj + REFINE_WARPS - 1) / REFINE_WARPS, 32 * REFINE_WARPS, 0, st>>>(
-                    B.gradx, B.grady, width, height, B.jobs, nj, B.refined, nullptr);
-                count_launch(&launch_counter());
-                VG_CUDA(cudaGetLastError());
-                h_refined.resize((size_t)2 * nj);
-                VG_CUDA(cudaMemcpyAsync(h_refined.data(), B.refined, sizeof(double) * 2 * nj, cudaMemcpyDeviceToHost, st));
-                VG_CUDA(cudaStreamSynchronize(st));
-                for (int j = 0; j < nj; j++) { corners[where[j]] = h_refined[2 * j]; corners[where[j] + 1] = h_refined[2 * j + 1]; }
-            }
-            pending.swap(still);
+        };
+        const int nl = std::min(lanes, passes);
+        if (nl == 1) drive(0);
+        else {
+            std::vector<std::thread> drivers;
+            for (int l = 0; l < nl; l++) drivers.emplace_back(drive, l);
+            for (auto &t : drivers) t.join();
         }
+        if (!error.empty()) return fail(VG_ERR_CUDA, error);
+        std::sort(still.begin(), still.end());
+        pending.swap(still);
     }
     return VG_OK;
 }

@@ -7,5 +7,7 @@ namespace vg {
 // images s1 / s2 optional (both or neither)
 int corner_response_launch(const unsigned char *img, int n_img, int width, int height, double sigma1, double sigma2,
                            float *resp, float *gradx, float *grady, float *imgrad, unsigned char *s1, unsigned char *s2,
-                           double *avg, long long *count, void *stream);
+                           double *avg, long long *count, void *stream, void *work, size_t work_bytes);
+// device bytes the launch needs as its work area (per-strip partial sums); work = NULL uses a scratch of the calling thread
+size_t corner_response_work_bytes(int n_img, int width, int height);
 }  // namespace vg
