@@ -34,6 +34,11 @@ struct ImageData {
     std::vector<std::vector<Vector2d>> detectedCornersVec;     // per image; empty: no board extracted
     int idxUL = 0, idxUR = 0, idxBL = 0, idxBR = 0;
     int imageWidth = 0, imageHeight = 0;
+    // "images" datasets (unified_calibration.cpp:279-309): the board and where its pictures are
+    int Nx = 0, Ny = 0;
+    double sqSize = 0;
+    bool useImages = false, improveDetection = false;
+    std::vector<std::string> imageNameVec;
     bool doNotSolve = false, doNotSolveGlobal = false;
     bool showOutliers = false;      // "show_outliers": the textual part of the reference's outlier report (no image windows here)
     int getFirstExtractedIdx() const
@@ -86,6 +91,8 @@ private:
     void initTransformChainInfo(ImageData &data, const json::Value &node);
     void initGridIR(ImageData &data, const json::Value &node);
     void readCorners(ImageData &data, const json::Value &node);
+    void initGrid(ImageData &data, const json::Value &node);
+    void extractGridProjections(ImageData &data);
     void initTransforms(const ImageData &data, const std::string &initName);
     void initGlobalTransform(const ImageData &data, const std::string &name);
     Transf estimateInitialGridGuess(const ImageData &data, int gridIdx) const;

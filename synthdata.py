@@ -278,6 +278,45 @@ def make_odometry(n: int = 40, seed: int = 20246, noise_px: float = 0.1, odo_noi
 
 
 # ---- synthetic board IMAGES (input of the corner detector) -----------------------------------------
+def board_image_intrinsics(width: int, height: int, model: int = EUCM) -> np.ndarray:
+    """The intrinsics render_board_image sees the board through: the ground-truth camera scaled to the image size."""
+    sc = width / IMAGE_W
+    intr = np.array({EUCM: EUCM_GT_LEFT, UCM: UCM_GT, MEI: MEI_GT}[model], dtype=np.float64).copy()
+    intr[-4:] *= sc
+    intr[-1] = intr[-1] / sc * (height / IMAGE_H)
+    intr[-3] = intr[-3] / sc * (height / IMAGE_H)
+    return intr
+
+
+def write_pgm(path: str, img: np.ndarray) -> None:
+    with open(path, "wb") as f:
+        f.write(b"P5\n# rendered board\n%d %d\n255\n" % (img.shape[1], img.shape[0]))
+        f.write(np.ascontiguousarray(img, dtype=np.uint8).tobytes())
+
+
+def write_png(path: str, img: np.ndarray, filter_type: int = 0) -> None:
+    """8-bit grey (H, W) or RGB (H, W, 3), non-interlaced; every line with the given filter (0 none, 1 sub, 2 up)."""
+    import struct
+    import zlib
+    a = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w = a.shape[:2]
+    ch = 1 if a.ndim == 2 else a.shape[2]
+    rows = a.reshape(h, w * ch).astype(np.int16)
+    if filter_type == 1:
+        f = rows.copy(); f[:, ch:] -= rows[:, :-ch]
+    elif filter_type == 2:
+        f = rows.copy(); f[1:] -= rows[:-1]
+    else:
+        f = rows
+    raw = b"".join(bytes([filter_type]) + (f[y] & 255).astype(np.uint8).tobytes() for y in range(h))
+
+    def chunk(tag, data):
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
+    with open(path, "wb") as out:
+        out.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 0 if ch == 1 else 2, 0, 0, 0)) +
+                  chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b""))
+
+
 def render_board_image(width: int = 320, height: int = 240, seed: int = 20250, nx: int = 9, ny: int = 6,
                        model: int = EUCM, supersample: int = 3, noise: float = 2.0):
     """An 8-bit image of the (nx+1) x (ny+1)-square checkerboard whose inner corners are the calibration board,
@@ -285,11 +324,7 @@ def render_board_image(width: int = 320, height: int = 240, seed: int = 20250, n
     sub-pixel (back-projection of the pixel, intersection with the board plane), box-filtered: the edges are
     anti-aliased as a real sensor would see them.  Returns (image uint8 (H, W), true corner positions (P, 2))."""
     board = make_board(nx, ny, 0.1)
-    sc = width / IMAGE_W
-    intr = np.array({EUCM: EUCM_GT_LEFT, UCM: UCM_GT, MEI: MEI_GT}[model], dtype=np.float64).copy()
-    intr[-4:] *= sc
-    intr[-1] = intr[-1] / sc * (height / IMAGE_H)
-    intr[-3] = intr[-3] / sc * (height / IMAGE_H)
+    intr = board_image_intrinsics(width, height, model)
     u = uniform(seed, 21, 6)
     rv = (2 * u[:3] - 1) * np.array([0.35, 0.35, 0.5])
     centre = board.mean(axis=0)

@@ -55,8 +55,9 @@ def test_config_errors_match_the_reference(cli, tmp_path):
     edit(path, lambda p: p["data"][0].update(init="nope"))
     assert "does not exist, impossible to initialize" in run(cli, path).stderr                 # :433
     path, _ = mk.write_mono(str(tmp_path / "f"), 4)
-    edit(path, lambda p: p["data"][0].update(type="images"))
-    assert "checkerboard detector" in run(cli, path).stderr
+    edit(path, lambda p: p["data"][0].update(type="images"))                                   # an "images" dataset needs
+    r = run(cli, path)                                                                         # object.cols / rows / size
+    assert r.returncode == 1 and "object.cols" in r.stderr
     assert "cannot open file" in run(cli, str(tmp_path / "missing.json")).stderr
     assert run(cli).returncode == 2
     # the odometry / prior datasets (unified_calibration.cpp:742-829)
@@ -186,3 +187,29 @@ def test_show_outliers_report(cli, tmp_path):
     assert "Sample #4" in r.stdout and "standard deviation : " in r.stdout
     m = re.search(r"err : (\S+)", r.stdout)
     assert m and float(m.group(1)) > 3.0
+
+
+@pytest.mark.gpu
+def test_images_dataset_detects_and_calibrates(cli, tmp_path):
+    """Dataset type "images" (unified_calibration.cpp:279-309, 632-647, 992-1062): the front end reads the pictures
+    (PGM / PNG), runs the checkerboard detector on the GPU, and calibrates from the corners it found.  Rendered boards:
+    the calibration must come back to the intrinsics the pictures were rendered with, from a start 5 % off."""
+    n = 14
+    path, info = mk.write_images(str(tmp_path), n)
+    r = run(cli, "--precision", "17", "--out", str(tmp_path) + "/", path)
+    assert r.returncode == 0, r.stderr
+    assert "missing.png : ERROR, file not found" in r.stdout                               # :1027-1030
+    assert "img_003.png : ERROR, pattern not found" in r.stdout                            # :1034-1038
+    m = re.search(r"DETECTION RATE : (\d+) of (\d+) detected", r.stdout)
+    assert m and int(m.group(2)) == n + 1 and int(m.group(1)) >= n - 3
+    intr, _ = parse_report(r.stdout)
+    rel = np.abs(intr["camera1"] - info["intr"]) / np.abs(info["intr"])
+    assert rel[2:].max() < 0.02 and rel.max() < 0.25, rel       # focal lengths, centre to 2 %; alpha / beta are weakly observed
+    rows = np.loadtxt(str(tmp_path / "image_error_0.txt"))
+    assert rows.shape[0] == int(m.group(1)) * 54
+    assert np.sqrt((rows[:, 0:2] ** 2).mean()) < 0.25           # sub-pixel corners: residual RMS well under a pixel
+    # the corners the calibration used are the detector's: compare with the Python binding on the same pictures
+    import visgeom_b200 as vg
+    img0, _ = sd.render_board_image(640, 480, seed=20400, model=sd.EUCM, supersample=2)
+    found, c = vg.detect_pattern(img0, improve=True)
+    assert found and np.abs(rows[:54, 0:2] + rows[:54, 2:4] - c).max() < 1e-9

@@ -1,0 +1,69 @@
+"""The front end's image reader (visgeom_b200/host/image_io.hpp; the reference calls cv::imread(name, 0),
+unified_calibration.cpp:1025): binary PGM and 8-bit PNG, against the arrays the files were written from and, where cv2
+is importable, against files written by OpenCV itself (libpng picks among all five line filters)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import synthdata as sd
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def imread(tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("img") / "image_probe")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-I" + os.path.join(ROOT, "include"),
+                           "-I" + os.path.join(ROOT, "visgeom_b200", "host"), os.path.join(ROOT, "tests", "image_probe.cpp"),
+                           "-o", exe, "-lz"])
+
+    def run(path):
+        out = subprocess.run([exe, path], capture_output=True, timeout=60, check=True).stdout
+        head, _, body = out.partition(b"\n")
+        w, h = (int(x) for x in head.split())
+        return None if w == 0 else np.frombuffer(body, dtype=np.uint8).reshape(h, w)
+    return run
+
+
+def test_pgm_and_png_round_trip(imread, tmp_path):
+    img, _ = sd.render_board_image(173, 131, seed=20250)
+    sd.write_pgm(str(tmp_path / "a.pgm"), img)
+    assert np.array_equal(imread(str(tmp_path / "a.pgm")), img)
+    for f in (0, 1, 2):
+        sd.write_png(str(tmp_path / f"f{f}.png"), img, filter_type=f)
+        assert np.array_equal(imread(str(tmp_path / f"f{f}.png")), img), f
+    rgb = np.random.default_rng(3).integers(0, 256, (37, 45, 3), dtype=np.uint8)
+    sd.write_png(str(tmp_path / "rgb.png"), rgb, filter_type=1)
+    r64 = rgb.astype(np.int64)
+    grey = ((r64[..., 0] * 4899 + r64[..., 1] * 9617 + r64[..., 2] * 1868 + 8192) >> 14).astype(np.uint8)
+    assert np.array_equal(imread(str(tmp_path / "rgb.png")), grey)
+
+
+def test_files_written_by_opencv(imread, tmp_path):
+    cv2 = pytest.importorskip("cv2")
+    img, _ = sd.render_board_image(320, 240, seed=20251, model=sd.MEI)
+    noise = np.random.default_rng(5).integers(0, 256, (61, 83), dtype=np.uint8)
+    for name, a in (("board", img), ("noise", noise)):
+        for ext in ("png", "pgm"):
+            path = str(tmp_path / f"{name}.{ext}")
+            assert cv2.imwrite(path, a)
+            assert np.array_equal(imread(path), a), path
+            assert np.array_equal(cv2.imread(path, 0), a)
+    # and OpenCV reads what the test data writer wrote
+    sd.write_png(str(tmp_path / "w.png"), img, filter_type=2)
+    assert np.array_equal(cv2.imread(str(tmp_path / "w.png"), 0), img)
+
+
+def test_unreadable_files_give_an_empty_image(imread, tmp_path):
+    assert imread(str(tmp_path / "missing.png")) is None                # cv::imread returns an empty Mat
+    (tmp_path / "junk.png").write_bytes(b"not an image at all, just bytes")
+    assert imread(str(tmp_path / "junk.png")) is None
+    img, _ = sd.render_board_image(64, 48, seed=1)
+    sd.write_png(str(tmp_path / "t.png"), img)
+    data = (tmp_path / "t.png").read_bytes()
+    (tmp_path / "cut.png").write_bytes(data[: len(data) // 2])
+    assert imread(str(tmp_path / "cut.png")) is None
+    (tmp_path / "cut.pgm").write_bytes(b"P5\n64 48\n255\n" + bytes(100))
+    assert imread(str(tmp_path / "cut.pgm")) is None

@@ -46,6 +46,38 @@ def write_mono(out_dir, n_img=20, model=sd.EUCM, seed=20241, skip=()):
     return path, d
 
 
+def write_images(out_dir, n_img=10, model=sd.EUCM, seed=20400, width=640, height=480, improve=True):
+    """Dataset type "images" (unified_calibration.cpp:279-309, 632-647): rendered pictures of the 9 x 6 board (PGM and PNG
+    files alternating, one missing file, one picture without a board), the camera started off its true intrinsics."""
+    import numpy as np
+    os.makedirs(out_dir, exist_ok=True)
+    truth, names = [], []
+    for i in range(n_img):
+        img, uv = sd.render_board_image(width, height, seed=seed + i, model=model, supersample=2)
+        if i == 3:
+            img = np.full_like(img, 120)                        # no board on this one
+        name = "img_%03d.%s" % (i, "png" if i % 2 else "pgm")
+        if i % 2:
+            sd.write_png(os.path.join(out_dir, name), img, filter_type=(i // 2) % 3)
+        else:
+            sd.write_pgm(os.path.join(out_dir, name), img)
+        names.append(name); truth.append(uv)
+    names.insert(5, "missing.png")                              # a file that does not exist: reported, skipped
+    truth.insert(5, None)
+    intr = sd.board_image_intrinsics(width, height, model)
+    init = intr.copy()
+    init[-4:-2] *= 1.05; init[-2] += 6.0; init[-1] -= 5.0
+    prob = {"transformations": [{"name": "xiCamBoard", "global": False, "constant": False, "prior": False}],
+            "cameras": [{"name": "camera1", "type": sd.MODEL_NAMES[model], "constant": False, "value": [float(v) for v in init]}],
+            "data": [{"type": "images", "camera": "camera1", "transform_chain": [{"name": "xiCamBoard", "direct": True}],
+                      "init": "xiCamBoard", "parameters": ["improve_detection"] if improve else [],
+                      "object": {"type": "checkboard", "cols": 9, "rows": 6, "size": 0.1},
+                      "images": {"prefix": out_dir.rstrip("/") + "/", "names": names}}]}
+    path = os.path.join(out_dir, "problem.json")
+    json.dump(prob, open(path, "w"), indent=1)
+    return path, dict(intr=intr, intr_init=init, truth=truth, names=names)
+
+
 def write_stereo(out_dir, n_pairs=20, seed=20244, prior=True):
     """The layout of data/calib_stereo_example.json: camera1 sees the board through xiCamBoardStereo, camera2
     through xiCam12^-1 o xiCamBoardStereo; xiCam12 is global, with a prior or (prior=False) initialised from the

@@ -73,12 +73,12 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 def build_cli(force: bool = False) -> str:
     """g++ -> visgeom_b200/bin/vg_calib: the reference's `calib` tool (JSON front end, host C++) over the C ABI."""
     srcs = [os.path.join(HOST, f) for f in ("calibration.cpp", "calib_main.cpp")]
-    deps = srcs + [os.path.join(HOST, "json.hpp")] + [os.path.join(INCLUDE, "visgeom_b200", f)
-                                                      for f in ("calibration.hpp", "camera.hpp", "geometry.hpp")] + [LIB]
+    deps = srcs + [os.path.join(HOST, f) for f in ("json.hpp", "image_io.hpp")] + [
+        os.path.join(INCLUDE, "visgeom_b200", f) for f in ("calibration.hpp", "camera.hpp", "geometry.hpp", "corner_detector.hpp")] + [LIB]
     if force or _stale(CLI, deps):
         os.makedirs(os.path.dirname(CLI), exist_ok=True)
         subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-I" + INCLUDE, "-I" + HOST] + srcs +
-                              ["-o", CLI, "-L" + HERE, "-lvisgeom_b200", "-Wl,-rpath,$ORIGIN/.."])
+                              ["-o", CLI, "-L" + HERE, "-lvisgeom_b200", "-lz", "-Wl,-rpath,$ORIGIN/.."])
     return CLI
 
 

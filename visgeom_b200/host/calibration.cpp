@@ -9,7 +9,9 @@
 #include <iostream>
 #include <stdexcept>
 
+#include "image_io.hpp"
 #include "json.hpp"
+#include "visgeom_b200/corner_detector.hpp"
 
 namespace visgeom_b200 {
 
@@ -125,8 +127,9 @@ void GenericCameraCalibration::initTransformChainInfo(ImageData &data, const jso
         if (f == "do_not_solve") data.doNotSolve = true;
         else if (f == "do_not_solve_global") data.doNotSolveGlobal = true;
         else if (f == "show_outliers") data.showOutliers = true;
-        else if (f == "check_extraction" || f == "improve_detection" || f == "user_guided" ||
-                 f == "save_outlire_images" || f == "draw_improved") { /* image / GUI options: nothing to do here */ }
+        else if (f == "improve_detection") data.improveDetection = true;
+        else if (f == "check_extraction" || f == "user_guided" ||
+                 f == "save_outlire_images" || f == "draw_improved") { /* GUI options: nothing to do here */ }
         else cout << "WARNING : UNKNOWN FLAG -- " << f << endl;
     }
     cout << "Camera : " << data.cameraName << endl;
@@ -186,6 +189,72 @@ void GenericCameraCalibration::readCorners(ImageData &data, const json::Value &n
             throw runtime_error("an image has " + std::to_string(cornerVec.size()) + " points, the object " +
                                 std::to_string(data.board.size()));
     }
+}
+
+// unified_calibration.cpp:279-309
+void GenericCameraCalibration::initGrid(ImageData &data, const json::Value &node)
+{
+    data.Nx = node.getInt("object.cols");
+    data.Ny = node.getInt("object.rows");
+    data.sqSize = node.getDouble("object.size");
+    data.board.clear();
+    for (int i = 0; i < data.Ny; i++)
+        for (int j = 0; j < data.Nx; j++) data.board.emplace_back(data.sqSize * j, data.sqSize * i, 0);
+    data.idxUL = 0;
+    data.idxUR = data.Nx - 1;
+    data.idxBL = data.Nx * (data.Ny - 1);
+    data.idxBR = data.Nx * data.Ny - 1;
+    data.useImages = true;
+    const string prefix = node.getString("images.prefix");
+    data.detectedCornersVec.clear();
+    for (const json::Value &x : node.child("images.names").arr) data.imageNameVec.push_back(prefix + x.str);
+    extractGridProjections(data);
+}
+
+// unified_calibration.cpp:992-1062: the reference runs CornerDetector image by image; here the images are read first and
+// the ones of one size go through the detector together (CornerDetector::detectPatterns -> vg_detect_pattern)
+void GenericCameraCalibration::extractGridProjections(ImageData &data)
+{
+    CornerDetector detector(data.Nx, data.Ny, 3, data.improveDetection);
+    string sequenceName;
+    for (const string &name : data.transNameVec)
+        if (!transformInfoMap[name].global) { sequenceName = name; break; }
+    const bool initialized = transformInfoMap[sequenceName].initialized;
+    const vector<bool> &initVec = sequenceInitMap[sequenceName];
+    const int n = (int)data.imageNameVec.size();
+    data.detectedCornersVec.assign(n, {});
+    vector<Mat8u> frames(n);
+    vector<string> error(n);
+    for (int i = 0; i < n; i++) {
+        if (initialized && !(i < (int)initVec.size() && initVec[i])) {
+            error[i] = " : ERROR, the pattern has not been found on the corresponding image";
+            continue;
+        }
+        frames[i] = image_io::imread_grey(data.imageNameVec[i]);
+        if (frames[i].empty()) error[i] = " : ERROR, file not found";
+        else if (data.imageWidth == 0) { data.imageWidth = frames[i].cols; data.imageHeight = frames[i].rows; }
+    }
+    // batches of equal size, in file order within a batch
+    std::map<std::pair<int, int>, vector<int>> bySize;
+    for (int i = 0; i < n; i++)
+        if (!frames[i].empty()) bySize[{frames[i].cols, frames[i].rows}].push_back(i);
+    for (const auto &group : bySize) {
+        vector<const Mat8u *> batch;
+        for (int i : group.second) batch.push_back(&frames[i]);
+        const vector<vector<Vector2d>> grids = detector.detectPatterns(batch);
+        for (size_t k = 0; k < group.second.size(); k++) {
+            const int i = group.second[k];
+            if (grids[k].empty()) error[i] = " : ERROR, pattern not found";
+            else data.detectedCornersVec[i] = grids[k];
+        }
+    }
+    int countSuccess = 0;
+    for (int i = 0; i < n; i++) {
+        cout << data.imageNameVec[i] << endl;
+        if (!error[i].empty()) cout << data.imageNameVec[i] << error[i] << endl;
+        else countSuccess++;
+    }
+    cout << endl << "DETECTION RATE : " << countSuccess << " of " << n << " detected" << endl;
 }
 
 Transf GenericCameraCalibration::getTransform(const string &name, int idx) const
@@ -378,8 +447,11 @@ void GenericCameraCalibration::parseData(const json::Value &root)
         } else if (dataType == "transformation_prior") {
             parseTransformationPrior(node);
         } else if (dataType == "images") {
-            throw runtime_error("dataset type \"images\" needs the checkerboard detector (OpenCV), which is outside this "
-                                "engine: extract the corners first and pass them as an \"ir_data\" dataset");
+            dataVec.emplace_back();
+            ImageData &data = dataVec.back();
+            initTransformChainInfo(data, node);
+            initGrid(data, node);
+            initTransforms(data, node.getString("init"));
         } else {
             throw runtime_error("dataset type \"" + dataType + "\" is not supported by this engine");
         }
