@@ -24,8 +24,12 @@ KEEP = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio',
         'smsp__warps_eligible.avg.per_cycle_active']
 rows = list(csv.reader(open(sys.argv[1])))
-hdr, units, vals = rows[0], rows[1], rows[2]
-for k in KEEP:
-    if k in hdr:
-        i = hdr.index(k)
-        print(f"{k:92s} {units[i]:16s} {vals[i]}")
+hdr, units = rows[0], rows[1]
+# `--all`: every captured launch (kernel name first); default: the first one
+for vals in (rows[2:] if "--all" in sys.argv else rows[2:3]):
+    if "--all" in sys.argv:
+        print("== " + vals[hdr.index("Kernel Name")] + "  grid " + vals[hdr.index("launch__grid_size")])
+    for k in KEEP:
+        if k in hdr:
+            i = hdr.index(k)
+            print(f"{k:92s} {units[i]:16s} {vals[i]}")

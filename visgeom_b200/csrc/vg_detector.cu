@@ -16,6 +16,8 @@
 #include "vg_detector_host.hpp"
 
 #include <atomic>
+#include <chrono>
+#include <cstdio>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -424,6 +426,17 @@ struct Request {
     int host_threads;
 };
 
+// VG_DETECT_TRACE=1: seconds spent per stage, summed over the passes of all lanes (they overlap, so the sum exceeds the
+// wall time), printed at the end of each call
+struct StageClock {
+    std::atomic<long long> ns[4];
+    StageClock() { for (auto &x : ns) x = 0; }
+};
+inline long long now_ns()
+{
+    return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 #define DET_CUDA(call)                                                                                      \
     do {                                                                                                    \
         cudaError_t e__ = (call);                                                                           \
@@ -431,14 +444,18 @@ struct Request {
     } while (0)
 
 // one pass: the images `ids` (indices into the request) at one scale; the ones without a pattern are appended to `still`
-std::string run_pass(Lane &B, const Request &q, const int *ids, const int np, const double sigma2, std::vector<int> &still)
+std::string run_pass(Lane &B, const Request &q, const int *ids, const int np, const double sigma2, std::vector<int> &still,
+                     StageClock &clk)
 {
+    long long t0 = now_ns();
+    auto lap = [&](const int stage) { const long long t = now_ns(); clk.ns[stage] += t - t0; t0 = t; };
     const int W = q.width, H = q.height, P = q.Nx * q.Ny;
     const size_t N = (size_t)W * H;
     const int R = (int)std::round(1.5 * sigma2);                    // INIT_RADIUS (:231)
     cudaStream_t st = B.st;
     // staged through pinned memory: the caller's pageable pages would serialise the lanes inside the driver
     for (int i = 0; i < np; i++) std::memcpy(B.h_img + (size_t)i * N, q.img + (size_t)ids[i] * N, N);
+    lap(0);
     DET_CUDA(cudaMemcpyAsync(B.img, B.h_img, N * np, cudaMemcpyHostToDevice, st));
     if (corner_response_launch(B.img, np, W, H, 0.7, sigma2, B.resp, B.gradx, B.grady, nullptr, B.s1, B.s2, B.avg, nullptr, st,
                                B.work, B.work_bytes))
@@ -462,6 +479,7 @@ std::string run_pass(Lane &B, const Request &q, const int *ids, const int np, co
             DET_CUDA(cudaMemcpyAsync(B.h_maxima + (size_t)i * B.cap, B.maxima + (size_t)i * B.cap,
                                      sizeof(det::Maximum) * B.h_count[i], cudaMemcpyDeviceToHost, st));
     DET_CUDA(cudaStreamSynchronize(st));
+    lap(1);
     // host stages, one image per thread
     std::vector<std::vector<det::Pt>> grids(np);
     std::vector<unsigned char> job_ok((size_t)np * P, 0);
@@ -481,6 +499,7 @@ std::string run_pass(Lane &B, const Request &q, const int *ids, const int np, co
             job_ok[(size_t)i * P + k] = det::init_point(F, grids[i][k], R, J.x) ? 1 : 0;
         }
     });
+    lap(2);
     // results; refinement of the grids found, while this pass's gradient maps are on the device
     std::vector<size_t> where;                                      // slot in q.corners of each packed job
     int nj = 0;
@@ -503,6 +522,7 @@ std::string run_pass(Lane &B, const Request &q, const int *ids, const int np, co
         DET_CUDA(cudaStreamSynchronize(st));
         for (int j = 0; j < nj; j++) { q.corners[where[j]] = B.h_refined[2 * j]; q.corners[where[j] + 1] = B.h_refined[2 * j + 1]; }
     }
+    lap(3);
     return std::string();
 }
 
@@ -542,6 +562,8 @@ int vg_detect_pattern(const unsigned char *img, int n_img, int width, int height
     std::vector<int> pending(n_img);
     for (int i = 0; i < n_img; i++) { pending[i] = i; found[i] = 0; }
     static const double SIGMA[3] = {1.4, 2, 1};                     // detectPattern's scales (:225)
+    StageClock clk;
+    const long long t_call = now_ns();
     for (int scale = 0; scale < 3 && !pending.empty(); scale++) {
         const int np = (int)pending.size(), passes = (np + chunk - 1) / chunk;
         std::atomic<int> next(0);
@@ -553,7 +575,7 @@ int vg_detect_pattern(const unsigned char *img, int n_img, int width, int height
             for (int b = next.fetch_add(1); b < passes; b = next.fetch_add(1)) {
                 std::vector<int> mine;
                 const std::string err = run_pass(pl.lane[l], q, pending.data() + (size_t)b * chunk, std::min(chunk, np - b * chunk),
-                                                 SIGMA[scale], mine);
+                                                 SIGMA[scale], mine, clk);
                 std::lock_guard<std::mutex> g(out_mu);
                 if (!err.empty() && error.empty()) error = err;
                 still.insert(still.end(), mine.begin(), mine.end());
@@ -571,6 +593,11 @@ int vg_detect_pattern(const unsigned char *img, int n_img, int width, int height
         std::sort(still.begin(), still.end());
         pending.swap(still);
     }
+    if (const char *e = std::getenv("VG_DETECT_TRACE"))
+        if (e[0] == '1')
+            std::fprintf(stderr, "[vg detect] %d images, %d per pass, %d lanes: wall %.2f ms; summed over passes: staging %.2f, "
+                         "upload + response + scan + download %.2f, host stages %.2f, refinement %.2f ms\n", n_img, chunk, lanes,
+                         (now_ns() - t_call) * 1e-6, clk.ns[0] * 1e-6, clk.ns[1] * 1e-6, clk.ns[2] * 1e-6, clk.ns[3] * 1e-6);
     return VG_OK;
 }
 

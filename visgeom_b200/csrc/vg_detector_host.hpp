@@ -344,6 +344,52 @@ struct Graph {
     bool linked(int a, int b) const { return std::find(arcs[a].begin(), arcs[a].end(), b) != arcs[a].end(); }
 };
 
+// The flood's angle test (:759-770) accepts a pixel at offset (x1, y1) from its candidate when the gradient there is
+// within tol(t) = min(pi / 5, t / 150 + 1 / t) of perpendicular to the offset, t = |(x1, y1)|: with c = offset . grad and
+// s = offset x grad, |atan2(s, c)| must lie in [pi / 2 - tol, pi / 2 + tol].  That is |c| <= |s| tan(tol) -- one
+// multiplication against a table of tan(tol) over the integer t^2 instead of an atan2 per pixel; within 1e-12 of the
+// boundary (and for s = 0) the reference's own expression decides, so the outcome is the reference's in every case.
+class AngleGate {
+public:
+    static constexpr int SPAN = 1 << 16;             // t^2 up to 65535: offsets up to 181 pixels (the flood reaches 140 + a ring)
+    AngleGate() : tan_tol_(SPAN)
+    {
+        for (int q = 1; q < SPAN; q++) {
+            const double t = std::sqrt((double)q);
+            tan_tol_[q] = std::tan(std::min(M_PI / 5, t / 150. + 1 / t));
+        }
+    }
+    // t > 0
+    bool accepts(const int t2, const double t, const double c, const double s) const
+    {
+        if (t2 < SPAN && s != 0) {
+            const double lim = std::fabs(s) * tan_tol_[t2], ac = std::fabs(c);
+            if (ac > lim * (1 + 1e-12)) return false;
+            if (ac < lim * (1 - 1e-12)) return true;
+        }
+        const double angle = std::fabs(std::atan2(s, c));
+        const double tol = std::min(M_PI / 5, t / 150. + 1 / t);
+        return !(angle < M_PI / 2 - tol || angle > M_PI / 2 + tol);
+    }
+
+private:
+    std::vector<double> tan_tol_;
+};
+inline const AngleGate &angle_gate() { static const AngleGate g; return g; }
+
+// the flood's ownership map: one 16-bit candidate index per pixel (the reference's Mat16s _idxMap), kept per host thread
+// and cleared cell by cell after use -- a flood owns a few thousand pixels of the million
+struct OwnerMap {
+    std::vector<int16_t> cell;
+    std::vector<uint32_t> touched;
+    void prepare(const size_t n)
+    {
+        if (cell.size() < n) cell.assign(n, (int16_t)-1);
+        touched.clear();
+    }
+    void reset() { for (uint32_t i : touched) cell[i] = -1; touched.clear(); }
+};
+
 // constructGraph (:612-836): every candidate floods outwards along the edges that leave it (pixels whose gradient is
 // strong enough and perpendicular to the ray from the candidate); where two floods touch, the candidates are linked.
 inline void construct_graph(const Frame &F, const std::vector<Pt> &cand, const int init_radius, Graph &G)
@@ -353,7 +399,10 @@ inline void construct_graph(const Frame &F, const std::vector<Pt> &cand, const i
     G.pt = cand;
     G.arcs.assign(n, {});
     G.sign.clear();
-    std::vector<int16_t> owner((size_t)F.W * F.H, (int16_t)-1);
+    static thread_local OwnerMap owner_map;
+    owner_map.prepare((size_t)F.W * F.H);
+    int16_t *owner = owner_map.cell.data();
+    const AngleGate &gate = angle_gate();
     std::vector<double> grad_min(n);
     std::queue<Cell> fringe;
     for (int i = 0; i < n; i++) {
@@ -368,9 +417,10 @@ inline void construct_graph(const Frame &F, const std::vector<Pt> &cand, const i
     while (!fringe.empty() && fringe.front().t < REACH) {
         const Cell e = fringe.front();
         fringe.pop();
-        int16_t &own = owner[(size_t)e.v * F.W + e.u];
-        if (own != -1) continue;
-        own = (int16_t)e.idx;
+        const size_t at = (size_t)e.v * F.W + e.u;
+        if (owner[at] != -1) continue;
+        owner[at] = (int16_t)e.idx;
+        owner_map.touched.push_back((uint32_t)at);
         bool touched = false;
         for (int k = 0; k < 8; k++) {
             const int u2 = e.u + du8[k], v2 = e.v + dv8[k];
@@ -402,20 +452,17 @@ inline void construct_graph(const Frame &F, const std::vector<Pt> &cand, const i
             const int u2 = e.u + du8[k], v2 = e.v + dv8[k];
             if (u2 < 0 || u2 >= F.W || v2 < 0 || v2 >= F.H) continue;
             if (owner[(size_t)v2 * F.W + u2] != -1) continue;
-            const double x1 = u2 - G.pt[e.idx].u, y1 = v2 - G.pt[e.idx].v;
+            const int ix = u2 - G.pt[e.idx].u, iy = v2 - G.pt[e.idx].v;
+            const double x1 = ix, y1 = iy;
             const double t = std::sqrt(x1 * x1 + y1 * y1);
             const double xg = F.gradx(v2, u2), yg = F.grady(v2, u2);
             const double across = std::fabs(xg * y1 - yg * x1);
             if (t > 0 && across / t < grad_min[e.idx]) continue;
-            if (t > 0) {
-                const double c = x1 * xg + y1 * yg, s = x1 * yg - y1 * xg;
-                const double angle = std::fabs(std::atan2(s, c));
-                const double tol = std::min(M_PI / 5, t / 150. + 1 / t);
-                if (angle < M_PI / 2 - tol || angle > M_PI / 2 + tol) continue;
-            }
+            if (t > 0 && !gate.accepts(ix * ix + iy * iy, t, x1 * xg + y1 * yg, x1 * yg - y1 * xg)) continue;
             fringe.push(Cell{e.t + 1, e.idx, u2, v2});
         }
     }
+    owner_map.reset();
 }
 
 // Eigen's Matrix<int, 2, 1>::norm(): the square root converted back to int
