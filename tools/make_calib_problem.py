@@ -1,7 +1,7 @@
 """Writes synthetic calibration problems in the reference's JSON format (README.md:36-223 of visgeom,
 dataset type "ir_data": pre-extracted corners, unified_calibration.cpp:234-277) for vg_calib / the tests.
 
-  python tools/make_calib_problem.py mono|stereo|odometry OUT_DIR [n_images]
+  python tools/make_calib_problem.py mono|stereo|odometry|images OUT_DIR [n_images]
 """
 from __future__ import annotations
 
@@ -129,4 +129,4 @@ def write_odometry(out_dir, n=30, seed=20246, anchor=True, prior=True):
 if __name__ == "__main__":
     kind, out = sys.argv[1], sys.argv[2]
     n = int(sys.argv[3]) if len(sys.argv) > 3 else 20
-    print({"mono": write_mono, "stereo": write_stereo, "odometry": write_odometry}[kind](out, n)[0])
+    print({"mono": write_mono, "stereo": write_stereo, "odometry": write_odometry, "images": write_images}[kind](out, n)[0])
