@@ -229,6 +229,49 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------------
+def detector_leg(vg, cpu_too):
+    """The stage that produces the observations (SURVEY.md 8f-4): CornerDetector::detectPattern with the sub-pixel
+    refinement on rendered 640 x 480 pictures of the board, host pictures in, corners out (vg_detect_pattern); next to it
+    the reference's own corner_detector.cpp (oracle/_ref) on one host thread -- what extractGridProjections does -- and
+    with one picture per thread on all of them."""
+    import synthdata as sd
+    base = [sd.render_board_image(640, 480, seed=20400 + k, model=(sd.EUCM, sd.MEI, sd.UCM)[k % 3], supersample=2) for k in range(6)]
+    n = 48
+    imgs = np.stack([base[k % 6][0] for k in range(n)])
+    vg.detect_pattern(imgs[:4])
+    best, found, corners = None, None, None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        found, corners = vg.detect_pattern(imgs, improve=True)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    out = {"images_per_s": n / best, "unit": "images/s", "images": n, "size": [640, 480], "found": int(found.sum()),
+           "what": "vg_detect_pattern, sub-pixel refinement on, pictures in host memory, best of 3 calls"}
+    if cpu_too:
+        try:
+            from concurrent.futures import ThreadPoolExecutor
+            from oracle.pyoracle import ReferenceDetector
+            ref = ReferenceDetector()
+            t0 = time.perf_counter()
+            agree = True
+            for k in range(6):
+                ok, c, _, _ = ref.detect_pattern(imgs[k], improve=True)
+                agree = agree and ok == bool(found[k]) and (not ok or float(np.abs(c - corners[k]).max()) < 1e-4)
+            one = 6 / (time.perf_counter() - t0)
+            cores = len(os.sched_getaffinity(0))
+            with ThreadPoolExecutor(cores) as ex:              # ctypes releases the GIL
+                t0 = time.perf_counter()
+                list(ex.map(lambda k: ref.detect_pattern(imgs[k % n], improve=True), range(3 * cores)))
+                many = 3 * cores / (time.perf_counter() - t0)
+            out["cpu_reference"] = {"single_thread_images_per_s": one, "images_per_s": many, "cores": cores, "kind": "reference",
+                                    "agrees_with_gpu": bool(agree),
+                                    "what": "the reference's corner_detector.cpp compiled in place (oracle/_ref, -O2; OpenCV and "
+                                            "Ceres are stand-ins): CornerDetector(9, 6, 3, true).detectPattern"}
+        except (OSError, FileNotFoundError) as e:
+            out["cpu_reference"] = {"unavailable": str(e)}
+    return out
+
+
 def lm_leg(make_problem, d, model_id, max_iter, threads=None):
     """LM iterations/s (BASELINE.json's second metric) of one solve from the perturbed initial guess:
     make_problem() -> an object with the visgeom_b200.Problem interface (the CUDA engine, or the oracle's
@@ -641,6 +684,8 @@ def run_ours(args):
                      "iters_per_s_scaled_to_workload": cpu_lm["iters_per_s"] * n_lm / n_img if cpu_lm["iters_per_s"] else None,
                      "kind": "port", "what": "oracle LM (restated Ceres trust-region loop, not Ceres itself), OpenMP evaluation"}
 
+    detector = detector_leg(vg, cpu_too=True) if rank == 0 and world == 1 else None
+
     if rank == 0:
         collective = None if world == 1 else ("nccl all-reduce callback" if state["nccl"] else
                                               "peer memory over NVLink, fused into the evaluation kernel (posted by the "
@@ -677,6 +722,8 @@ def run_ours(args):
             line["exchange_check"] = main["exchange_check"]
         if c5 is not None:
             line["c5"] = c5
+        if detector is not None:
+            line["detector"] = detector
         if failures:
             line["failures"] = failures
         print(json.dumps(line), flush=True)
