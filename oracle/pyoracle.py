@@ -170,6 +170,18 @@ class Oracle(_Evaluator):
         self.lib.vgo_odometry_prior_eval(C.byref(op), _dp(a), _dp(b), _dp(r), _dp(J1), _dp(J2))
         return r, J1, J2
 
+
+    def odometry_cost(self, errV, errW, lam, dq, intr_prior, xi1, xi2, intr):
+        """OdometryCost (odometry_cost_function.cpp) -> r, J1, J2 (6 x 6), J3 (6 x 3), zeta_prior, A."""
+        q = _f64(dq).reshape(-1, 2); ip = _f64(intr_prior); a = _f64(xi1); b = _f64(xi2); it = _f64(intr)
+        oc = OdometryPriorC()
+        self.lib.vgo_odometry_cost_init.argtypes = [C.POINTER(OdometryPriorC), C.c_double, C.c_double, C.c_double, C.c_int, c_dp, c_dp]
+        self.lib.vgo_odometry_cost_eval.argtypes = [C.POINTER(OdometryPriorC), C.c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]
+        if self.lib.vgo_odometry_cost_init(C.byref(oc), errV, errW, lam, q.shape[0], _dp(q), _dp(ip)):
+            raise ValueError("OdometryCost needs at least one increment")
+        r = np.zeros(6); J1 = np.zeros((6, 6)); J2 = np.zeros((6, 6)); J3 = np.zeros((6, 3))
+        self.lib.vgo_odometry_cost_eval(C.byref(oc), q.shape[0], _dp(q), _dp(a), _dp(b), _dp(it), _dp(r), _dp(J1), _dp(J2), _dp(J3))
+        return r, J1, J2, J3, np.array(oc.zeta_prior), np.array(oc.A).reshape(6, 6)
     def visual_cov(self, model, intr, xi_board, board, feature_variance, cam_poses):
         """TrajectoryVisualQuality::visualCov for n camera poses -> (n, 6, 6)."""
         intr = _f64(intr); xb = _f64(xi_board); board = _f64(board); poses = _f64(cam_poses).reshape(-1, 6)
@@ -376,6 +388,16 @@ class Reference(_Evaluator):
         r = np.zeros(6); J1 = np.zeros((6, 6)); J2 = np.zeros((6, 6))
         self.lib.vgref_odometry_prior(errV, errW, lam, _dp(o1), _dp(o2), _dp(a), _dp(b), _dp(r), _dp(J1), _dp(J2))
         return r, J1, J2
+
+
+    def odometry_cost(self, errV, errW, lam, dq, intr_prior, xi1, xi2, intr):
+        """The reference's own OdometryCost: constructor + Evaluate with three parameter blocks."""
+        q = _f64(dq).reshape(-1, 2); ip = _f64(intr_prior); a = _f64(xi1); b = _f64(xi2); it = _f64(intr)
+        r = np.zeros(6); J1 = np.zeros((6, 6)); J2 = np.zeros((6, 6)); J3 = np.zeros((6, 3)); zp = np.zeros(6); A = np.zeros((6, 6))
+        self.lib.vgref_odometry_cost.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int] + [c_dp] * 11
+        self.lib.vgref_odometry_cost(errV, errW, lam, q.shape[0], _dp(q), _dp(ip), _dp(a), _dp(b), _dp(it), _dp(r), _dp(J1), _dp(J2),
+                                     _dp(J3), _dp(zp), _dp(A))
+        return r, J1, J2, J3, zp, A
 
 
 class ReferenceDetector:

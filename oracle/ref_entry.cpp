@@ -6,6 +6,7 @@
 // with all Jacobian blocks requested.  No reference source is copied into this repository.
 #include "calibration/calib_cost_functions.h"
 #include "calibration/trajectory_generation.h"
+#include "calibration/odometry_cost_function.h"
 #include "projection/eucm.h"
 #include "projection/ucm.h"
 #include "projection/mei.h"
@@ -156,6 +157,23 @@ void vgref_odometry_prior(double errV, double errW, double lambda, const double 
     const double *params[2] = {xi1, xi2};
     double *jac[2] = {J1, J2};
     cost.Evaluate(params, r, (J1 || J2) ? jac : NULL);
+}
+
+// OdometryCost (odometry_cost_function.cpp:144-267): constructor from the prior intrinsics, then Evaluate with three
+// parameter blocks, as unified_calibration.cpp:718-731 hands them over.  zeta_prior / A (optional) receive what the
+// constructor left in the object.
+void vgref_odometry_cost(double errV, double errW, double lambda, int m, const double *dq, const double *intr_prior,
+                         const double *xi1, const double *xi2, const double *intr, double *r, double *J1, double *J2,
+                         double *J3, double *zeta_prior, double *A)
+{
+    vector<Vector2d> deltaQ;
+    for (int i = 0; i < m; i++) deltaQ.emplace_back(dq[2 * i], dq[2 * i + 1]);
+    OdometryCost cost(errV, errW, lambda, deltaQ, intr_prior);
+    const double *params[3] = {xi1, xi2, intr};
+    double *jac[3] = {J1, J2, J3};
+    cost.Evaluate(params, r, (J1 || J2 || J3) ? jac : NULL);
+    if (zeta_prior) cost._zetaPrior.toArray(zeta_prior);
+    if (A) for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) A[6 * i + j] = cost._A(i, j);
 }
 
 // TrajectoryVisualQuality::visualCov (trajectory_generation.cpp:185-206): the object is built through its own

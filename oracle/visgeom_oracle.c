@@ -810,11 +810,20 @@ void vgo_transformation_prior_eval(const vgo_transformation_prior *tp, const dou
 }
 
 /* calib_cost_functions.cpp:119-173 */
+static void odometry_information(vgo_odometry_prior *op, double errV, double errW, double lambda);
+
 void vgo_odometry_prior_init(vgo_odometry_prior *op, double errV, double errW, double lambda,
                              const double xi1[6], const double xi2[6])
 {
-    const double MIN_SIGMA_V = 0.01, MIN_SIGMA_W = 0.01, MIN_DELTA = 0.01, MIN_L = 0.01;
     vgo_inverse_compose(xi1, xi2, op->zeta_prior);          /* :122 */
+    odometry_information(op, errV, errW, lambda);
+}
+
+/* the information matrix _A from the prior motion: calib_cost_functions.cpp:124-172 and, word for word the same,
+ * odometry_cost_function.cpp:155-196 */
+static void odometry_information(vgo_odometry_prior *op, double errV, double errW, double lambda)
+{
+    const double MIN_SIGMA_V = 0.01, MIN_SIGMA_W = 0.01, MIN_DELTA = 0.01, MIN_L = 0.01;
     memset(op->A, 0, sizeof op->A);
     const double delta = fmax(norm3(op->zeta_prior + 3), MIN_DELTA);
     const double l = fmax(norm3(op->zeta_prior), MIN_L);
@@ -906,6 +915,124 @@ void vgo_odometry_prior_eval(const vgo_odometry_prior *op, const double xi1[6], 
         mat3_mul(R20, M, R20M);
         blockdiag6(R20, R20M, Jb);
         mat6_mul(op->A, Jb, J2);
+    }
+}
+
+/* ------------------------------------------------------------------ */
+/* OdometryCost, src/calibration/odometry_cost_function.cpp (the third residual block of the calibration,
+ * "odometry_intrinsic" datasets): the motion between two poses of a differential-drive platform, integrated from m
+ * pairs of wheel-angle increments (left, right) with the odometry intrinsics (r1, r2 wheel radii, g track gauge),
+ * compared with the motion xi1^-1 o xi2. */
+
+/* tf0n_jac_calc, :68-88, one step: zeta_i = (v, 0, w) from the increments (odom_zeta_i, :10-35) and its Jacobian
+ * w.r.t. (r1, r2, g) (zeta_i_jacobian, :38-65) */
+static void odometry_step(const double dq[2], const double in[3], double zeta_i[3], double jac[9])
+{
+    const double r1 = in[0], r2 = in[1], g = in[2];
+    const double j2c[4] = { r1 / 2, r2 / 2, -(r1 / g), r2 / g };
+    const double v = j2c[0] * dq[0] + j2c[1] * dq[1], w = j2c[2] * dq[0] + j2c[3] * dq[1];
+    /* A = [1 0; 0 0; 0 1], zeta_i = A * v_w: every entry is a two-term product sum */
+    zeta_i[0] = 1 * v + 0 * w; zeta_i[1] = 0 * v + 0 * w; zeta_i[2] = 0 * v + 1 * w;
+    jac[0] = dq[0] / 2; jac[1] = dq[1] / 2; jac[2] = 0;
+    jac[3] = 0; jac[4] = 0; jac[5] = 0;
+    jac[6] = -dq[0] / g; jac[7] = dq[1] / g; jac[8] = (r1 * dq[0] - r2 * dq[1]) / (g * g);
+}
+
+/* tf0n_jac_calc (:68-88) + calc_acc (:90-141): zeta_odo = 0Tn and d(zeta_odo's x, y, theta) / d(r1, r2, g) as the 6 x 3
+ * matrix calc_acc returns (rows x, y, -, -, -, theta).  tf = m transforms of scratch. */
+static void odometry_integrate(int m, const double *dq, const double in[3], double *tf, double zeta_odo[6], double jac6x3[18])
+{
+    double cur[6] = { 0, 0, 0, 0, 0, 0 };
+    for (int i = 0; i < m; i++) {
+        double z[3], jz[9], step[6], nxt[6];
+        odometry_step(dq + 2 * i, in, z, jz);
+        step[0] = z[0]; step[1] = z[1]; step[2] = 0; step[3] = 0; step[4] = 0; step[5] = z[2];
+        vgo_compose(cur, step, nxt);                        /* :82 */
+        memcpy(cur, nxt, sizeof cur);
+        memcpy(tf + 6 * (size_t)i, cur, sizeof cur);
+    }
+    memcpy(zeta_odo, tf + 6 * (size_t)(m - 1), 6 * sizeof(double));
+    if (!jac6x3) return;
+    double ACC[9] = { 0 };
+    for (int i = 0; i < m; i++) {
+        double z[3], jz[9], prev[6] = { 0, 0, 0, 0, 0, 0 }, R0j[9];
+        odometry_step(dq + 2 * i, in, z, jz);
+        if (i > 0) memcpy(prev, tf + 6 * (size_t)(i - 1), sizeof prev);
+        vgo_rotation_matrix(prev + 3, R0j);                 /* :110 */
+        /* tfi_n = tf0_i.inverse().compose(tf0_n), :112-114; inverse() = (-R^T t, -rot), transformation.h:112-119 */
+        const double *t0i = tf + 6 * (size_t)i;
+        double neg[3] = { -t0i[3], -t0i[4], -t0i[5] }, Rinv[9], inv[6], tin[6];
+        vgo_rotation_matrix(neg, Rinv);
+        double nR[9];
+        for (int k = 0; k < 9; k++) nR[k] = -Rinv[k];
+        mat3_vec(nR, t0i, inv);
+        inv[3] = neg[0]; inv[4] = neg[1]; inv[5] = neg[2];
+        vgo_compose(inv, zeta_odo, tin);
+        const double J[9] = { 1, 0, -tin[1], 0, 1, tin[0], 0, 0, 1 };       /* :119-122 */
+        double RJ[9], RJz[9];
+        mat3_mul(R0j, J, RJ);
+        mat3_mul(RJ, jz, RJz);
+        for (int k = 0; k < 9; k++) ACC[k] = ACC[k] + RJz[k];               /* :124 */
+    }
+    memset(jac6x3, 0, 18 * sizeof(double));
+    for (int j = 0; j < 3; j++) { jac6x3[j] = ACC[j]; jac6x3[3 + j] = ACC[3 + j]; jac6x3[15 + j] = ACC[6 + j]; }
+}
+
+/* the constructor, :144-197: the prior motion from the prior intrinsics, then _A.  Returns 0, or -1 without increments. */
+int vgo_odometry_cost_init(vgo_odometry_prior *oc, double errV, double errW, double lambda, int m, const double *dq,
+                           const double intr_prior[3])
+{
+    if (m < 1) return -1;
+    double *tf = (double *)malloc(sizeof(double) * 6 * (size_t)m);
+    odometry_integrate(m, dq, intr_prior, tf, oc->zeta_prior, NULL);
+    free(tf);
+    odometry_information(oc, errV, errW, lambda);
+    return 0;
+}
+
+/* Evaluate, :202-267.  J1, J2 6 x 6, J3 6 x 3, row-major; any may be NULL. */
+void vgo_odometry_cost_eval(const vgo_odometry_prior *oc, int m, const double *dq, const double xi1[6], const double xi2[6],
+                            const double intr[3], double r[6], double *J1, double *J2, double *J3)
+{
+    double *tf = (double *)malloc(sizeof(double) * 6 * (size_t)m);
+    double zeta[6], zeta_odo[6], jin[18], delta[6];
+    vgo_inverse_compose(xi1, xi2, zeta);                    /* :209 */
+    odometry_integrate(m, dq, intr, tf, zeta_odo, jin);     /* :218-219 */
+    free(tf);
+    vgo_inverse_compose(zeta_odo, zeta, delta);             /* :224 */
+    mat6_vec(oc->A, delta, r);                              /* :226 */
+    /* the first two blocks are OdometryPrior's with the integrated motion in the prior's place, :231-253 */
+    vgo_odometry_prior tmp = *oc;
+    memcpy(tmp.zeta_prior, zeta_odo, sizeof tmp.zeta_prior);
+    if (J1 || J2) { double r2[6]; vgo_odometry_prior_eval(&tmp, xi1, xi2, r2, J1, J2); }
+    if (J3) {                                               /* :256-264 */
+        double neg[3] = { -zeta_odo[3], -zeta_odo[4], -zeta_odo[5] }, R31[9], M[9], R31M[9], Jb[36];
+        vgo_rotation_matrix(neg, R31);
+        vgo_inter_omega_rot(zeta_odo + 3, M);
+        mat3_mul(R31, M, R31M);
+        blockdiag6(R31, R31M, Jb);
+        double nd[3] = { -delta[3], -delta[4], -delta[5] }, Rd[9], th[9], nRd[9], Rth[9], TT[36];
+        vgo_rotation_matrix(nd, Rd);
+        hat3(delta, th);
+        for (int i = 0; i < 9; i++) nRd[i] = -Rd[i];
+        mat3_mul(nRd, th, Rth);
+        memset(TT, 0, sizeof TT);
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) {
+                TT[6 * i + j] = Rd[3 * i + j];
+                TT[6 * i + j + 3] = Rth[3 * i + j];
+                TT[6 * (i + 3) + j + 3] = Rd[3 * i + j];
+            }
+        double nA[36], a[36], b[36];
+        for (int i = 0; i < 36; i++) nA[i] = -oc->A[i];
+        mat6_mul(nA, TT, a);                                /* ((-_A * TT) * J3) * jac_intrinsic, left to right */
+        mat6_mul(a, Jb, b);
+        for (int i = 0; i < 6; i++)
+            for (int j = 0; j < 3; j++) {
+                double s = b[6 * i] * jin[j];
+                for (int k = 1; k < 6; k++) s += b[6 * i + k] * jin[3 * k + j];
+                J3[3 * i + j] = s;
+            }
     }
 }
 

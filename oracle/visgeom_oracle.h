@@ -107,6 +107,12 @@ void vgo_odometry_prior_init(vgo_odometry_prior *op, double errV, double errW, d
 /* r: 6 doubles; J1, J2: 36 doubles row-major (Matrix6drm maps, .cpp:195,206) or NULL */
 void vgo_odometry_prior_eval(const vgo_odometry_prior *op, const double xi1[6], const double xi2[6],
                              double r[6], double *J1, double *J2);
+/* OdometryCost (src/calibration/odometry_cost_function.cpp): same record (prior motion + _A); m pairs of wheel-angle
+ * increments dq, odometry intrinsics (r1, r2, g) */
+int vgo_odometry_cost_init(vgo_odometry_prior *oc, double errV, double errW, double lambda, int m, const double *dq,
+                           const double intr_prior[3]);
+void vgo_odometry_cost_eval(const vgo_odometry_prior *oc, int m, const double *dq, const double xi1[6], const double xi2[6],
+                            const double intr[3], double r[6], double *J1, double *J2, double *J3);
 
 /* TrajectoryVisualQuality::visualCov (trajectory_generation.cpp:185-206): 6 x 6 covariance of each camera pose
  * localised on the board; cam_poses n x 6, out n x 36 row-major */
