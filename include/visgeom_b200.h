@@ -166,6 +166,17 @@ int vg_eval_odometry_prior(int n, double errV, double errW, double lambda,
                            const double *odom1 /* n x 6 */, const double *odom2 /* n x 6 */,
                            const double *xi1 /* n x 6 */, const double *xi2 /* n x 6 */,
                            double *r /* n x 6 */, double *J1 /* n x 36 */, double *J2 /* n x 36 */);
+/* OdometryCost (include/calibration/odometry_cost_function.h:33-59, src/calibration/odometry_cost_function.cpp:144-267:
+ * the residual block of "odometry_intrinsic" datasets, unified_calibration.cpp:718-731) for n blocks: the motion of a
+ * differential-drive platform integrated from wheel-angle increments against xi1^-1 o xi2.  Block b owns the pairs
+ * (left, right) dq[2 dq_offset[b] .. 2 dq_offset[b + 1]) (at least one); intr_prior = the (r1, r2, g) the constructor
+ * builds _zetaPrior and _A from, intr = the parameter block; r 6 per block, J1 / J2 (6 x 6, d r / d xi1, xi2) and J3
+ * (6 x 3, d r / d intr) row-major, any of the three may be NULL.  (The reference declares the functor
+ * SizedCostFunction<6, 6> while handing it three blocks, so its own "odometry_intrinsic" datasets cannot be added to a
+ * Ceres problem; Evaluate itself is well defined and is what this entry point offers.) */
+int vg_eval_odometry_cost(int n, double errV, double errW, double lambda, const int *dq_offset, const double *dq,
+                          const double *intr_prior, const double *xi1, const double *xi2, const double *intr, double *r,
+                          double *J1, double *J2, double *J3);
 
 /* TrajectoryVisualQuality::visualCov (trajectory_generation.cpp:185-206), batched over n camera poses:
  * the covariance of a camera pose localised on the board, from dP/dX of the model at every board point:

@@ -203,5 +203,45 @@ def priors(ref, orc):
     print(f"wrote {path}: {len(blob)} arrays, {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def odometry_cost(ref, orc):
+    """OdometryCost (odometry_cost_function.cpp:144-267) evaluated by the reference build on seeded inputs ->
+    reference_odometry_cost.npz: 40 blocks of 1 to 80 wheel-angle increments (straight runs, turns on the spot, increments
+    below MIN_L / MIN_DELTA), the parameter block off the prior intrinsics, poses near and far from the odometry."""
+    n = 40
+    errV, errW, lam = 0.1, 0.05, 0.003
+    intr_prior = np.array([0.1, 0.1, 0.5])
+    intr = np.array([0.103, 0.0985, 0.52])
+    blob = {"params": np.array([errV, errW, lam]), "intr_prior": intr_prior, "intr": intr}
+    lens = [1 + int(v) for v in (sd.uniform(79, 1, n) * 80)]
+    lens[0], lens[1] = 1, 80
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    u = sd.uniform(79, 2, 2 * off[-1]).reshape(-1, 2)
+    dq = 0.05 + 0.5 * u
+    for b in range(n):
+        sl = slice(off[b], off[b + 1])
+        if b % 5 == 1: dq[sl, 1] = dq[sl, 0]                       # straight
+        if b % 5 == 2: dq[sl, 1] = -dq[sl, 0]                      # turning on the spot
+        if b % 5 == 3: dq[sl] *= 1e-3                              # below MIN_L / MIN_DELTA
+        if b % 5 == 4: dq[sl, 0] *= -1                             # reversing one wheel
+    w = sd.uniform(79, 3, 12 * n).reshape(n, 12) * 2 - 1
+    xi1 = np.concatenate([w[:, 0:3], w[:, 3:6] * 0.8], axis=1)
+    xi2 = np.zeros((n, 6))
+    r = np.zeros((n, 6)); J1 = np.zeros((n, 6, 6)); J2 = np.zeros((n, 6, 6)); J3 = np.zeros((n, 6, 3))
+    zp = np.zeros((n, 6)); A = np.zeros((n, 6, 6))
+    for b in range(n):
+        q = dq[off[b]:off[b + 1]]
+        zeta = ref.odometry_cost(errV, errW, lam, q, intr_prior, np.zeros(6), np.zeros(6), intr_prior)[4]      # the prior motion
+        xi2[b] = orc.compose(xi1[b], zeta) + w[b, 6:12] * (0.02 if b % 3 else 0.3)
+        r[b], J1[b], J2[b], J3[b], zp[b], A[b] = ref.odometry_cost(errV, errW, lam, q, intr_prior, xi1[b], xi2[b], intr)
+    blob.update({"dq_offset": off, "dq": dq, "xi1": xi1, "xi2": xi2, "r": r, "J1": J1, "J2": J2, "J3": J3, "zeta_prior": zp, "A": A})
+    path = os.path.join(HERE, "reference_odometry_cost.npz")
+    np.savez_compressed(path, **blob)
+    print(f"wrote {path}: {len(blob)} arrays, {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "odometry_cost":       # the other files stay byte-identical
+        from oracle.pyoracle import Oracle, Reference
+        odometry_cost(Reference(), Oracle())
+    else:
+        main()

@@ -232,3 +232,46 @@ def test_visual_cov_matches_reference_and_oracle(gpu, oracle, model, name):
     assert gpu.visual_cov(model, d["intr_gt"], xi_board, d["board"], 0.04, np.zeros((0, 6))).shape == (0, 6, 6)
     with pytest.raises(gpu.VisgeomError, match="bad arguments"):
         gpu.visual_cov(model, d["intr_gt"], xi_board, d["board"], -1.0, cam)
+
+
+# ---- OdometryCost (src/calibration/odometry_cost_function.cpp) at the functor level -------------------------------------
+OC = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_odometry_cost.npz"))
+
+
+def test_odometry_cost_matches_reference_vectors(gpu):
+    errV, errW, lam = OC["params"]
+    off = OC["dq_offset"]
+    blocks = [OC["dq"][off[b]:off[b + 1]] for b in range(len(OC["r"]))]
+    r, J1, J2, J3 = gpu.eval_odometry_cost(errV, errW, lam, blocks, OC["intr_prior"], OC["xi1"], OC["xi2"], OC["intr"])
+    for b in range(len(r)):
+        assert_close(r[b], OC["r"][b], f"oc[{b}]: r", FUNCTOR_RTOL)
+        assert_close(J1[b], OC["J1"][b], f"oc[{b}]: J1", FUNCTOR_RTOL)
+        assert_close(J2[b], OC["J2"][b], f"oc[{b}]: J2", FUNCTOR_RTOL)
+        assert_close(J3[b], OC["J3"][b], f"oc[{b}]: J3", FUNCTOR_RTOL)
+    r2, a, b_, c = gpu.eval_odometry_cost(errV, errW, lam, blocks, OC["intr_prior"], OC["xi1"], OC["xi2"], OC["intr"], want_J=False)
+    assert a is None and b_ is None and c is None and np.array_equal(r, r2)
+
+
+def test_odometry_cost_matches_oracle_on_random_inputs(gpu, oracle):
+    n = 300
+    rng = np.random.default_rng(815)
+    blocks = [rng.uniform(-0.4, 0.6, (int(rng.integers(1, 120)), 2)) * rng.choice([1.0, 1.0, 1e-3]) for _ in range(n)]
+    ip = np.array([0.08, 0.081, 0.43]); it = ip * (1 + rng.normal(0, 0.03, 3))
+    xi1 = np.concatenate([rng.normal(0, 1, (n, 3)), rng.normal(0, 0.6, (n, 3))], axis=1)
+    xi2 = xi1 + np.concatenate([rng.normal(0, 0.4, (n, 3)), rng.normal(0, 0.3, (n, 3))], axis=1)
+    r, J1, J2, J3 = gpu.eval_odometry_cost(0.07, 0.09, 0.004, blocks, ip, xi1, xi2, it)
+    for b in range(n):
+        o = oracle.odometry_cost(0.07, 0.09, 0.004, blocks[b], ip, xi1[b], xi2[b], it)
+        for got, want, name in ((r[b], o[0], "r"), (J1[b], o[1], "J1"), (J2[b], o[2], "J2"), (J3[b], o[3], "J3")):
+            assert_close(got, want, f"oc[{b}]: {name}", 1e-10)
+
+
+def test_odometry_cost_api_errors(gpu):
+    import ctypes as C
+    z6 = np.zeros((1, 6)); i3 = np.array([0.1, 0.1, 0.5])
+    with pytest.raises(gpu.VisgeomError):
+        gpu.eval_odometry_cost(0.1, 0.1, 0.01, [np.zeros((0, 2))], i3, z6, z6, i3)      # a block without increments
+    with pytest.raises(gpu.VisgeomError):
+        gpu.eval_odometry_cost(0.1, 0.1, 0.0, [np.ones((3, 2))], i3, z6, z6, i3)        # lambda = 0 divides by zero
+    r, *_ = gpu.eval_odometry_cost(0.1, 0.1, 0.01, [], i3, np.zeros((0, 6)), np.zeros((0, 6)), i3)
+    assert r.shape == (0, 6)

@@ -135,3 +135,53 @@ def test_visual_cov_matches_reference_vectors(oracle, model, name):
     # the covariance of a localisation is symmetric positive definite
     w = np.linalg.eigvalsh((want[0] + want[0].T) / 2)
     assert w[0] > 0
+
+
+# ---- OdometryCost (src/calibration/odometry_cost_function.cpp; the residual block of "odometry_intrinsic" datasets) ----
+OC = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_odometry_cost.npz"))
+
+
+def _oc_block(b):
+    off = OC["dq_offset"]
+    return OC["dq"][off[b]:off[b + 1]]
+
+
+def test_odometry_cost_matches_reference_vectors(oracle):
+    errV, errW, lam = OC["params"]
+    for b in range(len(OC["r"])):
+        r, J1, J2, J3, zp, A = oracle.odometry_cost(errV, errW, lam, _oc_block(b), OC["intr_prior"], OC["xi1"][b], OC["xi2"][b], OC["intr"])
+        for got, name in ((r, "r"), (J1, "J1"), (J2, "J2"), (J3, "J3"), (zp, "zeta_prior"), (A, "A")):
+            want = OC[name][b]
+            assert np.abs(got - want).max() <= 1e-13 * max(1.0, np.abs(want).max()), (b, name)
+
+
+def test_odometry_cost_jacobians_are_derivatives(oracle):
+    """Central differences of the residual at the odometry (delta = 0).  d r / d intrinsics is exact for a single
+    increment; for longer chains the reference's calc_acc is itself an approximation (it differentiates the planar
+    position through the first-order term only: a few per cent off at 80 increments) -- the restatement follows the
+    reference, so the longer chains are held loosely.  The translation columns of d r / d xi2 are exact."""
+    errV, errW, lam = OC["params"]
+    for b in (0, 1, 7, 12, 26):
+        q, ip = _oc_block(b), OC["intr_prior"]
+        zeta = oracle.odometry_cost(errV, errW, lam, q, ip, np.zeros(6), np.zeros(6), OC["intr"])[4]
+        f = lambda x1, x2, it: oracle.odometry_cost(errV, errW, lam, q, ip, x1, x2, it)[0]
+        x1 = OC["xi1"][b]
+        x2 = oracle.compose(x1, oracle.odometry_cost(errV, errW, lam, q, OC["intr"], np.zeros(6), np.zeros(6), OC["intr"])[4])
+        _, J1, J2, J3, _, A = oracle.odometry_cost(errV, errW, lam, q, ip, x1, x2, OC["intr"])
+        h = 1e-6
+        num3 = np.stack([(f(x1, x2, OC["intr"] + h * e) - f(x1, x2, OC["intr"] - h * e)) / (2 * h) for e in np.eye(3)], axis=1)
+        assert np.abs(num3 - J3).max() <= (2e-6 if len(q) == 1 else 0.1) * max(1.0, np.abs(J3).max()), b
+        num2 = np.stack([(f(x1, x2 + h * e, OC["intr"]) - f(x1, x2 - h * e, OC["intr"])) / (2 * h) for e in np.eye(6)], axis=1)
+        assert np.abs(num2[:, :3] - J2[:, :3]).max() <= 2e-6 * max(1.0, np.abs(J2).max()), b      # translation columns
+        assert zeta.shape == (6,) and A.shape == (6, 6)
+
+
+def test_odometry_cost_equals_odometry_prior_on_the_same_motion(oracle):
+    """With the parameter block at the prior intrinsics the integrated motion IS the prior: residual and the first two
+    Jacobian blocks are OdometryPrior's for odom1 = 0, odom2 = that motion."""
+    errV, errW, lam = OC["params"]
+    for b in (2, 9, 33):
+        q, ip = _oc_block(b), OC["intr_prior"]
+        r, J1, J2, _, zp, _ = oracle.odometry_cost(errV, errW, lam, q, ip, OC["xi1"][b], OC["xi2"][b], ip)
+        r0, K1, K2 = oracle.odometry_prior(errV, errW, lam, np.zeros(6), zp, OC["xi1"][b], OC["xi2"][b])
+        assert np.abs(r - r0).max() < 1e-12 and np.abs(J1 - K1).max() < 1e-12 and np.abs(J2 - K2).max() < 1e-12

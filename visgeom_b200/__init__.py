@@ -103,6 +103,8 @@ def lib() -> C.CDLL:
         L.vg_eval_transformation_prior.argtypes = [C.c_int, c_dp, c_dp, c_dp, c_dp, c_dp]
         L.vg_eval_odometry_prior.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, c_dp, c_dp, c_dp, c_dp,
                                              c_dp, c_dp, c_dp]
+        L.vg_eval_odometry_cost.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, c_ip, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,
+                                            c_dp, c_dp, c_dp]
         L.vg_problem_peer_export.argtypes = [C.c_void_p, C.c_void_p]
         L.vg_problem_peer_connect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.vg_problem_peer_inbox.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), c_ip]
@@ -223,6 +225,25 @@ def eval_odometry_prior(errV, errW, lam, odom1, odom2, xi1, xi2, want_J=True):
     _check(lib().vg_eval_odometry_prior(n, errV, errW, lam, _dp(o1), _dp(o2), _dp(a), _dp(b), _dp(r),
                                         _dp(J1) if want_J else None, _dp(J2) if want_J else None))
     return r, J1, J2
+
+
+def eval_odometry_cost(errV, errW, lam, dq_list, intr_prior, xi1, xi2, intr, want_J=True):
+    """Batched OdometryCost::Evaluate (odometry_cost_function.cpp:202-267): dq_list[b] = the (m_b, 2) wheel-angle
+    increments of block b -> r (n, 6), J1, J2 (n, 6, 6), J3 (n, 6, 3)."""
+    a = _f64(xi1).reshape(-1, 6); b = _f64(xi2).reshape(-1, 6)
+    n = a.shape[0]
+    off = np.zeros(n + 1, dtype=np.int32)
+    for k in range(n):
+        off[k + 1] = off[k] + len(dq_list[k])
+    dq = _f64(np.concatenate([np.asarray(q, dtype=np.float64).reshape(-1, 2) for q in dq_list], axis=0)) if n else np.zeros((0, 2))
+    ip = _f64(intr_prior); it = _f64(intr)
+    r = np.empty((n, 6))
+    J1 = np.empty((n, 6, 6)) if want_J else None
+    J2 = np.empty((n, 6, 6)) if want_J else None
+    J3 = np.empty((n, 6, 3)) if want_J else None
+    _check(lib().vg_eval_odometry_cost(n, errV, errW, lam, off.ctypes.data_as(c_ip), _dp(dq), _dp(ip), _dp(a), _dp(b), _dp(it), _dp(r),
+                                       _dp(J1) if want_J else None, _dp(J2) if want_J else None, _dp(J3) if want_J else None))
+    return r, J1, J2, J3
 
 
 def visual_cov(model, intr, xi_board, board, feature_variance, cam_poses):

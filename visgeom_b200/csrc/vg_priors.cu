@@ -125,10 +125,19 @@ __device__ void tp_eval(const double *rec, const double *xi, double (&r)[6])
 }
 
 // ---- OdometryPrior -----------------------------------------------------------------------------------------
+__device__ void op_information(double errV, double errW, double lambda, const double *zp, double *rec);
+
 __device__ void op_setup(double errV, double errW, double lambda, const double *o1, const double *o2, double *rec)
 {
     double zp[6];
     se3_inverse_compose(o1, o2, zp);
+    op_information(errV, errW, lambda, zp, rec);
+}
+
+// rec = [zeta_prior | A]: the information matrix from the prior motion (calib_cost_functions.cpp:124-172 and, word for
+// word the same, odometry_cost_function.cpp:155-196)
+__device__ void op_information(double errV, double errW, double lambda, const double *zp, double *rec)
+{
     const double delta = fmax(sqrt(zp[3] * zp[3] + zp[4] * zp[4] + zp[5] * zp[5]), 0.01);
     const double l = fmax(sqrt(zp[0] * zp[0] + zp[1] * zp[1] + zp[2] * zp[2]), 0.01);
     double s, c;
@@ -341,6 +350,133 @@ __global__ void op_functor_kernel(int n, double errV, double errW, double lambda
         for (int k = 0; k < 36; k++) J1_out[36 * (size_t)i + k] = J1[k];
     if (J2_out)
         for (int k = 0; k < 36; k++) J2_out[36 * (size_t)i + k] = J2[k];
+}
+
+
+// ---- OdometryCost (src/calibration/odometry_cost_function.cpp; "odometry_intrinsic" blocks) ---------------------------
+// The motion between two poses of a differential-drive platform integrated from m pairs of wheel-angle increments with
+// the odometry intrinsics (r1, r2 wheel radii, g track gauge), held against xi1^-1 o xi2.
+
+// out = a o b as [t, r] (transformation.h:80-88: through quaternions)
+__device__ __forceinline__ void se3_compose(const double *a, const double *b, double *out)
+{
+    const Quat qa = quat_from_rotvec(a + 3), qb = quat_from_rotvec(b + 3);
+    double t[3];
+    quat_rotate(qa, b, t);
+    out[0] = t[0] + a[0]; out[1] = t[1] + a[1]; out[2] = t[2] + a[2];
+    quat_to_rotvec(quat_mul(qa, qb), out + 3);
+}
+
+// one increment (odom_zeta_i :10-35, zeta_i_jacobian :38-65): the planar step (v, 0, w) and d(v, -, w) / d(r1, r2, g)
+__device__ __forceinline__ void oc_step(const double *dq, const double r1, const double r2, const double g, double *step, double *jz)
+{
+    step[0] = (r1 / 2) * dq[0] + (r2 / 2) * dq[1];
+    step[1] = 0.0; step[2] = 0.0; step[3] = 0.0; step[4] = 0.0;
+    step[5] = -(r1 / g) * dq[0] + (r2 / g) * dq[1];
+    jz[0] = dq[0] / 2; jz[1] = dq[1] / 2; jz[2] = 0.0;
+    jz[3] = 0.0; jz[4] = 0.0; jz[5] = 0.0;
+    jz[6] = -dq[0] / g; jz[7] = dq[1] / g; jz[8] = (r1 * dq[0] - r2 * dq[1]) / (g * g);
+}
+
+// tf0n_jac_calc (:68-88): zeta_odo = the m steps composed
+__device__ void oc_integrate(const int m, const double *dq, const double *in, double *zeta_odo)
+{
+    double cur[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < m; i++) {
+        double step[6], jz[9], nxt[6];
+        oc_step(dq + 2 * i, in[0], in[1], in[2], step, jz);
+        se3_compose(cur, step, nxt);
+        for (int k = 0; k < 6; k++) cur[k] = nxt[k];
+    }
+    for (int k = 0; k < 6; k++) zeta_odo[k] = cur[k];
+}
+
+// calc_acc (:90-141): ACC = sum_i R(0T(i-1)) [1 0 -y; 0 1 x; 0 0 1] d zeta_i / d(r1, r2, g), (x, y) the translation of
+// iTn = (0Ti)^-1 o 0Tn.  The reference keeps every 0Ti in a vector; here the chain is walked a second time.
+__device__ void oc_accumulate(const int m, const double *dq, const double *in, const double *zeta_odo, double *acc)
+{
+    for (int k = 0; k < 9; k++) acc[k] = 0.0;
+    double prev[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < m; i++) {
+        double step[6], jz[9], cur[6], R0[9], Mu[9], tin[6];
+        oc_step(dq + 2 * i, in[0], in[1], in[2], step, jz);
+        se3_compose(prev, step, cur);
+        rodrigues_and_left_jacobian(prev[3], prev[4], prev[5], R0, Mu);
+        // (0Ti)^-1 = (-R^T t, -r) (transformation.h:112-119), then composed with 0Tn
+        double Ri[9], inv[6];
+        rodrigues_and_left_jacobian(-cur[3], -cur[4], -cur[5], Ri, Mu);
+        for (int a = 0; a < 3; a++) inv[a] = -(Ri[3 * a] * cur[0] + Ri[3 * a + 1] * cur[1] + Ri[3 * a + 2] * cur[2]);
+        inv[3] = -cur[3]; inv[4] = -cur[4]; inv[5] = -cur[5];
+        se3_compose(inv, zeta_odo, tin);
+        const double J[9] = {1, 0, -tin[1], 0, 1, tin[0], 0, 0, 1};
+        double RJ[9];
+        for (int a = 0; a < 3; a++)
+            for (int b = 0; b < 3; b++) RJ[3 * a + b] = R0[3 * a] * J[b] + R0[3 * a + 1] * J[3 + b] + R0[3 * a + 2] * J[6 + b];
+        for (int a = 0; a < 3; a++)
+            for (int b = 0; b < 3; b++) acc[3 * a + b] += RJ[3 * a] * jz[b] + RJ[3 * a + 1] * jz[3 + b] + RJ[3 * a + 2] * jz[6 + b];
+        for (int k = 0; k < 6; k++) prev[k] = cur[k];
+    }
+}
+
+// OdometryCost as a functor: one thread per block.  The first two Jacobian blocks are OdometryPrior's with the
+// integrated motion in the prior's place (:231-253); the third (:256-264) is
+// -A screwTransfInv(delta) blockdiag(R31, R31 M(zeta_odo)) [ACC rows x, y | 0 | ACC row theta].
+__global__ void oc_functor_kernel(int n, double errV, double errW, double lambda, const int *__restrict__ dq_offset,
+                                  const double *__restrict__ dq, const double *__restrict__ intr_prior, const double *x1,
+                                  const double *x2, const double *__restrict__ intr, double *r_out, double *J1_out, double *J2_out,
+                                  double *J3_out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int m = dq_offset[i + 1] - dq_offset[i];
+    const double *q = dq + 2 * (size_t)dq_offset[i];
+    double rec[OP_CONST], zp[6], zo[6], r[6], J1[36], J2[36];
+    oc_integrate(m, q, intr_prior, zp);                     // the constructor: prior motion -> A
+    op_information(errV, errW, lambda, zp, rec);
+    oc_integrate(m, q, intr, zo);
+    for (int k = 0; k < 6; k++) rec[k] = zo[k];
+    op_eval(rec, x1 + 6 * (size_t)i, x2 + 6 * (size_t)i, r, J1, J2);
+    for (int k = 0; k < 6; k++) r_out[6 * (size_t)i + k] = r[k];
+    if (J1_out)
+        for (int k = 0; k < 36; k++) J1_out[36 * (size_t)i + k] = J1[k];
+    if (J2_out)
+        for (int k = 0; k < 36; k++) J2_out[36 * (size_t)i + k] = J2[k];
+    if (!J3_out) return;
+    const double *A = rec + 6;
+    double acc[9], zeta[6], delta[6];
+    oc_accumulate(m, q, intr, zo, acc);
+    se3_inverse_compose(x1 + 6 * (size_t)i, x2 + 6 * (size_t)i, zeta);
+    se3_inverse_compose(zo, zeta, delta);
+    double R31[9], M3[9], Rd[9], Md[9], Mu[9];
+    rodrigues_and_left_jacobian(-zo[3], -zo[4], -zo[5], R31, Mu);
+    rodrigues_and_left_jacobian(zo[3], zo[4], zo[5], Mu, M3);
+    rodrigues_and_left_jacobian(-delta[3], -delta[4], -delta[5], Rd, Md);
+    // C = blockdiag(R31, R31 M3) * [ACC(0,:); ACC(1,:); 0; 0; 0; ACC(2,:)]   (6 x 3)
+    double R31M[9], Cm[18];
+    for (int a = 0; a < 3; a++)
+        for (int b = 0; b < 3; b++) R31M[3 * a + b] = R31[3 * a] * M3[b] + R31[3 * a + 1] * M3[3 + b] + R31[3 * a + 2] * M3[6 + b];
+    for (int a = 0; a < 3; a++)
+        for (int b = 0; b < 3; b++) {
+            Cm[3 * a + b] = R31[3 * a] * acc[b] + R31[3 * a + 1] * acc[3 + b];            // the third row of the top block is zero
+            Cm[3 * (a + 3) + b] = R31M[3 * a + 2] * acc[6 + b];                           // only theta's row is non-zero below
+        }
+    // D = screwTransfInv(delta) * C: [Rd, -Rd hat(t); 0, Rd]
+    const double h[9] = {0.0, -delta[2], delta[1], delta[2], 0.0, -delta[0], -delta[1], delta[0], 0.0};
+    double T[9], D[18];
+    for (int a = 0; a < 3; a++)
+        for (int b = 0; b < 3; b++) T[3 * a + b] = -(Rd[3 * a] * h[b] + Rd[3 * a + 1] * h[3 + b] + Rd[3 * a + 2] * h[6 + b]);
+    for (int a = 0; a < 3; a++)
+        for (int b = 0; b < 3; b++) {
+            double s = 0.0, w = 0.0;
+            for (int k = 0; k < 3; k++) { s += Rd[3 * a + k] * Cm[3 * k + b] + T[3 * a + k] * Cm[3 * (k + 3) + b]; w += Rd[3 * a + k] * Cm[3 * (k + 3) + b]; }
+            D[3 * a + b] = s; D[3 * (a + 3) + b] = w;
+        }
+    for (int a = 0; a < 6; a++)
+        for (int b = 0; b < 3; b++) {
+            double s = 0.0;
+            for (int k = 0; k < 6; k++) s += A[6 * a + k] * D[3 * k + b];
+            J3_out[18 * (size_t)i + 3 * a + b] = -s;
+        }
 }
 
 
@@ -759,6 +895,42 @@ int vg_eval_odometry_prior(int n, double errV, double errW, double lambda, const
     if (J1) VG_CUDA(j1.down(J1, 36 * m));
     if (J2) VG_CUDA(j2.down(J2, 36 * m));
     return VG_OK;
+}
+
+int vg_eval_odometry_cost(int n, double errV, double errW, double lambda, const int *dq_offset, const double *dq,
+                          const double *intr_prior, const double *xi1, const double *xi2, const double *intr, double *r,
+                          double *J1, double *J2, double *J3)
+{
+    if (n < 0 || (n > 0 && (!dq_offset || !dq || !intr_prior || !xi1 || !xi2 || !intr || !r)))
+        return fail(VG_ERR_INVALID, "vg_eval_odometry_cost: bad arguments");
+    for (int i = 0; i < n; i++)
+        if (dq_offset[i + 1] - dq_offset[i] < 1 || dq_offset[i] < 0)
+            return fail(VG_ERR_INVALID, "vg_eval_odometry_cost: every block needs at least one pair of increments");
+    if (!(lambda > 0.0)) return fail(VG_ERR_INVALID, "vg_eval_odometry_cost: lambda must be positive");
+    int rc = have_device();
+    if (rc || n == 0) return rc;
+    const size_t m = (size_t)n, total = (size_t)dq_offset[n];
+    DevBuf q, ip, it, x1, x2, dr, j1, j2, j3;
+    int *d_off = nullptr;
+    VG_CUDA(q.up(dq, 2 * total)); VG_CUDA(ip.up(intr_prior, 3)); VG_CUDA(it.up(intr, 3));
+    VG_CUDA(x1.up(xi1, 6 * m)); VG_CUDA(x2.up(xi2, 6 * m)); VG_CUDA(dr.alloc(6 * m));
+    if (J1) VG_CUDA(j1.alloc(36 * m));
+    if (J2) VG_CUDA(j2.alloc(36 * m));
+    if (J3) VG_CUDA(j3.alloc(18 * m));
+    VG_CUDA(cudaMalloc(&d_off, sizeof(int) * (m + 1)));
+    cudaError_t e = cudaMemcpy(d_off, dq_offset, sizeof(int) * (m + 1), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        oc_functor_kernel<<<(n + 63) / 64, 64>>>(n, errV, errW, lambda, d_off, q.p, ip.p, x1.p, x2.p, it.p, dr.p, J1 ? j1.p : nullptr,
+                                                 J2 ? j2.p : nullptr, J3 ? j3.p : nullptr);
+        count_launch(&launch_counter());
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = dr.down(r, 6 * m);
+    if (e == cudaSuccess && J1) e = j1.down(J1, 36 * m);
+    if (e == cudaSuccess && J2) e = j2.down(J2, 36 * m);
+    if (e == cudaSuccess && J3) e = j3.down(J3, 18 * m);
+    cudaFree(d_off);
+    return e == cudaSuccess ? VG_OK : fail_cuda(e, "vg_eval_odometry_cost");
 }
 
 int vg_visual_cov(int model, const double *intr, const double *xi_board, int P, const double *board, double feature_variance,
