@@ -22,6 +22,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
+#include <mutex>
 #include <queue>
 #include <utility>
 #include <vector>
@@ -377,8 +379,9 @@ private:
 };
 inline const AngleGate &angle_gate() { static const AngleGate g; return g; }
 
-// the flood's ownership map: one 16-bit candidate index per pixel (the reference's Mat16s _idxMap), kept per host thread
-// and cleared cell by cell after use -- a flood owns a few thousand pixels of the million
+// the flood's ownership map: one 16-bit candidate index per pixel (the reference's Mat16s _idxMap).  A flood owns a few
+// thousand pixels of the million, so a map is cleared cell by cell after use and handed back to a pool -- the worker
+// threads of a pass are short-lived, and a fresh 2 MB map per image would cost as much as a fifth of the flood.
 struct OwnerMap {
     std::vector<int16_t> cell;
     std::vector<uint32_t> touched;
@@ -390,6 +393,28 @@ struct OwnerMap {
     void reset() { for (uint32_t i : touched) cell[i] = -1; touched.clear(); }
 };
 
+class OwnerMapPool {
+public:
+    std::unique_ptr<OwnerMap> take()
+    {
+        std::lock_guard<std::mutex> g(mu_);
+        if (free_.empty()) return std::unique_ptr<OwnerMap>(new OwnerMap());
+        std::unique_ptr<OwnerMap> m = std::move(free_.back());
+        free_.pop_back();
+        return m;
+    }
+    void give(std::unique_ptr<OwnerMap> m)
+    {
+        std::lock_guard<std::mutex> g(mu_);
+        if (free_.size() < 64) free_.push_back(std::move(m));
+    }
+
+private:
+    std::mutex mu_;
+    std::vector<std::unique_ptr<OwnerMap>> free_;
+};
+inline OwnerMapPool &owner_maps() { static OwnerMapPool p; return p; }
+
 // constructGraph (:612-836): every candidate floods outwards along the edges that leave it (pixels whose gradient is
 // strong enough and perpendicular to the ray from the candidate); where two floods touch, the candidates are linked.
 inline void construct_graph(const Frame &F, const std::vector<Pt> &cand, const int init_radius, Graph &G)
@@ -399,7 +424,8 @@ inline void construct_graph(const Frame &F, const std::vector<Pt> &cand, const i
     G.pt = cand;
     G.arcs.assign(n, {});
     G.sign.clear();
-    static thread_local OwnerMap owner_map;
+    std::unique_ptr<OwnerMap> owner_map_ptr = owner_maps().take();
+    OwnerMap &owner_map = *owner_map_ptr;
     owner_map.prepare((size_t)F.W * F.H);
     int16_t *owner = owner_map.cell.data();
     const AngleGate &gate = angle_gate();
@@ -463,6 +489,7 @@ inline void construct_graph(const Frame &F, const std::vector<Pt> &cand, const i
         }
     }
     owner_map.reset();
+    owner_maps().give(std::move(owner_map_ptr));
 }
 
 // Eigen's Matrix<int, 2, 1>::norm(): the square root converted back to int
