@@ -115,3 +115,33 @@ def test_full_size_batch(gpu, monkeypatch):
                 assert np.array_equal(g0[k], grid), k
                 ok, refined, _, _ = ref.detect_pattern(imgs[k], improve=True)
                 assert np.abs(corners[k] - refined).max() < REFINE_TOL, k
+
+
+def test_random_pictures_against_the_reference_build(gpu):
+    """Thirty pictures of random size, camera model and noise level (boards cut by the border and pure noise among them),
+    each held against the reference build run on the box: found / not found, the integer grid exactly, the refined
+    corners to the tolerance above.  Needs oracle/_ref (it travels with the snapshot)."""
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libvisgeom_refdet.so")):
+        pytest.skip("oracle/_ref not present on this box")
+    from oracle.pyoracle import ReferenceDetector
+    ref = ReferenceDetector()
+    rng = np.random.default_rng(77)
+    n_found = 0
+    for trial in range(30):
+        w = int(rng.integers(200, 1000)); h = int(w * rng.uniform(0.6, 0.9))
+        img, _ = sd.render_board_image(w, h, seed=50000 + trial, model=(sd.EUCM, sd.MEI, sd.UCM)[trial % 3],
+                                       noise=float(rng.choice([0.5, 2.0, 6.0, 12.0])), supersample=2)
+        if trial % 7 == 3:
+            img = np.ascontiguousarray(img[:, : w * 2 // 3])
+        if trial % 11 == 5:
+            img = rng.integers(0, 256, img.shape, dtype=np.uint8)
+        ok, grid, _, _ = ref.detect_pattern(img, improve=False)
+        f0, g0 = gpu.detect_pattern(img, improve=False)
+        assert f0 == ok, trial
+        if ok:
+            n_found += 1
+            assert np.array_equal(g0, grid), trial
+            _, refined, _, _ = ref.detect_pattern(img, improve=True)
+            f1, c1 = gpu.detect_pattern(img, improve=True)
+            assert f1 and np.abs(c1 - refined).max() < REFINE_TOL, (trial, np.abs(c1 - refined).max())
+    assert n_found >= 15
