@@ -98,6 +98,12 @@ int vg_eval_chain(int model, const double *intr, int n_img, int P,
                   int chain_len, const int *status, const int *is_global,
                   const double *const *xi,
                   double *r, double *J_intr, double *const *J_xi, double *H);
+/* Optional: page-lock a caller-owned array (cudaHostRegister) so that vg_eval_chain's DMA writes it directly instead of
+ * going through a staging slot and a host memcpy -- worth it for arrays that live across many calls, as the residual /
+ * Jacobian arrays Ceres hands to CostFunction::Evaluate do.  vg_eval_chain recognises page-locked output arrays by
+ * itself (each output independently); results are identical either way.  Unregister before freeing the memory. */
+int vg_host_register(void *p, size_t bytes);
+int vg_host_unregister(void *p);
 
 int vg_eval_chain_dev(int model, const double *intr, int n_img, int P,
                       const double *board, const double *obs,

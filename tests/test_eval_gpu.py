@@ -221,3 +221,37 @@ def test_host_call_chunking(gpu, oracle, monkeypatch):
     compare_eval(g, o, "chunked stereo")
     g2 = gpu.eval_chain(*args, want_H=True, want_J=False)
     assert (g2["r"] == g["r"]).all() and (g2["H"] == g["H"]).all()
+
+
+def test_registered_output_arrays_are_written_directly(gpu):
+    """vg_host_register: page-locked output arrays take the DMA directly (no staging slot, no host memcpy); every output
+    independently -- all registered, only some, none -- and the bytes are the same in every case."""
+    s = sd.make_stereo(3000, seed=612)
+    args = (sd.EUCM, s["intr2_init"], s["board"], s["obs2"], [s["xi12_init"], s["xi_init"]], [I, D], [1, 0])
+    plain = gpu.eval_chain(*args, want_H=True)
+    out = gpu.eval_chain(*args, want_H=True)
+    for a in (out["r"], out["J_intr"], out["H"], *out["J_xi"]):
+        a[...] = -1.0
+    regs = [out["r"], out["J_intr"], out["H"], *out["J_xi"]]
+    for a in regs:
+        gpu.host_register(a)
+    try:
+        gpu.eval_chain(*args, want_H=True, out=out)
+        for k in ("r", "J_intr", "H"):
+            assert np.array_equal(out[k], plain[k]), k
+        for e in range(2):
+            assert np.array_equal(out["J_xi"][e], plain["J_xi"][e]), e
+    finally:
+        for a in regs:
+            gpu.host_unregister(a)
+    # only the largest array registered: the others still go through the staging slots
+    out["J_intr"][...] = -1.0; out["r"][...] = -1.0
+    gpu.host_register(out["J_intr"])
+    try:
+        gpu.eval_chain(*args, want_H=True, out=out)
+        assert np.array_equal(out["J_intr"], plain["J_intr"]) and np.array_equal(out["r"], plain["r"])
+        assert np.array_equal(out["J_xi"][1], plain["J_xi"][1])
+    finally:
+        gpu.host_unregister(out["J_intr"])
+    with pytest.raises(gpu.VisgeomError):
+        gpu.host_unregister(out["r"])                      # not registered: the CUDA error comes back as a message

@@ -77,6 +77,8 @@ def lib() -> C.CDLL:
                                      C.POINTER(C.c_longlong)]
     L.vg_corner_response_dev.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.vg_host_register.argtypes = [C.c_void_p, C.c_size_t]
+    L.vg_host_unregister.argtypes = [C.c_void_p]
     L.vg_detect_pattern.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.vg_detector_host_stages.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                           C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -334,6 +336,16 @@ def corner_response(imgs, sigma1=0.7, sigma2=1.4):
 
 def _vp(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+def host_register(a):
+    """Page-lock a numpy array the caller keeps across calls (vg_host_register): eval_chain(..., out=...) then lets the
+    DMA write it directly."""
+    _check(lib().vg_host_register(a.ctypes.data_as(C.c_void_p), a.nbytes))
+
+
+def host_unregister(a):
+    _check(lib().vg_host_unregister(a.ctypes.data_as(C.c_void_p)))
 
 
 def detect_pattern(imgs, nx=9, ny=6, improve=True):

@@ -7,6 +7,8 @@
 //     DMA at PCIe speed into pinned memory, never a pageable cudaMemcpy (which the driver stages and serialises);
 //   * that last hop is a plain memcpy at host memory speed: for large calls a few helper threads (VG_HOST_COPY_THREADS,
 //     default min(8, cores / 2), alive for the duration of the call) share it with the calling thread;
+//   * an output array that is page-locked (the caller pinned it once with vg_host_register: Ceres keeps its Jacobian
+//     arrays for the whole solve) is written by the DMA itself, without the staging hop and the memcpy;
 //   * all state -- streams, events, pinned slots, device workspace -- belongs to the CALLING THREAD (thread_local):
 //     Ceres may evaluate residual blocks from num_threads threads at once.
 // No CPU path: without a CUDA device the call fails with VG_ERR_CUDA.
@@ -118,12 +120,21 @@ struct HostCtx {
 thread_local std::unique_ptr<HostCtx> t_ctx;
 
 // one contiguous piece of a chunk's outputs: pinned staging offset -> the caller's array
-struct Piece { size_t off; char *user; size_t per_img; };
+// direct: the caller's array is page-locked (vg_host_register, or allocated pinned): the DMA writes it, no staging hop
+struct Piece { size_t off; char *user; size_t per_img; bool direct; };
+
+bool page_locked(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
 
 // copy-out of a chunk, shared between the calling thread (part 0) and the helpers (parts 1 .. T-1)
 void copy_share(const std::vector<Piece> &pieces, const char *h_out, size_t img0, size_t m, int part, int parts)
 {
     for (const Piece &p : pieces) {
+        if (p.direct) continue;
         const size_t bytes = m * p.per_img;
         const size_t lo = bytes * part / parts & ~size_t(63), hi = part + 1 == parts ? bytes : (bytes * (part + 1) / parts & ~size_t(63));
         if (hi > lo) memcpy(p.user + img0 * p.per_img + lo, h_out + p.off + lo, hi - lo);
@@ -144,6 +155,21 @@ void release_host_ctx() { t_ctx.reset(); }
 }  // namespace vg
 
 using namespace vg;
+
+extern "C" int vg_host_register(void *p, size_t bytes)
+{
+    if (!p || bytes == 0) return fail(VG_ERR_INVALID, "vg_host_register: null pointer or empty range");
+    if (vg_device_count() < 1) return fail(VG_ERR_CUDA, "no CUDA device: this engine has no CPU path");
+    const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    return e == cudaSuccess ? VG_OK : fail_cuda(e, "vg_host_register");
+}
+
+extern "C" int vg_host_unregister(void *p)
+{
+    if (!p) return fail(VG_ERR_INVALID, "vg_host_unregister: null pointer");
+    const cudaError_t e = cudaHostUnregister(p);
+    return e == cudaSuccess ? VG_OK : fail_cuda(e, "vg_host_unregister");
+}
 
 extern "C" int vg_eval_chain(int model, const double *intr, int n_img, int P,
                              const double *board, const double *obs,
@@ -183,7 +209,10 @@ extern "C" int vg_eval_chain(int model, const double *intr, int n_img, int P,
     if (CH > (size_t)n_img) CH = (size_t)n_img;
     const int chunks = (int)(((size_t)n_img + CH - 1) / CH);
     size_t off = 0;
-    auto add_piece = [&](double *user, size_t per) { pieces.push_back(Piece{off, reinterpret_cast<char *>(user), per}); off += up(CH * per); };
+    auto add_piece = [&](double *user, size_t per) {
+        pieces.push_back(Piece{off, reinterpret_cast<char *>(user), per, page_locked(user)});
+        off += up(CH * per);
+    };
     if (r) add_piece(r, row_bytes);
     if (J_intr) add_piece(J_intr, row_bytes * K);
     for (int e = 0; e < chain_len; e++)
@@ -224,7 +253,10 @@ extern "C" int vg_eval_chain(int model, const double *intr, int n_img, int P,
         if (hw > 0 && t > hw) t = hw;
         return t < 1 ? 1 : t;
     }();
-    const size_t total_out = (size_t)n_img * out_per;
+    size_t staged_per = 0;
+    for (const Piece &p : pieces)
+        if (!p.direct) staged_per += p.per_img;
+    const size_t total_out = (size_t)n_img * staged_per;           // what still goes through the pinned slots
     const int parts = total_out >= ((size_t)8 << 20) ? max_helpers : 1;
     Team team(chunks);
     std::vector<std::thread> helpers;
@@ -285,7 +317,8 @@ extern "C" int vg_eval_chain(int model, const double *intr, int n_img, int P,
         ce = launch_eval(model, chain_len, a, s.st, &launch_counter());
         if (ce != cudaSuccess) return finish(fail_cuda(ce, "reproj_eval_kernel launch"));
         for (const Piece &p : pieces) {
-            ce = cudaMemcpyAsync(s.h_out + p.off, s.d_out + p.off, m * p.per_img, cudaMemcpyDeviceToHost, s.st);
+            ce = cudaMemcpyAsync(p.direct ? p.user + i0 * p.per_img : s.h_out + p.off, s.d_out + p.off, m * p.per_img,
+                                 cudaMemcpyDeviceToHost, s.st);
             if (ce != cudaSuccess) return finish(fail_cuda(ce, "vg_eval_chain: download"));
         }
         ce = cudaEventRecord(s.done, s.st);
