@@ -82,7 +82,7 @@ def calib_probe(tmp_path_factory, vg):
     lib_dir = os.path.join(ROOT, "visgeom_b200")
     subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "include"),
                            "-I" + os.path.join(lib_dir, "host"), os.path.join(ROOT, "tests", "calib_probe.cpp"),
-                           os.path.join(lib_dir, "host", "calibration.cpp"), "-o", exe, "-L" + lib_dir, "-lvisgeom_b200", "-lz",
+                           os.path.join(lib_dir, "host", "calibration.cpp"), "-o", exe, "-L" + lib_dir, "-lvisgeom_b200", "-lz", "-lpthread",
                            "-Wl,-rpath," + lib_dir])
 
     def run(path):

@@ -78,7 +78,7 @@ def build_cli(force: bool = False) -> str:
     if force or _stale(CLI, deps):
         os.makedirs(os.path.dirname(CLI), exist_ok=True)
         subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-I" + INCLUDE, "-I" + HOST] + srcs +
-                              ["-o", CLI, "-L" + HERE, "-lvisgeom_b200", "-lz", "-Wl,-rpath,$ORIGIN/.."])
+                              ["-o", CLI, "-L" + HERE, "-lvisgeom_b200", "-lz", "-lpthread", "-Wl,-rpath,$ORIGIN/.."])
     return CLI
 
 

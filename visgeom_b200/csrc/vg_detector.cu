@@ -323,10 +323,11 @@ subpixel_evaluate_kernel(const float *__restrict__ gradx, const float *__restric
 // ---- pipeline ---------------------------------------------------------------------------------------------------------
 // Images go through in passes of a few images.  A pass = upload, response + scan on the GPU, the blurred images and the
 // maxima back, the host stages (one image per thread), the refinement of the grids found (while that pass's gradient
-// maps are still on the device), results out.  LANES passes are in flight at once, each on its own stream and buffers
+// maps are still on the device), results out.  DEFAULT_LANES passes are in flight at once, each on its own stream and buffers
 // and driven by its own host thread, so the copies and kernels of one pass run under the host stages of the others.
 // Buffers are kept between calls (grow only).
-constexpr int LANES = 3;
+constexpr int MAX_LANES = 6;
+constexpr int DEFAULT_LANES = 4;        // VG_DETECT_LANES overrides (developer knob)
 
 struct Lane {
     unsigned char *img = nullptr, *s1 = nullptr, *s2 = nullptr;
@@ -403,7 +404,7 @@ struct Lane {
 
 struct Pipeline {
     std::mutex mu;                      // one vg_detect_pattern at a time per process
-    Lane lane[LANES];
+    Lane lane[MAX_LANES];
 };
 Pipeline &pipeline() { static Pipeline p; return p; }
 
@@ -556,7 +557,9 @@ int vg_detect_pattern(const unsigned char *img, int n_img, int width, int height
     VG_CUDA(cudaGetDevice(&dev));
     Pipeline &pl = pipeline();
     std::lock_guard<std::mutex> lock(pl.mu);
-    const int lanes = std::max(1, std::min(LANES, (n_img + chunk - 1) / chunk));
+    int want_lanes = DEFAULT_LANES;
+    if (const char *e = std::getenv("VG_DETECT_LANES")) want_lanes = std::max(1, std::min(MAX_LANES, std::atoi(e)));
+    const int lanes = std::max(1, std::min(want_lanes, (n_img + chunk - 1) / chunk));
     for (int l = 0; l < lanes; l++) VG_CUDA(pl.lane[l].reserve(dev, width, height, chunk, P, cap));
     const Request q{img, width, height, Nx, Ny, improve, corners, found, hw};
     std::vector<int> pending(n_img);

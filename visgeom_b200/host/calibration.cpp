@@ -3,11 +3,13 @@
 #include "visgeom_b200/calibration.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <fstream>
 #include <iostream>
 #include <stdexcept>
+#include <thread>
 
 #include "image_io.hpp"
 #include "json.hpp"
@@ -225,12 +227,23 @@ void GenericCameraCalibration::extractGridProjections(ImageData &data)
     data.detectedCornersVec.assign(n, {});
     vector<Mat8u> frames(n);
     vector<string> error(n);
-    for (int i = 0; i < n; i++) {
-        if (initialized && !(i < (int)initVec.size() && initVec[i])) {
+    for (int i = 0; i < n; i++)
+        if (initialized && !(i < (int)initVec.size() && initVec[i]))
             error[i] = " : ERROR, the pattern has not been found on the corresponding image";
-            continue;
-        }
-        frames[i] = image_io::imread_grey(data.imageNameVec[i]);
+    {   // decoding is the slow part of this function once the detector runs on the GPU: all cores read pictures
+        std::atomic<int> next(0);
+        auto reader = [&] {
+            for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1))
+                if (error[i].empty()) frames[i] = image_io::imread_grey(data.imageNameVec[i]);
+        };
+        const int nt = std::max(1, std::min(n, (int)std::thread::hardware_concurrency()));
+        vector<std::thread> pool;
+        for (int t = 1; t < nt; t++) pool.emplace_back(reader);
+        reader();
+        for (std::thread &t : pool) t.join();
+    }
+    for (int i = 0; i < n; i++) {
+        if (!error[i].empty()) continue;
         if (frames[i].empty()) error[i] = " : ERROR, file not found";
         else if (data.imageWidth == 0) { data.imageWidth = frames[i].cols; data.imageHeight = frames[i].rows; }
     }
