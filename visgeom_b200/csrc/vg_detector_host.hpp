@@ -382,15 +382,24 @@ inline const AngleGate &angle_gate() { static const AngleGate g; return g; }
 // the flood's ownership map: one 16-bit candidate index per pixel (the reference's Mat16s _idxMap).  A flood owns a few
 // thousand pixels of the million, so a map is cleared cell by cell after use and handed back to a pool -- the worker
 // threads of a pass are short-lived, and a fresh 2 MB map per image would cost as much as a fifth of the flood.
+// `judged` remembers, per pixel, the last candidate whose flood has tested it (+(idx + 1): queued, -(idx + 1): refused).
+// The reference tests and queues a pixel again from every neighbour that is popped (five times on average); the test is
+// a function of pixel and candidate alone, and a second queued copy is popped after the first, when the pixel is owned
+// -- a no-op either way -- so skipping the repeats changes neither the ownership map nor the order of the arcs.
 struct OwnerMap {
-    std::vector<int16_t> cell;
-    std::vector<uint32_t> touched;
+    std::vector<int16_t> cell, judged;
+    std::vector<uint32_t> touched, touched_judged;
     void prepare(const size_t n)
     {
-        if (cell.size() < n) cell.assign(n, (int16_t)-1);
-        touched.clear();
+        if (cell.size() < n) { cell.assign(n, (int16_t)-1); judged.assign(n, (int16_t)0); }
+        touched.clear(); touched_judged.clear();
     }
-    void reset() { for (uint32_t i : touched) cell[i] = -1; touched.clear(); }
+    void reset()
+    {
+        for (uint32_t i : touched) cell[i] = -1;
+        for (uint32_t i : touched_judged) judged[i] = 0;
+        touched.clear(); touched_judged.clear();
+    }
 };
 
 class OwnerMapPool {
@@ -427,7 +436,7 @@ inline void construct_graph(const Frame &F, const std::vector<Pt> &cand, const i
     std::unique_ptr<OwnerMap> owner_map_ptr = owner_maps().take();
     OwnerMap &owner_map = *owner_map_ptr;
     owner_map.prepare((size_t)F.W * F.H);
-    int16_t *owner = owner_map.cell.data();
+    int16_t *owner = owner_map.cell.data(), *judged = owner_map.judged.data();
     const AngleGate &gate = angle_gate();
     std::vector<double> grad_min(n);
     std::queue<Cell> fringe;
@@ -477,7 +486,12 @@ inline void construct_graph(const Frame &F, const std::vector<Pt> &cand, const i
         for (int k = 0; k < 8; k++) {
             const int u2 = e.u + du8[k], v2 = e.v + dv8[k];
             if (u2 < 0 || u2 >= F.W || v2 < 0 || v2 >= F.H) continue;
-            if (owner[(size_t)v2 * F.W + u2] != -1) continue;
+            const size_t at2 = (size_t)v2 * F.W + u2;
+            if (owner[at2] != -1) continue;
+            const int16_t tag = (int16_t)(e.idx + 1), was = judged[at2];
+            if (was == tag || was == -tag) continue;                // this flood has judged the pixel already
+            if (was == 0) owner_map.touched_judged.push_back((uint32_t)at2);
+            judged[at2] = -tag;
             const int ix = u2 - G.pt[e.idx].u, iy = v2 - G.pt[e.idx].v;
             const double x1 = ix, y1 = iy;
             const double t = std::sqrt(x1 * x1 + y1 * y1);
@@ -485,6 +499,7 @@ inline void construct_graph(const Frame &F, const std::vector<Pt> &cand, const i
             const double across = std::fabs(xg * y1 - yg * x1);
             if (t > 0 && across / t < grad_min[e.idx]) continue;
             if (t > 0 && !gate.accepts(ix * ix + iy * iy, t, x1 * xg + y1 * yg, x1 * yg - y1 * xg)) continue;
+            judged[at2] = tag;
             fringe.push(Cell{e.t + 1, e.idx, u2, v2});
         }
     }
@@ -597,7 +612,7 @@ inline std::vector<Pt> detect_at_scale(const Frame &F, std::vector<Maximum> &max
     const std::vector<Pt> cand = select_candidates(F, maxima, Nx, Ny, init_radius);
     std::vector<Pt> out;
     if ((int)cand.size() < Nx * Ny) return out;
-    if (cand.size() > 32767) return out;               // the reference's index map is 16-bit; 10 Nx Ny candidates at most
+    if (cand.size() > 32766) return out;               // the reference's index map is 16-bit; 10 Nx Ny candidates at most
     Graph G;
     construct_graph(F, cand, init_radius, G);
     const std::vector<int> idx = select_pattern(G, Nx, Ny);
