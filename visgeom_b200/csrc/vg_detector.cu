@@ -17,7 +17,10 @@
 
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
+#include <deque>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -408,16 +411,76 @@ struct Pipeline {
 };
 Pipeline &pipeline() { static Pipeline p; return p; }
 
-template <typename Fn> void parallel_for(const int n, const int threads, Fn fn)
-{
-    const int nt = std::max(1, std::min(n, threads));
-    if (nt == 1) { for (int i = 0; i < n; i++) fn(i); return; }
-    std::atomic<int> next(0);
-    std::vector<std::thread> pool;
-    for (int t = 0; t < nt; t++)
-        pool.emplace_back([&] { for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) fn(i); });
-    for (auto &th : pool) th.join();
-}
+// The host threads of the pipeline: one pool for all lanes, alive for the process, so that the images of whichever
+// pass is ready keep every core busy (a pool per pass would idle at each pass's slowest image and pay its threads'
+// start-up sixteen times per call).
+class Workers {
+public:
+    static Workers &get() { static Workers w; return w; }
+    // fn(0) .. fn(n - 1) on the pool; returns when all are done.  The caller helps.
+    template <typename Fn> void run(const int n, Fn fn)
+    {
+        if (n <= 0) return;
+        Batch b;
+        b.fn = [&](int i) { fn(i); };
+        b.n = n;
+        std::unique_lock<std::mutex> g(mu_);
+        ensure_threads();
+        queue_.push_back(&b);
+        cv_.notify_all();
+        process(&b, g);
+        b.done_cv.wait(g, [&] { return b.finished == b.n; });
+    }
+
+private:
+    struct Batch {
+        std::function<void(int)> fn;
+        int n = 0, next = 0, finished = 0;           // guarded by mu_
+        std::condition_variable done_cv;
+    };
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<Batch *> queue_;                      // batches with unclaimed items
+    std::vector<std::thread> threads_;
+    bool stop_ = false;
+
+    void ensure_threads()
+    {
+        if (!threads_.empty()) return;
+        const int hw = std::max(2, (int)std::thread::hardware_concurrency());
+        for (int t = 0; t < hw - 1; t++) threads_.emplace_back([this] { loop(); });
+    }
+    // Claim and run items of b until none is left to claim.  mu_ is held on entry and on exit.  A batch lives on its
+    // owner's stack until finished == n, so it is only touched while that cannot be the case: under the lock, and
+    // never again after the increment that completes it.
+    void process(Batch *b, std::unique_lock<std::mutex> &g)
+    {
+        while (b->next < b->n) {
+            const int i = b->next++;
+            if (b->next == b->n) queue_.erase(std::find(queue_.begin(), queue_.end(), b));
+            g.unlock();
+            b->fn(i);
+            g.lock();
+            if (++b->finished == b->n) { b->done_cv.notify_all(); return; }
+        }
+    }
+    void loop()
+    {
+        std::unique_lock<std::mutex> g(mu_);
+        for (;;) {
+            cv_.wait(g, [&] { return stop_ || !queue_.empty(); });
+            if (stop_) return;
+            process(queue_.front(), g);
+        }
+    }
+    Workers() {}
+    ~Workers()
+    {
+        { std::lock_guard<std::mutex> g(mu_); stop_ = true; }
+        cv_.notify_all();
+        for (std::thread &t : threads_) t.join();
+    }
+};
 
 struct Request {
     const unsigned char *img;
@@ -455,7 +518,7 @@ std::string run_pass(Lane &B, const Request &q, const int *ids, const int np, co
     const int R = (int)std::round(1.5 * sigma2);                    // INIT_RADIUS (:231)
     cudaStream_t st = B.st;
     // staged through pinned memory: the caller's pageable pages would serialise the lanes inside the driver
-    for (int i = 0; i < np; i++) std::memcpy(B.h_img + (size_t)i * N, q.img + (size_t)ids[i] * N, N);
+    Workers::get().run(np, [&](const int i) { std::memcpy(B.h_img + (size_t)i * N, q.img + (size_t)ids[i] * N, N); });
     lap(0);
     DET_CUDA(cudaMemcpyAsync(B.img, B.h_img, N * np, cudaMemcpyHostToDevice, st));
     if (corner_response_launch(B.img, np, W, H, 0.7, sigma2, B.resp, B.gradx, B.grady, nullptr, B.s1, B.s2, B.avg, nullptr, st,
@@ -485,7 +548,7 @@ std::string run_pass(Lane &B, const Request &q, const int *ids, const int np, co
     std::vector<std::vector<det::Pt>> grids(np);
     std::vector<unsigned char> job_ok((size_t)np * P, 0);
     std::vector<RefineJob> jobs((size_t)np * P);
-    parallel_for(np, q.host_threads, [&](const int i) {
+    Workers::get().run(np, [&](const int i) {
         const det::Frame F{B.h_img + (size_t)i * N, B.h_s1 + (size_t)i * N, B.h_s2 + (size_t)i * N, W, H};
         std::vector<det::Maximum> mx(B.h_maxima + (size_t)i * B.cap, B.h_maxima + (size_t)i * B.cap + B.h_count[i]);
         grids[i] = det::detect_at_scale(F, mx, q.Nx, q.Ny, R);
