@@ -1194,3 +1194,73 @@ int vgo_evaluate_batch(int model, const double *intr, int n_img, int P,
     }
     return 0;
 }
+
+/* ------------------------------------------------------------------ */
+/* Batch loops for the CPU-baseline timings of the rows around the hot path (tools/aux_timing.py): what a caller of the
+ * reference does per point / per block, over n of them, OpenMP over the items. */
+
+/* ICamera::projectPoint + projectionJacobian + intrinsicJacobian per point (generic_camera.h:39-50) */
+void vgo_project_batch(int model, const double *params, long n, const double *X, double *uv, double *dPdX, double *dPdintr,
+                       unsigned char *ok, int threads)
+{
+    const int K = vgo_num_params(model);
+    (void)threads;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(threads > 1 ? threads : 1)
+#endif
+    for (long i = 0; i < n; i++) {
+        ok[i] = (unsigned char)vgo_project(model, params, X + 3 * i, uv + 2 * i);
+        vgo_projection_jacobian(model, params, X + 3 * i, dPdX + 6 * i, dPdX + 6 * i + 3);
+        vgo_intrinsic_jacobian(model, params, X + 3 * i, dPdintr + 2 * (size_t)K * i, dPdintr + 2 * (size_t)K * i + K);
+    }
+}
+
+/* TransformationPrior / OdometryPrior: functors built once (init), then Evaluate over all blocks -- the timed part */
+void vgo_transformation_prior_batch(int n, const double *stiffness, const double *xi_prior, const double *xi, double *r, double *J,
+                                    int reps, int threads)
+{
+    vgo_transformation_prior *tp = (vgo_transformation_prior *)malloc(sizeof(*tp) * (size_t)n);
+    for (int i = 0; i < n; i++) vgo_transformation_prior_init(tp + i, stiffness + 6 * i, xi_prior + 6 * i);
+    (void)threads;
+    for (int k = 0; k < reps; k++) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(threads > 1 ? threads : 1)
+#endif
+        for (int i = 0; i < n; i++) vgo_transformation_prior_eval(tp + i, xi + 6 * i, r + 6 * i, J + 36 * (size_t)i);
+    }
+    free(tp);
+}
+
+void vgo_odometry_prior_batch(int n, double errV, double errW, double lambda, const double *o1, const double *o2, const double *x1,
+                              const double *x2, double *r, double *J1, double *J2, int reps, int threads)
+{
+    vgo_odometry_prior *op = (vgo_odometry_prior *)malloc(sizeof(*op) * (size_t)n);
+    for (int i = 0; i < n; i++) vgo_odometry_prior_init(op + i, errV, errW, lambda, o1 + 6 * i, o2 + 6 * i);
+    (void)threads;
+    for (int k = 0; k < reps; k++) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(threads > 1 ? threads : 1)
+#endif
+        for (int i = 0; i < n; i++) vgo_odometry_prior_eval(op + i, x1 + 6 * i, x2 + 6 * i, r + 6 * i, J1 + 36 * (size_t)i, J2 + 36 * (size_t)i);
+    }
+    free(op);
+}
+
+void vgo_odometry_cost_batch(int n, double errV, double errW, double lambda, const int *dq_offset, const double *dq,
+                             const double *intr_prior, const double *x1, const double *x2, const double *intr, double *r,
+                             double *J1, double *J2, double *J3, int reps, int threads)
+{
+    vgo_odometry_prior *oc = (vgo_odometry_prior *)malloc(sizeof(*oc) * (size_t)n);
+    for (int i = 0; i < n; i++)
+        vgo_odometry_cost_init(oc + i, errV, errW, lambda, dq_offset[i + 1] - dq_offset[i], dq + 2 * (size_t)dq_offset[i], intr_prior);
+    (void)threads;
+    for (int k = 0; k < reps; k++) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(threads > 1 ? threads : 1)
+#endif
+        for (int i = 0; i < n; i++)
+            vgo_odometry_cost_eval(oc + i, dq_offset[i + 1] - dq_offset[i], dq + 2 * (size_t)dq_offset[i], x1 + 6 * i, x2 + 6 * i, intr,
+                                   r + 6 * i, J1 + 36 * (size_t)i, J2 + 36 * (size_t)i, J3 + 18 * (size_t)i);
+    }
+    free(oc);
+}

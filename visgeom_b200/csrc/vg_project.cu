@@ -3,7 +3,8 @@
 //   ICamera::projectPoint / projectionJacobian / intrinsicJacobian   generic_camera.h:39-50
 //   ICamera::projectPointCloud / reconstructPointCloud               generic_camera.h:64-113
 //   EnhancedCamera / UnifiedCamera / MeiCamera                       eucm.h:85-226, ucm.h:81-197, mei.h:90-285
-// batched over points: one thread per point, the same Camera<MODEL>::eval the calibration kernel uses (projection,
+// batched over points: one thread per point (a warp per 32 consecutive points, their structs moved through shared-memory
+// tiles so that global memory is touched in whole runs), the same Camera<MODEL>::eval the calibration kernel uses (projection,
 // dP/dX and dP/dintrinsics share rho, eta and their reciprocals).  HBM-bound: 24 B in, up to 16 + 48 + 16 K + 1 B out
 // per point.  There is no CPU path.
 #include "vg_common.h"
@@ -14,57 +15,100 @@
 namespace vg {
 namespace {
 
+// The arrays are arrays of small structs (3 doubles in; 2, 6 and 2 K doubles out per point): a thread that reads and
+// writes its own point's struct touches memory 24 ... 160 bytes apart from its neighbour's, a fraction of every sector
+// it moves.  So a warp takes 32 consecutive points, whose structs are one contiguous run of each array, and moves each
+// run through a shared-memory tile: the lanes read / write the run element by element (coalesced), each lane picks up
+// or drops its own struct in the tile (row pitch odd: no bank conflicts).
+constexpr int PP_WARPS = 8;
+
+template <int W>      // doubles per point
+__device__ __forceinline__ void tile_to_global(const double *tile, double *g, const long long p0, const int np, const int lane)
+{
+    for (int e = lane; e < np * W; e += 32) g[p0 * W + e] = tile[(e / W) * (W + 1) + e % W];
+}
+
 template <int MODEL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * PP_WARPS)
 project_points_kernel(const double *__restrict__ intr_g, const long long n, const double *__restrict__ X,
                       double *__restrict__ uv, double *__restrict__ dPdX, double *__restrict__ dPdintr,
                       unsigned char *__restrict__ ok_out)
 {
     using CAM = Camera<MODEL>;
     constexpr int K = CAM::K;
+    __shared__ double tiles[PP_WARPS][32 * (2 * K + 1)];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double *tile = tiles[wib];
     double intr[K];
 #pragma unroll
     for (int i = 0; i < K; i++) intr[i] = __ldg(intr_g + i);
     const typename CAM::Consts cc = CAM::prepare(intr);
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const double x = X[3 * i], y = X[3 * i + 1], z = X[3 * i + 2];
-        double u, v, Pu[3], Pv[3], Ju[K], Jv[K];
-        const bool ok = CAM::eval(intr, cc, x, y, z, u, v, Pu, Pv, Ju, Jv);
-        if (ok_out) ok_out[i] = ok ? 1 : 0;
+    const long long warps = (long long)gridDim.x * PP_WARPS, wid = (long long)blockIdx.x * PP_WARPS + wib;
+    for (long long p0 = wid * 32; p0 < n; p0 += warps * 32) {
+        const int np = (int)min(32LL, n - p0);
+        for (int e = lane; e < np * 3; e += 32) tile[(e / 3) * 4 + e % 3] = X[p0 * 3 + e];
+        __syncwarp();
+        const double x = tile[lane * 4], y = tile[lane * 4 + 1], z = tile[lane * 4 + 2];
+        __syncwarp();
+        double u = 0, v = 0, Pu[3], Pv[3], Ju[K], Jv[K];
+        bool ok = false;
+        if (lane < np) ok = CAM::eval(intr, cc, x, y, z, u, v, Pu, Pv, Ju, Jv);
+        const unsigned okmask = __ballot_sync(0xffffffffu, ok);
+        if (ok_out && lane < np) ok_out[p0 + lane] = ok ? 1 : 0;
         // a failed projection leaves the image point alone and zero Jacobians (eucm.h:46-54,141-150,198-206)
-        if (uv && ok) { uv[2 * i] = u; uv[2 * i + 1] = v; }
-        if (dPdX) {
-#pragma unroll
-            for (int q = 0; q < 3; q++) { dPdX[6 * i + q] = ok ? Pu[q] : 0.0; dPdX[6 * i + 3 + q] = ok ? Pv[q] : 0.0; }
-        }
         if (dPdintr) {
 #pragma unroll
-            for (int q = 0; q < K; q++) { dPdintr[2 * K * i + q] = ok ? Ju[q] : 0.0; dPdintr[2 * K * i + K + q] = ok ? Jv[q] : 0.0; }
+            for (int q = 0; q < K; q++) { tile[lane * (2 * K + 1) + q] = ok ? Ju[q] : 0.0; tile[lane * (2 * K + 1) + K + q] = ok ? Jv[q] : 0.0; }
+            __syncwarp();
+            tile_to_global<2 * K>(tile, dPdintr, p0, np, lane);
+            __syncwarp();
+        }
+        if (dPdX) {
+#pragma unroll
+            for (int q = 0; q < 3; q++) { tile[lane * 7 + q] = ok ? Pu[q] : 0.0; tile[lane * 7 + 3 + q] = ok ? Pv[q] : 0.0; }
+            __syncwarp();
+            tile_to_global<6>(tile, dPdX, p0, np, lane);
+            __syncwarp();
+        }
+        if (uv) {
+            tile[lane * 3] = u; tile[lane * 3 + 1] = v;
+            __syncwarp();
+            for (int e = lane; e < np * 2; e += 32)
+                if (okmask >> (e >> 1) & 1u) uv[p0 * 2 + e] = tile[(e >> 1) * 3 + (e & 1)];
+            __syncwarp();
         }
     }
 }
 
 // back-projection: EUCM eucm.h:85-106; UCM ucm.h:81-103 and MEI mei.h:90-112 (the reference ignores the distortion
-// terms there) share g = sqrt(1 + u2 (1 - xi^2))
+// terms there) share g = sqrt(1 + u2 (1 - xi^2)).  Same tiling as above.
 template <int MODEL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * PP_WARPS)
 reconstruct_points_kernel(const double *__restrict__ intr_g, const long long n, const double *__restrict__ uv,
                           double *__restrict__ X, unsigned char *__restrict__ ok_out)
 {
     constexpr int K = Camera<MODEL>::K;
+    __shared__ double tiles[PP_WARPS][32 * 4];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double *tile = tiles[wib];
     double p[K];
 #pragma unroll
     for (int i = 0; i < K; i++) p[i] = __ldg(intr_g + i);
     const double fu = p[K - 4], fv = p[K - 3], u0 = p[K - 2], v0 = p[K - 1];
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const double xn = (uv[2 * i] - u0) / fu, yn = (uv[2 * i + 1] - v0) / fv;
+    const long long warps = (long long)gridDim.x * PP_WARPS, wid = (long long)blockIdx.x * PP_WARPS + wib;
+    for (long long p0 = wid * 32; p0 < n; p0 += warps * 32) {
+        const int np = (int)min(32LL, n - p0);
+        for (int e = lane; e < np * 2; e += 32) tile[(e >> 1) * 3 + (e & 1)] = uv[p0 * 2 + e];
+        __syncwarp();
+        const double xn = (tile[lane * 3] - u0) / fu, yn = (tile[lane * 3 + 1] - v0) / fv;
+        __syncwarp();
         const double u2 = xn * xn + yn * yn;
-        bool ok = true;
+        bool ok = lane < np;
         double zz;
         if (MODEL == MODEL_EUCM) {
             const double alpha = p[0], beta = p[1], gamma = 1.0 - alpha;
             const double det = 1.0 - (alpha - gamma) * beta * u2;
-            ok = !(det < 0.0);
+            ok = ok && !(det < 0.0);
             zz = (1.0 - u2 * alpha * alpha * beta) / (gamma + alpha * sqrt(det));
         } else {
             const double xi = p[0];
@@ -72,8 +116,13 @@ reconstruct_points_kernel(const double *__restrict__ intr_g, const long long n, 
             const double en = -g - xi * u2, ed = xi * xi * u2 - 1.0;
             zz = ed / (ed + xi * en);
         }
-        if (ok_out) ok_out[i] = ok ? 1 : 0;
-        if (ok) { X[3 * i] = xn; X[3 * i + 1] = yn; X[3 * i + 2] = zz; }     // (a failed point is left alone, eucm.h:100)
+        const unsigned okmask = __ballot_sync(0xffffffffu, ok);
+        if (ok_out && lane < np) ok_out[p0 + lane] = ok ? 1 : 0;
+        tile[lane * 4] = xn; tile[lane * 4 + 1] = yn; tile[lane * 4 + 2] = zz;
+        __syncwarp();
+        for (int e = lane; e < np * 3; e += 32)                        // (a failed point is left alone, eucm.h:100)
+            if (okmask >> (e / 3) & 1u) X[p0 * 3 + e] = tile[(e / 3) * 4 + e % 3];
+        __syncwarp();
     }
 }
 
@@ -85,7 +134,7 @@ int grid_for(long long n)
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long blocks = (n + 255) / 256;
-    const long long cap = (long long)sms * 8;           // a multiple of the SM count; grid-stride beyond it
+    const long long cap = (long long)sms * 5;           // a multiple of the SM count (5 CTAs of 40 KB tiles fit an SM)
     return (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
 }
 
