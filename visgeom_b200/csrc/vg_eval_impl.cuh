@@ -727,11 +727,19 @@ reproj_eval_kernel(const EvalArgs args, const int G_rt, const int PCG_rt)
         }
     };
 
-    // Programmatic dependent launch: the next kernel of the stream may take this CTA's SM slot as soon as it is
-    // free and run its own prologue (above) under this grid's tail; nothing of global memory is touched before
-    // the grids this launch depends on have completed and flushed.
+    // Programmatic dependent launch: the next kernel of the stream may take this CTA's SM slot as soon as it is free.
+    // Which grids can be ahead of this one and still running?  Only evaluation launches -- they are the only kernels
+    // that release their dependents early; behind any other kernel this launch starts when that one has completed.
+    // An evaluation writes residuals, Jacobians, per-image blocks and, in its tail, the reduction's scratch and result:
+    // never what another evaluation READS in its main loop (observations, board, camera, poses).  So the main loop
+    // need not wait for the launch ahead: it runs under that launch's stragglers (2 500 groups over 592 CTAs are 4.2
+    // rounds: a fifth of the SM slots idle through the last one) and under its reduction tail, and waits only before
+    // it touches the reduction's scratch itself.  (Two launches on the same buffers write the same bytes.)  Exceptions
+    // that wait at the head: the LM loop on the device (its state and the poses come from the kernels ahead) and the CTA
+    // that collects a deferred peer exchange (it reads the previous launch's result).  VG_LATE_WAIT=0: always at the head.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const bool wait_at_head = LMD || !args.late_wait || (args.collect.n > 1 && blockIdx.x == gridDim.x - 1);
+    if (wait_at_head) asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // the LM loop on the device (vg_lm_dev.cuh).  A candidate's evaluation (mode 2): is the solve over (this launch was queued
     // ahead of the decision), or is only the gradient test due?  The two words are in flight while the prologue below
@@ -980,6 +988,9 @@ reproj_eval_kernel(const EvalArgs args, const int G_rt, const int PCG_rt)
     }
     if (tid == T0) bulk_wait_read_all();        // shared memory must outlive the TMA reads
     VG_PC_FLUSH_ALL
+    // (late wait, see the head: from here on the launch ahead must be over -- the reduction's scratch is shared with it,
+    // and a grid must not complete before the grid ahead of it in the stream has)
+    if (!wait_at_head) asm volatile("griddepcontrol.wait;" ::: "memory");
     if (args.H && args.cta_partial) {
 #pragma unroll
         for (int q = 0; q < LY::NPART; q++) {
@@ -1021,13 +1032,16 @@ cudaError_t launch_fixed(const EvalArgs &args, const LaunchPlan &pl, cudaStream_
     if (query_only || args.n_img <= 0) return cudaSuccess;
     // launched with programmatic stream serialization (developer knob VG_PDL=0: plain launch)
     static const bool pdl = [] { const char *e = getenv("VG_PDL"); return !(e && e[0] == '0'); }();
+    static const bool late = [] { const char *e = getenv("VG_LATE_WAIT"); return !(e && e[0] == '0'); }();
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(pl.threads); cfg.dynamicSmemBytes = (size_t)pl.smem; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-    const cudaError_t le = cudaLaunchKernelEx(&cfg, reproj_eval_kernel<MODEL, L, PC, LMD>, args, pl.G, pl.PCG);
+    EvalArgs launch_args = args;
+    launch_args.late_wait = pdl && late && !LMD ? 1 : 0;
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, reproj_eval_kernel<MODEL, L, PC, LMD>, launch_args, pl.G, pl.PCG);
     if (launches) count_launch(launches);
     return le != cudaSuccess ? le : cudaGetLastError();
 }
