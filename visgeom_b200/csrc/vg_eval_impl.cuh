@@ -715,9 +715,14 @@ reproj_eval_kernel(const EvalArgs args, const int G_rt, const int PCG_rt)
     }     // visible to everyone after the first __syncthreads below
 
     // this CTA's groups
+    // (several ranks: the last CTA takes no groups -- it is the one that exchanges the reduced system with the peers, at
+    // its head, while the others compute; the same partition in every launch of such a problem, so that its sums do not
+    // depend on the exchange mode)
     const int n_groups_all = (args.n_img + G - 1) / G;
-    const int my_groups = n_groups_all > (int)blockIdx.x ? (n_groups_all - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    auto group_first = [&](const int gi) { return (int)(((long long)blockIdx.x + (long long)gi * gridDim.x) * G); };
+    const int work_ctas = args.peer.n > 1 && gridDim.x > 1 ? (int)gridDim.x - 1 : (int)gridDim.x;
+    const int my_groups = (int)blockIdx.x < work_ctas && n_groups_all > (int)blockIdx.x
+                              ? (n_groups_all - 1 - (int)blockIdx.x) / work_ctas + 1 : 0;
+    auto group_first = [&](const int gi) { return (int)(((long long)blockIdx.x + (long long)gi * work_ctas) * G); };
     // poses of a batch of PCG groups starting at group gi0: thread t takes image (t % G) of group gi0 + t / G
     auto stage_poses = [&](const int gi0, const int t) {
         const int j = t / G, gq = t - j * G;
@@ -734,9 +739,10 @@ reproj_eval_kernel(const EvalArgs args, const int G_rt, const int PCG_rt)
     // never what another evaluation READS in its main loop (observations, board, camera, poses).  So the main loop
     // need not wait for the launch ahead: it runs under that launch's stragglers (2 500 groups over 592 CTAs are 4.2
     // rounds: a fifth of the SM slots idle through the last one) and under its reduction tail, and waits only before
-    // it touches the reduction's scratch itself.  (Two launches on the same buffers write the same bytes.)  Exceptions
+    // it touches the reduction's scratch itself.  (Two launches on the same buffers write the same bytes.)  The exception
     // that wait at the head: the LM loop on the device (its state and the poses come from the kernels ahead) and the CTA
-    // that collects a deferred peer exchange (it reads the previous launch's result).  VG_LATE_WAIT=0: always at the head.
+    // that collects a deferred peer exchange (it reads the previous launch's result; it has no groups of its own).
+    // VG_LATE_WAIT=0: always at the head.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const bool wait_at_head = LMD || !args.late_wait || (args.collect.n > 1 && blockIdx.x == gridDim.x - 1);
     if (wait_at_head) asm volatile("griddepcontrol.wait;" ::: "memory");
