@@ -299,3 +299,47 @@ def test_per_image_refinement_matches_oracle_one_problem_per_image(gpu, oracle):
     # the clean images end next to the ground truth
     clean = [i for i in range(d["n_img"]) if i not in (5, 11)]
     assert np.abs(x[clean] - d["xi_gt"][clean]).max() < 5e-3
+
+
+@pytest.mark.parametrize("model,n_img", [(sd.EUCM, 3000), (sd.MEI, 1500)])
+def test_overlapping_launches_give_the_single_launch_result(gpu, model, n_img):
+    """Evaluation launches do not wait for the evaluation ahead of them until they reach the reduction (late
+    griddepcontrol.wait): bursts of back-to-back launches -- on one problem, on two problems alternating on one stream,
+    with a parameter upload in between -- must leave exactly the bytes a lone launch leaves: cost, reduced system,
+    residuals."""
+    d = sd.make_mono(model, n_img, seed=4242)
+
+    def make(intr):
+        Pm = gpu.Problem(0)
+        cam = Pm.add_camera(model, intr)
+        tr = Pm.add_transform(d["xi_init"], is_global=False)
+        ds = Pm.add_dataset(cam, d["board"], d["obs"], [tr], [D])
+        Pm.materialize_jacobians(True)
+        return Pm, cam, tr, ds
+    A, camA, trA, dsA = make(d["intr_init"])
+    intr_b = d["intr_init"].copy(); intr_b[-4:] *= 1.01
+    B, camB, trB, dsB = make(intr_b)
+    B.set_stream(A.stream)
+    ca, ra = A.evaluate(want_reduced=True); res_a = A.residuals(dsA, n_img, d["P"])
+    cb, rb = B.evaluate(want_reduced=True); res_b = B.residuals(dsB, n_img, d["P"])
+    assert ca != cb
+    for _ in range(40):                                   # one problem, back to back
+        A.evaluate_async()
+    c, r = A.fetch_reduced()
+    assert c == ca and np.array_equal(r, ra) and np.array_equal(A.residuals(dsA, n_img, d["P"]), res_a)
+    for _ in range(30):                                   # two problems alternating on one stream
+        A.evaluate_async(); B.evaluate_async()
+    c, r = A.fetch_reduced(); c2, r2 = B.fetch_reduced()
+    assert c == ca and np.array_equal(r, ra) and c2 == cb and np.array_equal(r2, rb)
+    assert np.array_equal(B.residuals(dsB, n_img, d["P"]), res_b)
+    for k in range(6):                                    # parameters uploaded between the launches of a burst
+        A.set_camera(camA, intr_b if k % 2 == 0 else d["intr_init"])
+        A.evaluate_async(); A.evaluate_async()
+    c, r = A.fetch_reduced()
+    assert c == ca and np.array_equal(r, ra)
+    A.set_camera(camA, intr_b)
+    for _ in range(5):
+        A.evaluate_async()
+    c, r = A.fetch_reduced()
+    assert c == cb and np.array_equal(r, rb) and np.array_equal(A.residuals(dsA, n_img, d["P"]), res_b)
+    A.close(); B.close()
