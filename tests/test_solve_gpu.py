@@ -342,4 +342,4 @@ def test_overlapping_launches_give_the_single_launch_result(gpu, model, n_img):
         A.evaluate_async()
     c, r = A.fetch_reduced()
     assert c == cb and np.array_equal(r, rb) and np.array_equal(A.residuals(dsA, n_img, d["P"]), res_b)
-    A.close(); B.close()
+    B.close(); A.close()                                  # B borrows A's stream: it goes first

@@ -12,7 +12,10 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
     python bench.py --steps 2 --warmup 1 --cpu-seconds 0.5 > gpurun_out/fin_bench_under_ncu.log 2>&1
 ( echo "# tools/kernel_timing.py"; python tools/kernel_timing.py --n-img 10000 --steps 300 --modes full,normal;
   python tools/kernel_timing.py --n-img 25000 --steps 200 --modes full,normal;
+  python tools/kernel_timing.py --model 2 --n-img 10000 --steps 300 --modes full; python tools/kernel_timing.py --model 1 --n-img 10000 --steps 300 --modes full;
+  echo "# VG_LATE_WAIT=0 (every launch waits at its head for the launch ahead)"; VG_LATE_WAIT=0 python tools/kernel_timing.py --n-img 10000 --steps 300 --modes full;
   echo "# tools/lm_timing.py"; python tools/lm_timing.py 2>&1 | tail -3;
   echo "# tools/stereo_timing.py"; python tools/stereo_timing.py 2>&1 | tail -3;
-  echo "# tools/detector_timing.py 64"; python tools/detector_timing.py 64 2>&1 ) > gpurun_out/fin_timing.txt 2>&1
+  echo "# tools/detector_timing.py 128"; python tools/detector_timing.py 128 2>&1 ) > gpurun_out/fin_timing.txt 2>&1
+python tools/aux_timing.py > gpurun_out/fin_aux_timing.txt 2>&1
 tail -30 gpurun_out/fin_timing.txt

@@ -821,6 +821,9 @@ void vg_problem_destroy(vg_problem *p)
     if (p->h_peer_fail) cudaFreeHost(p->h_peer_fail);
     cudaEventDestroy(p->ev0); cudaEventDestroy(p->ev1);
     cudaStreamDestroy(p->own_stream);
+    // a caller's stream (vg_problem_set_stream) may be gone by now: what the calls above made of that must not surface
+    // as the error of the next launch
+    cudaGetLastError();
     delete p;
 }
 
