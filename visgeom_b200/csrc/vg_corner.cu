@@ -111,7 +111,8 @@ corner_response_kernel(const unsigned char *__restrict__ img, const int W, const
             const double gys = __dmul_rn(__dsub_rn((double)(s1c[2] - s1c[0]), __dmul_rn(0.3, (double)(s2c[2] - s2c[0]))), 0.5);
             f_gx = __double2float_rn(__dmul_rn(gxs, 0.01));
             f_gy = __double2float_rn(__dmul_rn(gys, 0.01));
-            f_mag = __double2float_rn(__dmul_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(gxs, gxs), __dmul_rn(gys, gys))), 0.01));
+            if (imgrad)        // (the detector pipeline does not ask for this map: its host stages recompute what they need)
+                f_mag = __double2float_rn(__dmul_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(gxs, gxs), __dmul_rn(gys, gys))), 0.01));
             // saddle response of the wider blur (:297-309).  -Iuu Ivv + Iuv^2 is a multiple of 1/16 below 2^21 and
             // |grad|^4 = n^2 with n < 2^15: both exact in integers, hence exact as doubles; what is rounded is
             // 0.001 * q and the final subtraction, as in the reference
