@@ -533,6 +533,11 @@ def run_ours(args):
                             "traffic_note": "bytes per launch from profiles/traffic.json (ncu --set full); below the algorithmic "
                                             "bytes when the 126 MB L2 still holds part of the outputs as the kernel ends",
                             "kernel": "reproj_eval_kernel", "kernel_us": kernel_us, "kernel_launches_timed": k_launches,
+                            "kernel_us_note": "elapsed time of the back-to-back launches / their number (CUDA events on the launching "
+                                              "stream): consecutive evaluation launches overlap -- a launch's main loop runs under the "
+                                              "stragglers of the one ahead (DESIGN.md section 4) -- so this is the kernel's cost per "
+                                              "launch in a stream of them; a lone launch (what ncu sees) takes about 27.5 us at C2",
+
                             "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src,
                             # the same bytes over the whole device-timed step (kernel + fused reduction tail + exchange)
                             "step_achieved": step_gbs, "step_frac": step_gbs / peak}}
