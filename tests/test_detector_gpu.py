@@ -145,3 +145,32 @@ def test_random_pictures_against_the_reference_build(gpu):
             f1, c1 = gpu.detect_pattern(img, improve=True)
             assert f1 and np.abs(c1 - refined).max() < REFINE_TOL, (trial, np.abs(c1 - refined).max())
     assert n_found >= 15
+
+
+def test_random_pictures_against_the_python_restatement(gpu, oracle):
+    """The same kind of check with the checker that always travels (oracle/detector_oracle.py, pinned on the reference
+    build's fixtures): the whole GPU + host pipeline's found flag and integer grid on pictures of no fixture, scale by
+    scale as detectPattern tries them."""
+    from oracle.detector_oracle import DetectorOracle
+    rng = np.random.default_rng(123)
+    n_found = 0
+    for trial in range(8):
+        w = int(rng.integers(200, 480)); h = int(w * rng.uniform(0.65, 0.85))
+        img, _ = sd.render_board_image(w, h, seed=62000 + trial, model=(sd.EUCM, sd.MEI, sd.UCM)[trial % 3],
+                                       noise=float(rng.choice([1.0, 6.0, 13.0])), supersample=2)
+        if trial == 3:
+            img = np.ascontiguousarray(img[:, : w * 3 // 5])
+        want = None
+        for sigma in (1.4, 2.0, 1.0):                       # corner_detector.cpp:225-245
+            m = oracle.corner_response(img, 0.7, sigma)
+            s2 = oracle.gaussian_blur_u8(img, 1 + 2 * int(np.ceil(sigma)), sigma)
+            cand, pat = DetectorOracle(img, m, s2, 9, 6, int(round(1.5 * sigma))).detect()
+            if len(pat) == 54:
+                want = np.array([cand[i] for i in pat], dtype=np.float64)
+                break
+        found, grid = gpu.detect_pattern(img, improve=False)
+        assert found == (want is not None), trial
+        if found:
+            n_found += 1
+            assert np.array_equal(grid, want), trial
+    assert n_found >= 4

@@ -141,3 +141,65 @@ def test_detect_pattern_fails_loudly_without_a_gpu(vg):
         vg.detect_pattern(IMAGES[0])
     with pytest.raises(vg.VisgeomError):
         vg.subpixel_refine(np.zeros((8, 8), np.float32), np.zeros((8, 8), np.float32), [[4, 4]], [3.0], [[4, 4, 0, 1.5, 0]])
+
+
+# ---- the Python restatement (oracle/detector_oracle.py): pinned on the fixtures, then used as the checker on new pictures ----
+def _python_oracle(oracle, img, sigma):
+    from oracle.detector_oracle import DetectorOracle
+    m = oracle.corner_response(img, 0.7, float(sigma))
+    s2 = oracle.gaussian_blur_u8(img, 1 + 2 * int(np.ceil(sigma)), float(sigma))
+    return DetectorOracle(img, m, s2, 9, 6, int(round(1.5 * sigma)))
+
+
+@pytest.mark.parametrize("k", range(N))
+def test_python_restatement_reproduces_the_fixture(oracle, k):
+    """candidates in graph order (the standard library's heap order among equal keys included), the pattern, initPoin's
+    values: exactly what the reference build recorded"""
+    first = True
+    for s, sigma in enumerate(SIGMAS):
+        D = _python_oracle(oracle, IMAGES[k], sigma)
+        cand, pat = D.detect()
+        assert np.array_equal(np.array(cand, dtype=np.int32).reshape(-1, 2), GOLD[f"{k}/scale{s}/cand"]), (k, s)
+        assert list(pat) == list(GOLD[f"{k}/scale{s}/pattern"]), (k, s)
+        if len(pat) == 54 and first:
+            first = False
+            grid = [cand[i] for i in pat]
+            assert np.array_equal(np.array(grid), GOLD[f"{k}/grid"])
+            assert np.array_equal(np.array([D.init_point(p) for p in grid]), GOLD[f"{k}/start"])
+
+
+def test_python_restatement_of_the_subpixel_cost(oracle):
+    from oracle.detector_oracle import subpixel_evaluate
+    m = oracle.corner_response(IMAGES[0], 0.7, 1.4)
+    for pr, x, ln, c, g in zip(GOLD["eval/prior"], GOLD["eval/x"], GOLD["eval/length"], GOLD["eval/cost"], GOLD["eval/grad"]):
+        cc, gg = subpixel_evaluate(m["gradx"], m["grady"], pr, float(ln), x)
+        assert abs(cc - c) <= 1e-12 * max(1.0, abs(c)) and np.abs(gg - g).max() <= 1e-12 * max(1.0, np.abs(g).max())
+
+
+def test_host_stages_equal_the_python_restatement_on_new_pictures(vg, oracle):
+    """pictures that are in no fixture (other sizes, seeds, noise levels; a board cut by the border), checked without the
+    reference build: the product's host stages against the Python restatement"""
+    import synthdata as sd
+    from oracle.detector_oracle import refinement_reach
+    rng = np.random.default_rng(99)
+    found = 0
+    for trial in range(8):
+        w = int(rng.integers(180, 420)); h = int(w * rng.uniform(0.65, 0.85))
+        img, _ = sd.render_board_image(w, h, seed=61000 + trial, model=(sd.EUCM, sd.MEI, sd.UCM)[trial % 3],
+                                       noise=float(rng.choice([1.0, 5.0, 11.0])), supersample=2)
+        if trial == 5:
+            img = np.ascontiguousarray(img[:, : w * 3 // 5])
+        for sigma in SIGMAS:
+            D = _python_oracle(oracle, img, sigma)
+            cand, pat = D.detect()
+            s1, s2, val, uv, R = _gpu_stage_stand_in(oracle, img, sigma)
+            r = vg.detector_host_stages(img, s1, s2, val, uv, R)
+            assert np.array_equal(r["cand"], np.array(cand, dtype=np.int32).reshape(-1, 2)), (trial, sigma)
+            assert r["found"] == (len(pat) == 54), (trial, sigma)
+            if r["found"]:
+                found += 1
+                grid = np.array([cand[i] for i in pat])
+                assert np.array_equal(r["grid"], grid)
+                assert np.array_equal(r["start"], np.array([D.init_point(tuple(p)) for p in grid]))
+                assert np.array_equal(r["reach"], refinement_reach(grid, 9))
+    assert found >= 10
