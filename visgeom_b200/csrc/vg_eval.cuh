@@ -78,6 +78,7 @@ struct EvalArgs {
     int n_img;
     int P;
     int late_wait;                      // set by the launcher: the main loop does not wait for the launch ahead (vg_eval_impl.cuh)
+    int wait_at_head;                   // set by the caller: a kernel ahead writes this launch's inputs and releases its dependents early
     // The LM loop's decision on the device (vg_lm_dev.cuh).  lm_mode 1: this is the solve's first evaluation -- the
     // thread that finishes red[] records the cost; 2: a candidate's evaluation -- every CTA leaves at once when the solve
     // is over (or only the gradient test is due), the packed blocks go to H or H_alt (LmState::hcur), and the finishing

@@ -733,8 +733,9 @@ reproj_eval_kernel(const EvalArgs args, const int G_rt, const int PCG_rt)
     };
 
     // Programmatic dependent launch: the next kernel of the stream may take this CTA's SM slot as soon as it is free.
-    // Which grids can be ahead of this one and still running?  Only evaluation launches -- they are the only kernels
-    // that release their dependents early; behind any other kernel this launch starts when that one has completed.
+    // Which grids can be ahead of this one and still running?  Only kernels that release their dependents early: other
+    // evaluation launches, and the LM step's kernels inside vg_problem_solve -- where the caller asks every evaluation to
+    // wait at its head (EvalArgs::wait_at_head); behind any other kernel this launch starts when that one has completed.
     // An evaluation writes residuals, Jacobians, per-image blocks and, in its tail, the reduction's scratch and result:
     // never what another evaluation READS in its main loop (observations, board, camera, poses).  So the main loop
     // need not wait for the launch ahead: it runs under that launch's stragglers (2 500 groups over 592 CTAs are 4.2
@@ -1046,7 +1047,7 @@ cudaError_t launch_fixed(const EvalArgs &args, const LaunchPlan &pl, cudaStream_
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
     EvalArgs launch_args = args;
-    launch_args.late_wait = pdl && late && !LMD ? 1 : 0;
+    launch_args.late_wait = pdl && late && !LMD && !args.wait_at_head ? 1 : 0;
     const cudaError_t le = cudaLaunchKernelEx(&cfg, reproj_eval_kernel<MODEL, L, PC, LMD>, launch_args, pl.G, pl.PCG);
     if (launches) count_launch(launches);
     return le != cudaSuccess ? le : cudaGetLastError();

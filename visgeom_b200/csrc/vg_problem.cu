@@ -114,6 +114,11 @@ struct vg_problem {
 
     // prepared state
     bool prepared = false;
+    // Evaluation launches normally do not wait for the launch ahead of them before their main loop (vg_eval_impl.cuh);
+    // that rests on the launch ahead not writing what an evaluation reads.  Inside vg_problem_solve the kernels ahead do
+    // (the back-substitution writes the candidate's poses) and release their dependents early: there, and for the first
+    // evaluation after a solve, every evaluation waits at its head.
+    bool in_solve = false, after_solve = false;
     int Ks = 0, n_pose = 0, cur = 0;
     int rank = 0, nranks = 1;
     vg_allreduce_fn allreduce = nullptr;
@@ -689,10 +694,12 @@ int evaluate_set(vg_problem *p, int s, bool timed, bool deferred = false)
             }
         }
         a.n_img = d.n_img; a.P = d.P;
+        a.wait_at_head = p->in_solve || p->after_solve;
         a.loss_b = d.loss_a * d.loss_a;
         cudaError_t e = launch_eval(p->cams[d.cam].model, d.L, a, p->stream, &launch_counter());
         if (e != cudaSuccess) return fail_cuda(e, "reproj_eval_kernel launch");
     }
+    p->after_solve = false;
     // no dataset with images on this rank (fewer images than ranks, or a problem of prior blocks only): nothing has
     // written segment E, and what it holds is the cross-rank SUM of this set's previous evaluation -- it must not be
     // contributed again
@@ -1462,6 +1469,11 @@ int vg_problem_solve(vg_problem *p, const vg_solve_options *opt, vg_solve_summar
     const double t_start = now_s();
     int rc = prepare(p);
     if (rc) return rc;
+    struct SolveScope {
+        vg_problem *p;
+        explicit SolveScope(vg_problem *q) : p(q) { p->in_solve = true; }
+        ~SolveScope() { p->in_solve = false; p->after_solve = true; }
+    } solve_scope(p);
     VG_CUDA(cudaSetDevice(p->device));
     memset(sum, 0, sizeof *sum);
     p->eval_ms = 0; p->n_eval = 0;

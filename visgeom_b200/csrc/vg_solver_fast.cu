@@ -90,7 +90,10 @@ __global__ void __launch_bounds__(F_THREADS)
 fast_factor_kernel(const FastDesc d, const int n_pose, const int Ks, double *scale, const LmConsts lm_in, double *ws,
                    double *rows, double *grp_rows, double *gmax_rows, unsigned int *tickets, int *fail_flag, const FastLm flm)
 {
-    asm volatile("griddepcontrol.wait;" ::: "memory");       // (programmatic dependent launch: see launch_fast_step)
+    // (programmatic dependent launch: see launch_fast_step.  This kernel does not release its own dependents early:
+    // measured, the evaluation's persistent CTAs waiting in the SM slots cost this grid more -- 65.7 -> 73.3 us per
+    // iteration at C2 -- than the hidden launch latency gives back)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     LmConsts lm = lm_in;
     const double *Hsrc = d.H;
     const int nblk = flm.st ? (int)gridDim.x - 1 : (int)gridDim.x;      // (with the loop's state on the device: one extra block)
@@ -589,6 +592,8 @@ __global__ void __launch_bounds__(256)
 fast_exchange_kernel(const int Ks, const int n_grp, const double *grp_rows, double *xbuf, double *row_out, int *fail_flag,
                      const PeerCtx pc_in, const LmState *st)
 {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     PeerCtx pc = pc_in;
     if (st) {                                   // (every rank takes the same decisions: all of them leave, or none)
         const int dn = __ldcg(&st->done);
@@ -689,9 +694,16 @@ cudaError_t launch_fast_step(const FastDesc &d, int n_pose, int Ks, double *scal
     const double *rows_in = grp_rows, *fail_src = nullptr;
     int n_rows_in = ng;
     if (peer && peer->n > 1) {
-        fast_exchange_kernel<<<1, 256, 0, sl.stream>>>(Ks, ng, grp_rows, xbuf, xrow, fail_flag, *peer, (const LmState *)flm.st);
+        cudaLaunchConfig_t xcfg = {};
+        xcfg.gridDim = dim3(1); xcfg.blockDim = dim3(256); xcfg.dynamicSmemBytes = 0; xcfg.stream = sl.stream;
+        cudaLaunchAttribute xattr[1];
+        xattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        xattr[0].val.programmaticStreamSerializationAllowed = 1;
+        xcfg.attrs = xattr; xcfg.numAttrs = between ? 0 : 1;
+        e = cudaLaunchKernelEx(&xcfg, fast_exchange_kernel, Ks, ng, (const double *)grp_rows, xbuf, xrow, fail_flag, *peer,
+                               (const LmState *)flm.st);
         if (sl.launches) count_launch(sl.launches);
-        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         rows_in = xrow; n_rows_in = 1; fail_src = xrow + npair + 1;
     }
