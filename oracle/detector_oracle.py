@@ -8,7 +8,7 @@ stage.  TEST INFRASTRUCTURE ONLY: imported by tests/ (and nothing else); the pro
     CornerDetector::constructGraph           :612-836
     extractSequence / selectBestOrthogonalChain / selectPattern / verifyDetection   :850-1076
     getCircle / getSamples / centralDifferences / getTransitions / initPoin        :1079-1298
-    improveCorners (the reach radMax)        :164-175
+    improveCorners                           :162-198  (+ ceres::GradientProblemSolver, third party, restated)
     SubpixelCorner::Evaluate                 :47-100   (+ ceres::BiCubicInterpolator, third party: Catmull-Rom)
     setZero, comp, normalizePoint            include/calibration/corner_detector.h:144-178
     CurveRasterizer, Polynomial2::Circle     include/utils/curve_rasterizer.h:31-66,168-259
@@ -21,8 +21,8 @@ reference's own order of operations and tie-breaking -- including the standard l
 candidates depends.  Slow (seconds per small image): for fixtures, not for throughput.
 
 Pinned on the reference's own corner_detector.cpp compiled where it lies (oracle/_ref, recorded in
-tests/golden/detector.npz): candidates in graph order, grid, initPoin values and SubpixelCorner's cost / gradient are
-reproduced exactly / to 1e-12 (tests/test_detector_oracle.py)."""
+tests/golden/detector.npz): candidates in graph order, grid, initPoin values, SubpixelCorner's cost / gradient, the
+refined corners and the minimiser's iteration counts are reproduced exactly (tests/test_detector_oracle.py)."""
 from __future__ import annotations
 
 import math
@@ -643,3 +643,182 @@ def subpixel_evaluate(gradx, grady, prior, length, params, steps=7):
             g[th] += eta * ((fvv * dvdth + fvu * dudth) * c - (fuv * dvdth + fuu * dudth) * s - fu * c - fv * s)
             g[4] += fvv * c * c + fuu * s * s - s * c * (fvu + fuv)
     return cost, np.array(g)
+
+
+# ---- improveCorners' minimisation (:176-196): ceres::GradientProblemSolver with default options -----------------------------
+# Ceres is a third-party dependency absent from /root/reference: its published line-search minimiser is restated here as
+# in oracle/shim/ceres/gradient_solver.h (L-BFGS, rank 20, H0 = I, pairs with s.y <= 1e-14 skipped; Wolfe search =
+# bracketing + zoom on the cubic through two (value, slope) samples; Ceres' default tolerances).  PARITY UNPINNED against
+# Ceres itself for the minimiser's path -- see DESIGN.md section 2.
+def _cubic_min(a, b, lo, hi):
+    """minimiser over [lo, hi] of the cubic through samples a, b = (x, f, g): midpoint, ends, real parts of p' roots"""
+    h = b[0] - a[0]
+    d = (b[1] - a[1]) / h
+    k3 = (a[2] + b[2] - 2.0 * d) / (h * h)
+    k2 = (3.0 * d - 2.0 * a[2] - b[2]) / h
+
+    def P(x):
+        t = x - a[0]
+        return a[1] + t * (a[2] + t * (k2 + t * k3))
+    best_x = 0.5 * (lo + hi)
+    best = P(best_x)
+    for x in (lo, hi):
+        v = P(x)
+        if v < best:
+            best, best_x = v, x
+    qa, qb, qc = 3.0 * k3, 2.0 * k2, a[2]
+    roots = []
+    if qa != 0.0:
+        D = qb * qb - 4.0 * qa * qc
+        sD = math.sqrt(abs(D))
+        if D >= 0.0:
+            if qb >= 0.0:
+                roots = [(-qb - sD) / (2.0 * qa), (2.0 * qc) / (-qb - sD)]
+            else:
+                roots = [(2.0 * qc) / (-qb + sD), (-qb + sD) / (2.0 * qa)]
+        else:
+            roots = [-qb / (2.0 * qa)] * 2
+    elif qb != 0.0:
+        roots = [-qc / qb]
+    for r in roots:
+        x = r + a[0]
+        if not (lo <= x <= hi):
+            continue
+        v = P(x)
+        if v < best:
+            best, best_x = v, x
+    return best_x
+
+
+def minimize_gradient_problem(fun, x0, max_iter=50, rank=20, f_tol=1e-6, g_tol=1e-10, x_tol=1e-8, min_step=1e-9, c1=1e-4, c2=0.9,
+                              expand=10.0, max_trials=20, max_restarts=5):
+    """fun(x) -> (cost, gradient).  Returns (x, iterations)."""
+    x = [float(v) for v in x0]
+    n = len(x)
+    f, g = fun(x)
+    g = [float(v) for v in g]
+    f_prev = 0.0
+    S, Y, SY = [], [], []
+    it = restarts = 0
+
+    def dot(a, b):
+        s = 0.0
+        for i in range(n):
+            s += a[i] * b[i]
+        return s
+    if max(abs(v) for v in g) <= g_tol:
+        return np.array(x), 0
+    while it < max_iter:
+        it += 1
+        steepest = not S
+        d = list(g)
+        if not steepest:
+            m = len(S)
+            alpha = [0.0] * m
+            for i in range(m - 1, -1, -1):
+                alpha[i] = dot(S[i], d) / SY[i]
+                for k in range(n):
+                    d[k] -= alpha[i] * Y[i][k]
+            for i in range(m):
+                beta = dot(Y[i], d) / SY[i]
+                for k in range(n):
+                    d[k] += S[i][k] * (alpha[i] - beta)
+        d = [-v for v in d]
+        slope = dot(g, d)
+        if not steepest and slope >= 0.0:
+            restarts += 1
+            if restarts > max_restarts:
+                break
+            S, Y, SY = [], [], []
+            d = [-v for v in g]
+            slope = dot(g, d)
+            steepest = True
+        gmax = max(abs(v) for v in g)
+        step0 = min(1.0, 1.0 / gmax) if (it == 1 or steepest) else min(1.0, 2.0 * (f - f_prev) / slope)
+        if not step0 > 0.0:
+            break
+        dmax = max(abs(v) for v in d)
+
+        def phi(a):
+            ft, gt = fun([x[i] + a * d[i] for i in range(n)])
+            return (a, ft, dot([float(v) for v in gt], d))
+        start = (0.0, f, slope)
+        prev, cur, lo, hi = start, phi(step0), start, start
+        zoom, ok, trials = False, True, 0
+        while True:                                        # bracketing
+            trials += 1
+            if cur[1] > start[1] + c1 * start[2] * cur[0] or (prev[0] > 0.0 and cur[1] > prev[1]):
+                zoom, lo, hi = True, prev, cur
+                break
+            if abs(cur[2]) <= -c2 * start[2]:
+                lo = hi = cur
+                break
+            if cur[2] >= 0.0:
+                zoom, lo, hi = True, cur, prev
+                break
+            if abs(cur[0] - prev[0]) * dmax < min_step:
+                ok = False
+                break
+            if trials >= max_trials:
+                lo = cur if cur[1] < lo[1] else lo
+                break
+            a = _cubic_min(prev, cur, cur[0], cur[0] * expand)
+            if a * dmax < min_step:
+                ok = False
+                break
+            prev, cur = cur, phi(a)
+        if not ok:
+            break
+        best = lo
+        if zoom:
+            if lo[1] > hi[1]:
+                lo, hi = hi, lo
+            sol = None
+            while True:
+                if trials >= max_trials or abs(hi[0] - lo[0]) * dmax < min_step:
+                    break
+                trials += 1
+                lb, ub = (lo, hi) if lo[0] < hi[0] else (hi, lo)
+                sol = phi(_cubic_min(lb, ub, lb[0], ub[0]))
+                if sol[1] > start[1] + c1 * start[2] * sol[0] or sol[1] >= lo[1]:
+                    hi = sol
+                    continue
+                if abs(sol[2]) <= -c2 * start[2]:
+                    break
+                if sol[2] * (hi[0] - lo[0]) >= 0.0:
+                    hi = lo
+                lo = sol
+            best = lo if (sol is None or sol[1] > lo[1]) else sol
+        if not best[0] > 0.0:
+            break
+        xn = [x[i] + best[0] * d[i] for i in range(n)]
+        fn, gn = fun(xn)
+        gn = [float(v) for v in gn]
+        s = [best[0] * d[i] for i in range(n)]
+        y = [gn[i] - g[i] for i in range(n)]
+        step_norm = math.sqrt(sum(v * v for v in s))
+        x_norm = math.sqrt(sum(v * v for v in xn))
+        sy = dot(s, y)
+        if sy > 1e-14:
+            if len(S) == rank:
+                S.pop(0); Y.pop(0); SY.pop(0)
+            S.append(s); Y.append(y); SY.append(sy)
+        f_prev, f, x, g = f, fn, xn, gn
+        if max(abs(v) for v in g) <= g_tol:
+            break
+        if step_norm <= x_tol * (x_norm + x_tol):
+            break
+        if abs(f_prev - f) <= f_tol * abs(f_prev):
+            break
+    return np.array(x), it
+
+
+def improve_corners(gradx, grady, grid, start, nx):
+    """improveCorners (:162-198) on the integer grid with initPoin's start values -> refined (n, 2), iterations (n,)"""
+    reach = refinement_reach(grid, nx)
+    out, its = [], []
+    for i in range(len(grid)):
+        prior = (float(grid[i][0]), float(grid[i][1]))
+        x, it = minimize_gradient_problem(lambda p: subpixel_evaluate(gradx, grady, prior, float(reach[i]), p), start[i])
+        out.append(x[:2]); its.append(it)
+    return np.array(out), np.array(its)

@@ -203,3 +203,13 @@ def test_host_stages_equal_the_python_restatement_on_new_pictures(vg, oracle):
                 assert np.array_equal(r["start"], np.array([D.init_point(tuple(p)) for p in grid]))
                 assert np.array_equal(r["reach"], refinement_reach(grid, 9))
     assert found >= 10
+
+
+@pytest.mark.parametrize("k,sigma", [(0, 1.4), (5, 1.0)])
+def test_python_restatement_of_the_refinement(oracle, k, sigma):
+    """improveCorners through the Python restatement of the minimiser: the reference build's refined corners and
+    iteration counts, bit for bit (the two restatements of Ceres' line search walk the same path)"""
+    from oracle.detector_oracle import improve_corners
+    m = oracle.corner_response(IMAGES[k], 0.7, sigma)
+    refined, its = improve_corners(m["gradx"], m["grady"], GOLD[f"{k}/grid"], GOLD[f"{k}/start"], 9)
+    assert np.array_equal(refined, GOLD[f"{k}/refined"]) and np.array_equal(its, GOLD[f"{k}/iters"])
