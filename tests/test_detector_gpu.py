@@ -151,7 +151,7 @@ def test_random_pictures_against_the_python_restatement(gpu, oracle):
     """The same kind of check with the checker that always travels (oracle/detector_oracle.py, pinned on the reference
     build's fixtures): the whole GPU + host pipeline's found flag and integer grid on pictures of no fixture, scale by
     scale as detectPattern tries them."""
-    from oracle.detector_oracle import DetectorOracle
+    from oracle.detector_oracle import DetectorOracle, improve_corners
     rng = np.random.default_rng(123)
     n_found = 0
     for trial in range(8):
@@ -164,7 +164,8 @@ def test_random_pictures_against_the_python_restatement(gpu, oracle):
         for sigma in (1.4, 2.0, 1.0):                       # corner_detector.cpp:225-245
             m = oracle.corner_response(img, 0.7, sigma)
             s2 = oracle.gaussian_blur_u8(img, 1 + 2 * int(np.ceil(sigma)), sigma)
-            cand, pat = DetectorOracle(img, m, s2, 9, 6, int(round(1.5 * sigma))).detect()
+            D = DetectorOracle(img, m, s2, 9, 6, int(round(1.5 * sigma)))
+            cand, pat = D.detect()
             if len(pat) == 54:
                 want = np.array([cand[i] for i in pat], dtype=np.float64)
                 break
@@ -173,4 +174,9 @@ def test_random_pictures_against_the_python_restatement(gpu, oracle):
         if found:
             n_found += 1
             assert np.array_equal(grid, want), trial
+            if n_found <= 3:                                # and the refinement, through the restated minimiser
+                start = np.array([D.init_point((int(p[0]), int(p[1]))) for p in want])
+                refined, _ = improve_corners(m["gradx"], m["grady"], want, start, 9)
+                _, got = gpu.detect_pattern(img, improve=True)
+                assert np.abs(got - refined).max() < REFINE_TOL, (trial, np.abs(got - refined).max())
     assert n_found >= 4
