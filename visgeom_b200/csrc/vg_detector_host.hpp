@@ -415,7 +415,7 @@ public:
     void give(std::unique_ptr<OwnerMap> m)
     {
         std::lock_guard<std::mutex> g(mu_);
-        if (free_.size() < 64) free_.push_back(std::move(m));
+        if (free_.size() < 32) free_.push_back(std::move(m));        // (4 bytes per pixel each: what does not fit is freed)
     }
 
 private:
