@@ -378,6 +378,14 @@ struct Lane {
             return cudaSuccess;
         if (st) cudaStreamSynchronize(st);
         release();
+        if (dev != device && st) {                   // the stream and the buffers belong to the device they were made on
+            int cur = device;
+            cudaGetDevice(&cur);
+            if (dev >= 0) cudaSetDevice(dev);
+            cudaStreamDestroy(st);
+            st = nullptr;
+            cudaSetDevice(cur);
+        }
         dev = device;
         cudaError_t e = st ? cudaSuccess : cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
         const size_t px = N * images_, nc = (size_t)P * images_;
