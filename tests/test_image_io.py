@@ -51,6 +51,11 @@ def test_files_written_by_opencv(imread, tmp_path):
             assert cv2.imwrite(path, a)
             assert np.array_equal(imread(path), a), path
             assert np.array_equal(cv2.imread(path, 0), a)
+    # a 16-bit picture: imread(name, 0) keeps the high byte
+    deep = (img.astype(np.uint16) << 8) | np.random.default_rng(6).integers(0, 256, img.shape, dtype=np.uint16)
+    path = str(tmp_path / "deep.png")
+    assert cv2.imwrite(path, deep)
+    assert np.array_equal(imread(path), cv2.imread(path, 0)) and np.array_equal(imread(path), img)
     # and OpenCV reads what the test data writer wrote
     sd.write_png(str(tmp_path / "w.png"), img, filter_type=2)
     assert np.array_equal(cv2.imread(str(tmp_path / "w.png"), 0), img)
@@ -67,3 +72,30 @@ def test_unreadable_files_give_an_empty_image(imread, tmp_path):
     assert imread(str(tmp_path / "cut.png")) is None
     (tmp_path / "cut.pgm").write_bytes(b"P5\n64 48\n255\n" + bytes(100))
     assert imread(str(tmp_path / "cut.pgm")) is None
+
+
+def test_palette_png(imread, tmp_path):
+    """colour type 3: indices into PLTE, converted like a colour picture"""
+    import struct
+    import zlib
+    rng = np.random.default_rng(8)
+    pal = rng.integers(0, 256, (16, 3), dtype=np.uint8)
+    idx = rng.integers(0, 16, (23, 31), dtype=np.uint8)
+    raw = b"".join(b"\x00" + idx[y].tobytes() for y in range(idx.shape[0]))
+
+    def chunk(tag, data):
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
+    path = str(tmp_path / "pal.png")
+    with open(path, "wb") as f:
+        f.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", 31, 23, 8, 3, 0, 0, 0)) + chunk(b"PLTE", pal.tobytes()) +
+                chunk(b"IDAT", zlib.compress(raw)) + chunk(b"IEND", b""))
+    p64 = pal.astype(np.int64)
+    grey = ((p64[:, 0] * 4899 + p64[:, 1] * 9617 + p64[:, 2] * 1868 + 8192) >> 14).astype(np.uint8)
+    got = imread(path)
+    assert np.array_equal(got, grey[idx])
+    try:
+        import cv2
+    except ImportError:
+        return
+    ref = cv2.imread(path, 0)
+    assert ref is not None and np.abs(got.astype(int) - ref.astype(int)).max() <= 1      # libpng's own rgb -> grey rounding

@@ -1,6 +1,6 @@
 // image_io.hpp -- reading calibration images as 8-bit grey (the reference calls cv::imread(fileName, 0),
 // unified_calibration.cpp:1025; OpenCV is not part of this engine).  Formats: binary PGM (P5, maxval <= 255) and
-// non-interlaced 8-bit PNG (grey, grey + alpha, RGB, RGBA; inflate through zlib).  Colour PNGs are converted with
+// non-interlaced 8- or 16-bit PNG (grey, grey + alpha, RGB, RGBA, 8-bit palette; inflate through zlib).  Colour PNGs are converted with
 // OpenCV's fixed-point BGR2GRAY weights (R 4899, G 9617, B 1868, >> 14); imread's own PNG path lets libpng do that
 // conversion, which can differ by one grey level -- calibration images are grey in practice.
 #pragma once
@@ -60,20 +60,24 @@ inline bool decode_png(const std::vector<uint8_t> &b, Mat8u &img)
     size_t p = 8;
     uint32_t w = 0, h = 0;
     int depth = 0, colour = 0, interlace = 0;
-    std::vector<uint8_t> z;
+    std::vector<uint8_t> z, palette;
     while (p + 12 <= b.size()) {
         const uint32_t len = be32(&b[p]);
         const char *type = reinterpret_cast<const char *>(&b[p + 4]);
         if (p + 12 + len > b.size()) return false;
         const uint8_t *d = &b[p + 8];
         if (!std::memcmp(type, "IHDR", 4) && len >= 13) { w = be32(d); h = be32(d + 4); depth = d[8]; colour = d[9]; interlace = d[12]; }
+        else if (!std::memcmp(type, "PLTE", 4)) palette.assign(d, d + len);
         else if (!std::memcmp(type, "IDAT", 4)) z.insert(z.end(), d, d + len);
         else if (!std::memcmp(type, "IEND", 4)) break;
         p += 12 + len;
     }
-    if (w == 0 || h == 0 || depth != 8 || interlace != 0) return false;
-    const int ch = colour == 0 ? 1 : colour == 4 ? 2 : colour == 2 ? 3 : colour == 6 ? 4 : 0;
-    if (ch == 0) return false;                          // palette images: not supported
+    if (w == 0 || h == 0 || (depth != 8 && depth != 16) || interlace != 0) return false;
+    if (colour == 3 && (depth != 8 || palette.size() < 3)) return false;
+    const int samples = colour == 0 || colour == 3 ? 1 : colour == 4 ? 2 : colour == 2 ? 3 : colour == 6 ? 4 : 0;
+    if (samples == 0) return false;
+    const int bps = depth / 8, ch = samples * bps;     // bytes per sample (16-bit: big endian, the high byte is kept -- what
+                                                       // libpng's strip_16 leaves cv::imread), bytes per pixel
     const size_t stride = (size_t)w * ch;
     std::vector<uint8_t> raw((stride + 1) * h);
     uLongf out_len = (uLongf)raw.size();
@@ -104,7 +108,12 @@ inline bool decode_png(const std::vector<uint8_t> &b, Mat8u &img)
         uint8_t *dst = &img.data[(size_t)w * y];
         for (uint32_t x = 0; x < w; x++) {
             const uint8_t *px = &cur[(size_t)x * ch];
-            dst[x] = ch <= 2 ? px[0] : (uint8_t)((px[0] * 4899 + px[1] * 9617 + px[2] * 1868 + 8192) >> 14);
+            if (colour == 3) {
+                const size_t e = (size_t)px[0] * 3;
+                if (e + 2 >= palette.size()) return false;
+                dst[x] = (uint8_t)((palette[e] * 4899 + palette[e + 1] * 9617 + palette[e + 2] * 1868 + 8192) >> 14);
+            } else if (samples <= 2) dst[x] = px[0];
+            else dst[x] = (uint8_t)((px[0] * 4899 + px[bps] * 9617 + px[2 * bps] * 1868 + 8192) >> 14);
         }
         prev.swap(cur);
     }
