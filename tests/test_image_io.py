@@ -99,3 +99,37 @@ def test_palette_png(imread, tmp_path):
         return
     ref = cv2.imread(path, 0)
     assert ref is not None and np.abs(got.astype(int) - ref.astype(int)).max() <= 1      # libpng's own rgb -> grey rounding
+
+
+def test_jpeg_luminance_matches_opencv(imread, tmp_path):
+    """baseline JPEG read as grey: only Y is reconstructed, with libjpeg's integer inverse DCT -- the pixels OpenCV returns.
+    Grey and colour files, 4:2:0 / 4:2:2 / 4:4:4 sampling, sizes that are not multiples of the MCU, restart intervals."""
+    cv2 = pytest.importorskip("cv2")
+    board, _ = sd.render_board_image(317, 243, seed=20252, model=sd.UCM)
+    rng = np.random.default_rng(9)
+    colour = np.stack([board, np.roll(board, 7, axis=1), rng.integers(0, 256, board.shape, dtype=np.uint8)], axis=-1)
+    noise = rng.integers(0, 256, (67, 129), dtype=np.uint8)
+    cases = []
+    for q in (50, 92, 100):
+        cases.append((board, [cv2.IMWRITE_JPEG_QUALITY, q]))
+    cases.append((noise, [cv2.IMWRITE_JPEG_QUALITY, 75]))
+    cases.append((board, [cv2.IMWRITE_JPEG_QUALITY, 85, cv2.IMWRITE_JPEG_RST_INTERVAL, 5]))
+    cases.append((colour, [cv2.IMWRITE_JPEG_QUALITY, 90]))
+    cases.append((colour[:131, :200], [cv2.IMWRITE_JPEG_QUALITY, 80, cv2.IMWRITE_JPEG_RST_INTERVAL, 3]))
+    for flag in ("IMWRITE_JPEG_SAMPLING_FACTOR_444", "IMWRITE_JPEG_SAMPLING_FACTOR_422", "IMWRITE_JPEG_SAMPLING_FACTOR_420"):
+        if hasattr(cv2, flag) and hasattr(cv2, "IMWRITE_JPEG_SAMPLING_FACTOR"):
+            cases.append((colour, [cv2.IMWRITE_JPEG_QUALITY, 88, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, getattr(cv2, flag)]))
+    for i, (a, params) in enumerate(cases):
+        path = str(tmp_path / f"c{i}.jpg")
+        assert cv2.imwrite(path, a, params)
+        want = cv2.imread(path, 0)
+        got = imread(path)
+        assert got is not None and got.shape == want.shape, (i, params)
+        assert np.array_equal(got, want), (i, params, int(np.abs(got.astype(int) - want.astype(int)).max()))
+    # progressive files are not decoded: an empty image, not garbage
+    path = str(tmp_path / "prog.jpg")
+    assert cv2.imwrite(path, board, [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])
+    assert imread(path) is None
+    data = open(str(tmp_path / "c0.jpg"), "rb").read()
+    (tmp_path / "cut.jpg").write_bytes(data[: len(data) // 2])
+    assert imread(str(tmp_path / "cut.jpg")) is None
