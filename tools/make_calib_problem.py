@@ -48,7 +48,7 @@ def write_mono(out_dir, n_img=20, model=sd.EUCM, seed=20241, skip=()):
 
 def write_images(out_dir, n_img=10, model=sd.EUCM, seed=20400, width=640, height=480, improve=True):
     """Dataset type "images" (unified_calibration.cpp:279-309, 632-647): rendered pictures of the 9 x 6 board (PGM and PNG
-    files alternating, one missing file, one picture without a board), the camera started off its true intrinsics."""
+    files alternating, one JPEG where cv2 can write it, one missing file, one picture without a board), the camera started off its true intrinsics."""
     import numpy as np
     os.makedirs(out_dir, exist_ok=True)
     truth, names = [], []
@@ -57,7 +57,18 @@ def write_images(out_dir, n_img=10, model=sd.EUCM, seed=20400, width=640, height
         if i == 3:
             img = np.full_like(img, 120)                        # no board on this one
         name = "img_%03d.%s" % (i, "png" if i % 2 else "pgm")
-        if i % 2:
+        jpeg = None
+        if i == 7:                                              # one JPEG among them, where OpenCV is there to write it
+            try:
+                import cv2
+                jpeg = "img_%03d.jpg" % i
+                if not cv2.imwrite(os.path.join(out_dir, jpeg), img, [cv2.IMWRITE_JPEG_QUALITY, 95]):
+                    jpeg = None
+            except ImportError:
+                jpeg = None
+        if jpeg:
+            name = jpeg
+        elif i % 2:
             sd.write_png(os.path.join(out_dir, name), img, filter_type=(i // 2) % 3)
         else:
             sd.write_pgm(os.path.join(out_dir, name), img)
