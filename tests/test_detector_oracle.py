@@ -213,3 +213,27 @@ def test_python_restatement_of_the_refinement(oracle, k, sigma):
     m = oracle.corner_response(IMAGES[k], 0.7, sigma)
     refined, its = improve_corners(m["gradx"], m["grady"], GOLD[f"{k}/grid"], GOLD[f"{k}/start"], 9)
     assert np.array_equal(refined, GOLD[f"{k}/refined"]) and np.array_equal(its, GOLD[f"{k}/iters"])
+
+
+@needs_ref
+def test_python_restatement_against_the_reference_build_on_random_pictures(oracle, refdet):
+    """beyond the fixtures: a dozen random pictures (three models, noise up to 12 grey levels, a cut board, pure noise),
+    every scale: candidates in graph order and the pattern, the Python restatement against the reference build"""
+    import synthdata as sd
+    rng = np.random.default_rng(2024)
+    found = 0
+    for trial in range(12):
+        w = int(rng.integers(160, 420)); h = int(w * rng.uniform(0.6, 0.9))
+        img, _ = sd.render_board_image(w, h, seed=63000 + trial, model=(sd.EUCM, sd.MEI, sd.UCM)[trial % 3],
+                                       noise=float(rng.choice([0.5, 4.0, 12.0])), supersample=2)
+        if trial == 4:
+            img = np.ascontiguousarray(img[:, : w // 2])
+        if trial == 9:
+            img = rng.integers(0, 256, img.shape, dtype=np.uint8)
+        for sigma in SIGMAS:
+            st = refdet.stages(img, sigma)
+            cand, pat = _python_oracle(oracle, img, sigma).detect()
+            assert np.array_equal(np.array(cand, dtype=np.int32).reshape(-1, 2), st["cand"]), (trial, sigma)
+            assert list(pat) == list(st["pattern"]), (trial, sigma)
+            found += len(pat) == 54
+    assert found >= 15
