@@ -274,7 +274,10 @@ void *vg_problem_stream(vg_problem *p);
 int vg_problem_set_stream(vg_problem *p, void *stream);
 /* vg_problem_evaluate without the read-back: queues the fused kernels, the shared-block
  * reduction and (multi-GPU) its all-reduce on the problem's stream and returns.
- * vg_problem_fetch_reduced then copies cost / reduced (nullable) to the host and waits. */
+ * vg_problem_fetch_reduced then copies cost / reduced (nullable) to the host and waits.
+ * Consecutive evaluations queued on one stream overlap on the device (a launch's main loop does not wait for the
+ * evaluation ahead of it); stream order holds for everything else: a copy or a kernel queued after an evaluation sees its
+ * complete result, and parameters uploaded between two evaluations are seen by the second one only. */
 int vg_problem_evaluate_async(vg_problem *p);
 int vg_problem_fetch_reduced(vg_problem *p, double *cost, double *reduced);
 
